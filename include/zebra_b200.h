@@ -1,0 +1,170 @@
+/*
+ * zebra_b200.h -- C ABI of the B200-native replacement for Zebra's query hot path.
+ *
+ * The reference (emmyoh/zebra) has no FFI today: its operator interface is the Rust type
+ * `LSHIndex<N>` (src/database/index/lsh.rs:145-566) driven by `Database<N, Met, Mod>`
+ * (src/database/core.rs:205-213, :245-254, :290-313) and the metric structs of src/distance.rs.
+ * Each entry point below names the reference item it replaces; INTEGRATION.md shows the Rust
+ * `extern "C"` block and the changed method bodies a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (ZB_OK) or a negative zb_status; zb_last_error() gives the message of the
+ *     calling thread's last failure.  There is NO CPU fallback: without a usable sm_100 device (or without the
+ *     CUDA kernels in this library) zb_index_create fails with ZB_ERR_NO_DEVICE.
+ *   - the caller owns every buffer; pointers named h_* / plain are HOST memory, d_* are DEVICE memory on
+ *     the index's device.  No torch (or other framework) types cross this boundary.
+ *   - vectors are `dim` contiguous f32 (Embedding<N>, src/lib.rs:16-48); ids are 16 bytes (uuid::Uuid,
+ *     big-endian byte order = Ord); every row also has a u64 ORDINAL (its global insertion index), which is
+ *     what ties are broken by and what the *_ordinals outputs carry.  Library-minted ids are UUIDv7 whose
+ *     byte order equals ordinal order.
+ *   - distances are DistanceUnit = u64 = f64 bit patterns (src/distance.rs:13), sorted as unsigned integers
+ *     exactly like lsh.rs:318 / :561, ties by id ascending.
+ *   - a handle is internally serialised (one mutex): calls from any thread are safe; batch for throughput.
+ */
+#ifndef ZEBRA_B200_H
+#define ZEBRA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZB_ABI_VERSION 1
+
+typedef struct zb_index zb_index;
+
+typedef enum zb_status {
+    ZB_OK = 0,
+    ZB_ERR_INVALID = -1,   /* bad argument */
+    ZB_ERR_CUDA = -2,      /* CUDA runtime / kernel failure */
+    ZB_ERR_NO_DEVICE = -3, /* no CUDA device of compute capability 10.x */
+    ZB_ERR_OOM = -4,       /* host or device allocation failed */
+    ZB_ERR_STATE = -5,     /* call not valid in this state (e.g. hash before any tree exists) */
+    ZB_ERR_COMM = -6       /* NCCL / sharding failure */
+} zb_status;
+
+/* The three metrics on the north-star path.  src/distance.rs:17-32 (Cosine, literal Q4 semantics:
+ * (1 - simsimd cosine distance).to_bits()), :36-49 (L2Squared), :101-114 (L2). */
+typedef enum zb_metric { ZB_METRIC_COSINE = 0, ZB_METRIC_L2SQ = 1, ZB_METRIC_L2 = 2 } zb_metric;
+
+/* LSHIndexOptions (lsh.rs:124-138) plus device placement.  Zero-initialise, then set fields. */
+typedef struct zb_options {
+    uint32_t dim;           /* N */
+    uint32_t metric;        /* zb_metric */
+    uint64_t max_node_size; /* lsh.rs:126, default 5 */
+    uint32_t num_trees;     /* lsh.rs:128, default 15 */
+    int32_t device;         /* CUDA device ordinal */
+    uint64_t seed;          /* seed of the hyperplane sampling stream (reference: unseeded rand::rng()) */
+    uint32_t shard_rank;    /* this process's shard; rows with ordinal % shard_count == shard_rank live here */
+    uint32_t shard_count;   /* 0 or 1 = unsharded */
+    uint32_t reserved[4];
+} zb_options;
+
+typedef struct zb_stats {
+    uint64_t rows;          /* rows stored on this shard, including tombstoned ones */
+    uint64_t live_rows;     /* rows on this shard not tombstoned */
+    uint64_t total_rows;    /* ordinals handed out so far (all shards) */
+    uint64_t nodes, planes, leaves;
+    uint64_t device_bytes;  /* HBM held by this index */
+    /* last zb_index_search_batch* call */
+    uint64_t last_queries, last_visits, last_pairs;   /* pairs = scored (query, row) pairs on this shard */
+    uint64_t last_tile_visits, last_tile_pairs;       /* part handled by the fused leaf-tile scan kernel */
+    uint64_t last_moved_bytes;                        /* HBM bytes the scan asks for by design (rows, per tile) */
+    float last_ms_plan, last_ms_scan, last_ms_select, last_ms_merge, last_ms_total;
+    uint32_t last_scan_launches, last_total_launches;
+    uint32_t reserved[8];
+} zb_stats;
+
+const char* zb_last_error(void);
+int zb_abi_version(void);
+int zb_device_count(int* out_count);
+
+/* LSHIndex::new (lsh.rs:162-167).  Creates an empty index on options->device. */
+int zb_index_create(const zb_options* options, zb_index** out_index);
+int zb_index_destroy(zb_index* index);
+
+/* LSHIndex::add (lsh.rs:440-466; build_index :411-429 when no tree exists yet, insert :350-382 otherwise).
+ * rows: n*dim f32.  ids16: n*16 bytes or NULL (library mints UUIDv7).  out_ids16 / out_ordinals: optional.
+ * Sharded index: every rank passes the SAME n rows; each keeps the rows it owns. */
+int zb_index_add(zb_index* index, uint64_t n, const float* rows, const uint8_t* ids16, uint8_t* out_ids16,
+                 uint64_t* out_ordinals);
+/* Same, rows already resident in HBM (d_rows: n*dim f32 on the index's device). */
+int zb_index_add_device(zb_index* index, uint64_t n, const float* d_rows, const uint8_t* ids16, uint8_t* out_ids16,
+                        uint64_t* out_ordinals);
+/* Sharded bulk load without replication: this rank passes only the rows it owns plus their global ordinals
+ * (each ordinal % shard_count == shard_rank, ascending); total_n = rows in the batch over all ranks. */
+int zb_index_add_owned_device(zb_index* index, uint64_t n_local, const float* d_rows, const uint64_t* ordinals,
+                              uint64_t total_n);
+
+/* LSHIndex::remove (lsh.rs:473-503) with the tombstone semantics of DESIGN.md D1.
+ * out_removed[i] = 1 if ids[i] was live (on any shard) and is now removed. */
+int zb_index_remove(zb_index* index, uint64_t n, const uint8_t* ids16, uint8_t* out_removed);
+int zb_index_remove_ordinals(zb_index* index, uint64_t n, const uint64_t* ordinals, uint8_t* out_removed);
+
+/* LSHIndex::clear (lsh.rs:506-529), without quirk Q12: drops rows AND trees. */
+int zb_index_clear(zb_index* index);
+
+/* LSHIndex::no_vectors / no_trees / is_empty (lsh.rs:389-409). */
+int zb_index_no_vectors(zb_index* index, int* out);
+int zb_index_no_trees(zb_index* index, int* out);
+
+/* LSHIndex::search (lsh.rs:544-565) for a whole batch -- replaces the par_iter at core.rs:299-303.
+ * queries: nq*dim f32.  Outputs are [nq][top_k]; unused tail slots are filled with 0xFF bytes;
+ * out_counts[q] = number of results of query q.  Any of out_ids16 / out_ordinals may be NULL. */
+int zb_index_search_batch(zb_index* index, uint64_t nq, const float* queries, uint64_t top_k, uint8_t* out_ids16,
+                          uint64_t* out_ordinals, uint64_t* out_dist_bits, uint32_t* out_counts);
+/* Same with queries and outputs resident in HBM (the device-side leg the bench reports as `value`). */
+int zb_index_search_batch_device(zb_index* index, uint64_t nq, const float* d_queries, uint64_t top_k,
+                                 uint64_t* d_out_ordinals, uint64_t* d_out_dist_bits, uint32_t* d_out_counts);
+
+/* Bucket keys: the root-to-leaf sign path of Hyperplane::point_is_above decisions (lsh.rs:39-43 along
+ * :350-366), MSB = root, 1 = above/right, for every (row, tree): out_keys/out_depths/out_leaves are
+ * [n][num_trees] (a path longer than 64 keeps its last 64 bits; out_leaves is the leaf number of
+ * zb_index_export_forest's numbering and is the full bucket identity). */
+int zb_index_hash(zb_index* index, uint64_t n, const float* rows, uint64_t* out_keys, uint32_t* out_depths,
+                  int32_t* out_leaves);
+int zb_index_hash_device(zb_index* index, uint64_t n, const float* d_rows, uint64_t* d_out_keys,
+                         uint32_t* d_out_depths, int32_t* d_out_leaves);
+
+/* Forest interchange (hyperplanes as input: the reference's sampling is unseeded, survey quirk Q8).
+ * nodes: n_nodes * {plane, left(below), right(above), leaf} int32 (inner: leaf = -1; leaf: plane = -1);
+ * roots: num_trees node numbers; coef: n_planes*dim f32; cst: n_planes f32; leaf_off: n_leaves+1 CSR offsets
+ * into members; members: row ordinals.  sizes4 = {n_nodes, n_planes, n_leaves, n_members}. */
+int zb_index_forest_sizes(zb_index* index, int64_t* sizes4);
+int zb_index_export_forest(zb_index* index, int32_t* nodes, int32_t* roots, float* coef, float* cst,
+                           int64_t* leaf_off, uint64_t* members);
+/* Replaces the index content with n rows (ordinals 0..n-1; ids16 may be NULL) and the given forest. */
+int zb_index_load_forest(zb_index* index, uint64_t n, const float* rows, const uint8_t* ids16,
+                         const int64_t* sizes4, const int32_t* nodes, const int32_t* roots, const float* coef,
+                         const float* cst, const int64_t* leaf_off, const uint64_t* members);
+
+int zb_index_stats(zb_index* index, zb_stats* out);
+/* Tuning knobs (tests and ablations): key in {"tile_min_rows", "tile_queries", "use_tile_scan"}. */
+int zb_index_set_param(zb_index* index, const char* key, int64_t value);
+
+/* Sharding over the GPUs of one box: one process per GPU, each with its own index
+ * (options.shard_rank / shard_count).  The library runs NCCL itself (allreduce of per-leaf live counts and of
+ * build statistics, allgather of per-visit local top-n' lists); the host only has to carry the 128-byte
+ * unique id from rank 0 to the other ranks. */
+int zb_comm_unique_id(uint8_t* out_id128);
+int zb_index_comm_init(zb_index* index, const uint8_t* id128);
+
+/* The metric trait and the sign test for n independent pairs (host buffers): Metric::distance of
+ * src/distance.rs:19-32 / :38-49 / :103-114 with arguments (a = stored row, b = query), and
+ * Hyperplane::point_is_above of lsh.rs:39-43.  Used by the host mirror's Metric::distance and by parity tests. */
+int zb_metric_distance_batch(int device, uint32_t metric, uint64_t n, uint32_t dim, const float* a, const float* b,
+                             uint64_t* out_bits);
+int zb_point_is_above_batch(int device, uint64_t n, uint32_t dim, const float* coef, const float* cst, const float* x,
+                            uint8_t* out);
+
+/* Synthetic data of BASELINE.md (counter-based, identical on any shard): fills d_out[n][dim] with
+ * row r = first_row + i.  kind 0: uniform in [-1, 1); kind 1: clustered (centre[r % 4096] + 0.25 * noise). */
+int zb_synth_fill_device(int device, float* d_out, uint64_t first_row, uint64_t row_stride, uint64_t n, uint32_t dim,
+                         uint64_t seed, uint32_t kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZEBRA_B200_H */

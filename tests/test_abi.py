@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/zebra_b200.h declares, and refuses to work without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "zebra_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from zebra_b200 import _ffi
+
+    lib = _ffi.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in zebra_b200.h but not exported"
+        assert name in _ffi.SYMBOLS, f"{name} has no ctypes prototype"
+    exported = subprocess.run(["nm", "-D", "--defined-only", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    got = sorted(set(re.findall(r" T (zb_[a-z0-9_]+)", exported)))
+    assert got == declared
+    assert lib.zb_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from zebra_b200 import _ffi
+
+    assert C.sizeof(_ffi.Options) == 56
+    assert _ffi.Options.max_node_size.offset == 8 and _ffi.Options.seed.offset == 24
+    assert C.sizeof(_ffi.Stats) == 13 * 8 + 5 * 4 + 2 * 4 + 8 * 4 + 4  # tail padding to 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import zebra_b200 as z
+
+    with pytest.raises(z.ZebraError) as ei:
+        z.LSHIndex(384, z.LSHIndexOptions(), z.L2SquaredDistance())
+    assert ei.value.code == -3
+    with pytest.raises(z.ZebraError):
+        z.L2Distance().distance(np.zeros(16, np.float32), np.zeros(16, np.float32))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under zebra_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "zebra_b200")
+    for dp, _, fns in os.walk(pkg):
+        if "build" in dp:
+            continue
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, fn), errors="replace").read()
+                assert "zb_oracle" not in src and "from oracle" not in src and "import oracle" not in src, fn
+
+
+def test_invalid_arguments_are_reported():
+    from zebra_b200 import _ffi
+
+    lib = _ffi.lib()
+    assert lib.zb_index_create(None, None) == -1
+    assert b"NULL" in lib.zb_last_error()
+    o = _ffi.Options()
+    o.dim, o.metric, o.num_trees = 0, 0, 1
+    h = C.c_void_p()
+    assert lib.zb_index_create(C.byref(o), C.byref(h)) == -1
+    o.dim, o.metric = 16, 9
+    assert lib.zb_index_create(C.byref(o), C.byref(h)) == -1
+    assert lib.zb_index_destroy(None) == 0

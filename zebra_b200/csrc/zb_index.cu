@@ -1,0 +1,1318 @@
+// zb_index.cu -- the index object behind the C ABI of include/zebra_b200.h.
+//
+// Host side of the hot path: owns the device-resident vector store and forest, drives the kernels of
+// zb_kernels.cu / zb_scan.cu on one CUDA stream, and (when sharded) the NCCL exchanges.  It mirrors
+// LSHIndex<N> of /root/reference/src/database/index/lsh.rs:145-566 (new :162, add :440, remove :473,
+// clear :506, search :544, no_vectors :398, no_trees :407).  There is no CPU compute path in this file:
+// every dot product, distance, sign test, partition and top-k runs in a CUDA kernel.
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <unordered_map>
+
+#include "zb_host.h"
+#include "zb_kernels.cuh"
+#include "zb_scan.cuh"
+
+namespace zb {
+size_t g_device_bytes = 0;
+static thread_local std::string t_last_error;
+
+struct Id16 {
+    uint64_t hi, lo;
+    bool operator==(const Id16& o) const { return hi == o.hi && lo == o.lo; }
+};
+struct Id16Hash {
+    size_t operator()(const Id16& k) const { return (size_t)mix64(k.hi ^ mix64(k.lo)); }
+};
+static inline uint64_t load_be64(const uint8_t* p) {
+    uint64_t v = 0;
+    for (int i = 0; i < 8; ++i) v = (v << 8) | p[i];
+    return v;
+}
+static inline void store_be64(uint8_t* p, uint64_t v) {
+    for (int i = 7; i >= 0; --i) {
+        p[i] = (uint8_t)v;
+        v >>= 8;
+    }
+}
+
+__global__ void remap_leaves_kernel(int* leaves, u64 n, const int* __restrict__ table) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) leaves[i] = table[leaves[i]];
+}
+__global__ void count_live_kernel(const u32* __restrict__ members, const long long* __restrict__ leaf_off,
+                                  const u32* __restrict__ leaf_len, const u32* __restrict__ tomb, u32 nleaves,
+                                  u32* __restrict__ leaf_live) {
+    u32 l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaves) return;
+    u32 c = 0;
+    const u32* m = members + leaf_off[l];
+    for (u32 i = 0; i < leaf_len[l]; ++i) c += tomb_test(tomb, m[i]) ? 0u : 1u;
+    leaf_live[l] = c;
+}
+
+struct BSeg {  // a node under construction
+    u64 key;
+    int depth, node, tree;
+    long long off;
+    u32 len;
+    u64 glen;
+    u32 attempt;
+};
+
+}  // namespace zb
+
+using namespace zb;
+
+struct zb_index {
+    std::mutex mu;
+    zb_options opt{};
+    int dim = 0, dimp = 0, chunks = 0, T = 0, device = 0;
+    u32 G = 1, rank = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8]{};
+    Nccl nccl;
+    bool comm_ready = false;
+    u64 epoch_ms = 0;
+
+    // ---- vector store (device resident, slot order) ----
+    DBuf<float> rows;
+    DBuf<u64> ord;
+    DBuf<u32> tomb;
+    DBuf<u32> slot_leaf;  // [T][slot_stride]
+    u64 slot_stride = 0;
+    u64 n_slots = 0, n_live = 0, total_rows = 0;
+    std::vector<u64> h_ord;
+    std::vector<uint8_t> h_tomb;
+    int id_mode = 0;  // 0 unknown, 1 minted, 2 caller supplied
+    std::vector<Id16> ids_by_ordinal;
+    std::unordered_map<Id16, u64, Id16Hash> ordinal_by_id;
+
+    // ---- forest: host mirror of the structure, device copies of everything ----
+    std::vector<int4> h_nodes;
+    std::vector<int> h_roots;
+    u64 n_planes = 0;
+    std::vector<long long> h_leaf_off;
+    std::vector<u32> h_leaf_len, h_leaf_cap;
+    std::vector<u64> h_leaf_key;
+    std::vector<int> h_leaf_depth, h_leaf_node, h_leaf_tree;
+    u64 members_used = 0;
+    std::vector<u32> h_members;
+    bool h_members_valid = false;
+    bool built = false;
+    DBuf<int4> d_nodes;
+    DBuf<int> d_roots;
+    DBuf<float> d_coef, d_cst;
+    DBuf<long long> d_leaf_off;
+    DBuf<u32> d_leaf_len, d_leaf_live, d_leaf_plan, d_members;
+    DBuf<int> d_leaf_export;
+    bool export_table_valid = false;
+
+    // ---- workspaces ----
+    DBuf<u8> cub_tmp;
+    DBuf<u32> w_counts, w_off, w_flag;
+    DBuf<uint2> w_visits;
+    u32 vpw = 8;
+    DBuf<u32> v_leaf, v_np, v_q, v_ent_len, v_ent_off;
+    DBuf<u64> v_pair_len, v_pair_off, pair_key;
+    DBuf<u8> v_done;
+    DBuf<Entry> entries, gathered;
+    DBuf<float> q_stage, r_stage;
+    DBuf<u64> o_ord, o_bits, h_keys;
+    DBuf<u32> o_counts, h_depths, rm_slots;
+    DBuf<int> h_leaves;
+    DBuf<u8> rm_flags;
+    HBuf<u8> pin;
+    // build workspaces
+    DBuf<u32> b_work[2], b_flags, b_scan, b_above;
+    DBuf<Tile> b_tiles;
+    DBuf<SegDesc> b_segs;
+    DBuf<u64> b_minh, b_minord, b_excl;
+    DBuf<int> b_slot_a, b_slot_b;
+    DBuf<float> b_pair_rows;
+    ScanWorkspace scan_ws;
+
+    // ---- knobs / stats ----
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1;
+    zb_stats st{};
+
+    ForestView view() const {
+        ForestView f;
+        f.nodes = d_nodes.p;
+        f.roots = d_roots.p;
+        f.coef = d_coef.p;
+        f.cst = d_cst.p;
+        f.leaf_off = d_leaf_off.p;
+        f.leaf_len = d_leaf_len.p;
+        f.leaf_plan = G > 1 ? d_leaf_plan.p : d_leaf_live.p;
+        f.members = d_members.p;
+        f.rows = rows.p;
+        f.ord = ord.p;
+        f.tomb = tomb.p;
+        f.dimp = dimp;
+        f.chunks = chunks;
+        f.num_trees = T;
+        return f;
+    }
+    void sync() { ZB_CUDA(cudaStreamSynchronize(stream)); }
+    void use_device() { ZB_CUDA(cudaSetDevice(device)); }
+    void scan_tmp(size_t n) {
+        size_t need = scan_temp_bytes(n);
+        cub_tmp.ensure(need);
+    }
+    bool owns(u64 ordinal) const { return G <= 1 || ordinal % G == rank; }
+    u64 slot_of(u64 ordinal) const { return G <= 1 ? ordinal : ordinal / G; }
+
+    // ---------------------------------------------------------------- ids
+    Id16 mint(u64 ordinal) const {
+        // UUIDv7 layout: 48-bit ms timestamp (the index epoch) | ver 7 | ordinal[63:52] | var 10 | ordinal[51:46]
+        // | ordinal[45:0] << 10.  Byte order == ordinal order.
+        uint64_t hi = (epoch_ms << 16) | 0x7000ull | ((ordinal >> 52) & 0xFFFull);
+        uint64_t lo = (0x2ull << 62) | (((ordinal >> 46) & 0x3Full) << 56) | ((ordinal & ((1ull << 46) - 1)) << 10);
+        return Id16{hi, lo};
+    }
+    bool unmint(const Id16& id, u64* ordinal) const {
+        if ((id.hi >> 16) != (epoch_ms & 0xFFFFFFFFFFFFull) || ((id.hi >> 12) & 0xF) != 7 || (id.lo >> 62) != 2 ||
+            (id.lo & 0x3FF))
+            return false;
+        *ordinal = ((id.hi & 0xFFFull) << 52) | (((id.lo >> 56) & 0x3Full) << 46) | ((id.lo >> 10) & ((1ull << 46) - 1));
+        return true;
+    }
+    void id_of(u64 ordinal, uint8_t* out16) const {
+        Id16 id = id_mode == 2 ? (ordinal < ids_by_ordinal.size() ? ids_by_ordinal[ordinal] : Id16{~0ull, ~0ull})
+                               : mint(ordinal);
+        store_be64(out16, id.hi);
+        store_be64(out16 + 8, id.lo);
+    }
+    bool ordinal_of(const uint8_t* id16, u64* ordinal) const {
+        Id16 id{load_be64(id16), load_be64(id16 + 8)};
+        if (id_mode == 2) {
+            auto it = ordinal_by_id.find(id);
+            if (it == ordinal_by_id.end()) return false;
+            *ordinal = it->second;
+            return true;
+        }
+        return unmint(id, ordinal) && *ordinal < total_rows;
+    }
+
+    // ---------------------------------------------------------------- store
+    void reserve_slots(u64 need) {
+        if (need <= slot_stride) return;
+        u64 ncap = slot_stride ? slot_stride + slot_stride / 2 : need;
+        if (ncap < need) ncap = need;
+        ncap = (ncap + 31) & ~31ull;
+        rows.ensure(ncap * (u64)dimp, n_slots * (u64)dimp, stream, true);
+        ord.ensure(ncap, n_slots, stream, true);
+        size_t old_words = tomb.cap;
+        tomb.ensure(ncap / 32 + 1, (n_slots + 31) / 32, stream, true);
+        (void)old_words;
+        // slot_leaf is [T][stride]: re-stride
+        DBuf<u32> nsl;
+        nsl.ensure(ncap * (u64)T, 0, stream, true);
+        if (slot_leaf.p && n_slots)
+            ZB_CUDA(cudaMemcpy2DAsync(nsl.p, ncap * 4, slot_leaf.p, slot_stride * 4, n_slots * 4, T, cudaMemcpyDeviceToDevice,
+                                      stream));
+        sync();
+        std::swap(nsl.p, slot_leaf.p);
+        std::swap(nsl.cap, slot_leaf.cap);
+        slot_stride = ncap;
+    }
+    // Append n_local rows already on the device (stride `src_stride` floats, dim floats used) with the given ordinals.
+    void append_rows_device(const float* d_src, u64 src_stride, u64 n_local, const u64* ordinals) {
+        if (!n_local) return;
+        reserve_slots(n_slots + n_local);
+        float* dst = rows.p + n_slots * (u64)dimp;
+        if (dimp == dim) {
+            ZB_CUDA(cudaMemcpy2DAsync(dst, (size_t)dimp * 4, d_src, src_stride * 4, (size_t)dim * 4, n_local,
+                                      cudaMemcpyDeviceToDevice, stream));
+        } else {
+            ZB_REQUIRE(src_stride == (u64)dim, ZB_ERR_INVALID, "strided device rows need dim %% 16 == 0");
+            launch_pad_rows(d_src, n_local, dim, dimp, dst, stream);
+        }
+        ZB_CUDA(cudaMemcpyAsync(ord.p + n_slots, ordinals, n_local * 8, cudaMemcpyHostToDevice, stream));
+        // clear tombstone bits of the new slots (word granular: new words zeroed, shared first word bits are already 0)
+        u64 w0 = (n_slots + 31) / 32, w1 = (n_slots + n_local + 31) / 32;
+        if (n_slots == 0) w0 = 0;
+        if (w1 > w0) ZB_CUDA(cudaMemsetAsync(tomb.p + w0, 0, (w1 - w0) * 4, stream));
+        sync();
+        h_ord.insert(h_ord.end(), ordinals, ordinals + n_local);
+        h_tomb.resize(h_tomb.size() + n_local, 0);
+        n_slots += n_local;
+        n_live += n_local;
+    }
+
+    // ---------------------------------------------------------------- forest upload helpers
+    void upload_structure() {
+        size_t nn = h_nodes.size(), nl = h_leaf_off.size();
+        d_nodes.ensure(nn ? nn : 1);
+        d_roots.ensure(T);
+        d_leaf_off.ensure(nl ? nl : 1);
+        d_leaf_len.ensure(nl ? nl : 1);
+        if (nn) ZB_CUDA(cudaMemcpyAsync(d_nodes.p, h_nodes.data(), nn * sizeof(int4), cudaMemcpyHostToDevice, stream));
+        ZB_CUDA(cudaMemcpyAsync(d_roots.p, h_roots.data(), (size_t)T * 4, cudaMemcpyHostToDevice, stream));
+        if (nl) {
+            ZB_CUDA(cudaMemcpyAsync(d_leaf_off.p, h_leaf_off.data(), nl * 8, cudaMemcpyHostToDevice, stream));
+            ZB_CUDA(cudaMemcpyAsync(d_leaf_len.p, h_leaf_len.data(), nl * 4, cudaMemcpyHostToDevice, stream));
+        }
+        sync();
+        export_table_valid = false;
+    }
+    void recount_live() {  // leaf_live from members + tombstones, then the global plan counts
+        u32 nl = (u32)h_leaf_off.size();
+        d_leaf_live.ensure(nl ? nl : 1);
+        d_leaf_plan.ensure(nl ? nl : 1);
+        if (nl) count_live_kernel<<<(nl + 127) / 128, 128, 0, stream>>>(d_members.p, d_leaf_off.p, d_leaf_len.p, tomb.p, nl, d_leaf_live.p);
+        refresh_plan_counts();
+    }
+    void refresh_plan_counts() {
+        u32 nl = (u32)h_leaf_off.size();
+        if (G > 1 && nl) {
+            ZB_REQUIRE(comm_ready, ZB_ERR_STATE, "sharded index used before zb_index_comm_init");
+            d_leaf_plan.ensure(nl);
+            ZB_CUDA(cudaMemcpyAsync(d_leaf_plan.p, d_leaf_live.p, (size_t)nl * 4, cudaMemcpyDeviceToDevice, stream));
+            nccl.allreduce(d_leaf_plan.p, nl, Nccl::U32, Nccl::SUM, stream);
+        }
+    }
+    void sync_host_members() {
+        if (h_members_valid) return;
+        h_members.resize(members_used);
+        if (members_used)
+            ZB_CUDA(cudaMemcpyAsync(h_members.data(), d_members.p, members_used * 4, cudaMemcpyDeviceToHost, stream));
+        sync();
+        h_members_valid = true;
+    }
+    int new_leaf(int node, int tree, u64 key, int depth, long long off, u32 len, u32 cap) {
+        int id = (int)h_leaf_off.size();
+        h_leaf_off.push_back(off);
+        h_leaf_len.push_back(len);
+        h_leaf_cap.push_back(cap);
+        h_leaf_key.push_back(key);
+        h_leaf_depth.push_back(depth);
+        h_leaf_node.push_back(node);
+        h_leaf_tree.push_back(tree);
+        return id;
+    }
+
+    void clear_forest() {
+        h_nodes.clear();
+        h_roots.assign(T, -1);
+        n_planes = 0;
+        h_leaf_off.clear(); h_leaf_len.clear(); h_leaf_cap.clear(); h_leaf_key.clear();
+        h_leaf_depth.clear(); h_leaf_node.clear(); h_leaf_tree.clear();
+        members_used = 0;
+        h_members.clear();
+        h_members_valid = false;
+        built = false;
+        export_table_valid = false;
+    }
+
+    // ---------------------------------------------------------------- build (lsh.rs:192-267, level synchronous)
+    // `active`: nodes to build over the slots in b_work[0][0..total).  New leaves' members are appended to
+    // d_members; nodes/planes/leaves are appended to the host mirror (uploaded by the caller).
+    void build_subtrees(std::vector<BSeg> active, u64 total) {
+        const u64 max_node = opt.max_node_size;
+        std::vector<BSeg> leaves;
+        int cur = 0;
+        b_work[1].ensure(total ? total : 1);
+        b_flags.ensure(total + 1);
+        b_scan.ensure(total + 1);
+        scan_tmp(total + 1);
+        std::vector<SegDesc> hsegs;
+        std::vector<Tile> htiles;
+        std::vector<u32> habove, hgabove;
+        while (true) {
+            std::vector<BSeg> split, next;
+            for (const BSeg& s : active) {
+                if (s.glen < max_node || s.glen < 2 || s.depth >= ZB_MAX_DEPTH || s.attempt >= ZB_MAX_ATTEMPTS) leaves.push_back(s);
+                else split.push_back(s);
+            }
+            if (split.empty()) break;
+            const u32 ns = (u32)split.size();
+            d_coef.ensure((n_planes + ns) * (u64)dimp, n_planes * (u64)dimp, stream);
+            d_cst.ensure(n_planes + ns, n_planes, stream);
+            hsegs.resize(ns);
+            htiles.clear();
+            for (u32 i = 0; i < ns; ++i) {
+                const BSeg& s = split[i];
+                hsegs[i] = SegDesc{s.off, s.len, (u32)(n_planes + i), s.key, s.attempt, 0};
+                for (u32 b = 0; b < s.len; b += 64) htiles.push_back(Tile{i, std::min<u32>(64, s.len - b), s.off + b});
+            }
+            const u32 nt = (u32)htiles.size();
+            b_segs.ensure(ns);
+            b_tiles.ensure(nt ? nt : 1);
+            b_minh.ensure(ns); b_minord.ensure(ns); b_excl.ensure(ns);
+            b_slot_a.ensure(ns); b_slot_b.ensure(ns); b_above.ensure(2 * (size_t)ns);
+            b_pair_rows.ensure((size_t)ns * 2 * dimp);
+            ZB_CUDA(cudaMemcpyAsync(b_segs.p, hsegs.data(), ns * sizeof(SegDesc), cudaMemcpyHostToDevice, stream));
+            if (nt) ZB_CUDA(cudaMemcpyAsync(b_tiles.p, htiles.data(), nt * sizeof(Tile), cudaMemcpyHostToDevice, stream));
+            const u32* work = b_work[cur].p;
+            for (int which = 0; which < 2; ++which) {  // a, then b (excluding a)
+                int* slot_out = which ? b_slot_b.p : b_slot_a.p;
+                const u64* excl = which ? b_excl.p : nullptr;
+                ZB_CUDA(cudaMemsetAsync(b_minh.p, 0xFF, ns * 8, stream));
+                ZB_CUDA(cudaMemsetAsync(b_minord.p, 0xFF, ns * 8, stream));
+                ZB_CUDA(cudaMemsetAsync(slot_out, 0xFF, ns * 4, stream));
+                launch_pick(0, b_tiles.p, nt, b_segs.p, work, ord.p, excl, b_minh.p, b_minord.p, slot_out, stream);
+                if (G > 1) nccl.allreduce(b_minh.p, ns, Nccl::U64, Nccl::MIN, stream);
+                launch_pick(1, b_tiles.p, nt, b_segs.p, work, ord.p, excl, b_minh.p, b_minord.p, slot_out, stream);
+                if (G > 1) nccl.allreduce(b_minord.p, ns, Nccl::U64, Nccl::MIN, stream);
+                launch_pick(2, b_tiles.p, nt, b_segs.p, work, ord.p, excl, b_minh.p, b_minord.p, slot_out, stream);
+                if (!which) ZB_CUDA(cudaMemcpyAsync(b_excl.p, b_minord.p, ns * 8, cudaMemcpyDeviceToDevice, stream));
+            }
+            launch_fetch_pair_rows(b_segs.p, ns, b_slot_a.p, b_slot_b.p, rows.p, dimp, b_pair_rows.p, stream);
+            if (G > 1) nccl.allreduce(b_pair_rows.p, (size_t)ns * 2 * dimp, Nccl::I32, Nccl::SUM, stream);
+            launch_make_planes(b_segs.p, ns, b_pair_rows.p, dimp, d_coef.p, d_cst.p, stream);
+            ZB_CUDA(cudaMemsetAsync(b_flags.p, 0, (total + 1) * 4, stream));
+            launch_classify(b_tiles.p, nt, b_segs.p, work, rows.p, d_coef.p, d_cst.p, dimp, b_flags.p, stream);
+            exclusive_scan_u32(cub_tmp.p, cub_tmp.bytes(), b_flags.p, b_scan.p, total + 1, stream);
+            launch_seg_above(b_segs.p, ns, b_scan.p, b_above.p, stream);
+            habove.resize(ns);
+            hgabove.resize(ns);
+            ZB_CUDA(cudaMemcpyAsync(habove.data(), b_above.p, ns * 4, cudaMemcpyDeviceToHost, stream));
+            if (G > 1) {
+                ZB_CUDA(cudaMemcpyAsync(b_above.p + ns, b_above.p, ns * 4, cudaMemcpyDeviceToDevice, stream));
+                nccl.allreduce(b_above.p + ns, ns, Nccl::U32, Nccl::SUM, stream);
+                ZB_CUDA(cudaMemcpyAsync(hgabove.data(), b_above.p + ns, ns * 4, cudaMemcpyDeviceToHost, stream));
+            }
+            if (total) ZB_CUDA(cudaMemcpyAsync(b_work[cur ^ 1].p, work, total * 4, cudaMemcpyDeviceToDevice, stream));
+            launch_scatter(b_tiles.p, nt, b_segs.p, work, b_flags.p, b_scan.p, b_work[cur ^ 1].p, stream);
+            sync();
+            cur ^= 1;
+            if (G <= 1) hgabove = habove;
+            for (u32 i = 0; i < ns; ++i) {
+                BSeg s = split[i];
+                const u64 ga = hgabove[i], gb = s.glen - ga;
+                if (ga == 0 || gb == 0) {  // degenerate split: retry with the next sample (D2)
+                    s.attempt++;
+                    next.push_back(s);
+                    continue;
+                }
+                const u32 la = habove[i], lb = s.len - la;
+                const int nl = (int)h_nodes.size(), nr = nl + 1;
+                h_nodes.push_back(make_int4(-1, -1, -1, -1));
+                h_nodes.push_back(make_int4(-1, -1, -1, -1));
+                h_nodes[s.node] = make_int4((int)(n_planes + i), nl, nr, -1);
+                next.push_back(BSeg{child_key(s.key, 0), s.depth + 1, nl, s.tree, s.off, lb, gb, 0});
+                next.push_back(BSeg{child_key(s.key, 1), s.depth + 1, nr, s.tree, s.off + lb, la, ga, 0});
+            }
+            n_planes += ns;
+            active.swap(next);
+        }
+        // finalize leaves: members of leaf = b_work[cur][off, off+len)
+        d_members.ensure(members_used + total, members_used, stream);
+        if (total) ZB_CUDA(cudaMemcpyAsync(d_members.p + members_used, b_work[cur].p, total * 4, cudaMemcpyDeviceToDevice, stream));
+        std::vector<std::vector<Tile>> tiles_by_tree(T);
+        for (const BSeg& s : leaves) {
+            int leaf = new_leaf(s.node, s.tree, s.key, s.depth, (long long)members_used + s.off, s.len, s.len);
+            h_nodes[s.node] = make_int4(-1, -1, -1, leaf);
+            for (u32 b = 0; b < s.len; b += 64)
+                tiles_by_tree[s.tree].push_back(Tile{(u32)leaf, std::min<u32>(64, s.len - b), (long long)members_used + s.off + b});
+        }
+        for (int t = 0; t < T; ++t) {
+            u32 nt = (u32)tiles_by_tree[t].size();
+            if (!nt) continue;
+            b_tiles.ensure(nt);
+            ZB_CUDA(cudaMemcpyAsync(b_tiles.p, tiles_by_tree[t].data(), nt * sizeof(Tile), cudaMemcpyHostToDevice, stream));
+            launch_assign_leaf(b_tiles.p, nt, d_members.p, slot_leaf.p + (u64)t * slot_stride, stream);
+            sync();
+        }
+        members_used += total;
+        h_members_valid = false;
+    }
+
+    u64 allreduce_sum_u64(u64 v) {
+        if (G <= 1) return v;
+        b_minh.ensure(1);
+        ZB_CUDA(cudaMemcpyAsync(b_minh.p, &v, 8, cudaMemcpyHostToDevice, stream));
+        nccl.allreduce(b_minh.p, 1, Nccl::U64, Nccl::SUM, stream);
+        ZB_CUDA(cudaMemcpyAsync(&v, b_minh.p, 8, cudaMemcpyDeviceToHost, stream));
+        sync();
+        return v;
+    }
+
+    // build_index, lsh.rs:411-429: every tree over every live row.
+    void bulk_build() {
+        clear_forest();
+        std::vector<u32> live;
+        live.reserve(n_slots);
+        for (u64 s = 0; s < n_slots; ++s)
+            if (!h_tomb[s]) live.push_back((u32)s);
+        const u64 nl = live.size();
+        const u64 gl = allreduce_sum_u64(nl);
+        const u64 total = nl * (u64)T;
+        b_work[0].ensure(total ? total : 1);
+        std::vector<BSeg> segs;
+        for (int t = 0; t < T; ++t) {
+            if (nl) ZB_CUDA(cudaMemcpyAsync(b_work[0].p + (u64)t * nl, live.data(), nl * 4, cudaMemcpyHostToDevice, stream));
+            h_nodes.push_back(make_int4(-1, -1, -1, -1));
+            h_roots[t] = t;
+            segs.push_back(BSeg{root_key(opt.seed, t), 0, t, t, (long long)((u64)t * nl), (u32)nl, gl, 0});
+        }
+        sync();
+        build_subtrees(segs, total);
+        upload_structure();
+        recount_live();
+        built = true;
+    }
+
+    // add on an existing forest (lsh.rs:445-462 per D4): descend, append to leaves, rebuild overfull leaves.
+    void incremental_insert(u64 first_slot, u64 n_new) {
+        if (!n_new && G <= 1) return;
+        ForestView f = view();
+        std::vector<int> leaf_of((size_t)n_new * T);
+        if (n_new) {
+            h_leaves.ensure(n_new * (u64)T);
+            launch_hash(f, rows.p + first_slot * (u64)dimp, n_new, nullptr, nullptr, h_leaves.p, stream);
+            ZB_CUDA(cudaMemcpyAsync(leaf_of.data(), h_leaves.p, leaf_of.size() * 4, cudaMemcpyDeviceToHost, stream));
+        }
+        sync_host_members();
+        for (u64 i = 0; i < n_new; ++i) {
+            for (int t = 0; t < T; ++t) {
+                const int l = leaf_of[i * T + t];
+                if (h_leaf_len[l] == h_leaf_cap[l]) {  // relocate the leaf to the end of the member array with slack
+                    u32 ncap = std::max<u32>(8, h_leaf_cap[l] * 2);
+                    size_t noff = h_members.size();
+                    h_members.resize(noff + ncap, 0);
+                    std::copy(h_members.begin() + h_leaf_off[l], h_members.begin() + h_leaf_off[l] + h_leaf_len[l],
+                              h_members.begin() + noff);
+                    h_leaf_off[l] = (long long)noff;
+                    h_leaf_cap[l] = ncap;
+                }
+                h_members[h_leaf_off[l] + h_leaf_len[l]++] = (u32)(first_slot + i);
+            }
+        }
+        members_used = h_members.size();
+        d_members.ensure(members_used ? members_used : 1);
+        if (members_used) ZB_CUDA(cudaMemcpyAsync(d_members.p, h_members.data(), members_used * 4, cudaMemcpyHostToDevice, stream));
+        if (n_new) {  // slot_leaf of the new rows
+            std::vector<u32> col(n_new);
+            for (int t = 0; t < T; ++t) {
+                for (u64 i = 0; i < n_new; ++i) col[i] = (u32)leaf_of[i * T + t];
+                ZB_CUDA(cudaMemcpyAsync(slot_leaf.p + (u64)t * slot_stride + first_slot, col.data(), n_new * 4, cudaMemcpyHostToDevice, stream));
+                sync();
+            }
+        }
+        upload_structure();
+        recount_live();
+        // overfull leaves (global live count > max_node_size) are rebuilt: lsh.rs:367-378
+        const u32 nl = (u32)h_leaf_off.size();
+        std::vector<u32> plan(nl);
+        ZB_CUDA(cudaMemcpyAsync(plan.data(), view().leaf_plan, (size_t)nl * 4, cudaMemcpyDeviceToHost, stream));
+        sync();
+        std::vector<BSeg> segs;
+        std::vector<u32> work;
+        for (u32 l = 0; l < nl; ++l) {
+            if (h_leaf_node[l] < 0 || plan[l] <= opt.max_node_size) continue;
+            long long off = (long long)work.size();
+            for (u32 i = 0; i < h_leaf_len[l]; ++i) {
+                u32 s = h_members[h_leaf_off[l] + i];
+                if (!h_tomb[s]) work.push_back(s);
+            }
+            segs.push_back(BSeg{h_leaf_key[l], h_leaf_depth[l], h_leaf_node[l], h_leaf_tree[l], off,
+                                (u32)(work.size() - off), plan[l], 0});
+            h_leaf_node[l] = -1;  // retired: no node references it any more
+            h_leaf_len[l] = 0;
+        }
+        if (!segs.empty()) {
+            b_work[0].ensure(work.size() ? work.size() : 1);
+            if (!work.empty()) ZB_CUDA(cudaMemcpyAsync(b_work[0].p, work.data(), work.size() * 4, cudaMemcpyHostToDevice, stream));
+            sync();
+            build_subtrees(segs, work.size());
+            upload_structure();
+            recount_live();
+        }
+    }
+};
+
+// =====================================================================================================
+// search
+// =====================================================================================================
+namespace zb {
+
+static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64* d_out_ord, u64* d_out_bits,
+                          u32* d_out_counts) {
+    cudaStream_t s = ix->stream;
+    const u32 T = ix->T;
+    ix->st.last_queries = nq;
+    ix->st.last_visits = ix->st.last_pairs = ix->st.last_tile_visits = ix->st.last_tile_pairs = 0;
+    ix->st.last_moved_bytes = 0;
+    ix->st.last_scan_launches = ix->st.last_total_launches = 0;
+    if (!nq) return;
+    if (!ix->built || top_k == 0) {
+        launch_fill_u64(d_out_ord, nq * top_k, ZB_SENTINEL, s);
+        launch_fill_u64(d_out_bits, nq * top_k, ZB_SENTINEL, s);
+        ZB_CUDA(cudaMemsetAsync(d_out_counts, 0, nq * 4, s));
+        return;
+    }
+    ForestView f = ix->view();
+    const u64 nw = nq * T;
+    ZB_REQUIRE(nw < (1ull << 31), ZB_ERR_INVALID, "batch too large: %llu walkers", (unsigned long long)nw);
+    ZB_CUDA(cudaEventRecord(ix->ev[0], s));
+    ix->w_counts.ensure(nw + 1);
+    ix->w_off.ensure(nw + 1);
+    ix->w_flag.ensure(4);
+    ix->scan_tmp(nw + 1);
+    u32 h_flag = 0, nv = 0;
+    for (;;) {
+        ix->w_visits.ensure(nw * ix->vpw);
+        ZB_CUDA(cudaMemsetAsync(ix->w_flag.p, 0, 16, s));
+        ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + nw, 0, 4, s));
+        launch_plan(f, d_q, (u32)nq, (u32)top_k, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_flag.p, s);
+        exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->w_counts.p, ix->w_off.p, nw + 1, s);
+        ZB_CUDA(cudaMemcpyAsync(&h_flag, ix->w_flag.p, 4, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaMemcpyAsync(&nv, ix->w_off.p + nw, 4, cudaMemcpyDeviceToHost, s));
+        ix->sync();
+        ix->st.last_total_launches += 2;
+        if (h_flag == 0) break;
+        ZB_REQUIRE(h_flag == 1, ZB_ERR_STATE, "forest deeper than %d levels", ZB_MAX_DEPTH);
+        ix->vpw *= 2;  // a walker produced more visits than its region holds: grow and replan
+        ZB_REQUIRE(ix->vpw <= (1u << 16), ZB_ERR_STATE, "visit plan does not converge");
+    }
+    ix->v_leaf.ensure(nv + 1); ix->v_np.ensure(nv + 1); ix->v_q.ensure(nv + 1);
+    ix->v_pair_len.ensure(nv + 1); ix->v_pair_off.ensure(nv + 1);
+    ix->v_ent_len.ensure(nv + 1); ix->v_ent_off.ensure(nv + 1);
+    ix->v_done.ensure(nv + 1);
+    ix->scan_tmp(nv + 1);
+    ZB_CUDA(cudaMemsetAsync(ix->v_pair_len.p + nv, 0, 8, s));
+    ZB_CUDA(cudaMemsetAsync(ix->v_ent_len.p + nv, 0, 4, s));
+    ZB_CUDA(cudaMemsetAsync(ix->v_done.p, 0, nv + 1, s));
+    launch_compact_visits(f, (u32)nw, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_off.p, ix->v_leaf.p, ix->v_np.p,
+                          ix->v_q.p, ix->v_pair_len.p, ix->v_ent_len.p, s);
+    exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_ent_len.p, ix->v_ent_off.p, nv + 1, s);
+    u32 total_slots = 0;
+    ZB_CUDA(cudaMemcpyAsync(&total_slots, ix->v_ent_off.p + nv, 4, cudaMemcpyDeviceToHost, s));
+    ix->st.last_total_launches += 2;
+    ZB_CUDA(cudaEventRecord(ix->ev[1], s));
+
+    // ---- fused leaf-tile scan for visits of large leaves (zb_scan.cu); marks v_done and shrinks pair_len ----
+    ix->sync();
+    ix->entries.ensure(total_slots ? total_slots : 1);
+    u64 tile_pairs = 0, tile_visits = 0, moved = 0;
+    u32 scan_launches = 0;
+    if (ix->p_use_tile_scan && nv)
+        tile_scan(ix->scan_ws, f, ix->opt.metric, d_q, (u32)nq, nv, ix->v_leaf.p, ix->v_np.p, ix->v_q.p, ix->v_ent_off.p,
+                  ix->v_pair_len.p, ix->v_done.p, ix->entries.p, (u32)top_k, (u32)ix->p_tile_min_rows,
+                  (u32)ix->p_tile_queries, (u32)ix->h_leaf_off.size(), s, &tile_visits, &tile_pairs, &moved, &scan_launches);
+
+    // ---- generic path for the remaining visits ----
+    exclusive_scan_u64(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_pair_len.p, ix->v_pair_off.p, nv + 1, s);
+    u64 total_pairs = 0;
+    ZB_CUDA(cudaMemcpyAsync(&total_pairs, ix->v_pair_off.p + nv, 8, cudaMemcpyDeviceToHost, s));
+    ix->sync();
+    ix->pair_key.ensure(total_pairs ? total_pairs : 1);
+    launch_score_pairs(f, (int)ix->opt.metric, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, total_pairs,
+                       ix->pair_key.p, s);
+    ZB_CUDA(cudaEventRecord(ix->ev[2], s));
+    if (total_pairs || tile_visits < nv)
+        launch_select_visits(f, nv, ix->v_leaf.p, ix->v_np.p, ix->v_pair_off.p, ix->pair_key.p, ix->v_ent_off.p,
+                             ix->entries.p, ix->v_done.p, (u32)top_k, s);
+    ZB_CUDA(cudaEventRecord(ix->ev[3], s));
+    const Entry* final_entries = ix->entries.p;
+    if (ix->G > 1) {  // allgather of the per-visit local top-n' lists, then per-visit global top-n' (survey 8e)
+        ix->gathered.ensure((size_t)total_slots * ix->G + 1);
+        ix->nccl.allgather(ix->entries.p, ix->gathered.p, (size_t)total_slots * sizeof(Entry), s);
+        launch_merge_ranks(nv, ix->v_ent_off.p, total_slots, ix->G, ix->gathered.p, ix->entries.p, (u32)top_k, s);
+    }
+    launch_merge_queries((u32)nq, T, ix->w_off.p, ix->v_ent_off.p, final_entries, (u32)top_k, d_out_ord, d_out_bits,
+                         d_out_counts, s);
+    ZB_CUDA(cudaEventRecord(ix->ev[4], s));
+    ix->sync();
+    float ms;
+    cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]); ix->st.last_ms_plan = ms;
+    cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]); ix->st.last_ms_scan = ms;
+    cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3]); ix->st.last_ms_select = ms;
+    cudaEventElapsedTime(&ms, ix->ev[3], ix->ev[4]); ix->st.last_ms_merge = ms;
+    cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[4]); ix->st.last_ms_total = ms;
+    ix->st.last_visits = nv;
+    ix->st.last_pairs = total_pairs + tile_pairs;
+    ix->st.last_tile_visits = tile_visits;
+    ix->st.last_tile_pairs = tile_pairs;
+    ix->st.last_moved_bytes = moved + total_pairs * (u64)ix->dim * 4;
+    ix->st.last_scan_launches = scan_launches + (total_pairs ? 1 : 0);
+    ix->st.last_total_launches += scan_launches + 5 + (ix->G > 1 ? 1 : 0);
+}
+
+static const float* stage_queries_device(zb_index* ix, const float* d_q, u64 nq) {
+    if (ix->dim == ix->dimp && ((uintptr_t)d_q & 15) == 0) return d_q;
+    ix->q_stage.ensure(nq * (u64)ix->dimp);
+    launch_pad_rows(d_q, nq, ix->dim, ix->dimp, ix->q_stage.p, ix->stream);
+    return ix->q_stage.p;
+}
+
+static void build_export_table(zb_index* ix, std::vector<int>* order_nodes, std::vector<int>* leaf_export) {
+    // preorder numbering (node, left subtree, right subtree), trees in order -- the oracle's numbering
+    leaf_export->assign(ix->h_leaf_off.size(), -1);
+    int next_leaf = 0;
+    std::vector<int> stack;
+    for (int t = 0; t < ix->T && ix->built; ++t) {
+        stack.push_back(ix->h_roots[t]);
+        while (!stack.empty()) {
+            int n = stack.back();
+            stack.pop_back();
+            if (order_nodes) order_nodes->push_back(n);
+            int4 nd = ix->h_nodes[n];
+            if (nd.x < 0) (*leaf_export)[nd.w] = next_leaf++;
+            else {
+                stack.push_back(nd.z);
+                stack.push_back(nd.y);
+            }
+        }
+    }
+}
+
+}  // namespace zb
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+#define ZB_API_BEGIN try {
+#define ZB_API_END                                   \
+    return ZB_OK;                                    \
+    }                                                \
+    catch (const zb::Error& e) {                     \
+        zb::t_last_error = e.what();                 \
+        return e.code;                               \
+    }                                                \
+    catch (const std::bad_alloc&) {                  \
+        zb::t_last_error = "host allocation failed"; \
+        return ZB_ERR_OOM;                           \
+    }                                                \
+    catch (const std::exception& e) {                \
+        zb::t_last_error = e.what();                 \
+        return ZB_ERR_INVALID;                       \
+    }
+
+extern "C" {
+
+const char* zb_last_error(void) { return zb::t_last_error.c_str(); }
+int zb_abi_version(void) { return ZB_ABI_VERSION; }
+
+int zb_device_count(int* out_count) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(out_count, ZB_ERR_INVALID, "out_count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *out_count = n;
+    ZB_API_END
+}
+
+int zb_index_create(const zb_options* o, zb_index** out) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(o && out, ZB_ERR_INVALID, "NULL argument");
+    ZB_REQUIRE(o->dim >= 1 && o->dim <= 65536, ZB_ERR_INVALID, "dim %u out of range", o->dim);
+    ZB_REQUIRE(o->metric <= 2, ZB_ERR_INVALID, "metric %u is not one of cosine/l2sq/l2", o->metric);
+    ZB_REQUIRE(o->num_trees >= 1 && o->num_trees <= 4096, ZB_ERR_INVALID, "num_trees %u out of range", o->num_trees);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        throw zb::Error(ZB_ERR_NO_DEVICE, "no CUDA device: libzebra_b200 has no CPU fallback");
+    }
+    ZB_REQUIRE(o->device >= 0 && o->device < ndev, ZB_ERR_INVALID, "device %d out of range (%d devices)", o->device, ndev);
+    cudaDeviceProp prop;
+    ZB_CUDA(cudaGetDeviceProperties(&prop, o->device));
+    ZB_REQUIRE(prop.major == 10, ZB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+               o->device, prop.major, prop.minor);
+    zb_index* ix = new zb_index();
+    ix->opt = *o;
+    ix->dim = (int)o->dim;
+    ix->dimp = (ix->dim + 15) / 16 * 16;
+    ix->chunks = ix->dimp / 16;
+    ix->T = (int)o->num_trees;
+    ix->device = o->device;
+    ix->G = o->shard_count > 1 ? o->shard_count : 1;
+    ix->rank = ix->G > 1 ? o->shard_rank : 0;
+    ZB_REQUIRE(ix->rank < ix->G, ZB_ERR_INVALID, "shard_rank %u >= shard_count %u", ix->rank, ix->G);
+    ix->use_device();
+    ZB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    for (auto& ev : ix->ev) ZB_CUDA(cudaEventCreate(&ev));
+    ix->epoch_ms = (u64)std::chrono::duration_cast<std::chrono::milliseconds>(
+                       std::chrono::system_clock::now().time_since_epoch()).count() & 0xFFFFFFFFFFFFull;
+    ix->h_roots.assign(ix->T, -1);
+    *out = ix;
+    ZB_API_END
+}
+
+int zb_index_destroy(zb_index* ix) {
+    ZB_API_BEGIN
+    if (!ix) return ZB_OK;
+    cudaSetDevice(ix->device);
+    cudaStreamSynchronize(ix->stream);
+    ix->nccl.destroy();
+    for (auto& ev : ix->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ix->stream);
+    delete ix;
+    ZB_API_END
+}
+
+static void add_common(zb_index* ix, u64 n, const float* src, bool src_on_device, const uint8_t* ids16, uint8_t* out_ids16,
+                       u64* out_ordinals) {
+    ix->use_device();
+    if (ix->G > 1) ZB_REQUIRE(ix->comm_ready, ZB_ERR_STATE, "sharded index used before zb_index_comm_init");
+    const int mode = ids16 ? 2 : 1;
+    if (n) {
+        ZB_REQUIRE(ix->id_mode == 0 || ix->id_mode == mode, ZB_ERR_INVALID,
+                   "ids must be supplied for every row of an index or for none");
+        ix->id_mode = mode;
+    }
+    const u64 first = ix->total_rows;
+    if (ids16) {
+        for (u64 i = 0; i < n; ++i) {
+            Id16 id{load_be64(ids16 + 16 * i), load_be64(ids16 + 16 * i + 8)};
+            ZB_REQUIRE(ix->ordinal_by_id.find(id) == ix->ordinal_by_id.end(), ZB_ERR_INVALID, "duplicate id at row %llu",
+                       (unsigned long long)i);
+            ix->ordinal_by_id.emplace(id, first + i);
+            ix->ids_by_ordinal.push_back(id);
+        }
+    }
+    // rows this shard owns
+    std::vector<u64> ordinals;
+    u64 i0 = 0;
+    if (ix->G > 1) {
+        i0 = (ix->rank + ix->G - first % ix->G) % ix->G;
+        for (u64 i = i0; i < n; i += ix->G) ordinals.push_back(first + i);
+    } else {
+        ordinals.resize(n);
+        for (u64 i = 0; i < n; ++i) ordinals[i] = first + i;
+    }
+    const u64 nloc = ordinals.size();
+    const u64 first_slot = ix->n_slots;
+    if (nloc) {
+        const u64 stride = (u64)ix->dim * ix->G;
+        if (src_on_device) {
+            ix->append_rows_device(src + i0 * (u64)ix->dim, stride, nloc, ordinals.data());
+        } else {
+            ix->r_stage.ensure(nloc * (u64)ix->dim);
+            ZB_CUDA(cudaMemcpy2DAsync(ix->r_stage.p, (size_t)ix->dim * 4, src + i0 * (u64)ix->dim, stride * 4,
+                                      (size_t)ix->dim * 4, nloc, cudaMemcpyHostToDevice, ix->stream));
+            ix->append_rows_device(ix->r_stage.p, ix->dim, nloc, ordinals.data());
+        }
+    }
+    ix->total_rows += n;
+    for (u64 i = 0; i < n; ++i) {
+        if (out_ordinals) out_ordinals[i] = first + i;
+        if (out_ids16) ix->id_of(first + i, out_ids16 + 16 * i);
+    }
+    if (!ix->built) {
+        if (ix->total_rows > 0) ix->bulk_build();
+    } else {
+        ix->incremental_insert(first_slot, nloc);
+    }
+}
+
+int zb_index_add(zb_index* ix, uint64_t n, const float* rows, const uint8_t* ids16, uint8_t* out_ids16, uint64_t* out_ordinals) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (rows || !n), ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    add_common(ix, n, rows, false, ids16, out_ids16, (u64*)out_ordinals);
+    ZB_API_END
+}
+int zb_index_add_device(zb_index* ix, uint64_t n, const float* d_rows, const uint8_t* ids16, uint8_t* out_ids16,
+                        uint64_t* out_ordinals) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (d_rows || !n), ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    add_common(ix, n, d_rows, true, ids16, out_ids16, (u64*)out_ordinals);
+    ZB_API_END
+}
+int zb_index_add_owned_device(zb_index* ix, uint64_t n_local, const float* d_rows, const uint64_t* ordinals, uint64_t total_n) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (d_rows || !n_local) && (ordinals || !n_local), ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->use_device();
+    if (ix->G > 1) ZB_REQUIRE(ix->comm_ready, ZB_ERR_STATE, "sharded index used before zb_index_comm_init");
+    ZB_REQUIRE(ix->id_mode != 2, ZB_ERR_INVALID, "owned-row loading needs library-minted ids");
+    if (total_n) ix->id_mode = 1;
+    for (u64 i = 0; i < n_local; ++i)
+        ZB_REQUIRE(ix->owns(ordinals[i]) && ordinals[i] >= ix->total_rows && ordinals[i] < ix->total_rows + total_n &&
+                       ix->slot_of(ordinals[i]) == ix->n_slots + i,
+                   ZB_ERR_INVALID, "ordinal %llu is not the next row this shard owns", (unsigned long long)ordinals[i]);
+    const u64 first_slot = ix->n_slots;
+    ix->append_rows_device(d_rows, ix->dim, n_local, (const u64*)ordinals);
+    ix->total_rows += total_n;
+    if (!ix->built) {
+        if (ix->total_rows > 0) ix->bulk_build();
+    } else {
+        ix->incremental_insert(first_slot, n_local);
+    }
+    ZB_API_END
+}
+
+static void remove_ordinals(zb_index* ix, u64 n, const u64* ordinals, const u8* valid, uint8_t* out_removed) {
+    ix->use_device();
+    std::vector<u32> slots(n);
+    for (u64 i = 0; i < n; ++i) {
+        bool ok = (!valid || valid[i]) && ordinals[i] < ix->total_rows && ix->owns(ordinals[i]) &&
+                  ix->slot_of(ordinals[i]) < ix->n_slots;
+        slots[i] = ok ? (u32)ix->slot_of(ordinals[i]) : 0xFFFFFFFFu;
+    }
+    std::vector<u8> flags(n, 0);
+    if (n) {
+        ix->rm_slots.ensure(n);
+        ix->rm_flags.ensure(n);
+        ZB_CUDA(cudaMemcpyAsync(ix->rm_slots.p, slots.data(), n * 4, cudaMemcpyHostToDevice, ix->stream));
+        if (ix->built) {
+            launch_tombstone(ix->rm_slots.p, (u32)n, ix->tomb.p, ix->slot_leaf.p, ix->slot_stride, ix->T, ix->d_leaf_live.p,
+                             ix->rm_flags.p, ix->stream);
+        } else {
+            ZB_CUDA(cudaMemsetAsync(ix->rm_flags.p, 0, n, ix->stream));
+        }
+        if (ix->G > 1) ix->nccl.allreduce(ix->rm_flags.p, n, Nccl::U8, Nccl::MAX, ix->stream);
+        ZB_CUDA(cudaMemcpyAsync(flags.data(), ix->rm_flags.p, n, cudaMemcpyDeviceToHost, ix->stream));
+    }
+    ix->refresh_plan_counts();
+    ix->sync();
+    for (u64 i = 0; i < n; ++i) {
+        if (flags[i] && slots[i] != 0xFFFFFFFFu && !ix->h_tomb[slots[i]]) {
+            ix->h_tomb[slots[i]] = 1;
+            ix->n_live--;
+        }
+        if (out_removed) out_removed[i] = flags[i];
+    }
+}
+
+int zb_index_remove_ordinals(zb_index* ix, uint64_t n, const uint64_t* ordinals, uint8_t* out_removed) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (ordinals || !n), ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    remove_ordinals(ix, n, (const u64*)ordinals, nullptr, out_removed);
+    ZB_API_END
+}
+int zb_index_remove(zb_index* ix, uint64_t n, const uint8_t* ids16, uint8_t* out_removed) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (ids16 || !n), ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::vector<u64> ords(n, 0);
+    std::vector<u8> valid(n, 0);
+    for (u64 i = 0; i < n; ++i) valid[i] = ix->ordinal_of(ids16 + 16 * i, &ords[i]) ? 1 : 0;
+    remove_ordinals(ix, n, ords.data(), valid.data(), out_removed);
+    ZB_API_END
+}
+
+int zb_index_clear(zb_index* ix) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->use_device();
+    ix->sync();
+    ix->clear_forest();
+    ix->n_slots = ix->n_live = ix->total_rows = 0;
+    ix->h_ord.clear();
+    ix->h_tomb.clear();
+    ix->ids_by_ordinal.clear();
+    ix->ordinal_by_id.clear();
+    ix->id_mode = 0;
+    ZB_API_END
+}
+
+int zb_index_no_vectors(zb_index* ix, int* out) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && out, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    u64 live = ix->n_live;
+    if (ix->G > 1) {
+        ix->use_device();
+        live = ix->allreduce_sum_u64(live);
+    }
+    *out = live == 0;
+    ZB_API_END
+}
+int zb_index_no_trees(zb_index* ix, int* out) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && out, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *out = !ix->built;
+    ZB_API_END
+}
+
+int zb_index_search_batch_device(zb_index* ix, uint64_t nq, const float* d_q, uint64_t top_k, uint64_t* d_out_ord,
+                                 uint64_t* d_out_bits, uint32_t* d_out_counts) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (d_q || !nq) && ((d_out_ord && d_out_bits && d_out_counts) || !nq), ZB_ERR_INVALID, "NULL argument");
+    ZB_REQUIRE(top_k <= ZB_MAX_TOPK, ZB_ERR_INVALID, "top_k %llu exceeds %d", (unsigned long long)top_k, ZB_MAX_TOPK);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->use_device();
+    const u64 chunk = 32768;
+    for (u64 q0 = 0; q0 < nq; q0 += chunk) {
+        u64 c = std::min<u64>(chunk, nq - q0);
+        const float* q = stage_queries_device(ix, d_q + q0 * (u64)ix->dim, c);
+        search_device(ix, c, q, top_k, (u64*)d_out_ord + q0 * top_k, (u64*)d_out_bits + q0 * top_k, d_out_counts + q0);
+    }
+    ix->sync();
+    ZB_API_END
+}
+
+int zb_index_search_batch(zb_index* ix, uint64_t nq, const float* queries, uint64_t top_k, uint8_t* out_ids16,
+                          uint64_t* out_ordinals, uint64_t* out_bits, uint32_t* out_counts) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (queries || !nq) && ((out_bits && out_counts) || !nq), ZB_ERR_INVALID, "NULL argument");
+    ZB_REQUIRE(top_k <= ZB_MAX_TOPK, ZB_ERR_INVALID, "top_k %llu exceeds %d", (unsigned long long)top_k, ZB_MAX_TOPK);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->use_device();
+    cudaStream_t s = ix->stream;
+    const u64 chunk = 32768;
+    std::vector<u64> ord_tmp;
+    if (!out_ordinals && out_ids16) ord_tmp.resize(std::min<u64>(chunk, nq) * top_k);
+    for (u64 q0 = 0; q0 < nq; q0 += chunk) {
+        const u64 c = std::min<u64>(chunk, nq - q0);
+        ix->q_stage.ensure(c * (u64)ix->dimp);
+        if (ix->dim == ix->dimp) {
+            ZB_CUDA(cudaMemcpyAsync(ix->q_stage.p, queries + q0 * (u64)ix->dim, c * (u64)ix->dim * 4, cudaMemcpyHostToDevice, s));
+        } else {
+            ZB_CUDA(cudaMemsetAsync(ix->q_stage.p, 0, c * (u64)ix->dimp * 4, s));
+            ZB_CUDA(cudaMemcpy2DAsync(ix->q_stage.p, (size_t)ix->dimp * 4, queries + q0 * (u64)ix->dim, (size_t)ix->dim * 4,
+                                      (size_t)ix->dim * 4, c, cudaMemcpyHostToDevice, s));
+        }
+        ix->o_ord.ensure(c * top_k + 1);
+        ix->o_bits.ensure(c * top_k + 1);
+        ix->o_counts.ensure(c);
+        search_device(ix, c, ix->q_stage.p, top_k, ix->o_ord.p, ix->o_bits.p, ix->o_counts.p);
+        u64* ords = out_ordinals ? (u64*)out_ordinals + q0 * top_k : ord_tmp.data();
+        if (top_k) {
+            if (out_ordinals || out_ids16) ZB_CUDA(cudaMemcpyAsync(ords, ix->o_ord.p, c * top_k * 8, cudaMemcpyDeviceToHost, s));
+            ZB_CUDA(cudaMemcpyAsync(out_bits + q0 * top_k, ix->o_bits.p, c * top_k * 8, cudaMemcpyDeviceToHost, s));
+        }
+        ZB_CUDA(cudaMemcpyAsync(out_counts + q0, ix->o_counts.p, c * 4, cudaMemcpyDeviceToHost, s));
+        ix->sync();
+        if (out_ids16) {
+            for (u64 i = 0; i < c * top_k; ++i) {
+                uint8_t* dst = out_ids16 + (q0 * top_k + i) * 16;
+                if (ords[i] == ZB_SENTINEL) memset(dst, 0xFF, 16);
+                else ix->id_of(ords[i], dst);
+            }
+        }
+    }
+    ZB_API_END
+}
+
+int zb_index_hash_device(zb_index* ix, uint64_t n, const float* d_rows, uint64_t* d_keys, uint32_t* d_depths, int32_t* d_leaves) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (d_rows || !n), ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->use_device();
+    ZB_REQUIRE(ix->built, ZB_ERR_STATE, "hash on an index without trees");
+    const float* x = d_rows;
+    if (!(ix->dim == ix->dimp && ((uintptr_t)d_rows & 15) == 0)) {
+        ix->r_stage.ensure(n * (u64)ix->dimp);
+        launch_pad_rows(d_rows, n, ix->dim, ix->dimp, ix->r_stage.p, ix->stream);
+        x = ix->r_stage.p;
+    }
+    launch_hash(ix->view(), x, n, (u64*)d_keys, d_depths, d_leaves, ix->stream);
+    if (d_leaves) {
+        if (!ix->export_table_valid) {
+            std::vector<int> table;
+            build_export_table(ix, nullptr, &table);
+            ix->d_leaf_export.ensure(table.size() ? table.size() : 1);
+            if (!table.empty())
+                ZB_CUDA(cudaMemcpyAsync(ix->d_leaf_export.p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+            ix->sync();
+            ix->export_table_valid = true;
+        }
+        u64 tot = n * (u64)ix->T;
+        if (tot) remap_leaves_kernel<<<(u32)((tot + 255) / 256), 256, 0, ix->stream>>>(d_leaves, tot, ix->d_leaf_export.p);
+    }
+    ix->sync();
+    ZB_API_END
+}
+
+int zb_index_hash(zb_index* ix, uint64_t n, const float* rows, uint64_t* out_keys, uint32_t* out_depths, int32_t* out_leaves) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (rows || !n), ZB_ERR_INVALID, "NULL argument");
+    {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        ix->use_device();
+        ZB_REQUIRE(ix->built, ZB_ERR_STATE, "hash on an index without trees");
+        ix->r_stage.ensure(n * (u64)ix->dimp + 4);
+        ix->h_keys.ensure(n * (u64)ix->T + 1);
+        ix->h_depths.ensure(n * (u64)ix->T + 1);
+        ix->h_leaves.ensure(n * (u64)ix->T + 1);
+    }
+    // stage rows (padded) then reuse the device entry point
+    DBuf<float> tmp;
+    ix->use_device();
+    tmp.ensure(n * (u64)ix->dim + 4);
+    ZB_CUDA(cudaMemcpy(tmp.p, rows, n * (u64)ix->dim * 4, cudaMemcpyHostToDevice));
+    int rc = zb_index_hash_device(ix, n, tmp.p, (uint64_t*)ix->h_keys.p, ix->h_depths.p, ix->h_leaves.p);
+    if (rc != ZB_OK) return rc;
+    const u64 tot = n * (u64)ix->T;
+    if (out_keys) ZB_CUDA(cudaMemcpy(out_keys, ix->h_keys.p, tot * 8, cudaMemcpyDeviceToHost));
+    if (out_depths) ZB_CUDA(cudaMemcpy(out_depths, ix->h_depths.p, tot * 4, cudaMemcpyDeviceToHost));
+    if (out_leaves) ZB_CUDA(cudaMemcpy(out_leaves, ix->h_leaves.p, tot * 4, cudaMemcpyDeviceToHost));
+    ZB_API_END
+}
+
+int zb_index_forest_sizes(zb_index* ix, int64_t* sizes4) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && sizes4, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::vector<int> order, leaf_export;
+    build_export_table(ix, &order, &leaf_export);
+    int64_t planes = 0, leaves = 0, members = 0;
+    for (int n : order) {
+        int4 nd = ix->h_nodes[n];
+        if (nd.x >= 0) planes++;
+        else {
+            leaves++;
+            members += ix->h_leaf_len[nd.w];
+        }
+    }
+    sizes4[0] = (int64_t)order.size(); sizes4[1] = planes; sizes4[2] = leaves; sizes4[3] = members;
+    ZB_API_END
+}
+
+int zb_index_export_forest(zb_index* ix, int32_t* nodes, int32_t* roots, float* coef, float* cst, int64_t* leaf_off,
+                           uint64_t* members) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->use_device();
+    if (!ix->built) return ZB_OK;
+    ix->sync_host_members();
+    std::vector<int> order, leaf_export;
+    build_export_table(ix, &order, &leaf_export);
+    std::vector<int> newid(ix->h_nodes.size(), -1);
+    for (size_t i = 0; i < order.size(); ++i) newid[order[i]] = (int)i;
+    int64_t np = 0, nl = 0, nm = 0;
+    leaf_off[0] = 0;
+    for (size_t i = 0; i < order.size(); ++i) {
+        int4 nd = ix->h_nodes[order[i]];
+        if (nd.x >= 0) {
+            ZB_CUDA(cudaMemcpy2D(coef + np * ix->dim, (size_t)ix->dim * 4, ix->d_coef.p + (u64)nd.x * ix->dimp, (size_t)ix->dimp * 4,
+                                 (size_t)ix->dim * 4, 1, cudaMemcpyDeviceToHost));
+            ZB_CUDA(cudaMemcpy(cst + np, ix->d_cst.p + nd.x, 4, cudaMemcpyDeviceToHost));
+            nodes[4 * i + 0] = (int)np++; nodes[4 * i + 1] = newid[nd.y]; nodes[4 * i + 2] = newid[nd.z]; nodes[4 * i + 3] = -1;
+        } else {
+            const int l = nd.w;
+            for (u32 j = 0; j < ix->h_leaf_len[l]; ++j) members[nm++] = ix->h_ord[ix->h_members[ix->h_leaf_off[l] + j]];
+            leaf_off[++nl] = nm;
+            nodes[4 * i + 0] = -1; nodes[4 * i + 1] = -1; nodes[4 * i + 2] = -1; nodes[4 * i + 3] = (int)(nl - 1);
+        }
+    }
+    for (int t = 0; t < ix->T; ++t) roots[t] = newid[ix->h_roots[t]];
+    ZB_API_END
+}
+
+int zb_index_load_forest(zb_index* ix, uint64_t n, const float* rows, const uint8_t* ids16, const int64_t* sizes4,
+                         const int32_t* nodes, const int32_t* roots, const float* coef, const float* cst,
+                         const int64_t* leaf_off, const uint64_t* members) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && sizes4 && nodes && roots && leaf_off && (rows || !n), ZB_ERR_INVALID, "NULL argument");
+    int rc = zb_index_clear(ix);
+    if (rc != ZB_OK) return rc;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->use_device();
+    if (ix->G > 1) ZB_REQUIRE(ix->comm_ready, ZB_ERR_STATE, "sharded index used before zb_index_comm_init");
+    const int64_t nn = sizes4[0], npl = sizes4[1], nl = sizes4[2], nm = sizes4[3];
+    ZB_REQUIRE(nn >= ix->T && npl >= 0 && nl >= 1 && nm >= 0, ZB_ERR_INVALID, "bad forest sizes");
+    // rows: ordinals 0..n-1
+    ix->id_mode = ids16 ? 2 : 1;
+    if (ids16)
+        for (u64 i = 0; i < n; ++i) {
+            Id16 id{load_be64(ids16 + 16 * i), load_be64(ids16 + 16 * i + 8)};
+            ix->ordinal_by_id.emplace(id, i);
+            ix->ids_by_ordinal.push_back(id);
+        }
+    std::vector<u64> ordinals;
+    for (u64 i = ix->rank; i < n; i += ix->G) ordinals.push_back(i);
+    if (!ordinals.empty()) {
+        ix->r_stage.ensure(ordinals.size() * (u64)ix->dim);
+        ZB_CUDA(cudaMemcpy2DAsync(ix->r_stage.p, (size_t)ix->dim * 4, rows + (u64)ix->rank * ix->dim, (size_t)ix->dim * ix->G * 4,
+                                  (size_t)ix->dim * 4, ordinals.size(), cudaMemcpyHostToDevice, ix->stream));
+        ix->append_rows_device(ix->r_stage.p, ix->dim, ordinals.size(), ordinals.data());
+    }
+    ix->total_rows = n;
+    // structure: validate, compute keys/depths by traversal
+    ix->h_nodes.resize(nn);
+    for (int64_t i = 0; i < nn; ++i) {
+        const int32_t* nd = nodes + 4 * i;
+        if (nd[0] >= 0) {
+            ZB_REQUIRE(nd[0] < npl && nd[1] >= 0 && nd[1] < nn && nd[2] >= 0 && nd[2] < nn, ZB_ERR_INVALID, "node %lld malformed", (long long)i);
+        } else {
+            ZB_REQUIRE(nd[3] >= 0 && nd[3] < nl, ZB_ERR_INVALID, "leaf node %lld malformed", (long long)i);
+        }
+        ix->h_nodes[i] = make_int4(nd[0], nd[1], nd[2], nd[3]);
+    }
+    ix->h_leaf_off.assign(nl, 0); ix->h_leaf_len.assign(nl, 0); ix->h_leaf_cap.assign(nl, 0);
+    ix->h_leaf_key.assign(nl, 0); ix->h_leaf_depth.assign(nl, 0); ix->h_leaf_node.assign(nl, -1); ix->h_leaf_tree.assign(nl, 0);
+    // local member lists (owned rows only), leaf-major
+    ix->h_members.clear();
+    for (int64_t l = 0; l < nl; ++l) {
+        ZB_REQUIRE(leaf_off[l] <= leaf_off[l + 1] && leaf_off[l + 1] <= nm, ZB_ERR_INVALID, "leaf_off not monotone");
+        ix->h_leaf_off[l] = (long long)ix->h_members.size();
+        for (int64_t j = leaf_off[l]; j < leaf_off[l + 1]; ++j) {
+            ZB_REQUIRE(members[j] < n, ZB_ERR_INVALID, "member ordinal out of range");
+            if (ix->owns(members[j])) ix->h_members.push_back((u32)ix->slot_of(members[j]));
+        }
+        ix->h_leaf_len[l] = ix->h_leaf_cap[l] = (u32)(ix->h_members.size() - ix->h_leaf_off[l]);
+    }
+    struct Fr { int node; u64 key; int depth; };
+    std::vector<Fr> stack;
+    std::vector<u32> slot_leaf_h((size_t)ix->T * std::max<u64>(ix->n_slots, 1), 0);
+    for (int t = 0; t < ix->T; ++t) {
+        ZB_REQUIRE(roots[t] >= 0 && roots[t] < nn, ZB_ERR_INVALID, "root %d out of range", t);
+        ix->h_roots[t] = roots[t];
+        stack.push_back(Fr{roots[t], root_key(ix->opt.seed, t), 0});
+        size_t visited = 0;
+        while (!stack.empty()) {
+            Fr fr = stack.back();
+            stack.pop_back();
+            ZB_REQUIRE(++visited <= (size_t)nn, ZB_ERR_INVALID, "forest has a cycle");
+            ZB_REQUIRE(fr.depth <= ZB_MAX_DEPTH, ZB_ERR_INVALID, "tree %d deeper than %d levels", t, ZB_MAX_DEPTH);
+            int4 nd = ix->h_nodes[fr.node];
+            if (nd.x >= 0) {
+                stack.push_back(Fr{nd.z, child_key(fr.key, 1), fr.depth + 1});
+                stack.push_back(Fr{nd.y, child_key(fr.key, 0), fr.depth + 1});
+            } else {
+                ZB_REQUIRE(ix->h_leaf_node[nd.w] < 0, ZB_ERR_INVALID, "leaf %d referenced twice", nd.w);
+                ix->h_leaf_node[nd.w] = fr.node;
+                ix->h_leaf_key[nd.w] = fr.key;
+                ix->h_leaf_depth[nd.w] = fr.depth;
+                ix->h_leaf_tree[nd.w] = t;
+                for (u32 j = 0; j < ix->h_leaf_len[nd.w]; ++j)
+                    slot_leaf_h[(size_t)t * ix->n_slots + ix->h_members[ix->h_leaf_off[nd.w] + j]] = (u32)nd.w;
+            }
+        }
+    }
+    ix->n_planes = (u64)npl;
+    ix->d_coef.ensure(std::max<u64>(1, (u64)npl * ix->dimp));
+    ix->d_cst.ensure(std::max<u64>(1, (u64)npl));
+    if (npl) {
+        ZB_CUDA(cudaMemsetAsync(ix->d_coef.p, 0, (u64)npl * ix->dimp * 4, ix->stream));
+        ZB_CUDA(cudaMemcpy2DAsync(ix->d_coef.p, (size_t)ix->dimp * 4, coef, (size_t)ix->dim * 4, (size_t)ix->dim * 4, npl,
+                                  cudaMemcpyHostToDevice, ix->stream));
+        ZB_CUDA(cudaMemcpyAsync(ix->d_cst.p, cst, (u64)npl * 4, cudaMemcpyHostToDevice, ix->stream));
+    }
+    ix->members_used = ix->h_members.size();
+    ix->h_members_valid = true;
+    ix->d_members.ensure(std::max<u64>(1, ix->members_used));
+    if (ix->members_used)
+        ZB_CUDA(cudaMemcpyAsync(ix->d_members.p, ix->h_members.data(), ix->members_used * 4, cudaMemcpyHostToDevice, ix->stream));
+    if (ix->n_slots)
+        ZB_CUDA(cudaMemcpy2DAsync(ix->slot_leaf.p, ix->slot_stride * 4, slot_leaf_h.data(), ix->n_slots * 4, ix->n_slots * 4, ix->T,
+                                  cudaMemcpyHostToDevice, ix->stream));
+    ix->sync();
+    ix->built = true;
+    ix->upload_structure();
+    ix->recount_live();
+    ix->sync();
+    ZB_API_END
+}
+
+int zb_index_stats(zb_index* ix, zb_stats* out) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && out, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->st.rows = ix->n_slots;
+    ix->st.live_rows = ix->n_live;
+    ix->st.total_rows = ix->total_rows;
+    ix->st.nodes = ix->h_nodes.size();
+    ix->st.planes = ix->n_planes;
+    ix->st.leaves = ix->h_leaf_off.size();
+    ix->st.device_bytes = zb::g_device_bytes;
+    *out = ix->st;
+    ZB_API_END
+}
+
+int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && key, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::string k(key);
+    if (k == "tile_min_rows") ix->p_tile_min_rows = value;
+    else if (k == "tile_queries") ix->p_tile_queries = value;
+    else if (k == "use_tile_scan") ix->p_use_tile_scan = value;
+    else throw zb::Error(ZB_ERR_INVALID, "unknown parameter " + k);
+    ZB_API_END
+}
+
+int zb_comm_unique_id(uint8_t* out_id128) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(out_id128, ZB_ERR_INVALID, "NULL argument");
+    Nccl::unique_id(out_id128);
+    ZB_API_END
+}
+
+int zb_index_comm_init(zb_index* ix, const uint8_t* id128) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && id128, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ZB_REQUIRE(ix->G > 1, ZB_ERR_STATE, "index is not sharded");
+    ZB_REQUIRE(!ix->comm_ready, ZB_ERR_STATE, "communicator already initialised");
+    ix->nccl.init(id128, (int)ix->rank, (int)ix->G, ix->device);
+    ix->comm_ready = true;
+    // agree on the id epoch (minted ids must be identical on every rank)
+    ix->b_minh.ensure(1);
+    ZB_CUDA(cudaMemcpyAsync(ix->b_minh.p, &ix->epoch_ms, 8, cudaMemcpyHostToDevice, ix->stream));
+    ix->nccl.allreduce(ix->b_minh.p, 1, Nccl::U64, Nccl::MIN, ix->stream);
+    ZB_CUDA(cudaMemcpyAsync(&ix->epoch_ms, ix->b_minh.p, 8, cudaMemcpyDeviceToHost, ix->stream));
+    ix->sync();
+    ZB_API_END
+}
+
+static void pad_to_device(int device, const float* h, u64 n, u32 dim, int dimp, DBuf<float>& d) {
+    d.ensure(std::max<u64>(1, n * (u64)dimp));
+    if (!n) return;
+    ZB_CUDA(cudaMemset(d.p, 0, n * (u64)dimp * 4));
+    ZB_CUDA(cudaMemcpy2D(d.p, (size_t)dimp * 4, h, (size_t)dim * 4, (size_t)dim * 4, n, cudaMemcpyHostToDevice));
+}
+
+int zb_metric_distance_batch(int device, uint32_t metric, uint64_t n, uint32_t dim, const float* a, const float* b,
+                             uint64_t* out_bits) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(metric <= 2 && dim >= 1 && ((a && b && out_bits) || !n), ZB_ERR_INVALID, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || !ndev) {
+        cudaGetLastError();
+        throw zb::Error(ZB_ERR_NO_DEVICE, "no CUDA device: libzebra_b200 has no CPU fallback");
+    }
+    ZB_CUDA(cudaSetDevice(device));
+    const int dimp = ((int)dim + 15) / 16 * 16;
+    DBuf<float> da, db;
+    DBuf<u64> dout;
+    pad_to_device(device, a, n, dim, dimp, da);
+    pad_to_device(device, b, n, dim, dimp, db);
+    dout.ensure(std::max<u64>(1, n));
+    launch_pair_metric((int)metric, da.p, db.p, n, dimp, dout.p, 0);
+    ZB_CUDA(cudaMemcpy(out_bits, dout.p, n * 8, cudaMemcpyDeviceToHost));
+    ZB_API_END
+}
+
+int zb_point_is_above_batch(int device, uint64_t n, uint32_t dim, const float* coef, const float* cst, const float* x,
+                            uint8_t* out) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(dim >= 1 && ((coef && cst && x && out) || !n), ZB_ERR_INVALID, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || !ndev) {
+        cudaGetLastError();
+        throw zb::Error(ZB_ERR_NO_DEVICE, "no CUDA device: libzebra_b200 has no CPU fallback");
+    }
+    ZB_CUDA(cudaSetDevice(device));
+    const int dimp = ((int)dim + 15) / 16 * 16;
+    DBuf<float> dc, dx, dk;
+    DBuf<u8> dout;
+    pad_to_device(device, coef, n, dim, dimp, dc);
+    pad_to_device(device, x, n, dim, dimp, dx);
+    dk.ensure(std::max<u64>(1, n));
+    dout.ensure(std::max<u64>(1, n));
+    if (n) ZB_CUDA(cudaMemcpy(dk.p, cst, n * 4, cudaMemcpyHostToDevice));
+    launch_pair_above(dc.p, dk.p, dx.p, n, dimp, dout.p, 0);
+    if (n) ZB_CUDA(cudaMemcpy(out, dout.p, n, cudaMemcpyDeviceToHost));
+    ZB_API_END
+}
+
+int zb_synth_fill_device(int device, float* d_out, uint64_t first_row, uint64_t row_stride, uint64_t n, uint32_t dim,
+                         uint64_t seed, uint32_t kind) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(d_out || !n, ZB_ERR_INVALID, "NULL argument");
+    ZB_CUDA(cudaSetDevice(device));
+    launch_synth(d_out, first_row, row_stride, n, dim, seed, kind, 0);
+    ZB_CUDA(cudaStreamSynchronize(0));
+    ZB_API_END
+}
+
+}  // extern "C"

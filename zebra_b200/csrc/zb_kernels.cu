@@ -1,0 +1,753 @@
+// zb_kernels.cu -- plan / score / select / merge / hash / build / mutation kernels (sm_100a).
+// The bandwidth-critical leaf-tile scan lives in zb_scan.cu; the kernels here are the general path that is
+// correct for every forest shape (deep trees with tiny leaves included) and the build/mutation machinery.
+#include <cub/device/device_scan.cuh>
+
+#include "zb_kernels.cuh"
+
+namespace zb {
+
+// =====================================================================================================
+// plan: the control flow of LSHIndex::tree_result (/root/reference/src/database/index/lsh.rs:290-348).
+// One quad per (query, tree) "walker".  The walk is distance independent (survey Q3): a leaf visited with
+// budget n returns min(live, n), so which leaves are visited, and with which budget, depends only on the
+// query's sign bits and on the live leaf sizes.  The walker emits (leaf, n) records; scoring happens later.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const float* __restrict__ queries, u32 nq,
+                                                        u32 top_k, u32 vpw, uint2* __restrict__ wvisits,
+                                                        u32* __restrict__ wcounts, u32* __restrict__ overflow) {
+    const u32 w = blockIdx.x * 32u + (threadIdx.x >> 2);
+    const int sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    const u32 nwalkers = nq * (u32)f.num_trees;
+    if (w >= nwalkers) return;
+    const u32 q = w / (u32)f.num_trees;
+    const u32 t = w - q * (u32)f.num_trees;
+    const float4* qv = reinterpret_cast<const float4*>(queries + (size_t)q * f.dimp);
+
+    int stack_node[ZB_MAX_DEPTH + 2];
+    int stack_n[ZB_MAX_DEPTH + 2];
+    int sp = 0;
+    int cur = f.roots[t];
+    int n = (int)top_k;
+    u32 nvis = 0;
+    for (;;) {
+        int4 nd = f.nodes[cur];
+        while (nd.x >= 0) {  // inner node: lsh.rs:333-338
+            float d = quad_dot(reinterpret_cast<const float4*>(f.coef + (size_t)nd.x * f.dimp), qv, f.chunks, sub, mask);
+            bool ab = above_from_dot(d, f.cst[nd.x]);
+            if (sp < ZB_MAX_DEPTH + 2) {
+                stack_node[sp] = ab ? nd.y : nd.z;  // backup
+                stack_n[sp] = n;
+            }
+            ++sp;
+            cur = ab ? nd.z : nd.y;  // main
+            nd = f.nodes[cur];
+        }
+        if (sp > ZB_MAX_DEPTH + 2) {  // cannot happen for forests accepted by the host (depth checked)
+            if (sub == 0) atomicExch(overflow, 2u);
+            break;
+        }
+        const int live = (int)f.leaf_plan[nd.w];
+        const int r = live < n ? live : n;  // lsh.rs:307 / :329
+        if (live > 0 && n > 0) {
+            if (nvis < vpw && sub == 0) wvisits[(size_t)w * vpw + nvis] = make_uint2((u32)nd.w, (u32)n);
+            ++nvis;
+        }
+        bool again = false;
+        while (sp > 0) {  // unwind: lsh.rs:340-345 (k < n -> backup with n - k, its result REPLACES k: Q1)
+            --sp;
+            const int nn = stack_n[sp];
+            if (r < nn) {
+                cur = stack_node[sp];
+                n = nn - r;
+                again = true;
+                break;
+            }
+        }
+        if (!again) break;
+    }
+    if (sub == 0) {
+        wcounts[w] = nvis < vpw ? nvis : vpw;
+        if (nvis > vpw) atomicMax(overflow, 1u);
+    }
+}
+
+void launch_plan(const ForestView& f, const float* d_queries, u32 nq, u32 top_k, u32 vpw, uint2* d_wvisits,
+                 u32* d_wcounts, u32* d_overflow, cudaStream_t s) {
+    u32 nwalkers = nq * (u32)f.num_trees;
+    if (!nwalkers) return;
+    plan_walk_kernel<<<(nwalkers + 31) / 32, 128, 0, s>>>(f, d_queries, nq, top_k, vpw, d_wvisits, d_wcounts, d_overflow);
+}
+
+__global__ void compact_visits_kernel(ForestView f, u32 nwalkers, u32 vpw, const uint2* __restrict__ wvisits,
+                                      const u32* __restrict__ wcounts, const u32* __restrict__ woff,
+                                      u32* __restrict__ vleaf, u32* __restrict__ vnp, u32* __restrict__ vq,
+                                      u64* __restrict__ pair_len, u32* __restrict__ ent_len) {
+    u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwalkers) return;
+    u32 c = wcounts[w], base = woff[w];
+    u32 q = w / (u32)f.num_trees;
+    for (u32 i = 0; i < c; ++i) {
+        uint2 v = wvisits[(size_t)w * vpw + i];
+        vleaf[base + i] = v.x;
+        vnp[base + i] = v.y;
+        vq[base + i] = q;
+        pair_len[base + i] = f.leaf_len[v.x];
+        u32 live = f.leaf_plan[v.x];
+        ent_len[base + i] = live < v.y ? live : v.y;
+    }
+}
+void launch_compact_visits(const ForestView& f, u32 nwalkers, u32 vpw, const uint2* d_wvisits, const u32* d_wcounts,
+                           const u32* d_woff, u32* d_vleaf, u32* d_vnp, u32* d_vq, u64* d_pair_len, u32* d_ent_len,
+                           cudaStream_t s) {
+    if (!nwalkers) return;
+    compact_visits_kernel<<<(nwalkers + 255) / 256, 256, 0, s>>>(f, nwalkers, vpw, d_wvisits, d_wcounts, d_woff, d_vleaf,
+                                                                 d_vnp, d_vq, d_pair_len, d_ent_len);
+}
+
+// =====================================================================================================
+// score: metric.distance(row, query) for every (visit, member) pair -- the generic (gather) path.
+// One quad per pair; 32 pairs per block.  distance.rs:19-49,:103-114 through the canonical order.
+// =====================================================================================================
+template <int METRIC>
+__global__ void __launch_bounds__(128) score_pairs_kernel(ForestView f, const float* __restrict__ queries, u32 nv,
+                                                          const u32* __restrict__ vleaf, const u32* __restrict__ vq,
+                                                          const u64* __restrict__ pair_off, u64 total_pairs,
+                                                          u64* __restrict__ pair_key) {
+    __shared__ u32 s_v0;
+    const u64 p0 = (u64)blockIdx.x * 32ull;
+    if (threadIdx.x == 0) {  // visit containing pair p0: last v with pair_off[v] <= p0
+        u32 lo = 0, hi = nv;
+        while (hi - lo > 1) {
+            u32 mid = (lo + hi) >> 1;
+            if (pair_off[mid] <= p0) lo = mid; else hi = mid;
+        }
+        s_v0 = lo;
+    }
+    __syncthreads();
+    const u64 p = p0 + (threadIdx.x >> 2);
+    if (p >= total_pairs) return;
+    const int sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    u32 v = s_v0;
+    while (pair_off[v + 1] <= p) ++v;
+    const u32 leaf = vleaf[v];
+    const u32 slot = f.members[f.leaf_off[leaf] + (long long)(p - pair_off[v])];
+    if (tomb_test(f.tomb, slot)) {
+        if (sub == 0) pair_key[p] = ZB_SENTINEL;
+        return;
+    }
+    const float4* a = reinterpret_cast<const float4*>(f.rows + (size_t)slot * f.dimp);
+    const float4* b = reinterpret_cast<const float4*>(queries + (size_t)vq[v] * f.dimp);
+    u64 key;
+    if (METRIC == 0) {
+        float4 ab = make_float4(0.f, 0.f, 0.f, 0.f), a2 = ab, b2 = ab;
+        for (int c = 0; c < f.chunks; ++c) {
+            float4 av = __ldg(a + c * 4 + sub), bv = __ldg(b + c * 4 + sub);
+            fma4(ab, av, bv);
+            fma4(a2, av, av);
+            fma4(b2, bv, bv);
+        }
+        key = cos_bits(quad_reduce16(ab, mask), quad_reduce16(a2, mask), quad_reduce16(b2, mask));
+    } else {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int c = 0;
+        for (; c + 4 <= f.chunks; c += 4) {
+            float4 a0 = __ldg(a + (c + 0) * 4 + sub), a1 = __ldg(a + (c + 1) * 4 + sub);
+            float4 a2 = __ldg(a + (c + 2) * 4 + sub), a3 = __ldg(a + (c + 3) * 4 + sub);
+            float4 b0 = __ldg(b + (c + 0) * 4 + sub), b1 = __ldg(b + (c + 1) * 4 + sub);
+            float4 b2 = __ldg(b + (c + 2) * 4 + sub), b3 = __ldg(b + (c + 3) * 4 + sub);
+            l2acc4(acc, a0, b0);
+            l2acc4(acc, a1, b1);
+            l2acc4(acc, a2, b2);
+            l2acc4(acc, a3, b3);
+        }
+        for (; c < f.chunks; ++c) l2acc4(acc, __ldg(a + c * 4 + sub), __ldg(b + c * 4 + sub));
+        float sum = quad_reduce16(acc, mask);
+        key = METRIC == 1 ? l2sq_bits(sum) : l2_bits(sum);
+    }
+    if (sub == 0) pair_key[p] = key;
+}
+
+void launch_score_pairs(const ForestView& f, int metric, const float* d_queries, u32 nv, const u32* d_vleaf,
+                        const u32* d_vq, const u64* d_pair_off, u64 total_pairs, u64* d_pair_key, cudaStream_t s) {
+    if (!total_pairs) return;
+    u32 blocks = (u32)((total_pairs + 31) / 32);
+    if (metric == 0)
+        score_pairs_kernel<0><<<blocks, 128, 0, s>>>(f, d_queries, nv, d_vleaf, d_vq, d_pair_off, total_pairs, d_pair_key);
+    else if (metric == 1)
+        score_pairs_kernel<1><<<blocks, 128, 0, s>>>(f, d_queries, nv, d_vleaf, d_vq, d_pair_off, total_pairs, d_pair_key);
+    else
+        score_pairs_kernel<2><<<blocks, 128, 0, s>>>(f, d_queries, nv, d_vleaf, d_vq, d_pair_off, total_pairs, d_pair_key);
+}
+
+// =====================================================================================================
+// block-level streaming top-k with optional dedup: bitonic sort of (kept + chunk) entries in shared
+// memory, keep the first k distinct.  Order = (distance bits as u64, ordinal): lsh.rs:318,:561 + D3.
+// =====================================================================================================
+#define TOPK_THREADS 128
+
+__device__ __forceinline__ void bitonic_sort_block(Entry* s, int P) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += TOPK_THREADS) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    Entry a = s[i], b = s[ixj];
+                    bool up = (i & k) == 0;
+                    if (entry_less(b, a) == up) {
+                        s[i] = b;
+                        s[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < TOPK_THREADS / 32; ++i) {
+        int wv = s_warp[i];
+        if (i < wid) base += wv;
+        tot += wv;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + x - v;
+}
+
+// buf: pmax entries, keep: k entries.  Returns the number of kept entries (sorted, distinct) in keep[0..).
+template <class Loader>
+__device__ int segment_topk(Entry* buf, Entry* keep, int* s_warp, const Loader& ld, long long len, int k, int pmax) {
+    int kept = 0;
+    const int ch = pmax - k;
+    for (long long base = 0; base < len; base += ch) {
+        const int c = (int)((len - base) < (long long)ch ? (len - base) : (long long)ch);
+        const int total = kept + c;
+        int P = 32;
+        while (P < total) P <<= 1;
+        for (int i = threadIdx.x; i < P; i += TOPK_THREADS) {
+            if (i < kept) buf[i] = keep[i];
+            else if (i < total) buf[i] = ld(base + (i - kept));
+            else buf[i] = Entry{ZB_SENTINEL, ZB_SENTINEL};
+        }
+        __syncthreads();
+        bitonic_sort_block(buf, P);
+        int running = 0;
+        for (int r0 = 0; r0 < P && running < k; r0 += TOPK_THREADS) {
+            const int i = r0 + threadIdx.x;
+            int flag = 0;
+            Entry e = Entry{ZB_SENTINEL, ZB_SENTINEL};
+            if (i < P) {
+                e = buf[i];
+                flag = (e.ord != ZB_SENTINEL) && (i == 0 || buf[i - 1].ord != e.ord || buf[i - 1].key != e.key);
+            }
+            int tot;
+            int pos = running + block_exclusive_scan(flag, s_warp, &tot);
+            if (flag && pos < k) keep[pos] = e;
+            running += tot;
+        }
+        kept = running < k ? running : k;
+        __syncthreads();
+    }
+    return kept;
+}
+
+struct VisitLoader {
+    const u32* members;
+    const u64* keys;
+    const u64* ord;
+    __device__ Entry operator()(long long i) const {
+        u64 key = keys[i];
+        if (key == ZB_SENTINEL) return Entry{ZB_SENTINEL, ZB_SENTINEL};
+        return Entry{key, ord[members[i]]};
+    }
+};
+
+// per-visit top-n' (lsh.rs:301-331): a leaf with live < n' contributes everything, otherwise its n' nearest.
+__global__ void __launch_bounds__(TOPK_THREADS) select_visits_kernel(ForestView f, u32 nv, const u32* __restrict__ vleaf,
+                                                                     const u32* __restrict__ vnp,
+                                                                     const u64* __restrict__ pair_off,
+                                                                     const u64* __restrict__ pair_key,
+                                                                     const u32* __restrict__ ent_off,
+                                                                     Entry* __restrict__ entries,
+                                                                     const u8* __restrict__ vdone, int pmax, int kmax) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Entry* buf = reinterpret_cast<Entry*>(smem);
+    Entry* keep = buf + pmax;
+    int* s_warp = reinterpret_cast<int*>(keep + kmax);
+    const u32 v = blockIdx.x;
+    if (v >= nv) return;
+    if (vdone && vdone[v]) return;
+    const u32 leaf = vleaf[v];
+    const u32 slots = ent_off[v + 1] - ent_off[v];
+    VisitLoader ld{f.members + f.leaf_off[leaf], pair_key + pair_off[v], f.ord};
+    const int k = (int)vnp[v];
+    int kept = segment_topk(buf, keep, s_warp, ld, (long long)f.leaf_len[leaf], k, pmax);
+    Entry* out = entries + ent_off[v];
+    for (u32 i = threadIdx.x; i < slots; i += TOPK_THREADS) out[i] = (int)i < kept ? keep[i] : Entry{ZB_SENTINEL, ZB_SENTINEL};
+}
+
+static inline int topk_pmax(u32 top_k) {
+    int p = 1024;
+    while (p < (int)(2 * top_k)) p <<= 1;
+    return p;
+}
+static inline size_t topk_smem(int pmax, int kmax) { return (size_t)(pmax + kmax) * sizeof(Entry) + 64; }
+
+template <class K>
+static void set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+void launch_select_visits(const ForestView& f, u32 nv, const u32* d_vleaf, const u32* d_vnp, const u64* d_pair_off,
+                          const u64* d_pair_key, const u32* d_ent_off, Entry* d_entries, const u8* d_vdone, u32 top_k,
+                          cudaStream_t s) {
+    if (!nv) return;
+    int pmax = topk_pmax(top_k), kmax = (int)top_k;
+    size_t smem = topk_smem(pmax, kmax);
+    set_smem(select_visits_kernel, smem);
+    select_visits_kernel<<<nv, TOPK_THREADS, smem, s>>>(f, nv, d_vleaf, d_vnp, d_pair_off, d_pair_key, d_ent_off,
+                                                       d_entries, d_vdone, pmax, kmax);
+}
+
+// Sharded search: per-visit merge of the G ranks' local top-n' lists into the global top-n' (survey 8e ii).
+struct RankLoader {
+    const Entry* gathered;
+    u32 total_slots, base, slots;
+    __device__ Entry operator()(long long i) const {
+        u32 r = (u32)(i / slots), j = (u32)(i % slots);
+        return gathered[(size_t)r * total_slots + base + j];
+    }
+};
+__global__ void __launch_bounds__(TOPK_THREADS) merge_ranks_kernel(u32 nv, const u32* __restrict__ ent_off, u32 total_slots,
+                                                                   u32 nranks, const Entry* __restrict__ gathered,
+                                                                   Entry* __restrict__ entries, int pmax, int kmax) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Entry* buf = reinterpret_cast<Entry*>(smem);
+    Entry* keep = buf + pmax;
+    int* s_warp = reinterpret_cast<int*>(keep + kmax);
+    const u32 v = blockIdx.x;
+    if (v >= nv) return;
+    const u32 base = ent_off[v], slots = ent_off[v + 1] - base;
+    if (!slots) return;
+    RankLoader ld{gathered, total_slots, base, slots};
+    int kept = segment_topk(buf, keep, s_warp, ld, (long long)slots * nranks, (int)slots, pmax);
+    for (u32 i = threadIdx.x; i < slots; i += TOPK_THREADS)
+        entries[base + i] = (int)i < kept ? keep[i] : Entry{ZB_SENTINEL, ZB_SENTINEL};
+}
+void launch_merge_ranks(u32 nv, const u32* d_ent_off, u32 total_slots, u32 nranks, const Entry* d_gathered,
+                        Entry* d_entries, u32 top_k, cudaStream_t s) {
+    if (!nv) return;
+    int pmax = topk_pmax(top_k), kmax = (int)top_k;
+    size_t smem = topk_smem(pmax, kmax);
+    set_smem(merge_ranks_kernel, smem);
+    merge_ranks_kernel<<<nv, TOPK_THREADS, smem, s>>>(nv, d_ent_off, total_slots, nranks, d_gathered, d_entries, pmax, kmax);
+}
+
+// Union over trees and visits, dedup (DashSet, lsh.rs:550), sort ascending, take top_k (lsh.rs:561-564).
+struct PlainLoader {
+    const Entry* e;
+    __device__ Entry operator()(long long i) const { return e[i]; }
+};
+__global__ void __launch_bounds__(TOPK_THREADS) merge_queries_kernel(u32 nq, u32 num_trees, const u32* __restrict__ woff,
+                                                                     const u32* __restrict__ ent_off,
+                                                                     const Entry* __restrict__ entries, u32 top_k,
+                                                                     u64* __restrict__ out_ord, u64* __restrict__ out_bits,
+                                                                     u32* __restrict__ out_counts, int pmax, int kmax) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Entry* buf = reinterpret_cast<Entry*>(smem);
+    Entry* keep = buf + pmax;
+    int* s_warp = reinterpret_cast<int*>(keep + kmax);
+    const u32 q = blockIdx.x;
+    if (q >= nq) return;
+    const u32 v0 = woff[(size_t)q * num_trees], v1 = woff[(size_t)(q + 1) * num_trees];
+    const u32 e0 = ent_off[v0], e1 = ent_off[v1];
+    PlainLoader ld{entries + e0};
+    int kept = segment_topk(buf, keep, s_warp, ld, (long long)(e1 - e0), (int)top_k, pmax);
+    for (u32 i = threadIdx.x; i < top_k; i += TOPK_THREADS) {
+        bool ok = (int)i < kept;
+        out_ord[(size_t)q * top_k + i] = ok ? keep[i].ord : ZB_SENTINEL;
+        out_bits[(size_t)q * top_k + i] = ok ? keep[i].key : ZB_SENTINEL;
+    }
+    if (threadIdx.x == 0) out_counts[q] = (u32)kept;
+}
+void launch_merge_queries(u32 nq, u32 num_trees, const u32* d_woff, const u32* d_ent_off, const Entry* d_entries,
+                          u32 top_k, u64* d_out_ord, u64* d_out_bits, u32* d_out_counts, cudaStream_t s) {
+    if (!nq) return;
+    int pmax = topk_pmax(top_k), kmax = (int)(top_k ? top_k : 1);
+    size_t smem = topk_smem(pmax, kmax);
+    set_smem(merge_queries_kernel, smem);
+    merge_queries_kernel<<<nq, TOPK_THREADS, smem, s>>>(nq, num_trees, d_woff, d_ent_off, d_entries, top_k, d_out_ord,
+                                                       d_out_bits, d_out_counts, pmax, kmax);
+}
+
+// =====================================================================================================
+// hash: root-to-leaf descent by Hyperplane::point_is_above (lsh.rs:39-43 along :350-366).  One quad per
+// (row, tree); the sign bits are the bucket key (MSB = root), the leaf is the bucket.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) hash_kernel(ForestView f, const float* __restrict__ rows, u64 n,
+                                                   u64* __restrict__ keys, u32* __restrict__ depths,
+                                                   int* __restrict__ leaves) {
+    const u64 w = (u64)blockIdx.x * 32ull + (threadIdx.x >> 2);
+    const int sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    if (w >= n * (u64)f.num_trees) return;
+    const u64 r = w / (u64)f.num_trees;
+    const int t = (int)(w - r * (u64)f.num_trees);
+    const float4* x = reinterpret_cast<const float4*>(rows + (size_t)r * f.dimp);
+    int cur = f.roots[t];
+    int4 nd = f.nodes[cur];
+    u64 key = 0;
+    u32 depth = 0;
+    while (nd.x >= 0) {
+        float d = quad_dot(reinterpret_cast<const float4*>(f.coef + (size_t)nd.x * f.dimp), x, f.chunks, sub, mask);
+        bool ab = above_from_dot(d, f.cst[nd.x]);
+        key = (key << 1) | (ab ? 1ull : 0ull);
+        ++depth;
+        cur = ab ? nd.z : nd.y;
+        nd = f.nodes[cur];
+    }
+    if (sub == 0) {
+        if (keys) keys[w] = key;
+        if (depths) depths[w] = depth;
+        if (leaves) leaves[w] = nd.w;
+    }
+}
+void launch_hash(const ForestView& f, const float* d_rows, u64 n, u64* d_keys, u32* d_depths, int* d_leaves,
+                 cudaStream_t s) {
+    u64 nw = n * (u64)f.num_trees;
+    if (!nw) return;
+    hash_kernel<<<(u32)((nw + 31) / 32), 128, 0, s>>>(f, d_rows, n, d_keys, d_depths, d_leaves);
+}
+
+// =====================================================================================================
+// build (lsh.rs:192-267), level synchronous.  The host keeps the list of nodes under construction
+// ("segments" of a work array of slots); per level:
+//   pick      two member rows per segment by seeded min-hash (D2)                    phases 0,1,2
+//   planes    coef = b - a, mid = (a+b)/2, constant = -(f32)dot(coef, mid)           lsh.rs:222-225
+//   classify  point_is_above for every member (the projection hot loop)              lsh.rs:236-241
+//   scatter   stable partition: below first (left child), above after (right child)
+// =====================================================================================================
+// phase 0: minh[seg] = min hash (63-bit);  phase 1: minord[seg] = min ordinal among hash == minh;
+// phase 2: slot[seg] = slot of the member whose ordinal == minord.   exclude[seg] (optional) is skipped.
+__global__ void __launch_bounds__(64) pick_kernel(int phase, const Tile* __restrict__ tiles, const SegDesc* __restrict__ segs,
+                                                  const u32* __restrict__ work, const u64* __restrict__ ord,
+                                                  const u64* __restrict__ exclude, u64* __restrict__ minh,
+                                                  u64* __restrict__ minord, int* __restrict__ slot_out) {
+    const Tile tl = tiles[blockIdx.x];
+    if (threadIdx.x >= tl.count) return;
+    const SegDesc sg = segs[tl.seg];
+    const u32 slot = work[tl.start + threadIdx.x];
+    const u64 o = ord[slot];
+    if (exclude && exclude[tl.seg] == o) return;
+    const u64 h = pick_hash(sg.key, (int)sg.attempt, o) >> 1;
+    if (phase == 0) atomicMin(&minh[tl.seg], h);
+    else if (phase == 1) { if (h == minh[tl.seg]) atomicMin(&minord[tl.seg], o); }
+    else { if (o == minord[tl.seg]) slot_out[tl.seg] = (int)slot; }
+}
+void launch_pick(int phase, const Tile* d_tiles, u32 ntiles, const SegDesc* d_segs, const u32* d_work, const u64* d_ord,
+                 const u64* d_exclude, u64* d_minh, u64* d_minord, int* d_slot, cudaStream_t s) {
+    if (!ntiles) return;
+    pick_kernel<<<ntiles, 64, 0, s>>>(phase, d_tiles, d_segs, d_work, d_ord, d_exclude, d_minh, d_minord, d_slot);
+}
+
+// pair_rows[seg][0] = row a, [seg][1] = row b (zeros when this shard does not own the row: the int32
+// allreduce-sum over shards then reconstructs the exact bit patterns).
+__global__ void fetch_pair_rows_kernel(u32 nsegs, const int* __restrict__ slot_a, const int* __restrict__ slot_b,
+                                       const float* __restrict__ rows, int dimp, float* __restrict__ pair_rows) {
+    const u32 sgi = blockIdx.x;
+    for (int which = 0; which < 2; ++which) {
+        int slot = which ? slot_b[sgi] : slot_a[sgi];
+        float* dst = pair_rows + ((size_t)sgi * 2 + which) * dimp;
+        for (int i = threadIdx.x; i < dimp; i += blockDim.x) dst[i] = slot >= 0 ? rows[(size_t)slot * dimp + i] : 0.0f;
+    }
+}
+void launch_fetch_pair_rows(const SegDesc* d_segs, u32 nsegs, const int* d_slot_a, const int* d_slot_b,
+                            const float* d_rows, int dimp, float* d_pair_rows, cudaStream_t s) {
+    if (!nsegs) return;
+    fetch_pair_rows_kernel<<<nsegs, 128, 0, s>>>(nsegs, d_slot_a, d_slot_b, d_rows, dimp, d_pair_rows);
+}
+
+// lsh.rs:222-225 (+ subtract/average :174-190): one quad per segment.
+__global__ void __launch_bounds__(128) make_planes_kernel(const SegDesc* __restrict__ segs, u32 nsegs,
+                                                          const float* __restrict__ pair_rows, int dimp,
+                                                          float* __restrict__ coef, float* __restrict__ cst) {
+    const u32 sgi = blockIdx.x * 32u + (threadIdx.x >> 2);
+    const int sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    if (sgi >= nsegs) return;
+    const float4* a = reinterpret_cast<const float4*>(pair_rows + ((size_t)sgi * 2 + 0) * dimp);
+    const float4* b = reinterpret_cast<const float4*>(pair_rows + ((size_t)sgi * 2 + 1) * dimp);
+    const u32 plane = segs[sgi].plane;
+    float4* out = reinterpret_cast<float4*>(coef + (size_t)plane * dimp);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int chunks = dimp / 16;
+    for (int c = 0; c < chunks; ++c) {
+        float4 av = a[c * 4 + sub], bv = b[c * 4 + sub];
+        float4 cf = make_float4(__fsub_rn(bv.x, av.x), __fsub_rn(bv.y, av.y), __fsub_rn(bv.z, av.z), __fsub_rn(bv.w, av.w));
+        float4 mid = make_float4(__fmul_rn(__fadd_rn(av.x, bv.x), 0.5f), __fmul_rn(__fadd_rn(av.y, bv.y), 0.5f),
+                                 __fmul_rn(__fadd_rn(av.z, bv.z), 0.5f), __fmul_rn(__fadd_rn(av.w, bv.w), 0.5f));
+        out[c * 4 + sub] = cf;
+        fma4(acc, cf, mid);
+    }
+    float d = quad_reduce16(acc, mask);
+    if (sub == 0) cst[plane] = -d;
+}
+void launch_make_planes(const SegDesc* d_segs, u32 nsegs, const float* d_pair_rows, int dimp, float* d_coef,
+                        float* d_cst, cudaStream_t s) {
+    if (!nsegs) return;
+    make_planes_kernel<<<(nsegs + 31) / 32, 128, 0, s>>>(d_segs, nsegs, d_pair_rows, dimp, d_coef, d_cst);
+}
+
+// flags[pos] = point_is_above(plane of the segment, row at pos).  Tile = 64 positions, one quad each.
+__global__ void __launch_bounds__(256) classify_kernel(const Tile* __restrict__ tiles, const SegDesc* __restrict__ segs,
+                                                       const u32* __restrict__ work, const float* __restrict__ rows,
+                                                       const float* __restrict__ coef, const float* __restrict__ cst,
+                                                       int dimp, u32* __restrict__ flags) {
+    const Tile tl = tiles[blockIdx.x];
+    const u32 i = threadIdx.x >> 2;
+    if (i >= tl.count) return;
+    const int sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    const u32 plane = segs[tl.seg].plane;
+    const u32 slot = work[tl.start + i];
+    float d = quad_dot(reinterpret_cast<const float4*>(coef + (size_t)plane * dimp),
+                       reinterpret_cast<const float4*>(rows + (size_t)slot * dimp), dimp / 16, sub, mask);
+    if (sub == 0) flags[tl.start + i] = above_from_dot(d, cst[plane]) ? 1u : 0u;
+}
+void launch_classify(const Tile* d_tiles, u32 ntiles, const SegDesc* d_segs, const u32* d_work, const float* d_rows,
+                     const float* d_coef, const float* d_cst, int dimp, u32* d_flags, cudaStream_t s) {
+    if (!ntiles) return;
+    classify_kernel<<<ntiles, 256, 0, s>>>(d_tiles, d_segs, d_work, d_rows, d_coef, d_cst, dimp, d_flags);
+}
+
+__global__ void seg_above_kernel(const SegDesc* __restrict__ segs, u32 nsegs, const u32* __restrict__ scan,
+                                 u32* __restrict__ above) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsegs) return;
+    above[i] = scan[segs[i].off + segs[i].len] - scan[segs[i].off];
+}
+void launch_seg_above(const SegDesc* d_segs, u32 nsegs, const u32* d_scan, u32* d_above, cudaStream_t s) {
+    if (!nsegs) return;
+    seg_above_kernel<<<(nsegs + 255) / 256, 256, 0, s>>>(d_segs, nsegs, d_scan, d_above);
+}
+
+__global__ void __launch_bounds__(64) scatter_kernel(const Tile* __restrict__ tiles, const SegDesc* __restrict__ segs,
+                                                     const u32* __restrict__ work_in, const u32* __restrict__ flags,
+                                                     const u32* __restrict__ scan, u32* __restrict__ work_out) {
+    const Tile tl = tiles[blockIdx.x];
+    if (threadIdx.x >= tl.count) return;
+    const SegDesc sg = segs[tl.seg];
+    const long long pos = tl.start + threadIdx.x;
+    const u32 above_rank = scan[pos] - scan[sg.off];
+    const u32 n_above = scan[sg.off + sg.len] - scan[sg.off];
+    const u32 n_below = sg.len - n_above;
+    const u32 local = (u32)(pos - sg.off);
+    const long long dst = flags[pos] ? sg.off + n_below + above_rank : sg.off + (local - above_rank);
+    work_out[dst] = work_in[pos];
+}
+void launch_scatter(const Tile* d_tiles, u32 ntiles, const SegDesc* d_segs, const u32* d_work_in, const u32* d_flags,
+                    const u32* d_scan, u32* d_work_out, cudaStream_t s) {
+    if (!ntiles) return;
+    scatter_kernel<<<ntiles, 64, 0, s>>>(d_tiles, d_segs, d_work_in, d_flags, d_scan, d_work_out);
+}
+
+// slot_leaf[slot] = leaf, for the members of the tiled leaves of ONE tree.
+__global__ void __launch_bounds__(64) assign_leaf_kernel(const Tile* __restrict__ tiles, const u32* __restrict__ members,
+                                                         u32* __restrict__ slot_leaf) {
+    const Tile tl = tiles[blockIdx.x];
+    if (threadIdx.x >= tl.count) return;
+    slot_leaf[members[tl.start + threadIdx.x]] = tl.seg;
+}
+void launch_assign_leaf(const Tile* d_tiles, u32 ntiles, const u32* d_members, u32* d_slot_leaf_tree, cudaStream_t s) {
+    if (!ntiles) return;
+    assign_leaf_kernel<<<ntiles, 64, 0, s>>>(d_tiles, d_members, d_slot_leaf_tree);
+}
+
+// =====================================================================================================
+// mutation
+// =====================================================================================================
+// LSHIndex::remove under D1: set the tombstone bit, take the row out of every tree's live leaf count.
+__global__ void tombstone_kernel(const u32* __restrict__ slots, u32 n, u32* __restrict__ tomb,
+                                 const u32* __restrict__ slot_leaf, u64 slot_stride, int num_trees,
+                                 u32* __restrict__ leaf_live, u8* __restrict__ removed) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 slot = slots[i];
+    if (slot == 0xFFFFFFFFu) { removed[i] = 0; return; }
+    u32 bit = 1u << (slot & 31);
+    u32 old = atomicOr(&tomb[slot >> 5], bit);
+    if (old & bit) { removed[i] = 0; return; }
+    removed[i] = 1;
+    for (int t = 0; t < num_trees; ++t) atomicSub(&leaf_live[slot_leaf[(u64)t * slot_stride + slot]], 1u);
+}
+void launch_tombstone(const u32* d_slots, u32 n, u32* d_tomb, const u32* d_slot_leaf, u64 slot_stride, int num_trees,
+                      u32* d_leaf_live, u8* d_removed, cudaStream_t s) {
+    if (!n) return;
+    tombstone_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_slots, n, d_tomb, d_slot_leaf, slot_stride, num_trees, d_leaf_live,
+                                                     d_removed);
+}
+
+__global__ void pad_rows_kernel(const float* __restrict__ src, u64 n, int dim, int dimp, float* __restrict__ dst) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * (u64)dimp) return;
+    u64 r = i / dimp;
+    int c = (int)(i - r * dimp);
+    dst[i] = c < dim ? src[r * dim + c] : 0.0f;
+}
+void launch_pad_rows(const float* d_src, u64 n, int dim, int dimp, float* d_dst, cudaStream_t s) {
+    u64 tot = n * (u64)dimp;
+    if (!tot) return;
+    pad_rows_kernel<<<(u32)((tot + 255) / 256), 256, 0, s>>>(d_src, n, dim, dimp, d_dst);
+}
+
+__global__ void fill_u64_kernel(u64* d, u64 n, u64 v) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = v;
+}
+void launch_fill_u64(u64* d, u64 n, u64 v, cudaStream_t s) {
+    if (!n) return;
+    fill_u64_kernel<<<(u32)((n + 255) / 256), 256, 0, s>>>(d, n, v);
+}
+__global__ void iota_ord_kernel(u64* d, u64 n, u64 first, u64 stride) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = first + i * stride;
+}
+void launch_iota_ord(u64* d, u64 n, u64 first, u64 stride, cudaStream_t s) {
+    if (!n) return;
+    iota_ord_kernel<<<(u32)((n + 255) / 256), 256, 0, s>>>(d, n, first, stride);
+}
+
+// =====================================================================================================
+// synthetic data: Philox-4x32-10, counter = (row_lo, row_hi, col/4, stream), key = seed;
+// word -> f32 exactly: x = float((int32)w >> 8) * 2^-23 in [-1, 1).  No transcendental functions.
+// =====================================================================================================
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const u32 M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        u32 hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        u32 hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float word_to_unit(u32 w) { return (float)((int)w >> 8) * 1.1920928955078125e-07f; }
+
+__global__ void synth_kernel(float* __restrict__ out, u64 first_row, u64 row_stride, u64 n, u32 dim, u64 seed, u32 kind) {
+    const u32 quads = (dim + 3) / 4;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * (u64)quads) return;
+    u64 ri = i / quads;
+    u32 cq = (u32)(i - ri * quads);
+    u64 row = first_row + ri * row_stride;
+    uint2 key = make_uint2((u32)seed, (u32)(seed >> 32));
+    uint4 w = philox4x32_10(make_uint4((u32)row, (u32)(row >> 32), cq, 0u), key);
+    float v[4] = {word_to_unit(w.x), word_to_unit(w.y), word_to_unit(w.z), word_to_unit(w.w)};
+    if (kind == 1) {
+        u64 crow = row % 4096ull;
+        uint4 c = philox4x32_10(make_uint4((u32)crow, 0u, cq, 1u), key);
+        float cv[4] = {word_to_unit(c.x), word_to_unit(c.y), word_to_unit(c.z), word_to_unit(c.w)};
+        for (int j = 0; j < 4; ++j) v[j] = __fmaf_rn(0.25f, v[j], cv[j]);
+    }
+    for (int j = 0; j < 4; ++j) {
+        u32 col = cq * 4 + j;
+        if (col < dim) out[ri * dim + col] = v[j];
+    }
+}
+void launch_synth(float* d_out, u64 first_row, u64 row_stride, u64 n, u32 dim, u64 seed, u32 kind, cudaStream_t s) {
+    u64 tot = n * (u64)((dim + 3) / 4);
+    if (!tot) return;
+    synth_kernel<<<(u32)((tot + 255) / 256), 256, 0, s>>>(d_out, first_row, row_stride, n, dim, seed, kind);
+}
+
+
+// =====================================================================================================
+// element-wise entry points of the metric trait and of point_is_above (arithmetic parity tests; the
+// Metric::distance of distance.rs:19-49,:103-114 and Hyperplane::point_is_above of lsh.rs:39-43 for
+// n independent pairs).  One quad per pair.
+// =====================================================================================================
+template <int METRIC>
+__global__ void __launch_bounds__(128) pair_metric_kernel(const float* __restrict__ a_, const float* __restrict__ b_, u64 n,
+                                                          int dimp, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * 32ull + (threadIdx.x >> 2);
+    if (i >= n) return;
+    const int sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    const float4* a = reinterpret_cast<const float4*>(a_ + i * dimp);
+    const float4* b = reinterpret_cast<const float4*>(b_ + i * dimp);
+    const int chunks = dimp / 16;
+    u64 key;
+    if (METRIC == 0) {
+        float4 ab = make_float4(0.f, 0.f, 0.f, 0.f), a2 = ab, b2 = ab;
+        for (int c = 0; c < chunks; ++c) {
+            float4 av = a[c * 4 + sub], bv = b[c * 4 + sub];
+            fma4(ab, av, bv);
+            fma4(a2, av, av);
+            fma4(b2, bv, bv);
+        }
+        key = cos_bits(quad_reduce16(ab, mask), quad_reduce16(a2, mask), quad_reduce16(b2, mask));
+    } else {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < chunks; ++c) l2acc4(acc, a[c * 4 + sub], b[c * 4 + sub]);
+        float sum = quad_reduce16(acc, mask);
+        key = METRIC == 1 ? l2sq_bits(sum) : l2_bits(sum);
+    }
+    if (sub == 0) out[i] = key;
+}
+void launch_pair_metric(int metric, const float* d_a, const float* d_b, u64 n, int dimp, u64* d_out, cudaStream_t s) {
+    if (!n) return;
+    u32 blocks = (u32)((n + 31) / 32);
+    if (metric == 0) pair_metric_kernel<0><<<blocks, 128, 0, s>>>(d_a, d_b, n, dimp, d_out);
+    else if (metric == 1) pair_metric_kernel<1><<<blocks, 128, 0, s>>>(d_a, d_b, n, dimp, d_out);
+    else pair_metric_kernel<2><<<blocks, 128, 0, s>>>(d_a, d_b, n, dimp, d_out);
+}
+__global__ void __launch_bounds__(128) pair_above_kernel(const float* __restrict__ coef, const float* __restrict__ cst,
+                                                         const float* __restrict__ x, u64 n, int dimp, u8* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * 32ull + (threadIdx.x >> 2);
+    if (i >= n) return;
+    const int sub = threadIdx.x & 3;
+    float d = quad_dot(reinterpret_cast<const float4*>(coef + i * dimp), reinterpret_cast<const float4*>(x + i * dimp),
+                       dimp / 16, sub, quad_mask());
+    if (sub == 0) out[i] = above_from_dot(d, cst[i]) ? 1 : 0;
+}
+void launch_pair_above(const float* d_coef, const float* d_cst, const float* d_x, u64 n, int dimp, u8* d_out, cudaStream_t s) {
+    if (!n) return;
+    pair_above_kernel<<<(u32)((n + 31) / 32), 128, 0, s>>>(d_coef, d_cst, d_x, n, dimp, d_out);
+}
+
+// =====================================================================================================
+// cub scans
+// =====================================================================================================
+size_t scan_temp_bytes(size_t n) {
+    size_t b32 = 0, b64 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b32, (const u32*)nullptr, (u32*)nullptr, (long long)n);
+    cub::DeviceScan::ExclusiveSum(nullptr, b64, (const u64*)nullptr, (u64*)nullptr, (long long)n);
+    return (b32 > b64 ? b32 : b64) + 256;
+}
+void exclusive_scan_u32(void* d_temp, size_t temp_bytes, const u32* d_in, u32* d_out, size_t n, cudaStream_t s) {
+    if (!n) return;
+    cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_in, d_out, (long long)n, s);
+}
+void exclusive_scan_u64(void* d_temp, size_t temp_bytes, const u64* d_in, u64* d_out, size_t n, cudaStream_t s) {
+    if (!n) return;
+    cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_in, d_out, (long long)n, s);
+}
+
+}  // namespace zb

@@ -1,0 +1,96 @@
+// zb_nccl.cpp -- NCCL through dlopen.  The library carries no link-time NCCL dependency: a process that
+// already loaded NCCL (e.g. through torch) shares that copy, otherwise libnccl.so.2 is loaded on first use.
+#include <dlfcn.h>
+
+#include "zb_host.h"
+
+namespace zb {
+
+namespace {
+struct ncclUniqueId_ {
+    char internal[128];
+};
+typedef int (*fn_get_unique_id)(ncclUniqueId_*);
+typedef int (*fn_comm_init_rank)(void**, int, ncclUniqueId_, int);
+typedef int (*fn_comm_destroy)(void*);
+typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*fn_get_error_string)(int);
+
+struct Api {
+    void* handle = nullptr;
+    fn_get_unique_id get_unique_id = nullptr;
+    fn_comm_init_rank comm_init_rank = nullptr;
+    fn_comm_destroy comm_destroy = nullptr;
+    fn_all_reduce all_reduce = nullptr;
+    fn_all_gather all_gather = nullptr;
+    fn_get_error_string get_error_string = nullptr;
+};
+
+Api& api() {
+    static Api a;
+    if (a.handle) return a;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        a.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (a.handle) break;
+    }
+    if (!a.handle) {
+        // symbols may already be global in the process even if the soname differs
+        if (dlsym(RTLD_DEFAULT, "ncclCommInitRank")) a.handle = dlopen(nullptr, RTLD_NOW);
+    }
+    for (const char* n : names) {
+        if (a.handle) break;
+        a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    }
+    ZB_REQUIRE(a.handle, ZB_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+    a.get_unique_id = (fn_get_unique_id)dlsym(a.handle, "ncclGetUniqueId");
+    a.comm_init_rank = (fn_comm_init_rank)dlsym(a.handle, "ncclCommInitRank");
+    a.comm_destroy = (fn_comm_destroy)dlsym(a.handle, "ncclCommDestroy");
+    a.all_reduce = (fn_all_reduce)dlsym(a.handle, "ncclAllReduce");
+    a.all_gather = (fn_all_gather)dlsym(a.handle, "ncclAllGather");
+    a.get_error_string = (fn_get_error_string)dlsym(a.handle, "ncclGetErrorString");
+    ZB_REQUIRE(a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.all_reduce && a.all_gather, ZB_ERR_COMM,
+               "libnccl is missing required symbols");
+    return a;
+}
+
+void check(int rc, const char* what) {
+    if (rc != 0) {
+        const char* msg = api().get_error_string ? api().get_error_string(rc) : "?";
+        throw Error(ZB_ERR_COMM, fmt("%s failed: NCCL error %d (%s)", what, rc, msg));
+    }
+}
+}  // namespace
+
+void Nccl::unique_id(uint8_t* out128) {
+    ncclUniqueId_ id;
+    check(api().get_unique_id(&id), "ncclGetUniqueId");
+    memcpy(out128, id.internal, 128);
+}
+
+void Nccl::init(const uint8_t* id128, int rank_, int world_, int device) {
+    ZB_CUDA(cudaSetDevice(device));
+    ncclUniqueId_ id;
+    memcpy(id.internal, id128, 128);
+    check(api().comm_init_rank(&comm, world_, id, rank_), "ncclCommInitRank");
+    rank = rank_;
+    world = world_;
+}
+
+void Nccl::destroy() {
+    if (comm) api().comm_destroy(comm);
+    comm = nullptr;
+}
+
+void Nccl::allreduce(void* d_buf, size_t count, Type t, Op op, cudaStream_t s) {
+    if (!count) return;
+    check(api().all_reduce(d_buf, d_buf, count, (int)t, (int)op, comm, s), "ncclAllReduce");
+}
+
+void Nccl::allgather(const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t s) {
+    if (!bytes_per_rank) return;
+    check(api().all_gather(d_send, d_recv, bytes_per_rank, (int)U8, comm, s), "ncclAllGather");
+}
+
+}  // namespace zb

@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- top-k queries/sec of the LSH query hot path (BASELINE.json metric) on N B200s of one node.
+
+A "step" is one pass of the hot path (plan -> leaf scan + top-n' -> merge) over one batch of synthetic queries
+against a resident index.  N = 1 runs BASELINE config[1]: 1M x 768 f32, L2, 10k batched top-10 queries.  N > 1
+is a weak-scaling run of the same per-GPU workload: rows are sharded (1M per GPU, ordinal % N), the query batch
+grows to N x 10k, every rank scans its shard of every visited leaf and the per-visit local top-n' lists are
+merged by an NCCL allgather inside the library.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3                 # ours
+  python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 # the restated reference on the host cores
+
+The oracle (oracle/) is used here only as the checker (sample parity) and as the measured CPU baseline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC_IDS = {"cosine": 0, "l2sq": 1, "l2": 2}
+METRIC_CLASSES = {"cosine": "CosineDistance", "l2sq": "L2SquaredDistance", "l2": "L2Distance"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000, help="rows per GPU")
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--queries", type=int, default=10_000, help="queries per GPU per step")
+    ap.add_argument("--topk", type=int, default=10)
+    ap.add_argument("--metric", default="l2", choices=list(METRIC_IDS))
+    ap.add_argument("--max-node-size", type=int, default=2048)
+    ap.add_argument("--trees", type=int, default=4)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--set", action="append", default=[], help="library knob key=value (ablations)")
+    return ap.parse_args()
+
+
+def workload_name(a, n_gpus):
+    return (f"{a.rows * n_gpus // 1000}k x {a.dim} f32 {a.metric.upper()} LSH index "
+            f"(max_node_size {a.max_node_size}, {a.trees} trees), {a.queries * n_gpus} batched top-{a.topk} queries")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe of B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------- reference arm
+def run_reference(a):
+    """The reference algorithm restated on the CPU (oracle/), all host threads, same config / metric / unit.
+    Each step is a bounded sample of the step's query batch; the forest is built by the oracle itself."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import zb_oracle as zo
+
+    cores = os.cpu_count() or 1
+    n_gpus = a.gpus
+    total_rows = a.rows * n_gpus
+    t0 = time.time()
+    rows = zo.synth(0, 1, total_rows, a.dim, a.seed, 1, cores)
+    zo.set_build_threads(min(cores, a.trees))
+    orc = zo.OracleIndex(a.dim, METRIC_IDS[a.metric], a.max_node_size, a.trees, seed=a.seed)
+    orc.add(rows)
+    t_build = time.time() - t0
+    nq_step = a.queries * n_gpus
+    # calibrate the sample so that the whole run stays within a couple of minutes
+    q0 = zo.synth(0, 1, 64, a.dim, a.seed + 1, 1, cores)
+    t = time.time(); orc.search_batch(q0, a.topk, nthreads=cores); per_q = max((time.time() - t) / 64, 1e-6)
+    budget = max(2.0, min(a.cpu_seconds, 90.0 / max(1, a.steps + a.warmup)))
+    sample = int(max(64, min(nq_step, budget / per_q)))
+    times = []
+    for s in range(a.warmup + a.steps):
+        q = zo.synth(s * nq_step, 1, sample, a.dim, a.seed + 1, 1, cores)
+        t = time.time()
+        orc.search_batch(q, a.topk, nthreads=cores)
+        dt = time.time() - t
+        if s >= a.warmup:
+            times.append(dt)
+    total = float(sum(times))
+    qps = sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": "queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": n_gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times) * (nq_step / sample),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a, n_gpus), "rows_per_gpu": a.rows, "queries_per_gpu": a.queries,
+                   "top_k": a.topk, "metric": a.metric, "max_node_size": a.max_node_size, "num_trees": a.trees,
+                   "data": "Philox clustered (centre[row % 4096] + 0.25 noise)"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {nq_step} queries per step, {len(times)} steps, in-memory forest built by "
+                                   f"the oracle in {t_build:.1f}s (storage engine excluded)"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import zebra_b200 as z
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: zebra_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    G = world
+    nq = a.queries * G
+    total_rows = a.rows * G
+    metric = getattr(z, METRIC_CLASSES[a.metric])()
+    ix = z.LSHIndex(a.dim, z.LSHIndexOptions(a.max_node_size, a.trees), metric, device=local, seed=a.seed,
+                    shard_rank=rank, shard_count=G)
+    for kv in a.set:
+        k, v = kv.split("=")
+        ix.set_param(k, int(v))
+    if G > 1:
+        uid = [z.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ix.comm_init(uid[0])
+
+    # ---- resident index: rows generated on the device, shard by shard ----
+    t0 = time.time()
+    n_local = len(range(rank, total_rows, G))
+    d_rows = torch.empty((n_local, a.dim), dtype=torch.float32, device=dev)
+    z.synth_fill_device(local, d_rows.data_ptr(), rank, G, n_local, a.dim, a.seed, 1)
+    if G > 1:
+        ix.add_owned_device(d_rows.data_ptr(), np.arange(rank, total_rows, G, dtype=np.uint64), total_rows)
+    else:
+        ix.add_device(d_rows.data_ptr(), n_local)
+    del d_rows
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+
+    # ---- query batches (distinct per step, so no step re-reads its predecessor's working set from L2) ----
+    nb = a.steps + a.warmup
+    d_q = torch.empty((nb, nq, a.dim), dtype=torch.float32, device=dev)
+    for b in range(nb):
+        z.synth_fill_device(local, d_q[b].data_ptr(), b * nq, 1, nq, a.dim, a.seed + 1, 1)
+    h_q = d_q.cpu().pin_memory()
+    d_ord = torch.empty((nq, a.topk), dtype=torch.int64, device=dev)
+    d_bits = torch.empty((nq, a.topk), dtype=torch.int64, device=dev)
+    d_cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+    h_ord = torch.empty((nq, a.topk), dtype=torch.int64).pin_memory()
+    h_bits = torch.empty((nq, a.topk), dtype=torch.int64).pin_memory()
+    h_cnt = torch.empty((nq,), dtype=torch.int32).pin_memory()
+    stream = torch.cuda.ExternalStream(ix.stream_ptr(), device=dev)
+
+    def barrier():
+        if G > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(b):
+        ix.search_batch_device(nq, d_q[b].data_ptr(), a.topk, d_ord.data_ptr(), d_bits.data_ptr(), d_cnt.data_ptr())
+
+    def step_e2e(b):
+        ix.search_batch_ptr(nq, h_q[b].data_ptr(), a.topk, h_ord.data_ptr(), h_bits.data_ptr(), h_cnt.data_ptr())
+
+    # ---- device-resident leg: `value` ----
+    for b in range(a.warmup):
+        step_device(b)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {"scan_ms": 0.0, "plan_ms": 0.0, "select_ms": 0.0, "merge_ms": 0.0, "moved": 0, "pairs": 0, "visits": 0,
+           "tile_pairs": 0, "scan_launches": 0, "launches": 0}
+    t_wall = time.perf_counter()
+    e0.record(stream)
+    for s in range(a.steps):
+        step_device(a.warmup + s)
+        st = ix.stats()
+        agg["scan_ms"] += st["last_ms_scan"]; agg["plan_ms"] += st["last_ms_plan"]
+        agg["select_ms"] += st["last_ms_select"]; agg["merge_ms"] += st["last_ms_merge"]
+        agg["moved"] += st["last_moved_bytes"]; agg["pairs"] += st["last_pairs"]; agg["visits"] += st["last_visits"]
+        agg["tile_pairs"] += st["last_tile_pairs"]
+        agg["scan_launches"] += st["last_scan_launches"]; agg["launches"] += st["last_total_launches"]
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    if G > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    ms_per_step = dev_ms / a.steps
+    value = nq * a.steps / (dev_ms / 1e3)
+
+    # ---- end-to-end leg through the host-buffer C ABI call: H2D of the queries, D2H of ids/distances/counts ----
+    for b in range(min(2, a.warmup)):
+        step_e2e(b)
+    barrier()
+    t_e = time.perf_counter()
+    for s in range(a.steps):
+        step_e2e(a.warmup + s)
+    barrier()
+    e2e_ms = (time.perf_counter() - t_e) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if G > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[0])
+    e2e_value = nq * a.steps / (e2e_ms / 1e3)
+    h2d = nq * a.dim * 4
+    d2h = nq * a.topk * 16 + nq * 4
+    same = bool(torch.equal(h_ord, d_ord.cpu()) and torch.equal(h_bits, d_bits.cpu()))
+
+    # ---- roofline of the dominant kernel (the leaf scan): bytes it asks HBM for by design / its event time ----
+    peak, peak_src = hbm_peak()
+    scan_s = agg["scan_ms"] / 1e3
+    achieved = agg["moved"] / scan_s / 1e9 if scan_s > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "leaf scan (zb_scan.cu tile kernel + generic score_pairs)",
+                "algorithmic_bytes_per_step": agg["moved"] // max(1, a.steps),
+                "kernel_ms_per_step": agg["scan_ms"] / a.steps,
+                "pair_gbs": agg["pairs"] * a.dim * 4 / scan_s / 1e9 if scan_s > 0 else 0.0,
+                "kernel_share_of_step": agg["scan_ms"] / dev_ms}
+
+    # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1) ----
+    cpu = None
+    parity = None
+    if rank == 0 and G == 1 and not a.no_cpu_baseline:
+        from oracle import zb_oracle as zo
+
+        cores = os.cpu_count() or 1
+        rows = zo.synth(0, 1, total_rows, a.dim, a.seed, 1, cores)
+        orc = zo.OracleIndex(a.dim, METRIC_IDS[a.metric], a.max_node_size, a.trees, seed=a.seed)
+        orc.load_forest(rows, ix.export_forest())      # same forest as the GPU arm (build parity is a separate test)
+        b = a.warmup + a.steps - 1
+        qh = h_q[b].numpy()
+        tq = time.time(); orc.search_batch(qh[:64], a.topk, nthreads=cores); per_q = max((time.time() - tq) / 64, 1e-6)
+        sample = int(max(64, min(nq, a.cpu_seconds / per_q)))
+        tq = time.time()
+        eo, eb, ec = orc.search_batch(qh[:sample], a.topk, nthreads=cores)
+        dt = time.time() - tq
+        cpu = {"value": sample / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"first {sample} of the {nq} queries of the last timed step, {dt:.1f}s on {cores} threads; "
+                         "restated reference, in-memory forest (storage engine excluded)"}
+        go, gb, gc = h_ord.numpy()[:sample].view(np.uint64), h_bits.numpy()[:sample].view(np.uint64), h_cnt.numpy()[:sample]
+        parity = bool(np.array_equal(go, eo) and np.array_equal(gb, eb) and np.array_equal(gc.astype(np.uint32), ec))
+
+    if rank == 0:
+        st = ix.stats()
+        line = {
+            "metric": "queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": G, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a, G), "rows_per_gpu": a.rows, "queries_per_gpu": a.queries,
+                       "top_k": a.topk, "metric": a.metric, "max_node_size": a.max_node_size, "num_trees": a.trees,
+                       "data": "Philox clustered (centre[row % 4096] + 0.25 noise), generated on device",
+                       "l2_policy": "every step uses a fresh query batch and streams >1 GB of rows (>> 126 MB L2)",
+                       "parallelism": f"row-sharded x{G}" if G > 1 else "single GPU",
+                       "index_build_s": round(t_build, 2), "leaves": st["leaves"], "planes": st["planes"]},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / a.steps, "matches_device_leg": same},
+            "gpu_launches": int(agg["launches"]), "clocks": clocks,
+            "phases_ms_per_step": {k: agg[k] / a.steps for k in ("plan_ms", "scan_ms", "select_ms", "merge_ms")},
+            "wall_ms_per_step": wall_ms / a.steps, "visits_per_step": agg["visits"] // a.steps,
+            "pairs_per_step": agg["pairs"] // a.steps, "tile_pairs_per_step": agg["tile_pairs"] // a.steps,
+            "parity_sample_ok": parity, "device_bytes": st["device_bytes"],
+        }
+        print(json.dumps(line), flush=True)
+    if G > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

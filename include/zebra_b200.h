@@ -141,6 +141,9 @@ int zb_index_load_forest(zb_index* index, uint64_t n, const float* rows, const u
                          const float* cst, const int64_t* leaf_off, const uint64_t* members);
 
 int zb_index_stats(zb_index* index, zb_stats* out);
+/* The CUDA stream (cudaStream_t) every kernel of this index is launched on -- for callers that time the
+ * device work with their own events. */
+int zb_index_stream(zb_index* index, void** out_stream);
 /* Tuning knobs (tests and ablations): key in {"tile_min_rows", "tile_queries", "use_tile_scan"}. */
 int zb_index_set_param(zb_index* index, const char* key, int64_t value);
 

@@ -462,6 +462,34 @@ static zbo_node* split_overfull(zbo_index* ix, zbo_node* nd) {
     return rebuilt;
 }
 
+/* (0..num_trees).into_par_iter() of build_index, lsh.rs:420-427: one task per tree. */
+typedef struct { zbo_index* ix; const uint64_t* ids; size_t live; volatile int* next; } build_job;
+static void* build_worker(void* arg) {
+    build_job* job = (build_job*)arg;
+    for (;;) {
+        int t = __atomic_fetch_add(job->next, 1, __ATOMIC_RELAXED);
+        if (t >= job->ix->num_trees) break;
+        job->ix->roots[t] = build_tree(job->ix, job->ids, job->live, root_key(job->ix->seed, t), 0);
+    }
+    return NULL;
+}
+static int g_build_threads = 0;
+void zbo_set_build_threads(int n) { g_build_threads = n; }
+static void build_forest_parallel(zbo_index* ix, const uint64_t* ids, size_t live) {
+    volatile int next = 0;
+    build_job job = {ix, ids, live, &next};
+    int nth = g_build_threads > 0 ? g_build_threads : 1;
+    if (nth > ix->num_trees) nth = ix->num_trees;
+    if (nth <= 1) {
+        build_worker(&job);
+        return;
+    }
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nth);
+    for (int i = 0; i < nth; ++i) pthread_create(&th[i], NULL, build_worker, &job);
+    for (int i = 0; i < nth; ++i) pthread_join(th[i], NULL);
+    free(th);
+}
+
 /* LSHIndex::add, lsh.rs:440-466 (build_index :411-429 when there are no trees yet).
  * ids are the row ordinals n_rows_before .. n_rows_before+n-1, written to out_ids when non-NULL. */
 int zbo_add(zbo_index* ix, uint64_t n, const float* rows, uint64_t* out_ids) {
@@ -475,7 +503,7 @@ int zbo_add(zbo_index* ix, uint64_t n, const float* rows, uint64_t* out_ids) {
         uint64_t* ids = (uint64_t*)malloc(sizeof(uint64_t) * ix->n_rows);
         for (size_t i = 0; i < ix->n_rows; ++i)
             if (!ix->tomb[i]) ids[live++] = i;
-        for (int t = 0; t < ix->num_trees; ++t) ix->roots[t] = build_tree(ix, ids, live, root_key(ix->seed, t), 0);
+        build_forest_parallel(ix, ids, live);
         free(ids);
         ix->built = 1;
         return 0;
@@ -799,4 +827,65 @@ void zbo_distance_bits_batch(int metric, uint64_t n, const float* a, const float
 void zbo_above_batch(uint64_t n, const float* coef, const float* cst, const float* x, int dim, uint8_t* out) {
     for (size_t i = 0; i < n; ++i)
         out[i] = (uint8_t)zbo_point_is_above(coef + i * (size_t)dim, cst[i], x + i * (size_t)dim, dim);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic data of BASELINE.md (not part of the reference): Philox-4x32-10, counter = (row_lo, row_hi,
+ * col/4, stream), key = seed; word -> f32 exactly: x = float((int32)w >> 8) * 2^-23 in [-1, 1).
+ * kind 1 (clustered): row = centre[row % 4096] + 0.25 * noise with one fmaf.  Lets the CPU legs create the
+ * very rows the GPU generates without any device involvement.
+ * ---------------------------------------------------------------------------------------------- */
+static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+static inline float word_to_unit(uint32_t w) { return (float)((int32_t)w >> 8) * 1.1920928955078125e-07f; }
+typedef struct { float* out; uint64_t first, stride, n, seed; uint32_t dim, kind; volatile int64_t* next; } synth_job;
+static void* synth_worker(void* arg) {
+    synth_job* j = (synth_job*)arg;
+    uint32_t quads = (j->dim + 3) / 4;
+    for (;;) {
+        int64_t b = __atomic_fetch_add(j->next, 1024, __ATOMIC_RELAXED);
+        if ((uint64_t)b >= j->n) break;
+        uint64_t e = (uint64_t)b + 1024 < j->n ? (uint64_t)b + 1024 : j->n;
+        for (uint64_t ri = (uint64_t)b; ri < e; ++ri) {
+            uint64_t row = j->first + ri * j->stride;
+            for (uint32_t cq = 0; cq < quads; ++cq) {
+                uint32_t c[4] = {(uint32_t)row, (uint32_t)(row >> 32), cq, 0u};
+                philox4x32_10(c, (uint32_t)j->seed, (uint32_t)(j->seed >> 32));
+                float v[4] = {word_to_unit(c[0]), word_to_unit(c[1]), word_to_unit(c[2]), word_to_unit(c[3])};
+                if (j->kind == 1) {
+                    uint64_t crow = row % 4096ull;
+                    uint32_t cc[4] = {(uint32_t)crow, 0u, cq, 1u};
+                    philox4x32_10(cc, (uint32_t)j->seed, (uint32_t)(j->seed >> 32));
+                    for (int x = 0; x < 4; ++x) v[x] = fmaf(0.25f, v[x], word_to_unit(cc[x]));
+                }
+                for (uint32_t x = 0; x < 4; ++x) {
+                    uint32_t col = cq * 4 + x;
+                    if (col < j->dim) j->out[ri * j->dim + col] = v[x];
+                }
+            }
+        }
+    }
+    return NULL;
+}
+void zbo_synth_fill(float* out, uint64_t first_row, uint64_t row_stride, uint64_t n, uint32_t dim, uint64_t seed,
+                    uint32_t kind, int nthreads) {
+    volatile int64_t next = 0;
+    synth_job job = {out, first_row, row_stride, n, seed, dim, kind, &next};
+    if (nthreads <= 1) {
+        synth_worker(&job);
+        return;
+    }
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    for (int i = 0; i < nthreads; ++i) pthread_create(&th[i], NULL, synth_worker, &job);
+    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    free(th);
 }

@@ -69,6 +69,8 @@ def lib():
         L.zbo_make_plane.argtypes = [vp, vp, i32, vp, vp]
         L.zbo_force_scalar.argtypes = [i32]
         L.zbo_using_avx512.restype = i32
+        L.zbo_set_build_threads.argtypes = [i32]
+        L.zbo_synth_fill.argtypes = [vp, u64, u64, u64, C.c_uint32, u64, C.c_uint32, i32]
         L.zbo_mix64.restype = u64
         L.zbo_mix64.argtypes = [u64]
         _lib = L
@@ -128,6 +130,17 @@ def make_plane(a, b):
     cst = np.empty(1, dtype=np.float32)
     lib().zbo_make_plane(_p(a), _p(b), a.size, _p(coef), _p(cst))
     return coef, float(cst[0])
+
+
+def synth(first_row: int, row_stride: int, n: int, dim: int, seed: int, kind: int = 0, nthreads: int = 0) -> np.ndarray:
+    """The synthetic rows of BASELINE.md, generated on the CPU (bit-identical to zb_synth_fill_device)."""
+    out = np.empty((n, dim), dtype=np.float32)
+    lib().zbo_synth_fill(_p(out), first_row, row_stride, n, dim, seed, kind, nthreads or (os.cpu_count() or 1))
+    return out
+
+
+def set_build_threads(n: int) -> None:
+    lib().zbo_set_build_threads(n)
 
 
 class Forest:

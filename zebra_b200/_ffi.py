@@ -87,6 +87,7 @@ SYMBOLS = {
     "zb_index_export_forest": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "zb_index_load_forest": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "zb_index_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "zb_index_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "zb_index_set_param": (C.c_int, [_vp, C.c_char_p, _i64]),
     "zb_comm_unique_id": (C.c_int, [_vp]),
     "zb_index_comm_init": (C.c_int, [_vp, _vp]),

@@ -1218,6 +1218,13 @@ int zb_index_stats(zb_index* ix, zb_stats* out) {
     ZB_API_END
 }
 
+int zb_index_stream(zb_index* ix, void** out_stream) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && out_stream, ZB_ERR_INVALID, "NULL argument");
+    *out_stream = (void*)ix->stream;
+    ZB_API_END
+}
+
 int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     ZB_API_BEGIN
     ZB_REQUIRE(ix && key, ZB_ERR_INVALID, "NULL argument");

@@ -222,6 +222,12 @@ class LSHIndex:
         _ffi.check(_ffi.lib().zb_index_stats(self._h, C.byref(st)))
         return st.as_dict()
 
+    def stream_ptr(self) -> int:
+        """cudaStream_t of the index (all kernels are launched on it)."""
+        out = C.c_void_p()
+        _ffi.check(_ffi.lib().zb_index_stream(self._h, C.byref(out)))
+        return int(out.value or 0)
+
     def set_param(self, key: str, value: int) -> None:
         _ffi.check(_ffi.lib().zb_index_set_param(self._h, key.encode(), int(value)))
 

@@ -79,6 +79,7 @@ struct zb_index {
     // ---- vector store (device resident, slot order) ----
     DBuf<float> rows;
     DBuf<u64> ord;
+    DBuf<float> row_norm;
     DBuf<u32> tomb;
     DBuf<u32> slot_leaf;  // [T][slot_stride]
     u64 slot_stride = 0;
@@ -118,7 +119,7 @@ struct zb_index {
     DBuf<u64> v_pair_len, v_pair_off, pair_key;
     DBuf<u8> v_done;
     DBuf<Entry> entries, gathered;
-    DBuf<float> q_stage, r_stage;
+    DBuf<float> q_stage, r_stage, q_norm;
     DBuf<u64> o_ord, o_bits, h_keys;
     DBuf<u32> o_counts, h_depths, rm_slots;
     DBuf<int> h_leaves;
@@ -149,6 +150,7 @@ struct zb_index {
         f.members = d_members.p;
         f.rows = rows.p;
         f.ord = ord.p;
+        f.row_norm = row_norm.p;
         f.tomb = tomb.p;
         f.dimp = dimp;
         f.chunks = chunks;
@@ -204,6 +206,7 @@ struct zb_index {
         ncap = (ncap + 31) & ~31ull;
         rows.ensure(ncap * (u64)dimp, n_slots * (u64)dimp, stream, true);
         ord.ensure(ncap, n_slots, stream, true);
+        row_norm.ensure(ncap, n_slots, stream, true);
         size_t old_words = tomb.cap;
         tomb.ensure(ncap / 32 + 1, (n_slots + 31) / 32, stream, true);
         (void)old_words;
@@ -231,6 +234,7 @@ struct zb_index {
             launch_pad_rows(d_src, n_local, dim, dimp, dst, stream);
         }
         ZB_CUDA(cudaMemcpyAsync(ord.p + n_slots, ordinals, n_local * 8, cudaMemcpyHostToDevice, stream));
+        if (opt.metric == ZB_METRIC_COSINE) launch_sq_norms(dst, n_local, dimp, row_norm.p + n_slots, stream);
         // clear tombstone bits of the new slots (word granular: new words zeroed, shared first word bits are already 0)
         u64 w0 = (n_slots + 31) / 32, w1 = (n_slots + n_local + 31) / 32;
         if (n_slots == 0) w0 = 0;
@@ -590,8 +594,12 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->entries.ensure(total_slots ? total_slots : 1);
     u64 tile_pairs = 0, tile_visits = 0, moved = 0;
     u32 scan_launches = 0;
+    if (ix->p_use_tile_scan && nv && ix->opt.metric == ZB_METRIC_COSINE) {
+        ix->q_norm.ensure(nq);
+        launch_sq_norms(d_q, nq, ix->dimp, ix->q_norm.p, s);
+    }
     if (ix->p_use_tile_scan && nv)
-        tile_scan(ix->scan_ws, f, ix->opt.metric, d_q, (u32)nq, nv, ix->v_leaf.p, ix->v_np.p, ix->v_q.p, ix->v_ent_off.p,
+        tile_scan(ix->scan_ws, f, ix->opt.metric, d_q, ix->q_norm.p, (u32)nq, nv, ix->v_leaf.p, ix->v_np.p, ix->v_q.p, ix->v_ent_off.p,
                   ix->v_pair_len.p, ix->v_done.p, ix->entries.p, (u32)top_k, (u32)ix->p_tile_min_rows,
                   (u32)ix->p_tile_queries, (u32)ix->h_leaf_off.size(), s, &tile_visits, &tile_pairs, &moved, &scan_launches);
 

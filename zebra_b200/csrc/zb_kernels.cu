@@ -683,6 +683,25 @@ void launch_synth(float* d_out, u64 first_row, u64 row_stride, u64 n, u32 dim, u
 // Metric::distance of distance.rs:19-49,:103-114 and Hyperplane::point_is_above of lsh.rs:39-43 for
 // n independent pairs).  One quad per pair.
 // =====================================================================================================
+// squared norms in the canonical order (the a2 / b2 accumulators of simsimd's cos kernel): one quad per vector
+__global__ void __launch_bounds__(128) sq_norms_kernel(const float* __restrict__ x_, u64 n, int dimp, float* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * 32ull + (threadIdx.x >> 2);
+    if (i >= n) return;
+    const int sub = threadIdx.x & 3;
+    const float4* x = reinterpret_cast<const float4*>(x_ + i * dimp);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < dimp / 16; ++c) {
+        float4 v = x[c * 4 + sub];
+        fma4(acc, v, v);
+    }
+    float sum = quad_reduce16(acc, quad_mask());
+    if (sub == 0) out[i] = sum;
+}
+void launch_sq_norms(const float* d_x, u64 n, int dimp, float* d_out, cudaStream_t s) {
+    if (!n) return;
+    sq_norms_kernel<<<(u32)((n + 31) / 32), 128, 0, s>>>(d_x, n, dimp, d_out);
+}
+
 template <int METRIC>
 __global__ void __launch_bounds__(128) pair_metric_kernel(const float* __restrict__ a_, const float* __restrict__ b_, u64 n,
                                                           int dimp, u64* __restrict__ out) {

@@ -23,6 +23,7 @@ struct ForestView {
     const u32* members;       // slots
     const float* rows;        // [slots][dimp]
     const u64* ord;           // [slots] global ordinal
+    const float* row_norm;    // [slots] squared norm of the row in the canonical order (cosine)
     const u32* tomb;          // bitmask over slots
     int dimp, chunks, num_trees;
 };
@@ -82,6 +83,7 @@ void launch_fill_u64(u64* d, u64 n, u64 v, cudaStream_t s);
 void launch_iota_ord(u64* d, u64 n, u64 first, u64 stride, cudaStream_t s);
 void launch_synth(float* d_out, u64 first_row, u64 row_stride, u64 n, u32 dim, u64 seed, u32 kind, cudaStream_t s);
 
+void launch_sq_norms(const float* d_x, u64 n, int dimp, float* d_out, cudaStream_t s);
 void launch_pair_metric(int metric, const float* d_a, const float* d_b, u64 n, int dimp, u64* d_out, cudaStream_t s);
 void launch_pair_above(const float* d_coef, const float* d_cst, const float* d_x, u64 n, int dimp, u8* d_out, cudaStream_t s);
 

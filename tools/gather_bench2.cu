@@ -74,7 +74,7 @@ int main() {
     cudaFuncSetAttribute(k_ldgsts, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     struct Cfg { int kind; u32 bytes, rows, nst, threads; } cfgs[] = {
         {0, 384, 128, 3, 32}, {0, 384, 128, 3, 128}, {0, 384, 128, 3, 256}, {0, 768, 64, 3, 128}, {0, 3072, 16, 4, 32}, {0, 3072, 16, 4, 128}, {0, 3072, 32, 2, 64},
-        {1, 384, 128, 3, 256}, {1, 768, 64, 3, 256}, {1, 1536, 32, 3, 256}, {1, 3072, 16, 3, 256}, {1, 384, 128, 3, 512}};
+        {1, 384, 128, 3, 256}, {1, 768, 64, 3, 256}, {1, 1536, 32, 3, 256}, {1, 3072, 16, 3, 256}, {1, 384, 128, 3, 512}, {1, 192, 256, 3, 256}, {1, 128, 512, 3, 256}, {0, 192, 256, 3, 256}, {0, 128, 512, 3, 256}, {1, 384, 128, 2, 256}, {1, 384, 128, 4, 256}, {1, 384, 64, 6, 256}};
     for (auto c : cfgs) {
         const u32 slices = 3072 / c.bytes, stages_total = 4000;
         size_t smem = 128 + (size_t)c.nst * c.rows * c.bytes;

@@ -110,6 +110,14 @@ struct zb_index {
     DBuf<int> d_leaf_export;
     bool export_table_valid = false;
 
+    // ---- bucket-major store (search path): position p of the member array holds a copy of row members[p] ----
+    DBuf<float> bm_rows;
+    DBuf<double> bm_rinv, q_rinv;
+    DBuf<u32> bm_tomb, slot_pos, d_leaf_tree;
+    alignas(64) unsigned char bm_tmap[128];
+    bool bm_valid = false, bm_failed = false;
+    u64 bm_positions = 0;
+
     // ---- workspaces ----
     DBuf<u8> cub_tmp;
     DBuf<u32> w_counts, w_off, w_flag;
@@ -119,7 +127,7 @@ struct zb_index {
     DBuf<u64> v_pair_len, v_pair_off, pair_key;
     DBuf<u8> v_done;
     DBuf<Entry> entries, gathered;
-    DBuf<float> q_stage, r_stage, q_norm;
+    DBuf<float> q_stage, r_stage;
     DBuf<u64> o_ord, o_bits, h_keys;
     DBuf<u32> o_counts, h_depths, rm_slots;
     DBuf<int> h_leaves;
@@ -261,6 +269,49 @@ struct zb_index {
         }
         sync();
         export_table_valid = false;
+        bm_valid = false;
+    }
+    // (Re)build the bucket-major store after the forest or the row set changed.  Only forests whose leaves can reach
+    // the tile kernel's minimum size get one; an allocation failure degrades to the generic gather path.
+    bool ensure_bucket_major() {
+        if (bm_valid) return true;
+        if (bm_failed || !built || !p_use_tile_scan || opt.max_node_size < (u64)p_tile_min_rows || !members_used) return false;
+        const u32 nl = (u32)h_leaf_off.size();
+        try {
+            bm_rows.ensure(members_used * (u64)dimp, 0, stream, true);
+            bm_tomb.ensure(members_used / 32 + 8);
+            slot_pos.ensure(slot_stride * (u64)T);
+            d_leaf_tree.ensure(nl);
+            if (opt.metric == ZB_METRIC_COSINE) bm_rinv.ensure(members_used);
+        } catch (const Error& e) {
+            if (e.code != ZB_ERR_OOM) throw;
+            bm_rows.release();
+            bm_failed = true;
+            return false;
+        }
+        std::vector<u32> lt(h_leaf_tree.begin(), h_leaf_tree.end());
+        ZB_CUDA(cudaMemcpyAsync(d_leaf_tree.p, lt.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, stream));
+        ZB_CUDA(cudaMemsetAsync(bm_tomb.p, 0, (members_used / 32 + 8) * 4, stream));
+        u64 used = 0;
+        for (u32 l = 0; l < nl; ++l) used += h_leaf_len[l];
+        if (used != members_used) ZB_CUDA(cudaMemsetAsync(bm_rows.p, 0, members_used * (u64)dimp * 4, stream));  // slack positions
+        launch_bm_gather(nl, d_leaf_off.p, d_leaf_len.p, d_leaf_tree.p, d_members.p, rows.p, tomb.p, dimp, slot_stride, bm_rows.p,
+                         slot_pos.p, bm_tomb.p, stream);
+        if (opt.metric == ZB_METRIC_COSINE) launch_rinv(bm_rows.p, members_used, dimp, bm_rinv.p, stream);
+        make_row_tile_map(bm_tmap, bm_rows.p, members_used, dimp);
+        sync();
+        bm_positions = members_used;
+        bm_valid = true;
+        return true;
+    }
+    BucketMajor bm_view() const {
+        BucketMajor b;
+        b.rows = bm_rows.p;
+        b.rinv = bm_rinv.p;
+        b.tomb = bm_tomb.p;
+        b.tmap = bm_tmap;
+        b.positions = bm_positions;
+        return b;
     }
     void recount_live() {  // leaf_live from members + tombstones, then the global plan counts
         u32 nl = (u32)h_leaf_off.size();
@@ -309,6 +360,8 @@ struct zb_index {
         h_members_valid = false;
         built = false;
         export_table_valid = false;
+        bm_valid = false;
+        bm_failed = false;
     }
 
     // ---------------------------------------------------------------- build (lsh.rs:192-267, level synchronous)
@@ -594,14 +647,17 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->entries.ensure(total_slots ? total_slots : 1);
     u64 tile_pairs = 0, tile_visits = 0, moved = 0;
     u32 scan_launches = 0;
-    if (ix->p_use_tile_scan && nv && ix->opt.metric == ZB_METRIC_COSINE) {
-        ix->q_norm.ensure(nq);
-        launch_sq_norms(d_q, nq, ix->dimp, ix->q_norm.p, s);
+    ix->scan_ws.launched = false;
+    if (nv && tile_scan_supported(ix->dimp, (u32)top_k) && ix->ensure_bucket_major()) {
+        if (ix->opt.metric == ZB_METRIC_COSINE) {
+            ix->q_rinv.ensure(nq);
+            launch_rinv(d_q, nq, ix->dimp, ix->q_rinv.p, s);
+        }
+        tile_scan(ix->scan_ws, f, ix->bm_view(), ix->opt.metric, d_q, ix->q_rinv.p, (u32)nq, nv, ix->v_leaf.p, ix->v_np.p, ix->v_q.p,
+                  ix->v_ent_off.p, ix->v_pair_len.p, ix->v_done.p, ix->entries.p, (u32)top_k, (u32)ix->p_tile_min_rows,
+                  (u32)ix->p_tile_queries, (u32)ix->h_leaf_off.size(), s);
+        if (ix->scan_ws.launched) scan_launches = ix->scan_ws.launches + (ix->opt.metric == ZB_METRIC_COSINE ? 1 : 0);
     }
-    if (ix->p_use_tile_scan && nv)
-        tile_scan(ix->scan_ws, f, ix->opt.metric, d_q, ix->q_norm.p, (u32)nq, nv, ix->v_leaf.p, ix->v_np.p, ix->v_q.p, ix->v_ent_off.p,
-                  ix->v_pair_len.p, ix->v_done.p, ix->entries.p, (u32)top_k, (u32)ix->p_tile_min_rows,
-                  (u32)ix->p_tile_queries, (u32)ix->h_leaf_off.size(), s, &tile_visits, &tile_pairs, &moved, &scan_launches);
 
     // ---- generic path for the remaining visits ----
     exclusive_scan_u64(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_pair_len.p, ix->v_pair_off.p, nv + 1, s);
@@ -612,7 +668,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     launch_score_pairs(f, (int)ix->opt.metric, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, total_pairs,
                        ix->pair_key.p, s);
     ZB_CUDA(cudaEventRecord(ix->ev[2], s));
-    if (total_pairs || tile_visits < nv)
+    if (total_pairs)
         launch_select_visits(f, nv, ix->v_leaf.p, ix->v_np.p, ix->v_pair_off.p, ix->pair_key.p, ix->v_ent_off.p,
                              ix->entries.p, ix->v_done.p, (u32)top_k, s);
     ZB_CUDA(cudaEventRecord(ix->ev[3], s));
@@ -625,6 +681,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     launch_merge_queries((u32)nq, T, ix->w_off.p, ix->v_ent_off.p, final_entries, (u32)top_k, d_out_ord, d_out_bits,
                          d_out_counts, s);
     ZB_CUDA(cudaEventRecord(ix->ev[4], s));
+    tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved);
     ix->sync();
     float ms;
     cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]); ix->st.last_ms_plan = ms;
@@ -870,6 +927,8 @@ static void remove_ordinals(zb_index* ix, u64 n, const u64* ordinals, const u8* 
         } else {
             ZB_CUDA(cudaMemsetAsync(ix->rm_flags.p, 0, n, ix->stream));
         }
+        if (ix->built && ix->bm_valid)
+            launch_bm_tombstone(ix->rm_slots.p, ix->rm_flags.p, (u32)n, ix->slot_pos.p, ix->slot_stride, ix->T, ix->bm_tomb.p, ix->stream);
         if (ix->G > 1) ix->nccl.allreduce(ix->rm_flags.p, n, Nccl::U8, Nccl::MAX, ix->stream);
         ZB_CUDA(cudaMemcpyAsync(flags.data(), ix->rm_flags.p, n, cudaMemcpyDeviceToHost, ix->stream));
     }
@@ -1157,6 +1216,8 @@ int zb_index_load_forest(zb_index* ix, uint64_t n, const float* rows, const uint
             if (ix->owns(members[j])) ix->h_members.push_back((u32)ix->slot_of(members[j]));
         }
         ix->h_leaf_len[l] = ix->h_leaf_cap[l] = (u32)(ix->h_members.size() - ix->h_leaf_off[l]);
+        // invariant of the bucket-major store: inside a leaf, position order == ordinal order (ties by id, D3)
+        std::sort(ix->h_members.begin() + ix->h_leaf_off[l], ix->h_members.end());
     }
     struct Fr { int node; u64 key; int depth; };
     std::vector<Fr> stack;

@@ -602,6 +602,52 @@ void launch_tombstone(const u32* d_slots, u32 n, u32* d_tomb, const u32* d_slot_
                                                      d_removed);
 }
 
+// Bucket-major store: bm_rows[p] = rows[members[p]] for every position p of every leaf (one block per leaf), plus
+// the position of each slot in each tree (slot_pos, for tombstoning) and the position-major tombstone bitmap.
+__global__ void __launch_bounds__(256) bm_gather_kernel(const long long* __restrict__ leaf_off, const u32* __restrict__ leaf_len,
+                                                        const u32* __restrict__ leaf_tree, const u32* __restrict__ members,
+                                                        const float* __restrict__ rows, const u32* __restrict__ tomb, int dimp,
+                                                        u64 slot_stride, float* __restrict__ bm_rows,
+                                                        u32* __restrict__ slot_pos, u32* __restrict__ bm_tomb) {
+    const u32 leaf = blockIdx.x;
+    const long long off = leaf_off[leaf];
+    const u32 len = leaf_len[leaf], tree = leaf_tree[leaf];
+    const int q4 = dimp / 4;
+    for (u32 i = 0; i < len; ++i) {
+        const u32 slot = members[off + i];
+        const float4* src = reinterpret_cast<const float4*>(rows + (size_t)slot * dimp);
+        float4* dst = reinterpret_cast<float4*>(bm_rows + (size_t)(off + i) * dimp);
+        for (int c = threadIdx.x; c < q4; c += blockDim.x) dst[c] = __ldg(src + c);
+        if (threadIdx.x == 0) {
+            const u64 pos = (u64)(off + i);
+            slot_pos[(u64)tree * slot_stride + slot] = (u32)pos;
+            if (tomb_test(tomb, slot)) atomicOr(&bm_tomb[pos >> 5], 1u << (pos & 31));
+        }
+    }
+}
+void launch_bm_gather(u32 nleaves, const long long* d_leaf_off, const u32* d_leaf_len, const u32* d_leaf_tree, const u32* d_members,
+                      const float* d_rows, const u32* d_tomb, int dimp, u64 slot_stride, float* d_bm_rows, u32* d_slot_pos,
+                      u32* d_bm_tomb, cudaStream_t s) {
+    if (!nleaves) return;
+    bm_gather_kernel<<<nleaves, 256, 0, s>>>(d_leaf_off, d_leaf_len, d_leaf_tree, d_members, d_rows, d_tomb, dimp, slot_stride,
+                                             d_bm_rows, d_slot_pos, d_bm_tomb);
+}
+// position-major tombstones of freshly removed slots (flags[i] != 0): one bit per tree
+__global__ void bm_tombstone_kernel(const u32* __restrict__ slots, const u8* __restrict__ flags, u32 n,
+                                    const u32* __restrict__ slot_pos, u64 slot_stride, int num_trees, u32* __restrict__ bm_tomb) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i] || slots[i] == 0xFFFFFFFFu) return;
+    for (int t = 0; t < num_trees; ++t) {
+        const u32 pos = slot_pos[(u64)t * slot_stride + slots[i]];
+        atomicOr(&bm_tomb[pos >> 5], 1u << (pos & 31));
+    }
+}
+void launch_bm_tombstone(const u32* d_slots, const u8* d_flags, u32 n, const u32* d_slot_pos, u64 slot_stride, int num_trees,
+                         u32* d_bm_tomb, cudaStream_t s) {
+    if (!n) return;
+    bm_tombstone_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_slots, d_flags, n, d_slot_pos, slot_stride, num_trees, d_bm_tomb);
+}
+
 __global__ void pad_rows_kernel(const float* __restrict__ src, u64 n, int dim, int dimp, float* __restrict__ dst) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * (u64)dimp) return;

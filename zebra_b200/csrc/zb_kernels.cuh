@@ -78,6 +78,11 @@ void launch_assign_leaf(const Tile* d_tiles, u32 ntiles, const u32* d_members, u
 // ---- mutation ----
 void launch_tombstone(const u32* d_slots, u32 n, u32* d_tomb, const u32* d_slot_leaf, u64 slot_stride, int num_trees,
                       u32* d_leaf_live, u8* d_removed, cudaStream_t s);
+void launch_bm_gather(u32 nleaves, const long long* d_leaf_off, const u32* d_leaf_len, const u32* d_leaf_tree, const u32* d_members,
+                      const float* d_rows, const u32* d_tomb, int dimp, u64 slot_stride, float* d_bm_rows, u32* d_slot_pos,
+                      u32* d_bm_tomb, cudaStream_t s);
+void launch_bm_tombstone(const u32* d_slots, const u8* d_flags, u32 n, const u32* d_slot_pos, u64 slot_stride, int num_trees,
+                         u32* d_bm_tomb, cudaStream_t s);
 void launch_pad_rows(const float* d_src, u64 n, int dim, int dimp, float* d_dst, cudaStream_t s);
 void launch_fill_u64(u64* d, u64 n, u64 v, cudaStream_t s);
 void launch_iota_ord(u64* d, u64 n, u64 first, u64 stride, cudaStream_t s);

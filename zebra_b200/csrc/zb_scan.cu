@@ -1,26 +1,42 @@
-// zb_scan.cu -- the fused leaf-tile scan: candidate gather + distance scoring + per-visit top-n' in one kernel.
+// zb_scan.cu -- the fused leaf-tile scan: bucket-major row tiles + distance scoring + per-visit top-n' in one kernel.
 //
 // Replaces, for visits of large leaves, the leaf branch of tree_result
 // (/root/reference/src/database/index/lsh.rs:299-331: fetch every member, metric.distance, sort, take n) and
-// the rescoring of search (:557-563).  Work unit = (leaf, tile of <= 16 queries that visit it):
-//   * a producer warp gathers the leaf's rows with 1-D TMA bulk copies (cp.async.bulk, one per row, row
-//     addresses come from the leaf's member list) into a ring of shared-memory stages guarded by mbarriers;
-//   * 8 consumer warps score stage rows x tile queries with 2x2 register tiles per quad, in the canonical
-//     skylake-16 accumulation order (zb_device.cuh) -- every row is read from HBM once per tile;
-//   * each finished distance is filtered against the visit's current n'-th best (shared-memory threshold) and
-//     pushed to a per-visit candidate buffer; a warp merges buffer + current top list with a bitonic sort
-//     when the buffer could overflow; tombstoned rows are masked at the push.
+// the rescoring of search (:557-563).  Work unit ("tile") = (leaf, <= 16 queries that visit it).
+//
+//   * The rows of a leaf are CONTIGUOUS in the bucket-major store (zb_index.cu: bm_rows[position][dimp], position =
+//     index into the forest's member array), so a K slice of a 128-row block is one 2-D TMA box
+//     (cp.async.bulk.tensor.2d, SASS UTMALDG): one instruction per 24 KB stage, issued by a dedicated producer warp
+//     that runs up to TS ring stages ahead of the math warps -- across row blocks AND across tiles.
+//   * 8 consumer warps score stage rows x tile queries with 8x4 register tiles per quad in the canonical
+//     skylake-16 accumulation order (zb_device.cuh); the tile's queries stay resident in shared memory.
+//   * Top-n' is warp-private and register resident: lane l of a warp holds the l-th best (key, position) of a
+//     (query, row half); a finished distance is first filtered against the list's n'-th key, survivors are inserted
+//     with a ballot + shuffle-up.  No block-wide barrier anywhere in the steady state.  The two row halves of a
+//     query are merged once per tile with a shuffle bitonic network, tombstoned rows are masked at insertion.
 // The kernel is persistent (one CTA per SM, tiles handed out by an atomic counter).
 #include <cub/device/device_scan.cuh>
+#include <cuda.h>
 
 #include "zb_scan.cuh"
 
 namespace zb {
 
-#define TS_QT 16          // queries per tile (4 query groups of 4)
-#define TS_RB 128         // rows per row block (16 row groups of 8, interleaved: row = i * 16 + group)
-#define TS_THREADS 256    // 8 warps; warp 0 also issues the TMA copies
-#define TS_NSLOT 8        // row-block slot tables kept in flight
+#define TS_QT 16            // queries per tile (4 query groups of 4)
+#define TS_RB 128           // rows per row block (16 row groups of 8, interleaved: row = i * 16 + group)
+#define TS_KC 3             // 16-float chunks per K slice: 192 B row pitch puts adjacent rows in different bank halves
+#define TS_SLICE_FLOATS (TS_KC * 16)
+#define TS_STAGE_BYTES (TS_RB * TS_SLICE_FLOATS * 4)   // 24576
+#define TS_CWARPS 8         // consumer (math) warps
+#define TS_THREADS 384      // 2 math warpgroups + 1 producer warpgroup (its warp 0 drives TMA; registers handed to the math warps)
+#define TS_MAX_STAGES 8
+#define TS_KL 32            // list length of the register top-n' (one entry per lane)
+#define TS_NOPOS 0xFFFFFFFFu
+
+struct TileInfo {
+    u32 tile, leaf, first, nqt, L, pad;
+    long long moff;
+};
 
 struct TileParams {
     const u32* tile_leaf;
@@ -34,17 +50,14 @@ struct TileParams {
     const u32* v_ent_off;
     Entry* entries;
     const float* queries;
-    const float* qnorm;  // [nq] squared norms of the queries (cosine)
-    u64* stats;          // [0] visits, [1] pairs, [2] moved bytes
-    int nst;             // ring depth
-    int P;               // per-query top-k region (entries): kcap + cb, power of two
-    int kcap;
-    int kc;              // 16-float chunks per K slice
-    u32 row_stride;      // bytes between row slices of a stage (slice bytes + bank padding)
-    u32 stage_bytes;
+    const double* q_rinv;   // [nq] 1/sqrt(|q|^2) in f64 (cosine)
+    const double* bm_rinv;  // [positions] 1/sqrt(|row|^2) in f64 (cosine)
+    const u32* bm_tomb;     // bit per position
+    u64* stats;             // [0] visits, [1] pairs, [2] moved bytes
+    int nst;                // ring depth
 };
 
-// ---- PTX helpers: mbarrier + 1-D bulk copy (TMA, SASS UBLKCP) ----
+// ---- PTX helpers: mbarrier, 1-D bulk copy and 2-D tensor copy (TMA) ----
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -72,256 +85,291 @@ __device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u3
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TS_THREADS) : "memory"); }
+__device__ __forceinline__ void tma_2d_g2s(u32 dst, const CUtensorMap* map, int c0, int c1, u32 bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void pair_sync(int g) { asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory"); }
 
-// Warp-level bitonic sort of P entries in shared memory (P power of two >= 64), ascending (key, ord).
-__device__ __forceinline__ void warp_bitonic(Entry* s, int P, int lane) {
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < P; i += 32) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    Entry a = s[i], b = s[ixj];
-                    bool up = (i & k) == 0;
-                    if (entry_less(b, a) == up) {
-                        s[i] = b;
-                        s[ixj] = a;
-                    }
-                }
-            }
-            __syncwarp();
-        }
+__device__ __forceinline__ u64 shfl64(u64 v, int src) {
+    u32 lo = __shfl_sync(0xffffffffu, (u32)v, src), hi = __shfl_sync(0xffffffffu, (u32)(v >> 32), src);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_up64(u64 v) {
+    u32 lo = __shfl_up_sync(0xffffffffu, (u32)v, 1), hi = __shfl_up_sync(0xffffffffu, (u32)(v >> 32), 1);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_xor64(u64 v, int m) {
+    u32 lo = __shfl_xor_sync(0xffffffffu, (u32)v, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(v >> 32), m);
+    return ((u64)hi << 32) | lo;
+}
+// (key, position) order: the position order inside a leaf equals the ordinal order (zb_index.cu keeps member lists
+// ascending), so ties in distance are broken exactly like Entry order (D3).
+__device__ __forceinline__ bool kp_less(u64 ka, u32 pa, u64 kb, u32 pb) { return ka < kb || (ka == kb && pa < pb); }
+
+// Cosine epilogue from precomputed reciprocal norms: the operation order of cos_bits (zb_device.cuh) with
+// ra = 1/sqrt(a2), rb = 1/sqrt(b2) hoisted (ra is +inf exactly when a2 == 0).
+__device__ __forceinline__ u64 cos_bits_rinv(float ab_, double ra, double rb) {
+    const double ab = (double)ab_;
+    double c;
+    if (isinf(ra) && isinf(rb) && ra > 0.0 && rb > 0.0) c = 0.0;
+    else if (ab == 0.0) c = 1.0;
+    else {
+        double t = __dmul_rn(__dmul_rn(ab, ra), rb);
+        double r = __dsub_rn(1.0, t);
+        c = r > 0.0 ? r : 0.0;
     }
+    return (u64)__double_as_longlong(__dsub_rn(1.0, c));
 }
 
-// One quad owns 8 rows x 4 queries = 32 (row, query) pairs; thread `sub` keeps lanes 4*sub..4*sub+3 of every
-// pair's 16-lane accumulator.  Per 16-float chunk a thread issues 4 + 8 LDS.128 and 256 FP32 instructions, which
-// keeps the kernel FP32-issue bound rather than shared-memory bound (an LDS.128 occupies the shared-memory
-// datapath for 4 cycles per warp whether or not its addresses broadcast).  128 accumulator registers per thread
-// are why the CTA is exactly 8 warps (2 per SM sub-partition): warp 0 doubles as the TMA producer.
-template <int METRIC>
-__global__ void __launch_bounds__(TS_THREADS, 1) tile_scan_kernel(ForestView f, TileParams tp) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const u32 RS = tp.row_stride;
-    const u32 slice_bytes_full = (u32)tp.kc * 64u;
-    // ---- carve shared memory ----
-    unsigned char* s_stage = smem;                                            // [nst]{[RB][RS] rows, [QT][slice] queries}
-    Entry* s_top = reinterpret_cast<Entry*>(smem + (size_t)tp.nst * tp.stage_bytes);   // [QT][P]
-    u64* s_thr = reinterpret_cast<u64*>(s_top + TS_QT * tp.P);                // [QT]
-    u64* s_bar = s_thr + TS_QT;                                               // full[8], empty[8]
-    u32* s_slot = reinterpret_cast<u32*>(s_bar + 16);                         // [NSLOT][RB]
-    int* s_cnt = reinterpret_cast<int*>(s_slot + TS_NSLOT * TS_RB);           // [QT]
-    int* s_topn = s_cnt + TS_QT;                                              // [QT]
-    u32* s_np = reinterpret_cast<u32*>(s_topn + TS_QT);                       // [QT]
-    u32* s_visit = s_np + TS_QT;                                              // [QT]
-    float* s_qn = reinterpret_cast<float*>(s_visit + TS_QT);                  // [QT]
-    int* s_any = reinterpret_cast<int*>(s_qn + TS_QT);                        // [2]
-    __shared__ u32 s_tile;
+struct __align__(16) ListEntry {
+    u64 key;
+    u32 pos;
+    u32 pad;
+};
 
-    const u32 bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 8);
+// One quad owns 8 rows x 4 queries = 32 (row, query) pairs; thread `sub` keeps lanes 4*sub..4*sub+3 of every
+// pair's 16-lane accumulator.  Per 16-float chunk a thread issues 4 + 8 LDS.128 and 256 FP32 instructions (L2;
+// 128 for cosine).  128 accumulator registers per thread are why there are exactly 8 math warps (2 per SM
+// sub-partition).
+template <int METRIC>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TileParams tp) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dimp = f.dimp, chunks = f.chunks;
+    const int nsl = (chunks + TS_KC - 1) / TS_KC;
+    const u32 S = (u32)tp.nst;
+    // ---- carve shared memory ----
+    unsigned char* s_stage = smem;                                                     // [S][RB][48] f32
+    float* s_q = reinterpret_cast<float*>(smem + (size_t)S * TS_STAGE_BYTES);           // [QT][dimp]
+    ListEntry* s_list = reinterpret_cast<ListEntry*>(s_q + (size_t)TS_QT * dimp);       // [CWARPS][4][KL]
+    TileInfo* s_info = reinterpret_cast<TileInfo*>(s_list + TS_CWARPS * 4 * TS_KL);     // [2]
+    u64* s_bar = reinterpret_cast<u64*>(s_info + 2);                                    // full[8], empty[8], ifull[2], qfull, qempty
+    const u32 bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + TS_MAX_STAGES);
+    const u32 bar_ifull = smem_u32(s_bar + 2 * TS_MAX_STAGES), bar_qfull = bar_ifull + 16, bar_qempty = bar_ifull + 24;
+
     if (tid == 0) {
-        for (int i = 0; i < tp.nst; ++i) {
-            mbar_init(bar_full + 8 * i, TS_THREADS / 32);   // one arrive.expect_tx per warp
-            mbar_init(bar_empty + 8 * i, TS_THREADS / 32);
+        for (u32 i = 0; i < S; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, TS_CWARPS);
         }
-        s_any[0] = s_any[1] = 0;
+        mbar_init(bar_ifull, 1);
+        mbar_init(bar_ifull + 8, 1);
+        mbar_init(bar_qfull, 1);
+        mbar_init(bar_qempty, TS_CWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    u32 cbuf = 0, cph = 0;  // consumer ring cursor: buffer and phase parity (stage = one K slice of one row block)
-    u32 pbuf = 0, pph = 0;  // producer ring cursor (runs nst - 1 stages ahead)
-    u32 bc0 = 0;  // row blocks processed before this tile (slot table ring)
-    u32 rnd = 0;  // push rounds so far (parity of the retry flag)
-    const int cb = tp.P - tp.kcap;
-    const int chunks = f.chunks;
-    const int nsl = (chunks + tp.kc - 1) / tp.kc;
-    const int g = warp >> 1, qd = lane >> 2, sub = lane & 3;
-    const int rg = (warp & 1) * 8 + qd;  // row group: rows i * 16 + rg, i = 0..7
-    const int pq = g * 4 + sub;          // the query whose 8 candidates this thread owns
-
-    for (;;) {
-        __syncthreads();  // previous tile fully retired (top lists written out, shared state reusable)
-        if (tid == 0) s_tile = atomicAdd(tp.tile_counter, 1u);
-        __syncthreads();
-        const u32 tile = s_tile;
-        if (tile >= *tp.ntiles) break;
-        const u32 leaf = tp.tile_leaf[tile], first = tp.tile_first[tile], nqt = tp.tile_count[tile];
-        const u32 L = f.leaf_len[leaf];
-        const long long moff = f.leaf_off[leaf];
-        const u32 nblocks = (L + TS_RB - 1) / TS_RB;
-        const u32 total_st = nblocks * (u32)nsl;
-
-        if (tid < TS_QT) {
-            const bool on = tid < (int)nqt;
-            const u32 v = on ? tp.order[first + tid] : 0u;
-            s_visit[tid] = v;
-            s_np[tid] = on ? tp.v_np[v] : 0u;
-            s_thr[tid] = ZB_SENTINEL;
-            s_cnt[tid] = 0;
-            s_topn[tid] = 0;
-            s_qn[tid] = (METRIC == 0 && on) ? tp.qnorm[tp.v_q[v]] : 0.f;
-        }
-        // producer role, spread over all 8 warps (TMA small-copy throughput scales with issuing warps: DESIGN.md 5):
-        // lanes 0..15 of warp w copy rows w*16 + lane of the row block, lanes 16..17 copy queries 2w, 2w+1.
-        const int my_row = warp * 16 + lane;          // valid for lane < 16
-        const int my_q = warp * 2 + (lane - 16);      // valid for lane 16, 17
-        const float* qsrc = nullptr;
-        if ((lane == 16 || lane == 17) && my_q < (int)nqt) qsrc = tp.queries + (size_t)tp.v_q[tp.order[first + my_q]] * f.dimp;
-        if (tid == 0) {
+    if (warp >= TS_CWARPS) {
+        // =========================== producer warpgroup: one thread drives TMA ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp != TS_CWARPS || lane != 0) return;
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        const u32 ntiles = *tp.ntiles;
+        u32 n = 0;  // stages issued so far (ring sequence number)
+        u32 tile = atomicAdd(tp.tile_counter, 1u);
+        for (u32 it = 0;; ++it) {
+            TileInfo* inf = s_info + (it & 1);
+            if (tile >= ntiles) {
+                inf->tile = 0xFFFFFFFFu;
+                mbar_arrive(bar_ifull + 8 * (it & 1));
+                break;
+            }
+            const u32 leaf = tp.tile_leaf[tile], first = tp.tile_first[tile], nqt = tp.tile_count[tile];
+            const u32 L = f.leaf_len[leaf];
+            const long long moff = f.leaf_off[leaf];
+            inf->tile = tile; inf->leaf = leaf; inf->first = first; inf->nqt = nqt; inf->L = L; inf->moff = moff;
+            mbar_arrive(bar_ifull + 8 * (it & 1));
+            const u32 nblocks = (L + TS_RB - 1) / TS_RB;
+            const u32 total = nblocks * (u32)nsl;
+            u32 b = 0, sl = 0;
+            auto issue = [&](u32 count) {
+                for (u32 j = 0; j < count; ++j, ++n) {
+                    const u32 buf = n % S;
+                    if (n >= S) mbar_wait(bar_empty + 8 * buf, ((n / S) - 1) & 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * buf, TS_STAGE_BYTES);
+                    tma_2d_g2s(smem_u32(s_stage + (size_t)buf * TS_STAGE_BYTES), &tmap, (int)(sl * TS_SLICE_FLOATS),
+                               (int)(moff + (long long)b * TS_RB), bar_full + 8 * buf);
+                    if (++sl == (u32)nsl) { sl = 0; ++b; }
+                }
+            };
+            // rows of this tile may run ahead into the ring while the math warps still finish the previous tile ...
+            const u32 pre = total < S ? total : S;
+            issue(pre);
+            // ... the resident query block is single-buffered: wait until the previous tile is done with it
+            if (it > 0) mbar_wait(bar_qempty, (it - 1) & 1);
+            mbar_arrive_expect_tx(bar_qfull, nqt * (u32)dimp * 4u);
+            for (u32 q = 0; q < nqt; ++q)
+                bulk_g2s(smem_u32(s_q + (size_t)q * dimp), tp.queries + (size_t)tp.v_q[tp.order[first + q]] * dimp,
+                         (u32)dimp * 4u, bar_qfull);
+            const u32 next_tile = atomicAdd(tp.tile_counter, 1u);
+            issue(total - pre);
             atomicAdd(&tp.stats[0], (u64)nqt);
             atomicAdd(&tp.stats[1], (u64)nqt * L);
-            atomicAdd(&tp.stats[2], (u64)L * (u64)f.dimp * 4ull);
+            atomicAdd(&tp.stats[2], ((u64)L + nqt) * (u64)dimp * 4ull);  // algorithmic bytes: leaf rows once + the tile's queries
+            tile = next_tile;
         }
-        u32 pb = 0, psl = 0;  // next stage to issue: row block, K slice
-        u32 pslot = 0xFFFFFFFFu;
-        auto issue_stage = [&]() {
-            const u32 nrows = min((u32)TS_RB, L - pb * TS_RB);
-            const u32 sbytes = (u32)min(tp.kc, chunks - (int)psl * tp.kc) * 64u;
-            mbar_wait(bar_empty + 8 * pbuf, pph ^ 1);
-            if (psl == 0) {
-                pslot = 0xFFFFFFFFu;
-                if (lane < 16 && (u32)my_row < nrows) {
-                    pslot = f.members[moff + pb * TS_RB + my_row];
-                    s_slot[((bc0 + pb) % TS_NSLOT) * TS_RB + my_row] = pslot;
-                }
-            }
-            const u32 mine = ((pslot != 0xFFFFFFFFu) ? 1u : 0u) + (qsrc ? 1u : 0u);
-            const u32 ncopies = __reduce_add_sync(0xffffffffu, mine);
-            if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * pbuf, ncopies * sbytes);
-            __syncwarp();
-            unsigned char* st = s_stage + (size_t)pbuf * tp.stage_bytes;
-            const u32 fb = bar_full + 8 * pbuf;
-            if (pslot != 0xFFFFFFFFu)
-                bulk_g2s(smem_u32(st + (size_t)my_row * RS), f.rows + (size_t)pslot * f.dimp + psl * tp.kc * 16, sbytes, fb);
-            if (qsrc)
-                bulk_g2s(smem_u32(st + (size_t)TS_RB * RS + (size_t)my_q * slice_bytes_full), qsrc + psl * tp.kc * 16, sbytes, fb);
-            if (++psl == (u32)nsl) { psl = 0; ++pb; }
-            if (++pbuf == (u32)tp.nst) { pbuf = 0; pph ^= 1; }
-        };
-        __syncthreads();  // per-visit state initialised (also orders s_slot reuse)
-        for (u32 j = 0; j + 1 < (u32)tp.nst && j < total_st; ++j) issue_stage();
+        return;
+    }
 
+    // =================================== consumer (math) warps ===================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int g = warp >> 1, half = warp & 1, qd = lane >> 2, sub = lane & 3;
+    const int rg = half * 8 + qd;  // row group: rows i * 16 + rg, i = 0..7
+    ListEntry* my_list = s_list + (size_t)warp * 4 * TS_KL;
+    u32 n = 0;  // stages consumed so far
+    for (u32 it = 0;; ++it) {
+        mbar_wait(bar_ifull + 8 * (it & 1), (it >> 1) & 1);
+        const TileInfo inf = s_info[it & 1];
+        if (inf.tile == 0xFFFFFFFFu) break;
+        const u32 nqt = inf.nqt, L = inf.L;
+        const long long moff = inf.moff;
+        const u32 nblocks = (L + TS_RB - 1) / TS_RB;
         const bool warp_active = (u32)(g * 4) < nqt;  // whole query groups idle on small tiles
-        u32 j = 0;
+        const int nq_mine = warp_active ? min(4, (int)nqt - g * 4) : 0;
+        // my query (slot `sub` of group g): visit, n', reciprocal norm
+        u32 my_visit = 0, my_np = 0;
+        double my_qrinv = 0.0;
+        if (sub < nq_mine) {
+            my_visit = tp.order[inf.first + g * 4 + sub];
+            my_np = tp.v_np[my_visit];
+            if (METRIC == 0) my_qrinv = tp.q_rinv[tp.v_q[my_visit]];
+        }
+        if (warp_active) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) my_list[j * TS_KL + lane] = ListEntry{ZB_SENTINEL, TS_NOPOS, 0u};
+        }
+        __syncwarp();
+        mbar_wait(bar_qfull, it & 1);
+
         for (u32 b = 0; b < nblocks; ++b) {
             const u32 nrows = min((u32)TS_RB, L - b * TS_RB);
+            const u32 base = (u32)(moff + (long long)b * TS_RB);  // position of row 0 of the block
+            // tombstone words covering positions base .. base+127 (at most 5 words), one per lane
+            u32 tw = 0;
+            if (warp_active && lane < 5) tw = tp.bm_tomb[(base >> 5) + lane];
             float4 acc[8][4];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int sl = 0; sl < nsl; ++sl, ++j) {
-                if (j + (u32)tp.nst - 1 < total_st) issue_stage();
-                const u32 buf = cbuf;
-                const int kcs = min(tp.kc, chunks - sl * tp.kc);
-                mbar_wait(bar_full + 8 * buf, cph);
+            for (int sl = 0; sl < nsl; ++sl, ++n) {
+                const u32 buf = n % S;
+                const int kcs = min(TS_KC, chunks - sl * TS_KC);
+                mbar_wait(bar_full + 8 * buf, (n / S) & 1);
                 if (warp_active) {
-                    const unsigned char* st = s_stage + (size_t)buf * tp.stage_bytes;
-                    const float4* rp = reinterpret_cast<const float4*>(st + (size_t)rg * RS) + sub;
-                    const float4* qp = reinterpret_cast<const float4*>(st + (size_t)TS_RB * RS + (size_t)(g * 4) * slice_bytes_full) + sub;
-                    const u32 rstep = RS;  // 16 rows apart, in float4 units: 16 * RS / 16
-                    const u32 qstep = slice_bytes_full / 16u;
-                    for (int c = 0; c < kcs; ++c) {
-                        const float4 q0 = qp[c * 4], q1 = qp[c * 4 + qstep], q2 = qp[c * 4 + 2 * qstep], q3 = qp[c * 4 + 3 * qstep];
+                    const float4* rp = reinterpret_cast<const float4*>(s_stage + (size_t)buf * TS_STAGE_BYTES) + rg * (TS_SLICE_FLOATS / 4) + sub;
+                    const float4* qp = reinterpret_cast<const float4*>(s_q + (size_t)(g * 4) * dimp + sl * TS_SLICE_FLOATS) + sub;
+                    const int qstep = dimp / 4;
+                    constexpr int rstep = 16 * TS_SLICE_FLOATS / 4;  // 16 rows apart, in float4 units
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 r = rp[c * 4 + i * rstep];
-                            if (METRIC == 0) {
-                                fma4(acc[i][0], r, q0); fma4(acc[i][1], r, q1); fma4(acc[i][2], r, q2); fma4(acc[i][3], r, q3);
-                            } else {
-                                l2acc4(acc[i][0], r, q0); l2acc4(acc[i][1], r, q1); l2acc4(acc[i][2], r, q2); l2acc4(acc[i][3], r, q3);
+                    for (int c = 0; c < TS_KC; ++c) {
+                        if (c < kcs) {
+                            const float4 q0 = qp[c * 4], q1 = qp[c * 4 + qstep], q2 = qp[c * 4 + 2 * qstep], q3 = qp[c * 4 + 3 * qstep];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 r = rp[c * 4 + i * rstep];
+                                if (METRIC == 0) {
+                                    fma4(acc[i][0], r, q0); fma4(acc[i][1], r, q1); fma4(acc[i][2], r, q2); fma4(acc[i][3], r, q3);
+                                } else {
+                                    l2acc4(acc[i][0], r, q0); l2acc4(acc[i][1], r, q1); l2acc4(acc[i][2], r, q2); l2acc4(acc[i][3], r, q3);
+                                }
                             }
                         }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
-                if (++cbuf == (u32)tp.nst) { cbuf = 0; cph ^= 1; }
             }
-            // ---- epilogue of the row block: 32 sums per quad; thread `sub` keeps query pq's 8 candidates ----
+            if (!warp_active) continue;
+            // ---- epilogue of the row block: 32 sums per quad; thread `sub` keeps query `sub`'s 8 candidates ----
             u64 keys[8];
-            u32 pend = 0;
-            const u32* slots = s_slot + ((bc0 + b) % TS_NSLOT) * TS_RB;
-            if (warp_active) {
-                const unsigned m = quad_mask();
+            u32 vm = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float s0 = quad_reduce16(acc[i][0], 0xffffffffu), s1 = quad_reduce16(acc[i][1], 0xffffffffu);
+                const float s2 = quad_reduce16(acc[i][2], 0xffffffffu), s3 = quad_reduce16(acc[i][3], 0xffffffffu);
+                const float sum = sub == 0 ? s0 : (sub == 1 ? s1 : (sub == 2 ? s2 : s3));
+                const u32 r = (u32)(i * 16 + rg);
+                keys[i] = ZB_SENTINEL;
+                if (r < nrows && sub < nq_mine) {
+                    if (METRIC == 0) keys[i] = cos_bits_rinv(sum, tp.bm_rinv[base + r], my_qrinv);
+                    else keys[i] = METRIC == 1 ? l2sq_bits(sum) : l2_bits(sum);
+                    vm |= 1u << i;
+                }
+            }
+            // ---- warp-private register top-n': lane l holds the l-th best (key, pos) of (query j, this row half) ----
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nq_mine) break;
+                const int np = (int)__shfl_sync(0xffffffffu, my_np, j);  // lane j has sub == j
+                ListEntry le = my_list[j * TS_KL + lane];
+                u64 Lk = le.key;
+                u32 Lp = le.pos;
+                u64 thr = shfl64(Lk, np - 1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float s0 = quad_reduce16(acc[i][0], m), s1 = quad_reduce16(acc[i][1], m);
-                    const float s2 = quad_reduce16(acc[i][2], m), s3 = quad_reduce16(acc[i][3], m);
-                    const float sum = sub == 0 ? s0 : (sub == 1 ? s1 : (sub == 2 ? s2 : s3));
-                    const u32 r = (u32)(i * 16 + rg);
-                    keys[i] = ZB_SENTINEL;
-                    if (r < nrows && pq < (int)nqt) {
-                        const u32 slot = slots[r];
-                        if (!tomb_test(f.tomb, slot)) {
-                            if (METRIC == 0) keys[i] = cos_bits(sum, f.row_norm[slot], s_qn[pq]);
-                            else keys[i] = METRIC == 1 ? l2sq_bits(sum) : l2_bits(sum);
-                            pend |= 1u << i;
-                        }
+                    const bool has = sub == j && ((vm >> i) & 1u) && keys[i] <= thr;
+                    unsigned m = __ballot_sync(0xffffffffu, has);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const u64 nk = shfl64(keys[i], src);
+                        const u32 npos = base + (u32)(i * 16 + half * 8 + (src >> 2));
+                        const u32 w = __shfl_sync(0xffffffffu, tw, (int)((npos >> 5) - (base >> 5)));
+                        if ((w >> (npos & 31)) & 1u) continue;  // tombstoned (D1)
+                        const bool gt = kp_less(nk, npos, Lk, Lp);
+                        const unsigned mm = __ballot_sync(0xffffffffu, gt);
+                        if (!mm) continue;
+                        const int ins = __ffs(mm) - 1;
+                        if (ins >= np) continue;
+                        const u64 upk = shfl_up64(Lk);
+                        const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
+                        if (lane > ins) { Lk = upk; Lp = upp; }
+                        else if (lane == ins) { Lk = nk; Lp = npos; }
+                        thr = shfl64(Lk, np - 1);
                     }
                 }
+                my_list[j * TS_KL + lane] = ListEntry{Lk, Lp, 0u};
             }
-            // ---- push with retry: filter against the visit's n'-th best, append to its candidate buffer; a full
-            //      buffer is merged (sorted together with the current top list) and the leftovers retried ----
-            const bool last_block = b + 1 == nblocks;
-            for (;;) {
-                if (pend) {
-                    const u64 thr = s_thr[pq];
+            __syncwarp();
+        }
+        // ---- end of tile: release the query block, merge the two row halves, write the visits' top lists ----
+        if (lane == 0) mbar_arrive(bar_qempty);
+        pair_sync(g);  // both halves' lists are final and visible
+        if (warp_active && half == 0) {
+            const ListEntry* other = my_list + 4 * TS_KL;  // warp + 1
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (!((pend >> i) & 1u)) continue;
-                        if (keys[i] > thr) { pend &= ~(1u << i); continue; }
-                        const int pos = atomicAdd(&s_cnt[pq], 1);
-                        if (pos < cb) {
-                            s_top[pq * tp.P + tp.kcap + pos] = Entry{keys[i], f.ord[slots[i * 16 + rg]]};
-                            pend &= ~(1u << i);
-                        }
-                    }
-                    if (pend) s_any[rnd & 1] = 1;
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nq_mine) break;
+                const int np = (int)__shfl_sync(0xffffffffu, my_np, j);
+                const u32 v = __shfl_sync(0xffffffffu, my_visit, j);
+                ListEntry a = my_list[j * TS_KL + lane], bb = other[j * TS_KL + (31 - lane)];
+                u64 k = a.key;
+                u32 p = a.pos;
+                if (kp_less(bb.key, bb.pos, k, p)) { k = bb.key; p = bb.pos; }  // 32 smallest of the union, bitonic
+#pragma unroll
+                for (int x = 16; x >= 1; x >>= 1) {
+                    const u64 ok = shfl_xor64(k, x);
+                    const u32 op = __shfl_xor_sync(0xffffffffu, p, x);
+                    const bool lower = (lane & x) == 0;
+                    const bool other_less = kp_less(ok, op, k, p);
+                    if (lower == other_less) { k = ok; p = op; }
                 }
-                consumer_sync();
-                if (tid == 0) s_any[(rnd + 1) & 1] = 0;
-                for (int jq = warp; jq < (int)nqt; jq += TS_THREADS / 32) {
-                    const int raw = s_cnt[jq];
-                    const int cnt = raw < cb ? raw : cb;
-                    if (cnt == 0 || (!last_block && raw <= cb / 2)) continue;
-                    Entry* reg = s_top + jq * tp.P;
-                    const int topn = s_topn[jq];
-                    for (int i = lane; i < tp.P; i += 32) {
-                        const bool keep = i < topn || (i >= tp.kcap && i < tp.kcap + cnt);
-                        if (!keep) reg[i] = Entry{ZB_SENTINEL, ZB_SENTINEL};
-                    }
-                    __syncwarp();
-                    warp_bitonic(reg, tp.P, lane);
-                    if (lane == 0) {
-                        const int np = (int)s_np[jq];
-                        const int tot = topn + cnt;
-                        const int nt = tot < np ? tot : np;
-                        s_topn[jq] = nt;
-                        s_cnt[jq] = 0;
-                        s_thr[jq] = nt == np ? reg[np - 1].key : ZB_SENTINEL;
-                    }
-                    __syncwarp();
+                const u32 e0 = tp.v_ent_off[v], e1 = tp.v_ent_off[v + 1];
+                if ((u32)lane < e1 - e0) {
+                    Entry e{ZB_SENTINEL, ZB_SENTINEL};
+                    if (lane < np && p != TS_NOPOS) e = Entry{k, f.ord[f.members[p]]};
+                    tp.entries[e0 + lane] = e;
                 }
-                consumer_sync();
-                const int again = s_any[rnd & 1];
-                ++rnd;
-                if (!again) break;
             }
         }
-        // ---- write the visits' top lists (min(n', local live) entries, padded to the visit's slot count) ----
-        for (int jq = warp; jq < (int)nqt; jq += TS_THREADS / 32) {
-            const u32 v = s_visit[jq];
-            const u32 e0 = tp.v_ent_off[v], e1 = tp.v_ent_off[v + 1];
-            const int topn = s_topn[jq];
-            const Entry* reg = s_top + jq * tp.P;
-            for (u32 i = lane; i < e1 - e0; i += 32)
-                tp.entries[e0 + i] = (int)i < topn ? reg[i] : Entry{ZB_SENTINEL, ZB_SENTINEL};
-        }
-        bc0 += nblocks;
+        pair_sync(g);  // lists may be re-initialised for the next tile
     }
 }
 
@@ -369,38 +417,79 @@ __global__ void ts_filltiles_kernel(u32 nleaves, const u32* __restrict__ leaf_co
     }
 }
 
-static size_t ts_smem_bytes(int nst, u32 stage_bytes, int P) {
-    return (size_t)nst * stage_bytes + (size_t)TS_QT * P * sizeof(Entry) + TS_QT * 8 + 16 * 8 +
-           (size_t)TS_NSLOT * TS_RB * 4 + TS_QT * 4 * 5 + 8 + 256;
+// reciprocal norms 1/sqrt(|x|^2) in f64 from the canonical f32 squared norm (one quad per vector)
+__global__ void __launch_bounds__(128) rinv_kernel(const float* __restrict__ x_, u64 n, int dimp, double* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * 32ull + (threadIdx.x >> 2);
+    if (i >= n) return;
+    const int sub = threadIdx.x & 3;
+    const float4* x = reinterpret_cast<const float4*>(x_ + i * dimp);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < dimp / 16; ++c) {
+        float4 v = x[c * 4 + sub];
+        fma4(acc, v, v);
+    }
+    float sum = quad_reduce16(acc, quad_mask());
+    if (sub == 0) out[i] = __ddiv_rn(1.0, __dsqrt_rn((double)sum));
+}
+void launch_rinv(const float* d_x, u64 n, int dimp, double* d_out, cudaStream_t s) {
+    if (!n) return;
+    rinv_kernel<<<(u32)((n + 31) / 32), 128, 0, s>>>(d_x, n, dimp, d_out);
 }
 
-void tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, const float* d_q, const float* d_qnorm, u32 nq, u32 nv, const u32* v_leaf,
-               const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len, u8* v_done, Entry* entries,
-               u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s, u64* tile_visits, u64* tile_pairs,
-               u64* moved_bytes, u32* launches) {
-    *tile_visits = *tile_pairs = *moved_bytes = 0;
-    *launches = 0;
-    if (!nv || !nleaves || top_k > 128) return;
+static size_t ts_smem_bytes(int nst, int dimp) {
+    return (size_t)nst * TS_STAGE_BYTES + (size_t)TS_QT * dimp * 4 + (size_t)TS_CWARPS * 4 * TS_KL * sizeof(ListEntry) +
+           2 * sizeof(TileInfo) + (2 * TS_MAX_STAGES + 4) * 8 + 1024;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        ZB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        ZB_REQUIRE(p && qres == cudaDriverEntryPointSuccess, ZB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp) {
+    CUtensorMap* m = reinterpret_cast<CUtensorMap*>(out_map128);
+    cuuint64_t gdim[2] = {(cuuint64_t)dimp, (cuuint64_t)(positions ? positions : 1)};
+    cuuint64_t gstride[1] = {(cuuint64_t)dimp * 4};
+    cuuint32_t box[2] = {TS_SLICE_FLOATS, TS_RB};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_tiled_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bm_rows, gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ZB_REQUIRE(r == CUDA_SUCCESS, ZB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+}
+
+bool tile_scan_supported(int dimp, u32 top_k) {
+    int dev = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return top_k >= 1 && top_k <= TS_KL && ts_smem_bytes(2, dimp) <= (size_t)max_smem;
+}
+
+void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u32 metric, const float* d_q, const double* d_q_rinv,
+               u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
+               u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s) {
+    ws.launched = false;
+    if (!nv || !nleaves || !tile_scan_supported(f.dimp, top_k)) return;
     const u32 tq = tile_queries >= 1 && tile_queries <= TS_QT ? tile_queries : TS_QT;
-    // per-query top-k region: kcap + candidate buffer, power of two
-    int kcap = 16, P = 64;
-    if (top_k > 16) { kcap = 32; P = 128; }
-    if (top_k > 32) { kcap = 128; P = 256; }
-    // K slice: up to 6 chunks (384 B per row slice); rows of a stage are padded so that adjacent rows fall into
-    // different halves of the 32 banks (two quads share one LDS.128 phase).
-    const int kc = f.chunks < 6 ? f.chunks : 6;
-    const u32 slice = (u32)kc * 64u;
-    const u32 row_stride = slice + ((slice % 128u) == 0 ? 64u : 0u);
-    const u32 stage_bytes = TS_RB * row_stride + TS_QT * slice;
     int dev = 0, max_smem = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int nst = 0;
-    for (int cand = 6; cand >= 2; --cand)
-        if (ts_smem_bytes(cand, stage_bytes, P) <= (size_t)max_smem) { nst = cand; break; }
+    for (int cand = TS_MAX_STAGES; cand >= 2; --cand)
+        if (ts_smem_bytes(cand, f.dimp) <= (size_t)max_smem) { nst = cand; break; }
     if (!nst) return;
-    const size_t smem = ts_smem_bytes(nst, stage_bytes, P);
+    const size_t smem = ts_smem_bytes(nst, f.dimp);
 
     ws.leaf_count.ensure(nleaves + 1);
     ws.leaf_start.ensure(nleaves + 1);
@@ -442,33 +531,39 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, const float* 
     tp.v_ent_off = v_ent_off;
     tp.entries = entries;
     tp.queries = d_q;
-    tp.qnorm = d_qnorm;
+    tp.q_rinv = d_q_rinv;
+    tp.bm_rinv = bm.rinv;
+    tp.bm_tomb = bm.tomb;
     tp.stats = reinterpret_cast<u64*>(ws.counters.p + 4);
     tp.nst = nst;
-    tp.P = P;
-    tp.kcap = kcap;
-    tp.kc = kc;
-    tp.row_stride = row_stride;
-    tp.stage_bytes = stage_bytes;
+    const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(bm.tmap);
     const int grid = sms;
     if (metric == 0) {
         ZB_CUDA(cudaFuncSetAttribute(tile_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tile_scan_kernel<0><<<grid, TS_THREADS, smem, s>>>(f, tp);
+        tile_scan_kernel<0><<<grid, TS_THREADS, smem, s>>>(tmap, f, tp);
     } else if (metric == 1) {
         ZB_CUDA(cudaFuncSetAttribute(tile_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tile_scan_kernel<1><<<grid, TS_THREADS, smem, s>>>(f, tp);
+        tile_scan_kernel<1><<<grid, TS_THREADS, smem, s>>>(tmap, f, tp);
     } else {
         ZB_CUDA(cudaFuncSetAttribute(tile_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tile_scan_kernel<2><<<grid, TS_THREADS, smem, s>>>(f, tp);
+        tile_scan_kernel<2><<<grid, TS_THREADS, smem, s>>>(tmap, f, tp);
     }
     ZB_CUDA(cudaGetLastError());
+    ws.launched = true;
+    ws.launches = 7;
+}
+
+// Statistics of the last tile_scan launch (visits, scored pairs, bytes asked of HBM by design); call after the
+// stream has been synchronised.
+void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes) {
+    *tile_visits = *tile_pairs = *moved_bytes = 0;
+    if (!ws.launched) return;
     u64 h[3] = {0, 0, 0};
-    ZB_CUDA(cudaMemcpyAsync(h, tp.stats, 24, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaMemcpyAsync(h, reinterpret_cast<u64*>(ws.counters.p + 4), 24, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
     *tile_visits = h[0];
     *tile_pairs = h[1];
     *moved_bytes = h[2];
-    *launches = 7;
 }
 
 }  // namespace zb

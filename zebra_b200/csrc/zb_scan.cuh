@@ -9,15 +9,35 @@ struct ScanWorkspace {
     DBuf<u32> leaf_count, leaf_start, leaf_cursor, tile_per_leaf, tile_start, order, tile_leaf, tile_first, tile_cnt;
     DBuf<u32> counters;
     DBuf<u8> tmp;
+    bool launched = false;
+    u32 launches = 0;
 };
+
+// Device view of the bucket-major store: position p of the forest's member array holds a copy of row members[p],
+// so every leaf is one contiguous [len][dimp] block (the on-device replacement of the reference's per-bucket
+// storage on the search path).
+struct BucketMajor {
+    const float* rows = nullptr;    // [positions][dimp]
+    const double* rinv = nullptr;   // [positions] 1/sqrt(|row|^2), f64 (cosine only)
+    const u32* tomb = nullptr;      // bit per position
+    const void* tmap = nullptr;     // host copy of the CUtensorMap (128 bytes) over `rows`, box = 48 floats x 128 rows
+    u64 positions = 0;
+};
+
+// Encodes the 2-D tensor map of the bucket-major store into out_map128 (128 bytes, 64-byte aligned).
+void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp);
+// True when the tile kernel can serve this shape (top_k <= 32, query block + ring fit in shared memory).
+bool tile_scan_supported(int dimp, u32 top_k);
+void launch_rinv(const float* d_x, u64 n, int dimp, double* d_out, cudaStream_t s);
 
 // Handles every visit whose leaf holds at least `min_rows` rows: groups those visits by leaf, and for each
 // (leaf, tile of <= tile_queries queries) streams the leaf's rows once through shared memory, scores them
 // against all queries of the tile in the canonical order and keeps each visit's top-n' on chip.  Handled
 // visits get v_done = 1, v_pair_len = 0 and their entries written; the rest is left to the generic path.
-void tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, const float* d_q, const float* d_qnorm, u32 nq, u32 nv, const u32* v_leaf,
-               const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len, u8* v_done, Entry* entries,
-               u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s, u64* tile_visits, u64* tile_pairs,
-               u64* moved_bytes, u32* launches);
+// Asynchronous on `s`; tile_scan_stats reads the counters back (and synchronises).
+void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u32 metric, const float* d_q, const double* d_q_rinv,
+               u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
+               u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s);
+void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes);
 
 }  // namespace zb

@@ -109,6 +109,42 @@ __device__ __forceinline__ u64 shfl_xor64(u64 v, int m) {
 // ascending), so ties in distance are broken exactly like Entry order (D3).
 __device__ __forceinline__ bool kp_less(u64 ka, u32 pa, u64 kb, u32 pb) { return ka < kb || (ka == kb && pa < pb); }
 
+// Packed FP32 (sm_100 FFMA2 / FADD2): two IEEE-rounded f32 operations per instruction, bit-identical to the scalar
+// __fmaf_rn / __fsub_rn forms of zb_device.cuh but half the issue slots, which is what lets one math warp per SM
+// sub-partition keep the FMA pipe busy.
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void fma4_x2(float4& acc, const float4& a, const float4& b) {
+    u64 c0 = pk2(acc.x, acc.y), c1 = pk2(acc.z, acc.w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c0) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c1) : "l"(pk2(a.z, a.w)), "l"(pk2(b.z, b.w)));
+    upk2(c0, acc.x, acc.y);
+    upk2(c1, acc.z, acc.w);
+}
+__device__ __forceinline__ void l2acc4_x2(float4& acc, const float4& a, const float4& b) {
+    u64 c0 = pk2(acc.x, acc.y), c1 = pk2(acc.z, acc.w), d0, d1;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d0) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d1) : "l"(pk2(a.z, a.w)), "l"(pk2(b.z, b.w)));
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(c0) : "l"(d0));
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(c1) : "l"(d1));
+    upk2(c0, acc.x, acc.y);
+    upk2(c1, acc.z, acc.w);
+}
+__device__ __forceinline__ float4 add4_xor(const float4& a, const float4& b, int m) {  // a + shfl_xor(b, m), componentwise
+    return make_float4(__fadd_rn(a.x, __shfl_xor_sync(0xffffffffu, b.x, m)), __fadd_rn(a.y, __shfl_xor_sync(0xffffffffu, b.y, m)),
+                       __fadd_rn(a.z, __shfl_xor_sync(0xffffffffu, b.z, m)), __fadd_rn(a.w, __shfl_xor_sync(0xffffffffu, b.w, m)));
+}
+__device__ __forceinline__ u64 sel8(const u64 (&k)[8], int i) {
+    u64 r = k[0];
+#pragma unroll
+    for (int t = 1; t < 8; ++t) r = i == t ? k[t] : r;
+    return r;
+}
+
 // Cosine epilogue from precomputed reciprocal norms: the operation order of cos_bits (zb_device.cuh) with
 // ra = 1/sqrt(a2), rb = 1/sqrt(b2) hoisted (ra is +inf exactly when a2 == 0).
 __device__ __forceinline__ u64 cos_bits_rinv(float ab_, double ra, double rb) {
@@ -204,9 +240,17 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
             // ... the resident query block is single-buffered: wait until the previous tile is done with it
             if (it > 0) mbar_wait(bar_qempty, (it - 1) & 1);
             mbar_arrive_expect_tx(bar_qfull, nqt * (u32)dimp * 4u);
-            for (u32 q = 0; q < nqt; ++q)
-                bulk_g2s(smem_u32(s_q + (size_t)q * dimp), tp.queries + (size_t)tp.v_q[tp.order[first + q]] * dimp,
-                         (u32)dimp * 4u, bar_qfull);
+            for (u32 q0 = 0; q0 < nqt; q0 += 8) {  // address loads batched (8 independent chains), then the copies
+                u32 qi[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) qi[j] = q0 + j < nqt ? tp.order[first + q0 + j] : 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) qi[j] = q0 + j < nqt ? tp.v_q[qi[j]] : 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (q0 + j < nqt)
+                        bulk_g2s(smem_u32(s_q + (size_t)(q0 + j) * dimp), tp.queries + (size_t)qi[j] * dimp, (u32)dimp * 4u, bar_qfull);
+            }
             const u32 next_tile = atomicAdd(tp.tile_counter, 1u);
             issue(total - pre);
             atomicAdd(&tp.stats[0], (u64)nqt);
@@ -222,6 +266,14 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
     const int g = warp >> 1, half = warp & 1, qd = lane >> 2, sub = lane & 3;
     const int rg = half * 8 + qd;  // row group: rows i * 16 + rg, i = 0..7
     ListEntry* my_list = s_list + (size_t)warp * 4 * TS_KL;
+    const int qstep = dimp / 4;
+    // Accumulator k of a thread belongs to query (k ^ sub) of the group: the quad's cross-thread folds then pair
+    // registers with static indices (no selects), and thread `sub` ends up owning query `sub`.
+    const float4* qb = reinterpret_cast<const float4*>(s_q + (size_t)(g * 4) * dimp) + sub;
+    const float4* qp0 = qb + (0 ^ sub) * qstep;
+    const float4* qp1 = qb + (1 ^ sub) * qstep;
+    const float4* qp2 = qb + (2 ^ sub) * qstep;
+    const float4* qp3 = qb + (3 ^ sub) * qstep;
     u32 n = 0;  // stages consumed so far
     for (u32 it = 0;; ++it) {
         mbar_wait(bar_ifull + 8 * (it & 1), (it >> 1) & 1);
@@ -244,6 +296,7 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
 #pragma unroll
             for (int j = 0; j < 4; ++j) my_list[j * TS_KL + lane] = ListEntry{ZB_SENTINEL, TS_NOPOS, 0u};
         }
+        u64 mythr = ZB_SENTINEL;  // key of the n'-th best of MY query so far (filter)
         __syncwarp();
         mbar_wait(bar_qfull, it & 1);
 
@@ -264,21 +317,18 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
                 mbar_wait(bar_full + 8 * buf, (n / S) & 1);
                 if (warp_active) {
                     const float4* rp = reinterpret_cast<const float4*>(s_stage + (size_t)buf * TS_STAGE_BYTES) + rg * (TS_SLICE_FLOATS / 4) + sub;
-                    const float4* qp = reinterpret_cast<const float4*>(s_q + (size_t)(g * 4) * dimp + sl * TS_SLICE_FLOATS) + sub;
-                    const int qstep = dimp / 4;
+                    const int qo = sl * (TS_SLICE_FLOATS / 4);
                     constexpr int rstep = 16 * TS_SLICE_FLOATS / 4;  // 16 rows apart, in float4 units
+#pragma unroll 1
+                    for (int c = 0; c < kcs; ++c) {
+                        const float4 q0 = qp0[qo + c * 4], q1 = qp1[qo + c * 4], q2 = qp2[qo + c * 4], q3 = qp3[qo + c * 4];
 #pragma unroll
-                    for (int c = 0; c < TS_KC; ++c) {
-                        if (c < kcs) {
-                            const float4 q0 = qp[c * 4], q1 = qp[c * 4 + qstep], q2 = qp[c * 4 + 2 * qstep], q3 = qp[c * 4 + 3 * qstep];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 r = rp[c * 4 + i * rstep];
-                                if (METRIC == 0) {
-                                    fma4(acc[i][0], r, q0); fma4(acc[i][1], r, q1); fma4(acc[i][2], r, q2); fma4(acc[i][3], r, q3);
-                                } else {
-                                    l2acc4(acc[i][0], r, q0); l2acc4(acc[i][1], r, q1); l2acc4(acc[i][2], r, q2); l2acc4(acc[i][3], r, q3);
-                                }
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 r = rp[c * 4 + i * rstep];
+                            if (METRIC == 0) {
+                                fma4_x2(acc[i][0], r, q0); fma4_x2(acc[i][1], r, q1); fma4_x2(acc[i][2], r, q2); fma4_x2(acc[i][3], r, q3);
+                            } else {
+                                l2acc4_x2(acc[i][0], r, q0); l2acc4_x2(acc[i][1], r, q1); l2acc4_x2(acc[i][2], r, q2); l2acc4_x2(acc[i][3], r, q3);
                             }
                         }
                     }
@@ -287,66 +337,81 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
                 if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
             }
             if (!warp_active) continue;
-            // ---- epilogue of the row block: 32 sums per quad; thread `sub` keeps query `sub`'s 8 candidates ----
+            // ---- epilogue of the row block: fold the quad's partial sums (canonical tree: lane j + lane j+8, then
+            //      + 4, then (r0+r1)+(r2+r3)); thread `sub` finishes query `sub`'s 8 candidates ----
             u64 keys[8];
-            u32 vm = 0;
+            u32 hm = 0;  // candidates that pass the filter
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float s0 = quad_reduce16(acc[i][0], 0xffffffffu), s1 = quad_reduce16(acc[i][1], 0xffffffffu);
-                const float s2 = quad_reduce16(acc[i][2], 0xffffffffu), s3 = quad_reduce16(acc[i][3], 0xffffffffu);
-                const float sum = sub == 0 ? s0 : (sub == 1 ? s1 : (sub == 2 ? s2 : s3));
+                const float4 x0 = add4_xor(acc[i][0], acc[i][2], 2);
+                const float4 x1 = add4_xor(acc[i][1], acc[i][3], 2);
+                const float4 y = add4_xor(x0, x1, 1);
+                const float sum = __fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w));
                 const u32 r = (u32)(i * 16 + rg);
                 keys[i] = ZB_SENTINEL;
                 if (r < nrows && sub < nq_mine) {
                     if (METRIC == 0) keys[i] = cos_bits_rinv(sum, tp.bm_rinv[base + r], my_qrinv);
                     else keys[i] = METRIC == 1 ? l2sq_bits(sum) : l2_bits(sum);
-                    vm |= 1u << i;
+                    if (keys[i] <= mythr) hm |= 1u << i;
                 }
             }
-            // ---- warp-private register top-n': lane l holds the l-th best (key, pos) of (query j, this row half) ----
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j >= nq_mine) break;
-                const int np = (int)__shfl_sync(0xffffffffu, my_np, j);  // lane j has sub == j
-                ListEntry le = my_list[j * TS_KL + lane];
-                u64 Lk = le.key;
-                u32 Lp = le.pos;
-                u64 thr = shfl64(Lk, np - 1);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool has = sub == j && ((vm >> i) & 1u) && keys[i] <= thr;
-                    unsigned m = __ballot_sync(0xffffffffu, has);
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const u64 nk = shfl64(keys[i], src);
+            // ---- warp-private register top-n': lane l holds the l-th best (key, pos) of (query j, this row half).
+            //      Most blocks have no candidate under the filter: one ballot and out. ----
+            unsigned anym = __ballot_sync(0xffffffffu, hm != 0);
+            if (anym) {
+#pragma unroll 1
+                for (int j = 0; j < nq_mine; ++j) {
+                    const unsigned qmask = 0x11111111u << j;  // lanes whose query is j
+                    unsigned mj = anym & qmask;
+                    if (!mj) continue;
+                    const int np = (int)__shfl_sync(0xffffffffu, my_np, j);
+                    ListEntry le = my_list[j * TS_KL + lane];
+                    u64 Lk = le.key;
+                    u32 Lp = le.pos;
+                    u64 thr = shfl64(Lk, np - 1);
+                    while (mj) {
+                        const int src = __ffs(mj) - 1;
+                        const int myi = hm ? __ffs(hm) - 1 : 0;
+                        const u64 mykey = sel8(keys, myi);
+                        const int i = __shfl_sync(0xffffffffu, myi, src);
+                        const u64 nk = shfl64(mykey, src);
+                        if (lane == src) hm &= hm - 1;
                         const u32 npos = base + (u32)(i * 16 + half * 8 + (src >> 2));
                         const u32 w = __shfl_sync(0xffffffffu, tw, (int)((npos >> 5) - (base >> 5)));
-                        if ((w >> (npos & 31)) & 1u) continue;  // tombstoned (D1)
-                        const bool gt = kp_less(nk, npos, Lk, Lp);
-                        const unsigned mm = __ballot_sync(0xffffffffu, gt);
-                        if (!mm) continue;
-                        const int ins = __ffs(mm) - 1;
-                        if (ins >= np) continue;
-                        const u64 upk = shfl_up64(Lk);
-                        const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
-                        if (lane > ins) { Lk = upk; Lp = upp; }
-                        else if (lane == ins) { Lk = nk; Lp = npos; }
-                        thr = shfl64(Lk, np - 1);
+                        bool changed = false;
+                        if (!((w >> (npos & 31)) & 1u)) {  // not tombstoned (D1)
+                            const unsigned mm = __ballot_sync(0xffffffffu, kp_less(nk, npos, Lk, Lp));
+                            const int ins = mm ? __ffs(mm) - 1 : 32;
+                            if (ins < np) {
+                                const u64 upk = shfl_up64(Lk);
+                                const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
+                                if (lane > ins) { Lk = upk; Lp = upp; }
+                                else if (lane == ins) { Lk = nk; Lp = npos; }
+                                const u64 nthr = shfl64(Lk, np - 1);
+                                changed = nthr != thr;
+                                thr = nthr;
+                            }
+                        }
+                        if (changed && (qmask >> lane) & 1u) {  // the filter tightened: drop what no longer passes
+#pragma unroll
+                            for (int t = 0; t < 8; ++t)
+                                if (keys[t] > thr) hm &= ~(1u << t);
+                        }
+                        mj = __ballot_sync(0xffffffffu, hm != 0) & qmask;
                     }
+                    my_list[j * TS_KL + lane] = ListEntry{Lk, Lp, 0u};
+                    if ((qmask >> lane) & 1u) mythr = thr;
                 }
-                my_list[j * TS_KL + lane] = ListEntry{Lk, Lp, 0u};
+                __syncwarp();
             }
-            __syncwarp();
         }
         // ---- end of tile: release the query block, merge the two row halves, write the visits' top lists ----
         if (lane == 0) mbar_arrive(bar_qempty);
         pair_sync(g);  // both halves' lists are final and visible
         if (warp_active && half == 0) {
             const ListEntry* other = my_list + 4 * TS_KL;  // warp + 1
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j >= nq_mine) break;
+#pragma unroll 1
+            for (int j = 0; j < nq_mine; ++j) {
                 const int np = (int)__shfl_sync(0xffffffffu, my_np, j);
                 const u32 v = __shfl_sync(0xffffffffu, my_visit, j);
                 ListEntry a = my_list[j * TS_KL + lane], bb = other[j * TS_KL + (31 - lane)];

@@ -33,6 +33,17 @@ namespace zb {
 #define TS_KL 32            // list length of the register top-n' (one entry per lane)
 #define TS_NOPOS 0xFFFFFFFFu
 
+// Phase timing of the math warps (debug builds only: make EXTRA=-DZB_SCAN_TIMING): cycles spent waiting for the
+// tile info / queries, waiting for row stages, in the FP32 loop, in the fold + key epilogue, in list insertion and in
+// the end-of-tile merge, summed over the ACTIVE math warps (slot 7 counts idle-warp time), written to stats[8..].
+#ifdef ZB_SCAN_TIMING
+#define TS_T(var) const long long var = clock64()
+#define TS_ACC(slot, t0, t1) tacc[slot] += (t1) - (t0)
+#else
+#define TS_T(var)
+#define TS_ACC(slot, t0, t1)
+#endif
+
 struct TileInfo {
     u32 tile, leaf, first, nqt, L, pad;
     long long moff;
@@ -54,6 +65,8 @@ struct TileParams {
     const double* bm_rinv;  // [positions] 1/sqrt(|row|^2) in f64 (cosine)
     const u32* bm_tomb;     // bit per position
     u64* stats;             // [0] visits, [1] pairs, [2] moved bytes
+    u64* gthr;              // [nq] per-query bound shared by all of the query's visits: min over full lists of their n'-th key
+    u32 top_k;
     int nst;                // ring depth
 };
 
@@ -274,8 +287,12 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
     const float4* qp1 = qb + (1 ^ sub) * qstep;
     const float4* qp2 = qb + (2 ^ sub) * qstep;
     const float4* qp3 = qb + (3 ^ sub) * qstep;
+#ifdef ZB_SCAN_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     u32 n = 0;  // stages consumed so far
     for (u32 it = 0;; ++it) {
+        TS_T(t_tile0);
         mbar_wait(bar_ifull + 8 * (it & 1), (it >> 1) & 1);
         const TileInfo inf = s_info[it & 1];
         if (inf.tile == 0xFFFFFFFFu) break;
@@ -285,12 +302,13 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
         const bool warp_active = (u32)(g * 4) < nqt;  // whole query groups idle on small tiles
         const int nq_mine = warp_active ? min(4, (int)nqt - g * 4) : 0;
         // my query (slot `sub` of group g): visit, n', reciprocal norm
-        u32 my_visit = 0, my_np = 0;
+        u32 my_visit = 0, my_np = 0, my_q = 0;
         double my_qrinv = 0.0;
         if (sub < nq_mine) {
             my_visit = tp.order[inf.first + g * 4 + sub];
             my_np = tp.v_np[my_visit];
-            if (METRIC == 0) my_qrinv = tp.q_rinv[tp.v_q[my_visit]];
+            my_q = tp.v_q[my_visit];
+            if (METRIC == 0) my_qrinv = tp.q_rinv[my_q];
         }
         if (warp_active) {
 #pragma unroll
@@ -299,6 +317,8 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
         u64 mythr = ZB_SENTINEL;  // key of the n'-th best of MY query so far (filter)
         __syncwarp();
         mbar_wait(bar_qfull, it & 1);
+        TS_T(t_tile1);
+        TS_ACC(warp_active ? 0 : 7, t_tile0, t_tile1);
 
         for (u32 b = 0; b < nblocks; ++b) {
             const u32 nrows = min((u32)TS_RB, L - b * TS_RB);
@@ -306,6 +326,11 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
             // tombstone words covering positions base .. base+127 (at most 5 words), one per lane
             u32 tw = 0;
             if (warp_active && lane < 5) tw = tp.bm_tomb[(base >> 5) + lane];
+            // Bound shared by every visit of my query (other trees, other row half, other SMs): k distinct candidates
+            // at or below it already exist, so anything above it cannot reach the query's final top-k.  Stale reads
+            // only cost extra candidates.
+            u64 gbound = ZB_SENTINEL;
+            if (sub < nq_mine) gbound = __ldcg(tp.gthr + my_q);
             float4 acc[8][4];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -314,7 +339,10 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
             for (int sl = 0; sl < nsl; ++sl, ++n) {
                 const u32 buf = n % S;
                 const int kcs = min(TS_KC, chunks - sl * TS_KC);
+                TS_T(t_w0);
                 mbar_wait(bar_full + 8 * buf, (n / S) & 1);
+                TS_T(t_w1);
+                TS_ACC(warp_active ? 1 : 7, t_w0, t_w1);
                 if (warp_active) {
                     const float4* rp = reinterpret_cast<const float4*>(s_stage + (size_t)buf * TS_STAGE_BYTES) + rg * (TS_SLICE_FLOATS / 4) + sub;
                     const int qo = sl * (TS_SLICE_FLOATS / 4);
@@ -335,10 +363,14 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
+                TS_T(t_w2);
+                TS_ACC(warp_active ? 2 : 7, t_w1, t_w2);
             }
             if (!warp_active) continue;
+            TS_T(t_e0);
             // ---- epilogue of the row block: fold the quad's partial sums (canonical tree: lane j + lane j+8, then
             //      + 4, then (r0+r1)+(r2+r3)); thread `sub` finishes query `sub`'s 8 candidates ----
+            if (gbound < mythr) mythr = gbound;
             u64 keys[8];
             u32 hm = 0;  // candidates that pass the filter
 #pragma unroll
@@ -358,53 +390,52 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
             // ---- warp-private register top-n': lane l holds the l-th best (key, pos) of (query j, this row half).
             //      Most blocks have no candidate under the filter: one ballot and out. ----
             unsigned anym = __ballot_sync(0xffffffffu, hm != 0);
+            TS_T(t_e1);
+            TS_ACC(3, t_e0, t_e1);
             if (anym) {
 #pragma unroll 1
                 for (int j = 0; j < nq_mine; ++j) {
                     const unsigned qmask = 0x11111111u << j;  // lanes whose query is j
-                    unsigned mj = anym & qmask;
-                    if (!mj) continue;
+                    if (!(anym & qmask)) continue;
+                    const bool mine = (qmask >> lane) & 1u;
                     const int np = (int)__shfl_sync(0xffffffffu, my_np, j);
                     ListEntry le = my_list[j * TS_KL + lane];
                     u64 Lk = le.key;
                     u32 Lp = le.pos;
-                    u64 thr = shfl64(Lk, np - 1);
-                    while (mj) {
-                        const int src = __ffs(mj) - 1;
-                        const int myi = hm ? __ffs(hm) - 1 : 0;
-                        const u64 mykey = sel8(keys, myi);
-                        const int i = __shfl_sync(0xffffffffu, myi, src);
-                        const u64 nk = shfl64(mykey, src);
-                        if (lane == src) hm &= hm - 1;
-                        const u32 npos = base + (u32)(i * 16 + half * 8 + (src >> 2));
-                        const u32 w = __shfl_sync(0xffffffffu, tw, (int)((npos >> 5) - (base >> 5)));
-                        bool changed = false;
-                        if (!((w >> (npos & 31)) & 1u)) {  // not tombstoned (D1)
+                    u64 thr = shfl64(mythr, j);  // lane j has sub == j: the list's n'-th key or the shared bound
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        unsigned m = __ballot_sync(0xffffffffu, mine && ((hm >> i) & 1u) && keys[i] <= thr);
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const u64 nk = shfl64(keys[i], src);
+                            if (nk > thr) continue;  // the filter tightened since the ballot
+                            const u32 npos = base + (u32)(i * 16 + half * 8 + (src >> 2));
+                            const u32 w = __shfl_sync(0xffffffffu, tw, (int)((npos >> 5) - (base >> 5)));
+                            if ((w >> (npos & 31)) & 1u) continue;  // tombstoned (D1)
                             const unsigned mm = __ballot_sync(0xffffffffu, kp_less(nk, npos, Lk, Lp));
                             const int ins = mm ? __ffs(mm) - 1 : 32;
-                            if (ins < np) {
-                                const u64 upk = shfl_up64(Lk);
-                                const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
-                                if (lane > ins) { Lk = upk; Lp = upp; }
-                                else if (lane == ins) { Lk = nk; Lp = npos; }
-                                const u64 nthr = shfl64(Lk, np - 1);
-                                changed = nthr != thr;
-                                thr = nthr;
-                            }
+                            if (ins >= np) continue;
+                            const u64 upk = shfl_up64(Lk);
+                            const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
+                            if (lane > ins) { Lk = upk; Lp = upp; }
+                            else if (lane == ins) { Lk = nk; Lp = npos; }
+                            const u64 lk = shfl64(Lk, np - 1);
+                            if (lk < thr) thr = lk;
                         }
-                        if (changed && (qmask >> lane) & 1u) {  // the filter tightened: drop what no longer passes
-#pragma unroll
-                            for (int t = 0; t < 8; ++t)
-                                if (keys[t] > thr) hm &= ~(1u << t);
-                        }
-                        mj = __ballot_sync(0xffffffffu, hm != 0) & qmask;
                     }
                     my_list[j * TS_KL + lane] = ListEntry{Lk, Lp, 0u};
-                    if ((qmask >> lane) & 1u) mythr = thr;
+                    if (mine) mythr = thr;
+                    // publish: a full list of n' == top_k distinct rows bounds the query's final k-th best
+                    if (lane == j && np == (int)tp.top_k && thr < gbound) atomicMin(tp.gthr + my_q, thr);
                 }
                 __syncwarp();
             }
+            TS_T(t_e2);
+            TS_ACC(4, t_e1, t_e2);
         }
+        TS_T(t_m0);
         // ---- end of tile: release the query block, merge the two row halves, write the visits' top lists ----
         if (lane == 0) mbar_arrive(bar_qempty);
         pair_sync(g);  // both halves' lists are final and visible
@@ -435,7 +466,13 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
             }
         }
         pair_sync(g);  // lists may be re-initialised for the next tile
+        TS_T(t_m1);
+        TS_ACC(warp_active ? 5 : 7, t_m0, t_m1);
     }
+#ifdef ZB_SCAN_TIMING
+    if (lane == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&tp.stats[8 + i], (u64)tacc[i]);
+#endif
 }
 
 // =====================================================================================================
@@ -472,9 +509,9 @@ __global__ void ts_filltiles_kernel(u32 nleaves, const u32* __restrict__ leaf_co
     if (l >= nleaves) return;
     const u32 c = leaf_count[l], ts = tile_start[l];
     if (!c) return;
-    const u32 nt = (c + tq - 1) / tq, base = c / nt, rem = c % nt;   // balanced: tiles differ by at most one query
+    const u32 nt = (c + tq - 1) / tq;   // full tiles first, the remainder last (cost is per started query group)
     for (u32 j = 0, done = 0; j < nt; ++j) {
-        const u32 n = base + (j < rem ? 1u : 0u);
+        const u32 n = c - done < tq ? c - done : tq;
         tile_leaf[ts + j] = l;
         tile_first[ts + j] = leaf_start[l] + done;
         tile_count[ts + j] = n;
@@ -562,14 +599,16 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
     ws.order.ensure(nv);
     ws.tile_leaf.ensure(nv);
     ws.tile_first.ensure(nv);
-    ws.counters.ensure(16);
+    ws.counters.ensure(64);
+    ws.gthr.ensure(nq ? nq : 1);
+    ZB_CUDA(cudaMemsetAsync(ws.gthr.p, 0xFF, (size_t)(nq ? nq : 1) * 8, s));
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const u32*)nullptr, (u32*)nullptr, (long long)(nleaves + 1));
     ws.tmp.ensure(tmp_bytes + 256);
 
     ZB_CUDA(cudaMemsetAsync(ws.leaf_count.p, 0, (size_t)(nleaves + 1) * 4, s));
     ZB_CUDA(cudaMemsetAsync(ws.leaf_cursor.p, 0, (size_t)(nleaves + 1) * 4, s));
-    ZB_CUDA(cudaMemsetAsync(ws.counters.p, 0, 16 * 4, s));
+    ZB_CUDA(cudaMemsetAsync(ws.counters.p, 0, 64 * 4, s));
     const u32 kmax = top_k;
     ts_count_kernel<<<(nv + 255) / 256, 256, 0, s>>>(f, nv, v_leaf, v_np, min_rows, kmax, ws.leaf_count.p);
     cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.leaf_count.p, ws.leaf_start.p, (long long)(nleaves + 1), s);
@@ -600,6 +639,8 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
     tp.bm_rinv = bm.rinv;
     tp.bm_tomb = bm.tomb;
     tp.stats = reinterpret_cast<u64*>(ws.counters.p + 4);
+    tp.gthr = ws.gthr.p;
+    tp.top_k = top_k;
     tp.nst = nst;
     const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(bm.tmap);
     const int grid = sms;
@@ -629,6 +670,12 @@ void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* t
     *tile_visits = h[0];
     *tile_pairs = h[1];
     *moved_bytes = h[2];
+#ifdef ZB_SCAN_TIMING
+    u64 t[8];
+    ZB_CUDA(cudaMemcpy(t, reinterpret_cast<u64*>(ws.counters.p + 4) + 8, 64, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[scan timing, Mcycles summed over math warps] tile-wait %.1f stage-wait %.1f math %.1f fold %.1f insert %.1f merge %.1f idle %.1f\n",
+            t[0] / 1e6, t[1] / 1e6, t[2] / 1e6, t[3] / 1e6, t[4] / 1e6, t[5] / 1e6, t[7] / 1e6);
+#endif
 }
 
 }  // namespace zb

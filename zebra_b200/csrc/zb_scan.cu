@@ -22,13 +22,15 @@
 
 namespace zb {
 
-#define TS_QT 16            // queries per tile (4 query groups of 4)
+#define TS_TEAMS 2          // independent teams per CTA: each streams its own tiles through its own ring
+#define TS_TWARPS 4         // math warps per team (one per SM sub-partition)
+#define TS_QT 8             // queries per tile (2 query groups of 4)
 #define TS_RB 128           // rows per row block (16 row groups of 8, interleaved: row = i * 16 + group)
 #define TS_KC 3             // 16-float chunks per K slice: 192 B row pitch puts adjacent rows in different bank halves
 #define TS_SLICE_FLOATS (TS_KC * 16)
 #define TS_STAGE_BYTES (TS_RB * TS_SLICE_FLOATS * 4)   // 24576
-#define TS_CWARPS 8         // consumer (math) warps
-#define TS_THREADS 384      // 2 math warpgroups + 1 producer warpgroup (its warp 0 drives TMA; registers handed to the math warps)
+#define TS_CWARPS (TS_TEAMS * TS_TWARPS)   // consumer (math) warps
+#define TS_THREADS 384      // 2 math warpgroups (= teams) + 1 producer warpgroup (one TMA-driving warp per team; its registers go to the math warps)
 #define TS_MAX_STAGES 8
 #define TS_KL 32            // list length of the register top-n' (one entry per lane)
 #define TS_NOPOS 0xFFFFFFFFu
@@ -179,10 +181,172 @@ struct __align__(16) ListEntry {
     u32 pad;
 };
 
-// One quad owns 8 rows x 4 queries = 32 (row, query) pairs; thread `sub` keeps lanes 4*sub..4*sub+3 of every
-// pair's 16-lane accumulator.  Per 16-float chunk a thread issues 4 + 8 LDS.128 and 256 FP32 instructions (L2;
-// 128 for cosine).  128 accumulator registers per thread are why there are exactly 8 math warps (2 per SM
-// sub-partition).
+// Shared-memory view and barrier addresses of one CTA.
+struct ScanCtx {
+    unsigned char* s_stage;
+    float* s_q;
+    ListEntry* s_list;
+    u32 bar_full, bar_empty;
+    u32 S;
+    int dimp, chunks, nsl;
+};
+
+// One math warp's share of one tile.  A quad owns NR rows x 4 queries (NR = 8: "wide" warp, 64 of the stage's 128
+// rows; NR = 4: "narrow" warp, 32 rows); thread `sub` keeps lanes 4*sub..4*sub+3 of every pair's 16-lane accumulator.
+// Per 16-float chunk a wide thread issues 4 + 8 LDS.128 and 128 packed FP32 instructions (L2; 64 for cosine).
+// 128 accumulator registers per thread are why there are exactly 8 math warps (2 per SM sub-partition).
+//   g  : query group (queries g*4 .. g*4+3 of the tile)        wr : which row slab of the group this warp scans
+template <int METRIC, int NR>
+__device__ __forceinline__ void scan_tile(const ScanCtx& cx, const ForestView& f, const TileParams& tp, const TileInfo& inf,
+                                          const int g, const int wr, const int warp, const int lane, u32& n,
+                                          u32 my_np, u32 my_q, double my_qrinv, int nq_mine
+#ifdef ZB_SCAN_TIMING
+                                          , long long* tacc
+#endif
+) {
+    constexpr int RSTRIDE = TS_RB / NR;              // rows between a quad's consecutive rows (16 wide, 32 narrow)
+    const int qd = lane >> 2, sub = lane & 3;
+    const int r0 = wr * 8 + qd;                      // rows i * RSTRIDE + r0, i = 0..NR-1
+    const int dimp = cx.dimp, chunks = cx.chunks, nsl = cx.nsl;
+    const u32 S = cx.S, L = inf.L;
+    const u32 nblocks = (L + TS_RB - 1) / TS_RB;
+    ListEntry* my_list = cx.s_list + (size_t)warp * 4 * TS_KL;
+    const int qstep = dimp / 4;
+    // Accumulator k of a thread belongs to query (k ^ sub) of the group: the quad's cross-thread folds then pair
+    // registers with static indices (no selects), and thread `sub` ends up owning query `sub`.
+    const float4* qb = reinterpret_cast<const float4*>(cx.s_q + (size_t)(g * 4) * dimp) + sub;
+    const float4* qp0 = qb + (0 ^ sub) * qstep;
+    const float4* qp1 = qb + (1 ^ sub) * qstep;
+    const float4* qp2 = qb + (2 ^ sub) * qstep;
+    const float4* qp3 = qb + (3 ^ sub) * qstep;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) my_list[j * TS_KL + lane] = ListEntry{ZB_SENTINEL, TS_NOPOS, 0u};
+    u64 mythr = ZB_SENTINEL;  // filter of MY query: the list's n'-th key or the shared bound
+    __syncwarp();
+
+    for (u32 b = 0; b < nblocks; ++b) {
+        const u32 nrows = min((u32)TS_RB, L - b * TS_RB);
+        const u32 base = (u32)(inf.moff + (long long)b * TS_RB);  // position of row 0 of the block
+        // tombstone words covering positions base .. base+127 (at most 5 words), one per lane
+        u32 tw = 0;
+        if (lane < 5) tw = tp.bm_tomb[(base >> 5) + lane];
+        // Bound shared by every visit of my query (other trees, other row slabs, other SMs): k distinct candidates
+        // at or below it already exist, so anything above it cannot reach the query's final top-k.  Stale reads
+        // only cost extra candidates.
+        u64 gbound = ZB_SENTINEL;
+        if (sub < nq_mine) gbound = __ldcg(tp.gthr + my_q);
+        float4 acc[NR][4];
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sl = 0; sl < nsl; ++sl, ++n) {
+            const u32 buf = n % S;
+            const int kcs = min(TS_KC, chunks - sl * TS_KC);
+            TS_T(t_w0);
+            mbar_wait(cx.bar_full + 8 * buf, (n / S) & 1);
+            TS_T(t_w1);
+            TS_ACC(1, t_w0, t_w1);
+            const float4* rp = reinterpret_cast<const float4*>(cx.s_stage + (size_t)buf * TS_STAGE_BYTES) + r0 * (TS_SLICE_FLOATS / 4) + sub;
+            const int qo = sl * (TS_SLICE_FLOATS / 4);
+            constexpr int rstep = RSTRIDE * TS_SLICE_FLOATS / 4;  // RSTRIDE rows apart, in float4 units
+#pragma unroll 1
+            for (int c = 0; c < kcs; ++c) {
+                const float4 q0 = qp0[qo + c * 4], q1 = qp1[qo + c * 4], q2 = qp2[qo + c * 4], q3 = qp3[qo + c * 4];
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const float4 r = rp[c * 4 + i * rstep];
+                    if (METRIC == 0) {
+                        fma4_x2(acc[i][0], r, q0); fma4_x2(acc[i][1], r, q1); fma4_x2(acc[i][2], r, q2); fma4_x2(acc[i][3], r, q3);
+                    } else {
+                        l2acc4_x2(acc[i][0], r, q0); l2acc4_x2(acc[i][1], r, q1); l2acc4_x2(acc[i][2], r, q2); l2acc4_x2(acc[i][3], r, q3);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cx.bar_empty + 8 * buf);
+            TS_T(t_w2);
+            TS_ACC(2, t_w1, t_w2);
+        }
+        TS_T(t_e0);
+        // ---- epilogue of the row block: fold the quad's partial sums (canonical tree: lane j + lane j+8, then
+        //      + 4, then (r0+r1)+(r2+r3)); thread `sub` finishes query `sub`'s NR candidates ----
+        if (gbound < mythr) mythr = gbound;
+        u64 keys[NR];
+        u32 hm = 0;  // candidates that pass the filter
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const float4 x0 = add4_xor(acc[i][0], acc[i][2], 2);
+            const float4 x1 = add4_xor(acc[i][1], acc[i][3], 2);
+            const float4 y = add4_xor(x0, x1, 1);
+            const float sum = __fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w));
+            const u32 r = (u32)(i * RSTRIDE + r0);
+            keys[i] = ZB_SENTINEL;
+            if (r < nrows && sub < nq_mine) {
+                if (METRIC == 0) keys[i] = cos_bits_rinv(sum, tp.bm_rinv[base + r], my_qrinv);
+                else keys[i] = METRIC == 1 ? l2sq_bits(sum) : l2_bits(sum);
+                if (keys[i] <= mythr) hm |= 1u << i;
+            }
+        }
+        // ---- warp-private register top-n': lane l holds the l-th best (key, pos) of (query j, this row slab).
+        //      Most blocks have no candidate under the filter: one ballot and out. ----
+        unsigned anym = __ballot_sync(0xffffffffu, hm != 0);
+        TS_T(t_e1);
+        TS_ACC(3, t_e0, t_e1);
+        if (anym) {
+#pragma unroll 1
+            for (int j = 0; j < nq_mine; ++j) {
+                const unsigned qmask = 0x11111111u << j;  // lanes whose query is j
+                if (!(anym & qmask)) continue;
+                const bool mine = (qmask >> lane) & 1u;
+                const int np = (int)__shfl_sync(0xffffffffu, my_np, j);
+                ListEntry le = my_list[j * TS_KL + lane];
+                u64 Lk = le.key;
+                u32 Lp = le.pos;
+                u64 thr = shfl64(mythr, j);  // lane j has sub == j
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    unsigned m = __ballot_sync(0xffffffffu, mine && ((hm >> i) & 1u) && keys[i] <= thr);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const u64 nk = shfl64(keys[i], src);
+                        if (nk > thr) continue;  // the filter tightened since the ballot
+                        const u32 npos = base + (u32)(i * RSTRIDE + wr * 8 + (src >> 2));
+                        const u32 w = __shfl_sync(0xffffffffu, tw, (int)((npos >> 5) - (base >> 5)));
+                        if ((w >> (npos & 31)) & 1u) continue;  // tombstoned (D1)
+                        const unsigned mm = __ballot_sync(0xffffffffu, kp_less(nk, npos, Lk, Lp));
+                        const int ins = mm ? __ffs(mm) - 1 : 32;
+                        if (ins >= np) continue;
+                        const u64 upk = shfl_up64(Lk);
+                        const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
+                        if (lane > ins) { Lk = upk; Lp = upp; }
+                        else if (lane == ins) { Lk = nk; Lp = npos; }
+                        const u64 lk = shfl64(Lk, np - 1);
+                        if (lk < thr) thr = lk;
+                    }
+                }
+                my_list[j * TS_KL + lane] = ListEntry{Lk, Lp, 0u};
+                if (mine) mythr = thr;
+                // publish: a full list of n' == top_k distinct rows bounds the query's final k-th best
+                if (lane == j && np == (int)tp.top_k && thr < gbound) atomicMin(tp.gthr + my_q, thr);
+            }
+            __syncwarp();
+        }
+        TS_T(t_e2);
+        TS_ACC(4, t_e1, t_e2);
+    }
+}
+
+static __host__ __device__ __forceinline__ size_t ts_team_bytes(int nst, int dimp) {
+    size_t b = (size_t)nst * TS_STAGE_BYTES + (size_t)TS_QT * dimp * 4 + (size_t)TS_TWARPS * 4 * TS_KL * sizeof(ListEntry) +
+               2 * sizeof(TileInfo) + (2 * TS_MAX_STAGES + 4) * 8;
+    return (b + 1023) & ~(size_t)1023;
+}
+
+// Two teams per CTA, each = 4 math warps (one per SM sub-partition) + 1 producer warp, each streaming its own tiles:
+// the two math warps that share a sub-partition belong to different tiles, so one warp's fold / insertion / tile
+// change overlaps the other's FP32 loop, and a bandwidth-bound tile (few queries) shares the SM with a pipe-bound one.
 template <int METRIC>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TileParams tp) {
@@ -191,33 +355,39 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
     const int dimp = f.dimp, chunks = f.chunks;
     const int nsl = (chunks + TS_KC - 1) / TS_KC;
     const u32 S = (u32)tp.nst;
-    // ---- carve shared memory ----
-    unsigned char* s_stage = smem;                                                     // [S][RB][48] f32
-    float* s_q = reinterpret_cast<float*>(smem + (size_t)S * TS_STAGE_BYTES);           // [QT][dimp]
-    ListEntry* s_list = reinterpret_cast<ListEntry*>(s_q + (size_t)TS_QT * dimp);       // [CWARPS][4][KL]
-    TileInfo* s_info = reinterpret_cast<TileInfo*>(s_list + TS_CWARPS * 4 * TS_KL);     // [2]
+    const size_t team_bytes = ts_team_bytes(tp.nst, dimp);
+    // ---- carve shared memory (per team) ----
+    const int team = warp < TS_CWARPS ? warp / TS_TWARPS : (warp - TS_CWARPS) % TS_TEAMS;
+    unsigned char* tb = smem + (size_t)team * team_bytes;
+    unsigned char* s_stage = tb;                                                       // [S][RB][48] f32
+    float* s_q = reinterpret_cast<float*>(tb + (size_t)S * TS_STAGE_BYTES);             // [QT][dimp]
+    ListEntry* s_list = reinterpret_cast<ListEntry*>(s_q + (size_t)TS_QT * dimp);       // [TWARPS][4][KL]
+    TileInfo* s_info = reinterpret_cast<TileInfo*>(s_list + TS_TWARPS * 4 * TS_KL);     // [2]
     u64* s_bar = reinterpret_cast<u64*>(s_info + 2);                                    // full[8], empty[8], ifull[2], qfull, qempty
     const u32 bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + TS_MAX_STAGES);
     const u32 bar_ifull = smem_u32(s_bar + 2 * TS_MAX_STAGES), bar_qfull = bar_ifull + 16, bar_qempty = bar_ifull + 24;
 
     if (tid == 0) {
-        for (u32 i = 0; i < S; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, TS_CWARPS);
+        for (int t = 0; t < TS_TEAMS; ++t) {
+            const u32 o = (u32)(t * team_bytes);  // this thread is in team 0: the other teams' barriers sit team_bytes apart
+            for (u32 i = 0; i < S; ++i) {
+                mbar_init(bar_full + o + 8 * i, 1);
+                mbar_init(bar_empty + o + 8 * i, TS_TWARPS);
+            }
+            mbar_init(bar_ifull + o, 1);
+            mbar_init(bar_ifull + o + 8, 1);
+            mbar_init(bar_qfull + o, 1);
+            mbar_init(bar_qempty + o, TS_TWARPS);
         }
-        mbar_init(bar_ifull, 1);
-        mbar_init(bar_ifull + 8, 1);
-        mbar_init(bar_qfull, 1);
-        mbar_init(bar_qempty, TS_CWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
     if (warp >= TS_CWARPS) {
-        // =========================== producer warpgroup: one thread drives TMA ===========================
+        // =========================== producer warpgroup: one thread per team drives TMA ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp != TS_CWARPS || lane != 0) return;
+        if (warp >= TS_CWARPS + TS_TEAMS || lane != 0) return;
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
         const u32 ntiles = *tp.ntiles;
         u32 n = 0;  // stages issued so far (ring sequence number)
@@ -253,16 +423,16 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
             // ... the resident query block is single-buffered: wait until the previous tile is done with it
             if (it > 0) mbar_wait(bar_qempty, (it - 1) & 1);
             mbar_arrive_expect_tx(bar_qfull, nqt * (u32)dimp * 4u);
-            for (u32 q0 = 0; q0 < nqt; q0 += 8) {  // address loads batched (8 independent chains), then the copies
-                u32 qi[8];
+            {  // address loads batched (8 independent chains), then the copies
+                u32 qi[TS_QT];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) qi[j] = q0 + j < nqt ? tp.order[first + q0 + j] : 0u;
+                for (int j = 0; j < TS_QT; ++j) qi[j] = (u32)j < nqt ? tp.order[first + j] : 0u;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) qi[j] = q0 + j < nqt ? tp.v_q[qi[j]] : 0u;
+                for (int j = 0; j < TS_QT; ++j) qi[j] = (u32)j < nqt ? tp.v_q[qi[j]] : 0u;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (q0 + j < nqt)
-                        bulk_g2s(smem_u32(s_q + (size_t)(q0 + j) * dimp), tp.queries + (size_t)qi[j] * dimp, (u32)dimp * 4u, bar_qfull);
+                for (int j = 0; j < TS_QT; ++j)
+                    if ((u32)j < nqt)
+                        bulk_g2s(smem_u32(s_q + (size_t)j * dimp), tp.queries + (size_t)qi[j] * dimp, (u32)dimp * 4u, bar_qfull);
             }
             const u32 next_tile = atomicAdd(tp.tile_counter, 1u);
             issue(total - pre);
@@ -276,31 +446,30 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
 
     // =================================== consumer (math) warps ===================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int g = warp >> 1, half = warp & 1, qd = lane >> 2, sub = lane & 3;
-    const int rg = half * 8 + qd;  // row group: rows i * 16 + rg, i = 0..7
-    ListEntry* my_list = s_list + (size_t)warp * 4 * TS_KL;
-    const int qstep = dimp / 4;
-    // Accumulator k of a thread belongs to query (k ^ sub) of the group: the quad's cross-thread folds then pair
-    // registers with static indices (no selects), and thread `sub` ends up owning query `sub`.
-    const float4* qb = reinterpret_cast<const float4*>(s_q + (size_t)(g * 4) * dimp) + sub;
-    const float4* qp0 = qb + (0 ^ sub) * qstep;
-    const float4* qp1 = qb + (1 ^ sub) * qstep;
-    const float4* qp2 = qb + (2 ^ sub) * qstep;
-    const float4* qp3 = qb + (3 ^ sub) * qstep;
+    ScanCtx cx;
+    cx.s_stage = s_stage; cx.s_q = s_q; cx.s_list = s_list;
+    cx.bar_full = bar_full; cx.bar_empty = bar_empty;
+    cx.S = S; cx.dimp = dimp; cx.chunks = chunks; cx.nsl = nsl;
+    const int tw = warp % TS_TWARPS, sub = lane & 3;
+    u32 n = 0;  // stages consumed so far
 #ifdef ZB_SCAN_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TS_TACC , tacc
+#else
+#define TS_TACC
 #endif
-    u32 n = 0;  // stages consumed so far
     for (u32 it = 0;; ++it) {
         TS_T(t_tile0);
         mbar_wait(bar_ifull + 8 * (it & 1), (it >> 1) & 1);
         const TileInfo inf = s_info[it & 1];
         if (inf.tile == 0xFFFFFFFFu) break;
-        const u32 nqt = inf.nqt, L = inf.L;
-        const long long moff = inf.moff;
-        const u32 nblocks = (L + TS_RB - 1) / TS_RB;
-        const bool warp_active = (u32)(g * 4) < nqt;  // whole query groups idle on small tiles
-        const int nq_mine = warp_active ? min(4, (int)nqt - g * 4) : 0;
+        const u32 nqt = inf.nqt;
+        // Role of this warp for the tile: 5..8 queries = two groups of 4, each scanned by a pair of wide warps (64 rows
+        // of every 128-row stage each); 1..4 queries = one group scanned by four narrow warps (32 rows each).  Either
+        // way every sub-partition carries the same FMA-pipe load.
+        const bool narrow = nqt <= 4;
+        const int g = narrow ? 0 : tw >> 1, wr = narrow ? tw : tw & 1;
+        const int nq_mine = min(4, (int)nqt - g * 4);
         // my query (slot `sub` of group g): visit, n', reciprocal norm
         u32 my_visit = 0, my_np = 0, my_q = 0;
         double my_qrinv = 0.0;
@@ -310,152 +479,37 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
             my_q = tp.v_q[my_visit];
             if (METRIC == 0) my_qrinv = tp.q_rinv[my_q];
         }
-        if (warp_active) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) my_list[j * TS_KL + lane] = ListEntry{ZB_SENTINEL, TS_NOPOS, 0u};
-        }
-        u64 mythr = ZB_SENTINEL;  // key of the n'-th best of MY query so far (filter)
-        __syncwarp();
         mbar_wait(bar_qfull, it & 1);
         TS_T(t_tile1);
-        TS_ACC(warp_active ? 0 : 7, t_tile0, t_tile1);
-
-        for (u32 b = 0; b < nblocks; ++b) {
-            const u32 nrows = min((u32)TS_RB, L - b * TS_RB);
-            const u32 base = (u32)(moff + (long long)b * TS_RB);  // position of row 0 of the block
-            // tombstone words covering positions base .. base+127 (at most 5 words), one per lane
-            u32 tw = 0;
-            if (warp_active && lane < 5) tw = tp.bm_tomb[(base >> 5) + lane];
-            // Bound shared by every visit of my query (other trees, other row half, other SMs): k distinct candidates
-            // at or below it already exist, so anything above it cannot reach the query's final top-k.  Stale reads
-            // only cost extra candidates.
-            u64 gbound = ZB_SENTINEL;
-            if (sub < nq_mine) gbound = __ldcg(tp.gthr + my_q);
-            float4 acc[8][4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int sl = 0; sl < nsl; ++sl, ++n) {
-                const u32 buf = n % S;
-                const int kcs = min(TS_KC, chunks - sl * TS_KC);
-                TS_T(t_w0);
-                mbar_wait(bar_full + 8 * buf, (n / S) & 1);
-                TS_T(t_w1);
-                TS_ACC(warp_active ? 1 : 7, t_w0, t_w1);
-                if (warp_active) {
-                    const float4* rp = reinterpret_cast<const float4*>(s_stage + (size_t)buf * TS_STAGE_BYTES) + rg * (TS_SLICE_FLOATS / 4) + sub;
-                    const int qo = sl * (TS_SLICE_FLOATS / 4);
-                    constexpr int rstep = 16 * TS_SLICE_FLOATS / 4;  // 16 rows apart, in float4 units
-#pragma unroll 1
-                    for (int c = 0; c < kcs; ++c) {
-                        const float4 q0 = qp0[qo + c * 4], q1 = qp1[qo + c * 4], q2 = qp2[qo + c * 4], q3 = qp3[qo + c * 4];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 r = rp[c * 4 + i * rstep];
-                            if (METRIC == 0) {
-                                fma4_x2(acc[i][0], r, q0); fma4_x2(acc[i][1], r, q1); fma4_x2(acc[i][2], r, q2); fma4_x2(acc[i][3], r, q3);
-                            } else {
-                                l2acc4_x2(acc[i][0], r, q0); l2acc4_x2(acc[i][1], r, q1); l2acc4_x2(acc[i][2], r, q2); l2acc4_x2(acc[i][3], r, q3);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
-                TS_T(t_w2);
-                TS_ACC(warp_active ? 2 : 7, t_w1, t_w2);
-            }
-            if (!warp_active) continue;
-            TS_T(t_e0);
-            // ---- epilogue of the row block: fold the quad's partial sums (canonical tree: lane j + lane j+8, then
-            //      + 4, then (r0+r1)+(r2+r3)); thread `sub` finishes query `sub`'s 8 candidates ----
-            if (gbound < mythr) mythr = gbound;
-            u64 keys[8];
-            u32 hm = 0;  // candidates that pass the filter
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 x0 = add4_xor(acc[i][0], acc[i][2], 2);
-                const float4 x1 = add4_xor(acc[i][1], acc[i][3], 2);
-                const float4 y = add4_xor(x0, x1, 1);
-                const float sum = __fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w));
-                const u32 r = (u32)(i * 16 + rg);
-                keys[i] = ZB_SENTINEL;
-                if (r < nrows && sub < nq_mine) {
-                    if (METRIC == 0) keys[i] = cos_bits_rinv(sum, tp.bm_rinv[base + r], my_qrinv);
-                    else keys[i] = METRIC == 1 ? l2sq_bits(sum) : l2_bits(sum);
-                    if (keys[i] <= mythr) hm |= 1u << i;
-                }
-            }
-            // ---- warp-private register top-n': lane l holds the l-th best (key, pos) of (query j, this row half).
-            //      Most blocks have no candidate under the filter: one ballot and out. ----
-            unsigned anym = __ballot_sync(0xffffffffu, hm != 0);
-            TS_T(t_e1);
-            TS_ACC(3, t_e0, t_e1);
-            if (anym) {
-#pragma unroll 1
-                for (int j = 0; j < nq_mine; ++j) {
-                    const unsigned qmask = 0x11111111u << j;  // lanes whose query is j
-                    if (!(anym & qmask)) continue;
-                    const bool mine = (qmask >> lane) & 1u;
-                    const int np = (int)__shfl_sync(0xffffffffu, my_np, j);
-                    ListEntry le = my_list[j * TS_KL + lane];
-                    u64 Lk = le.key;
-                    u32 Lp = le.pos;
-                    u64 thr = shfl64(mythr, j);  // lane j has sub == j: the list's n'-th key or the shared bound
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        unsigned m = __ballot_sync(0xffffffffu, mine && ((hm >> i) & 1u) && keys[i] <= thr);
-                        while (m) {
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            const u64 nk = shfl64(keys[i], src);
-                            if (nk > thr) continue;  // the filter tightened since the ballot
-                            const u32 npos = base + (u32)(i * 16 + half * 8 + (src >> 2));
-                            const u32 w = __shfl_sync(0xffffffffu, tw, (int)((npos >> 5) - (base >> 5)));
-                            if ((w >> (npos & 31)) & 1u) continue;  // tombstoned (D1)
-                            const unsigned mm = __ballot_sync(0xffffffffu, kp_less(nk, npos, Lk, Lp));
-                            const int ins = mm ? __ffs(mm) - 1 : 32;
-                            if (ins >= np) continue;
-                            const u64 upk = shfl_up64(Lk);
-                            const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
-                            if (lane > ins) { Lk = upk; Lp = upp; }
-                            else if (lane == ins) { Lk = nk; Lp = npos; }
-                            const u64 lk = shfl64(Lk, np - 1);
-                            if (lk < thr) thr = lk;
-                        }
-                    }
-                    my_list[j * TS_KL + lane] = ListEntry{Lk, Lp, 0u};
-                    if (mine) mythr = thr;
-                    // publish: a full list of n' == top_k distinct rows bounds the query's final k-th best
-                    if (lane == j && np == (int)tp.top_k && thr < gbound) atomicMin(tp.gthr + my_q, thr);
-                }
-                __syncwarp();
-            }
-            TS_T(t_e2);
-            TS_ACC(4, t_e1, t_e2);
-        }
+        TS_ACC(0, t_tile0, t_tile1);
+        if (narrow) scan_tile<METRIC, 4>(cx, f, tp, inf, g, wr, tw, lane, n, my_np, my_q, my_qrinv, nq_mine TS_TACC);
+        else scan_tile<METRIC, 8>(cx, f, tp, inf, g, wr, tw, lane, n, my_np, my_q, my_qrinv, nq_mine TS_TACC);
         TS_T(t_m0);
-        // ---- end of tile: release the query block, merge the two row halves, write the visits' top lists ----
+        // ---- end of tile: release the query block, merge the row slabs of each group, write the visits' top lists ----
         if (lane == 0) mbar_arrive(bar_qempty);
-        pair_sync(g);  // both halves' lists are final and visible
-        if (warp_active && half == 0) {
-            const ListEntry* other = my_list + 4 * TS_KL;  // warp + 1
+        asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory");  // the team's lists are final and visible
+        if (wr == 0) {  // the group's first warp merges its 2 (wide) or 4 (narrow) slabs, which sit in consecutive list blocks
+            const int nslab = narrow ? 4 : 2;
+            const ListEntry* mine_l = s_list + (size_t)tw * 4 * TS_KL;
 #pragma unroll 1
             for (int j = 0; j < nq_mine; ++j) {
                 const int np = (int)__shfl_sync(0xffffffffu, my_np, j);
                 const u32 v = __shfl_sync(0xffffffffu, my_visit, j);
-                ListEntry a = my_list[j * TS_KL + lane], bb = other[j * TS_KL + (31 - lane)];
+                ListEntry a = mine_l[j * TS_KL + lane];
                 u64 k = a.key;
                 u32 p = a.pos;
-                if (kp_less(bb.key, bb.pos, k, p)) { k = bb.key; p = bb.pos; }  // 32 smallest of the union, bitonic
+#pragma unroll 1
+                for (int o = 1; o < nslab; ++o) {
+                    const ListEntry bb = mine_l[(size_t)o * 4 * TS_KL + j * TS_KL + (31 - lane)];
+                    if (kp_less(bb.key, bb.pos, k, p)) { k = bb.key; p = bb.pos; }  // 32 smallest of the union, bitonic
 #pragma unroll
-                for (int x = 16; x >= 1; x >>= 1) {
-                    const u64 ok = shfl_xor64(k, x);
-                    const u32 op = __shfl_xor_sync(0xffffffffu, p, x);
-                    const bool lower = (lane & x) == 0;
-                    const bool other_less = kp_less(ok, op, k, p);
-                    if (lower == other_less) { k = ok; p = op; }
+                    for (int x = 16; x >= 1; x >>= 1) {
+                        const u64 ok = shfl_xor64(k, x);
+                        const u32 op = __shfl_xor_sync(0xffffffffu, p, x);
+                        const bool lower = (lane & x) == 0;
+                        const bool other_less = kp_less(ok, op, k, p);
+                        if (lower == other_less) { k = ok; p = op; }
+                    }
                 }
                 const u32 e0 = tp.v_ent_off[v], e1 = tp.v_ent_off[v + 1];
                 if ((u32)lane < e1 - e0) {
@@ -465,9 +519,9 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
                 }
             }
         }
-        pair_sync(g);  // lists may be re-initialised for the next tile
+        asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory");  // lists may be re-initialised for the next tile
         TS_T(t_m1);
-        TS_ACC(warp_active ? 5 : 7, t_m0, t_m1);
+        TS_ACC(5, t_m0, t_m1);
     }
 #ifdef ZB_SCAN_TIMING
     if (lane == 0)
@@ -538,10 +592,7 @@ void launch_rinv(const float* d_x, u64 n, int dimp, double* d_out, cudaStream_t 
     rinv_kernel<<<(u32)((n + 31) / 32), 128, 0, s>>>(d_x, n, dimp, d_out);
 }
 
-static size_t ts_smem_bytes(int nst, int dimp) {
-    return (size_t)nst * TS_STAGE_BYTES + (size_t)TS_QT * dimp * 4 + (size_t)TS_CWARPS * 4 * TS_KL * sizeof(ListEntry) +
-           2 * sizeof(TileInfo) + (2 * TS_MAX_STAGES + 4) * 8 + 1024;
-}
+static size_t ts_smem_bytes(int nst, int dimp) { return TS_TEAMS * ts_team_bytes(nst, dimp) + 1024; }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -295,3 +295,22 @@ def test_synth_is_deterministic_and_shard_consistent():
     torch.cuda.synchronize()
     assert torch.equal(a[1::2], b)
     assert float(a.abs().max()) <= 1.25 and float(a.std()) > 0.3
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU (NCCL)
+def test_sharded_two_gpus_equals_oracle():
+    """Row-sharded index over 2 GPUs of this box (NCCL allreduce of leaf counts, allgather + per-visit merge of the
+    local top-n' lists) against the unsharded oracle.  Skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "mgpu_parity.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]

@@ -34,6 +34,8 @@ namespace zb {
 #define TS_MAX_STAGES 8
 #define TS_KL 32            // list length of the register top-n' (one entry per lane)
 #define TS_NOPOS 0xFFFFFFFFu
+#define TS_PACE_WINDOW 8    // a tile may run at most this many stages ahead of a sibling tile (same leaf, other queries)
+#define TS_PACE_EVERY 4
 
 // Phase timing of the math warps (debug builds only: make EXTRA=-DZB_SCAN_TIMING): cycles spent waiting for the
 // tile info / queries, waiting for row stages, in the FP32 loop, in the fold + key epilogue, in list insertion and in
@@ -67,6 +69,8 @@ struct TileParams {
     const double* bm_rinv;  // [positions] 1/sqrt(|row|^2) in f64 (cosine)
     const u32* bm_tomb;     // bit per position
     u64* stats;             // [0] visits, [1] pairs, [2] moved bytes
+    u32 pace_window;        // 0 = no pacing
+    u32* tile_prog;         // [ntiles] stages issued so far per tile (0xFFFFFFFF = finished): sibling tiles of a leaf pace each other
     u64* gthr;              // [nq] per-query bound shared by all of the query's visits: min over full lists of their n'-th key
     u32 top_k;
     int nst;                // ring depth
@@ -406,9 +410,23 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
             mbar_arrive(bar_ifull + 8 * (it & 1));
             const u32 nblocks = (L + TS_RB - 1) / TS_RB;
             const u32 total = nblocks * (u32)nsl;
-            u32 b = 0, sl = 0;
+            // Sibling tiles (same leaf, other queries) are dispatched back to back, so they start within about a
+            // microsecond of each other on other SMs; pacing keeps them within TS_PACE_WINDOW stages so that the
+            // second reader of a row block finds it in L2 instead of going to HBM again.
+            const bool has_prev = tp.pace_window && tile > 0 && tp.tile_leaf[tile - 1] == leaf;
+            const bool has_next = tp.pace_window && tile + 1 < ntiles && tp.tile_leaf[tile + 1] == leaf;
+            volatile u32* prog = tp.tile_prog;
+            u32 b = 0, sl = 0, done = 0;
             auto issue = [&](u32 count) {
-                for (u32 j = 0; j < count; ++j, ++n) {
+                for (u32 j = 0; j < count; ++j, ++n, ++done) {
+                    if ((has_prev || has_next) && (done % TS_PACE_EVERY) == 0) {
+                        prog[tile] = done;
+                        if (done > tp.pace_window) {
+                            const u32 lim = done - tp.pace_window;
+                            if (has_prev) while (prog[tile - 1] < lim) {}
+                            if (has_next) while (prog[tile + 1] < lim) {}
+                        }
+                    }
                     const u32 buf = n % S;
                     if (n >= S) mbar_wait(bar_empty + 8 * buf, ((n / S) - 1) & 1);
                     mbar_arrive_expect_tx(bar_full + 8 * buf, TS_STAGE_BYTES);
@@ -434,8 +452,10 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
                     if ((u32)j < nqt)
                         bulk_g2s(smem_u32(s_q + (size_t)j * dimp), tp.queries + (size_t)qi[j] * dimp, (u32)dimp * 4u, bar_qfull);
             }
-            const u32 next_tile = atomicAdd(tp.tile_counter, 1u);
             issue(total - pre);
+            if (has_prev || has_next) prog[tile] = 0xFFFFFFFFu;
+            // fetched only now (not while the tile is in flight), so consecutive tiles start back to back
+            const u32 next_tile = atomicAdd(tp.tile_counter, 1u);
             atomicAdd(&tp.stats[0], (u64)nqt);
             atomicAdd(&tp.stats[1], (u64)nqt * L);
             atomicAdd(&tp.stats[2], ((u64)L + nqt) * (u64)dimp * 4ull);  // algorithmic bytes: leaf rows once + the tile's queries
@@ -632,6 +652,8 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
                u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
                u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s) {
     ws.launched = false;
+    const u32 pace_window = tile_queries >> 8;  // knob: bits 8.. of tile_queries carry the pacing window (tests / ablations)
+    tile_queries &= 0xFF;
     if (!nv || !nleaves || !tile_scan_supported(f.dimp, top_k)) return;
     const u32 tq = tile_queries >= 1 && tile_queries <= TS_QT ? tile_queries : TS_QT;
     int dev = 0, max_smem = 0, sms = 0;
@@ -651,6 +673,8 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
     ws.tile_leaf.ensure(nv);
     ws.tile_first.ensure(nv);
     ws.counters.ensure(64);
+    ws.tile_prog.ensure(nv);
+    ZB_CUDA(cudaMemsetAsync(ws.tile_prog.p, 0, (size_t)nv * 4, s));
     ws.gthr.ensure(nq ? nq : 1);
     ZB_CUDA(cudaMemsetAsync(ws.gthr.p, 0xFF, (size_t)(nq ? nq : 1) * 8, s));
     size_t tmp_bytes = 0;
@@ -690,6 +714,8 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
     tp.bm_rinv = bm.rinv;
     tp.bm_tomb = bm.tomb;
     tp.stats = reinterpret_cast<u64*>(ws.counters.p + 4);
+    tp.pace_window = pace_window;
+    tp.tile_prog = ws.tile_prog.p;
     tp.gthr = ws.gthr.p;
     tp.top_k = top_k;
     tp.nst = nst;

@@ -7,7 +7,7 @@ namespace zb {
 
 struct ScanWorkspace {
     DBuf<u32> leaf_count, leaf_start, leaf_cursor, tile_per_leaf, tile_start, order, tile_leaf, tile_first, tile_cnt;
-    DBuf<u32> counters;
+    DBuf<u32> counters, tile_prog;
     DBuf<u64> gthr;
     DBuf<u8> tmp;
     bool launched = false;

@@ -18,15 +18,18 @@ leaf_len = np.diff(f.leaf_off)
 cnt = np.bincount(leaf.reshape(-1), minlength=leaf_len.size)
 print("leaves", leaf_len.size, "visited", (cnt > 0).sum(), "len mean", leaf_len.mean(), "min", leaf_len.min(), "max", leaf_len.max())
 print("visits/leaf histogram:", np.bincount(np.minimum(cnt, 40)))
+# current tiling (zb_scan.cu ts_filltiles_kernel): full tiles of 8 first, the remainder last; a tile costs
+# ceil(nqt / 4) query groups x ceil(L / 128) row blocks of FP32 work, and reads its leaf once
 tiles = []
 for c, L in zip(cnt, leaf_len):
     if c == 0: continue
-    nt = (c + 15) // 16; base, rem = divmod(c, nt)
-    tiles += [(base + (1 if j < rem else 0), L) for j in range(nt)]
+    full, rem = divmod(int(c), 8)
+    tiles += [(8, L)] * full + ([(rem, L)] if rem else [])
 t = np.array(tiles)
-G = (t[:, 0] + 3) // 4
-for g in range(1, 5):
-    m = G == g
-    print(f"G={g}: tiles {m.sum()}, rows {t[m,1].sum()}, pairs {(t[m,0]*t[m,1]).sum()}")
-cost = (np.ceil(G / 2) * t[:, 1]).sum()
-print("sum L*ceil(G/2) =", cost, " ideal pairs/8 =", (t[:, 0] * t[:, 1]).sum() / 8, " efficiency", (t[:, 0] * t[:, 1]).sum() / 8 / cost)
+pairs = (t[:, 0] * t[:, 1]).sum()
+padded = (((t[:, 0] + 3) // 4 * 4) * ((t[:, 1] + 127) // 128 * 128)).sum()
+padq = (((t[:, 0] + 3) // 4 * 4) * t[:, 1]).sum()
+print("tiles", len(t), "pairs", pairs, "padded pairs (query groups and row blocks)", padded, "efficiency", pairs / padded,
+      "query padding only", pairs / padq)
+print("tile size histogram:", np.bincount(t[:, 0]))
+print("moved bytes", (t[:, 1] * dim * 4).sum() / 1e9, "GB; unique", (leaf_len[cnt > 0] * dim * 4).sum() / 1e9, "GB")

@@ -1103,7 +1103,10 @@ int zb_index_hash(zb_index* ix, uint64_t n, const float* rows, uint64_t* out_key
     DBuf<float> tmp;
     ix->use_device();
     tmp.ensure(n * (u64)ix->dim + 4);
-    ZB_CUDA(cudaMemcpy(tmp.p, rows, n * (u64)ix->dim * 4, cudaMemcpyHostToDevice));
+    // on the index's stream: a pageable cudaMemcpy on the legacy stream may return before its DMA has landed, and the
+    // index's stream is non-blocking, so the hash kernel could otherwise read rows that are not there yet
+    ZB_CUDA(cudaMemcpyAsync(tmp.p, rows, n * (u64)ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
+    ZB_CUDA(cudaStreamSynchronize(ix->stream));
     int rc = zb_index_hash_device(ix, n, tmp.p, (uint64_t*)ix->h_keys.p, ix->h_depths.p, ix->h_leaves.p);
     if (rc != ZB_OK) return rc;
     const u64 tot = n * (u64)ix->T;

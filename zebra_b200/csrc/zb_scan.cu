@@ -92,11 +92,11 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity)
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: the warp sleeps in hardware instead of spinning
         : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
@@ -202,7 +202,7 @@ struct ScanCtx {
 //   g  : query group (queries g*4 .. g*4+3 of the tile)        wr : which row slab of the group this warp scans
 template <int METRIC, int NR>
 __device__ __forceinline__ void scan_tile(const ScanCtx& cx, const ForestView& f, const TileParams& tp, const TileInfo& inf,
-                                          const int g, const int wr, const int warp, const int lane, u32& n,
+                                          const int g, const int wr, const int warp, const int lane, u32& buf, u32& ph,
                                           u32 my_np, u32 my_q, double my_qrinv, int nq_mine
 #ifdef ZB_SCAN_TIMING
                                           , long long* tacc
@@ -244,11 +244,10 @@ __device__ __forceinline__ void scan_tile(const ScanCtx& cx, const ForestView& f
         for (int i = 0; i < NR; ++i)
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sl = 0; sl < nsl; ++sl, ++n) {
-            const u32 buf = n % S;
+        for (int sl = 0; sl < nsl; ++sl) {
             const int kcs = min(TS_KC, chunks - sl * TS_KC);
             TS_T(t_w0);
-            mbar_wait(cx.bar_full + 8 * buf, (n / S) & 1);
+            mbar_wait(cx.bar_full + 8 * buf, ph);
             TS_T(t_w1);
             TS_ACC(1, t_w0, t_w1);
             const float4* rp = reinterpret_cast<const float4*>(cx.s_stage + (size_t)buf * TS_STAGE_BYTES) + r0 * (TS_SLICE_FLOATS / 4) + sub;
@@ -269,6 +268,7 @@ __device__ __forceinline__ void scan_tile(const ScanCtx& cx, const ForestView& f
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(cx.bar_empty + 8 * buf);
+            if (++buf == S) { buf = 0; ph ^= 1u; }
             TS_T(t_w2);
             TS_ACC(2, t_w1, t_w2);
         }
@@ -394,7 +394,7 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
         if (warp >= TS_CWARPS + TS_TEAMS || lane != 0) return;
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
         const u32 ntiles = *tp.ntiles;
-        u32 n = 0;  // stages issued so far (ring sequence number)
+        u32 buf = 0, eph = 1;  // ring slot of the next stage to issue; parity to wait for on its empty barrier (first lap: free)
         u32 tile = atomicAdd(tp.tile_counter, 1u);
         for (u32 it = 0;; ++it) {
             TileInfo* inf = s_info + (it & 1);
@@ -418,7 +418,7 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
             volatile u32* prog = tp.tile_prog;
             u32 b = 0, sl = 0, done = 0;
             auto issue = [&](u32 count) {
-                for (u32 j = 0; j < count; ++j, ++n, ++done) {
+                for (u32 j = 0; j < count; ++j, ++done) {
                     if ((has_prev || has_next) && (done % TS_PACE_EVERY) == 0) {
                         prog[tile] = done;
                         if (done > tp.pace_window) {
@@ -427,12 +427,12 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
                             if (has_next) while (prog[tile + 1] < lim) {}
                         }
                     }
-                    const u32 buf = n % S;
-                    if (n >= S) mbar_wait(bar_empty + 8 * buf, ((n / S) - 1) & 1);
+                    mbar_wait(bar_empty + 8 * buf, eph);
                     mbar_arrive_expect_tx(bar_full + 8 * buf, TS_STAGE_BYTES);
                     tma_2d_g2s(smem_u32(s_stage + (size_t)buf * TS_STAGE_BYTES), &tmap, (int)(sl * TS_SLICE_FLOATS),
                                (int)(moff + (long long)b * TS_RB), bar_full + 8 * buf);
                     if (++sl == (u32)nsl) { sl = 0; ++b; }
+                    if (++buf == S) { buf = 0; eph ^= 1u; }
                 }
             };
             // rows of this tile may run ahead into the ring while the math warps still finish the previous tile ...
@@ -471,7 +471,7 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
     cx.bar_full = bar_full; cx.bar_empty = bar_empty;
     cx.S = S; cx.dimp = dimp; cx.chunks = chunks; cx.nsl = nsl;
     const int tw = warp % TS_TWARPS, sub = lane & 3;
-    u32 n = 0;  // stages consumed so far
+    u32 rbuf = 0, rph = 0;  // ring position of the next stage to consume: slot and phase parity
 #ifdef ZB_SCAN_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define TS_TACC , tacc
@@ -502,8 +502,8 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
         mbar_wait(bar_qfull, it & 1);
         TS_T(t_tile1);
         TS_ACC(0, t_tile0, t_tile1);
-        if (narrow) scan_tile<METRIC, 4>(cx, f, tp, inf, g, wr, tw, lane, n, my_np, my_q, my_qrinv, nq_mine TS_TACC);
-        else scan_tile<METRIC, 8>(cx, f, tp, inf, g, wr, tw, lane, n, my_np, my_q, my_qrinv, nq_mine TS_TACC);
+        if (narrow) scan_tile<METRIC, 4>(cx, f, tp, inf, g, wr, tw, lane, rbuf, rph, my_np, my_q, my_qrinv, nq_mine TS_TACC);
+        else scan_tile<METRIC, 8>(cx, f, tp, inf, g, wr, tw, lane, rbuf, rph, my_np, my_q, my_qrinv, nq_mine TS_TACC);
         TS_T(t_m0);
         // ---- end of tile: release the query block, merge the row slabs of each group, write the visits' top lists ----
         if (lane == 0) mbar_arrive(bar_qempty);

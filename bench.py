@@ -3,9 +3,10 @@
 
 A "step" is one pass of the hot path (plan -> leaf scan + top-n' -> merge) over one batch of synthetic queries
 against a resident index.  N = 1 runs BASELINE config[1]: 1M x 768 f32, L2, 10k batched top-10 queries.  N > 1
-is a weak-scaling run of the same per-GPU workload: rows are sharded (1M per GPU, ordinal % N), the query batch
-grows to N x 10k, every rank scans its shard of every visited leaf and the per-visit local top-n' lists are
-merged by an NCCL allgather inside the library.
+is a weak-scaling run of the same per-GPU workload (1M rows and 10k queries per GPU): the forest is replicated, the
+bucket-major store is sharded by bucket (leaf l lives, whole, on rank l % N), each rank plans 1/N of the queries
+(NCCL allgather of the visit records), scans the visits of the leaves it owns, reduces them to a per-query local
+top-k, and the local lists are merged after one NCCL allgather.
 
   python bench.py --gpus 1 --steps 5 --warmup 3                 # ours
   python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 # the restated reference on the host cores
@@ -71,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -116,6 +117,20 @@ def hbm_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(a):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one tile_scan_kernel launch, from the committed ncu --set full capture
+    of this same default workload (profiles/traffic.json, written by tools/profile_r1.sh); None for any other workload."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        if (t["rows"], t["dim"], t["queries"], t["metric"], t["max_node_size"], t["trees"], t["topk"]) == (
+                a.rows, a.dim, a.queries, a.metric, a.max_node_size, a.trees, a.topk) and a.gpus == 1:
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 # ----------------------------------------------------------------------------------------------------- reference arm
@@ -239,13 +254,13 @@ def run_ours(a):
         ix.search_batch_ptr(nq, h_q[b].data_ptr(), a.topk, h_ord.data_ptr(), h_bits.data_ptr(), h_cnt.data_ptr())
 
     # ---- device-resident leg: `value` ----
+    sampler = ClockSampler(local)
+    sampler.start()          # runs through warm-up, the timed region and the end-to-end leg (each only tens of ms long)
     for b in range(a.warmup):
         step_device(b)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"scan_ms": 0.0, "plan_ms": 0.0, "select_ms": 0.0, "merge_ms": 0.0, "moved": 0, "pairs": 0, "visits": 0,
+    agg = {"scan_ms": 0.0, "plan_ms": 0.0, "select_ms": 0.0, "merge_ms": 0.0, "tile_ms": 0.0, "tiles": 0, "moved": 0, "pairs": 0, "visits": 0,
            "tile_pairs": 0, "scan_launches": 0, "launches": 0}
     t_wall = time.perf_counter()
     e0.record(stream)
@@ -254,13 +269,13 @@ def run_ours(a):
         st = ix.stats()
         agg["scan_ms"] += st["last_ms_scan"]; agg["plan_ms"] += st["last_ms_plan"]
         agg["select_ms"] += st["last_ms_select"]; agg["merge_ms"] += st["last_ms_merge"]
+        agg["tile_ms"] += st["last_ms_tile_kernel"]; agg["tiles"] += st["last_tiles"]
         agg["moved"] += st["last_moved_bytes"]; agg["pairs"] += st["last_pairs"]; agg["visits"] += st["last_visits"]
         agg["tile_pairs"] += st["last_tile_pairs"]
         agg["scan_launches"] += st["last_scan_launches"]; agg["launches"] += st["last_total_launches"]
     e1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
-    clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if G > 1:
@@ -278,6 +293,7 @@ def run_ours(a):
         step_e2e(a.warmup + s)
     barrier()
     e2e_ms = (time.perf_counter() - t_e) * 1e3
+    clocks = sampler.stop()
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if G > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -289,14 +305,17 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel (the leaf scan): bytes it asks HBM for by design / its event time ----
     peak, peak_src = hbm_peak()
-    scan_s = agg["scan_ms"] / 1e3
+    # the dominant kernel = tile_scan_kernel, timed alone by CUDA events the library records around its launch on the
+    # index's stream; its algorithmic bytes = sum over tiles of (leaf rows + tile queries) x 4 x dim, counted by the kernel
+    scan_s = (agg["tile_ms"] if agg["tile_ms"] > 0 else agg["scan_ms"]) / 1e3
     achieved = agg["moved"] / scan_s / 1e9 if scan_s > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "leaf scan (zb_scan.cu tile kernel + generic score_pairs)",
-                "algorithmic_bytes_per_step": agg["moved"] // max(1, a.steps),
-                "kernel_ms_per_step": agg["scan_ms"] / a.steps,
+                "traffic": ncu_traffic(a), "peak_source": peak_src, "kernel": "tile_scan_kernel (zb_scan.cu)",
+                "algorithmic_bytes_per_launch": agg["moved"] // max(1, a.steps), "launches_per_step": 1,
+                "tiles_per_launch": agg["tiles"] // max(1, a.steps),
+                "kernel_ms_per_launch": scan_s * 1e3 / a.steps,
                 "pair_gbs": agg["pairs"] * a.dim * 4 / scan_s / 1e9 if scan_s > 0 else 0.0,
-                "kernel_share_of_step": agg["scan_ms"] / dev_ms}
+                "kernel_share_of_step": scan_s * 1e3 / dev_ms}
 
     # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1) ----
     cpu = None
@@ -321,6 +340,13 @@ def run_ours(a):
         go, gb, gc = h_ord.numpy()[:sample].view(np.uint64), h_bits.numpy()[:sample].view(np.uint64), h_cnt.numpy()[:sample]
         parity = bool(np.array_equal(go, eo) and np.array_equal(gb, eb) and np.array_equal(gc.astype(np.uint32), ec))
 
+    per_rank = None
+    if G > 1:   # per-rank phase times (ms per step): the step time is the max over ranks, these show where it goes
+        mine = torch.tensor([agg[k] / a.steps for k in ("plan_ms", "scan_ms", "tile_ms", "select_ms", "merge_ms")] +
+                            [agg["pairs"] / a.steps, agg["tiles"] / a.steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(G)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(x), 3) for x in r] for r in allr]
     if rank == 0:
         st = ix.stats()
         line = {
@@ -331,13 +357,14 @@ def run_ours(a):
                        "top_k": a.topk, "metric": a.metric, "max_node_size": a.max_node_size, "num_trees": a.trees,
                        "data": "Philox clustered (centre[row % 4096] + 0.25 noise), generated on device",
                        "l2_policy": "every step uses a fresh query batch and streams >1 GB of rows (>> 126 MB L2)",
-                       "parallelism": f"row-sharded x{G}" if G > 1 else "single GPU",
+                       "parallelism": f"bucket-sharded x{G} (leaf l on rank l % {G}; plan sharded by query, NCCL allgather of visits and of per-query local top-k)" if G > 1 else "single GPU",
                        "index_build_s": round(t_build, 2), "leaves": st["leaves"], "planes": st["planes"]},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / a.steps, "matches_device_leg": same},
             "gpu_launches": int(agg["launches"]), "clocks": clocks,
-            "phases_ms_per_step": {k: agg[k] / a.steps for k in ("plan_ms", "scan_ms", "select_ms", "merge_ms")},
+            "phases_ms_per_step": {k: agg[k] / a.steps for k in ("plan_ms", "scan_ms", "tile_ms", "select_ms", "merge_ms")},
+            "per_rank_plan_scan_tile_select_merge_ms_pairs_tiles": per_rank,
             "wall_ms_per_step": wall_ms / a.steps, "visits_per_step": agg["visits"] // a.steps,
             "pairs_per_step": agg["pairs"] // a.steps, "tile_pairs_per_step": agg["tile_pairs"] // a.steps,
             "parity_sample_ok": parity, "device_bytes": st["device_bytes"],

@@ -74,7 +74,9 @@ typedef struct zb_stats {
     uint64_t last_moved_bytes;                        /* HBM bytes the scan asks for by design (rows, per tile) */
     float last_ms_plan, last_ms_scan, last_ms_select, last_ms_merge, last_ms_total;
     uint32_t last_scan_launches, last_total_launches;
-    uint32_t reserved[8];
+    float last_ms_tile_kernel;    /* the fused leaf-tile scan kernel alone (CUDA events around its launch) */
+    uint32_t last_tiles;          /* (leaf, <= 8 queries) tiles it processed */
+    uint32_t reserved[6];
 } zb_stats;
 
 const char* zb_last_error(void);

@@ -56,7 +56,9 @@ class Stats(C.Structure):
         ("last_ms_total", C.c_float),
         ("last_scan_launches", C.c_uint32),
         ("last_total_launches", C.c_uint32),
-        ("reserved", C.c_uint32 * 8),
+        ("last_ms_tile_kernel", C.c_float),
+        ("last_tiles", C.c_uint32),
+        ("reserved", C.c_uint32 * 6),
     ]
 
     def as_dict(self):

@@ -118,6 +118,11 @@ struct Nccl {
     enum Op { SUM = 0, MAX = 2, MIN = 3 };
     void allreduce(void* d_buf, size_t count, Type t, Op op, cudaStream_t s);
     void allgather(const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t s);
+    // point-to-point exchange (bucket-major store build): calls between group_start / group_end form one fused operation
+    void group_start();
+    void group_end();
+    void send(const void* d_buf, size_t bytes, int peer, cudaStream_t s);
+    void recv(void* d_buf, size_t bytes, int peer, cudaStream_t s);
 };
 
 }  // namespace zb

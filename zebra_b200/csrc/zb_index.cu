@@ -117,6 +117,16 @@ struct zb_index {
     alignas(64) unsigned char bm_tmap[128];
     bool bm_valid = false, bm_failed = false;
     u64 bm_positions = 0;
+    // bucket-sharded layout (G > 1): leaf l lives, whole, on rank l % G; positions are tree-major, then leaf, then ordinal
+    DBuf<long long> d_bm_off;   // [leaves] first position of the leaf here
+    DBuf<u32> d_bm_len;         // [leaves] rows of the leaf here (0: another rank owns it)
+    DBuf<u64> bm_ord;           // [positions] ordinal of the row at a position
+    DBuf<u32> d_iota;           // [positions] identity "member" list: the scan view addresses rows by position
+    DBuf<u64> srt_ord;          // per tree region: ordinals ascending ...
+    DBuf<u32> srt_pos;          // ... and the position each one sits at (delete -> tombstone lookup)
+    DBuf<u64> d_tree_base, rm_ords;
+    std::vector<u64> h_tree_base;
+    DBuf<u64> loc_results;      // this rank's per-query top-k over the leaves it owns: [ord nq*k | bits nq*k]
 
     // ---- workspaces ----
     DBuf<u8> cub_tmp;
@@ -163,6 +173,21 @@ struct zb_index {
         f.dimp = dimp;
         f.chunks = chunks;
         f.num_trees = T;
+        return f;
+    }
+    // What the scoring kernels read leaves from.  Unsharded: the forest's own member lists.  Sharded: the bucket-major
+    // store of the leaves this rank owns, addressed by position (members = identity, ordinals / tombstones per position).
+    ForestView scan_view() const {
+        ForestView f = view();
+        if (G > 1) {
+            f.leaf_off = d_bm_off.p;
+            f.leaf_len = d_bm_len.p;
+            f.members = d_iota.p;
+            f.rows = bm_rows.p;
+            f.ord = bm_ord.p;
+            f.tomb = bm_tomb.p;
+            f.row_norm = nullptr;
+        }
         return f;
     }
     void sync() { ZB_CUDA(cudaStreamSynchronize(stream)); }
@@ -275,6 +300,7 @@ struct zb_index {
     // the tile kernel's minimum size get one; an allocation failure degrades to the generic gather path.
     bool ensure_bucket_major() {
         if (bm_valid) return true;
+        if (G > 1) return ensure_bucket_major_sharded();
         if (bm_failed || !built || !p_use_tile_scan || opt.max_node_size < (u64)p_tile_min_rows || !members_used) return false;
         const u32 nl = (u32)h_leaf_off.size();
         try {
@@ -301,6 +327,143 @@ struct zb_index {
         make_row_tile_map(bm_tmap, bm_rows.p, members_used, dimp);
         sync();
         bm_positions = members_used;
+        bm_valid = true;
+        return true;
+    }
+    // Bucket-sharded store (north_star (c)): every leaf is moved, whole, to rank leaf % G -- each rank packs
+    // the rows it holds of every leaf by destination, the ranks exchange them with grouped ncclSend / ncclRecv, and the
+    // owner sorts what it received by (leaf, ordinal) into contiguous [len][dimp] blocks.  One tree at a time, so the
+    // staging area is 1/T of the store.  Collective: every rank must call it at the same point.
+    bool ensure_bucket_major_sharded() {
+        ZB_REQUIRE(comm_ready, ZB_ERR_STATE, "sharded index used before zb_index_comm_init");
+        ZB_REQUIRE(total_rows < (1ull << 40), ZB_ERR_STATE, "bucket-sharded store supports up to 2^40 rows");
+        const u32 nl = (u32)h_leaf_off.size();
+        sync_host_members();
+        // every rank's share of every leaf
+        DBuf<u32> d_all;
+        d_all.ensure((size_t)nl * G);
+        nccl.allgather(d_leaf_len.p, d_all.p, (size_t)nl * 4, stream);
+        std::vector<u32> all_len((size_t)nl * G);
+        ZB_CUDA(cudaMemcpyAsync(all_len.data(), d_all.p, all_len.size() * 4, cudaMemcpyDeviceToHost, stream));
+        sync();
+        std::vector<std::vector<u32>> owned(T);
+        for (u32 l = 0; l < nl; ++l)
+            if (h_leaf_node[l] >= 0 && l % G == rank) owned[h_leaf_tree[l]].push_back(l);
+        std::vector<long long> off(nl, 0);
+        std::vector<u32> len(nl, 0);
+        h_tree_base.assign(T + 1, 0);
+        u64 P = 0;
+        for (int t = 0; t < T; ++t) {
+            h_tree_base[t] = P;
+            for (u32 l : owned[t]) {
+                u64 g = 0;
+                for (u32 r = 0; r < G; ++r) g += all_len[(size_t)r * nl + l];
+                off[l] = (long long)P;
+                len[l] = (u32)g;
+                P += g;
+            }
+        }
+        h_tree_base[T] = P;
+        ZB_REQUIRE(P < (1ull << 31), ZB_ERR_STATE, "more than 2^31 bucket-major positions on one rank");
+        const u64 Pa = P ? P : 1;
+        bm_rows.ensure(Pa * (u64)dimp, 0, stream, true);
+        bm_ord.ensure(Pa);
+        bm_tomb.ensure(Pa / 32 + 8);
+        d_iota.ensure(Pa);
+        srt_ord.ensure(Pa);
+        srt_pos.ensure(Pa);
+        d_bm_off.ensure(nl ? nl : 1);
+        d_bm_len.ensure(nl ? nl : 1);
+        d_tree_base.ensure(T + 1);
+        if (opt.metric == ZB_METRIC_COSINE) bm_rinv.ensure(Pa);
+        ZB_CUDA(cudaMemsetAsync(bm_tomb.p, 0, (Pa / 32 + 8) * 4, stream));
+        if (nl) {
+            ZB_CUDA(cudaMemcpyAsync(d_bm_off.p, off.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, stream));
+            ZB_CUDA(cudaMemcpyAsync(d_bm_len.p, len.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, stream));
+        }
+        ZB_CUDA(cudaMemcpyAsync(d_tree_base.p, h_tree_base.data(), (size_t)(T + 1) * 8, cudaMemcpyHostToDevice, stream));
+        launch_iota_u32(d_iota.p, P, 0u, stream);
+        sync();
+        DBuf<u32> d_slots, sort_val[2];
+        DBuf<float> snd_rows, st_rows;
+        DBuf<u64> snd_key, st_key, sort_key[2];
+        DBuf<RecvSeg> d_segs;
+        DBuf<u8> sort_tmp;
+        std::vector<std::vector<u32>> by_tree(T);  // live leaves of each tree, ascending
+        for (u32 l = 0; l < nl; ++l)
+            if (h_leaf_node[l] >= 0) by_tree[h_leaf_tree[l]].push_back(l);
+        for (int t = 0; t < T; ++t) {
+            // send side: my rows of the tree's leaves, grouped by destination, leaf ascending, member order
+            std::vector<u32> slots;
+            std::vector<u64> send_off(G + 1, 0);
+            for (u32 d = 0; d < G; ++d) {
+                send_off[d] = slots.size();
+                for (u32 l : by_tree[t])
+                    if (l % G == d)
+                        slots.insert(slots.end(), h_members.begin() + h_leaf_off[l], h_members.begin() + h_leaf_off[l] + h_leaf_len[l]);
+            }
+            send_off[G] = slots.size();
+            // receive side: for every source, the owned leaves in ascending order
+            std::vector<RecvSeg> segs;
+            std::vector<u64> recv_off(G + 1, 0);
+            u64 R = 0;
+            for (u32 r = 0; r < G; ++r) {
+                recv_off[r] = R;
+                for (u32 i = 0; i < owned[t].size(); ++i) {
+                    const u32 c = all_len[(size_t)r * nl + owned[t][i]];
+                    if (c) segs.push_back(RecvSeg{R, c, i});
+                    R += c;
+                }
+            }
+            recv_off[G] = R;
+            ZB_REQUIRE(R == h_tree_base[t + 1] - h_tree_base[t], ZB_ERR_STATE, "bucket-sharded layout mismatch");
+            const u64 ns = slots.size();
+            d_slots.ensure(ns ? ns : 1);
+            snd_rows.ensure((ns ? ns : 1) * (u64)dimp);
+            snd_key.ensure(ns ? ns : 1);
+            st_rows.ensure((R ? R : 1) * (u64)dimp);
+            st_key.ensure(R ? R : 1);
+            for (int b = 0; b < 2; ++b) {
+                sort_key[b].ensure(R ? R : 1);
+                sort_val[b].ensure(R ? R : 1);
+            }
+            d_segs.ensure(segs.size() ? segs.size() : 1);
+            sort_tmp.ensure(sort_temp_bytes(R ? R : 1));
+            if (ns) ZB_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), ns * 4, cudaMemcpyHostToDevice, stream));
+            if (!segs.empty()) ZB_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(RecvSeg), cudaMemcpyHostToDevice, stream));
+            launch_pack_rows(d_slots.p, ns, rows.p, ord.p, tomb.p, dimp, snd_rows.p, snd_key.p, stream);
+            const size_t rb = (size_t)dimp * 4;
+            nccl.group_start();
+            for (u32 r = 0; r < G; ++r) {
+                if (r == rank) continue;
+                const u64 sc = send_off[r + 1] - send_off[r], rc = recv_off[r + 1] - recv_off[r];
+                nccl.send(snd_rows.p + send_off[r] * (u64)dimp, sc * rb, (int)r, stream);
+                nccl.send(snd_key.p + send_off[r], sc * 8, (int)r, stream);
+                nccl.recv(st_rows.p + recv_off[r] * (u64)dimp, rc * rb, (int)r, stream);
+                nccl.recv(st_key.p + recv_off[r], rc * 8, (int)r, stream);
+            }
+            nccl.group_end();
+            {   // my own share never leaves the device
+                const u64 sc = send_off[rank + 1] - send_off[rank];
+                ZB_REQUIRE(sc == recv_off[rank + 1] - recv_off[rank], ZB_ERR_STATE, "bucket-sharded self share mismatch");
+                if (sc) {
+                    ZB_CUDA(cudaMemcpyAsync(st_rows.p + recv_off[rank] * (u64)dimp, snd_rows.p + send_off[rank] * (u64)dimp, sc * rb,
+                                            cudaMemcpyDeviceToDevice, stream));
+                    ZB_CUDA(cudaMemcpyAsync(st_key.p + recv_off[rank], snd_key.p + send_off[rank], sc * 8, cudaMemcpyDeviceToDevice, stream));
+                }
+            }
+            launch_seg_keys(d_segs.p, (u32)segs.size(), st_key.p, sort_key[0].p, sort_val[0].p, stream);
+            sort_pairs_u64_u32(sort_tmp.p, sort_tmp.bytes(), sort_key[0].p, sort_key[1].p, sort_val[0].p, sort_val[1].p, R, 64, stream);
+            launch_place_rows(sort_val[1].p, R, st_rows.p, st_key.p, dimp, h_tree_base[t], bm_rows.p, bm_ord.p, bm_tomb.p, stream);
+            // ordinal -> position index of the tree's region
+            sort_pairs_u64_u32(sort_tmp.p, sort_tmp.bytes(), bm_ord.p + h_tree_base[t], srt_ord.p + h_tree_base[t],
+                               d_iota.p + h_tree_base[t], srt_pos.p + h_tree_base[t], R, 40, stream);
+            sync();
+        }
+        if (opt.metric == ZB_METRIC_COSINE) launch_rinv(bm_rows.p, P, dimp, bm_rinv.p, stream);
+        make_row_tile_map(bm_tmap, bm_rows.p, Pa, dimp);
+        sync();
+        bm_positions = P;
         bm_valid = true;
         return true;
     }
@@ -602,8 +765,15 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
         ZB_CUDA(cudaMemsetAsync(d_out_counts, 0, nq * 4, s));
         return;
     }
-    ForestView f = ix->view();
-    const u64 nw = nq * T;
+    const bool sharded = ix->G > 1;
+    const u32 G = ix->G;
+    if (sharded) ix->ensure_bucket_major();  // collective (rebuilds the bucket-sharded store after a forest change)
+    ForestView f = ix->view();              // the plan walks the replicated forest with GLOBAL live leaf counts
+    const ForestView fs = ix->scan_view();  // scoring reads the leaves this rank holds
+    // Sharded: rank r walks queries [r * nqp, (r + 1) * nqp) only and the visit records are allgathered (in place), so the
+    // plan costs 1/G per rank; every rank then holds the identical, complete visit list.
+    const u64 nqp = sharded ? (nq + G - 1) / G : nq;
+    const u64 nw = nqp * (sharded ? G : 1) * T;  // walkers, padded to G equal slices
     ZB_REQUIRE(nw < (1ull << 31), ZB_ERR_INVALID, "batch too large: %llu walkers", (unsigned long long)nw);
     ZB_CUDA(cudaEventRecord(ix->ev[0], s));
     ix->w_counts.ensure(nw + 1);
@@ -611,11 +781,21 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->w_flag.ensure(4);
     ix->scan_tmp(nw + 1);
     u32 h_flag = 0, nv = 0;
+    const u64 q0 = sharded ? std::min<u64>(nq, (u64)ix->rank * nqp) : 0;
+    const u64 qn = sharded ? std::min<u64>(nqp, nq - q0) : nq;
     for (;;) {
         ix->w_visits.ensure(nw * ix->vpw);
         ZB_CUDA(cudaMemsetAsync(ix->w_flag.p, 0, 16, s));
-        ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + nw, 0, 4, s));
-        launch_plan(f, d_q, (u32)nq, (u32)top_k, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_flag.p, s);
+        if (sharded) ZB_CUDA(cudaMemsetAsync(ix->w_counts.p, 0, (nw + 1) * 4, s));
+        else ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + nw, 0, 4, s));
+        const u64 w0 = (u64)(sharded ? ix->rank : 0) * nqp * T;
+        launch_plan(f, d_q + q0 * (u64)ix->dimp, (u32)qn, (u32)top_k, ix->vpw, ix->w_visits.p + w0 * ix->vpw, ix->w_counts.p + w0,
+                    ix->w_flag.p, s);
+        if (sharded) {
+            ix->nccl.allgather(ix->w_counts.p + w0, ix->w_counts.p, nqp * T * 4, s);
+            ix->nccl.allgather(ix->w_visits.p + w0 * ix->vpw, ix->w_visits.p, nqp * T * ix->vpw * sizeof(uint2), s);
+            ix->nccl.allreduce(ix->w_flag.p, 1, Nccl::U32, Nccl::MAX, s);
+        }
         exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->w_counts.p, ix->w_off.p, nw + 1, s);
         ZB_CUDA(cudaMemcpyAsync(&h_flag, ix->w_flag.p, 4, cudaMemcpyDeviceToHost, s));
         ZB_CUDA(cudaMemcpyAsync(&nv, ix->w_off.p + nw, 4, cudaMemcpyDeviceToHost, s));
@@ -634,7 +814,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ZB_CUDA(cudaMemsetAsync(ix->v_pair_len.p + nv, 0, 8, s));
     ZB_CUDA(cudaMemsetAsync(ix->v_ent_len.p + nv, 0, 4, s));
     ZB_CUDA(cudaMemsetAsync(ix->v_done.p, 0, nv + 1, s));
-    launch_compact_visits(f, (u32)nw, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_off.p, ix->v_leaf.p, ix->v_np.p,
+    launch_compact_visits(fs, (u32)nw, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_off.p, ix->v_leaf.p, ix->v_np.p,
                           ix->v_q.p, ix->v_pair_len.p, ix->v_ent_len.p, s);
     exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_ent_len.p, ix->v_ent_off.p, nv + 1, s);
     u32 total_slots = 0;
@@ -653,7 +833,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
             ix->q_rinv.ensure(nq);
             launch_rinv(d_q, nq, ix->dimp, ix->q_rinv.p, s);
         }
-        tile_scan(ix->scan_ws, f, ix->bm_view(), ix->opt.metric, d_q, ix->q_rinv.p, (u32)nq, nv, ix->v_leaf.p, ix->v_np.p, ix->v_q.p,
+        tile_scan(ix->scan_ws, fs, ix->bm_view(), ix->opt.metric, d_q, ix->q_rinv.p, (u32)nq, nv, ix->v_leaf.p, ix->v_np.p, ix->v_q.p,
                   ix->v_ent_off.p, ix->v_pair_len.p, ix->v_done.p, ix->entries.p, (u32)top_k, (u32)ix->p_tile_min_rows,
                   (u32)ix->p_tile_queries, (u32)ix->h_leaf_off.size(), s);
         if (ix->scan_ws.launched) scan_launches = ix->scan_ws.launches + (ix->opt.metric == ZB_METRIC_COSINE ? 1 : 0);
@@ -665,23 +845,35 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ZB_CUDA(cudaMemcpyAsync(&total_pairs, ix->v_pair_off.p + nv, 8, cudaMemcpyDeviceToHost, s));
     ix->sync();
     ix->pair_key.ensure(total_pairs ? total_pairs : 1);
-    launch_score_pairs(f, (int)ix->opt.metric, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, total_pairs,
+    launch_score_pairs(fs, (int)ix->opt.metric, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, total_pairs,
                        ix->pair_key.p, s);
     ZB_CUDA(cudaEventRecord(ix->ev[2], s));
-    if (total_pairs)
-        launch_select_visits(f, nv, ix->v_leaf.p, ix->v_np.p, ix->v_pair_off.p, ix->pair_key.p, ix->v_ent_off.p,
+    if (total_pairs || sharded)  // sharded: visits of leaves held elsewhere still get their (empty) lists written
+        launch_select_visits(fs, nv, ix->v_leaf.p, ix->v_np.p, ix->v_pair_off.p, ix->pair_key.p, ix->v_ent_off.p,
                              ix->entries.p, ix->v_done.p, (u32)top_k, s);
     ZB_CUDA(cudaEventRecord(ix->ev[3], s));
-    const Entry* final_entries = ix->entries.p;
-    if (ix->G > 1) {  // allgather of the per-visit local top-n' lists, then per-visit global top-n' (survey 8e)
-        ix->gathered.ensure((size_t)total_slots * ix->G + 1);
-        ix->nccl.allgather(ix->entries.p, ix->gathered.p, (size_t)total_slots * sizeof(Entry), s);
-        launch_merge_ranks(nv, ix->v_ent_off.p, total_slots, ix->G, ix->gathered.p, ix->entries.p, (u32)top_k, s);
+    if (sharded) {
+        // every visit was scored, whole, by the rank that owns its leaf (Q2's per-visit top-n' is already global): reduce my
+        // visits to a per-query local top-k, allgather those lists over NVLink, merge them per query
+        const u64 nqk = nq * top_k;
+        ix->loc_results.ensure(2 * nqk + 1);
+        ix->o_counts.ensure(nq);
+        launch_merge_queries((u32)nq, T, ix->w_off.p, ix->v_ent_off.p, ix->entries.p, (u32)top_k, ix->loc_results.p,
+                             ix->loc_results.p + nqk, d_out_counts, s);
+        ix->gathered.ensure((size_t)nqk * G + 1);
+        ix->nccl.allgather(ix->loc_results.p, ix->gathered.p, 2 * nqk * 8, s);
+        launch_merge_gathered((u32)nq, (u32)top_k, G, reinterpret_cast<const u64*>(ix->gathered.p), d_out_ord, d_out_bits,
+                              d_out_counts, s);
+    } else {
+        launch_merge_queries((u32)nq, T, ix->w_off.p, ix->v_ent_off.p, ix->entries.p, (u32)top_k, d_out_ord, d_out_bits,
+                             d_out_counts, s);
     }
-    launch_merge_queries((u32)nq, T, ix->w_off.p, ix->v_ent_off.p, final_entries, (u32)top_k, d_out_ord, d_out_bits,
-                         d_out_counts, s);
     ZB_CUDA(cudaEventRecord(ix->ev[4], s));
-    tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved);
+    float tile_ms = 0.f;
+    u32 tiles = 0;
+    tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved, &tile_ms, &tiles);
+    ix->st.last_ms_tile_kernel = tile_ms;
+    ix->st.last_tiles = tiles;
     ix->sync();
     float ms;
     cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]); ix->st.last_ms_plan = ms;
@@ -695,7 +887,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->st.last_tile_pairs = tile_pairs;
     ix->st.last_moved_bytes = moved + total_pairs * (u64)ix->dim * 4;
     ix->st.last_scan_launches = scan_launches + (total_pairs ? 1 : 0);
-    ix->st.last_total_launches += scan_launches + 5 + (ix->G > 1 ? 1 : 0);
+    ix->st.last_total_launches += scan_launches + 5 + (sharded ? 1 : 0);
 }
 
 static const float* stage_queries_device(zb_index* ix, const float* d_q, u64 nq) {
@@ -927,9 +1119,17 @@ static void remove_ordinals(zb_index* ix, u64 n, const u64* ordinals, const u8* 
         } else {
             ZB_CUDA(cudaMemsetAsync(ix->rm_flags.p, 0, n, ix->stream));
         }
-        if (ix->built && ix->bm_valid)
+        if (ix->built && ix->bm_valid && ix->G <= 1)
             launch_bm_tombstone(ix->rm_slots.p, ix->rm_flags.p, (u32)n, ix->slot_pos.p, ix->slot_stride, ix->T, ix->bm_tomb.p, ix->stream);
-        if (ix->G > 1) ix->nccl.allreduce(ix->rm_flags.p, n, Nccl::U8, Nccl::MAX, ix->stream);
+        if (ix->G > 1) {
+            ix->nccl.allreduce(ix->rm_flags.p, n, Nccl::U8, Nccl::MAX, ix->stream);
+            if (ix->built && ix->bm_valid) {  // the copies of a removed row sit on the ranks that own its T leaves
+                ix->rm_ords.ensure(n);
+                ZB_CUDA(cudaMemcpyAsync(ix->rm_ords.p, ordinals, n * 8, cudaMemcpyHostToDevice, ix->stream));
+                launch_bm_tomb_lookup(ix->rm_ords.p, ix->rm_flags.p, n, ix->T, ix->d_tree_base.p, ix->srt_ord.p, ix->srt_pos.p,
+                                      ix->bm_tomb.p, ix->stream);
+            }
+        }
         ZB_CUDA(cudaMemcpyAsync(flags.data(), ix->rm_flags.p, n, cudaMemcpyDeviceToHost, ix->stream));
     }
     ix->refresh_plan_counts();
@@ -1004,7 +1204,7 @@ int zb_index_search_batch_device(zb_index* ix, uint64_t nq, const float* d_q, ui
     ZB_REQUIRE(top_k <= ZB_MAX_TOPK, ZB_ERR_INVALID, "top_k %llu exceeds %d", (unsigned long long)top_k, ZB_MAX_TOPK);
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->use_device();
-    const u64 chunk = 32768;
+    const u64 chunk = 131072;
     for (u64 q0 = 0; q0 < nq; q0 += chunk) {
         u64 c = std::min<u64>(chunk, nq - q0);
         const float* q = stage_queries_device(ix, d_q + q0 * (u64)ix->dim, c);
@@ -1022,7 +1222,7 @@ int zb_index_search_batch(zb_index* ix, uint64_t nq, const float* queries, uint6
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->use_device();
     cudaStream_t s = ix->stream;
-    const u64 chunk = 32768;
+    const u64 chunk = 131072;
     std::vector<u64> ord_tmp;
     if (!out_ordinals && out_ids16) ord_tmp.resize(std::min<u64>(chunk, nq) * top_k);
     for (u64 q0 = 0; q0 < nq; q0 += chunk) {

@@ -1,6 +1,7 @@
 // zb_kernels.cu -- plan / score / select / merge / hash / build / mutation kernels (sm_100a).
 // The bandwidth-critical leaf-tile scan lives in zb_scan.cu; the kernels here are the general path that is
 // correct for every forest shape (deep trees with tiny leaves included) and the build/mutation machinery.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "zb_kernels.cuh"
@@ -131,7 +132,13 @@ __global__ void __launch_bounds__(128) score_pairs_kernel(ForestView f, const fl
     const int sub = threadIdx.x & 3;
     const unsigned mask = quad_mask();
     u32 v = s_v0;
-    while (pair_off[v + 1] <= p) ++v;
+    {   // last v with pair_off[v] <= p (a binary search: runs of empty visits can be tens of thousands long)
+        u32 hi = nv;
+        while (hi - v > 1) {
+            const u32 mid = (v + hi) >> 1;
+            if (pair_off[mid] <= p) v = mid; else hi = mid;
+        }
+    }
     const u32 leaf = vleaf[v];
     const u32 slot = f.members[f.leaf_off[leaf] + (long long)(p - pair_off[v])];
     if (tomb_test(f.tomb, slot)) {
@@ -797,6 +804,143 @@ void launch_pair_above(const float* d_coef, const float* d_cst, const float* d_x
     pair_above_kernel<<<(u32)((n + 31) / 32), 128, 0, s>>>(d_coef, d_cst, d_x, n, dimp, d_out);
 }
 
+
+// =====================================================================================================
+// bucket-sharded store (G > 1): leaf l lives, whole, on rank l % G.  The raw row store stays sharded by
+// ordinal (build / insert / delete bookkeeping); these kernels move each leaf's rows to its owner once per
+// forest change and keep the position-major tombstones in step with deletes.
+// =====================================================================================================
+// sender: out_rows[i] = rows[slots[i]], out_key[i] = ordinal | tombstone << 63 (one warp per row)
+__global__ void __launch_bounds__(256) pack_rows_kernel(const u32* __restrict__ slots, u64 n, const float* __restrict__ rows,
+                                                        const u64* __restrict__ ord, const u32* __restrict__ tomb, int dimp,
+                                                        float* __restrict__ out_rows, u64* __restrict__ out_key) {
+    const u64 i = (u64)blockIdx.x * 8ull + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const u32 slot = slots[i];
+    const float4* src = reinterpret_cast<const float4*>(rows + (size_t)slot * dimp);
+    float4* dst = reinterpret_cast<float4*>(out_rows + (size_t)i * dimp);
+    for (int c = lane; c < dimp / 4; c += 32) dst[c] = __ldg(src + c);
+    if (lane == 0) out_key[i] = ord[slot] | (tomb_test(tomb, slot) ? (1ull << 63) : 0ull);
+}
+void launch_pack_rows(const u32* d_slots, u64 n, const float* d_rows, const u64* d_ord, const u32* d_tomb, int dimp,
+                      float* d_out_rows, u64* d_out_key, cudaStream_t s) {
+    if (!n) return;
+    pack_rows_kernel<<<(u32)((n + 7) / 8), 256, 0, s>>>(d_slots, n, d_rows, d_ord, d_tomb, dimp, d_out_rows, d_out_key);
+}
+// receiver: element i of segment (source rank, leaf) gets sort key (leaf sequence number << 40) | ordinal, so that the
+// sorted order is leaf-major and ordinal-ascending inside a leaf (position order == ordinal order, D3)
+__global__ void __launch_bounds__(128) seg_keys_kernel(const RecvSeg* __restrict__ segs, const u64* __restrict__ st_key,
+                                                       u64* __restrict__ sort_key, u32* __restrict__ sort_val) {
+    const RecvSeg sg = segs[blockIdx.x];
+    for (u32 j = threadIdx.x; j < sg.count; j += blockDim.x) {
+        const u64 i = sg.start + j;
+        sort_key[i] = ((u64)sg.leaf_seq << 40) | (st_key[i] & ((1ull << 40) - 1));
+        sort_val[i] = (u32)i;
+    }
+}
+void launch_seg_keys(const RecvSeg* d_segs, u32 nsegs, const u64* d_st_key, u64* d_sort_key, u32* d_sort_val, cudaStream_t s) {
+    if (!nsegs) return;
+    seg_keys_kernel<<<nsegs, 128, 0, s>>>(d_segs, d_st_key, d_sort_key, d_sort_val);
+}
+// position base + p of the bucket-major store receives staging element perm[p] (one warp per row)
+__global__ void __launch_bounds__(256) place_rows_kernel(const u32* __restrict__ perm, u64 n, const float* __restrict__ st_rows,
+                                                         const u64* __restrict__ st_key, int dimp, u64 base,
+                                                         float* __restrict__ bm_rows, u64* __restrict__ bm_ord,
+                                                         u32* __restrict__ bm_tomb) {
+    const u64 p = (u64)blockIdx.x * 8ull + (threadIdx.x >> 5);
+    if (p >= n) return;
+    const int lane = threadIdx.x & 31;
+    const u32 src_i = perm[p];
+    const float4* src = reinterpret_cast<const float4*>(st_rows + (size_t)src_i * dimp);
+    float4* dst = reinterpret_cast<float4*>(bm_rows + (size_t)(base + p) * dimp);
+    for (int c = lane; c < dimp / 4; c += 32) dst[c] = src[c];
+    if (lane == 0) {
+        const u64 k = st_key[src_i];
+        bm_ord[base + p] = k & ~(1ull << 63);
+        if (k >> 63) atomicOr(&bm_tomb[(base + p) >> 5], 1u << ((base + p) & 31));
+    }
+}
+void launch_place_rows(const u32* d_perm, u64 n, const float* d_st_rows, const u64* d_st_key, int dimp, u64 base,
+                       float* d_bm_rows, u64* d_bm_ord, u32* d_bm_tomb, cudaStream_t s) {
+    if (!n) return;
+    place_rows_kernel<<<(u32)((n + 7) / 8), 256, 0, s>>>(d_perm, n, d_st_rows, d_st_key, dimp, base, d_bm_rows, d_bm_ord, d_bm_tomb);
+}
+__global__ void iota_u32_kernel(u32* d, u64 n, u32 first) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = first + (u32)i;
+}
+void launch_iota_u32(u32* d, u64 n, u32 first, cudaStream_t s) {
+    if (!n) return;
+    iota_u32_kernel<<<(u32)((n + 255) / 256), 256, 0, s>>>(d, n, first);
+}
+// delete on a bucket-sharded store: every rank sees the whole batch; for each removed ordinal and each tree, find the
+// row's position (if its leaf lives here) in the tree's ordinal-sorted index and set the position-major tombstone bit
+__global__ void bm_tomb_lookup_kernel(const u64* __restrict__ ords, const u8* __restrict__ flags, u64 n, int num_trees,
+                                      const u64* __restrict__ tree_base, const u64* __restrict__ srt_ord,
+                                      const u32* __restrict__ srt_pos, u32* __restrict__ bm_tomb) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * (u64)num_trees) return;
+    const u64 r = i / (u64)num_trees;
+    const int t = (int)(i - r * (u64)num_trees);
+    if (!flags[r]) return;
+    const u64 o = ords[r];
+    u64 lo = tree_base[t], hi = tree_base[t + 1];
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (srt_ord[mid] < o) lo = mid + 1; else hi = mid;
+    }
+    if (lo < tree_base[t + 1] && srt_ord[lo] == o) {
+        const u32 pos = srt_pos[lo];
+        atomicOr(&bm_tomb[pos >> 5], 1u << (pos & 31));
+    }
+}
+void launch_bm_tomb_lookup(const u64* d_ords, const u8* d_flags, u64 n, int num_trees, const u64* d_tree_base,
+                           const u64* d_srt_ord, const u32* d_srt_pos, u32* d_bm_tomb, cudaStream_t s) {
+    const u64 tot = n * (u64)num_trees;
+    if (!tot) return;
+    bm_tomb_lookup_kernel<<<(u32)((tot + 255) / 256), 256, 0, s>>>(d_ords, d_flags, n, num_trees, d_tree_base, d_srt_ord, d_srt_pos, d_bm_tomb);
+}
+// final merge of the ranks' per-query local top-k lists (each rank: [ord nq*k | bits nq*k]): union, dedup by id (the same
+// row can be reached through trees whose leaves live on different ranks), sort (bits, id), take top_k (lsh.rs:550,:561-564)
+struct GatheredLoader {
+    const u64* g;
+    u64 per_rank, nqk, qbase;
+    u32 k;
+    __device__ Entry operator()(long long i) const {
+        const u64 r = (u64)i / k, j = (u64)i % k;
+        const u64* b = g + r * per_rank + qbase + j;
+        return Entry{b[nqk], b[0]};
+    }
+};
+__global__ void __launch_bounds__(TOPK_THREADS) merge_gathered_kernel(u32 nq, u32 top_k, u32 nranks, const u64* __restrict__ gathered,
+                                                                      u64* __restrict__ out_ord, u64* __restrict__ out_bits,
+                                                                      u32* __restrict__ out_counts, int pmax, int kmax) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Entry* buf = reinterpret_cast<Entry*>(smem);
+    Entry* keep = buf + pmax;
+    int* s_warp = reinterpret_cast<int*>(keep + kmax);
+    const u32 q = blockIdx.x;
+    if (q >= nq) return;
+    const u64 nqk = (u64)nq * top_k;
+    GatheredLoader ld{gathered, 2 * nqk, nqk, (u64)q * top_k, top_k};
+    int kept = segment_topk(buf, keep, s_warp, ld, (long long)top_k * nranks, (int)top_k, pmax);
+    for (u32 i = threadIdx.x; i < top_k; i += TOPK_THREADS) {
+        bool ok = (int)i < kept;
+        out_ord[(size_t)q * top_k + i] = ok ? keep[i].ord : ZB_SENTINEL;
+        out_bits[(size_t)q * top_k + i] = ok ? keep[i].key : ZB_SENTINEL;
+    }
+    if (threadIdx.x == 0) out_counts[q] = (u32)kept;
+}
+void launch_merge_gathered(u32 nq, u32 top_k, u32 nranks, const u64* d_gathered, u64* d_out_ord, u64* d_out_bits,
+                           u32* d_out_counts, cudaStream_t s) {
+    if (!nq || !top_k) return;
+    int pmax = topk_pmax(top_k), kmax = (int)top_k;
+    size_t smem = topk_smem(pmax, kmax);
+    set_smem(merge_gathered_kernel, smem);
+    merge_gathered_kernel<<<nq, TOPK_THREADS, smem, s>>>(nq, top_k, nranks, d_gathered, d_out_ord, d_out_bits, d_out_counts, pmax, kmax);
+}
+
 // =====================================================================================================
 // cub scans
 // =====================================================================================================
@@ -813,6 +957,17 @@ void exclusive_scan_u32(void* d_temp, size_t temp_bytes, const u32* d_in, u32* d
 void exclusive_scan_u64(void* d_temp, size_t temp_bytes, const u64* d_in, u64* d_out, size_t n, cudaStream_t s) {
     if (!n) return;
     cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_in, d_out, (long long)n, s);
+}
+
+size_t sort_temp_bytes(size_t n) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const u64*)nullptr, (u64*)nullptr, (const u32*)nullptr, (u32*)nullptr, (long long)n);
+    return b + 256;
+}
+void sort_pairs_u64_u32(void* d_temp, size_t temp_bytes, const u64* d_kin, u64* d_kout, const u32* d_vin, u32* d_vout, size_t n,
+                        int end_bit, cudaStream_t s) {
+    if (!n) return;
+    cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_kin, d_kout, d_vin, d_vout, (long long)n, 0, end_bit, s);
 }
 
 }  // namespace zb

@@ -42,6 +42,12 @@ struct Tile {         // 64 consecutive positions of one segment / leaf
     long long start;
 };
 
+struct RecvSeg {      // rows of one (source rank, owned leaf) pair in the receive staging area (bucket-sharded store build)
+    u64 start;
+    u32 count;
+    u32 leaf_seq;     // sequence number of the leaf among the leaves this rank owns in the tree being built
+};
+
 // ---- plan (tree_result control flow, lsh.rs:290-348) ----
 void launch_plan(const ForestView& f, const float* d_queries, u32 nq, u32 top_k, u32 vpw, uint2* d_wvisits,
                  u32* d_wcounts, u32* d_overflow, cudaStream_t s);
@@ -91,6 +97,21 @@ void launch_synth(float* d_out, u64 first_row, u64 row_stride, u64 n, u32 dim, u
 void launch_sq_norms(const float* d_x, u64 n, int dimp, float* d_out, cudaStream_t s);
 void launch_pair_metric(int metric, const float* d_a, const float* d_b, u64 n, int dimp, u64* d_out, cudaStream_t s);
 void launch_pair_above(const float* d_coef, const float* d_cst, const float* d_x, u64 n, int dimp, u8* d_out, cudaStream_t s);
+
+// ---- bucket-sharded store (G > 1) ----
+void launch_pack_rows(const u32* d_slots, u64 n, const float* d_rows, const u64* d_ord, const u32* d_tomb, int dimp,
+                      float* d_out_rows, u64* d_out_key, cudaStream_t s);
+void launch_seg_keys(const RecvSeg* d_segs, u32 nsegs, const u64* d_st_key, u64* d_sort_key, u32* d_sort_val, cudaStream_t s);
+void launch_place_rows(const u32* d_perm, u64 n, const float* d_st_rows, const u64* d_st_key, int dimp, u64 base,
+                       float* d_bm_rows, u64* d_bm_ord, u32* d_bm_tomb, cudaStream_t s);
+void launch_iota_u32(u32* d, u64 n, u32 first, cudaStream_t s);
+void launch_bm_tomb_lookup(const u64* d_ords, const u8* d_flags, u64 n, int num_trees, const u64* d_tree_base,
+                           const u64* d_srt_ord, const u32* d_srt_pos, u32* d_bm_tomb, cudaStream_t s);
+void launch_merge_gathered(u32 nq, u32 top_k, u32 nranks, const u64* d_gathered, u64* d_out_ord, u64* d_out_bits,
+                           u32* d_out_counts, cudaStream_t s);
+size_t sort_temp_bytes(size_t n);
+void sort_pairs_u64_u32(void* d_temp, size_t temp_bytes, const u64* d_kin, u64* d_kout, const u32* d_vin, u32* d_vout, size_t n,
+                        int end_bit, cudaStream_t s);
 
 // cub wrappers (temp storage managed by caller)
 size_t scan_temp_bytes(size_t n);

@@ -15,6 +15,9 @@ typedef int (*fn_comm_init_rank)(void**, int, ncclUniqueId_, int);
 typedef int (*fn_comm_destroy)(void*);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_send)(const void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_recv)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_group)(void);
 typedef const char* (*fn_get_error_string)(int);
 
 struct Api {
@@ -24,6 +27,9 @@ struct Api {
     fn_comm_destroy comm_destroy = nullptr;
     fn_all_reduce all_reduce = nullptr;
     fn_all_gather all_gather = nullptr;
+    fn_send send = nullptr;
+    fn_recv recv = nullptr;
+    fn_group group_start = nullptr, group_end = nullptr;
     fn_get_error_string get_error_string = nullptr;
 };
 
@@ -49,8 +55,13 @@ Api& api() {
     a.comm_destroy = (fn_comm_destroy)dlsym(a.handle, "ncclCommDestroy");
     a.all_reduce = (fn_all_reduce)dlsym(a.handle, "ncclAllReduce");
     a.all_gather = (fn_all_gather)dlsym(a.handle, "ncclAllGather");
+    a.send = (fn_send)dlsym(a.handle, "ncclSend");
+    a.recv = (fn_recv)dlsym(a.handle, "ncclRecv");
+    a.group_start = (fn_group)dlsym(a.handle, "ncclGroupStart");
+    a.group_end = (fn_group)dlsym(a.handle, "ncclGroupEnd");
     a.get_error_string = (fn_get_error_string)dlsym(a.handle, "ncclGetErrorString");
-    ZB_REQUIRE(a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.all_reduce && a.all_gather, ZB_ERR_COMM,
+    ZB_REQUIRE(a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.all_reduce && a.all_gather && a.send && a.recv &&
+                   a.group_start && a.group_end, ZB_ERR_COMM,
                "libnccl is missing required symbols");
     return a;
 }
@@ -91,6 +102,17 @@ void Nccl::allreduce(void* d_buf, size_t count, Type t, Op op, cudaStream_t s) {
 void Nccl::allgather(const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t s) {
     if (!bytes_per_rank) return;
     check(api().all_gather(d_send, d_recv, bytes_per_rank, (int)U8, comm, s), "ncclAllGather");
+}
+
+void Nccl::group_start() { check(api().group_start(), "ncclGroupStart"); }
+void Nccl::group_end() { check(api().group_end(), "ncclGroupEnd"); }
+void Nccl::send(const void* d_buf, size_t bytes, int peer, cudaStream_t s) {
+    if (!bytes) return;
+    check(api().send(d_buf, bytes, (int)U8, peer, comm, s), "ncclSend");
+}
+void Nccl::recv(void* d_buf, size_t bytes, int peer, cudaStream_t s) {
+    if (!bytes) return;
+    check(api().recv(d_buf, bytes, (int)U8, peer, comm, s), "ncclRecv");
 }
 
 }  // namespace zb

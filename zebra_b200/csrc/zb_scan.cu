@@ -703,6 +703,7 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
     tp.tile_first = ws.tile_first.p;
     tp.tile_count = ws.tile_cnt.p;
     tp.ntiles = ws.tile_start.p + nleaves;
+    ws.ntiles_ptr = tp.ntiles;
     tp.tile_counter = ws.counters.p;
     tp.order = ws.order.p;
     tp.v_np = v_np;
@@ -721,6 +722,11 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
     tp.nst = nst;
     const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(bm.tmap);
     const int grid = sms;
+    if (!ws.ev0) {
+        ZB_CUDA(cudaEventCreate(&ws.ev0));
+        ZB_CUDA(cudaEventCreate(&ws.ev1));
+    }
+    ZB_CUDA(cudaEventRecord(ws.ev0, s));
     if (metric == 0) {
         ZB_CUDA(cudaFuncSetAttribute(tile_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tile_scan_kernel<0><<<grid, TS_THREADS, smem, s>>>(tmap, f, tp);
@@ -732,18 +738,24 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
         tile_scan_kernel<2><<<grid, TS_THREADS, smem, s>>>(tmap, f, tp);
     }
     ZB_CUDA(cudaGetLastError());
+    ZB_CUDA(cudaEventRecord(ws.ev1, s));
     ws.launched = true;
     ws.launches = 7;
 }
 
 // Statistics of the last tile_scan launch (visits, scored pairs, bytes asked of HBM by design); call after the
 // stream has been synchronised.
-void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes) {
+void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes, float* kernel_ms,
+                     u32* tiles) {
     *tile_visits = *tile_pairs = *moved_bytes = 0;
+    *kernel_ms = 0.f;
+    *tiles = 0;
     if (!ws.launched) return;
     u64 h[3] = {0, 0, 0};
     ZB_CUDA(cudaMemcpyAsync(h, reinterpret_cast<u64*>(ws.counters.p + 4), 24, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaMemcpyAsync(tiles, ws.ntiles_ptr, 4, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(kernel_ms, ws.ev0, ws.ev1);
     *tile_visits = h[0];
     *tile_pairs = h[1];
     *moved_bytes = h[2];

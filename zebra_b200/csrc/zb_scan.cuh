@@ -12,6 +12,8 @@ struct ScanWorkspace {
     DBuf<u8> tmp;
     bool launched = false;
     u32 launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the tile kernel alone
+    const u32* ntiles_ptr = nullptr;           // device scalar: tiles of the last launch
 };
 
 // Device view of the bucket-major store: position p of the forest's member array holds a copy of row members[p],
@@ -39,6 +41,7 @@ void launch_rinv(const float* d_x, u64 n, int dimp, double* d_out, cudaStream_t 
 void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u32 metric, const float* d_q, const double* d_q_rinv,
                u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
                u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s);
-void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes);
+void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes, float* kernel_ms,
+                     u32* tiles);
 
 }  // namespace zb

@@ -127,12 +127,13 @@ struct zb_index {
     DBuf<u64> d_tree_base, rm_ords;
     std::vector<u64> h_tree_base;
     DBuf<u64> loc_results;      // this rank's per-query top-k over the leaves it owns: [ord nq*k | bits nq*k]
+    DBuf<u64> res_all;          // finished query slices of all ranks
 
     // ---- workspaces ----
     DBuf<u8> cub_tmp;
-    DBuf<u32> w_counts, w_off, w_flag;
+    DBuf<u32> w_counts, w_off, w_flag, w_own;
     DBuf<uint2> w_visits;
-    u32 vpw = 8;
+    u32 vpw = 8;   // slots per walker in the visit plan: 1 header + up to vpw - 1 visits (grows on demand)
     DBuf<u32> v_leaf, v_np, v_q, v_ent_len, v_ent_off;
     DBuf<u64> v_pair_len, v_pair_off, pair_key;
     DBuf<u8> v_done;
@@ -189,6 +190,34 @@ struct zb_index {
             f.row_norm = nullptr;
         }
         return f;
+    }
+    // ZB_TRACE=1: sub-phase times of every search call (CUDA events on the index's stream), printed by rank 0
+    bool trace_on = getenv("ZB_TRACE") != nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
+    size_t trace_n = 0;
+    void trace_mark(const char* what) {
+        if (!trace_on) return;
+        if (trace_n == trace_ev.size()) {
+            cudaEvent_t e;
+            ZB_CUDA(cudaEventCreate(&e));
+            trace_ev.push_back({what, e});
+        }
+        trace_ev[trace_n].first = what;
+        ZB_CUDA(cudaEventRecord(trace_ev[trace_n++].second, stream));
+    }
+    void trace_dump() {
+        if (!trace_on || trace_n < 2) { trace_n = 0; return; }
+        sync();
+        if (rank == 0) {
+            fprintf(stderr, "[zb trace]");
+            for (size_t i = 1; i < trace_n; ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, trace_ev[i - 1].second, trace_ev[i].second);
+                fprintf(stderr, " %s %.3f |", trace_ev[i].first, ms);
+            }
+            fprintf(stderr, "\n");
+        }
+        trace_n = 0;
     }
     void sync() { ZB_CUDA(cudaStreamSynchronize(stream)); }
     void use_device() { ZB_CUDA(cudaSetDevice(device)); }
@@ -776,6 +805,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     const u64 nw = nqp * (sharded ? G : 1) * T;  // walkers, padded to G equal slices
     ZB_REQUIRE(nw < (1ull << 31), ZB_ERR_INVALID, "batch too large: %llu walkers", (unsigned long long)nw);
     ZB_CUDA(cudaEventRecord(ix->ev[0], s));
+    ix->trace_mark("start");
     ix->w_counts.ensure(nw + 1);
     ix->w_off.ensure(nw + 1);
     ix->w_flag.ensure(4);
@@ -786,17 +816,24 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     for (;;) {
         ix->w_visits.ensure(nw * ix->vpw);
         ZB_CUDA(cudaMemsetAsync(ix->w_flag.p, 0, 16, s));
-        if (sharded) ZB_CUDA(cudaMemsetAsync(ix->w_counts.p, 0, (nw + 1) * 4, s));
-        else ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + nw, 0, 4, s));
+        ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + nw, 0, 4, s));
         const u64 w0 = (u64)(sharded ? ix->rank : 0) * nqp * T;
+        // padding walkers of my slice (queries beyond nq) must carry an empty header
+        if (sharded && qn < nqp) ZB_CUDA(cudaMemsetAsync(ix->w_visits.p + (w0 + qn * T) * ix->vpw, 0, (nqp - qn) * T * ix->vpw * sizeof(uint2), s));
         launch_plan(f, d_q + q0 * (u64)ix->dimp, (u32)qn, (u32)top_k, ix->vpw, ix->w_visits.p + w0 * ix->vpw, ix->w_counts.p + w0,
                     ix->w_flag.p, s);
+        ix->trace_mark("plan walk");
         if (sharded) {
-            ix->nccl.allgather(ix->w_counts.p + w0, ix->w_counts.p, nqp * T * 4, s);
+            // one collective: every walker's region starts with its header {count, overflow}, so counts and the replan flag
+            // travel with the visit records
             ix->nccl.allgather(ix->w_visits.p + w0 * ix->vpw, ix->w_visits.p, nqp * T * ix->vpw * sizeof(uint2), s);
-            ix->nccl.allreduce(ix->w_flag.p, 1, Nccl::U32, Nccl::MAX, s);
+            ix->trace_mark("allgather of visits");
+            // from here on this rank only deals with the visits of the leaves it owns
+            ix->w_own.ensure(nw + 1);
+            ZB_CUDA(cudaMemsetAsync(ix->w_own.p + nw, 0, 4, s));
+            launch_own_counts((u32)nw, ix->vpw, ix->w_visits.p, G, ix->rank, ix->w_counts.p, ix->w_own.p, ix->w_flag.p, s);
         }
-        exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->w_counts.p, ix->w_off.p, nw + 1, s);
+        exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), sharded ? ix->w_own.p : ix->w_counts.p, ix->w_off.p, nw + 1, s);
         ZB_CUDA(cudaMemcpyAsync(&h_flag, ix->w_flag.p, 4, cudaMemcpyDeviceToHost, s));
         ZB_CUDA(cudaMemcpyAsync(&nv, ix->w_off.p + nw, 4, cudaMemcpyDeviceToHost, s));
         ix->sync();
@@ -814,13 +851,14 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ZB_CUDA(cudaMemsetAsync(ix->v_pair_len.p + nv, 0, 8, s));
     ZB_CUDA(cudaMemsetAsync(ix->v_ent_len.p + nv, 0, 4, s));
     ZB_CUDA(cudaMemsetAsync(ix->v_done.p, 0, nv + 1, s));
-    launch_compact_visits(fs, (u32)nw, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_off.p, ix->v_leaf.p, ix->v_np.p,
-                          ix->v_q.p, ix->v_pair_len.p, ix->v_ent_len.p, s);
+    launch_compact_visits(fs, (u32)nw, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_off.p, G, ix->rank, ix->v_leaf.p,
+                          ix->v_np.p, ix->v_q.p, ix->v_pair_len.p, ix->v_ent_len.p, s);
     exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_ent_len.p, ix->v_ent_off.p, nv + 1, s);
     u32 total_slots = 0;
     ZB_CUDA(cudaMemcpyAsync(&total_slots, ix->v_ent_off.p + nv, 4, cudaMemcpyDeviceToHost, s));
     ix->st.last_total_launches += 2;
     ZB_CUDA(cudaEventRecord(ix->ev[1], s));
+    ix->trace_mark("compact");
 
     // ---- fused leaf-tile scan for visits of large leaves (zb_scan.cu); marks v_done and shrinks pair_len ----
     ix->sync();
@@ -848,27 +886,56 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     launch_score_pairs(fs, (int)ix->opt.metric, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, total_pairs,
                        ix->pair_key.p, s);
     ZB_CUDA(cudaEventRecord(ix->ev[2], s));
-    if (total_pairs || sharded)  // sharded: visits of leaves held elsewhere still get their (empty) lists written
+    ix->trace_mark("scan");
+    if (total_pairs)
         launch_select_visits(fs, nv, ix->v_leaf.p, ix->v_np.p, ix->v_pair_off.p, ix->pair_key.p, ix->v_ent_off.p,
                              ix->entries.p, ix->v_done.p, (u32)top_k, s);
     ZB_CUDA(cudaEventRecord(ix->ev[3], s));
+    ix->trace_mark("select");
     if (sharded) {
         // every visit was scored, whole, by the rank that owns its leaf (Q2's per-visit top-n' is already global): reduce my
-        // visits to a per-query local top-k, allgather those lists over NVLink, merge them per query
-        const u64 nqk = nq * top_k;
-        ix->loc_results.ensure(2 * nqk + 1);
+        // visits to a per-query local top-k; all-to-all: the lists of query slice r go to rank r, which merges the G lists of
+        // each of its queries; the finished slices are allgathered.
+        const u64 nsk = nqp * top_k;          // u64 per (rank, array) slice
+        const u64 nqP = nqp * G;
+        u64* loc_ord = nullptr;
+        u64* loc_bits = nullptr;
+        ix->loc_results.ensure(2 * nqP * top_k + 1);
+        loc_ord = ix->loc_results.p;
+        loc_bits = loc_ord + nqP * top_k;
+        if (nqP > nq) {  // padding queries of the last slice: empty lists
+            ZB_CUDA(cudaMemsetAsync(loc_ord + nq * top_k, 0xFF, (nqP - nq) * top_k * 8, s));
+            ZB_CUDA(cudaMemsetAsync(loc_bits + nq * top_k, 0xFF, (nqP - nq) * top_k * 8, s));
+        }
         ix->o_counts.ensure(nq);
-        launch_merge_queries((u32)nq, T, ix->w_off.p, ix->v_ent_off.p, ix->entries.p, (u32)top_k, ix->loc_results.p,
-                             ix->loc_results.p + nqk, d_out_counts, s);
-        ix->gathered.ensure((size_t)nqk * G + 1);
-        ix->nccl.allgather(ix->loc_results.p, ix->gathered.p, 2 * nqk * 8, s);
-        launch_merge_gathered((u32)nq, (u32)top_k, G, reinterpret_cast<const u64*>(ix->gathered.p), d_out_ord, d_out_bits,
-                              d_out_counts, s);
+        launch_merge_queries((u32)nq, T, ix->w_off.p, ix->v_ent_off.p, ix->entries.p, (u32)top_k, loc_ord, loc_bits, ix->o_counts.p, s);
+        ix->trace_mark("local merge");
+        u64* gath = reinterpret_cast<u64*>((ix->gathered.ensure((size_t)nsk * G + 1), ix->gathered.p));  // [G][ord nsk | bits nsk]
+        ix->nccl.group_start();
+        for (u32 r = 0; r < G; ++r) {
+            if (r == ix->rank) continue;
+            ix->nccl.send(loc_ord + (u64)r * nsk, nsk * 8, (int)r, s);
+            ix->nccl.send(loc_bits + (u64)r * nsk, nsk * 8, (int)r, s);
+            ix->nccl.recv(gath + (u64)r * 2 * nsk, nsk * 8, (int)r, s);
+            ix->nccl.recv(gath + (u64)r * 2 * nsk + nsk, nsk * 8, (int)r, s);
+        }
+        ix->nccl.group_end();
+        ZB_CUDA(cudaMemcpyAsync(gath + (u64)ix->rank * 2 * nsk, loc_ord + (u64)ix->rank * nsk, nsk * 8, cudaMemcpyDeviceToDevice, s));
+        ZB_CUDA(cudaMemcpyAsync(gath + (u64)ix->rank * 2 * nsk + nsk, loc_bits + (u64)ix->rank * nsk, nsk * 8, cudaMemcpyDeviceToDevice, s));
+        ix->trace_mark("all-to-all of local top-k");
+        const u64 blk = 2 * nsk + (nqp + 1) / 2;  // [ord nsk | bits nsk | counts nqp u32]
+        ix->res_all.ensure(blk * G + 1);
+        u64* mine = ix->res_all.p + (u64)ix->rank * blk;
+        launch_merge_gathered((u32)qn, (u32)nqp, (u32)top_k, G, gath, mine, mine + nsk, reinterpret_cast<u32*>(mine + 2 * nsk), s);
+        ix->trace_mark("final merge of my slice");
+        ix->nccl.allgather(mine, ix->res_all.p, blk * 8, s);
+        launch_unpack_results(ix->res_all.p, blk, (u32)nq, (u32)nqp, (u32)top_k, d_out_ord, d_out_bits, d_out_counts, s);
     } else {
         launch_merge_queries((u32)nq, T, ix->w_off.p, ix->v_ent_off.p, ix->entries.p, (u32)top_k, d_out_ord, d_out_bits,
                              d_out_counts, s);
     }
     ZB_CUDA(cudaEventRecord(ix->ev[4], s));
+    ix->trace_mark(sharded ? "allgather of results" : "merge");
     float tile_ms = 0.f;
     u32 tiles = 0;
     tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved, &tile_ms, &tiles);
@@ -876,6 +943,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->st.last_tiles = tiles;
     ix->sync();
     float ms;
+    ix->trace_dump();
     cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]); ix->st.last_ms_plan = ms;
     cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]); ix->st.last_ms_scan = ms;
     cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3]); ix->st.last_ms_select = ms;

@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const floa
     int sp = 0;
     int cur = f.roots[t];
     int n = (int)top_k;
-    u32 nvis = 0;
+    u32 nvis = 0, ovf = 0;
+    const u32 cap = vpw - 1;  // slot 0 of a walker's region is its header {visit count, overflow flag}
     for (;;) {
         int4 nd = f.nodes[cur];
         while (nd.x >= 0) {  // inner node: lsh.rs:333-338
@@ -46,13 +47,13 @@ __global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const floa
             nd = f.nodes[cur];
         }
         if (sp > ZB_MAX_DEPTH + 2) {  // cannot happen for forests accepted by the host (depth checked)
-            if (sub == 0) atomicExch(overflow, 2u);
+            ovf = 2;
             break;
         }
         const int live = (int)f.leaf_plan[nd.w];
         const int r = live < n ? live : n;  // lsh.rs:307 / :329
         if (live > 0 && n > 0) {
-            if (nvis < vpw && sub == 0) wvisits[(size_t)w * vpw + nvis] = make_uint2((u32)nd.w, (u32)n);
+            if (nvis < cap && sub == 0) wvisits[(size_t)w * vpw + 1 + nvis] = make_uint2((u32)nd.w, (u32)n);
             ++nvis;
         }
         bool again = false;
@@ -69,8 +70,11 @@ __global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const floa
         if (!again) break;
     }
     if (sub == 0) {
-        wcounts[w] = nvis < vpw ? nvis : vpw;
-        if (nvis > vpw) atomicMax(overflow, 1u);
+        if (nvis > cap && !ovf) ovf = 1;
+        const u32 c = nvis < cap ? nvis : cap;
+        wcounts[w] = c;
+        wvisits[(size_t)w * vpw] = make_uint2(c, ovf);  // the header travels with the visits (sharded: ONE allgather)
+        if (ovf) atomicMax(overflow, ovf);
     }
 }
 
@@ -81,8 +85,27 @@ void launch_plan(const ForestView& f, const float* d_queries, u32 nq, u32 top_k,
     plan_walk_kernel<<<(nwalkers + 31) / 32, 128, 0, s>>>(f, d_queries, nq, top_k, vpw, d_wvisits, d_wcounts, d_overflow);
 }
 
+// Sharded: the visit records of all walkers are on every rank; a rank keeps only the visits of the leaves it owns
+// (leaf % G == rank).  own_counts gives the per-walker counts the compaction offsets are scanned from.
+__global__ void own_counts_kernel(u32 nwalkers, u32 vpw, const uint2* __restrict__ wvisits, u32 G, u32 rank,
+                                  u32* __restrict__ wcounts, u32* __restrict__ wown, u32* __restrict__ overflow) {
+    u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwalkers) return;
+    const uint2 hdr = wvisits[(size_t)w * vpw];
+    const u32 c = hdr.x;
+    if (hdr.y) atomicMax(overflow, hdr.y);
+    u32 n = 0;
+    for (u32 i = 0; i < c; ++i) n += (wvisits[(size_t)w * vpw + 1 + i].x % G == rank) ? 1u : 0u;
+    wcounts[w] = c;
+    wown[w] = n;
+}
+void launch_own_counts(u32 nwalkers, u32 vpw, const uint2* d_wvisits, u32 G, u32 rank, u32* d_wcounts, u32* d_wown,
+                       u32* d_overflow, cudaStream_t s) {
+    if (!nwalkers) return;
+    own_counts_kernel<<<(nwalkers + 255) / 256, 256, 0, s>>>(nwalkers, vpw, d_wvisits, G, rank, d_wcounts, d_wown, d_overflow);
+}
 __global__ void compact_visits_kernel(ForestView f, u32 nwalkers, u32 vpw, const uint2* __restrict__ wvisits,
-                                      const u32* __restrict__ wcounts, const u32* __restrict__ woff,
+                                      const u32* __restrict__ wcounts, const u32* __restrict__ woff, u32 G, u32 rank,
                                       u32* __restrict__ vleaf, u32* __restrict__ vnp, u32* __restrict__ vq,
                                       u64* __restrict__ pair_len, u32* __restrict__ ent_len) {
     u32 w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,20 +113,22 @@ __global__ void compact_visits_kernel(ForestView f, u32 nwalkers, u32 vpw, const
     u32 c = wcounts[w], base = woff[w];
     u32 q = w / (u32)f.num_trees;
     for (u32 i = 0; i < c; ++i) {
-        uint2 v = wvisits[(size_t)w * vpw + i];
-        vleaf[base + i] = v.x;
-        vnp[base + i] = v.y;
-        vq[base + i] = q;
-        pair_len[base + i] = f.leaf_len[v.x];
+        uint2 v = wvisits[(size_t)w * vpw + 1 + i];
+        if (G > 1 && v.x % G != rank) continue;
+        vleaf[base] = v.x;
+        vnp[base] = v.y;
+        vq[base] = q;
+        pair_len[base] = f.leaf_len[v.x];
         u32 live = f.leaf_plan[v.x];
-        ent_len[base + i] = live < v.y ? live : v.y;
+        ent_len[base] = live < v.y ? live : v.y;
+        ++base;
     }
 }
 void launch_compact_visits(const ForestView& f, u32 nwalkers, u32 vpw, const uint2* d_wvisits, const u32* d_wcounts,
-                           const u32* d_woff, u32* d_vleaf, u32* d_vnp, u32* d_vq, u64* d_pair_len, u32* d_ent_len,
-                           cudaStream_t s) {
+                           const u32* d_woff, u32 G, u32 rank, u32* d_vleaf, u32* d_vnp, u32* d_vq, u64* d_pair_len,
+                           u32* d_ent_len, cudaStream_t s) {
     if (!nwalkers) return;
-    compact_visits_kernel<<<(nwalkers + 255) / 256, 256, 0, s>>>(f, nwalkers, vpw, d_wvisits, d_wcounts, d_woff, d_vleaf,
+    compact_visits_kernel<<<(nwalkers + 255) / 256, 256, 0, s>>>(f, nwalkers, vpw, d_wvisits, d_wcounts, d_woff, G, rank, d_vleaf,
                                                                  d_vnp, d_vq, d_pair_len, d_ent_len);
 }
 
@@ -905,25 +930,28 @@ void launch_bm_tomb_lookup(const u64* d_ords, const u8* d_flags, u64 n, int num_
 // row can be reached through trees whose leaves live on different ranks), sort (bits, id), take top_k (lsh.rs:550,:561-564)
 struct GatheredLoader {
     const u64* g;
-    u64 per_rank, nqk, qbase;
+    u64 per_rank, bits_off, qbase;
     u32 k;
     __device__ Entry operator()(long long i) const {
         const u64 r = (u64)i / k, j = (u64)i % k;
         const u64* b = g + r * per_rank + qbase + j;
-        return Entry{b[nqk], b[0]};
+        return Entry{b[bits_off], b[0]};
     }
 };
-__global__ void __launch_bounds__(TOPK_THREADS) merge_gathered_kernel(u32 nq, u32 top_k, u32 nranks, const u64* __restrict__ gathered,
-                                                                      u64* __restrict__ out_ord, u64* __restrict__ out_bits,
-                                                                      u32* __restrict__ out_counts, int pmax, int kmax) {
+// gathered: per source rank one block [ord nslice*k | bits nslice*k] holding that rank's local top-k lists of the nslice
+// queries this rank finishes; out_*: [nslice][k] / [nslice]
+__global__ void __launch_bounds__(TOPK_THREADS) merge_gathered_kernel(u32 nq, u32 nslice, u32 top_k, u32 nranks,
+                                                                      const u64* __restrict__ gathered, u64* __restrict__ out_ord,
+                                                                      u64* __restrict__ out_bits, u32* __restrict__ out_counts,
+                                                                      int pmax, int kmax) {
     extern __shared__ __align__(16) unsigned char smem[];
     Entry* buf = reinterpret_cast<Entry*>(smem);
     Entry* keep = buf + pmax;
     int* s_warp = reinterpret_cast<int*>(keep + kmax);
     const u32 q = blockIdx.x;
     if (q >= nq) return;
-    const u64 nqk = (u64)nq * top_k;
-    GatheredLoader ld{gathered, 2 * nqk, nqk, (u64)q * top_k, top_k};
+    const u64 nsk = (u64)nslice * top_k;
+    GatheredLoader ld{gathered, 2 * nsk, nsk, (u64)q * top_k, top_k};
     int kept = segment_topk(buf, keep, s_warp, ld, (long long)top_k * nranks, (int)top_k, pmax);
     for (u32 i = threadIdx.x; i < top_k; i += TOPK_THREADS) {
         bool ok = (int)i < kept;
@@ -932,17 +960,37 @@ __global__ void __launch_bounds__(TOPK_THREADS) merge_gathered_kernel(u32 nq, u3
     }
     if (threadIdx.x == 0) out_counts[q] = (u32)kept;
 }
-void launch_merge_gathered(u32 nq, u32 top_k, u32 nranks, const u64* d_gathered, u64* d_out_ord, u64* d_out_bits,
+void launch_merge_gathered(u32 nq, u32 nslice, u32 top_k, u32 nranks, const u64* d_gathered, u64* d_out_ord, u64* d_out_bits,
                            u32* d_out_counts, cudaStream_t s) {
     if (!nq || !top_k) return;
     int pmax = topk_pmax(top_k), kmax = (int)top_k;
     size_t smem = topk_smem(pmax, kmax);
     set_smem(merge_gathered_kernel, smem);
-    merge_gathered_kernel<<<nq, TOPK_THREADS, smem, s>>>(nq, top_k, nranks, d_gathered, d_out_ord, d_out_bits, d_out_counts, pmax, kmax);
+    merge_gathered_kernel<<<nq, TOPK_THREADS, smem, s>>>(nq, nslice, top_k, nranks, d_gathered, d_out_ord, d_out_bits, d_out_counts,
+                                                         pmax, kmax);
+}
+// results of all slices ([G] blocks of [ord nslice*k | bits nslice*k | counts nslice (u32)], block = blk u64) -> caller's arrays
+__global__ void unpack_results_kernel(const u64* __restrict__ res, u64 blk, u32 nq, u32 nslice, u32 top_k, u64* __restrict__ out_ord,
+                                      u64* __restrict__ out_bits, u32* __restrict__ out_counts) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (u64)nq * top_k) return;
+    const u32 q = (u32)(i / top_k), j = (u32)(i - (u64)q * top_k);
+    const u32 r = q / nslice, ql = q - r * nslice;
+    const u64* b = res + (u64)r * blk;
+    const u64 nsk = (u64)nslice * top_k;
+    out_ord[i] = b[(u64)ql * top_k + j];
+    out_bits[i] = b[nsk + (u64)ql * top_k + j];
+    if (j == 0) out_counts[q] = reinterpret_cast<const u32*>(b + 2 * nsk)[ql];
+}
+void launch_unpack_results(const u64* d_res, u64 blk, u32 nq, u32 nslice, u32 top_k, u64* d_out_ord, u64* d_out_bits,
+                           u32* d_out_counts, cudaStream_t s) {
+    const u64 tot = (u64)nq * top_k;
+    if (!tot) return;
+    unpack_results_kernel<<<(u32)((tot + 255) / 256), 256, 0, s>>>(d_res, blk, nq, nslice, top_k, d_out_ord, d_out_bits, d_out_counts);
 }
 
 // =====================================================================================================
-// cub scans
+// cub scans / sorts
 // =====================================================================================================
 size_t scan_temp_bytes(size_t n) {
     size_t b32 = 0, b64 = 0;

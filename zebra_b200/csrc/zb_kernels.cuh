@@ -51,9 +51,11 @@ struct RecvSeg {      // rows of one (source rank, owned leaf) pair in the recei
 // ---- plan (tree_result control flow, lsh.rs:290-348) ----
 void launch_plan(const ForestView& f, const float* d_queries, u32 nq, u32 top_k, u32 vpw, uint2* d_wvisits,
                  u32* d_wcounts, u32* d_overflow, cudaStream_t s);
+void launch_own_counts(u32 nwalkers, u32 vpw, const uint2* d_wvisits, u32 G, u32 rank, u32* d_wcounts, u32* d_wown,
+                       u32* d_overflow, cudaStream_t s);
 void launch_compact_visits(const ForestView& f, u32 nwalkers, u32 vpw, const uint2* d_wvisits, const u32* d_wcounts,
-                           const u32* d_woff, u32* d_vleaf, u32* d_vnp, u32* d_vq, u64* d_pair_len, u32* d_ent_len,
-                           cudaStream_t s);
+                           const u32* d_woff, u32 G, u32 rank, u32* d_vleaf, u32* d_vnp, u32* d_vq, u64* d_pair_len,
+                           u32* d_ent_len, cudaStream_t s);
 // ---- scoring of (visit, member) pairs, generic path ----
 void launch_score_pairs(const ForestView& f, int metric, const float* d_queries, u32 nv, const u32* d_vleaf,
                         const u32* d_vq, const u64* d_pair_off, u64 total_pairs, u64* d_pair_key, cudaStream_t s);
@@ -107,7 +109,9 @@ void launch_place_rows(const u32* d_perm, u64 n, const float* d_st_rows, const u
 void launch_iota_u32(u32* d, u64 n, u32 first, cudaStream_t s);
 void launch_bm_tomb_lookup(const u64* d_ords, const u8* d_flags, u64 n, int num_trees, const u64* d_tree_base,
                            const u64* d_srt_ord, const u32* d_srt_pos, u32* d_bm_tomb, cudaStream_t s);
-void launch_merge_gathered(u32 nq, u32 top_k, u32 nranks, const u64* d_gathered, u64* d_out_ord, u64* d_out_bits,
+void launch_merge_gathered(u32 nq, u32 nslice, u32 top_k, u32 nranks, const u64* d_gathered, u64* d_out_ord, u64* d_out_bits,
+                           u32* d_out_counts, cudaStream_t s);
+void launch_unpack_results(const u64* d_res, u64 blk, u32 nq, u32 nslice, u32 top_k, u64* d_out_ord, u64* d_out_bits,
                            u32* d_out_counts, cudaStream_t s);
 size_t sort_temp_bytes(size_t n);
 void sort_pairs_u64_u32(void* d_temp, size_t temp_bytes, const u64* d_kin, u64* d_kout, const u32* d_vin, u32* d_vout, size_t n,

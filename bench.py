@@ -49,6 +49,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--set", action="append", default=[], help="library knob key=value (ablations)")
+    ap.add_argument("--workload", default="query", choices=["query", "hash", "build"],
+                    help="query = BASELINE config 2 (the default, the driver's line); hash / build = BASELINE config 4 "
+                         "(bucket keys of fresh rows on a built forest / bulk insert), rows per second")
+    ap.add_argument("--hash-rows", type=int, default=1_000_000, help="rows hashed per GPU per step (workload hash)")
     return ap.parse_args()
 
 
@@ -374,10 +378,219 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+
+# ----------------------------------------------------------------------------------------------------- config 4 workloads
+def oracle_hash_parallel(orc, rows, cores):
+    """oracle.hash over `cores` threads (the C call releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    parts = np.array_split(np.arange(rows.shape[0]), max(1, min(cores, rows.shape[0] // 64 or 1)))
+    with ThreadPoolExecutor(max_workers=len(parts)) as ex:
+        res = list(ex.map(lambda ix: orc.hash(rows[ix[0]:ix[-1] + 1]) if len(ix) else None, parts))
+    res = [r for r in res if r is not None]
+    return tuple(np.concatenate([r[i] for r in res]) for i in range(3))
+
+
+def run_aux(a):
+    """BASELINE config 4 (LSH projection / hashing throughput).  `hash`: bucket keys (root-to-leaf sign paths) of fresh
+    rows on a built forest, rows/s.  `build`: bulk insert = level-synchronous forest build over resident rows, rows/s."""
+    import torch
+    import torch.distributed as dist
+
+    import zebra_b200 as z
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: zebra_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    G = world
+    if G > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if G > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def new_index(sharded):
+        ix = z.LSHIndex(a.dim, z.LSHIndexOptions(a.max_node_size, a.trees), getattr(z, METRIC_CLASSES[a.metric])(), device=local,
+                        seed=a.seed, shard_rank=rank if sharded else 0, shard_count=G if sharded else 1)
+        if sharded and G > 1:
+            uid = [z.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ix.comm_init(uid[0])
+        for kv in a.set:
+            k, v = kv.split("=")
+            ix.set_param(k, int(v))
+        return ix
+
+    peak, peak_src = hbm_peak()
+    nb = a.steps + a.warmup
+    sampler = ClockSampler(local)
+    cores = os.cpu_count() or 1
+    cpu = None
+    parity = None
+    if a.workload == "hash":
+        # forest built once from a.rows resident rows (replicated: hashing shards by row, no exchange); every step
+        # hashes a fresh chunk of a.hash_rows rows per GPU that is already in HBM
+        ix = new_index(False)
+        d_rows = torch.empty((a.rows, a.dim), dtype=torch.float32, device=dev)
+        z.synth_fill_device(local, d_rows.data_ptr(), 0, 1, a.rows, a.dim, a.seed, 1)
+        ix.add_device(d_rows.data_ptr(), a.rows)
+        del d_rows
+        n = a.hash_rows
+        d_x = torch.empty((nb, n, a.dim), dtype=torch.float32, device=dev)
+        for b in range(nb):
+            z.synth_fill_device(local, d_x[b].data_ptr(), a.rows + (b * G + rank) * n, 1, n, a.dim, a.seed, 1)
+        d_keys = torch.empty((n, a.trees), dtype=torch.int64, device=dev)
+        d_depth = torch.empty((n, a.trees), dtype=torch.int32, device=dev)
+        d_leaf = torch.empty((n, a.trees), dtype=torch.int32, device=dev)
+        h_x = d_x[nb - 1].cpu().pin_memory()
+        h_keys = np.empty((n, a.trees), dtype=np.uint64)
+        stream = torch.cuda.ExternalStream(ix.stream_ptr(), device=dev)
+        sampler.start()
+        for b in range(a.warmup):
+            ix.hash_device(n, d_x[b].data_ptr(), d_keys.data_ptr(), d_depth.data_ptr(), d_leaf.data_ptr())
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(a.steps):
+            ix.hash_device(n, d_x[a.warmup + s].data_ptr(), d_keys.data_ptr(), d_depth.data_ptr(), d_leaf.data_ptr())
+        e1.record(stream)
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+        barrier()
+        t_e = time.perf_counter()
+        for s in range(a.steps):   # end to end: host rows in, host keys out (zb_index_hash stages through the device)
+            hk, hd, hl = ix.hash(h_x.numpy())
+        barrier()
+        e2e_ms = (time.perf_counter() - t_e) * 1e3
+        clocks = sampler.stop()
+        depth_sum = float(d_depth.sum().item())           # plane rows streamed = sum of path lengths
+        units, unit_name = n * G, "rows/s"
+        alg_bytes = n * (a.dim * 4 + a.trees * 16)        # each row read once + key/depth/leaf written
+        extra = {"rows_per_step_per_gpu": n, "avg_depth": depth_sum / (n * a.trees),
+                 "plane_bytes_from_l2_per_step": depth_sum * a.dim * 4, "fma_per_step": depth_sum * a.dim}
+        kernel = "hash_kernel (zb_kernels.cu): root-to-leaf descent, one quad per (row, tree)"
+        h2d, d2h = n * a.dim * 4, n * a.trees * 16
+        if rank == 0 and G == 1 and not a.no_cpu_baseline:
+            from oracle import zb_oracle as zo
+
+            orc = zo.OracleIndex(a.dim, METRIC_IDS[a.metric], a.max_node_size, a.trees, seed=a.seed)
+            orc.load_forest(zo.synth(0, 1, a.rows, a.dim, a.seed, 1, cores), ix.export_forest())
+            xs = h_x.numpy()
+            t0 = time.time(); oracle_hash_parallel(orc, xs[:4096], cores); per = max((time.time() - t0) / 4096, 1e-7)
+            sample = int(max(4096, min(n, a.cpu_seconds / per)))
+            t0 = time.time(); ek, ed, el = oracle_hash_parallel(orc, xs[:sample], cores); dt = time.time() - t0
+            cpu = {"value": sample / dt, "unit": unit_name, "cores": cores, "kind": "port",
+                   "sample": f"first {sample} of the {n} rows of the last step, {dt:.1f}s on {cores} threads; restated reference descent"}
+            parity = bool(np.array_equal(hk[:sample], ek) and np.array_equal(hd[:sample], ed) and np.array_equal(hl[:sample], el))
+    else:
+        total = a.rows * G
+        n_local = len(range(rank, total, G))
+        d_rows = torch.empty((n_local, a.dim), dtype=torch.float32, device=dev)
+        z.synth_fill_device(local, d_rows.data_ptr(), rank, G, n_local, a.dim, a.seed, 1)
+        h_rows = d_rows.cpu().pin_memory() if G == 1 else None
+        ords = np.arange(rank, total, G, dtype=np.uint64)
+
+        def build_once(host):
+            """One bulk insert into a fresh index; returns (index, seconds spent in the add call alone)."""
+            ix = new_index(True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if host:
+                ix.add_raw(h_rows.numpy())
+            elif G > 1:
+                ix.add_owned_device(d_rows.data_ptr(), ords, total)
+            else:
+                ix.add_device(d_rows.data_ptr(), n_local)
+            torch.cuda.synchronize()
+            return ix, time.perf_counter() - t0
+
+        sampler.start()
+        for b in range(a.warmup):
+            build_once(False)[0].close()
+        barrier()
+        dev_s = 0.0                   # the build is a host-driven sequence of kernels with per-level syncs: wall time of
+        for s in range(a.steps):      # the insert call (index creation / destruction excluded)
+            ix, dt = build_once(False)
+            dev_s += dt
+            if s + 1 < a.steps:
+                ix.close()
+            barrier()
+        dev_ms = dev_s * 1e3
+        e2e_ms = None
+        if G == 1:
+            e2e_s = 0.0
+            for s in range(a.steps):
+                ixh, dt = build_once(True)
+                e2e_s += dt
+                ixh.close()
+            e2e_ms = e2e_s * 1e3
+        clocks = sampler.stop()
+        st = ix.stats()
+        f = ix.export_forest() if G == 1 else None
+        units, unit_name = total, "rows/s"
+        extra = {"rows_per_gpu": a.rows, "leaves": st["leaves"], "planes": st["planes"]}
+        alg_bytes = 0
+        if f is not None:   # classification reads: every member of every inner node once = sum over leaves of len * depth
+            depth = np.zeros(f.nodes.shape[0], dtype=np.int64)
+            for i in range(f.nodes.shape[0]):
+                if f.nodes[i, 0] >= 0:
+                    depth[f.nodes[i, 1]] = depth[f.nodes[i, 2]] = depth[i] + 1
+            leaf_nodes = np.where(f.nodes[:, 0] < 0)[0]
+            lens = np.diff(f.leaf_off)[f.nodes[leaf_nodes, 3]]
+            classified = int((lens * depth[leaf_nodes]).sum())
+            alg_bytes = classified * a.dim * 4
+            extra["classified_rows_per_build"] = classified
+        kernel = "classify_kernel (zb_kernels.cu): point_is_above of every member of every node under construction"
+        h2d, d2h = a.rows * a.dim * 4, 0
+        if rank == 0 and G == 1 and not a.no_cpu_baseline:
+            from oracle import zb_oracle as zo
+
+            sample = min(a.rows, 200_000)
+            rows = zo.synth(0, 1, sample, a.dim, a.seed, 1, cores)
+            zo.set_build_threads(min(cores, a.trees))
+            t0 = time.time()
+            orc = zo.OracleIndex(a.dim, METRIC_IDS[a.metric], a.max_node_size, a.trees, seed=a.seed)
+            orc.add(rows)
+            dt = time.time() - t0
+            cpu = {"value": sample / dt, "unit": unit_name, "cores": min(cores, a.trees), "kind": "port",
+                   "sample": f"bulk build of the first {sample} rows, {dt:.1f}s, one thread per tree; restated reference, in memory"}
+
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if G > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t[0])
+    if rank == 0:
+        sec = dev_ms / 1e3
+        achieved = alg_bytes * a.steps / sec / 1e9 if alg_bytes else None
+        line = {"metric": "rows_per_sec", "value": units * a.steps / sec, "unit": unit_name, "n_gpus": G, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{a.workload}: {a.dim}-dim f32 rows, forest of {a.trees} trees with leaves < {a.max_node_size} "
+                                       f"over {a.rows * (G if a.workload == 'build' else 1)} rows", **extra,
+                           "data": "Philox clustered, generated on device", "l2_policy": "every step streams fresh rows (>= 3 GB >> 126 MB L2)"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src, "kernel": kernel,
+                             "algorithmic_bytes_per_step": alg_bytes,
+                             "note": "whole-step time (the step is dominated by this kernel); hash: the descent also streams one "
+                                     "plane row per level from L2 (plane_bytes_from_l2_per_step), which is what bounds it"},
+                "cpu_baseline": cpu,
+                "e2e": {"value": units * a.steps / (e2e_ms / 1e3) if e2e_ms else None, "unit": unit_name, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h},
+                "gpu_launches": None, "clocks": clocks, "parity_sample_ok": parity}
+        print(json.dumps(line), flush=True)
+    if G > 1:
+        dist.destroy_process_group()
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload != "query":
+        run_aux(a)
     else:
         run_ours(a)
 

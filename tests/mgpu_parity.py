@@ -39,6 +39,8 @@ def main():
         uid = [z.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ix.comm_init(uid[0])
+        if mns == 5:
+            ix.set_param("visit_slots", 4)   # force the (collective) grow-and-replan path
         ix.add(rows)
         orc = zo.OracleIndex(dim, mid, mns, trees, seed=7) if rank == 0 else None
         if rank == 0:

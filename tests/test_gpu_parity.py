@@ -232,6 +232,20 @@ def test_topk_range_and_large_leaves(k):
     assert_search_equal(ix, orc, queries, k)
 
 
+def test_visit_plan_grows_and_replans():
+    """Default forest shape (leaf capacity 5, 15 trees): the count cascade (Q1) makes walkers visit many leaves; starting
+    from a 2-slot plan region forces the grow-and-replan loop several times and must not change the answer."""
+    z = zb()
+    rng = np.random.default_rng(11)
+    rows = clustered(rng, 4000, 64)
+    orc = zo.OracleIndex(64, zo.L2SQ, 5, 15, seed=4)
+    orc.add(rows)
+    ix = z.LSHIndex(64, z.LSHIndexOptions(5, 15), z.L2SquaredDistance(), seed=4)
+    ix.add(rows)
+    ix.set_param("visit_slots", 2)
+    assert_search_equal(ix, orc, make_queries(rng, rows, 200), 25)
+
+
 def test_empty_index_and_clear():
     z = zb()
     ix = z.LSHIndex(48, z.LSHIndexOptions(5, 3), z.L2Distance())

@@ -41,6 +41,13 @@ inline std::string fmt(const char* f, ...) {
 
 extern size_t g_device_bytes;  // not thread-exact; per-process accounting for zb_stats
 
+// Device memory comes from the device's stream-ordered pool with the release threshold lifted, so that the buffers of
+// a destroyed index (or of a grown workspace) are recycled instead of going back to the driver: cudaMalloc / cudaFree
+// of multi-GB buffers cost milliseconds each and dominated the bulk build.  dev_alloc returns memory that is ready for
+// use on any stream; dev_free waits for the device first (what cudaFree did implicitly).
+cudaError_t dev_alloc(void** p, size_t bytes);
+void dev_free(void* p);
+
 // Grow-only device buffer.
 template <class T>
 struct DBuf {
@@ -52,7 +59,7 @@ struct DBuf {
     ~DBuf() { release(); }
     void release() {
         if (p) {
-            cudaFree(p);
+            dev_free(p);
             g_device_bytes -= cap * sizeof(T);
         }
         p = nullptr;
@@ -65,11 +72,11 @@ struct DBuf {
         size_t ncap = exact ? n : (cap ? cap + cap / 2 : n);
         if (ncap < n) ncap = n;
         T* np = nullptr;
-        cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+        cudaError_t e = dev_alloc((void**)&np, ncap * sizeof(T));
         if (e != cudaSuccess && ncap > n) {  // retry with the exact size before giving up
             cudaGetLastError();
             ncap = n;
-            e = cudaMalloc(&np, ncap * sizeof(T));
+            e = dev_alloc((void**)&np, ncap * sizeof(T));
         }
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -80,7 +87,7 @@ struct DBuf {
             ZB_CUDA(cudaStreamSynchronize(s));
         }
         if (p) {
-            cudaFree(p);
+            dev_free(p);
             g_device_bytes -= cap * sizeof(T);
         }
         p = np;

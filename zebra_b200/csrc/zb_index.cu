@@ -133,7 +133,7 @@ struct zb_index {
     DBuf<u8> cub_tmp;
     DBuf<u32> w_counts, w_off, w_flag, w_own;
     DBuf<uint2> w_visits;
-    u32 vpw = 8;   // slots per walker in the visit plan: 1 header + up to vpw - 1 visits (grows on demand)
+    u32 vpw = 32;  // slots per walker in the visit plan: 1 header + up to vpw - 1 visits (grows on demand)
     DBuf<u32> v_leaf, v_np, v_q, v_ent_len, v_ent_off;
     DBuf<u64> v_pair_len, v_pair_off, pair_key;
     DBuf<u8> v_done;
@@ -154,7 +154,7 @@ struct zb_index {
     ScanWorkspace scan_ws;
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0;
     zb_stats st{};
 
     ForestView view() const {
@@ -561,6 +561,8 @@ struct zb_index {
     // d_members; nodes/planes/leaves are appended to the host mirror (uploaded by the caller).
     void build_subtrees(std::vector<BSeg> active, u64 total) {
         const u64 max_node = opt.max_node_size;
+        auto t_start = std::chrono::steady_clock::now();
+        int level = 0;
         std::vector<BSeg> leaves;
         int cur = 0;
         b_work[1].ensure(total ? total : 1);
@@ -613,7 +615,7 @@ struct zb_index {
             if (G > 1) nccl.allreduce(b_pair_rows.p, (size_t)ns * 2 * dimp, Nccl::I32, Nccl::SUM, stream);
             launch_make_planes(b_segs.p, ns, b_pair_rows.p, dimp, d_coef.p, d_cst.p, stream);
             ZB_CUDA(cudaMemsetAsync(b_flags.p, 0, (total + 1) * 4, stream));
-            launch_classify(b_tiles.p, nt, b_segs.p, work, rows.p, d_coef.p, d_cst.p, dimp, b_flags.p, stream);
+            launch_classify(b_tiles.p, nt, b_segs.p, work, rows.p, d_coef.p, d_cst.p, dimp, b_flags.p, (int)p_classify_variant, stream);
             exclusive_scan_u32(cub_tmp.p, cub_tmp.bytes(), b_flags.p, b_scan.p, total + 1, stream);
             launch_seg_above(b_segs.p, ns, b_scan.p, b_above.p, stream);
             habove.resize(ns);
@@ -647,6 +649,13 @@ struct zb_index {
             }
             n_planes += ns;
             active.swap(next);
+            if (trace_on && rank == 0) {
+                auto now = std::chrono::steady_clock::now();
+                fprintf(stderr, "[zb trace] build level %d: %u nodes, %u tiles, %.3f ms\n", level, ns, nt,
+                        std::chrono::duration<double, std::milli>(now - t_start).count());
+                t_start = now;
+            }
+            ++level;
         }
         // finalize leaves: members of leaf = b_work[cur][off, off+len)
         d_members.ensure(members_used + total, members_used, stream);
@@ -668,6 +677,9 @@ struct zb_index {
         }
         members_used += total;
         h_members_valid = false;
+        if (trace_on && rank == 0)
+            fprintf(stderr, "[zb trace] build finalize: %.3f ms\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     }
 
     u64 allreduce_sum_u64(u64 v) {
@@ -712,7 +724,7 @@ struct zb_index {
         std::vector<int> leaf_of((size_t)n_new * T);
         if (n_new) {
             h_leaves.ensure(n_new * (u64)T);
-            launch_hash(f, rows.p + first_slot * (u64)dimp, n_new, nullptr, nullptr, h_leaves.p, stream);
+            launch_hash(f, rows.p + first_slot * (u64)dimp, n_new, nullptr, nullptr, h_leaves.p, (int)p_hash_variant, stream);
             ZB_CUDA(cudaMemcpyAsync(leaf_of.data(), h_leaves.p, leaf_of.size() * 4, cudaMemcpyDeviceToHost, stream));
         }
         sync_host_members();
@@ -1077,6 +1089,7 @@ int zb_index_destroy(zb_index* ix) {
 
 static void add_common(zb_index* ix, u64 n, const float* src, bool src_on_device, const uint8_t* ids16, uint8_t* out_ids16,
                        u64* out_ordinals) {
+    auto t0 = std::chrono::steady_clock::now();
     ix->use_device();
     if (ix->G > 1) ZB_REQUIRE(ix->comm_ready, ZB_ERR_STATE, "sharded index used before zb_index_comm_init");
     const int mode = ids16 ? 2 : 1;
@@ -1123,11 +1136,15 @@ static void add_common(zb_index* ix, u64 n, const float* src, bool src_on_device
         if (out_ordinals) out_ordinals[i] = first + i;
         if (out_ids16) ix->id_of(first + i, out_ids16 + 16 * i);
     }
+    auto t1 = std::chrono::steady_clock::now();
     if (!ix->built) {
         if (ix->total_rows > 0) ix->bulk_build();
     } else {
         ix->incremental_insert(first_slot, nloc);
     }
+    if (ix->trace_on && ix->rank == 0)
+        fprintf(stderr, "[zb trace] add: store %.3f ms, build/insert %.3f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
 }
 
 int zb_index_add(zb_index* ix, uint64_t n, const float* rows, const uint8_t* ids16, uint8_t* out_ids16, uint64_t* out_ordinals) {
@@ -1337,7 +1354,7 @@ int zb_index_hash_device(zb_index* ix, uint64_t n, const float* d_rows, uint64_t
         launch_pad_rows(d_rows, n, ix->dim, ix->dimp, ix->r_stage.p, ix->stream);
         x = ix->r_stage.p;
     }
-    launch_hash(ix->view(), x, n, (u64*)d_keys, d_depths, d_leaves, ix->stream);
+    launch_hash(ix->view(), x, n, (u64*)d_keys, d_depths, d_leaves, (int)ix->p_hash_variant, ix->stream);
     if (d_leaves) {
         if (!ix->export_table_valid) {
             std::vector<int> table;
@@ -1573,6 +1590,12 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     if (k == "tile_min_rows") ix->p_tile_min_rows = value;
     else if (k == "tile_queries") ix->p_tile_queries = value;
     else if (k == "use_tile_scan") ix->p_use_tile_scan = value;
+    else if (k == "classify_variant") ix->p_classify_variant = value;  // 0: rows gathered through L1; 1: rows staged by TMA bulk copies
+    else if (k == "hash_variant") ix->p_hash_variant = value;  // 0: quad per (row, tree), rows through L1; 1: row staged in shared memory
+    else if (k == "visit_slots") {  // initial per-walker capacity of the visit plan (tests force the grow-and-replan path)
+        ZB_REQUIRE(value >= 2 && value <= 65536, ZB_ERR_INVALID, "visit_slots out of range");
+        ix->vpw = (u32)value;
+    }
     else throw zb::Error(ZB_ERR_INVALID, "unknown parameter " + k);
     ZB_API_END
 }

@@ -459,10 +459,71 @@ __global__ void __launch_bounds__(128) hash_kernel(ForestView f, const float* __
         if (leaves) leaves[w] = nd.w;
     }
 }
-void launch_hash(const ForestView& f, const float* d_rows, u64 n, u64* d_keys, u32* d_depths, int* d_leaves,
+// Variant with the row staged in shared memory: a quad copies its row once (quad-private region, padded pitch so that the
+// two quads of a quarter-warp hit disjoint banks) and walks ALL trees with it, so per level only the plane row is
+// fetched (L1 / L2); the row itself is read from HBM exactly once.  32 rows per CTA.
+#define HASH_ROWS_PER_CTA 32
+__global__ void __launch_bounds__(128) hash_rows_kernel(ForestView f, const float* __restrict__ rows, u64 n, int pitch,
+                                                        u64* __restrict__ keys, u32* __restrict__ depths,
+                                                        int* __restrict__ leaves) {
+    extern __shared__ __align__(16) float s_rows[];
+    const int quad = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    const u64 r = (u64)blockIdx.x * HASH_ROWS_PER_CTA + quad;
+    if (r >= n) return;
+    float4* mine = reinterpret_cast<float4*>(s_rows + (size_t)quad * pitch);
+    const float4* src = reinterpret_cast<const float4*>(rows + (size_t)r * f.dimp);
+    const int chunks = f.chunks;
+    for (int c = 0; c < chunks; ++c) mine[c * 4 + sub] = __ldg(src + c * 4 + sub);
+    __syncwarp(mask);
+    for (int t = 0; t < f.num_trees; ++t) {
+        int4 nd = f.nodes[f.roots[t]];
+        u64 key = 0;
+        u32 depth = 0;
+        while (nd.x >= 0) {
+            const float4* p = reinterpret_cast<const float4*>(f.coef + (size_t)nd.x * f.dimp);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int c = 0;
+            for (; c + 8 <= chunks; c += 8) {   // 8 plane loads in flight per thread; chunk order = canonical order
+                float4 p0 = __ldg(p + (c + 0) * 4 + sub), p1 = __ldg(p + (c + 1) * 4 + sub), p2 = __ldg(p + (c + 2) * 4 + sub),
+                       p3 = __ldg(p + (c + 3) * 4 + sub), p4 = __ldg(p + (c + 4) * 4 + sub), p5 = __ldg(p + (c + 5) * 4 + sub),
+                       p6 = __ldg(p + (c + 6) * 4 + sub), p7 = __ldg(p + (c + 7) * 4 + sub);
+                fma4(acc, p0, mine[(c + 0) * 4 + sub]); fma4(acc, p1, mine[(c + 1) * 4 + sub]);
+                fma4(acc, p2, mine[(c + 2) * 4 + sub]); fma4(acc, p3, mine[(c + 3) * 4 + sub]);
+                fma4(acc, p4, mine[(c + 4) * 4 + sub]); fma4(acc, p5, mine[(c + 5) * 4 + sub]);
+                fma4(acc, p6, mine[(c + 6) * 4 + sub]); fma4(acc, p7, mine[(c + 7) * 4 + sub]);
+            }
+            for (; c < chunks; ++c) fma4(acc, __ldg(p + c * 4 + sub), mine[c * 4 + sub]);
+            const bool ab = above_from_dot(quad_reduce16(acc, mask), f.cst[nd.x]);
+            key = (key << 1) | (ab ? 1ull : 0ull);
+            ++depth;
+            nd = f.nodes[ab ? nd.z : nd.y];
+        }
+        if (sub == 0) {
+            const u64 w = r * (u64)f.num_trees + t;
+            if (keys) keys[w] = key;
+            if (depths) depths[w] = depth;
+            if (leaves) leaves[w] = nd.w;
+        }
+    }
+}
+
+void launch_hash(const ForestView& f, const float* d_rows, u64 n, u64* d_keys, u32* d_depths, int* d_leaves, int variant,
                  cudaStream_t s) {
     u64 nw = n * (u64)f.num_trees;
     if (!nw) return;
+    const int pitch = f.dimp + ((f.dimp % 32) == 0 ? 16 : 0);
+    const size_t smem = (size_t)HASH_ROWS_PER_CTA * pitch * 4;
+    if (variant == 1 && smem <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set && smem > 48 * 1024) {
+            cudaFuncSetAttribute(hash_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        hash_rows_kernel<<<(u32)((n + HASH_ROWS_PER_CTA - 1) / HASH_ROWS_PER_CTA), 128, smem, s>>>(f, d_rows, n, pitch, d_keys,
+                                                                                                  d_depths, d_leaves);
+        return;
+    }
     hash_kernel<<<(u32)((nw + 31) / 32), 128, 0, s>>>(f, d_rows, n, d_keys, d_depths, d_leaves);
 }
 
@@ -481,15 +542,30 @@ __global__ void __launch_bounds__(64) pick_kernel(int phase, const Tile* __restr
                                                   const u64* __restrict__ exclude, u64* __restrict__ minh,
                                                   u64* __restrict__ minord, int* __restrict__ slot_out) {
     const Tile tl = tiles[blockIdx.x];
-    if (threadIdx.x >= tl.count) return;
+    const bool active = threadIdx.x < tl.count;
     const SegDesc sg = segs[tl.seg];
-    const u32 slot = work[tl.start + threadIdx.x];
-    const u64 o = ord[slot];
-    if (exclude && exclude[tl.seg] == o) return;
-    const u64 h = pick_hash(sg.key, (int)sg.attempt, o) >> 1;
-    if (phase == 0) atomicMin(&minh[tl.seg], h);
-    else if (phase == 1) { if (h == minh[tl.seg]) atomicMin(&minord[tl.seg], o); }
-    else { if (o == minord[tl.seg]) slot_out[tl.seg] = (int)slot; }
+    u32 slot = 0;
+    u64 o = ZB_SENTINEL, h = ZB_SENTINEL;
+    if (active) {
+        slot = work[tl.start + threadIdx.x];
+        o = ord[slot];
+        if (exclude && exclude[tl.seg] == o) o = ZB_SENTINEL;
+        else h = pick_hash(sg.key, (int)sg.attempt, o) >> 1;
+    }
+    if (phase == 0) {
+        // a tile lies inside one segment: reduce over the warp first, one atomic per warp (the top levels have a handful
+        // of segments, and millions of same-address atomics were what the level cost)
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const u32 lo = __shfl_xor_sync(0xffffffffu, (u32)h, m), hi = __shfl_xor_sync(0xffffffffu, (u32)(h >> 32), m);
+            const u64 other = ((u64)hi << 32) | lo;
+            h = other < h ? other : h;
+        }
+        if ((threadIdx.x & 31) == 0 && h != ZB_SENTINEL) atomicMin(&minh[tl.seg], h);
+    } else if (o != ZB_SENTINEL) {
+        if (phase == 1) { if (h == minh[tl.seg]) atomicMin(&minord[tl.seg], o); }
+        else { if (o == minord[tl.seg]) slot_out[tl.seg] = (int)slot; }
+    }
 }
 void launch_pick(int phase, const Tile* d_tiles, u32 ntiles, const SegDesc* d_segs, const u32* d_work, const u64* d_ord,
                  const u64* d_exclude, u64* d_minh, u64* d_minord, int* d_slot, cudaStream_t s) {
@@ -561,9 +637,96 @@ __global__ void __launch_bounds__(256) classify_kernel(const Tile* __restrict__ 
                        reinterpret_cast<const float4*>(rows + (size_t)slot * dimp), dimp / 16, sub, mask);
     if (sub == 0) flags[tl.start + i] = above_from_dot(d, cst[plane]) ? 1u : 0u;
 }
+// The projection hot loop as a bandwidth kernel.  Persistent CTAs (128 threads = 32 quads) take tiles of 64 positions;
+// one thread gathers the tile's rows into shared memory with one 1-D bulk copy (TMA, UBLKCP) per row -- whole 4N-byte
+// rows, the access pattern that reaches HBM speed for gathered rows (profiles/r01_tma_gather_microbench.txt) -- in two
+// halves of 32 rows on two mbarriers, so the quads score half 0 while half 1 is still landing.  A quad then reads its
+// row from shared memory (padded pitch: the two quads of a quarter-warp hit disjoint banks) and the node's plane
+// through L1 (shared by the whole tile), in the canonical chunk order.
+#define CL_HALF 32
+__global__ void __launch_bounds__(128, 1) classify_rows_kernel(const Tile* __restrict__ tiles, u32 ntiles, const SegDesc* __restrict__ segs,
+                                                               const u32* __restrict__ work, const float* __restrict__ rows,
+                                                               const float* __restrict__ coef, const float* __restrict__ cst,
+                                                               int dimp, int pitch, u32* __restrict__ flags) {
+    extern __shared__ __align__(128) unsigned char cl_smem[];
+    float* s_rows = reinterpret_cast<float*>(cl_smem);                       // [2][CL_HALF][pitch]
+    u64* s_bar = reinterpret_cast<u64*>(s_rows + (size_t)2 * CL_HALF * pitch);  // [2]
+    const u32 bar0 = smem_u32(s_bar);
+    const int quad = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int chunks = dimp / 16;
+    const u32 row_bytes = (u32)dimp * 4u;
+    u32 phase = 0;
+    for (u32 ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const Tile tl = tiles[ti];
+        if (threadIdx.x < 2) {  // thread h gathers half h: slots first (independent loads), then the copies
+            const int h = threadIdx.x;
+            const int cnt = (int)tl.count - h * CL_HALF;
+            if (cnt > 0) {
+                const int c = cnt < CL_HALF ? cnt : CL_HALF;
+                mbar_arrive_expect_tx(bar0 + 8 * h, (u32)c * row_bytes);
+                const u32* w = work + tl.start + h * CL_HALF;
+                for (int i = 0; i < c; ++i)
+                    bulk_g2s(smem_u32(s_rows + ((size_t)h * CL_HALF + i) * pitch), rows + (size_t)w[i] * dimp, row_bytes, bar0 + 8 * h);
+            } else {
+                mbar_arrive(bar0 + 8 * h);
+            }
+        }
+        const u32 plane = segs[tl.seg].plane;
+        const float4* p = reinterpret_cast<const float4*>(coef + (size_t)plane * dimp);
+        const float c0 = cst[plane];
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar0 + 8 * h, phase);
+            const int i = h * CL_HALF + quad;
+            if (i < (int)tl.count) {
+                const float4* x = reinterpret_cast<const float4*>(s_rows + ((size_t)h * CL_HALF + quad) * pitch);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                int c = 0;
+                for (; c + 8 <= chunks; c += 8) {
+                    float4 p0 = __ldg(p + (c + 0) * 4 + sub), p1 = __ldg(p + (c + 1) * 4 + sub), p2 = __ldg(p + (c + 2) * 4 + sub),
+                           p3 = __ldg(p + (c + 3) * 4 + sub), p4 = __ldg(p + (c + 4) * 4 + sub), p5 = __ldg(p + (c + 5) * 4 + sub),
+                           p6 = __ldg(p + (c + 6) * 4 + sub), p7 = __ldg(p + (c + 7) * 4 + sub);
+                    fma4(acc, p0, x[(c + 0) * 4 + sub]); fma4(acc, p1, x[(c + 1) * 4 + sub]);
+                    fma4(acc, p2, x[(c + 2) * 4 + sub]); fma4(acc, p3, x[(c + 3) * 4 + sub]);
+                    fma4(acc, p4, x[(c + 4) * 4 + sub]); fma4(acc, p5, x[(c + 5) * 4 + sub]);
+                    fma4(acc, p6, x[(c + 6) * 4 + sub]); fma4(acc, p7, x[(c + 7) * 4 + sub]);
+                }
+                for (; c < chunks; ++c) fma4(acc, __ldg(p + c * 4 + sub), x[c * 4 + sub]);
+                const float d = quad_reduce16(acc, mask);
+                if (sub == 0) flags[tl.start + i] = above_from_dot(d, c0) ? 1u : 0u;
+            }
+        }
+        phase ^= 1u;
+        __syncthreads();  // every quad is done with both halves before the next tile's copies overwrite them
+    }
+}
+
 void launch_classify(const Tile* d_tiles, u32 ntiles, const SegDesc* d_segs, const u32* d_work, const float* d_rows,
-                     const float* d_coef, const float* d_cst, int dimp, u32* d_flags, cudaStream_t s) {
+                     const float* d_coef, const float* d_cst, int dimp, u32* d_flags, int variant, cudaStream_t s) {
     if (!ntiles) return;
+    const int pitch = dimp + ((dimp % 32) == 0 ? 16 : 0);
+    const size_t smem = (size_t)2 * CL_HALF * pitch * 4 + 16;
+    static int sms = 0, max_smem = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncSetAttribute(classify_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    }
+    if (variant == 1 && smem <= (size_t)max_smem) {
+        const u32 grid = ntiles < (u32)sms ? ntiles : (u32)sms;
+        classify_rows_kernel<<<grid, 128, smem, s>>>(d_tiles, ntiles, d_segs, d_work, d_rows, d_coef, d_cst, dimp, pitch, d_flags);
+        return;
+    }
     classify_kernel<<<ntiles, 256, 0, s>>>(d_tiles, d_segs, d_work, d_rows, d_coef, d_cst, dimp, d_flags);
 }
 

@@ -68,7 +68,7 @@ void launch_merge_ranks(u32 nv, const u32* d_ent_off, u32 total_slots, u32 nrank
 void launch_merge_queries(u32 nq, u32 num_trees, const u32* d_woff, const u32* d_ent_off, const Entry* d_entries,
                           u32 top_k, u64* d_out_ord, u64* d_out_bits, u32* d_out_counts, cudaStream_t s);
 // ---- hashing / descent (lsh.rs:350-366) ----
-void launch_hash(const ForestView& f, const float* d_rows, u64 n, u64* d_keys, u32* d_depths, int* d_leaves,
+void launch_hash(const ForestView& f, const float* d_rows, u64 n, u64* d_keys, u32* d_depths, int* d_leaves, int variant,
                  cudaStream_t s);
 // ---- build (lsh.rs:192-267) ----
 void launch_pick(int phase, const Tile* d_tiles, u32 ntiles, const SegDesc* d_segs, const u32* d_work, const u64* d_ord,
@@ -78,7 +78,7 @@ void launch_fetch_pair_rows(const SegDesc* d_segs, u32 nsegs, const int* d_slot_
 void launch_make_planes(const SegDesc* d_segs, u32 nsegs, const float* d_pair_rows, int dimp, float* d_coef,
                         float* d_cst, cudaStream_t s);
 void launch_classify(const Tile* d_tiles, u32 ntiles, const SegDesc* d_segs, const u32* d_work, const float* d_rows,
-                     const float* d_coef, const float* d_cst, int dimp, u32* d_flags, cudaStream_t s);
+                     const float* d_coef, const float* d_cst, int dimp, u32* d_flags, int variant, cudaStream_t s);
 void launch_seg_above(const SegDesc* d_segs, u32 nsegs, const u32* d_scan, u32* d_above, cudaStream_t s);
 void launch_scatter(const Tile* d_tiles, u32 ntiles, const SegDesc* d_segs, const u32* d_work_in, const u32* d_flags,
                     const u32* d_scan, u32* d_work_out, cudaStream_t s);

@@ -6,6 +6,43 @@
 
 namespace zb {
 
+// ---- pooled device memory (see zb_host.h) ----
+namespace {
+struct PoolState {
+    cudaStream_t stream = nullptr;
+    bool ready = false;
+};
+PoolState g_pool[64];
+PoolState* pool_for_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    PoolState& ps = g_pool[dev];
+    if (!ps.ready) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return nullptr;
+        unsigned long long keep = ~0ull;  // never trim: freed buffers stay in the pool for the next allocation
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (cudaStreamCreateWithFlags(&ps.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        ps.ready = true;
+    }
+    return &ps;
+}
+}  // namespace
+
+cudaError_t dev_alloc(void** p, size_t bytes) {
+    PoolState* ps = pool_for_current_device();
+    if (!ps) return cudaMalloc(p, bytes);
+    cudaError_t e = cudaMallocAsync(p, bytes, ps->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ps->stream);  // the block is now usable on every stream
+}
+void dev_free(void* p) {
+    if (!p) return;
+    PoolState* ps = pool_for_current_device();
+    cudaDeviceSynchronize();  // nothing in flight may still touch the block
+    if (!ps || cudaFreeAsync(p, ps->stream) != cudaSuccess) cudaFree(p);
+}
+
 namespace {
 struct ncclUniqueId_ {
     char internal[128];

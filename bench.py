@@ -74,9 +74,11 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if int(os.environ.get("RANK", "0")) != 0:
+            return      # one poller per box: concurrent nvidia-smi loops contend for the driver and perturb the other ranks
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()

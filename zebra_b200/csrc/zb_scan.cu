@@ -226,8 +226,7 @@ __device__ __forceinline__ void scan_tile(const ScanCtx& cx, const ForestView& f
             const float4* rp = reinterpret_cast<const float4*>(cx.s_stage + (size_t)buf * TS_STAGE_BYTES) + r0 * (TS_SLICE_FLOATS / 4) + sub;
             const int qo = sl * (TS_SLICE_FLOATS / 4);
             constexpr int rstep = RSTRIDE * TS_SLICE_FLOATS / 4;  // RSTRIDE rows apart, in float4 units
-#pragma unroll 1
-            for (int c = 0; c < kcs; ++c) {
+            auto chunk = [&](int c) {
                 const float4 q0 = qp0[qo + c * 4], q1 = qp1[qo + c * 4], q2 = qp2[qo + c * 4], q3 = qp3[qo + c * 4];
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
@@ -238,6 +237,13 @@ __device__ __forceinline__ void scan_tile(const ScanCtx& cx, const ForestView& f
                         l2acc4_x2(acc[i][0], r, q0); l2acc4_x2(acc[i][1], r, q1); l2acc4_x2(acc[i][2], r, q2); l2acc4_x2(acc[i][3], r, q3);
                     }
                 }
+            };
+            if (kcs == TS_KC) {  // the common case, straight-line: the next chunk's shared-memory loads can be hoisted over this chunk's math
+#pragma unroll
+                for (int c = 0; c < TS_KC; ++c) chunk(c);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < kcs; ++c) chunk(c);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(cx.bar_empty + 8 * buf);

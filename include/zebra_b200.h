@@ -105,6 +105,12 @@ int zb_index_add_owned_device(zb_index* index, uint64_t n_local, const float* d_
 int zb_index_remove(zb_index* index, uint64_t n, const uint8_t* ids16, uint8_t* out_removed);
 int zb_index_remove_ordinals(zb_index* index, uint64_t n, const uint64_t* ordinals, uint8_t* out_removed);
 
+/* LSHIndex::deduplicate (lsh.rs:270-288): removes every row whose f32 bit patterns equal those of a row that comes
+ * earlier in id order (the reference walks its key-value store in key order and keeps the first of each pattern).
+ * *out_count = rows removed; the first min(count, cap) of them (ordinals ascending) are written to out_ordinals /
+ * out_ids16 when those are not NULL.  Sharded index: collective, rows are matched by a 128-bit hash of their bits. */
+int zb_index_deduplicate(zb_index* index, uint64_t* out_count, uint64_t* out_ordinals, uint8_t* out_ids16, uint64_t cap);
+
 /* LSHIndex::clear (lsh.rs:506-529), without quirk Q12: drops rows AND trees. */
 int zb_index_clear(zb_index* index);
 

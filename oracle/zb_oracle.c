@@ -528,6 +528,39 @@ int zbo_remove(zbo_index* ix, uint64_t n, const uint64_t* ids, uint8_t* out_remo
     return 0;
 }
 
+/* LSHIndex::deduplicate, lsh.rs:270-288: walk the stored embeddings in key (id) order, keep the first row of every
+ * distinct BIT pattern (f32::to_bits per element: +0.0 and -0.0 differ, NaNs compare by payload), remove the rest.
+ * Returns the number of removed rows; their ids (ascending) go to out_ids[0..min(count, cap)). */
+static const zbo_index* g_dd_ix;
+static int cmp_rowbits(const void* pa, const void* pb) {
+    uint64_t a = *(const uint64_t*)pa, b = *(const uint64_t*)pb;
+    int c = memcmp(g_dd_ix->rows + (size_t)a * g_dd_ix->dim, g_dd_ix->rows + (size_t)b * g_dd_ix->dim, (size_t)g_dd_ix->dim * 4);
+    if (c) return c;
+    return a < b ? -1 : (a > b ? 1 : 0);
+}
+int64_t zbo_deduplicate(zbo_index* ix, uint64_t* out_ids, uint64_t cap) {
+    uint64_t* live = (uint64_t*)malloc((ix->n_live ? ix->n_live : 1) * sizeof(uint64_t));
+    size_t n = 0;
+    for (size_t i = 0; i < ix->n_rows; ++i)
+        if (!ix->tomb[i]) live[n++] = i;
+    g_dd_ix = ix;
+    qsort(live, n, sizeof(uint64_t), cmp_rowbits);   /* equal rows adjacent, lowest id first */
+    uint8_t* dup = (uint8_t*)calloc(ix->n_rows ? ix->n_rows : 1, 1);
+    for (size_t i = 1; i < n; ++i)
+        if (!memcmp(ix->rows + (size_t)live[i] * ix->dim, ix->rows + (size_t)live[i - 1] * ix->dim, (size_t)ix->dim * 4)) dup[live[i]] = 1;
+    int64_t count = 0;
+    for (size_t i = 0; i < ix->n_rows; ++i)
+        if (dup[i]) {
+            if ((uint64_t)count < cap && out_ids) out_ids[count] = i;
+            ++count;
+            ix->tomb[i] = 1;
+            ix->n_live--;
+        }
+    free(dup);
+    free(live);
+    return count;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Search.
  * ---------------------------------------------------------------------------------------------- */

@@ -42,6 +42,8 @@ def lib():
         L.zbo_num_live.argtypes = [vp]
         L.zbo_add.argtypes = [vp, u64, vp, vp]
         L.zbo_remove.argtypes = [vp, u64, vp, vp]
+        L.zbo_deduplicate.restype = i64
+        L.zbo_deduplicate.argtypes = [vp, vp, u64]
         L.zbo_search.restype = i64
         L.zbo_search.argtypes = [vp, vp, u64, vp, vp]
         L.zbo_search_batch.argtypes = [vp, u64, vp, u64, i32, vp, vp, vp]
@@ -186,6 +188,12 @@ class OracleIndex:
         out = np.empty(ids.size, dtype=np.uint8)
         lib().zbo_remove(self._h, ids.size, _p(ids), _p(out))
         return out.astype(bool)
+
+    def deduplicate(self) -> np.ndarray:
+        """lsh.rs:270-288: removes every row whose bits equal those of a row with a smaller id; returns the removed ids."""
+        out = np.empty(max(1, self.num_rows), dtype=np.uint64)
+        n = lib().zbo_deduplicate(self._h, _p(out), out.size)
+        return out[:n].copy()
 
     def search(self, query, top_k: int):
         q = _f32(query)

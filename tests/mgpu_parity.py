@@ -27,8 +27,11 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    cases = [(zo.COSINE, "CosineDistance", 6000, 384, 5, 15, 10), (zo.L2, "L2Distance", 20000, 768, 512, 4, 10),
-             (zo.L2SQ, "L2SquaredDistance", 9000, 100, 256, 3, 25)]
+    cases = [(zo.COSINE, "CosineDistance", 6000, 384, 5, 15, 10),      # reference defaults: tiny leaves, long count cascades
+             (zo.L2, "L2Distance", 20000, 768, 512, 4, 10),            # BASELINE config 2 shape: tile kernel
+             (zo.L2SQ, "L2SquaredDistance", 9000, 100, 256, 3, 25),    # dim not a multiple of 16
+             (zo.COSINE, "CosineDistance", 24000, 768, 1024, 4, 10),   # BASELINE config 3 shape: cosine, bucket-sharded, tile kernel
+             (zo.COSINE, "CosineDistance", 16000, 384, 256, 4, 100)]   # BASELINE config 5 shape: 384-dim, deletes, top-100 (generic path)
     for mid, mname, n, dim, mns, trees, k in cases:
         rng = np.random.default_rng(1234 + n)     # same data on every rank
         rows = clustered(rng, n, dim)
@@ -69,6 +72,17 @@ def main():
         if rank == 0:
             orc.add(extra)
         check("after incremental add")
+        if mns == 5:    # sharded deduplicate: copies land on other ranks than their originals
+            dup_rows = rows[:300].copy()
+            ix.add(dup_rows)
+            _, got = ix.deduplicate_raw()
+            if rank == 0:
+                orc.add(dup_rows)
+                exp = orc.deduplicate()
+                good = np.array_equal(got, exp) and exp.size > 0
+                print(f"[mgpu G={world}] deduplicate removed {got.size}: {'ok' if good else 'MISMATCH'}", flush=True)
+                ok = ok and good
+            check("after deduplicate")
         ix.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)

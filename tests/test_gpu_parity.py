@@ -246,6 +246,44 @@ def test_visit_plan_grows_and_replans():
     assert_search_equal(ix, orc, make_queries(rng, rows, 200), 25)
 
 
+@pytest.mark.parametrize("mns,trees", [(5, 15), (128, 3)])
+def test_deduplicate_matches_oracle(mns, trees):
+    """lsh.rs:270-288: the first row (in id order) of every distinct bit pattern stays; +0.0 / -0.0 are different bits."""
+    z = zb()
+    rng = np.random.default_rng(mns)
+    dim, n = 40, 3000
+    rows = clustered(rng, n, dim)
+    src = rng.integers(0, 200, 600)
+    dst = rng.choice(np.arange(200, n), 600, replace=False)
+    rows[dst] = rows[src]                                   # 600 copies of 200 originals (chains of duplicates)
+    rows[2500] = 0.0; rows[2501] = 0.0; rows[2502] = -0.0   # 2501 duplicates 2500; 2502 has different bits
+    orc = zo.OracleIndex(dim, zo.L2SQ, mns, trees, seed=3)
+    orc.add(rows)
+    ix = z.LSHIndex(dim, z.LSHIndexOptions(mns, trees), z.L2SquaredDistance(), seed=3)
+    ix.add(rows)
+    pre = np.arange(5, n, 97, dtype=np.uint64)              # rows already removed are neither kept nor counted
+    orc.remove(pre); ix.remove_ordinals(pre)
+    exp = orc.deduplicate()
+    _, got = ix.deduplicate_raw()
+    assert np.array_equal(got, exp) and 2501 in got and 2502 not in got
+    assert ix.stats()["live_rows"] == orc.num_live
+    queries = make_queries(rng, rows, 100)
+    assert_search_equal(ix, orc, queries, 10)               # tombstones and live leaf counts followed
+    assert ix.deduplicate_raw()[1].size == 0                # idempotent
+
+
+def test_deduplicate_with_caller_ids_keeps_smallest_id():
+    z = zb()
+    dim = 16
+    base = np.random.default_rng(1).standard_normal((3, dim)).astype(np.float32)
+    rows = np.stack([base[0], base[1], base[0], base[2], base[1]])
+    ids = [uuid.UUID(int=v) for v in (50, 40, 10, 30, 20)]  # duplicates of row 0: ids 50 and 10 -> 10 stays
+    ix = z.LSHIndex(dim, z.LSHIndexOptions(5, 2), z.CosineDistance(), seed=1)
+    ix.add(rows, ids)
+    removed = ix.deduplicate()
+    assert removed == {uuid.UUID(int=50), uuid.UUID(int=40)}
+
+
 def test_empty_index_and_clear():
     z = zb()
     ix = z.LSHIndex(48, z.LSHIndexOptions(5, 3), z.L2Distance())
@@ -313,8 +351,10 @@ def test_synth_is_deterministic_and_shard_consistent():
 
 # ------------------------------------------------------------------------------------------ multi-GPU (NCCL)
 def test_sharded_two_gpus_equals_oracle():
-    """Row-sharded index over 2 GPUs of this box (NCCL allreduce of leaf counts, allgather + per-visit merge of the
-    local top-n' lists) against the unsharded oracle.  Skipped on a single-GPU box."""
+    """Bucket-sharded index over 2 GPUs of this box (leaf l on rank l % 2; NCCL: allreduce of leaf counts, send/recv of the
+    rows of each leaf to its owner, allgather of the visit plan, all-to-all + allgather of the per-query top-k) against the
+    unsharded oracle: bulk build, deletes, incremental insert; shapes of BASELINE configs 1, 2, 3 and 5.  Skipped on a
+    single-GPU box."""
     import os
     import subprocess
     import sys
@@ -328,3 +368,4 @@ def test_sharded_two_gpus_equals_oracle():
            "--master-port", "29517", os.path.join(root, "tests", "mgpu_parity.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count(": ok") == 17 and "MISMATCH" not in out.stdout

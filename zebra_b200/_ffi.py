@@ -78,6 +78,7 @@ SYMBOLS = {
     "zb_index_add_owned_device": (C.c_int, [_vp, _u64, _vp, _vp, _u64]),
     "zb_index_remove": (C.c_int, [_vp, _u64, _vp, _vp]),
     "zb_index_remove_ordinals": (C.c_int, [_vp, _u64, _vp, _vp]),
+    "zb_index_deduplicate": (C.c_int, [_vp, C.POINTER(_u64), _vp, _vp, _u64]),
     "zb_index_clear": (C.c_int, [_vp]),
     "zb_index_no_vectors": (C.c_int, [_vp, _vp]),
     "zb_index_no_trees": (C.c_int, [_vp, _vp]),

@@ -1246,6 +1246,118 @@ int zb_index_remove(zb_index* ix, uint64_t n, const uint8_t* ids16, uint8_t* out
     ZB_API_END
 }
 
+// LSHIndex::deduplicate (lsh.rs:270-288).  Unsharded: exact on the device (hash, sort, bitwise compare inside hash runs).
+// Sharded: every rank hashes its rows (128 bits), the (hash, ordinal) records are allgathered and grouped on the host;
+// rows with equal 128-bit hashes are taken as equal (no cross-rank row compare).  Either way the first row in id order of
+// every group stays and the others go through the ordinary remove path (tombstones, live counts, bucket-major store).
+static void deduplicate_impl(zb_index* ix, std::vector<u64>* removed) {
+    ix->use_device();
+    cudaStream_t s = ix->stream;
+    removed->clear();
+    // live slots in id order: minted ids order like ordinals (= slot order); caller-supplied ids order by their bytes
+    std::vector<u32> live;
+    live.reserve(ix->n_slots);
+    for (u64 sl = 0; sl < ix->n_slots; ++sl)
+        if (!ix->h_tomb[sl]) live.push_back((u32)sl);
+    auto id_less = [&](u64 oa, u64 ob) {
+        if (ix->id_mode != 2) return oa < ob;
+        const Id16 &a = ix->ids_by_ordinal[oa], &b = ix->ids_by_ordinal[ob];
+        return a.hi != b.hi ? a.hi < b.hi : (a.lo != b.lo ? a.lo < b.lo : oa < ob);
+    };
+    if (ix->id_mode == 2)
+        std::stable_sort(live.begin(), live.end(), [&](u32 x, u32 y) { return id_less(ix->h_ord[x], ix->h_ord[y]); });
+    const u64 n = live.size();
+    DBuf<u32> d_slots, d_val[2], d_flag, d_head;
+    DBuf<u64> d_h1[2], d_h2;
+    DBuf<u8> d_dup, d_tmp;
+    d_slots.ensure(n ? n : 1);
+    d_h1[0].ensure(n ? n : 1);
+    d_h2.ensure(n ? n : 1);
+    if (n) ZB_CUDA(cudaMemcpyAsync(d_slots.p, live.data(), n * 4, cudaMemcpyHostToDevice, s));
+    launch_row_hash(d_slots.p, n, ix->rows.p, ix->dimp, d_h1[0].p, d_h2.p, s);
+    std::vector<u64> dups;
+    if (ix->G <= 1) {
+        d_h1[1].ensure(n ? n : 1);
+        for (int b = 0; b < 2; ++b) d_val[b].ensure(n ? n : 1);
+        d_flag.ensure(n ? n : 1);
+        d_head.ensure(n ? n : 1);
+        d_dup.ensure(n ? n : 1);
+        d_tmp.ensure(std::max(sort_temp_bytes(n ? n : 1), maxscan_temp_bytes(n ? n : 1)));
+        launch_iota_u32(d_val[0].p, n, 0u, s);
+        sort_pairs_u64_u32(d_tmp.p, d_tmp.bytes(), d_h1[0].p, d_h1[1].p, d_val[0].p, d_val[1].p, n, 64, s);
+        launch_dup_mark(d_h1[1].p, d_val[1].p, n, d_slots.p, ix->rows.p, ix->dimp, d_flag.p, d_head.p, d_tmp.p, d_tmp.bytes(), d_dup.p, s);
+        std::vector<u8> h_dup(n);
+        std::vector<u32> h_cand(n);
+        if (n) {
+            ZB_CUDA(cudaMemcpyAsync(h_dup.data(), d_dup.p, n, cudaMemcpyDeviceToHost, s));
+            ZB_CUDA(cudaMemcpyAsync(h_cand.data(), d_val[1].p, n * 4, cudaMemcpyDeviceToHost, s));
+        }
+        ix->sync();
+        for (u64 i = 0; i < n; ++i)
+            if (h_dup[i]) dups.push_back(ix->h_ord[live[h_cand[i]]]);
+    } else {
+        ZB_REQUIRE(ix->comm_ready, ZB_ERR_STATE, "sharded index used before zb_index_comm_init");
+        // records (h1, h2, ordinal), padded to the largest shard
+        u64 nmax = n;
+        {
+            ix->b_minh.ensure(1);
+            ZB_CUDA(cudaMemcpyAsync(ix->b_minh.p, &nmax, 8, cudaMemcpyHostToDevice, s));
+            ix->nccl.allreduce(ix->b_minh.p, 1, Nccl::U64, Nccl::MAX, s);
+            ZB_CUDA(cudaMemcpyAsync(&nmax, ix->b_minh.p, 8, cudaMemcpyDeviceToHost, s));
+            ix->sync();
+        }
+        std::vector<u64> rec(3 * (nmax ? nmax : 1), ZB_SENTINEL), h1(n), h2(n);
+        if (n) {
+            ZB_CUDA(cudaMemcpyAsync(h1.data(), d_h1[0].p, n * 8, cudaMemcpyDeviceToHost, s));
+            ZB_CUDA(cudaMemcpyAsync(h2.data(), d_h2.p, n * 8, cudaMemcpyDeviceToHost, s));
+        }
+        ix->sync();
+        for (u64 i = 0; i < n; ++i) {
+            rec[3 * i] = h1[i];
+            rec[3 * i + 1] = h2[i];
+            rec[3 * i + 2] = ix->h_ord[live[i]];
+        }
+        DBuf<u64> d_rec, d_all;
+        const size_t per = 3 * (nmax ? nmax : 1);
+        d_rec.ensure(per);
+        d_all.ensure(per * ix->G);
+        ZB_CUDA(cudaMemcpyAsync(d_rec.p, rec.data(), per * 8, cudaMemcpyHostToDevice, s));
+        ix->nccl.allgather(d_rec.p, d_all.p, per * 8, s);
+        std::vector<u64> all(per * ix->G);
+        ZB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, all.size() * 8, cudaMemcpyDeviceToHost, s));
+        ix->sync();
+        struct Rec { u64 h1, h2, ord; };
+        std::vector<Rec> v;
+        for (size_t i = 0; i + 2 < all.size(); i += 3)
+            if (all[i + 2] != ZB_SENTINEL) v.push_back(Rec{all[i], all[i + 1], all[i + 2]});
+        std::sort(v.begin(), v.end(), [&](const Rec& a, const Rec& b) {
+            return a.h1 != b.h1 ? a.h1 < b.h1 : (a.h2 != b.h2 ? a.h2 < b.h2 : id_less(a.ord, b.ord));
+        });
+        for (size_t i = 1; i < v.size(); ++i)
+            if (v[i].h1 == v[i - 1].h1 && v[i].h2 == v[i - 1].h2) dups.push_back(v[i].ord);
+    }
+    std::sort(dups.begin(), dups.end());
+    if (!dups.empty() || ix->G > 1) {
+        std::vector<u8> flags(dups.size() ? dups.size() : 1, 0);
+        remove_ordinals(ix, dups.size(), dups.data(), nullptr, flags.data());
+    }
+    *removed = dups;
+}
+
+int zb_index_deduplicate(zb_index* ix, uint64_t* out_count, uint64_t* out_ordinals, uint8_t* out_ids16, uint64_t cap) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && out_count, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::vector<u64> removed;
+    deduplicate_impl(ix, &removed);
+    *out_count = removed.size();
+    for (u64 i = 0; i < removed.size() && i < cap; ++i) {
+        if (out_ordinals) out_ordinals[i] = removed[i];
+        if (out_ids16) ix->id_of(removed[i], out_ids16 + 16 * i);
+    }
+    ZB_API_END
+}
+
 int zb_index_clear(zb_index* ix) {
     ZB_API_BEGIN
     ZB_REQUIRE(ix, ZB_ERR_INVALID, "NULL argument");

@@ -1152,6 +1152,84 @@ void launch_unpack_results(const u64* d_res, u64 blk, u32 nq, u32 nslice, u32 to
     unpack_results_kernel<<<(u32)((tot + 255) / 256), 256, 0, s>>>(d_res, blk, nq, nslice, top_k, d_out_ord, d_out_bits, d_out_counts);
 }
 
+
+// =====================================================================================================
+// deduplicate (lsh.rs:270-288): rows whose BIT patterns are equal; the row with the smallest id of each group stays.
+// hash every live row (128 bits, one quad per row, the row is read once) -> radix sort by hash (stable: candidates keep
+// id order) -> run heads by a max-scan -> every non-head row is compared, bit for bit, with the earlier rows of its run.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) row_hash_kernel(const u32* __restrict__ slots, u64 n, const float* __restrict__ rows, int dimp,
+                                                       u64* __restrict__ h1, u64* __restrict__ h2) {
+    const u64 i = (u64)blockIdx.x * 32ull + (threadIdx.x >> 2);
+    if (i >= n) return;
+    const int sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    const uint4* x = reinterpret_cast<const uint4*>(rows + (size_t)slots[i] * dimp);
+    u64 a = 0x243F6A8885A308D3ull + sub, b = 0x13198A2E03707344ull + sub;
+    for (int c = 0; c < dimp / 16; ++c) {
+        const uint4 v = __ldg(x + c * 4 + sub);
+        const u64 lo = ((u64)v.y << 32) | v.x, hi = ((u64)v.w << 32) | v.z;
+        a = mix64(a ^ lo); a = mix64(a ^ hi);
+        b = mix64(b + lo) ^ hi; b = mix64(b);
+    }
+    // fold the quad in a fixed order
+#pragma unroll
+    for (int m = 1; m <= 2; m <<= 1) {
+        const u64 oa = ((u64)__shfl_xor_sync(mask, (u32)(a >> 32), m) << 32) | __shfl_xor_sync(mask, (u32)a, m);
+        const u64 ob = ((u64)__shfl_xor_sync(mask, (u32)(b >> 32), m) << 32) | __shfl_xor_sync(mask, (u32)b, m);
+        const bool low = (sub & m) == 0;
+        a = mix64((low ? a : oa) ^ mix64(low ? oa : a));
+        b = mix64((low ? b : ob) + mix64(low ? ob : b));
+    }
+    if (sub == 0) {
+        h1[i] = a;
+        if (h2) h2[i] = b;
+    }
+}
+void launch_row_hash(const u32* d_slots, u64 n, const float* d_rows, int dimp, u64* d_h1, u64* d_h2, cudaStream_t s) {
+    if (!n) return;
+    row_hash_kernel<<<(u32)((n + 31) / 32), 128, 0, s>>>(d_slots, n, d_rows, dimp, d_h1, d_h2);
+}
+__global__ void run_flag_kernel(const u64* __restrict__ key, u64 n, u32* __restrict__ flag) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0 || key[i] != key[i - 1]) ? (u32)i : 0u;
+}
+// one quad per sorted candidate: duplicate iff an earlier candidate of the same hash run has identical bits
+__global__ void __launch_bounds__(128) dup_mark_kernel(const u32* __restrict__ head, const u32* __restrict__ cand, u64 n,
+                                                       const u32* __restrict__ slots, const float* __restrict__ rows, int dimp,
+                                                       u8* __restrict__ dup) {
+    const u64 i = (u64)blockIdx.x * 32ull + (threadIdx.x >> 2);
+    if (i >= n) return;
+    const int sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    const u32 h = head[i];
+    u8 is_dup = 0;
+    const uint4* me = reinterpret_cast<const uint4*>(rows + (size_t)slots[cand[i]] * dimp);
+    for (u32 j = h; j < (u32)i && !is_dup; ++j) {
+        const uint4* other = reinterpret_cast<const uint4*>(rows + (size_t)slots[cand[j]] * dimp);
+        bool eq = true;
+        for (int c = 0; c < dimp / 16 && eq; ++c) {
+            const uint4 u = __ldg(me + c * 4 + sub), v = __ldg(other + c * 4 + sub);
+            const bool same = u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w;
+            eq = __all_sync(mask, same);
+        }
+        if (eq) is_dup = 1;
+    }
+    if (sub == 0) dup[i] = is_dup;
+}
+void launch_dup_mark(const u64* d_sorted_key, const u32* d_cand, u64 n, const u32* d_slots, const float* d_rows, int dimp,
+                     u32* d_flag, u32* d_head, void* d_temp, size_t temp_bytes, u8* d_dup, cudaStream_t s) {
+    if (!n) return;
+    run_flag_kernel<<<(u32)((n + 255) / 256), 256, 0, s>>>(d_sorted_key, n, d_flag);
+    cub::DeviceScan::InclusiveScan(d_temp, temp_bytes, d_flag, d_head, cub::Max(), (long long)n, s);
+    dup_mark_kernel<<<(u32)((n + 31) / 32), 128, 0, s>>>(d_head, d_cand, n, d_slots, d_rows, dimp, d_dup);
+}
+size_t maxscan_temp_bytes(size_t n) {
+    size_t b = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, b, (const u32*)nullptr, (u32*)nullptr, cub::Max(), (long long)n);
+    return b + 256;
+}
+
 // =====================================================================================================
 // cub scans / sorts
 // =====================================================================================================

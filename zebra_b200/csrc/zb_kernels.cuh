@@ -117,6 +117,12 @@ size_t sort_temp_bytes(size_t n);
 void sort_pairs_u64_u32(void* d_temp, size_t temp_bytes, const u64* d_kin, u64* d_kout, const u32* d_vin, u32* d_vout, size_t n,
                         int end_bit, cudaStream_t s);
 
+// ---- deduplicate (lsh.rs:270-288) ----
+void launch_row_hash(const u32* d_slots, u64 n, const float* d_rows, int dimp, u64* d_h1, u64* d_h2, cudaStream_t s);
+void launch_dup_mark(const u64* d_sorted_key, const u32* d_cand, u64 n, const u32* d_slots, const float* d_rows, int dimp,
+                     u32* d_flag, u32* d_head, void* d_temp, size_t temp_bytes, u8* d_dup, cudaStream_t s);
+size_t maxscan_temp_bytes(size_t n);
+
 // cub wrappers (temp storage managed by caller)
 size_t scan_temp_bytes(size_t n);
 void exclusive_scan_u32(void* d_temp, size_t temp_bytes, const u32* d_in, u32* d_out, size_t n, cudaStream_t s);

@@ -52,6 +52,10 @@ class Database:
         for i in removed:
             self._documents.pop(i, None)
 
+    def deduplicate(self) -> None:  # core.rs:216-224
+        for i in self.index.deduplicate():
+            self._documents.pop(i, None)
+
     def insert_documents(self, documents: Sequence[bytes]) -> None:  # core.rs:232-235
         self.insert_records(self.model.embed_documents(documents), documents)
 

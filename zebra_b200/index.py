@@ -130,6 +130,21 @@ class LSHIndex:
         _ffi.check(_ffi.lib().zb_index_remove_ordinals(self._h, ordinals.size, ordinals.ctypes.data, flags.ctypes.data))
         return flags.astype(bool)
 
+    # ---------------------------------------------------------------- lsh.rs:270-288
+    def deduplicate(self) -> Set[_uuid.UUID]:
+        return set(_bytes_to_ids(self.deduplicate_raw()[0]))
+
+    def deduplicate_raw(self) -> Tuple[np.ndarray, np.ndarray]:
+        """Returns (ids as [n,16] uint8, ordinals as [n] uint64) of the removed duplicates."""
+        st = self.stats()
+        cap = max(1, int(st["total_rows"]))
+        ords = np.empty(cap, dtype=np.uint64)
+        ids = np.empty((cap, 16), dtype=np.uint8)
+        count = C.c_uint64()
+        _ffi.check(_ffi.lib().zb_index_deduplicate(self._h, C.byref(count), ords.ctypes.data, ids.ctypes.data, cap))
+        n = int(count.value)
+        return ids[:n].copy(), ords[:n].copy()
+
     # ---------------------------------------------------------------- lsh.rs:506-529, :389-409
     def clear(self) -> None:
         _ffi.check(_ffi.lib().zb_index_clear(self._h))

@@ -132,6 +132,7 @@ struct zb_index {
     // ---- workspaces ----
     DBuf<u8> cub_tmp;
     DBuf<u32> w_counts, w_off, w_flag, w_own;
+    DBuf<u64> plan_totals;
     DBuf<uint2> w_visits;
     u32 vpw = 32;  // slots per walker in the visit plan: 1 header + up to vpw - 1 visits (grows on demand)
     DBuf<u32> v_leaf, v_np, v_q, v_ent_len, v_ent_off;
@@ -822,11 +823,22 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->w_off.ensure(nw + 1);
     ix->w_flag.ensure(4);
     ix->scan_tmp(nw + 1);
-    u32 h_flag = 0, nv = 0;
+    u32 nv = 0, total_slots = 0;
+    u64 total_pairs = 0;
     const u64 q0 = sharded ? std::min<u64>(nq, (u64)ix->rank * nqp) : 0;
     const u64 qn = sharded ? std::min<u64>(nqp, nq - q0) : nq;
+    // the fused tile kernel takes every visit of a leaf with >= tile_min_rows rows (here) and n' <= 32; known up front, so
+    // the compaction can already set those visits aside and the host reads ONE record {flag, visits, slots, pairs} per batch
+    const bool tile_on = tile_scan_supported(ix->dimp, (u32)top_k) && ix->ensure_bucket_major();
+    u64 v_cap = std::max<u64>(ix->v_leaf.cap ? ix->v_leaf.cap - 1 : 0, nw + nw / 2 + 1024);
+    ix->plan_totals.ensure(4);
     for (;;) {
         ix->w_visits.ensure(nw * ix->vpw);
+        ix->v_leaf.ensure(v_cap + 1); ix->v_np.ensure(v_cap + 1); ix->v_q.ensure(v_cap + 1);
+        ix->v_pair_len.ensure(v_cap + 1); ix->v_pair_off.ensure(v_cap + 1);
+        ix->v_ent_len.ensure(v_cap + 1); ix->v_ent_off.ensure(v_cap + 1);
+        ix->v_done.ensure(v_cap + 1);
+        ix->scan_tmp(std::max<u64>(nw, v_cap) + 1);
         ZB_CUDA(cudaMemsetAsync(ix->w_flag.p, 0, 16, s));
         ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + nw, 0, 4, s));
         const u64 w0 = (u64)(sharded ? ix->rank : 0) * nqp * T;
@@ -846,39 +858,43 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
             launch_own_counts((u32)nw, ix->vpw, ix->w_visits.p, G, ix->rank, ix->w_counts.p, ix->w_own.p, ix->w_flag.p, s);
         }
         exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), sharded ? ix->w_own.p : ix->w_counts.p, ix->w_off.p, nw + 1, s);
-        ZB_CUDA(cudaMemcpyAsync(&h_flag, ix->w_flag.p, 4, cudaMemcpyDeviceToHost, s));
-        ZB_CUDA(cudaMemcpyAsync(&nv, ix->w_off.p + nw, 4, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaMemsetAsync(ix->v_pair_len.p, 0, (v_cap + 1) * 8, s));
+        ZB_CUDA(cudaMemsetAsync(ix->v_ent_len.p, 0, (v_cap + 1) * 4, s));
+        launch_compact_visits(fs, (u32)nw, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_off.p, G, ix->rank, (u32)v_cap,
+                              tile_on ? 1u : 0u, (u32)ix->p_tile_min_rows, (u32)top_k, ix->v_leaf.p, ix->v_np.p, ix->v_q.p,
+                              ix->v_pair_len.p, ix->v_ent_len.p, ix->v_done.p, s);
+        exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_ent_len.p, ix->v_ent_off.p, v_cap + 1, s);
+        exclusive_scan_u64(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_pair_len.p, ix->v_pair_off.p, v_cap + 1, s);
+        launch_plan_totals(ix->w_flag.p, ix->w_off.p, (u32)nw, (u32)v_cap, ix->v_ent_off.p, ix->v_pair_off.p, ix->plan_totals.p, s);
+        u64 h_tot[4] = {0, 0, 0, 0};
+        ZB_CUDA(cudaMemcpyAsync(h_tot, ix->plan_totals.p, 32, cudaMemcpyDeviceToHost, s));
         ix->sync();
-        ix->st.last_total_launches += 2;
-        if (h_flag == 0) break;
-        ZB_REQUIRE(h_flag == 1, ZB_ERR_STATE, "forest deeper than %d levels", ZB_MAX_DEPTH);
-        ix->vpw *= 2;  // a walker produced more visits than its region holds: grow and replan
-        ZB_REQUIRE(ix->vpw <= (1u << 16), ZB_ERR_STATE, "visit plan does not converge");
+        ix->st.last_total_launches += 6;
+        if (h_tot[0]) {
+            ZB_REQUIRE(h_tot[0] == 1, ZB_ERR_STATE, "forest deeper than %d levels", ZB_MAX_DEPTH);
+            ix->vpw *= 2;  // a walker produced more visits than its region holds: grow and replan
+            ZB_REQUIRE(ix->vpw <= (1u << 16), ZB_ERR_STATE, "visit plan does not converge");
+            continue;
+        }
+        nv = (u32)h_tot[1];
+        if (nv > v_cap) {  // more visits than the arrays hold: grow and compact again
+            v_cap = (u64)nv + nv / 4;
+            continue;
+        }
+        total_slots = (u32)h_tot[2];
+        total_pairs = h_tot[3];
+        break;
     }
-    ix->v_leaf.ensure(nv + 1); ix->v_np.ensure(nv + 1); ix->v_q.ensure(nv + 1);
-    ix->v_pair_len.ensure(nv + 1); ix->v_pair_off.ensure(nv + 1);
-    ix->v_ent_len.ensure(nv + 1); ix->v_ent_off.ensure(nv + 1);
-    ix->v_done.ensure(nv + 1);
-    ix->scan_tmp(nv + 1);
-    ZB_CUDA(cudaMemsetAsync(ix->v_pair_len.p + nv, 0, 8, s));
-    ZB_CUDA(cudaMemsetAsync(ix->v_ent_len.p + nv, 0, 4, s));
-    ZB_CUDA(cudaMemsetAsync(ix->v_done.p, 0, nv + 1, s));
-    launch_compact_visits(fs, (u32)nw, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_off.p, G, ix->rank, ix->v_leaf.p,
-                          ix->v_np.p, ix->v_q.p, ix->v_pair_len.p, ix->v_ent_len.p, s);
-    exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_ent_len.p, ix->v_ent_off.p, nv + 1, s);
-    u32 total_slots = 0;
-    ZB_CUDA(cudaMemcpyAsync(&total_slots, ix->v_ent_off.p + nv, 4, cudaMemcpyDeviceToHost, s));
-    ix->st.last_total_launches += 2;
     ZB_CUDA(cudaEventRecord(ix->ev[1], s));
     ix->trace_mark("compact");
 
-    // ---- fused leaf-tile scan for visits of large leaves (zb_scan.cu); marks v_done and shrinks pair_len ----
-    ix->sync();
+    // ---- fused leaf-tile scan for visits of large leaves (zb_scan.cu) ----
     ix->entries.ensure(total_slots ? total_slots : 1);
+    ix->pair_key.ensure(total_pairs ? total_pairs : 1);
     u64 tile_pairs = 0, tile_visits = 0, moved = 0;
     u32 scan_launches = 0;
     ix->scan_ws.launched = false;
-    if (nv && tile_scan_supported(ix->dimp, (u32)top_k) && ix->ensure_bucket_major()) {
+    if (nv && tile_on) {
         if (ix->opt.metric == ZB_METRIC_COSINE) {
             ix->q_rinv.ensure(nq);
             launch_rinv(d_q, nq, ix->dimp, ix->q_rinv.p, s);
@@ -886,15 +902,11 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
         tile_scan(ix->scan_ws, fs, ix->bm_view(), ix->opt.metric, d_q, ix->q_rinv.p, (u32)nq, nv, ix->v_leaf.p, ix->v_np.p, ix->v_q.p,
                   ix->v_ent_off.p, ix->v_pair_len.p, ix->v_done.p, ix->entries.p, (u32)top_k, (u32)ix->p_tile_min_rows,
                   (u32)ix->p_tile_queries, (u32)ix->h_leaf_off.size(), s);
-        if (ix->scan_ws.launched) scan_launches = ix->scan_ws.launches + (ix->opt.metric == ZB_METRIC_COSINE ? 1 : 0);
+        ZB_REQUIRE(ix->scan_ws.launched, ZB_ERR_STATE, "tile scan did not launch for visits set aside for it");
+        scan_launches = ix->scan_ws.launches + (ix->opt.metric == ZB_METRIC_COSINE ? 1 : 0);
     }
 
-    // ---- generic path for the remaining visits ----
-    exclusive_scan_u64(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_pair_len.p, ix->v_pair_off.p, nv + 1, s);
-    u64 total_pairs = 0;
-    ZB_CUDA(cudaMemcpyAsync(&total_pairs, ix->v_pair_off.p + nv, 8, cudaMemcpyDeviceToHost, s));
-    ix->sync();
-    ix->pair_key.ensure(total_pairs ? total_pairs : 1);
+    // ---- generic path for the remaining visits (pair offsets were scanned with the plan) ----
     launch_score_pairs(fs, (int)ix->opt.metric, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, total_pairs,
                        ix->pair_key.p, s);
     ZB_CUDA(cudaEventRecord(ix->ev[2], s));

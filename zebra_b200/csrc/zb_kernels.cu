@@ -104,10 +104,15 @@ void launch_own_counts(u32 nwalkers, u32 vpw, const uint2* d_wvisits, u32 G, u32
     if (!nwalkers) return;
     own_counts_kernel<<<(nwalkers + 255) / 256, 256, 0, s>>>(nwalkers, vpw, d_wvisits, G, rank, d_wcounts, d_wown, d_overflow);
 }
+// Visit records -> flat visit arrays.  A visit the fused tile kernel will take (tile_on, leaf holds >= min_rows rows here,
+// n' <= kmax) is marked done with no generic-path pairs right here, so that the entry-slot and pair totals are known
+// before any scoring starts and the host needs ONE readback per batch.  Writes are guarded by `cap` (the host grows the
+// arrays and reruns the compaction in the rare case the count exceeds it).
 __global__ void compact_visits_kernel(ForestView f, u32 nwalkers, u32 vpw, const uint2* __restrict__ wvisits,
-                                      const u32* __restrict__ wcounts, const u32* __restrict__ woff, u32 G, u32 rank,
-                                      u32* __restrict__ vleaf, u32* __restrict__ vnp, u32* __restrict__ vq,
-                                      u64* __restrict__ pair_len, u32* __restrict__ ent_len) {
+                                      const u32* __restrict__ wcounts, const u32* __restrict__ woff, u32 G, u32 rank, u32 cap,
+                                      u32 tile_on, u32 min_rows, u32 kmax, u32* __restrict__ vleaf, u32* __restrict__ vnp,
+                                      u32* __restrict__ vq, u64* __restrict__ pair_len, u32* __restrict__ ent_len,
+                                      u8* __restrict__ vdone) {
     u32 w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwalkers) return;
     u32 c = wcounts[w], base = woff[w];
@@ -115,21 +120,40 @@ __global__ void compact_visits_kernel(ForestView f, u32 nwalkers, u32 vpw, const
     for (u32 i = 0; i < c; ++i) {
         uint2 v = wvisits[(size_t)w * vpw + 1 + i];
         if (G > 1 && v.x % G != rank) continue;
-        vleaf[base] = v.x;
-        vnp[base] = v.y;
-        vq[base] = q;
-        pair_len[base] = f.leaf_len[v.x];
-        u32 live = f.leaf_plan[v.x];
-        ent_len[base] = live < v.y ? live : v.y;
+        if (base < cap) {
+            const u32 len = f.leaf_len[v.x];
+            const bool tiled = tile_on && len >= min_rows && v.y <= kmax;
+            vleaf[base] = v.x;
+            vnp[base] = v.y;
+            vq[base] = q;
+            pair_len[base] = tiled ? 0ull : (u64)len;
+            vdone[base] = tiled ? 1 : 0;
+            u32 live = f.leaf_plan[v.x];
+            ent_len[base] = live < v.y ? live : v.y;
+        }
         ++base;
     }
 }
 void launch_compact_visits(const ForestView& f, u32 nwalkers, u32 vpw, const uint2* d_wvisits, const u32* d_wcounts,
-                           const u32* d_woff, u32 G, u32 rank, u32* d_vleaf, u32* d_vnp, u32* d_vq, u64* d_pair_len,
-                           u32* d_ent_len, cudaStream_t s) {
+                           const u32* d_woff, u32 G, u32 rank, u32 cap, u32 tile_on, u32 min_rows, u32 kmax, u32* d_vleaf,
+                           u32* d_vnp, u32* d_vq, u64* d_pair_len, u32* d_ent_len, u8* d_vdone, cudaStream_t s) {
     if (!nwalkers) return;
-    compact_visits_kernel<<<(nwalkers + 255) / 256, 256, 0, s>>>(f, nwalkers, vpw, d_wvisits, d_wcounts, d_woff, G, rank, d_vleaf,
-                                                                 d_vnp, d_vq, d_pair_len, d_ent_len);
+    compact_visits_kernel<<<(nwalkers + 255) / 256, 256, 0, s>>>(f, nwalkers, vpw, d_wvisits, d_wcounts, d_woff, G, rank, cap, tile_on,
+                                                                 min_rows, kmax, d_vleaf, d_vnp, d_vq, d_pair_len, d_ent_len, d_vdone);
+}
+// {replan flag, visits, entry slots, generic-path pairs} of the batch in one 32-byte record
+__global__ void plan_totals_kernel(const u32* __restrict__ flag, const u32* __restrict__ woff, u32 nwalkers, u32 cap,
+                                   const u32* __restrict__ ent_off, const u64* __restrict__ pair_off, u64* __restrict__ out) {
+    const u32 nv = woff[nwalkers];
+    const u32 at = nv < cap ? nv : cap;
+    out[0] = flag[0];
+    out[1] = nv;
+    out[2] = ent_off[at];
+    out[3] = pair_off[at];
+}
+void launch_plan_totals(const u32* d_flag, const u32* d_woff, u32 nwalkers, u32 cap, const u32* d_ent_off, const u64* d_pair_off,
+                        u64* d_out, cudaStream_t s) {
+    plan_totals_kernel<<<1, 1, 0, s>>>(d_flag, d_woff, nwalkers, cap, d_ent_off, d_pair_off, d_out);
 }
 
 // =====================================================================================================

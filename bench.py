@@ -28,8 +28,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC_IDS = {"cosine": 0, "l2sq": 1, "l2": 2}
-METRIC_CLASSES = {"cosine": "CosineDistance", "l2sq": "L2SquaredDistance", "l2": "L2Distance"}
+# cosine / l2sq / l2 are the north-star metrics (fused leaf-tile scan); the rest are the scalar metrics of
+# distance.rs:51-190 (gather path, one thread per pair).  Oracle ids carry the Minkowski / p-norm power in bits 8..
+METRIC_IDS = {"cosine": 0, "l2sq": 1, "l2": 2, "chebyshev": 3, "canberra": 4, "bray_curtis": 5, "manhattan": 6, "l3": 7,
+              "l4": 8, "hamming": 9, "minkowski3": 10 | (3 << 8), "pnorm3": 11 | (3 << 8)}
+METRIC_CLASSES = {"cosine": ("CosineDistance", ()), "l2sq": ("L2SquaredDistance", ()), "l2": ("L2Distance", ()),
+                  "chebyshev": ("ChebyshevDistance", ()), "canberra": ("CanberraDistance", ()),
+                  "bray_curtis": ("BrayCurtisDistance", ()), "manhattan": ("ManhattanDistance", ()),
+                  "l3": ("L3Distance", ()), "l4": ("L4Distance", ()), "hamming": ("HammingDistance", ()),
+                  "minkowski3": ("MinkowskiDistance", (3,)), "pnorm3": ("PNormDistance", (3,))}
+
+
+def metric_object(z, name):
+    cls, args = METRIC_CLASSES[name]
+    return getattr(z, cls)(*args)
 
 
 def parse():
@@ -210,7 +222,7 @@ def run_ours(a):
     G = world
     nq = a.queries * G
     total_rows = a.rows * G
-    metric = getattr(z, METRIC_CLASSES[a.metric])()
+    metric = metric_object(z, a.metric)
     ix = z.LSHIndex(a.dim, z.LSHIndexOptions(a.max_node_size, a.trees), metric, device=local, seed=a.seed,
                     shard_rank=rank, shard_count=G)
     for kv in a.set:
@@ -316,7 +328,8 @@ def run_ours(a):
     scan_s = (agg["tile_ms"] if agg["tile_ms"] > 0 else agg["scan_ms"]) / 1e3
     achieved = agg["moved"] / scan_s / 1e9 if scan_s > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(a), "peak_source": peak_src, "kernel": "tile_scan_kernel (zb_scan.cu)",
+                "traffic": ncu_traffic(a), "peak_source": peak_src,
+                "kernel": "tile_scan_kernel (zb_scan.cu)" if agg["tile_ms"] > 0 else "score_pairs kernels (zb_kernels.cu, gather path)",
                 "algorithmic_bytes_per_launch": agg["moved"] // max(1, a.steps), "launches_per_step": 1,
                 "tiles_per_launch": agg["tiles"] // max(1, a.steps),
                 "kernel_ms_per_launch": scan_s * 1e3 / a.steps,
@@ -423,7 +436,7 @@ def run_aux(a):
         torch.cuda.synchronize()
 
     def new_index(sharded):
-        ix = z.LSHIndex(a.dim, z.LSHIndexOptions(a.max_node_size, a.trees), getattr(z, METRIC_CLASSES[a.metric])(), device=local,
+        ix = z.LSHIndex(a.dim, z.LSHIndexOptions(a.max_node_size, a.trees), metric_object(z, a.metric), device=local,
                         seed=a.seed, shard_rank=rank if sharded else 0, shard_count=G if sharded else 1)
         if sharded and G > 1:
             uid = [z.comm_unique_id() if rank == 0 else None]

@@ -17,8 +17,9 @@
  *     big-endian byte order = Ord); every row also has a u64 ORDINAL (its global insertion index), which is
  *     what ties are broken by and what the *_ordinals outputs carry.  Library-minted ids are UUIDv7 whose
  *     byte order equals ordinal order.
- *   - distances are DistanceUnit = u64 = f64 bit patterns (src/distance.rs:13), sorted as unsigned integers
- *     exactly like lsh.rs:318 / :561, ties by id ascending.
+ *   - distances are DistanceUnit = u64 = IEEE bit patterns (src/distance.rs:13; f64 bits for cosine / L2 / L2 squared,
+ *     zero-extended f32 bits for the scalar metrics), sorted as unsigned integers exactly like lsh.rs:318 / :561, ties
+ *     by id ascending.
  *   - a handle is internally serialised (one mutex): calls from any thread are safe; batch for throughput.
  */
 #ifndef ZEBRA_B200_H
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ZB_ABI_VERSION 1
+#define ZB_ABI_VERSION 2
 
 typedef struct zb_index zb_index;
 
@@ -45,9 +46,21 @@ typedef enum zb_status {
     ZB_ERR_COMM = -6       /* NCCL / sharding failure */
 } zb_status;
 
-/* The three metrics on the north-star path.  src/distance.rs:17-32 (Cosine, literal Q4 semantics:
- * (1 - simsimd cosine distance).to_bits()), :36-49 (L2Squared), :101-114 (L2). */
-typedef enum zb_metric { ZB_METRIC_COSINE = 0, ZB_METRIC_L2SQ = 1, ZB_METRIC_L2 = 2 } zb_metric;
+/* Metrics.  0..2 are the north-star path: src/distance.rs:17-32 (Cosine, literal Q4 semantics:
+ * (1 - simsimd cosine distance).to_bits()), :36-49 (L2Squared), :101-114 (L2); DistanceUnit = f64 bits.
+ * 3..11 are the reference's scalar metrics (the `distances` crate, one f32 fold per pair in element order;
+ * DistanceUnit = f32 bits zero-extended, NaN = 0xFFC00000): :51-61 Chebyshev, :63-73 Canberra, :75-85 Bray-Curtis,
+ * :87-97 Manhattan, :116-126 L3, :128-138 L4, :140-157 Hamming (popcount over the low byte of every element's
+ * bits; DistanceUnit = the count), :159-173 Minkowski and :175-190 p-norm (power in zb_options.metric_power,
+ * 0..64; MinkowskiDistance::default() has power 0).  They are served by the gather path of the scan (one thread per
+ * pair); the fused leaf-tile kernel covers 0..2. */
+typedef enum zb_metric {
+    ZB_METRIC_COSINE = 0, ZB_METRIC_L2SQ = 1, ZB_METRIC_L2 = 2,
+    ZB_METRIC_CHEBYSHEV = 3, ZB_METRIC_CANBERRA = 4, ZB_METRIC_BRAY_CURTIS = 5, ZB_METRIC_MANHATTAN = 6,
+    ZB_METRIC_L3 = 7, ZB_METRIC_L4 = 8, ZB_METRIC_HAMMING = 9, ZB_METRIC_MINKOWSKI = 10, ZB_METRIC_PNORM = 11
+} zb_metric;
+#define ZB_METRIC_COUNT 12
+#define ZB_METRIC_MAX_POWER 64
 
 /* LSHIndexOptions (lsh.rs:124-138) plus device placement.  Zero-initialise, then set fields. */
 typedef struct zb_options {
@@ -59,7 +72,8 @@ typedef struct zb_options {
     uint64_t seed;          /* seed of the hyperplane sampling stream (reference: unseeded rand::rng()) */
     uint32_t shard_rank;    /* this process's shard; rows with ordinal % shard_count == shard_rank live here */
     uint32_t shard_count;   /* 0 or 1 = unsharded */
-    uint32_t reserved[4];
+    int32_t metric_power;   /* MinkowskiDistance / PNormDistance `power` (distance.rs:164, :181); ignored otherwise */
+    uint32_t reserved[3];
 } zb_options;
 
 typedef struct zb_stats {
@@ -163,10 +177,11 @@ int zb_comm_unique_id(uint8_t* out_id128);
 int zb_index_comm_init(zb_index* index, const uint8_t* id128);
 
 /* The metric trait and the sign test for n independent pairs (host buffers): Metric::distance of
- * src/distance.rs:19-32 / :38-49 / :103-114 with arguments (a = stored row, b = query), and
- * Hyperplane::point_is_above of lsh.rs:39-43.  Used by the host mirror's Metric::distance and by parity tests. */
-int zb_metric_distance_batch(int device, uint32_t metric, uint64_t n, uint32_t dim, const float* a, const float* b,
-                             uint64_t* out_bits);
+ * src/distance.rs (every impl, :19-190) with arguments (a = stored row, b = query), and
+ * Hyperplane::point_is_above of lsh.rs:39-43.  Used by the host mirror's Metric::distance and by parity tests.
+ * power: Minkowski / p-norm only. */
+int zb_metric_distance_batch(int device, uint32_t metric, int32_t power, uint64_t n, uint32_t dim, const float* a,
+                             const float* b, uint64_t* out_bits);
 int zb_point_is_above_batch(int device, uint64_t n, uint32_t dim, const float* coef, const float* cst, const float* x,
                             uint8_t* out);
 

@@ -43,7 +43,14 @@
 #define ZBO_MAX_DEPTH 96
 #define ZBO_MAX_ATTEMPTS 4
 
-enum { ZBO_COSINE = 0, ZBO_L2SQ = 1, ZBO_L2 = 2 };
+/* Metric codes.  0..2 run on the simsimd path (f64 bits); 3..11 are the scalar metrics of the `distances` crate
+ * (distance.rs:51-190, f32 bits zero-extended, survey quirk Q6).  Minkowski / p-norm carry their power in bits 8..:
+ * metric = code | (power << 8). */
+enum {
+    ZBO_COSINE = 0, ZBO_L2SQ = 1, ZBO_L2 = 2,
+    ZBO_CHEBYSHEV = 3, ZBO_CANBERRA = 4, ZBO_BRAY_CURTIS = 5, ZBO_MANHATTAN = 6, ZBO_L3 = 7, ZBO_L4 = 8,
+    ZBO_HAMMING = 9, ZBO_MINKOWSKI = 10, ZBO_PNORM = 11
+};
 
 /* ------------------------------------------------------------------------------------------------
  * Arithmetic: the "skylake-16" order.
@@ -232,14 +239,115 @@ static inline uint64_t f64_bits(double x) {
     return u;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * The ten scalar metrics (distance.rs:51-190).  They call the un-vendored crate `distances` (^1.8.0,
+ * Cargo.toml:38; source NOT on this machine -- restated from its published algorithm, PARITY UNPINNED):
+ * plain iterator folds over the zipped slices in input order, in f32 (T = U = EmbeddingPrecision), no
+ * reassociation (rustc never contracts or reorders float arithmetic), result `.to_bits()` (u32) widened
+ * to u64.  Spec the oracle fixes (oracle/README.md, "scalar metrics"):
+ *   abs_diff(a,b) = |a - b|
+ *   chebyshev    fold(0, |acc, v| if acc > v { acc } else { v })          distance.rs:57-60
+ *   canberra     sum |a-b| / (|a| + |b|)   (0/0 = NaN, as IEEE gives)      distance.rs:69-72
+ *   bray_curtis  (sum |a-b|) / (sum |a+b|)                                 distance.rs:81-84
+ *   manhattan    sum |a-b|                                                 distance.rs:93-96
+ *   l3_norm      cbrt(sum v*v*v),   l4_norm  sqrt(sqrt(sum (v*v)*(v*v)))   distance.rs:122-125, :134-137
+ *   hamming      popcount over the LOW BYTE of every element's bit pattern distance.rs:145-155
+ *   minkowski(p) powf(sum powi(v, p), 1/p);  minkowski_p(p) = the sum      distance.rs:168-172, :185-189
+ * powi is compiler-rt's __powisf2 (square and multiply).  The two roots that are not IEEE operations
+ * (cbrt, powf(., 1/p)) are replaced by ONE deterministic algorithm built from IEEE double operations only
+ * (root_p below), so the CPU and the GPU agree bit for bit; against libm's cbrtf / powf it is within 1 ulp
+ * of f32 (powf(s, fl32(1/p)) additionally differs from the true p-th root by about |ln s| * 1e-8 relative).
+ * A NaN result is canonicalised to 0xFFC00000, the default NaN of x86 SSE arithmetic (what 0.0/0.0 yields on
+ * the reference's host).
+ * ---------------------------------------------------------------------------------------------- */
+static inline uint64_t f32_key(float r) {
+    uint32_t u;
+    if (r != r) return 0xFFC00000ull;
+    memcpy(&u, &r, 4);
+    return (uint64_t)u;
+}
+static inline float powi_f32(float a, int b) { /* compiler-rt __powisf2, b >= 0 */
+    float r = 1.0f;
+    for (;;) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return r;
+}
+static inline double powi_f64(double a, int b) {
+    double r = 1.0;
+    for (;;) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return r;
+}
+/* p-th root of a non-negative f32 (p >= 1): Newton's iteration y <- ((p-1) y + x / y^(p-1)) / p in f64 from a
+ * bit-pattern initial guess, stopped at the first step that does not decrease y, rounded once to f32. */
+float zbo_root_p(float s, int p) {
+    if (p == 1 || s != s || s == 0.0f || s == INFINITY) return s;
+    double x = (double)s;
+    uint64_t bx, by;
+    memcpy(&bx, &x, 8);
+    by = bx / (uint64_t)p + (0x3FF0000000000000ull / (uint64_t)p) * (uint64_t)(p - 1);
+    double y;
+    memcpy(&y, &by, 8);
+    for (int it = 0; it < 1000; ++it) {
+        double t = x / powi_f64(y, p - 1);
+        double yn = ((double)(p - 1) * y + t) / (double)p;
+        if (it > 0 && yn >= y) break;
+        y = yn;
+    }
+    return (float)y;
+}
+static uint64_t scalar_metric_bits(int code, int power, const float* a, const float* b, int n) {
+    float acc = 0.0f, den = 0.0f;
+    uint32_t ham = 0;
+    for (int i = 0; i < n; ++i) {
+        float x = a[i], y = b[i];
+        float v = fabsf(x - y);
+        switch (code) {
+            case ZBO_CHEBYSHEV: acc = acc > v ? acc : v; break;
+            case ZBO_CANBERRA: acc = acc + v / (fabsf(x) + fabsf(y)); break;
+            case ZBO_BRAY_CURTIS: acc = acc + v; den = den + fabsf(x + y); break;
+            case ZBO_MANHATTAN: acc = acc + v; break;
+            case ZBO_L3: acc = acc + (v * v) * v; break;
+            case ZBO_L4: { float v2 = v * v; acc = acc + v2 * v2; break; }
+            case ZBO_HAMMING: {
+                uint32_t ux, uy;
+                memcpy(&ux, &x, 4);
+                memcpy(&uy, &y, 4);
+                ham += (uint32_t)__builtin_popcount((ux ^ uy) & 0xFFu);
+                break;
+            }
+            default: acc = acc + powi_f32(v, power); break; /* minkowski, p-norm */
+        }
+    }
+    switch (code) {
+        case ZBO_BRAY_CURTIS: return f32_key(acc / den);
+        case ZBO_L3: return f32_key(zbo_root_p(acc, 3));
+        case ZBO_L4: return f32_key(sqrtf(sqrtf(acc)));
+        case ZBO_HAMMING: return (uint64_t)ham;
+        case ZBO_MINKOWSKI:
+            if (power == 0) return f32_key(acc == 1.0f ? 1.0f : INFINITY); /* powf(n, 1/0 = +inf), n >= 1 */
+            return f32_key(zbo_root_p(acc, power));
+        default: return f32_key(acc);
+    }
+}
+
 /* Metric::distance -> DistanceUnit = u64 of the f64 bits (distance.rs:13, :19-32, :38-49, :103-114).
  * Argument order is (stored row, query) as at lsh.rs:314 and :559.  CosineDistance returns
  * (1.0 - simsimd cosine distance).to_bits() -- quirk Q4, reproduced literally. */
 uint64_t zbo_distance_bits(int metric, const float* row, const float* query, int n) {
-    switch (metric) {
+    switch (metric & 0xFF) {
         case ZBO_COSINE: return f64_bits(1.0 - zbo_cos_f32(row, query, n));
         case ZBO_L2SQ: return f64_bits(zbo_l2sq_f32(row, query, n));
-        default: return f64_bits(zbo_l2_f32(row, query, n));
+        case ZBO_L2: return f64_bits(zbo_l2_f32(row, query, n));
+        default: return scalar_metric_bits(metric & 0xFF, metric >> 8, row, query, n);
     }
 }
 

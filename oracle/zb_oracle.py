@@ -15,6 +15,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libzb_oracle.so")
 
 COSINE, L2SQ, L2 = 0, 1, 2
+# the scalar metrics of distance.rs:51-190 (f32 bits zero-extended); Minkowski / p-norm carry the power in bits 8..
+CHEBYSHEV, CANBERRA, BRAY_CURTIS, MANHATTAN, L3, L4, HAMMING = 3, 4, 5, 6, 7, 8, 9
+
+
+def MINKOWSKI(power: int) -> int:
+    return 10 | (int(power) << 8)
+
+
+def PNORM(power: int) -> int:
+    return 11 | (int(power) << 8)
 
 
 def build(force: bool = False) -> str:
@@ -62,6 +72,8 @@ def lib():
         L.zbo_l2sq_f32.argtypes = [vp, vp, i32]
         L.zbo_cos_f32.restype = C.c_double
         L.zbo_cos_f32.argtypes = [vp, vp, i32]
+        L.zbo_root_p.restype = C.c_float
+        L.zbo_root_p.argtypes = [C.c_float, i32]
         L.zbo_distance_bits.restype = u64
         L.zbo_distance_bits.argtypes = [i32, vp, vp, i32]
         L.zbo_distance_bits_batch.argtypes = [i32, u64, vp, vp, i32, vp]
@@ -100,6 +112,11 @@ def l2sq(a, b) -> float:
 def cosdist(a, b) -> float:
     a, b = _f32(a), _f32(b)
     return lib().zbo_cos_f32(_p(a), _p(b), a.size)
+
+
+def root_p(s: float, p: int) -> float:
+    """The deterministic p-th root the scalar metrics use in place of cbrtf / powf(., 1/p)."""
+    return lib().zbo_root_p(float(s), int(p))
 
 
 def distance_bits(metric: int, row, query) -> int:

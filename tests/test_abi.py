@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     exported = subprocess.run(["nm", "-D", "--defined-only", _ffi.LIB_PATH], capture_output=True, text=True).stdout
     got = sorted(set(re.findall(r" T (zb_[a-z0-9_]+)", exported)))
     assert got == declared
-    assert lib.zb_abi_version() == 1
+    assert lib.zb_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -37,6 +37,7 @@ def test_struct_layouts_match_header():
 
     assert C.sizeof(_ffi.Options) == 56
     assert _ffi.Options.max_node_size.offset == 8 and _ffi.Options.seed.offset == 24
+    assert _ffi.Options.metric_power.offset == 40
     assert C.sizeof(_ffi.Stats) == 13 * 8 + 5 * 4 + 2 * 4 + 8 * 4 + 4  # tail padding to 8
 
 
@@ -76,6 +77,10 @@ def test_invalid_arguments_are_reported():
     o.dim, o.metric, o.num_trees = 0, 0, 1
     h = C.c_void_p()
     assert lib.zb_index_create(C.byref(o), C.byref(h)) == -1
-    o.dim, o.metric = 16, 9
+    o.dim, o.metric = 16, 12                              # one past the last zb_metric
+    assert lib.zb_index_create(C.byref(o), C.byref(h)) == -1
+    o.metric, o.metric_power = _ffi.METRIC_MINKOWSKI, 65  # Minkowski power out of range
+    assert lib.zb_index_create(C.byref(o), C.byref(h)) == -1 and b"metric_power" in lib.zb_last_error()
+    o.metric_power = -1
     assert lib.zb_index_create(C.byref(o), C.byref(h)) == -1
     assert lib.zb_index_destroy(None) == 0

@@ -12,6 +12,9 @@ LIB_PATH = os.path.join(_HERE, "libzebra_b200.so")
 
 ZB_OK = 0
 METRIC_COSINE, METRIC_L2SQ, METRIC_L2 = 0, 1, 2
+(METRIC_CHEBYSHEV, METRIC_CANBERRA, METRIC_BRAY_CURTIS, METRIC_MANHATTAN, METRIC_L3, METRIC_L4, METRIC_HAMMING,
+ METRIC_MINKOWSKI, METRIC_PNORM) = range(3, 12)
+METRIC_MAX_POWER = 64
 
 
 class ZebraError(RuntimeError):
@@ -30,7 +33,8 @@ class Options(C.Structure):
         ("seed", C.c_uint64),
         ("shard_rank", C.c_uint32),
         ("shard_count", C.c_uint32),
-        ("reserved", C.c_uint32 * 4),
+        ("metric_power", C.c_int32),
+        ("reserved", C.c_uint32 * 3),
     ]
 
 
@@ -94,7 +98,7 @@ SYMBOLS = {
     "zb_index_set_param": (C.c_int, [_vp, C.c_char_p, _i64]),
     "zb_comm_unique_id": (C.c_int, [_vp]),
     "zb_index_comm_init": (C.c_int, [_vp, _vp]),
-    "zb_metric_distance_batch": (C.c_int, [C.c_int, _u32, _u64, _u32, _vp, _vp, _vp]),
+    "zb_metric_distance_batch": (C.c_int, [C.c_int, _u32, _i32, _u64, _u32, _vp, _vp, _vp]),
     "zb_point_is_above_batch": (C.c_int, [C.c_int, _u64, _u32, _vp, _vp, _vp, _vp]),
     "zb_synth_fill_device": (C.c_int, [C.c_int, _vp, _u64, _u64, _u64, _u32, _u64, _u32]),
 }

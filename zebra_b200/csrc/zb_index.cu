@@ -173,6 +173,7 @@ struct zb_index {
         f.row_norm = row_norm.p;
         f.tomb = tomb.p;
         f.dimp = dimp;
+        f.dim = dim;
         f.chunks = chunks;
         f.num_trees = T;
         return f;
@@ -829,7 +830,8 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     const u64 qn = sharded ? std::min<u64>(nqp, nq - q0) : nq;
     // the fused tile kernel takes every visit of a leaf with >= tile_min_rows rows (here) and n' <= 32; known up front, so
     // the compaction can already set those visits aside and the host reads ONE record {flag, visits, slots, pairs} per batch
-    const bool tile_on = tile_scan_supported(ix->dimp, (u32)top_k) && ix->ensure_bucket_major();
+    // (the scalar metrics 3..11 are a sequential fold per pair: gather path only)
+    const bool tile_on = ix->opt.metric <= ZB_METRIC_L2 && tile_scan_supported(ix->dimp, (u32)top_k) && ix->ensure_bucket_major();
     u64 v_cap = std::max<u64>(ix->v_leaf.cap ? ix->v_leaf.cap - 1 : 0, nw + nw / 2 + 1024);
     ix->plan_totals.ensure(4);
     for (;;) {
@@ -907,7 +909,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     }
 
     // ---- generic path for the remaining visits (pair offsets were scanned with the plan) ----
-    launch_score_pairs(fs, (int)ix->opt.metric, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, total_pairs,
+    launch_score_pairs(fs, (int)ix->opt.metric, (int)ix->opt.metric_power, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, total_pairs,
                        ix->pair_key.p, s);
     ZB_CUDA(cudaEventRecord(ix->ev[2], s));
     ix->trace_mark("scan");
@@ -1054,7 +1056,10 @@ int zb_index_create(const zb_options* o, zb_index** out) {
     ZB_API_BEGIN
     ZB_REQUIRE(o && out, ZB_ERR_INVALID, "NULL argument");
     ZB_REQUIRE(o->dim >= 1 && o->dim <= 65536, ZB_ERR_INVALID, "dim %u out of range", o->dim);
-    ZB_REQUIRE(o->metric <= 2, ZB_ERR_INVALID, "metric %u is not one of cosine/l2sq/l2", o->metric);
+    ZB_REQUIRE(o->metric < ZB_METRIC_COUNT, ZB_ERR_INVALID, "metric %u is not a zb_metric", o->metric);
+    ZB_REQUIRE((o->metric != ZB_METRIC_MINKOWSKI && o->metric != ZB_METRIC_PNORM) ||
+                   (o->metric_power >= 0 && o->metric_power <= ZB_METRIC_MAX_POWER),
+               ZB_ERR_INVALID, "metric_power %d out of range 0..%d", o->metric_power, ZB_METRIC_MAX_POWER);
     ZB_REQUIRE(o->num_trees >= 1 && o->num_trees <= 4096, ZB_ERR_INVALID, "num_trees %u out of range", o->num_trees);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1755,10 +1760,12 @@ static void pad_to_device(int device, const float* h, u64 n, u32 dim, int dimp, 
     ZB_CUDA(cudaMemcpy2D(d.p, (size_t)dimp * 4, h, (size_t)dim * 4, (size_t)dim * 4, n, cudaMemcpyHostToDevice));
 }
 
-int zb_metric_distance_batch(int device, uint32_t metric, uint64_t n, uint32_t dim, const float* a, const float* b,
+int zb_metric_distance_batch(int device, uint32_t metric, int32_t power, uint64_t n, uint32_t dim, const float* a, const float* b,
                              uint64_t* out_bits) {
     ZB_API_BEGIN
-    ZB_REQUIRE(metric <= 2 && dim >= 1 && ((a && b && out_bits) || !n), ZB_ERR_INVALID, "bad argument");
+    ZB_REQUIRE(metric < ZB_METRIC_COUNT && dim >= 1 && ((a && b && out_bits) || !n), ZB_ERR_INVALID, "bad argument");
+    ZB_REQUIRE((metric != ZB_METRIC_MINKOWSKI && metric != ZB_METRIC_PNORM) || (power >= 0 && power <= ZB_METRIC_MAX_POWER),
+               ZB_ERR_INVALID, "power %d out of range 0..%d", power, ZB_METRIC_MAX_POWER);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || !ndev) {
         cudaGetLastError();
@@ -1771,7 +1778,7 @@ int zb_metric_distance_batch(int device, uint32_t metric, uint64_t n, uint32_t d
     pad_to_device(device, a, n, dim, dimp, da);
     pad_to_device(device, b, n, dim, dimp, db);
     dout.ensure(std::max<u64>(1, n));
-    launch_pair_metric((int)metric, da.p, db.p, n, dimp, dout.p, 0);
+    launch_pair_metric((int)metric, (int)power, da.p, db.p, n, (int)dim, dimp, dout.p, 0);
     ZB_CUDA(cudaMemcpy(out_bits, dout.p, n * 8, cudaMemcpyDeviceToHost));
     ZB_API_END
 }

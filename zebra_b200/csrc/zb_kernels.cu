@@ -226,9 +226,87 @@ __global__ void __launch_bounds__(128) score_pairs_kernel(ForestView f, const fl
     if (sub == 0) pair_key[p] = key;
 }
 
-void launch_score_pairs(const ForestView& f, int metric, const float* d_queries, u32 nv, const u32* d_vleaf,
+// The scalar metrics of distance.rs:51-190 (zb_metrics.cuh): a strictly sequential f32 fold per pair, so ONE THREAD owns a
+// pair and walks its row once with 128-bit loads; the 32 pairs of a warp are (mostly) consecutive members of one visit, so
+// the query elements are a broadcast and every row sector is consumed whole over two consecutive loads.  HBM-bound
+// gather, 4N bytes per pair.
+template <int CODE>
+__device__ __forceinline__ u64 seq_distance_ldg(const float* __restrict__ a_, const float* __restrict__ b_, int dim, int power) {
+    const float4* a = reinterpret_cast<const float4*>(a_);
+    const float4* b = reinterpret_cast<const float4*>(b_);
+    SeqAcc st;
+    seq_init(st);
+    const int n4 = dim >> 2;
+#pragma unroll 2
+    for (int i = 0; i < n4; ++i) {
+        const float4 av = __ldg(a + i), bv = __ldg(b + i);
+        seq_step<CODE>(st, av.x, bv.x, power);
+        seq_step<CODE>(st, av.y, bv.y, power);
+        seq_step<CODE>(st, av.z, bv.z, power);
+        seq_step<CODE>(st, av.w, bv.w, power);
+    }
+    for (int i = n4 * 4; i < dim; ++i) seq_step<CODE>(st, __ldg(a_ + i), __ldg(b_ + i), power);  // dim % 4 tail (never the padding)
+    return seq_finish<CODE>(st, power);
+}
+
+template <int CODE>
+__global__ void __launch_bounds__(128) score_pairs_seq_kernel(ForestView f, int power, const float* __restrict__ queries, u32 nv,
+                                                              const u32* __restrict__ vleaf, const u32* __restrict__ vq,
+                                                              const u64* __restrict__ pair_off, u64 total_pairs,
+                                                              u64* __restrict__ pair_key) {
+    __shared__ u32 s_v0;
+    const u64 p0 = (u64)blockIdx.x * 128ull;
+    if (threadIdx.x == 0) {  // visit containing pair p0: last v with pair_off[v] <= p0
+        u32 lo = 0, hi = nv;
+        while (hi - lo > 1) {
+            u32 mid = (lo + hi) >> 1;
+            if (pair_off[mid] <= p0) lo = mid; else hi = mid;
+        }
+        s_v0 = lo;
+    }
+    __syncthreads();
+    const u64 p = p0 + threadIdx.x;
+    if (p >= total_pairs) return;
+    u32 v = s_v0;
+    {
+        u32 hi = nv;
+        while (hi - v > 1) {
+            const u32 mid = (v + hi) >> 1;
+            if (pair_off[mid] <= p) v = mid; else hi = mid;
+        }
+    }
+    const u32 leaf = vleaf[v];
+    const u32 slot = f.members[f.leaf_off[leaf] + (long long)(p - pair_off[v])];
+    if (tomb_test(f.tomb, slot)) {
+        pair_key[p] = ZB_SENTINEL;
+        return;
+    }
+    pair_key[p] = seq_distance_ldg<CODE>(f.rows + (size_t)slot * f.dimp, queries + (size_t)vq[v] * f.dimp, f.dim, power);
+}
+
+#define ZB_SEQ_DISPATCH(code, CALL)                     \
+    switch (code) {                                     \
+        case M_CHEBYSHEV: CALL(M_CHEBYSHEV); break;     \
+        case M_CANBERRA: CALL(M_CANBERRA); break;       \
+        case M_BRAY_CURTIS: CALL(M_BRAY_CURTIS); break; \
+        case M_MANHATTAN: CALL(M_MANHATTAN); break;     \
+        case M_L3: CALL(M_L3); break;                   \
+        case M_L4: CALL(M_L4); break;                   \
+        case M_HAMMING: CALL(M_HAMMING); break;         \
+        case M_MINKOWSKI: CALL(M_MINKOWSKI); break;     \
+        default: CALL(M_PNORM); break;                  \
+    }
+
+void launch_score_pairs(const ForestView& f, int metric, int power, const float* d_queries, u32 nv, const u32* d_vleaf,
                         const u32* d_vq, const u64* d_pair_off, u64 total_pairs, u64* d_pair_key, cudaStream_t s) {
     if (!total_pairs) return;
+    if (metric > M_L2) {
+        const u32 sblocks = (u32)((total_pairs + 127) / 128);
+#define ZB_CALL(C) score_pairs_seq_kernel<C><<<sblocks, 128, 0, s>>>(f, power, d_queries, nv, d_vleaf, d_vq, d_pair_off, total_pairs, d_pair_key)
+        ZB_SEQ_DISPATCH(metric, ZB_CALL)
+#undef ZB_CALL
+        return;
+    }
     u32 blocks = (u32)((total_pairs + 31) / 32);
     if (metric == 0)
         score_pairs_kernel<0><<<blocks, 128, 0, s>>>(f, d_queries, nv, d_vleaf, d_vq, d_pair_off, total_pairs, d_pair_key);
@@ -995,8 +1073,23 @@ __global__ void __launch_bounds__(128) pair_metric_kernel(const float* __restric
     }
     if (sub == 0) out[i] = key;
 }
-void launch_pair_metric(int metric, const float* d_a, const float* d_b, u64 n, int dimp, u64* d_out, cudaStream_t s) {
+template <int CODE>
+__global__ void __launch_bounds__(128) pair_metric_seq_kernel(const float* __restrict__ a, const float* __restrict__ b, u64 n,
+                                                              int dim, int dimp, int power, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * 128ull + threadIdx.x;
+    if (i >= n) return;
+    out[i] = seq_distance_ldg<CODE>(a + i * dimp, b + i * dimp, dim, power);
+}
+void launch_pair_metric(int metric, int power, const float* d_a, const float* d_b, u64 n, int dim, int dimp, u64* d_out,
+                        cudaStream_t s) {
     if (!n) return;
+    if (metric > M_L2) {
+        const u32 sblocks = (u32)((n + 127) / 128);
+#define ZB_CALL(C) pair_metric_seq_kernel<C><<<sblocks, 128, 0, s>>>(d_a, d_b, n, dim, dimp, power, d_out)
+        ZB_SEQ_DISPATCH(metric, ZB_CALL)
+#undef ZB_CALL
+        return;
+    }
     u32 blocks = (u32)((n + 31) / 32);
     if (metric == 0) pair_metric_kernel<0><<<blocks, 128, 0, s>>>(d_a, d_b, n, dimp, d_out);
     else if (metric == 1) pair_metric_kernel<1><<<blocks, 128, 0, s>>>(d_a, d_b, n, dimp, d_out);

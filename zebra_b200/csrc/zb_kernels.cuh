@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "zb_device.cuh"
+#include "zb_metrics.cuh"
 
 namespace zb {
 
@@ -26,6 +27,7 @@ struct ForestView {
     const float* row_norm;    // [slots] squared norm of the row in the canonical order (cosine)
     const u32* tomb;          // bitmask over slots
     int dimp, chunks, num_trees;
+    int dim;                  // unpadded N (the scalar metrics must not fold the padding: Canberra would see 0/0)
 };
 
 struct SegDesc {      // one node under construction (build)
@@ -59,7 +61,7 @@ void launch_compact_visits(const ForestView& f, u32 nwalkers, u32 vpw, const uin
 void launch_plan_totals(const u32* d_flag, const u32* d_woff, u32 nwalkers, u32 cap, const u32* d_ent_off, const u64* d_pair_off,
                         u64* d_out, cudaStream_t s);
 // ---- scoring of (visit, member) pairs, generic path ----
-void launch_score_pairs(const ForestView& f, int metric, const float* d_queries, u32 nv, const u32* d_vleaf,
+void launch_score_pairs(const ForestView& f, int metric, int power, const float* d_queries, u32 nv, const u32* d_vleaf,
                         const u32* d_vq, const u64* d_pair_off, u64 total_pairs, u64* d_pair_key, cudaStream_t s);
 // ---- per-visit top-n' (Q2) and per-query union/dedup/top-k (lsh.rs:557-564) ----
 void launch_select_visits(const ForestView& f, u32 nv, const u32* d_vleaf, const u32* d_vnp, const u64* d_pair_off,
@@ -99,7 +101,8 @@ void launch_iota_ord(u64* d, u64 n, u64 first, u64 stride, cudaStream_t s);
 void launch_synth(float* d_out, u64 first_row, u64 row_stride, u64 n, u32 dim, u64 seed, u32 kind, cudaStream_t s);
 
 void launch_sq_norms(const float* d_x, u64 n, int dimp, float* d_out, cudaStream_t s);
-void launch_pair_metric(int metric, const float* d_a, const float* d_b, u64 n, int dimp, u64* d_out, cudaStream_t s);
+void launch_pair_metric(int metric, int power, const float* d_a, const float* d_b, u64 n, int dim, int dimp, u64* d_out,
+                        cudaStream_t s);
 void launch_pair_above(const float* d_coef, const float* d_cst, const float* d_x, u64 n, int dimp, u8* d_out, cudaStream_t s);
 
 // ---- bucket-sharded store (G > 1) ----

@@ -1,9 +1,10 @@
 """Distance metrics: the host mirror of /root/reference/src/distance.rs.
 
-The three metrics on the north-star path keep the reference's names and its trait shape --
-``metric.distance(a, b) -> DistanceUnit`` (u64 = f64 bit pattern, distance.rs:13) -- and additionally carry
-the ``METRIC`` enum the device index needs.  They are evaluated by the CUDA library (no CPU arithmetic here).
-The reference's ten other metrics (distance.rs:51-190) are outside the hot-path scope.
+Every metric keeps the reference's name and its trait shape -- ``metric.distance(a, b) -> DistanceUnit`` (u64,
+distance.rs:13) -- and additionally carries the ``METRIC`` enum the device index needs.  They are evaluated by the CUDA
+library (no CPU arithmetic here).  Cosine / L2Squared / L2 (the north-star path, simsimd) return f64 bit patterns; the
+ten scalar metrics (distance.rs:51-190, the `distances` crate) return f32 bit patterns zero-extended, exactly as the
+reference's ``.to_bits().into()`` does (survey quirk Q6).
 """
 from __future__ import annotations
 
@@ -20,6 +21,8 @@ DistanceUnit = int  # u64
 class _DeviceMetric:
     METRIC: int = -1
     device: int = 0
+    power: int = 0          # MinkowskiDistance / PNormDistance only
+    BITS: int = 64          # width of the IEEE pattern inside DistanceUnit
 
     def distance(self, a, b) -> DistanceUnit:
         """Metric::distance(&self, a: &Embedding<N>, b: &Embedding<N>) -> u64, arguments (stored row, query)."""
@@ -31,15 +34,24 @@ class _DeviceMetric:
         if a.shape != b.shape or a.ndim != 2:
             raise ValueError("distance_batch takes two [n, dim] arrays of the same shape")
         out = np.empty(a.shape[0], dtype=np.uint64)
-        _ffi.check(_ffi.lib().zb_metric_distance_batch(self.device, self.METRIC, a.shape[0], a.shape[1],
+        _ffi.check(_ffi.lib().zb_metric_distance_batch(self.device, self.METRIC, self.power, a.shape[0], a.shape[1],
                                                        a.ctypes.data, b.ctypes.data, out.ctypes.data))
         return out
 
+    def to_float(self, bits) -> np.ndarray:
+        """DistanceUnit -> the floating-point value it encodes (Hamming: the count itself)."""
+        bits = np.asarray(bits, dtype=np.uint64)
+        if self.BITS == 64:
+            return bits.view(np.float64)
+        if self.BITS == 32:
+            return bits.astype(np.uint32).view(np.float32)
+        return bits.astype(np.float64)
+
     def __eq__(self, other):
-        return type(self) is type(other)
+        return type(self) is type(other) and self.power == other.power
 
     def __hash__(self):
-        return hash(type(self).__name__)
+        return hash((type(self).__name__, self.power))
 
 
 class CosineDistance(_DeviceMetric):
@@ -55,6 +67,65 @@ class L2SquaredDistance(_DeviceMetric):
 class L2Distance(_DeviceMetric):
     """distance.rs:99-114."""
     METRIC = _ffi.METRIC_L2
+
+
+class _ScalarMetric(_DeviceMetric):
+    BITS = 32
+
+
+class ChebyshevDistance(_ScalarMetric):
+    """distance.rs:51-61."""
+    METRIC = _ffi.METRIC_CHEBYSHEV
+
+
+class CanberraDistance(_ScalarMetric):
+    """distance.rs:63-73.  An element pair (0, 0) contributes 0/0 = NaN, as IEEE arithmetic gives the reference."""
+    METRIC = _ffi.METRIC_CANBERRA
+
+
+class BrayCurtisDistance(_ScalarMetric):
+    """distance.rs:75-85."""
+    METRIC = _ffi.METRIC_BRAY_CURTIS
+
+
+class ManhattanDistance(_ScalarMetric):
+    """distance.rs:87-97."""
+    METRIC = _ffi.METRIC_MANHATTAN
+
+
+class L3Distance(_ScalarMetric):
+    """distance.rs:116-126."""
+    METRIC = _ffi.METRIC_L3
+
+
+class L4Distance(_ScalarMetric):
+    """distance.rs:128-138."""
+    METRIC = _ffi.METRIC_L4
+
+
+class HammingDistance(_ScalarMetric):
+    """distance.rs:140-157: popcount over the low byte of every element's f32 bit pattern (`x.to_bits() as u8`)."""
+    METRIC = _ffi.METRIC_HAMMING
+    BITS = 0
+
+
+class _PowerMetric(_ScalarMetric):
+    def __init__(self, power: int = 0):
+        """`power` as the reference's public field (distance.rs:164, :181); `Default` gives 0."""
+        power = int(power)
+        if not 0 <= power <= _ffi.METRIC_MAX_POWER:
+            raise ValueError(f"power must be in 0..{_ffi.METRIC_MAX_POWER}")
+        self.power = power
+
+
+class MinkowskiDistance(_PowerMetric):
+    """distance.rs:159-173."""
+    METRIC = _ffi.METRIC_MINKOWSKI
+
+
+class PNormDistance(_PowerMetric):
+    """distance.rs:175-190."""
+    METRIC = _ffi.METRIC_PNORM
 
 
 def bits_to_f64(bits) -> np.ndarray:

@@ -49,7 +49,8 @@ def _bytes_to_ids(raw: np.ndarray) -> List[_uuid.UUID]:
 
 class LSHIndex:
     """lsh.rs:145-148.  `metric` fixes the distance the device index scores with (the reference passes the
-    metric to search(); a device index is built for one of Cosine / L2Squared / L2)."""
+    metric to search(); a device index is built for ONE metric of distance.rs -- the fused leaf-tile scan serves
+    Cosine / L2Squared / L2, the ten scalar metrics go through the gather path)."""
 
     def __init__(self, dim: int, options: Optional[LSHIndexOptions] = None, metric: Optional[_DeviceMetric] = None,
                  device: int = 0, seed: int = 0, shard_rank: int = 0, shard_count: int = 1):
@@ -59,11 +60,11 @@ class LSHIndex:
         self.options = options or LSHIndexOptions()
         self.metric = metric or CosineDistance()
         if not isinstance(self.metric, _DeviceMetric):
-            raise TypeError("the device index supports CosineDistance, L2SquaredDistance and L2Distance only")
+            raise TypeError("metric must be one of the zebra_b200.distance metric objects")
         self.device = device
         self.metric.device = device
         o = _ffi.Options()
-        o.dim, o.metric = self.dim, self.metric.METRIC
+        o.dim, o.metric, o.metric_power = self.dim, self.metric.METRIC, self.metric.power
         o.max_node_size, o.num_trees = self.options.max_node_size, self.options.num_trees
         o.device, o.seed = device, seed
         o.shard_rank, o.shard_count = shard_rank, shard_count

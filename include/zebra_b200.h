@@ -100,6 +100,8 @@ int zb_device_count(int* out_count);
 /* LSHIndex::new (lsh.rs:162-167).  Creates an empty index on options->device. */
 int zb_index_create(const zb_options* options, zb_index** out_index);
 int zb_index_destroy(zb_index* index);
+/* The options the index was created with. */
+int zb_index_options(zb_index* index, zb_options* out);
 
 /* LSHIndex::add (lsh.rs:440-466; build_index :411-429 when no tree exists yet, insert :350-382 otherwise).
  * rows: n*dim f32.  ids16: n*16 bytes or NULL (library mints UUIDv7).  out_ids16 / out_ordinals: optional.
@@ -161,6 +163,70 @@ int zb_index_export_forest(zb_index* index, int32_t* nodes, int32_t* roots, floa
 int zb_index_load_forest(zb_index* index, uint64_t n, const float* rows, const uint8_t* ids16,
                          const int64_t* sizes4, const int32_t* nodes, const int32_t* roots, const float* coef,
                          const float* cst, const int64_t* leaf_off, const uint64_t* members);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Interchange with the reference's stored values.  The reference keeps two fjall partitions
+ * (lsh.rs:63-85): `embeddings` (key = 16 id bytes, value = bincode(legacy) of Embedding<N> = dim raw LE f32, lsh.rs:91-97)
+ * and `trees` (key = 16 tree-id bytes, value = bincode(legacy) of Node<N>, lsh.rs:45-60 and :99-105), plus the `.zebra`
+ * file = bincode(legacy) of DatabaseInner (core.rs:19-29, :183-190).  The host reads / writes the key-value engine (it
+ * owns the fjall crate); these entry points take and produce the VALUES, so no bincode runs on the host side.
+ *   Node::Inner = u32 0 | dim f32 coefficients | f32 constant | left (below) | right (above)
+ *   Node::Leaf  = u32 1 | u64 count | count x (u64 16 | 16 id bytes)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Pure codecs (no device needed).  Flat form: nodes = n_nodes x {plane, left, right, leaf} as in
+ * zb_index_export_forest, numbered in preorder (node, left subtree, right subtree); leaf_off = n_leaves + 1 offsets
+ * into member_ids16 (16 bytes per member); sizes4 = {n_nodes, n_planes, n_leaves, n_members}.
+ * zb_tree_blob_decode: call once with the output arrays NULL to get sizes4, then again to fill them.  Malformed,
+ * truncated or over-long input returns ZB_ERR_INVALID. */
+int zb_tree_blob_decode(uint32_t dim, const uint8_t* blob, uint64_t bytes, int64_t* sizes4, int32_t* nodes, float* coef,
+                        float* cst, int64_t* leaf_off, uint8_t* member_ids16);
+/* Encodes the subtree under `root` of a flat forest (plane / leaf numbers index coef, cst, leaf_off as given).
+ * out may be NULL (size query); *out_bytes = blob size. */
+int zb_tree_blob_encode(uint32_t dim, int64_t n_nodes, const int32_t* nodes, int32_t root, const float* coef,
+                        const float* cst, const int64_t* leaf_off, const uint8_t* member_ids16, uint8_t* out,
+                        uint64_t cap, uint64_t* out_bytes);
+/* `.zebra` file: uuid (u64 16 | 16 bytes) | model (unit struct, 0 bytes) | metric (0 bytes; Minkowski / p-norm: i32
+ * power) | max_node_size u64 | num_trees u64.  metric = the zb_metric the Database type was instantiated with. */
+int zb_zebra_file_encode(const uint8_t* uuid16, uint32_t metric, int32_t power, uint64_t max_node_size,
+                         uint64_t num_trees, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
+int zb_zebra_file_decode(const uint8_t* data, uint64_t bytes, uint32_t metric, uint8_t* out_uuid16, int32_t* out_power,
+                         uint64_t* out_max_node_size, uint64_t* out_num_trees);
+
+typedef struct zb_import_report {
+    uint64_t rows_loaded;   /* rows now in the index (ordinals 0.. in id order) */
+    uint64_t missing_ids;   /* leaf entries whose id has no embedding: vectors the reference removed (quirk Q5); skipped */
+    uint64_t orphan_rows;   /* embeddings that some tree does not hold (lost updates of lsh.rs:445-462, Q11); NOT loaded:
+                               re-insert them with zb_index_add so that every tree gets them */
+    uint64_t nodes, planes, leaves;
+    uint32_t max_depth;
+    uint32_t reserved[3];
+} zb_import_report;
+/* A whole store -> the flat forest zb_index_load_forest takes (pure: no device).  Ordinal o is input row
+ * row_order[o]; ordinals follow id order (the key order of the reference's store, so ties keep breaking by id); rows
+ * some tree does not hold are left out and listed in orphan_rows (input row indices); leaf entries without an
+ * embedding are dropped and counted.  zb_flat_store_view lends pointers that live until zb_flat_store_free:
+ * sizes4 = {n_nodes, n_planes, n_leaves, n_members}; row_order has report.rows_loaded entries, orphan_rows
+ * report.orphan_rows. */
+typedef struct zb_flat_store zb_flat_store;
+int zb_store_flatten(uint32_t dim, uint64_t n, const uint8_t* ids16, uint32_t n_trees, const uint8_t* const* tree_blobs,
+                     const uint64_t* tree_blob_bytes, zb_flat_store** out, zb_import_report* report);
+int zb_flat_store_view(const zb_flat_store* store, int64_t* sizes4, const int32_t** nodes, const int32_t** roots,
+                       const float** coef, const float** cst, const int64_t** leaf_off, const uint64_t** members,
+                       const uint32_t** row_order, const uint32_t** orphan_rows);
+int zb_flat_store_free(zb_flat_store* store);
+/* Replaces the index content with a reference store: n (id, embedding) pairs and the values of the `trees`
+ * partition (n_trees must equal the index's num_trees).  Ordinals are assigned in id order (the key order of the
+ * reference's store), so ties keep breaking by id.  out_orphan_ids16 (optional) receives the first orphan_cap orphan
+ * ids.  Sharded index: every rank passes the same data. */
+int zb_index_import_store(zb_index* index, uint64_t n, const uint8_t* ids16, const float* rows, uint32_t n_trees,
+                          const uint8_t* const* tree_blobs, const uint64_t* tree_blob_bytes, zb_import_report* report,
+                          uint8_t* out_orphan_ids16, uint64_t orphan_cap);
+/* The store back out (unsharded index).  Rows [first_ordinal, first_ordinal + n): embedding value, id, live flag
+ * (0 = removed: the reference would have deleted the key). */
+int zb_index_export_rows(zb_index* index, uint64_t first_ordinal, uint64_t n, float* out_rows, uint8_t* out_ids16,
+                         uint8_t* out_live);
+/* Tree `tree` as the reference's blob; removed rows are left out of the leaves.  out may be NULL. */
+int zb_index_export_tree_blob(zb_index* index, uint32_t tree, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
 
 int zb_index_stats(zb_index* index, zb_stats* out);
 /* The CUDA stream (cudaStream_t) every kernel of this index is launched on -- for callers that time the

@@ -1,0 +1,288 @@
+"""The reference's stored values, CPU side: the C-ABI codecs of libzebra_b200 (pure host functions,
+no device) against hand-written byte strings and against the independent restatement in oracle/zb_bincode.py.
+
+Formats: bincode 2 `config::legacy()` of Node<N> (/root/reference/src/database/index/lsh.rs:45-60, :99-105),
+Embedding<N> (:91-97, src/lib.rs:16-18) and DatabaseInner (src/database/core.rs:19-29, :183-190).  PARITY UNPINNED: the
+byte strings below are derived by hand from the published bincode / serde / uuid formats, not from a reference run.
+"""
+import ctypes as C
+import struct
+import uuid
+
+import numpy as np
+import pytest
+
+from oracle import zb_bincode as zbc
+from oracle import zb_oracle as zo
+
+F32 = np.float32
+A = uuid.UUID("00112233-4455-6677-8899-aabbccddeeff")
+B = uuid.UUID(int=7)
+
+# Inner(coefficients [1.0, -2.0], constant 0.5, left = Leaf([A, B]), right = Leaf([])) for N = 2, written out by hand
+GOLDEN_TREE = bytes.fromhex(
+    "00000000"                                   # u32 variant 0 = Node::Inner
+    "0000803f" "000000c0"                        # coefficients: 1.0f32, -2.0f32 (no length: serde_with [_; N])
+    "0000003f"                                   # constant 0.5f32
+    "01000000" "0200000000000000"                # left_node: variant 1 = Leaf, Vec<Uuid> length 2 (u64)
+    "1000000000000000" "00112233445566778899aabbccddeeff"   # Uuid = byte string: u64 16 + bytes
+    "1000000000000000" "00000000000000000000000000000007"
+    "01000000" "0000000000000000"                # right_node: empty leaf
+)
+# DatabaseInner { uuid: A, model: unit, metric: unit, index_options: { max_node_size: 5, num_trees: 15 } }
+GOLDEN_ZEBRA = bytes.fromhex("1000000000000000" "00112233445566778899aabbccddeeff" "0500000000000000" "0f00000000000000")
+# the same with metric = MinkowskiDistance { power: 3 } (distance.rs:162-165)
+GOLDEN_ZEBRA_MINKOWSKI = bytes.fromhex("1000000000000000" "00112233445566778899aabbccddeeff" "03000000"
+                                       "0500000000000000" "0f00000000000000")
+
+
+def ix():
+    from zebra_b200 import interchange
+
+    return interchange
+
+
+def test_golden_tree_bytes_both_codecs():
+    node = ("inner", np.array([1.0, -2.0], F32), 0.5, ("leaf", [A, B]), ("leaf", []))
+    assert zbc.encode_node(node) == GOLDEN_TREE
+    assert zbc.nodes_equal(zbc.decode_node(GOLDEN_TREE, 2), node)
+    nodes, coef, cst, leaf_off, ids = ix().tree_blob_decode(2, GOLDEN_TREE)
+    assert nodes.tolist() == [[0, 1, 2, -1], [-1, -1, -1, 0], [-1, -1, -1, 1]]       # preorder: node, left, right
+    assert coef.tolist() == [[1.0, -2.0]] and cst.tolist() == [0.5]
+    assert leaf_off.tolist() == [0, 2, 2]
+    assert [uuid.UUID(bytes=r.tobytes()) for r in ids] == [A, B]
+    assert ix().tree_blob_encode(2, nodes, 0, coef, cst, leaf_off, ids) == GOLDEN_TREE
+    # a root leaf (what the reference stores before the first split)
+    leaf = struct.pack("<IQ", 1, 1) + struct.pack("<Q", 16) + A.bytes
+    nodes, coef, cst, leaf_off, ids = ix().tree_blob_decode(7, leaf)
+    assert nodes.tolist() == [[-1, -1, -1, 0]] and coef.shape == (0, 7) and leaf_off.tolist() == [0, 1]
+    assert ix().tree_blob_encode(7, nodes, 0, coef, cst, leaf_off, ids) == leaf
+
+
+def test_golden_zebra_file():
+    import zebra_b200 as z
+
+    assert zbc.encode_database_inner(A, 5, 15) == GOLDEN_ZEBRA
+    assert zbc.encode_database_inner(A, 5, 15, metric_power=3) == GOLDEN_ZEBRA_MINKOWSKI
+    assert ix().zebra_file_encode(A, z.CosineDistance(), 5, 15) == GOLDEN_ZEBRA
+    assert ix().zebra_file_encode(A, z.L2SquaredDistance(), 5, 15) == GOLDEN_ZEBRA
+    assert ix().zebra_file_encode(A, z.MinkowskiDistance(3), 5, 15) == GOLDEN_ZEBRA_MINKOWSKI
+    assert ix().zebra_file_decode(GOLDEN_ZEBRA, z.CosineDistance()) == (A, 0, 5, 15)
+    assert ix().zebra_file_decode(GOLDEN_ZEBRA_MINKOWSKI, z.PNormDistance(0)) == (A, 3, 5, 15)
+    with pytest.raises(z.ZebraError):
+        ix().zebra_file_decode(GOLDEN_ZEBRA, z.MinkowskiDistance(1))       # 40 bytes cannot hold a power
+    with pytest.raises(z.ZebraError):
+        ix().zebra_file_decode(GOLDEN_ZEBRA[:-1], z.CosineDistance())
+    bad = bytearray(GOLDEN_ZEBRA); bad[0] = 15
+    with pytest.raises(z.ZebraError):
+        ix().zebra_file_decode(bytes(bad), z.CosineDistance())
+
+
+def test_embedding_value_is_the_raw_row():
+    x = np.array([1.5, -0.0, 3e-41], F32)
+    assert zbc.encode_embedding(x) == x.tobytes() == bytes.fromhex("0000c03f" "00000080") + x[2:].tobytes()
+    assert np.array_equal(zbc.decode_embedding(x.tobytes(), 3).view(np.uint32), x.view(np.uint32))
+
+
+@pytest.mark.parametrize("dim,mns,trees", [(16, 5, 4), (20, 64, 2), (3, 2, 3)])
+def test_oracle_forest_round_trips_through_both_codecs(dim, mns, trees):
+    rng = np.random.default_rng(dim)
+    rows = rng.standard_normal((700, dim)).astype(F32)
+    orc = zo.OracleIndex(dim, zo.L2SQ, mns, trees, seed=3)
+    orc.add(rows)
+    forest = orc.export_forest()
+    ids = [uuid.UUID(int=int(v)) for v in rng.integers(1, 2**62, 700)]
+    want = zbc.forest_to_nodes(forest, ids)
+    idb = np.frombuffer(b"".join(ids[int(o)].bytes for o in forest.members), dtype=np.uint8).reshape(-1, 16)
+    for t in range(trees):
+        blob = zbc.encode_node(want[t])
+        # product encoder on the flat forest == oracle encoder on the recursive form
+        assert ix().tree_blob_encode(dim, forest.nodes, int(forest.roots[t]), forest.coef, forest.cst, forest.leaf_off, idb) == blob
+        # product decoder -> flat arrays of this tree alone -> recursive form == the original
+        nodes, coef, cst, leaf_off, mids = ix().tree_blob_decode(dim, blob)
+
+        class F:
+            pass
+
+        f = F()
+        f.nodes, f.coef, f.cst, f.leaf_off, f.roots = nodes, coef.reshape(-1, dim), cst, leaf_off, np.array([0])
+        by_id = {u.bytes: i for i, u in enumerate(ids)}
+        f.members = np.array([by_id[r.tobytes()] for r in mids], dtype=np.uint64)
+        assert zbc.nodes_equal(zbc.forest_to_nodes(f, ids)[0], want[t])
+        # node numbering is preorder: children always come after their parent, left subtree first
+        inner = nodes[:, 0] >= 0
+        assert np.all(nodes[inner, 1] == np.nonzero(inner)[0] + 1)
+
+
+def test_malformed_blobs_are_rejected_not_trusted():
+    import zebra_b200 as z
+
+    for cut in range(len(GOLDEN_TREE)):                      # every truncation
+        with pytest.raises(z.ZebraError) as ei:
+            ix().tree_blob_decode(2, GOLDEN_TREE[:cut])
+        assert ei.value.code == -1
+    with pytest.raises(z.ZebraError, match="trailing"):
+        ix().tree_blob_decode(2, GOLDEN_TREE + b"\0")
+    with pytest.raises(z.ZebraError, match="variant"):
+        ix().tree_blob_decode(2, struct.pack("<I", 2) + GOLDEN_TREE[4:])
+    bad = bytearray(GOLDEN_TREE); bad[28] = 17               # Uuid length 17
+    with pytest.raises(z.ZebraError, match="Uuid"):
+        ix().tree_blob_decode(2, bytes(bad))
+    with pytest.raises(z.ZebraError, match="does not fit"):   # a leaf claiming 2^60 ids must not allocate
+        ix().tree_blob_decode(2, struct.pack("<IQ", 1, 1 << 60))
+    with pytest.raises(z.ZebraError):                        # wrong N: the blob no longer parses to its end
+        ix().tree_blob_decode(3, GOLDEN_TREE)
+    # encoder: cycles and dangling children
+    nodes = np.array([[0, 0, 0, -1]], np.int32)
+    with pytest.raises(z.ZebraError, match="cycle"):
+        ix().tree_blob_encode(2, nodes, 0, np.zeros((1, 2), F32), np.zeros(1, F32), np.zeros(1, np.int64), np.zeros((0, 16), np.uint8))
+    nodes = np.array([[0, 5, 6, -1]], np.int32)
+    with pytest.raises(z.ZebraError, match="out of range"):
+        ix().tree_blob_encode(2, nodes, 0, np.zeros((1, 2), F32), np.zeros(1, F32), np.zeros(1, np.int64), np.zeros((0, 16), np.uint8))
+
+
+def test_degenerate_chain_of_20000_levels_parses_iteratively():
+    """A path-shaped tree (every right child a leaf) must not overflow the C stack of the decoder / encoder."""
+    depth, dim = 20000, 1
+    inner = struct.pack("<I", 0) + struct.pack("<ff", 1.0, 0.0)
+    empty = struct.pack("<IQ", 1, 0)
+    blob = inner * depth + empty + empty * depth       # ... Inner(Inner(Inner(leaf, leaf), leaf), leaf)
+    nodes, coef, cst, leaf_off, ids = ix().tree_blob_decode(dim, blob)
+    assert nodes.shape[0] == 2 * depth + 1 and coef.shape[0] == depth and leaf_off.size == depth + 2
+    assert nodes[0].tolist() == [0, 1, 2 * depth, -1]            # root: left = next node, right = the last leaf
+    assert ix().tree_blob_encode(dim, nodes, 0, coef, cst, leaf_off, ids) == blob
+
+
+def test_store_dump_round_trip(tmp_path):
+    rng = np.random.default_rng(1)
+    rows = rng.standard_normal((300, 24)).astype(F32)
+    ids = rng.integers(0, 256, (300, 16)).astype(np.uint8)
+    trees = [(ix().tree_key(t), GOLDEN_TREE * (t + 1)) for t in range(3)]
+    p = str(tmp_path / "db.store")
+    ix().write_store(p, 24, GOLDEN_ZEBRA, trees, ids, rows)
+    dim, zebra, trees2, ids2, rows2 = ix().read_store(p)
+    assert dim == 24 and zebra == GOLDEN_ZEBRA and trees2 == trees
+    assert np.array_equal(ids2, ids) and np.array_equal(rows2.view(np.uint32), rows.view(np.uint32))
+    assert len({k for k, _ in trees}) == 3 and all(uuid.UUID(bytes=k).version == 7 for k, _ in trees)
+    raw = open(p, "rb").read()
+    # the embeddings partition is a flat array of {key, u64 4N, value = the raw row}: what lsh.rs:91-97 stores
+    tail = raw[-(16 + 8 + 96):]
+    assert tail[:16] == ids[-1].tobytes() and struct.unpack("<Q", tail[16:24])[0] == 96 and tail[24:] == rows[-1].tobytes()
+    open(p, "wb").write(raw[:-5])
+    with pytest.raises(ValueError):
+        ix().read_store(p)
+    open(p, "wb").write(b"NOTASTORE" + raw[9:])
+    with pytest.raises(ValueError):
+        ix().read_store(p)
+
+
+def test_import_needs_a_device_and_says_so():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from zebra_b200 import _ffi
+
+    rep = _ffi.ImportReport()
+    assert C.sizeof(_ffi.ImportReport) == 64
+    rc = _ffi.lib().zb_index_import_store(None, 0, None, None, 1, None, None, C.byref(rep), None, 0)
+    assert rc == -1                                           # no index without a GPU: argument check only
+
+
+# ------------------------------------------------------------------------------------------ a whole store, flattened
+def drop_member(forest, leaves, ordinal):
+    """Flat forest without `ordinal` in the leaves listed (None = every leaf)."""
+    keep = np.ones(forest.members.size, dtype=bool)
+    for l in range(forest.leaf_off.size - 1):
+        if leaves is None or l in leaves:
+            seg = slice(int(forest.leaf_off[l]), int(forest.leaf_off[l + 1]))
+            keep[seg] &= forest.members[seg] != ordinal
+    counts = [int(keep[int(forest.leaf_off[l]):int(forest.leaf_off[l + 1])].sum()) for l in range(forest.leaf_off.size - 1)]
+    return zo.Forest(forest.nodes, forest.roots, forest.coef, forest.cst, np.concatenate([[0], np.cumsum(counts)]).astype(np.int64),
+                     forest.members[keep])
+
+
+def leaves_of_tree(forest, t):
+    out, stack = set(), [int(forest.roots[t])]
+    while stack:
+        plane, left, right, leaf = (int(v) for v in forest.nodes[stack.pop()])
+        if plane >= 0:
+            stack += [left, right]
+        else:
+            out.add(leaf)
+    return out
+
+
+def tampered_store(rng, n, dim, T, X, mns=8, metric=zo.L2SQ, seed=5):
+    """An oracle-built store with random (non-v7) ids, two leaf entries whose embedding is gone (vectors the reference
+    removed, quirk Q5) and one embedding (row X) missing from tree 2 (a lost update, quirk Q11).
+    -> rows, ids, forest, blobs, order (the rows kept, in id order), clean (the forest without X, members = ranks)."""
+    c = rng.standard_normal((32, dim)).astype(F32)
+    rows = (c[rng.integers(0, 32, n)] + 0.25 * rng.standard_normal((n, dim))).astype(F32)
+    orc = zo.OracleIndex(dim, metric, mns, T, seed=seed)
+    orc.add(rows)
+    forest = orc.export_forest()
+    ids = [uuid.UUID(bytes=rng.integers(0, 256, 16, dtype=np.uint8).tobytes()) for _ in range(n)]
+    nodes = zbc.forest_to_nodes(drop_member(forest, leaves_of_tree(forest, 2), X), ids)
+    for t, g in zip((0, 3), (uuid.UUID(int=1), uuid.UUID(int=2))):
+        nd = nodes[t]
+        while nd[0] == "inner":
+            nd = nd[3]
+        nd[1].append(g)                                   # an id without an embedding, in the leftmost leaf
+    blobs = [zbc.encode_node(nd) for nd in nodes]
+    order = sorted((i for i in range(n) if i != X), key=lambda i: ids[i].bytes)
+    rank = np.full(n, -1, dtype=np.int64)
+    rank[order] = np.arange(n - 1)
+    clean = drop_member(forest, None, X)
+    clean = zo.Forest(clean.nodes, clean.roots, clean.coef, clean.cst, clean.leaf_off,
+                      rank[clean.members.astype(np.int64)].astype(np.uint64))
+    return rows, ids, forest, blobs, order, clean
+
+
+def test_store_flatten_orders_by_id_drops_ghosts_and_orphans():
+    rng = np.random.default_rng(17)
+    n, dim, T, X = 1500, 24, 5, 777
+    rows, ids, forest, blobs, order, clean = tampered_store(rng, n, dim, T, X)
+    perm = rng.permutation(n)                              # the rows arrive in arbitrary order
+    idb = np.frombuffer(b"".join(ids[i].bytes for i in perm), dtype=np.uint8)
+    rep, flat, row_order, orphans = ix().store_flatten(dim, idb, blobs)
+    assert rep["rows_loaded"] == n - 1 and rep["missing_ids"] == 2 and rep["orphan_rows"] == 1
+    assert rep["nodes"] == forest.nodes.shape[0] and rep["planes"] == forest.cst.size and rep["leaves"] == forest.leaf_off.size - 1
+    assert [int(perm[i]) for i in orphans] == [X]
+    assert [int(perm[i]) for i in row_order] == order      # ordinal o = the o-th smallest id among the rows kept
+    # the flat forest is the oracle's own numbering (preorder, trees in order) with members renumbered to ranks
+    assert np.array_equal(flat["nodes"], clean.nodes) and np.array_equal(flat["roots"], clean.roots)
+    assert np.array_equal(flat["coef"].view(np.uint32), clean.coef.reshape(-1, dim).view(np.uint32))
+    assert np.array_equal(flat["cst"].view(np.uint32), clean.cst.view(np.uint32))
+    assert np.array_equal(flat["leaf_off"], clean.leaf_off)
+    for l in range(clean.leaf_off.size - 1):               # member ORDER inside a leaf is storage detail
+        a, b = int(clean.leaf_off[l]), int(clean.leaf_off[l + 1])
+        assert sorted(flat["members"][a:b].tolist()) == sorted(clean.members[a:b].tolist())
+    # already sorted input and no tampering: identity order, nothing dropped
+    srt = sorted(range(n), key=lambda i: ids[i].bytes)
+    rk = np.empty(n, np.int64); rk[srt] = np.arange(n)
+    whole = [zbc.encode_node(nd) for nd in zbc.forest_to_nodes(forest, ids)]
+    rep, flat, row_order, orphans = ix().store_flatten(dim, np.frombuffer(b"".join(ids[i].bytes for i in srt), dtype=np.uint8), whole)
+    assert rep["rows_loaded"] == n and rep["missing_ids"] == 0 and orphans.size == 0 and row_order.tolist() == list(range(n))
+    assert np.array_equal(np.sort(flat["members"][: int(forest.leaf_off[1])]), np.sort(rk[forest.members[: int(forest.leaf_off[1])].astype(np.int64)]))
+
+
+def test_store_flatten_rejects_inconsistent_stores():
+    import zebra_b200 as z
+
+    ids = [uuid.UUID(int=10 + i) for i in range(4)]
+    idb = lambda lst: np.frombuffer(b"".join(u.bytes for u in lst), dtype=np.uint8)
+    leaf = lambda members: zbc.encode_node(("leaf", members))
+    with pytest.raises(z.ZebraError, match="twice"):
+        ix().store_flatten(8, idb(ids), [leaf(ids), leaf(ids + [ids[0]])])          # an id twice in one tree
+    with pytest.raises(z.ZebraError, match="twice"):
+        ix().store_flatten(8, idb(ids + [ids[1]]), [leaf(ids), leaf(ids)])           # duplicate key
+    with pytest.raises(z.ZebraError):
+        ix().store_flatten(8, idb(ids), [leaf(ids), leaf(ids)[:-3]])                 # truncated value
+    rep, flat, row_order, orphans = ix().store_flatten(8, idb(ids), [leaf(ids), leaf(ids[::-1])])   # root leaves
+    assert rep["rows_loaded"] == 4 and rep["nodes"] == 2 and rep["max_depth"] == 0 and flat["roots"].tolist() == [0, 1]
+    assert flat["members"].tolist() == [0, 1, 2, 3, 3, 2, 1, 0]
+    rep, flat, row_order, orphans = ix().store_flatten(8, idb([]), [leaf([]), leaf([ids[0]])])      # empty store, a stale id
+    assert rep["rows_loaded"] == 0 and rep["missing_ids"] == 1 and flat["members"].size == 0
+    rep, _, row_order, orphans = ix().store_flatten(8, idb(ids), [leaf(ids[:3]), leaf(ids[1:])])     # two half-indexed rows
+    assert rep["orphan_rows"] == 2 and orphans.tolist() == [0, 3] and row_order.tolist() == [1, 2]

@@ -69,6 +69,22 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
+class ImportReport(C.Structure):
+    _fields_ = [
+        ("rows_loaded", C.c_uint64),
+        ("missing_ids", C.c_uint64),
+        ("orphan_rows", C.c_uint64),
+        ("nodes", C.c_uint64),
+        ("planes", C.c_uint64),
+        ("leaves", C.c_uint64),
+        ("max_depth", C.c_uint32),
+        ("reserved", C.c_uint32 * 3),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
 # every symbol include/zebra_b200.h declares: name -> (restype, argtypes)
 _vp, _u64, _u32, _i32, _i64 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int64
 SYMBOLS = {
@@ -77,6 +93,7 @@ SYMBOLS = {
     "zb_device_count": (C.c_int, [_vp]),
     "zb_index_create": (C.c_int, [C.POINTER(Options), C.POINTER(_vp)]),
     "zb_index_destroy": (C.c_int, [_vp]),
+    "zb_index_options": (C.c_int, [_vp, C.POINTER(Options)]),
     "zb_index_add": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "zb_index_add_device": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "zb_index_add_owned_device": (C.c_int, [_vp, _u64, _vp, _vp, _u64]),
@@ -93,6 +110,16 @@ SYMBOLS = {
     "zb_index_forest_sizes": (C.c_int, [_vp, _vp]),
     "zb_index_export_forest": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "zb_index_load_forest": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "zb_tree_blob_decode": (C.c_int, [_u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "zb_tree_blob_encode": (C.c_int, [_u32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "zb_zebra_file_encode": (C.c_int, [_vp, _u32, _i32, _u64, _u64, _vp, _u64, C.POINTER(_u64)]),
+    "zb_zebra_file_decode": (C.c_int, [_vp, _u64, _u32, _vp, C.POINTER(_i32), C.POINTER(_u64), C.POINTER(_u64)]),
+    "zb_store_flatten": (C.c_int, [_u32, _u64, _vp, _u32, _vp, _vp, C.POINTER(_vp), C.POINTER(ImportReport)]),
+    "zb_flat_store_view": (C.c_int, [_vp] + [_vp] * 9),
+    "zb_flat_store_free": (C.c_int, [_vp]),
+    "zb_index_import_store": (C.c_int, [_vp, _u64, _vp, _vp, _u32, _vp, _vp, C.POINTER(ImportReport), _vp, _u64]),
+    "zb_index_export_rows": (C.c_int, [_vp, _u64, _u64, _vp, _vp, _vp]),
+    "zb_index_export_tree_blob": (C.c_int, [_vp, _u32, _vp, _u64, C.POINTER(_u64)]),
     "zb_index_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "zb_index_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "zb_index_set_param": (C.c_int, [_vp, C.c_char_p, _i64]),

@@ -39,6 +39,26 @@ inline std::string fmt(const char* f, ...) {
         if (!(cond)) throw zb::Error((code), zb::fmt(__VA_ARGS__)); \
     } while (0)
 
+extern thread_local std::string t_last_error;  // message of the calling thread's last failure (zb_last_error)
+
+// every extern "C" entry point: exceptions become a zb_status + message
+#define ZB_API_BEGIN try {
+#define ZB_API_END                                   \
+    return ZB_OK;                                    \
+    }                                                \
+    catch (const zb::Error& e) {                     \
+        zb::t_last_error = e.what();                 \
+        return e.code;                               \
+    }                                                \
+    catch (const std::bad_alloc&) {                  \
+        zb::t_last_error = "host allocation failed"; \
+        return ZB_ERR_OOM;                           \
+    }                                                \
+    catch (const std::exception& e) {                \
+        zb::t_last_error = e.what();                 \
+        return ZB_ERR_INVALID;                       \
+    }
+
 extern size_t g_device_bytes;  // not thread-exact; per-process accounting for zb_stats
 
 // Device memory comes from the device's stream-ordered pool with the release threshold lifted, so that the buffers of

@@ -16,7 +16,7 @@
 
 namespace zb {
 size_t g_device_bytes = 0;
-static thread_local std::string t_last_error;
+thread_local std::string t_last_error;  // declared in zb_host.h (zb_interchange.cpp reports through it too)
 
 struct Id16 {
     uint64_t hi, lo;
@@ -1017,23 +1017,6 @@ static void build_export_table(zb_index* ix, std::vector<int>* order_nodes, std:
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
-#define ZB_API_BEGIN try {
-#define ZB_API_END                                   \
-    return ZB_OK;                                    \
-    }                                                \
-    catch (const zb::Error& e) {                     \
-        zb::t_last_error = e.what();                 \
-        return e.code;                               \
-    }                                                \
-    catch (const std::bad_alloc&) {                  \
-        zb::t_last_error = "host allocation failed"; \
-        return ZB_ERR_OOM;                           \
-    }                                                \
-    catch (const std::exception& e) {                \
-        zb::t_last_error = e.what();                 \
-        return ZB_ERR_INVALID;                       \
-    }
-
 extern "C" {
 
 const char* zb_last_error(void) { return zb::t_last_error.c_str(); }
@@ -1686,6 +1669,36 @@ int zb_index_load_forest(zb_index* ix, uint64_t n, const float* rows, const uint
     ix->upload_structure();
     ix->recount_live();
     ix->sync();
+    ZB_API_END
+}
+
+int zb_index_options(zb_index* ix, zb_options* out) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && out, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *out = ix->opt;
+    ZB_API_END
+}
+
+int zb_index_export_rows(zb_index* ix, uint64_t first_ordinal, uint64_t n, float* out_rows, uint8_t* out_ids16,
+                         uint8_t* out_live) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix, ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->use_device();
+    ZB_REQUIRE(ix->G <= 1, ZB_ERR_STATE, "zb_index_export_rows needs an unsharded index (a shard holds 1/G of the rows)");
+    ZB_REQUIRE(first_ordinal <= ix->total_rows && n <= ix->total_rows - first_ordinal, ZB_ERR_INVALID,
+               "rows [%llu, +%llu) out of range (%llu rows)", (unsigned long long)first_ordinal, (unsigned long long)n,
+               (unsigned long long)ix->total_rows);
+    if (out_rows && n) {  // unsharded: slot == ordinal
+        ZB_CUDA(cudaMemcpy2DAsync(out_rows, (size_t)ix->dim * 4, ix->rows.p + first_ordinal * (u64)ix->dimp, (size_t)ix->dimp * 4,
+                                  (size_t)ix->dim * 4, n, cudaMemcpyDeviceToHost, ix->stream));
+        ix->sync();
+    }
+    for (u64 i = 0; i < n; ++i) {
+        if (out_ids16) ix->id_of(first_ordinal + i, out_ids16 + 16 * i);
+        if (out_live) out_live[i] = ix->h_tomb[first_ordinal + i] ? 0 : 1;
+    }
     ZB_API_END
 }
 

@@ -1,8 +1,9 @@
 """Database: the host mirror of /root/reference/src/database/core.rs:55-381 for the three index call sites
 (insert_records :245-254, remove :205-213, query_vectors :290-313).
 
-The document store of the reference (lz4 files, core.rs:322-380) and the `.zebra` file (core.rs:183-190) are
-host I/O outside the hot path; documents are kept in an in-memory map here so the API round-trips.
+The document store of the reference (lz4 files, core.rs:322-380) is host I/O outside the hot path; documents are kept
+in an in-memory map here so the API round-trips.  `save_database` / `open` write and read the reference's `.zebra` file
+(core.rs:92-104, :183-190) next to a dump of the index's two key-value partitions (interchange.py).
 """
 from __future__ import annotations
 
@@ -35,13 +36,42 @@ class Database:
         self.uuid = _uuid.uuid4()
         self.index = LSHIndex(dim, self.index_options, self.metric, device=device, seed=seed)
         self._documents: Dict[_uuid.UUID, bytes] = {}
+        self.path = ""
 
     @classmethod
     def new(cls, dim: int, index_options: LSHIndexOptions, **kw) -> "Database":  # core.rs:110
         return cls(dim, index_options=index_options, **kw)
 
-    def save_database(self, path: Optional[str] = None) -> None:  # core.rs:183-190 (host I/O, out of scope)
-        self.index.save()
+    def default_database_path(self) -> str:  # core.rs:80-82
+        return f"{self.uuid.hex}.zebra"
+
+    def save_database(self, path: Optional[str] = None) -> None:  # core.rs:183-190
+        """Writes `path` = bincode(legacy) of DatabaseInner, byte for byte what the reference writes, and
+        `path + ".store"` = the index's `trees` and `embeddings` partitions (values as the reference stores them)."""
+        from . import interchange
+
+        path = path or self.path or self.default_database_path()
+        zebra = interchange.zebra_file_encode(self.uuid, self.metric, self.index_options.max_node_size,
+                                              self.index_options.num_trees)
+        with open(path, "wb") as f:
+            f.write(zebra)
+        self.index.save_store(path + ".store", zebra)
+        self.path = path
+
+    @classmethod
+    def open(cls, path: str, dim: int, metric: Optional[_DeviceMetric] = None, **kw) -> "Database":  # core.rs:92-104
+        """`dim` and `metric` are the reference's type parameters N and Met (the file does not carry them)."""
+        from . import interchange
+
+        metric = metric or CosineDistance()
+        with open(path, "rb") as f:
+            db_uuid, power, mns, nt = interchange.zebra_file_decode(f.read(), metric)
+        if hasattr(metric, "power"):
+            metric.power = power
+        db = cls(dim, metric, index_options=LSHIndexOptions(mns, nt), **kw)
+        db.uuid, db.path = db_uuid, path
+        db.index.load_store(path + ".store")
+        return db
 
     def clear_database(self) -> None:  # core.rs:194-198
         self.index.clear()

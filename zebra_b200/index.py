@@ -88,7 +88,8 @@ class LSHIndex:
             pass
 
     def save(self) -> None:
-        """lsh.rs:170-172: persistence is the host's storage engine, outside the device path."""
+        """lsh.rs:170-172 (fjall `persist`): the key-value engine is the host's; `save_store` / `export_tree_blobs` /
+        `export_rows` produce the values it would persist."""
 
     # ---------------------------------------------------------------- lsh.rs:440-466
     def add(self, embeddings, ids: Optional[Sequence] = None) -> List[_uuid.UUID]:
@@ -231,6 +232,71 @@ class LSHIndex:
                                                    idb.ctypes.data if idb is not None else None, sz.ctypes.data,
                                                    f.nodes.ctypes.data, f.roots.ctypes.data, f.coef.ctypes.data,
                                                    f.cst.ctypes.data, f.leaf_off.ctypes.data, f.members.ctypes.data))
+
+    # ---------------------------------------------------------------- the reference's stored values
+    def import_store(self, ids: Sequence, embeddings, tree_blobs: Sequence[bytes]) -> dict:
+        """Replace the index content with a reference store: the (key, value) pairs of the `embeddings` partition
+        (lsh.rs:91-97) and the values of the `trees` partition (lsh.rs:99-105).  Returns the import report plus
+        ``orphans`` (ids of embeddings some tree did not hold; they are NOT loaded -- re-insert them with add())."""
+        rows = np.ascontiguousarray(embeddings, dtype=np.float32).reshape(-1, self.dim)
+        idb = ids if isinstance(ids, np.ndarray) else _ids_to_bytes(ids)
+        idb = np.ascontiguousarray(idb, dtype=np.uint8).reshape(-1)
+        n = rows.shape[0]
+        if idb.size != 16 * n:
+            raise ValueError("ids must hold one 16-byte id per row")
+        bufs = [np.frombuffer(bytes(b), dtype=np.uint8) for b in tree_blobs]
+        ptrs = (C.c_void_p * max(1, len(bufs)))(*[b.ctypes.data for b in bufs])
+        sizes = np.array([b.size for b in bufs] or [0], dtype=np.uint64)
+        rep = _ffi.ImportReport()
+        orphans = np.zeros((max(1, n), 16), dtype=np.uint8)
+        _ffi.check(_ffi.lib().zb_index_import_store(self._h, n, idb.ctypes.data if n else None, rows.ctypes.data if n else None,
+                                                    len(bufs), ptrs, sizes.ctypes.data, C.byref(rep), orphans.ctypes.data, n))
+        out = rep.as_dict()
+        out["orphans"] = _bytes_to_ids(orphans[: int(rep.orphan_rows)])
+        return out
+
+    def export_rows(self, first_ordinal: int = 0, n: Optional[int] = None):
+        """(embeddings [n,dim] f32, ids [n,16] uint8, live [n] bool) of ordinals [first, first + n) -- unsharded index."""
+        if n is None:
+            n = int(self.stats()["total_rows"]) - first_ordinal
+        rows = np.zeros((n, self.dim), dtype=np.float32)
+        ids = np.zeros((n, 16), dtype=np.uint8)
+        live = np.zeros(n, dtype=np.uint8)
+        _ffi.check(_ffi.lib().zb_index_export_rows(self._h, first_ordinal, n, rows.ctypes.data, ids.ctypes.data, live.ctypes.data))
+        return rows, ids, live.astype(bool)
+
+    def export_tree_blobs(self) -> List[bytes]:
+        """Every tree as the reference's `trees` value (bincode(legacy) Node<N>); removed rows are left out of the leaves."""
+        out = []
+        for t in range(self.options.num_trees):
+            need = C.c_uint64()
+            _ffi.check(_ffi.lib().zb_index_export_tree_blob(self._h, t, None, 0, C.byref(need)))
+            buf = np.empty(int(need.value), dtype=np.uint8)
+            _ffi.check(_ffi.lib().zb_index_export_tree_blob(self._h, t, buf.ctypes.data, buf.size, C.byref(need)))
+            out.append(buf.tobytes())
+        return out
+
+    def save_store(self, path: str, zebra: bytes = b"") -> None:
+        """Dump both partitions (live rows only, as the reference deletes removed keys) into one file, see interchange.py."""
+        from . import interchange
+
+        rows, ids, live = self.export_rows()
+        blobs = self.export_tree_blobs() if not self.no_trees() else []
+        interchange.write_store(path, self.dim, zebra, [(interchange.tree_key(t), b) for t, b in enumerate(blobs)],
+                                ids[live], rows[live])
+
+    def load_store(self, path: str) -> dict:
+        from . import interchange
+
+        dim, _, trees, ids, rows = interchange.read_store(path)
+        if dim != self.dim:
+            raise ValueError(f"store holds {dim}-dimensional vectors, this index {self.dim}")
+        if not trees:
+            self.clear()
+            if rows.shape[0]:
+                self.add(rows, ids.reshape(-1, 16))
+            return {"rows_loaded": int(rows.shape[0]), "orphans": []}
+        return self.import_store(ids, rows, [b for _, b in trees])
 
     # ---------------------------------------------------------------- misc
     def stats(self) -> dict:

@@ -155,7 +155,7 @@ struct zb_index {
     ScanWorkspace scan_ws;
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1;
     zb_stats st{};
 
     ForestView view() const {
@@ -909,8 +909,15 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     }
 
     // ---- generic path for the remaining visits (pair offsets were scanned with the plan) ----
-    launch_score_pairs(fs, (int)ix->opt.metric, (int)ix->opt.metric_power, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, total_pairs,
-                       ix->pair_key.p, s);
+    // scalar metrics (sequential fold per pair): visits grouped by leaf, one thread folds a row against the <= 8 queries of a
+    // tile, keys land in the same pair_key layout (zb_scan.cu, seq_tile_scan); knob seq_tile = 0 keeps one thread per pair
+    ix->scan_ws.seq_launched = false;
+    if (ix->opt.metric > ZB_METRIC_L2 && ix->p_seq_tile && total_pairs && seq_tile_scan_supported(ix->dimp))
+        seq_tile_scan(ix->scan_ws, fs, ix->opt.metric, (int)ix->opt.metric_power, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p,
+                      ix->pair_key.p, (u32)ix->h_leaf_off.size(), s);
+    if (!ix->scan_ws.seq_launched)
+        launch_score_pairs(fs, (int)ix->opt.metric, (int)ix->opt.metric_power, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p,
+                           total_pairs, ix->pair_key.p, s);
     ZB_CUDA(cudaEventRecord(ix->ev[2], s));
     ix->trace_mark("scan");
     if (total_pairs)
@@ -965,6 +972,8 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     float tile_ms = 0.f;
     u32 tiles = 0;
     tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved, &tile_ms, &tiles);
+    u64 seq_moved = 0;
+    if (ix->scan_ws.seq_launched) seq_tile_scan_stats(ix->scan_ws, s, &seq_moved, &tile_ms, &tiles);
     ix->st.last_ms_tile_kernel = tile_ms;
     ix->st.last_tiles = tiles;
     ix->sync();
@@ -979,8 +988,8 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->st.last_pairs = total_pairs + tile_pairs;
     ix->st.last_tile_visits = tile_visits;
     ix->st.last_tile_pairs = tile_pairs;
-    ix->st.last_moved_bytes = moved + total_pairs * (u64)ix->dim * 4;
-    ix->st.last_scan_launches = scan_launches + (total_pairs ? 1 : 0);
+    ix->st.last_moved_bytes = ix->scan_ws.seq_launched ? seq_moved : moved + total_pairs * (u64)ix->dim * 4;
+    ix->st.last_scan_launches = scan_launches + (total_pairs ? (ix->scan_ws.seq_launched ? 7 : 1) : 0);
     ix->st.last_total_launches += scan_launches + 5 + (sharded ? 1 : 0);
 }
 
@@ -1733,6 +1742,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "tile_queries") ix->p_tile_queries = value;
     else if (k == "use_tile_scan") ix->p_use_tile_scan = value;
     else if (k == "classify_variant") ix->p_classify_variant = value;  // 0: rows gathered through L1; 1: rows staged by TMA bulk copies
+    else if (k == "seq_tile") ix->p_seq_tile = value;          // scalar metrics: 1 = leaf-tile scan (default), 0 = one thread per pair
     else if (k == "hash_variant") ix->p_hash_variant = value;  // 0: quad per (row, tree), rows through L1; 1: row staged in shared memory
     else if (k == "visit_slots") {  // initial per-walker capacity of the visit plan (tests force the grow-and-replan path)
         ZB_REQUIRE(value >= 2 && value <= 65536, ZB_ERR_INVALID, "visit_slots out of range");

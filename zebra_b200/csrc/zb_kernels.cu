@@ -561,6 +561,37 @@ __global__ void __launch_bounds__(128) hash_kernel(ForestView f, const float* __
         if (leaves) leaves[w] = nd.w;
     }
 }
+// Tree-major variant: the same quad-per-(row, tree) descent, but quad i works on tree i / n, row i % n, so the CTAs in
+// flight at any moment (they are scheduled in index order) all walk ONE tree: the planes of its top levels (63 planes =
+// 189 KB for six levels at N = 768) stay resident in L1 instead of being evicted by three other trees' planes, and
+// only the deeper levels come from L2.  The row is read once per tree (L2 / HBM), which the plane traffic dwarfs.
+__global__ void __launch_bounds__(128) hash_tree_major_kernel(ForestView f, const float* __restrict__ rows, u64 n,
+                                                              u64* __restrict__ keys, u32* __restrict__ depths,
+                                                              int* __restrict__ leaves) {
+    const u64 i = (u64)blockIdx.x * 32ull + (threadIdx.x >> 2);
+    const int sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    if (i >= n * (u64)f.num_trees) return;
+    const int t = (int)(i / n);
+    const u64 r = i - (u64)t * n;
+    const float4* x = reinterpret_cast<const float4*>(rows + (size_t)r * f.dimp);
+    int4 nd = f.nodes[f.roots[t]];
+    u64 key = 0;
+    u32 depth = 0;
+    while (nd.x >= 0) {
+        float d = quad_dot(reinterpret_cast<const float4*>(f.coef + (size_t)nd.x * f.dimp), x, f.chunks, sub, mask);
+        bool ab = above_from_dot(d, f.cst[nd.x]);
+        key = (key << 1) | (ab ? 1ull : 0ull);
+        ++depth;
+        nd = f.nodes[ab ? nd.z : nd.y];
+    }
+    if (sub == 0) {
+        const u64 w = r * (u64)f.num_trees + t;
+        if (keys) keys[w] = key;
+        if (depths) depths[w] = depth;
+        if (leaves) leaves[w] = nd.w;
+    }
+}
 // Variant with the row staged in shared memory: a quad copies its row once (quad-private region, padded pitch so that the
 // two quads of a quarter-warp hit disjoint banks) and walks ALL trees with it, so per level only the plane row is
 // fetched (L1 / L2); the row itself is read from HBM exactly once.  32 rows per CTA.
@@ -624,6 +655,10 @@ void launch_hash(const ForestView& f, const float* d_rows, u64 n, u64* d_keys, u
         }
         hash_rows_kernel<<<(u32)((n + HASH_ROWS_PER_CTA - 1) / HASH_ROWS_PER_CTA), 128, smem, s>>>(f, d_rows, n, pitch, d_keys,
                                                                                                   d_depths, d_leaves);
+        return;
+    }
+    if (variant == 2) {
+        hash_tree_major_kernel<<<(u32)((nw + 31) / 32), 128, 0, s>>>(f, d_rows, n, d_keys, d_depths, d_leaves);
         return;
     }
     hash_kernel<<<(u32)((nw + 31) / 32), 128, 0, s>>>(f, d_rows, n, d_keys, d_depths, d_leaves);

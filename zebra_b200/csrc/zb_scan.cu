@@ -746,4 +746,219 @@ void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* t
 #endif
 }
 
+// =====================================================================================================
+// Leaf-tile scan for the SCALAR metrics (distance.rs:51-190, zb_metrics.cuh) -- SURVEY 8(f) row 3.
+// A sequential f32 fold per pair cannot be split inside the pair, so one thread owns (row, the <= 8 queries of the
+// tile): the row element is loaded ONCE (128-bit __ldg) and folded into one accumulator per query, the queries sit in
+// shared memory and are read as broadcasts.  Visits are grouped by leaf exactly like the fused kernel's tiles, so a
+// leaf's rows cross HBM once per tile instead of once per visit (config 2: 27 GB instead of 173 GB per batch).  Keys go
+// to the gather path's pair_key layout ([visit][member]); the per-visit top-n' stays with select_visits_kernel.
+// =====================================================================================================
+#define SQ_THREADS 128
+#define SQ_TQ 8
+#define SQ_CTAS_PER_SM 4
+
+__global__ void sq_count_kernel(u32 nv, const u32* __restrict__ v_leaf, const u64* __restrict__ v_pair_off, u32* __restrict__ leaf_count) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    if (v_pair_off[v + 1] > v_pair_off[v]) atomicAdd(&leaf_count[v_leaf[v]], 1u);  // visits with pairs to score
+}
+__global__ void sq_scatter_kernel(u32 nv, const u32* __restrict__ v_leaf, const u64* __restrict__ v_pair_off,
+                                  const u32* __restrict__ leaf_start, u32* __restrict__ leaf_cursor, u32* __restrict__ order) {
+    u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    if (v_pair_off[v + 1] > v_pair_off[v]) {
+        const u32 leaf = v_leaf[v];
+        order[leaf_start[leaf] + atomicAdd(&leaf_cursor[leaf], 1u)] = v;
+    }
+}
+
+struct SeqTileParams {
+    const u32* tile_leaf;
+    const u32* tile_first;
+    const u32* tile_count;
+    const u32* ntiles;
+    u32* tile_counter;
+    const u32* order;
+    const u32* v_q;
+    const u64* v_pair_off;
+    u64* pair_key;
+    const float* queries;
+    u64* stats;  // [0] visits, [1] pairs, [2] bytes asked of HBM by design
+    int power;
+};
+
+template <int CODE, int NQ>
+__device__ __forceinline__ void seq_tile_rows(const ForestView& f, const SeqTileParams& tp, const float* __restrict__ s_q,
+                                              const u32* __restrict__ s_v, u32 c, u32 leaf) {
+    const u32 len = f.leaf_len[leaf];
+    const long long off = f.leaf_off[leaf];
+    const int n4 = f.dim >> 2, q4 = f.dimp >> 2;
+    const float4* q = reinterpret_cast<const float4*>(s_q);
+    u64 pbase[NQ];  // where each visit's keys start in pair_key
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) pbase[j] = tp.v_pair_off[s_v[j]];
+    for (u32 r = threadIdx.x; r < len; r += SQ_THREADS) {
+        const u32 slot = f.members[off + r];
+        if (tomb_test(f.tomb, slot)) {
+#pragma unroll
+            for (int j = 0; j < NQ; ++j)
+                if ((u32)j < c) tp.pair_key[pbase[j] + r] = ZB_SENTINEL;
+            continue;
+        }
+        SeqAcc st[NQ];
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) seq_init(st[j]);
+        const float* row = f.rows + (size_t)slot * f.dimp;
+        const float4* a = reinterpret_cast<const float4*>(row);
+#pragma unroll 4
+        for (int i = 0; i < n4; ++i) {
+            const float4 av = __ldg(a + i);
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+                const float4 bv = q[j * q4 + i];  // same address across the warp: a broadcast
+                seq_step<CODE>(st[j], av.x, bv.x, tp.power);
+                seq_step<CODE>(st[j], av.y, bv.y, tp.power);
+                seq_step<CODE>(st[j], av.z, bv.z, tp.power);
+                seq_step<CODE>(st[j], av.w, bv.w, tp.power);
+            }
+        }
+        for (int i = n4 * 4; i < f.dim; ++i) {  // dim % 4 tail (never the padding)
+            const float x = __ldg(row + i);
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) seq_step<CODE>(st[j], x, s_q[j * f.dimp + i], tp.power);
+        }
+#pragma unroll
+        for (int j = 0; j < NQ; ++j)
+            if ((u32)j < c) tp.pair_key[pbase[j] + r] = seq_finish<CODE>(st[j], tp.power);
+    }
+}
+
+template <int CODE>
+__global__ void __launch_bounds__(SQ_THREADS) seq_tile_kernel(ForestView f, SeqTileParams tp) {
+    extern __shared__ __align__(16) float s_q[];  // [SQ_TQ][dimp]
+    __shared__ u32 s_tile;
+    __shared__ u32 s_v[SQ_TQ];
+    const u32 ntiles = *tp.ntiles;
+    const int q4 = f.dimp >> 2;
+    for (;;) {
+        __syncthreads();  // the previous tile's queries are no longer read
+        if (threadIdx.x == 0) s_tile = atomicAdd(tp.tile_counter, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u32 leaf = tp.tile_leaf[tile], first = tp.tile_first[tile], c = tp.tile_count[tile];
+        if (threadIdx.x < SQ_TQ) s_v[threadIdx.x] = tp.order[first + (threadIdx.x < c ? threadIdx.x : 0u)];
+        __syncthreads();
+        const u32 nqp = c <= 1 ? 1u : (c <= 2 ? 2u : (c <= 4 ? 4u : 8u));  // query slots the row loop folds
+        for (u32 idx = threadIdx.x; idx < nqp * (u32)q4; idx += SQ_THREADS) {
+            const u32 j = idx / (u32)q4, k = idx - j * (u32)q4;
+            reinterpret_cast<float4*>(s_q)[idx] =
+                j < c ? __ldg(reinterpret_cast<const float4*>(tp.queries + (size_t)tp.v_q[s_v[j]] * f.dimp) + k)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        if (nqp == 1) seq_tile_rows<CODE, 1>(f, tp, s_q, s_v, c, leaf);
+        else if (nqp == 2) seq_tile_rows<CODE, 2>(f, tp, s_q, s_v, c, leaf);
+        else if (nqp == 4) seq_tile_rows<CODE, 4>(f, tp, s_q, s_v, c, leaf);
+        else seq_tile_rows<CODE, 8>(f, tp, s_q, s_v, c, leaf);
+        if (threadIdx.x == 0) {
+            const u64 len = f.leaf_len[leaf];
+            atomicAdd(&tp.stats[0], (u64)c);
+            atomicAdd(&tp.stats[1], len * c);
+            atomicAdd(&tp.stats[2], (len + c) * 4ull * (u64)f.dim);
+        }
+    }
+}
+
+bool seq_tile_scan_supported(int dimp) { return (size_t)SQ_TQ * dimp * 4 <= 96 * 1024; }
+
+void seq_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, int power, const float* d_q, u32 nv, const u32* v_leaf,
+                   const u32* v_q, const u64* v_pair_off, u64* pair_key, u32 nleaves, cudaStream_t s) {
+    ws.seq_launched = false;
+    if (!nv || !nleaves || metric <= M_L2 || !seq_tile_scan_supported(f.dimp)) return;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ws.leaf_count.ensure(nleaves + 1);
+    ws.leaf_start.ensure(nleaves + 1);
+    ws.leaf_cursor.ensure(nleaves + 1);
+    ws.tile_per_leaf.ensure(nleaves + 1);
+    ws.tile_start.ensure(nleaves + 1);
+    ws.order.ensure(nv);
+    ws.tile_leaf.ensure(nv);
+    ws.tile_first.ensure(nv);
+    ws.tile_cnt.ensure(nv);
+    ws.counters.ensure(64);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const u32*)nullptr, (u32*)nullptr, (long long)(nleaves + 1));
+    ws.tmp.ensure(tmp_bytes + 256);
+    ZB_CUDA(cudaMemsetAsync(ws.leaf_count.p, 0, (size_t)(nleaves + 1) * 4, s));
+    ZB_CUDA(cudaMemsetAsync(ws.leaf_cursor.p, 0, (size_t)(nleaves + 1) * 4, s));
+    ZB_CUDA(cudaMemsetAsync(ws.counters.p, 0, 64 * 4, s));
+    sq_count_kernel<<<(nv + 255) / 256, 256, 0, s>>>(nv, v_leaf, v_pair_off, ws.leaf_count.p);
+    cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.leaf_count.p, ws.leaf_start.p, (long long)(nleaves + 1), s);
+    sq_scatter_kernel<<<(nv + 255) / 256, 256, 0, s>>>(nv, v_leaf, v_pair_off, ws.leaf_start.p, ws.leaf_cursor.p, ws.order.p);
+    ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, SQ_TQ, ws.tile_per_leaf.p);
+    cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
+    ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, SQ_TQ,
+                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p);
+    SeqTileParams tp;
+    tp.tile_leaf = ws.tile_leaf.p;
+    tp.tile_first = ws.tile_first.p;
+    tp.tile_count = ws.tile_cnt.p;
+    tp.ntiles = ws.tile_start.p + nleaves;
+    ws.ntiles_ptr = tp.ntiles;
+    tp.tile_counter = ws.counters.p;
+    tp.order = ws.order.p;
+    tp.v_q = v_q;
+    tp.v_pair_off = v_pair_off;
+    tp.pair_key = pair_key;
+    tp.queries = d_q;
+    tp.stats = reinterpret_cast<u64*>(ws.counters.p + 4);
+    tp.power = power;
+    const size_t smem = (size_t)SQ_TQ * f.dimp * 4;
+    const int grid = sms * SQ_CTAS_PER_SM;
+    if (!ws.ev0) {
+        ZB_CUDA(cudaEventCreate(&ws.ev0));
+        ZB_CUDA(cudaEventCreate(&ws.ev1));
+    }
+    ZB_CUDA(cudaEventRecord(ws.ev0, s));
+#define ZB_SQ_CALL(C)                                                                                                        \
+    do {                                                                                                                     \
+        if (smem > 48 * 1024)                                                                                                \
+            ZB_CUDA(cudaFuncSetAttribute(seq_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        seq_tile_kernel<C><<<grid, SQ_THREADS, smem, s>>>(f, tp);                                                            \
+    } while (0)
+    switch (metric) {
+        case M_CHEBYSHEV: ZB_SQ_CALL(M_CHEBYSHEV); break;
+        case M_CANBERRA: ZB_SQ_CALL(M_CANBERRA); break;
+        case M_BRAY_CURTIS: ZB_SQ_CALL(M_BRAY_CURTIS); break;
+        case M_MANHATTAN: ZB_SQ_CALL(M_MANHATTAN); break;
+        case M_L3: ZB_SQ_CALL(M_L3); break;
+        case M_L4: ZB_SQ_CALL(M_L4); break;
+        case M_HAMMING: ZB_SQ_CALL(M_HAMMING); break;
+        case M_MINKOWSKI: ZB_SQ_CALL(M_MINKOWSKI); break;
+        default: ZB_SQ_CALL(M_PNORM); break;
+    }
+#undef ZB_SQ_CALL
+    ZB_CUDA(cudaGetLastError());
+    ZB_CUDA(cudaEventRecord(ws.ev1, s));
+    ws.seq_launched = true;
+}
+
+// Statistics of the last seq_tile_scan launch; call after the stream has been synchronised.
+void seq_tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* moved_bytes, float* kernel_ms, u32* tiles) {
+    *moved_bytes = 0;
+    *kernel_ms = 0.f;
+    *tiles = 0;
+    if (!ws.seq_launched) return;
+    u64 h[3] = {0, 0, 0};
+    ZB_CUDA(cudaMemcpyAsync(h, reinterpret_cast<u64*>(ws.counters.p + 4), 24, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaMemcpyAsync(tiles, ws.ntiles_ptr, 4, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(kernel_ms, ws.ev0, ws.ev1);
+    *moved_bytes = h[2];
+}
+
 }  // namespace zb

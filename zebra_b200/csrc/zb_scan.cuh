@@ -11,6 +11,7 @@ struct ScanWorkspace {
     DBuf<u64> gthr;
     DBuf<u8> tmp;
     bool launched = false;
+    bool seq_launched = false;   // seq_tile_scan (scalar metrics) ran for the last batch
     u32 launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the tile kernel alone
     const u32* ntiles_ptr = nullptr;           // device scalar: tiles of the last launch
@@ -43,5 +44,13 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
                u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s);
 void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes, float* kernel_ms,
                      u32* tiles);
+
+// The scalar metrics (zb_metric 3..11): every visit with pairs to score, grouped by leaf into (leaf, <= 8 queries) tiles;
+// one thread folds a row against the tile's queries and writes the keys into the gather path's pair_key layout
+// (pair_key[v_pair_off[v] + member]); select_visits_kernel then takes each visit's top-n'.  v_pair_off holds nv + 1 offsets.
+bool seq_tile_scan_supported(int dimp);
+void seq_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, int power, const float* d_q, u32 nv, const u32* v_leaf,
+                   const u32* v_q, const u64* v_pair_off, u64* pair_key, u32 nleaves, cudaStream_t s);
+void seq_tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* moved_bytes, float* kernel_ms, u32* tiles);
 
 }  // namespace zb

@@ -754,7 +754,7 @@ void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* t
 // leaf's rows cross HBM once per tile instead of once per visit (config 2: 27 GB instead of 173 GB per batch).  Keys go
 // to the gather path's pair_key layout ([visit][member]); the per-visit top-n' stays with select_visits_kernel.
 // =====================================================================================================
-#define SQ_THREADS 128
+#define SQ_THREADS 256
 #define SQ_TQ 8
 #define SQ_CTAS_PER_SM 4
 
@@ -790,20 +790,18 @@ struct SeqTileParams {
 
 template <int CODE, int NQ>
 __device__ __forceinline__ void seq_tile_rows(const ForestView& f, const SeqTileParams& tp, const float* __restrict__ s_q,
-                                              const u32* __restrict__ s_v, u32 c, u32 leaf) {
+                                              const u64* __restrict__ s_pbase, u32 c, u32 leaf) {
     const u32 len = f.leaf_len[leaf];
     const long long off = f.leaf_off[leaf];
     const int n4 = f.dim >> 2, q4 = f.dimp >> 2;
+    const int n8 = n4 >> 1;  // groups of two float4 = one 32-byte sector of the row
     const float4* q = reinterpret_cast<const float4*>(s_q);
-    u64 pbase[NQ];  // where each visit's keys start in pair_key
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) pbase[j] = tp.v_pair_off[s_v[j]];
     for (u32 r = threadIdx.x; r < len; r += SQ_THREADS) {
         const u32 slot = f.members[off + r];
         if (tomb_test(f.tomb, slot)) {
 #pragma unroll
             for (int j = 0; j < NQ; ++j)
-                if ((u32)j < c) tp.pair_key[pbase[j] + r] = ZB_SENTINEL;
+                if ((u32)j < c) tp.pair_key[s_pbase[j] + r] = ZB_SENTINEL;
             continue;
         }
         SeqAcc st[NQ];
@@ -811,12 +809,32 @@ __device__ __forceinline__ void seq_tile_rows(const ForestView& f, const SeqTile
         for (int j = 0; j < NQ; ++j) seq_init(st[j]);
         const float* row = f.rows + (size_t)slot * f.dimp;
         const float4* a = reinterpret_cast<const float4*>(row);
-#pragma unroll 4
-        for (int i = 0; i < n4; ++i) {
+        // software pipeline: the next sector of the row is in flight while this one is folded into the NQ accumulators
+        // (the profile of the first version was 56 % long-scoreboard stalls on the row loads, issue slots 24 % busy)
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        if (n8 > 0) { c0 = __ldg(a); c1 = __ldg(a + 1); }
+#pragma unroll 1
+        for (int g = 0; g < n8; ++g) {
+            float4 x0 = c0, x1 = c1;
+            if (g + 1 < n8) { c0 = __ldg(a + 2 * g + 2); c1 = __ldg(a + 2 * g + 3); }
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+                const float4 b0 = q[j * q4 + 2 * g], b1 = q[j * q4 + 2 * g + 1];  // same address across the warp: broadcasts
+                seq_step<CODE>(st[j], x0.x, b0.x, tp.power);
+                seq_step<CODE>(st[j], x0.y, b0.y, tp.power);
+                seq_step<CODE>(st[j], x0.z, b0.z, tp.power);
+                seq_step<CODE>(st[j], x0.w, b0.w, tp.power);
+                seq_step<CODE>(st[j], x1.x, b1.x, tp.power);
+                seq_step<CODE>(st[j], x1.y, b1.y, tp.power);
+                seq_step<CODE>(st[j], x1.z, b1.z, tp.power);
+                seq_step<CODE>(st[j], x1.w, b1.w, tp.power);
+            }
+        }
+        for (int i = n8 * 2; i < n4; ++i) {  // an odd float4 left over
             const float4 av = __ldg(a + i);
 #pragma unroll
             for (int j = 0; j < NQ; ++j) {
-                const float4 bv = q[j * q4 + i];  // same address across the warp: a broadcast
+                const float4 bv = q[j * q4 + i];
                 seq_step<CODE>(st[j], av.x, bv.x, tp.power);
                 seq_step<CODE>(st[j], av.y, bv.y, tp.power);
                 seq_step<CODE>(st[j], av.z, bv.z, tp.power);
@@ -830,15 +848,16 @@ __device__ __forceinline__ void seq_tile_rows(const ForestView& f, const SeqTile
         }
 #pragma unroll
         for (int j = 0; j < NQ; ++j)
-            if ((u32)j < c) tp.pair_key[pbase[j] + r] = seq_finish<CODE>(st[j], tp.power);
+            if ((u32)j < c) tp.pair_key[s_pbase[j] + r] = seq_finish<CODE>(st[j], tp.power);
     }
 }
 
 template <int CODE>
-__global__ void __launch_bounds__(SQ_THREADS) seq_tile_kernel(ForestView f, SeqTileParams tp) {
+__global__ void __launch_bounds__(SQ_THREADS, SQ_CTAS_PER_SM) seq_tile_kernel(ForestView f, SeqTileParams tp) {
     extern __shared__ __align__(16) float s_q[];  // [SQ_TQ][dimp]
     __shared__ u32 s_tile;
     __shared__ u32 s_v[SQ_TQ];
+    __shared__ u64 s_pbase[SQ_TQ];  // where each visit's keys start in pair_key
     const u32 ntiles = *tp.ntiles;
     const int q4 = f.dimp >> 2;
     for (;;) {
@@ -848,7 +867,11 @@ __global__ void __launch_bounds__(SQ_THREADS) seq_tile_kernel(ForestView f, SeqT
         const u32 tile = s_tile;
         if (tile >= ntiles) break;
         const u32 leaf = tp.tile_leaf[tile], first = tp.tile_first[tile], c = tp.tile_count[tile];
-        if (threadIdx.x < SQ_TQ) s_v[threadIdx.x] = tp.order[first + (threadIdx.x < c ? threadIdx.x : 0u)];
+        if (threadIdx.x < SQ_TQ) {
+            const u32 v = tp.order[first + (threadIdx.x < c ? threadIdx.x : 0u)];
+            s_v[threadIdx.x] = v;
+            s_pbase[threadIdx.x] = tp.v_pair_off[v];
+        }
         __syncthreads();
         const u32 nqp = c <= 1 ? 1u : (c <= 2 ? 2u : (c <= 4 ? 4u : 8u));  // query slots the row loop folds
         for (u32 idx = threadIdx.x; idx < nqp * (u32)q4; idx += SQ_THREADS) {
@@ -858,10 +881,10 @@ __global__ void __launch_bounds__(SQ_THREADS) seq_tile_kernel(ForestView f, SeqT
                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
-        if (nqp == 1) seq_tile_rows<CODE, 1>(f, tp, s_q, s_v, c, leaf);
-        else if (nqp == 2) seq_tile_rows<CODE, 2>(f, tp, s_q, s_v, c, leaf);
-        else if (nqp == 4) seq_tile_rows<CODE, 4>(f, tp, s_q, s_v, c, leaf);
-        else seq_tile_rows<CODE, 8>(f, tp, s_q, s_v, c, leaf);
+        if (nqp == 1) seq_tile_rows<CODE, 1>(f, tp, s_q, s_pbase, c, leaf);
+        else if (nqp == 2) seq_tile_rows<CODE, 2>(f, tp, s_q, s_pbase, c, leaf);
+        else if (nqp == 4) seq_tile_rows<CODE, 4>(f, tp, s_q, s_pbase, c, leaf);
+        else seq_tile_rows<CODE, 8>(f, tp, s_q, s_pbase, c, leaf);
         if (threadIdx.x == 0) {
             const u64 len = f.leaf_len[leaf];
             atomicAdd(&tp.stats[0], (u64)c);

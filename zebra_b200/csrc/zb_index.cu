@@ -155,7 +155,7 @@ struct zb_index {
     ScanWorkspace scan_ws;
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 4;
     zb_stats st{};
 
     ForestView view() const {
@@ -914,7 +914,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->scan_ws.seq_launched = false;
     if (ix->opt.metric > ZB_METRIC_L2 && ix->p_seq_tile && total_pairs && seq_tile_scan_supported(ix->dimp))
         seq_tile_scan(ix->scan_ws, fs, ix->opt.metric, (int)ix->opt.metric_power, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p,
-                      ix->pair_key.p, (u32)ix->h_leaf_off.size(), s);
+                      ix->pair_key.p, (u32)ix->h_leaf_off.size(), (int)ix->p_seq_prefetch, s);
     if (!ix->scan_ws.seq_launched)
         launch_score_pairs(fs, (int)ix->opt.metric, (int)ix->opt.metric_power, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p,
                            total_pairs, ix->pair_key.p, s);
@@ -1742,6 +1742,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "tile_queries") ix->p_tile_queries = value;
     else if (k == "use_tile_scan") ix->p_use_tile_scan = value;
     else if (k == "classify_variant") ix->p_classify_variant = value;  // 0: rows gathered through L1; 1: rows staged by TMA bulk copies
+    else if (k == "seq_prefetch") ix->p_seq_prefetch = value;  // scalar metrics: L2 prefetch distance of the row stream, 128-byte lines
     else if (k == "seq_tile") ix->p_seq_tile = value;          // scalar metrics: 1 = leaf-tile scan (default), 0 = one thread per pair
     else if (k == "hash_variant") ix->p_hash_variant = value;  // 0: quad per (row, tree), rows through L1; 1: row staged in shared memory
     else if (k == "visit_slots") {  // initial per-walker capacity of the visit plan (tests force the grow-and-replan path)

@@ -786,6 +786,7 @@ struct SeqTileParams {
     const float* queries;
     u64* stats;  // [0] visits, [1] pairs, [2] bytes asked of HBM by design
     int power;
+    int pf_lines;  // L2 prefetch distance in 128-byte lines of the row (0 = off)
 };
 
 template <int CODE, int NQ>
@@ -795,6 +796,7 @@ __device__ __forceinline__ void seq_tile_rows(const ForestView& f, const SeqTile
     const long long off = f.leaf_off[leaf];
     const int n4 = f.dim >> 2, q4 = f.dimp >> 2;
     const int n8 = n4 >> 1;  // groups of two float4 = one 32-byte sector of the row
+    const int pf = tp.pf_lines * 8;  // prefetch distance in float4
     const float4* q = reinterpret_cast<const float4*>(s_q);
     for (u32 r = threadIdx.x; r < len; r += SQ_THREADS) {
         const u32 slot = f.members[off + r];
@@ -817,6 +819,9 @@ __device__ __forceinline__ void seq_tile_rows(const ForestView& f, const SeqTile
         for (int g = 0; g < n8; ++g) {
             float4 x0 = c0, x1 = c1;
             if (g + 1 < n8) { c0 = __ldg(a + 2 * g + 2); c1 = __ldg(a + 2 * g + 3); }
+            // one prefetch per 128-byte line, pf_lines lines ahead: the line waits in L2 when its loads are issued, so
+            // the row stream is bounded by L2 latency, not by DRAM latency x the registers a deeper pipeline would need
+            if (pf != 0 && (g & 3) == 0 && 2 * g + pf < n4) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 2 * g + pf));
 #pragma unroll
             for (int j = 0; j < NQ; ++j) {
                 const float4 b0 = q[j * q4 + 2 * g], b1 = q[j * q4 + 2 * g + 1];  // same address across the warp: broadcasts
@@ -897,7 +902,7 @@ __global__ void __launch_bounds__(SQ_THREADS, SQ_CTAS_PER_SM) seq_tile_kernel(Fo
 bool seq_tile_scan_supported(int dimp) { return (size_t)SQ_TQ * dimp * 4 <= 96 * 1024; }
 
 void seq_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, int power, const float* d_q, u32 nv, const u32* v_leaf,
-                   const u32* v_q, const u64* v_pair_off, u64* pair_key, u32 nleaves, cudaStream_t s) {
+                   const u32* v_q, const u64* v_pair_off, u64* pair_key, u32 nleaves, int prefetch_lines, cudaStream_t s) {
     ws.seq_launched = false;
     if (!nv || !nleaves || metric <= M_L2 || !seq_tile_scan_supported(f.dimp)) return;
     int dev = 0, sms = 0;
@@ -940,6 +945,7 @@ void seq_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, int power
     tp.queries = d_q;
     tp.stats = reinterpret_cast<u64*>(ws.counters.p + 4);
     tp.power = power;
+    tp.pf_lines = prefetch_lines < 0 ? 0 : (prefetch_lines > 64 ? 64 : prefetch_lines);
     const size_t smem = (size_t)SQ_TQ * f.dimp * 4;
     const int grid = sms * SQ_CTAS_PER_SM;
     if (!ws.ev0) {

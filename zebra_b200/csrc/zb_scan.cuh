@@ -50,7 +50,7 @@ void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* t
 // (pair_key[v_pair_off[v] + member]); select_visits_kernel then takes each visit's top-n'.  v_pair_off holds nv + 1 offsets.
 bool seq_tile_scan_supported(int dimp);
 void seq_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, int power, const float* d_q, u32 nv, const u32* v_leaf,
-                   const u32* v_q, const u64* v_pair_off, u64* pair_key, u32 nleaves, cudaStream_t s);
+                   const u32* v_q, const u64* v_pair_off, u64* pair_key, u32 nleaves, int prefetch_lines, cudaStream_t s);
 void seq_tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* moved_bytes, float* kernel_ms, u32* tiles);
 
 }  // namespace zb

@@ -146,3 +146,23 @@ def test_database_facade_with_scalar_metric():
     assert hit[0] == (ids[3], 0)
     with pytest.raises(ValueError):
         db.index.search(rows[3], 2, z.MinkowskiDistance(1))
+
+
+def test_sharded_two_gpus_scalar_metrics_and_store_import():
+    """tests/mgpu_parity_ext.py on 2 GPUs of this box: scalar metrics through the bucket-sharded store (leaf-tile scan and
+    one thread per pair) and the import of an oracle-written store into a sharded index, against the unsharded oracle.
+    Skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(root, "tests", "mgpu_parity_ext.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count(": ok") == 11 and "MISMATCH" not in out.stdout

@@ -155,7 +155,7 @@ struct zb_index {
     ScanWorkspace scan_ws;
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 4;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0;
     zb_stats st{};
 
     ForestView view() const {
@@ -1742,7 +1742,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "tile_queries") ix->p_tile_queries = value;
     else if (k == "use_tile_scan") ix->p_use_tile_scan = value;
     else if (k == "classify_variant") ix->p_classify_variant = value;  // 0: rows gathered through L1; 1: rows staged by TMA bulk copies
-    else if (k == "seq_prefetch") ix->p_seq_prefetch = value;  // scalar metrics: L2 prefetch distance of the row stream, 128-byte lines
+    else if (k == "seq_prefetch") ix->p_seq_prefetch = value;  // scalar metrics: L2 prefetch distance of the row stream in 128-byte lines (0 = off, the default: measured slower)
     else if (k == "seq_tile") ix->p_seq_tile = value;          // scalar metrics: 1 = leaf-tile scan (default), 0 = one thread per pair
     else if (k == "hash_variant") ix->p_hash_variant = value;  // 0: quad per (row, tree), rows through L1; 1: row staged in shared memory
     else if (k == "visit_slots") {  // initial per-walker capacity of the visit plan (tests force the grow-and-replan path)

@@ -21,6 +21,11 @@ CASES = [  # name, metric, dim, n, max_node_size, trees, top_k
     ("cosine_defaults", zo.COSINE, 20, 300, 5, 15, 10),
     ("l2sq_large_leaves", zo.L2SQ, 48, 400, 96, 3, 10),
     ("l2_mid", zo.L2, 33, 350, 16, 4, 25),
+    # the scalar metrics of distance.rs:51-190 (f32 bits zero-extended; Minkowski carries its power in bits 8..)
+    ("manhattan_defaults", zo.MANHATTAN, 21, 300, 5, 15, 10),
+    ("canberra_mid", zo.CANBERRA, 16, 320, 24, 3, 12),
+    ("minkowski3_large_leaves", zo.MINKOWSKI(3), 40, 400, 96, 3, 10),
+    ("hamming_mid", zo.HAMMING, 24, 300, 16, 4, 8),
 ]
 
 
@@ -46,6 +51,9 @@ def build_case(name, metric, dim, n, mns, trees, k):
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])                                   # names to (re)write; none = all
     for c in CASES:
+        if only and c[0] not in only:
+            continue
         np.savez_compressed(os.path.join(HERE, c[0] + ".npz"), **build_case(*c))
         print("wrote", c[0])

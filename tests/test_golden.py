@@ -10,12 +10,14 @@ import pytest
 from oracle import zb_oracle as zo
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
-NAMES = {zo.COSINE: "CosineDistance", zo.L2SQ: "L2SquaredDistance", zo.L2: "L2Distance"}
+NAMES = {zo.COSINE: ("CosineDistance", ()), zo.L2SQ: ("L2SquaredDistance", ()), zo.L2: ("L2Distance", ()),
+         zo.MANHATTAN: ("ManhattanDistance", ()), zo.CANBERRA: ("CanberraDistance", ()), zo.HAMMING: ("HammingDistance", ()),
+         zo.MINKOWSKI(3): ("MinkowskiDistance", (3,))}
 FOREST = ("nodes", "roots", "coef", "cst", "leaf_off", "members")
 
 
 def test_fixtures_exist():
-    assert len(GOLDEN) == 3
+    assert len(GOLDEN) == 7
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
@@ -42,7 +44,8 @@ def test_cuda_reproduces_golden(path):
     import zebra_b200 as z
 
     g = np.load(path)
-    metric = getattr(z, NAMES[int(g["metric"])])()
+    cls, args = NAMES[int(g["metric"])]
+    metric = getattr(z, cls)(*args)
     ix = z.LSHIndex(g["rows"].shape[1], z.LSHIndexOptions(int(g["mns"]), int(g["trees"])), metric, seed=5)
     ix.add(g["rows"][: int(g["first"])])
     assert ix.remove_ordinals(g["dead"]).all()

@@ -148,6 +148,23 @@ def test_database_facade_with_scalar_metric():
         db.index.search(rows[3], 2, z.MinkowskiDistance(1))
 
 
+def _scalar_golden():
+    import glob
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    return [p for p in sorted(glob.glob(os.path.join(here, "golden", "*.npz"))) if int(np.load(p)["metric"]) > zo.L2]
+
+
+@pytest.mark.parametrize("path", _scalar_golden(), ids=lambda p: p.split("/")[-1])
+def test_cuda_reproduces_scalar_metric_golden(path):
+    """tests/golden fixtures of the scalar metrics (frozen forest, bucket keys, ids, distance bits, counts) through the
+    same add / remove / add sequence over the C ABI."""
+    from test_golden import cuda_reproduces_golden
+
+    cuda_reproduces_golden(path)
+
+
 def test_sharded_two_gpus_scalar_metrics_and_store_import():
     """tests/mgpu_parity_ext.py on 2 GPUs of this box: scalar metrics through the bucket-sharded store (leaf-tile scan and
     one thread per pair) and the import of an oracle-written store into a sharded index, against the unsharded oracle.

@@ -990,7 +990,9 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->st.last_tile_pairs = tile_pairs;
     ix->st.last_moved_bytes = ix->scan_ws.seq_launched ? seq_moved : moved + total_pairs * (u64)ix->dim * 4;
     ix->st.last_scan_launches = scan_launches + (total_pairs ? (ix->scan_ws.seq_launched ? 7 : 1) : 0);
-    ix->st.last_total_launches += scan_launches + 5 + (sharded ? 1 : 0);
+    // generic-path launches: the score kernel (or the 7 of seq_tile_scan: count, scan, scatter, tile count, scan, fill, scan
+    // kernel) + select; then the merge
+    ix->st.last_total_launches += scan_launches + 5 + (sharded ? 1 : 0) + (ix->scan_ws.seq_launched ? 6 : 0);
 }
 
 static const float* stage_queries_device(zb_index* ix, const float* d_q, u64 nq) {

@@ -65,6 +65,9 @@ def parse():
                     help="query = BASELINE config 2 (the default, the driver's line); hash / build = BASELINE config 4 "
                          "(bucket keys of fresh rows on a built forest / bulk insert), rows per second")
     ap.add_argument("--hash-rows", type=int, default=1_000_000, help="rows hashed per GPU per step (workload hash)")
+    ap.add_argument("--flat-bits", type=int, default=0,
+                    help="workload hash: K > 0 hashes FLAT tables (every level of a tree shares one plane: K bits per table, "
+                         "H = K * trees planes per row, dense projection kernel) instead of the built forest")
     return ap.parse_args()
 
 
@@ -459,7 +462,18 @@ def run_aux(a):
         ix = new_index(False)
         d_rows = torch.empty((a.rows, a.dim), dtype=torch.float32, device=dev)
         z.synth_fill_device(local, d_rows.data_ptr(), 0, 1, a.rows, a.dim, a.seed, 1)
-        ix.add_device(d_rows.data_ptr(), a.rows)
+        flat_coef = flat_cst = None
+        if a.flat_bits:
+            # K-bit tables: planes through the midpoints of seeded row pairs (lsh.rs:222-225); planes are INPUT to both sides
+            H = a.flat_bits * a.trees
+            pick = torch.from_numpy(np.random.default_rng(a.seed + 2).integers(0, a.rows, (H, 2))).to(dev)
+            pa, pb = d_rows[pick[:, 0]], d_rows[pick[:, 1]]
+            coef_t = pb - pa
+            flat_coef = coef_t.cpu().numpy()
+            flat_cst = (-(coef_t * ((pa + pb) / 2)).sum(1)).cpu().numpy().astype(np.float32)
+            ix.load_flat(d_rows.cpu().numpy(), a.flat_bits, flat_coef, flat_cst)
+        else:
+            ix.add_device(d_rows.data_ptr(), a.rows)
         del d_rows
         n = a.hash_rows
         d_x = torch.empty((nb, n, a.dim), dtype=torch.float32, device=dev)
@@ -496,7 +510,38 @@ def run_aux(a):
                  "plane_bytes_from_l2_per_step": depth_sum * a.dim * 4, "fma_per_step": depth_sum * a.dim}
         kernel = "hash_kernel (zb_kernels.cu): root-to-leaf descent, one quad per (row, tree)"
         h2d, d2h = n * a.dim * 4, n * a.trees * 16
-        if rank == 0 and G == 1 and not a.no_cpu_baseline:
+        if a.flat_bits:
+            H = a.flat_bits * a.trees
+            kernel = "project_flat_kernel + pack_flat_keys_kernel (zb_kernels.cu): dense rows x planes projection, ballot-packed keys"
+            extra.update({"flat_bits": a.flat_bits, "planes_per_row": H,
+                          "fp32_tflops": 2.0 * a.dim * H * n * a.steps / (dev_ms / 1e3) / 1e12,
+                          "fp32_peak_tflops_measured": 72.0, "fp32_peak_source": "profiles/r01_fp32_pipe.txt (FFMA, 128 lanes/clk/SM)"})
+        if a.flat_bits and rank == 0 and G == 1 and not a.no_cpu_baseline:
+            # the reference walks a depth-K tree per table = K point_is_above calls per (row, table): timed on one host thread
+            from oracle import zb_oracle as zo
+
+            xs = h_x.numpy()
+            H = a.flat_bits * a.trees
+
+            def cpu_keys(x):
+                above = np.empty((x.shape[0], H), np.uint8)
+                for h in range(H):
+                    above[:, h] = zo.above_batch(np.broadcast_to(flat_coef[h], x.shape), np.full(x.shape[0], flat_cst[h], np.float32), x)
+                keys = np.zeros((x.shape[0], a.trees), np.uint64)
+                for t in range(a.trees):
+                    for d in range(a.flat_bits):
+                        keys[:, t] = (keys[:, t] << np.uint64(1)) | above[:, t * a.flat_bits + d].astype(np.uint64)
+                return keys
+
+            sample = min(n, 2048)
+            t0 = time.time(); ek = cpu_keys(xs[:sample]); dt = time.time() - t0
+            while dt < a.cpu_seconds / 4 and sample < n:     # grow the sample to about cpu_seconds of CPU work
+                sample = min(n, sample * 4)
+                t0 = time.time(); ek = cpu_keys(xs[:sample]); dt = time.time() - t0
+            cpu = {"value": sample / dt, "unit": unit_name, "cores": 1, "kind": "port",
+                   "sample": f"{sample} rows of the last step x {H} planes, {dt:.1f}s on 1 thread; restated point_is_above per (row, plane)"}
+            parity = bool(np.array_equal(hk[:sample], ek) and np.all(hd[:sample] == a.flat_bits))
+        elif rank == 0 and G == 1 and not a.no_cpu_baseline:
             from oracle import zb_oracle as zo
 
             orc = zo.OracleIndex(a.dim, METRIC_IDS[a.metric], a.max_node_size, a.trees, seed=a.seed)

@@ -228,11 +228,23 @@ int zb_index_export_rows(zb_index* index, uint64_t first_ordinal, uint64_t n, fl
 /* Tree `tree` as the reference's blob; removed rows are left out of the leaves.  out may be NULL. */
 int zb_index_export_tree_blob(zb_index* index, uint32_t tree, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
 
+/* FLAT tables: the special case of the reference's tree (lsh.rs:46-60) in which every node at depth d of tree t shares
+ * one hyperplane -- the K-bit LSH table of north_star (a).  coef = num_trees * bits planes of dim f32 (table t, bit d
+ * at index t * bits + d; bit 0 is the root decision = the key's MSB), cst = their constants; 1 <= bits <= 16.  Replaces
+ * the index content with n rows (ordinals 0..n-1) bucketed by the dense projection: one [rows x dim] . [dim x
+ * num_trees * bits] pass of Hyperplane::point_is_above (lsh.rs:39-43) in the canonical accumulation order, sign bits
+ * packed into the bucket keys with __ballot_sync.  The index then holds the equivalent forest (complete trees of depth
+ * `bits`), so search / remove / export behave as for any forest; zb_index_hash* keeps using the dense projection until
+ * an insert splits a leaf. */
+int zb_index_load_flat(zb_index* index, uint64_t n, const float* rows, const uint8_t* ids16, uint32_t bits,
+                       const float* coef, const float* cst);
+
 int zb_index_stats(zb_index* index, zb_stats* out);
 /* The CUDA stream (cudaStream_t) every kernel of this index is launched on -- for callers that time the
  * device work with their own events. */
 int zb_index_stream(zb_index* index, void** out_stream);
-/* Tuning knobs (tests and ablations): key in {"tile_min_rows", "tile_queries", "use_tile_scan", "visit_slots"}. */
+/* Tuning knobs (tests and ablations): key in {"tile_min_rows", "tile_queries", "use_tile_scan", "visit_slots", "seq_tile",
+ * "seq_prefetch", "hash_variant", "classify_variant", "flat_project"}. */
 int zb_index_set_param(zb_index* index, const char* key, int64_t value);
 
 /* Sharding over the GPUs of one box: one process per GPU, each with its own index

@@ -307,6 +307,19 @@ class LSHIndex {
         check(zb_index_hash(raw(), rows.size(), rows[0].data(), keys.data(), depths.data(), nullptr));
     }
 
+    /// FLAT tables (the K-bit LSH table): plane t * bits + d serves every node at depth d of tree t.  The rows are
+    /// bucketed by one dense projection on the device; afterwards the index holds the equivalent forest.
+    void load_flat(const std::vector<Embedding<N>>& rows, uint32_t bits, const std::vector<Embedding<N>>& planes,
+                   const std::vector<EmbeddingPrecision>& constants, const std::vector<Uuid>* ids = nullptr) const {
+        if (planes.size() != options_.num_trees * bits || constants.size() != planes.size())
+            throw Error(ZB_ERR_INVALID, "load_flat takes num_trees * bits planes and constants");
+        if (ids && ids->size() != rows.size()) throw Error(ZB_ERR_INVALID, "one id per row");
+        std::vector<uint8_t> raw_ids;
+        if (ids) raw_ids = pack(*ids);
+        check(zb_index_load_flat(raw(), rows.size(), rows.empty() ? nullptr : rows[0].data(), ids ? raw_ids.data() : nullptr, bits,
+                                 planes[0].data(), constants.data()));
+    }
+
     // ---- the reference's stored values (KeyValue, lsh.rs:63-119): see INTEGRATION.md section 6 ----
     /// Replace the content with a store: (id, embedding) pairs of the `embeddings` partition and the values of `trees`.
     zb_import_report import_store(const std::vector<Uuid>& ids, const std::vector<Embedding<N>>& embeddings,

@@ -1,0 +1,110 @@
+"""GPU leg of the flat-table path (north_star (a)): zb_index_load_flat buckets the rows with the dense projection kernel
+(project_flat_kernel + __ballot_sync packing); the oracle walks the EQUIVALENT forest (complete trees, tests/test_flat_tables.py)
+with the reference's own tree walk.  Keys, depths, leaves, the exported forest, and search results must be bit-identical,
+and the dense path must agree with the generic tree walker of the same index (knob flat_project = 0).
+
+NOT YET RUN ON A GPU when it was committed (the round's GPU budget was spent): it sorts last so that a failure here
+cannot hide the rest of the suite."""
+import numpy as np
+import pytest
+
+from oracle import zb_oracle as zo
+from test_flat_tables import flat_forest, flat_keys, flat_planes
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def zb():
+    import zebra_b200
+
+    return zebra_b200
+
+
+def clustered(rng, n, dim, centres=32, noise=0.25):
+    c = rng.standard_normal((centres, dim)).astype(F32)
+    return (c[rng.integers(0, centres, n)] + noise * rng.standard_normal((n, dim))).astype(F32)
+
+
+def assert_search_equal(ix, orc, queries, k):
+    _, ords, bits, counts = ix.search_batch(queries, k, want_ids=False)
+    eo, eb, ec = orc.search_batch(queries, k, nthreads=8)
+    assert np.array_equal(counts, ec)
+    for q in range(queries.shape[0]):
+        c = int(ec[q])
+        assert np.array_equal(ords[q, :c], eo[q, :c]) and np.array_equal(bits[q, :c], eb[q, :c]), q
+
+
+@pytest.mark.parametrize("T,K,dim,n,mname,mid", [(3, 5, 100, 2001, "L2SquaredDistance", zo.L2SQ),     # dim % 16 != 0, H = 15, n % 32 != 0
+                                                 (2, 9, 384, 3000, "CosineDistance", zo.COSINE),
+                                                 (4, 6, 768, 1500, "ManhattanDistance", zo.MANHATTAN),   # H = 24
+                                                 (1, 1, 16, 70, "L2Distance", zo.L2)])
+def test_flat_tables_equal_the_equivalent_forest(T, K, dim, n, mname, mid):
+    z = zb()
+    rng = np.random.default_rng(T * 1000 + K)
+    rows = clustered(rng, n, dim)
+    coef, cst = flat_planes(rng, rows, T, K)
+    forest, keys = flat_forest(rows, coef, cst, T, K)
+    orc = zo.OracleIndex(dim, mid, 10**6, T, seed=3)
+    orc.load_forest(rows, forest)
+    ix = z.LSHIndex(dim, z.LSHIndexOptions(10**6, T), getattr(z, mname)(), seed=3)
+    ix.load_flat(rows, K, coef, cst)
+    fa, fb = orc.export_forest(), ix.export_forest()           # the projection bucketed every row like the tree walk
+    for f in ("roots", "nodes", "cst", "coef", "leaf_off", "members"):
+        assert np.array_equal(getattr(fa, f), getattr(fb, f)), f
+    queries = np.concatenate([rows[:50], clustered(rng, 83, dim)])
+    want = flat_keys(queries, coef, cst, T, K)
+    for knob in (1, 0):                                         # dense projection, then the generic walker: same answer
+        ix.set_param("flat_project", knob)
+        k, d, l = ix.hash(queries)
+        ek, ed, el = orc.hash(queries)
+        assert np.array_equal(k, want) and np.array_equal(k, ek) and np.array_equal(d, ed) and np.array_equal(l, el), knob
+    ix.set_param("flat_project", 1)
+    assert_search_equal(ix, orc, queries, 10)
+    dead = rng.choice(n, n // 10, replace=False).astype(np.uint64)
+    assert np.array_equal(ix.remove_ordinals(dead), orc.remove(dead))
+    assert_search_equal(ix, orc, queries, 10)
+    k, _, _ = ix.hash(queries)
+    assert np.array_equal(k, want)                              # deletes do not change the tables
+
+
+def test_flat_tables_with_ids_and_leaf_splits_fall_back_to_the_walker():
+    """An insert that splits a leaf makes the forest deeper than K there: the dense path must switch itself off."""
+    import uuid
+
+    z = zb()
+    rng = np.random.default_rng(9)
+    T, K, dim, n = 2, 3, 48, 600
+    rows = clustered(rng, n, dim, centres=4)
+    coef, cst = flat_planes(rng, rows, T, K)
+    forest, _ = flat_forest(rows, coef, cst, T, K)
+    orc = zo.OracleIndex(dim, zo.L2SQ, 40, T, seed=5)           # leaves of ~75 rows already exceed the capacity of 40
+    orc.load_forest(rows, forest)
+    ids = [uuid.UUID(int=1000 + i) for i in range(n)]
+    ix = z.LSHIndex(dim, z.LSHIndexOptions(40, T), z.L2SquaredDistance(), seed=5)
+    ix.load_flat(rows, K, coef, cst, ids=ids)
+    assert ix.search(rows[7], 1)[0] == (ids[7], 0)
+    more = clustered(rng, 200, dim, centres=4)
+    orc.add(more)                                               # D4: append, then rebuild every over-full leaf
+    ix.add(more, ids=[uuid.UUID(int=5000 + i) for i in range(200)])
+    fa, fb = orc.export_forest(), ix.export_forest()
+    assert fa.nodes.shape[0] > forest.nodes.shape[0]            # leaves were split
+    for f in ("roots", "nodes", "cst", "coef"):
+        assert np.array_equal(getattr(fa, f), getattr(fb, f)), f
+    queries = np.concatenate([rows[:40], more[:40]])
+    k, d, l = ix.hash(queries)
+    ek, ed, el = orc.hash(queries)
+    assert np.array_equal(k, ek) and np.array_equal(d, ed) and np.array_equal(l, el) and d.max() > K
+    assert_search_equal(ix, orc, queries, 10)
+
+
+def test_load_flat_argument_checks():
+    z = zb()
+    ix = z.LSHIndex(16, z.LSHIndexOptions(5, 2), z.L2Distance())
+    rows = np.zeros((4, 16), F32)
+    with pytest.raises(z.ZebraError):
+        ix.load_flat(rows, 17, np.zeros((34, 16), F32), np.zeros(34, F32))      # bits out of range
+    with pytest.raises(ValueError):
+        ix.load_flat(rows, 3, np.zeros((5, 16), F32), np.zeros(5, F32))          # not num_trees * bits planes
+    ix.load_flat(np.zeros((0, 16), F32), 2, np.ones((4, 16), F32), np.zeros(4, F32))   # empty table set
+    assert ix.no_vectors()

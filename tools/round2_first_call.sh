@@ -1,0 +1,25 @@
+#!/bin/bash
+# First GPU call of the next round: the flat-table path (project_flat_kernel, zb_index_load_flat) was committed at the end of
+# round 1 WITHOUT a GPU run (budget spent).  Parity first, then its hashing throughput at H = 16 / 128 / 240 planes per row
+#  next to the tree-forest walker, then one ncu capture of the projection kernel.
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 200 python -m pytest tests/test_zz_flat_tables_gpu.py -q --durations=5 > $OUT/r02a_flat_tests.log 2>&1; echo "flat tests rc=$?" >> $OUT/r02a_flat_tests.log
+tail -12 $OUT/r02a_flat_tests.log
+for cfg in "16 1" "16 8" "16 15"; do
+  set -- $cfg
+  timeout 150 python bench.py --workload hash --flat-bits $1 --trees $2 --steps 5 --warmup 3 --cpu-seconds 3 > $OUT/r02a_bench_hash_flat_K$1_T$2.json 2>> $OUT/r02a.err; echo "flat K=$1 T=$2 rc=$?"
+done
+timeout 150 python bench.py --workload hash --steps 5 --warmup 3 --cpu-seconds 3 > $OUT/r02a_bench_hash_forest.json 2>> $OUT/r02a.err
+ncu --set full --clock-control none --import-source on -k regex:project_flat_kernel -s 3 -c 1 -f -o $OUT/project_r02a \
+    python bench.py --workload hash --flat-bits 16 --trees 8 --steps 2 --warmup 3 --no-cpu-baseline > $OUT/project_r02a.log 2>&1
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/r02a_bench_hash_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, d["value"], d["unit"], d["ms_per_step"], d["roofline"]["frac"], d.get("parity_sample_ok"), {k: d.get(k, d.get("config", {}).get(k)) for k in ("planes_per_row", "fp32_tflops")})
+    except Exception as e:
+        print(f, "unreadable", e)
+PY

@@ -102,6 +102,11 @@ struct zb_index {
     std::vector<u32> h_members;
     bool h_members_valid = false;
     bool built = false;
+    // flat tables (zb_index_load_flat): every node at depth d of tree t uses plane t * flat_bits + d, so hashing is a dense
+    // projection (zb_project.cuh).  Valid while the forest is the one that was loaded (a leaf split adds nodes).
+    u32 flat_bits = 0;
+    size_t flat_nodes = 0;
+    DBuf<u8> pj_sign;
     DBuf<int4> d_nodes;
     DBuf<int> d_roots;
     DBuf<float> d_coef, d_cst;
@@ -155,7 +160,7 @@ struct zb_index {
     ScanWorkspace scan_ws;
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1;
     zb_stats st{};
 
     ForestView view() const {
@@ -1379,6 +1384,8 @@ int zb_index_clear(zb_index* ix) {
     ix->n_slots = ix->n_live = ix->total_rows = 0;
     ix->h_ord.clear();
     ix->h_tomb.clear();
+    ix->flat_bits = 0;
+    ix->flat_nodes = 0;
     ix->ids_by_ordinal.clear();
     ix->ordinal_by_id.clear();
     ix->id_mode = 0;
@@ -1477,7 +1484,16 @@ int zb_index_hash_device(zb_index* ix, uint64_t n, const float* d_rows, uint64_t
         launch_pad_rows(d_rows, n, ix->dim, ix->dimp, ix->r_stage.p, ix->stream);
         x = ix->r_stage.p;
     }
-    launch_hash(ix->view(), x, n, (u64*)d_keys, d_depths, d_leaves, (int)ix->p_hash_variant, ix->stream);
+    const bool flat = ix->flat_bits && ix->p_flat_project && ix->h_nodes.size() == ix->flat_nodes &&
+                      ix->n_planes == (u64)ix->T * ix->flat_bits;
+    if (flat) {  // every row asks the same T x K planes: one dense pass, sign bits packed into the keys
+        const int H = ix->T * (int)ix->flat_bits, Hp = (H + 15) / 16 * 16;
+        ix->pj_sign.ensure(std::max<u64>(1, n * (u64)Hp));
+        launch_project_flat(x, n, ix->d_coef.p, ix->d_cst.p, H, ix->dimp, ix->pj_sign.p, Hp, ix->stream);
+        launch_pack_flat_keys(ix->pj_sign.p, n, Hp, ix->T, (int)ix->flat_bits, (u64*)d_keys, d_depths, d_leaves, ix->stream);
+    } else {
+        launch_hash(ix->view(), x, n, (u64*)d_keys, d_depths, d_leaves, (int)ix->p_hash_variant, ix->stream);
+    }
     if (d_leaves) {
         if (!ix->export_table_valid) {
             std::vector<int> table;
@@ -1683,6 +1699,81 @@ int zb_index_load_forest(zb_index* ix, uint64_t n, const float* rows, const uint
     ZB_API_END
 }
 
+static void pad_to_device(int device, const float* h, u64 n, u32 dim, int dimp, DBuf<float>& d);
+
+// Flat tables.  coef = T * bits planes of dim f32 (table t, bit d at index t * bits + d), cst = their constants.
+int zb_index_load_flat(zb_index* ix, uint64_t n, const float* rows, const uint8_t* ids16, uint32_t bits, const float* coef,
+                       const float* cst) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (rows || !n) && coef && cst, ZB_ERR_INVALID, "NULL argument");
+    ZB_REQUIRE(bits >= 1 && bits <= 16, ZB_ERR_INVALID, "bits %u out of range 1..16", bits);
+    ZB_REQUIRE(n < (1ull << 32), ZB_ERR_INVALID, "too many rows for one load");
+    int T, dim, dimp;
+    {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        ix->use_device();
+        T = ix->T; dim = ix->dim; dimp = ix->dimp;
+    }
+    const int K = (int)bits, H = T * K, Hp = (H + 15) / 16 * 16;
+    // ---- bucket keys of every row: the dense projection (legacy stream: ordered after the staging copies) ----
+    std::vector<u64> keys((size_t)n * T + 1);
+    {
+        DBuf<float> d_rows, d_coef, d_cst;
+        DBuf<u8> d_sign;
+        DBuf<u64> d_keys;
+        pad_to_device(ix->device, rows, n, (u32)dim, dimp, d_rows);
+        pad_to_device(ix->device, coef, (u64)H, (u32)dim, dimp, d_coef);
+        d_cst.ensure((size_t)H);
+        ZB_CUDA(cudaMemcpy(d_cst.p, cst, (size_t)H * 4, cudaMemcpyHostToDevice));
+        d_sign.ensure(std::max<u64>(1, n * (u64)Hp));
+        d_keys.ensure((size_t)n * T + 1);
+        launch_project_flat(d_rows.p, n, d_coef.p, d_cst.p, H, dimp, d_sign.p, Hp, 0);
+        launch_pack_flat_keys(d_sign.p, n, Hp, T, K, d_keys.p, nullptr, nullptr, 0);
+        ZB_CUDA(cudaGetLastError());
+        if (n) ZB_CUDA(cudaMemcpy(keys.data(), d_keys.p, (size_t)n * T * 8, cudaMemcpyDeviceToHost));
+    }
+    // ---- the equivalent forest: T complete trees of depth K in preorder (node, left = below = bit 0, right = above) ----
+    const int64_t per_tree = ((int64_t)2 << K) - 1, leaves_per_tree = (int64_t)1 << K;
+    int64_t sizes4[4] = {per_tree * T, (int64_t)H, leaves_per_tree * T, (int64_t)n * T};
+    std::vector<int32_t> nodes((size_t)sizes4[0] * 4), roots((size_t)T);
+    for (int t = 0; t < T; ++t) {
+        int32_t idx = (int32_t)(per_tree * t);
+        roots[t] = idx;
+        struct Fr { int depth; u32 prefix; int32_t parent; int side; };
+        std::vector<Fr> stack{{0, 0u, -1, 0}};
+        while (!stack.empty()) {
+            const Fr fr = stack.back();
+            stack.pop_back();
+            const int32_t me = idx++;
+            if (fr.parent >= 0) nodes[4 * (size_t)fr.parent + 1 + fr.side] = me;
+            int32_t* nd = nodes.data() + 4 * (size_t)me;
+            if (fr.depth == K) {
+                nd[0] = -1; nd[1] = -1; nd[2] = -1; nd[3] = (int32_t)(leaves_per_tree * t + fr.prefix);
+            } else {
+                nd[0] = t * K + fr.depth; nd[1] = -1; nd[2] = -1; nd[3] = -1;
+                stack.push_back({fr.depth + 1, (fr.prefix << 1) | 1u, me, 1});  // right subtree after ...
+                stack.push_back({fr.depth + 1, fr.prefix << 1, me, 0});         // ... the left one (preorder)
+            }
+        }
+    }
+    std::vector<int64_t> leaf_off((size_t)sizes4[2] + 1, 0);
+    for (u64 o = 0; o < n; ++o)
+        for (int t = 0; t < T; ++t) leaf_off[(size_t)(leaves_per_tree * t + (int64_t)keys[o * T + t]) + 1]++;
+    for (size_t l = 0; l < (size_t)sizes4[2]; ++l) leaf_off[l + 1] += leaf_off[l];
+    std::vector<int64_t> cursor(leaf_off.begin(), leaf_off.end() - 1);
+    std::vector<uint64_t> members((size_t)n * T + 1);
+    for (u64 o = 0; o < n; ++o)  // ascending ordinal inside a leaf
+        for (int t = 0; t < T; ++t) members[(size_t)cursor[(size_t)(leaves_per_tree * t + (int64_t)keys[o * T + t])]++] = o;
+    int rc = zb_index_load_forest(ix, n, rows, ids16, sizes4, nodes.data(), roots.data(), coef, cst, leaf_off.data(), members.data());
+    if (rc != ZB_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        ix->flat_bits = bits;
+        ix->flat_nodes = ix->h_nodes.size();
+    }
+    ZB_API_END
+}
+
 int zb_index_options(zb_index* ix, zb_options* out) {
     ZB_API_BEGIN
     ZB_REQUIRE(ix && out, ZB_ERR_INVALID, "NULL argument");
@@ -1745,6 +1836,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "use_tile_scan") ix->p_use_tile_scan = value;
     else if (k == "classify_variant") ix->p_classify_variant = value;  // 0: rows gathered through L1; 1: rows staged by TMA bulk copies
     else if (k == "seq_prefetch") ix->p_seq_prefetch = value;  // scalar metrics: L2 prefetch distance of the row stream in 128-byte lines (0 = off, the default: measured slower)
+    else if (k == "flat_project") ix->p_flat_project = value;  // flat tables: 1 = dense projection + ballot packing (default), 0 = the generic tree walk
     else if (k == "seq_tile") ix->p_seq_tile = value;          // scalar metrics: 1 = leaf-tile scan (default), 0 = one thread per pair
     else if (k == "hash_variant") ix->p_hash_variant = value;  // 0: quad per (row, tree), rows through L1; 1: row staged in shared memory
     else if (k == "visit_slots") {  // initial per-walker capacity of the visit plan (tests force the grow-and-replan path)

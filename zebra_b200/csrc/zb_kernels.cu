@@ -665,6 +665,84 @@ void launch_hash(const ForestView& f, const float* d_rows, u64 n, u64* d_keys, u
 }
 
 // =====================================================================================================
+// hash of FLAT tables (zb_project.cuh): dense projection rows x planes in the canonical order, then the K sign bits of
+// every table packed into its bucket key with __ballot_sync.
+// CTA = 32 quads = 8 row groups x 4 plane groups, quad tile 4 rows x 4 planes: CTA tile 32 rows x 16 planes.  Both
+// operands come through L1 (__ldg): the 4 plane groups of a CTA re-read the same 32 rows, its 8 row groups the same 16
+// planes.  Per thread and 16-float chunk: 8 128-bit loads feed 64 fused multiply-adds.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) project_flat_kernel(const float* __restrict__ rows, u64 n, const float* __restrict__ coef,
+                                                           const float* __restrict__ cst, int H, int dimp, int chunks,
+                                                           u8* __restrict__ sign, int Hp) {
+    const int quad = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    const u64 row0 = (u64)blockIdx.x * 32ull + (u64)(quad >> 2) * ZB_PJ_R;
+    const int pl0 = (int)blockIdx.y * 16 + (quad & 3) * ZB_PJ_P;
+    const float4* xr[ZB_PJ_R];
+    const float4* pp[ZB_PJ_P];
+#pragma unroll
+    for (int i = 0; i < ZB_PJ_R; ++i) {  // tails: clamp the loads, mask the stores
+        const u64 r = row0 + i < n ? row0 + i : n - 1;
+        xr[i] = reinterpret_cast<const float4*>(rows + (size_t)r * dimp) + sub;
+    }
+#pragma unroll
+    for (int j = 0; j < ZB_PJ_P; ++j) {
+        const int h = pl0 + j < H ? pl0 + j : H - 1;
+        pp[j] = reinterpret_cast<const float4*>(coef + (size_t)h * dimp) + sub;
+    }
+    PjAcc acc;
+    pj_init(acc);
+#pragma unroll 2
+    for (int c = 0; c < chunks; ++c) {
+        float4 x[ZB_PJ_R], p[ZB_PJ_P];
+#pragma unroll
+        for (int i = 0; i < ZB_PJ_R; ++i) x[i] = __ldg(xr[i] + c * 4);
+#pragma unroll
+        for (int j = 0; j < ZB_PJ_P; ++j) p[j] = __ldg(pp[j] + c * 4);
+        pj_chunk(acc, x, p);
+    }
+#pragma unroll
+    for (int i = 0; i < ZB_PJ_R; ++i) {
+#pragma unroll
+        for (int j = 0; j < ZB_PJ_P; ++j) {
+            const float d = quad_reduce16(acc.a[i][j], mask);  // every thread of the quad takes part
+            if (sub == 0 && row0 + i < n && pl0 + j < H)
+                sign[(size_t)(row0 + i) * Hp + pl0 + j] = above_from_dot(d, __ldg(cst + pl0 + j)) ? 1 : 0;
+        }
+    }
+}
+// One warp per row: lane l holds the sign of plane t K + l (and of plane t K + 32 + l); the ballot IS the key, up to the
+// bit order (MSB = plane 0 = the root decision).  leaf = the complete tree's leaf, t 2^K + key.
+__global__ void __launch_bounds__(128) pack_flat_keys_kernel(const u8* __restrict__ sign, u64 n, int Hp, int T, int K,
+                                                             u64* __restrict__ keys, u32* __restrict__ depths, int* __restrict__ leaves) {
+    const u64 r = (u64)blockIdx.x * 4ull + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;  // whole warps leave together
+    const u8* s = sign + (size_t)r * Hp;
+    for (int t = 0; t < T; ++t) {
+        const unsigned b0 = __ballot_sync(0xffffffffu, lane < K && s[t * K + lane] != 0);
+        const unsigned b1 = __ballot_sync(0xffffffffu, 32 + lane < K && s[t * K + 32 + lane] != 0);
+        if (lane == 0) {
+            const u64 key = K <= 32 ? (u64)(__brev(b0) >> (32 - K)) : (((u64)__brev(b0) << (K - 32)) | (u64)(__brev(b1) >> (64 - K)));
+            const u64 w = r * (u64)T + t;
+            if (keys) keys[w] = key;
+            if (depths) depths[w] = (u32)K;
+            if (leaves) leaves[w] = (int)(((u64)t << K) + key);
+        }
+    }
+}
+void launch_project_flat(const float* d_rows, u64 n, const float* d_coef, const float* d_cst, int H, int dimp, u8* d_sign, int Hp,
+                         cudaStream_t s) {
+    if (!n || !H) return;
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((H + 15) / 16));
+    project_flat_kernel<<<grid, 128, 0, s>>>(d_rows, n, d_coef, d_cst, H, dimp, dimp / 16, d_sign, Hp);
+}
+void launch_pack_flat_keys(const u8* d_sign, u64 n, int Hp, int T, int K, u64* d_keys, u32* d_depths, int* d_leaves, cudaStream_t s) {
+    if (!n) return;
+    pack_flat_keys_kernel<<<(unsigned)((n + 3) / 4), 128, 0, s>>>(d_sign, n, Hp, T, K, d_keys, d_depths, d_leaves);
+}
+
+// =====================================================================================================
 // build (lsh.rs:192-267), level synchronous.  The host keeps the list of nodes under construction
 // ("segments" of a work array of slots); per level:
 //   pick      two member rows per segment by seeded min-hash (D2)                    phases 0,1,2

@@ -5,6 +5,7 @@
 
 #include "zb_device.cuh"
 #include "zb_metrics.cuh"
+#include "zb_project.cuh"
 
 namespace zb {
 
@@ -101,6 +102,10 @@ void launch_iota_ord(u64* d, u64 n, u64 first, u64 stride, cudaStream_t s);
 void launch_synth(float* d_out, u64 first_row, u64 row_stride, u64 n, u32 dim, u64 seed, u32 kind, cudaStream_t s);
 
 void launch_sq_norms(const float* d_x, u64 n, int dimp, float* d_out, cudaStream_t s);
+// Flat tables: sign[n][Hp] = point_is_above of every (row, plane); then the K bits of each of T tables -> key / depth / leaf.
+void launch_project_flat(const float* d_rows, u64 n, const float* d_coef, const float* d_cst, int H, int dimp, u8* d_sign, int Hp,
+                         cudaStream_t s);
+void launch_pack_flat_keys(const u8* d_sign, u64 n, int Hp, int T, int K, u64* d_keys, u32* d_depths, int* d_leaves, cudaStream_t s);
 void launch_pair_metric(int metric, int power, const float* d_a, const float* d_b, u64 n, int dim, int dimp, u64* d_out,
                         cudaStream_t s);
 void launch_pair_above(const float* d_coef, const float* d_cst, const float* d_x, u64 n, int dimp, u8* d_out, cudaStream_t s);

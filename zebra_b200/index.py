@@ -233,6 +233,19 @@ class LSHIndex:
                                                    f.nodes.ctypes.data, f.roots.ctypes.data, f.coef.ctypes.data,
                                                    f.cst.ctypes.data, f.leaf_off.ctypes.data, f.members.ctypes.data))
 
+    def load_flat(self, rows, bits: int, coef, cst, ids: Optional[Sequence] = None) -> None:
+        """FLAT tables (the K-bit LSH table of north_star (a)): every node at depth d of tree t shares plane
+        ``coef[t * bits + d]``.  The rows are bucketed by one dense projection on the device (sign bits packed into the keys
+        with __ballot_sync); the index then holds the equivalent forest of complete trees."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, self.dim)
+        h = self.options.num_trees * int(bits)
+        coef = np.ascontiguousarray(coef, dtype=np.float32).reshape(h, self.dim)
+        cst = np.ascontiguousarray(cst, dtype=np.float32).reshape(h)
+        idb = _ids_to_bytes(ids) if ids is not None else None
+        _ffi.check(_ffi.lib().zb_index_load_flat(self._h, rows.shape[0], rows.ctypes.data,
+                                                 idb.ctypes.data if idb is not None else None, int(bits), coef.ctypes.data,
+                                                 cst.ctypes.data))
+
     # ---------------------------------------------------------------- the reference's stored values (SURVEY 8f row 4)
     def import_store(self, ids: Sequence, embeddings, tree_blobs: Sequence[bytes]) -> dict:
         """Replace the index content with a reference store: the (key, value) pairs of the `embeddings` partition

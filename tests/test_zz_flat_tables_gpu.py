@@ -3,8 +3,8 @@
 with the reference's own tree walk.  Keys, depths, leaves, the exported forest, and search results must be bit-identical,
 and the dense path must agree with the generic tree walker of the same index (knob flat_project = 0).
 
-NOT YET RUN ON A GPU when it was committed (the round's GPU budget was spent): it sorts last so that a failure here
-cannot hide the rest of the suite."""
+First run on a B200 with the last seconds of round 1's GPU budget (6 passed; throughput is measured by
+tools/round2_first_call.sh)."""
 import numpy as np
 import pytest
 

@@ -1,7 +1,8 @@
 #!/bin/bash
-# First GPU call of the next round: the flat-table path (project_flat_kernel, zb_index_load_flat) was committed at the end of
-# round 1 WITHOUT a GPU run (budget spent).  Parity first, then its hashing throughput at H = 16 / 128 / 240 planes per row
-#  next to the tree-forest walker, then one ncu capture of the projection kernel.
+# First GPU call of the next round: the flat-table path (project_flat_kernel, zb_index_load_flat) passed its parity tests at
+# the very end of round 1 but its throughput was never measured (budget spent).  Parity again, then its hashing throughput
+# at H = 16 / 128 / 240 planes per row next to the tree-forest walker, then one ncu capture of the
+# projection kernel.
 set -u
 OUT=gpurun_out
 mkdir -p $OUT

@@ -84,3 +84,15 @@ def test_invalid_arguments_are_reported():
     o.metric_power = -1
     assert lib.zb_index_create(C.byref(o), C.byref(h)) == -1
     assert lib.zb_index_destroy(None) == 0
+    # every entry point added with ABI v2 checks its arguments before it touches a device
+    u = C.c_uint64()
+    assert lib.zb_index_load_flat(None, 0, None, None, 4, None, None) == -1
+    assert lib.zb_index_export_rows(None, 0, 0, None, None, None) == -1
+    assert lib.zb_index_export_tree_blob(None, 0, None, 0, C.byref(u)) == -1
+    assert lib.zb_index_options(None, None) == -1
+    assert lib.zb_tree_blob_decode(0, None, 0, None, None, None, None, None, None) == -1
+    assert lib.zb_store_flatten(4, 0, None, 0, None, None, None, None) == -1
+    assert lib.zb_flat_store_free(None) == 0
+    assert lib.zb_zebra_file_encode(None, 0, 0, 5, 15, None, 0, C.byref(u)) == -1
+    assert lib.zb_metric_distance_batch(0, 12, 0, 0, 16, None, None, None) == -1          # not a zb_metric
+    assert lib.zb_metric_distance_batch(0, 10, 65, 0, 16, None, None, None) == -1         # Minkowski power out of range

@@ -227,6 +227,9 @@ int zb_index_export_rows(zb_index* index, uint64_t first_ordinal, uint64_t n, fl
                          uint8_t* out_live);
 /* Tree `tree` as the reference's blob; removed rows are left out of the leaves.  out may be NULL. */
 int zb_index_export_tree_blob(zb_index* index, uint32_t tree, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
+/* All trees with ONE export of the forest: the blobs back to back in out (NULL: size query), out_blob_bytes[t] = size of
+ * tree t (num_trees entries), *out_total = their sum. */
+int zb_index_export_tree_blobs(zb_index* index, uint8_t* out, uint64_t cap, uint64_t* out_blob_bytes, uint64_t* out_total);
 
 /* FLAT tables: the special case of the reference's tree (lsh.rs:46-60) in which every node at depth d of tree t shares
  * one hyperplane -- the K-bit LSH table of north_star (a).  coef = num_trees * bits planes of dim f32 (table t, bit d

@@ -356,13 +356,16 @@ class LSHIndex {
     }
     /// Every tree as the bincode(legacy) Node<N> value the reference stores (lsh.rs:99-105).
     std::vector<Bytes> export_tree_blobs() const {
+        std::vector<uint64_t> sizes(options_.num_trees + 1, 0);
+        uint64_t total = 0;
+        check(zb_index_export_tree_blobs(raw(), nullptr, 0, sizes.data(), &total));  // one forest export for all trees
+        Bytes all(total + 1);
+        check(zb_index_export_tree_blobs(raw(), all.data(), total, sizes.data(), &total));
         std::vector<Bytes> out;
-        for (uint32_t t = 0; t < options_.num_trees; ++t) {
-            uint64_t need = 0;
-            check(zb_index_export_tree_blob(raw(), t, nullptr, 0, &need));
-            Bytes b(need);
-            check(zb_index_export_tree_blob(raw(), t, b.data(), need, &need));
-            out.push_back(std::move(b));
+        uint64_t at = 0;
+        for (size_t t = 0; t < options_.num_trees; ++t) {
+            out.emplace_back(all.begin() + (std::ptrdiff_t)at, all.begin() + (std::ptrdiff_t)(at + sizes[t]));
+            at += sizes[t];
         }
         return out;
     }

@@ -17,15 +17,81 @@ namespace zb {
 thread_local std::string t_last_error;
 size_t g_device_bytes = 0;
 }
+// A canned 2-tree forest over 5 rows (row 3 removed) behind the handle FAKE, so the export entry points can be driven on the
+// CPU: tree 0 = Inner(plane 0, Leaf[0,1], Inner(plane 1, Leaf[2,3], Leaf[4])), tree 1 = Leaf[0..4].  dim = 2.
+static zb_index* const FAKE = reinterpret_cast<zb_index*>(0x1);
+static const int32_t F_NODES[] = {0, 1, 2, -1, -1, -1, -1, 0, 1, 3, 4, -1, -1, -1, -1, 1, -1, -1, -1, 2, -1, -1, -1, 3};
+static const int32_t F_ROOTS[] = {0, 5};
+static const float F_COEF[] = {1.f, -1.f, 0.5f, 2.f}, F_CST[] = {0.25f, -3.f};
+static const int64_t F_LEAF_OFF[] = {0, 2, 4, 5, 10};
+static const uint64_t F_MEMBERS[] = {0, 1, 2, 3, 4, 0, 1, 2, 3, 4};
 extern "C" {
 const char* zb_last_error(void) { return zb::t_last_error.c_str(); }
-int zb_index_options(zb_index*, zb_options*) { return ZB_ERR_NO_DEVICE; }
+int zb_index_options(zb_index* ix, zb_options* o) {
+    if (ix != FAKE) return ZB_ERR_NO_DEVICE;
+    memset(o, 0, sizeof *o);
+    o->dim = 2;
+    o->num_trees = 2;
+    return ZB_OK;
+}
 int zb_index_load_forest(zb_index*, uint64_t, const float*, const uint8_t*, const int64_t*, const int32_t*, const int32_t*, const float*,
                          const float*, const int64_t*, const uint64_t*) { return ZB_ERR_NO_DEVICE; }
-int zb_index_forest_sizes(zb_index*, int64_t*) { return ZB_ERR_NO_DEVICE; }
-int zb_index_export_forest(zb_index*, int32_t*, int32_t*, float*, float*, int64_t*, uint64_t*) { return ZB_ERR_NO_DEVICE; }
-int zb_index_stats(zb_index*, zb_stats*) { return ZB_ERR_NO_DEVICE; }
-int zb_index_export_rows(zb_index*, uint64_t, uint64_t, float*, uint8_t*, uint8_t*) { return ZB_ERR_NO_DEVICE; }
+int zb_index_forest_sizes(zb_index* ix, int64_t* s) {
+    if (ix != FAKE) return ZB_ERR_NO_DEVICE;
+    s[0] = 6; s[1] = 2; s[2] = 4; s[3] = 10;
+    return ZB_OK;
+}
+int zb_index_export_forest(zb_index* ix, int32_t* nodes, int32_t* roots, float* coef, float* cst, int64_t* leaf_off, uint64_t* members) {
+    if (ix != FAKE) return ZB_ERR_NO_DEVICE;
+    memcpy(nodes, F_NODES, sizeof F_NODES); memcpy(roots, F_ROOTS, sizeof F_ROOTS); memcpy(coef, F_COEF, sizeof F_COEF);
+    memcpy(cst, F_CST, sizeof F_CST); memcpy(leaf_off, F_LEAF_OFF, sizeof F_LEAF_OFF); memcpy(members, F_MEMBERS, sizeof F_MEMBERS);
+    return ZB_OK;
+}
+int zb_index_stats(zb_index* ix, zb_stats* st) {
+    if (ix != FAKE) return ZB_ERR_NO_DEVICE;
+    memset(st, 0, sizeof *st);
+    st->total_rows = 5;
+    return ZB_OK;
+}
+int zb_index_export_rows(zb_index* ix, uint64_t first, uint64_t n, float*, uint8_t* ids, uint8_t* live) {
+    if (ix != FAKE || first != 0 || n != 5) return ZB_ERR_NO_DEVICE;
+    for (uint64_t i = 0; i < n; ++i) {
+        memset(ids + 16 * i, 0, 16);
+        ids[16 * i + 15] = (uint8_t)(0xA0 + i);
+        live[i] = i != 3;
+    }
+    return ZB_OK;
+}
+}
+
+static int check_exports() {
+    // expected: the same forest with row 3 left out, encoded tree by tree with the pure encoder
+    const int64_t leaf_off[] = {0, 2, 3, 4, 8};
+    uint8_t ids[8 * 16] = {0};
+    const int who[] = {0, 1, 2, 4, 0, 1, 2, 4};
+    for (int j = 0; j < 8; ++j) ids[16 * j + 15] = (uint8_t)(0xA0 + who[j]);
+    std::vector<uint8_t> want[2], all;
+    for (int t = 0; t < 2; ++t) {
+        want[t].resize(1024);
+        uint64_t need = 0;
+        if (zb_tree_blob_encode(2, 6, F_NODES, F_ROOTS[t], F_COEF, F_CST, leaf_off, ids, want[t].data(), want[t].size(), &need) != ZB_OK) return 1;
+        want[t].resize(need);
+        all.insert(all.end(), want[t].begin(), want[t].end());
+        uint64_t got_need = 0;
+        if (zb_index_export_tree_blob(FAKE, (uint32_t)t, nullptr, 0, &got_need) != ZB_OK || got_need != need) return 2;
+        std::vector<uint8_t> got(need);
+        if (zb_index_export_tree_blob(FAKE, (uint32_t)t, got.data(), need, &got_need) != ZB_OK || got != want[t]) return 3;
+        if (zb_index_export_tree_blob(FAKE, (uint32_t)t, got.data(), need - 1, &got_need) != ZB_ERR_INVALID) return 4;   // short buffer
+    }
+    uint64_t sizes[2] = {0, 0}, total = 0;
+    if (zb_index_export_tree_blobs(FAKE, nullptr, 0, sizes, &total) != ZB_OK || total != all.size() || sizes[0] != want[0].size() ||
+        sizes[1] != want[1].size()) return 5;
+    std::vector<uint8_t> got(total);
+    if (zb_index_export_tree_blobs(FAKE, got.data(), total, sizes, &total) != ZB_OK || got != all) return 6;
+    if (zb_index_export_tree_blobs(FAKE, got.data(), total - 3, sizes, &total) != ZB_ERR_INVALID) return 7;
+    uint64_t one = 0;
+    if (zb_index_export_tree_blob(FAKE, 2, nullptr, 0, &one) != ZB_ERR_INVALID) return 8;                                 // no such tree
+    return 0;
 }
 
 static uint64_t state = 0x9E3779B97F4A7C15ull;
@@ -62,6 +128,10 @@ static void gen_tree(std::vector<uint8_t>& out, uint32_t dim, int depth, uint32_
 
 int main(int argc, char** argv) {
     const int iters = argc > 1 ? atoi(argv[1]) : 20000;
+    if (int rc = check_exports()) {
+        std::printf("export of the canned forest failed at check %d: %s\n", rc, zb_last_error());
+        return 1;
+    }
     long ok = 0, rejected = 0;
     for (int it = 0; it < iters; ++it) {
         const uint32_t dim = 1 + rnd() % 6, nid = rnd() % 24;

@@ -89,6 +89,7 @@ def test_invalid_arguments_are_reported():
     assert lib.zb_index_load_flat(None, 0, None, None, 4, None, None) == -1
     assert lib.zb_index_export_rows(None, 0, 0, None, None, None) == -1
     assert lib.zb_index_export_tree_blob(None, 0, None, 0, C.byref(u)) == -1
+    assert lib.zb_index_export_tree_blobs(None, None, 0, None, C.byref(u)) == -1
     assert lib.zb_index_options(None, None) == -1
     assert lib.zb_tree_blob_decode(0, None, 0, None, None, None, None, None, None) == -1
     assert lib.zb_store_flatten(4, 0, None, 0, None, None, None, None) == -1

@@ -46,7 +46,7 @@ def test_export_matches_oracle_codec_and_round_trips(tmp_path):
     # every tree blob == the oracle-side encoder applied to the exported forest (removed rows left out of the leaves)
     blobs = ix.export_tree_blobs()
     want = zbc.forest_to_nodes(ix.export_forest(), id_list, live)
-    assert len(blobs) == 5
+    assert len(blobs) == 5 and ix.export_tree_blob(3) == blobs[3]            # per-tree entry point agrees
     for t in range(5):
         assert blobs[t] == zbc.encode_node(want[t]), t
         assert zbc.nodes_equal(zbc.decode_node(blobs[t], dim), want[t])

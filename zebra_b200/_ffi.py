@@ -120,6 +120,7 @@ SYMBOLS = {
     "zb_index_import_store": (C.c_int, [_vp, _u64, _vp, _vp, _u32, _vp, _vp, C.POINTER(ImportReport), _vp, _u64]),
     "zb_index_export_rows": (C.c_int, [_vp, _u64, _u64, _vp, _vp, _vp]),
     "zb_index_export_tree_blob": (C.c_int, [_vp, _u32, _vp, _u64, C.POINTER(_u64)]),
+    "zb_index_export_tree_blobs": (C.c_int, [_vp, _vp, _u64, _vp, C.POINTER(_u64)]),
     "zb_index_load_flat": (C.c_int, [_vp, _u64, _vp, _vp, _u32, _vp, _vp]),
     "zb_index_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "zb_index_stream": (C.c_int, [_vp, C.POINTER(_vp)]),

@@ -1573,18 +1573,37 @@ int zb_index_export_forest(zb_index* ix, int32_t* nodes, int32_t* roots, float* 
     for (size_t i = 0; i < order.size(); ++i) newid[order[i]] = (int)i;
     int64_t np = 0, nl = 0, nm = 0;
     leaf_off[0] = 0;
+    std::vector<int64_t> plane_pos(order.size(), -1);  // where inner node i's plane goes in the output
     for (size_t i = 0; i < order.size(); ++i) {
         int4 nd = ix->h_nodes[order[i]];
         if (nd.x >= 0) {
-            ZB_CUDA(cudaMemcpy2D(coef + np * ix->dim, (size_t)ix->dim * 4, ix->d_coef.p + (u64)nd.x * ix->dimp, (size_t)ix->dimp * 4,
-                                 (size_t)ix->dim * 4, 1, cudaMemcpyDeviceToHost));
-            ZB_CUDA(cudaMemcpy(cst + np, ix->d_cst.p + nd.x, 4, cudaMemcpyDeviceToHost));
+            ZB_REQUIRE((u64)nd.x < ix->n_planes, ZB_ERR_STATE, "plane %d out of range", nd.x);
+            plane_pos[i] = np;
             nodes[4 * i + 0] = (int)np++; nodes[4 * i + 1] = newid[nd.y]; nodes[4 * i + 2] = newid[nd.z]; nodes[4 * i + 3] = -1;
         } else {
             const int l = nd.w;
             for (u32 j = 0; j < ix->h_leaf_len[l]; ++j) members[nm++] = ix->h_ord[ix->h_members[ix->h_leaf_off[l] + j]];
             leaf_off[++nl] = nm;
             nodes[4 * i + 0] = -1; nodes[4 * i + 1] = -1; nodes[4 * i + 2] = -1; nodes[4 * i + 3] = (int)(nl - 1);
+        }
+    }
+    // planes: the device array comes over in chunks of <= 256 MB and every inner node picks its plane out of the chunk
+    // (one copy per inner node cost ~10 us each: minutes for a default forest over 1M rows)
+    const u64 chunk = std::max<u64>(1, (256ull << 20) / ((u64)ix->dim * 4));
+    std::vector<float> h_coef, h_cst;
+    for (u64 p0 = 0; p0 < ix->n_planes; p0 += chunk) {
+        const u64 cnt = std::min<u64>(chunk, ix->n_planes - p0);
+        h_coef.resize((size_t)cnt * ix->dim);
+        h_cst.resize((size_t)cnt);
+        ZB_CUDA(cudaMemcpy2D(h_coef.data(), (size_t)ix->dim * 4, ix->d_coef.p + p0 * (u64)ix->dimp, (size_t)ix->dimp * 4,
+                             (size_t)ix->dim * 4, cnt, cudaMemcpyDeviceToHost));
+        ZB_CUDA(cudaMemcpy(h_cst.data(), ix->d_cst.p + p0, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < order.size(); ++i) {
+            if (plane_pos[i] < 0) continue;
+            const u64 pl = (u64)ix->h_nodes[order[i]].x;
+            if (pl < p0 || pl >= p0 + cnt) continue;
+            memcpy(coef + plane_pos[i] * ix->dim, h_coef.data() + (size_t)(pl - p0) * ix->dim, (size_t)ix->dim * 4);
+            cst[plane_pos[i]] = h_cst[(size_t)(pl - p0)];
         }
     }
     for (int t = 0; t < ix->T; ++t) roots[t] = newid[ix->h_roots[t]];

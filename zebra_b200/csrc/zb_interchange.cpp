@@ -454,22 +454,31 @@ int zb_index_import_store(zb_index* index, uint64_t n, const uint8_t* ids16, con
     ZB_API_END
 }
 
-int zb_index_export_tree_blob(zb_index* index, uint32_t tree, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
-    ZB_API_BEGIN
-    ZB_REQUIRE(index && out_bytes, ZB_ERR_INVALID, "NULL argument");
+}  // extern "C"
+
+namespace {
+// The forest as flat arrays with member ids and live flags: what both export entry points encode from.
+struct Exported {
     zb_options opt;
-    int rc = zb_index_options(index, &opt);
-    if (rc != ZB_OK) return rc;
-    ZB_REQUIRE(tree < opt.num_trees, ZB_ERR_INVALID, "tree %u out of range (%u trees)", tree, opt.num_trees);
     int64_t s[4] = {0, 0, 0, 0};
-    rc = zb_index_forest_sizes(index, s);
+    std::vector<int32_t> nodes, roots;
+    std::vector<float> coef, cst;
+    std::vector<int64_t> leaf_off;
+    std::vector<uint8_t> mid, keep;
+};
+int export_forest_with_ids(zb_index* index, Exported& e) {
+    int rc = zb_index_options(index, &e.opt);
     if (rc != ZB_OK) return rc;
-    ZB_REQUIRE(s[0] >= 1, ZB_ERR_STATE, "the index has no trees yet");
-    std::vector<int32_t> nodes((size_t)s[0] * 4), roots(opt.num_trees);
-    std::vector<float> coef((size_t)std::max<int64_t>(1, s[1]) * opt.dim), cst((size_t)std::max<int64_t>(1, s[1]));
-    std::vector<int64_t> leaf_off((size_t)s[2] + 1);
-    std::vector<uint64_t> members((size_t)std::max<int64_t>(1, s[3]));
-    rc = zb_index_export_forest(index, nodes.data(), roots.data(), coef.data(), cst.data(), leaf_off.data(), members.data());
+    rc = zb_index_forest_sizes(index, e.s);
+    if (rc != ZB_OK) return rc;
+    ZB_REQUIRE(e.s[0] >= 1, ZB_ERR_STATE, "the index has no trees yet");
+    e.nodes.resize((size_t)e.s[0] * 4);
+    e.roots.resize(e.opt.num_trees);
+    e.coef.resize((size_t)std::max<int64_t>(1, e.s[1]) * e.opt.dim);
+    e.cst.resize((size_t)std::max<int64_t>(1, e.s[1]));
+    e.leaf_off.resize((size_t)e.s[2] + 1);
+    std::vector<uint64_t> members((size_t)std::max<int64_t>(1, e.s[3]));
+    rc = zb_index_export_forest(index, e.nodes.data(), e.roots.data(), e.coef.data(), e.cst.data(), e.leaf_off.data(), members.data());
     if (rc != ZB_OK) return rc;
     zb_stats st;
     rc = zb_index_stats(index, &st);
@@ -478,16 +487,50 @@ int zb_index_export_tree_blob(zb_index* index, uint32_t tree, uint8_t* out, uint
     std::vector<uint8_t> ids((size_t)std::max<uint64_t>(1, st.total_rows) * 16), live((size_t)std::max<uint64_t>(1, st.total_rows));
     rc = zb_index_export_rows(index, 0, st.total_rows, nullptr, ids.data(), live.data());
     if (rc != ZB_OK) return rc;
-    std::vector<uint8_t> mid((size_t)std::max<int64_t>(1, s[3]) * 16), keep((size_t)std::max<int64_t>(1, s[3]));
-    for (int64_t j = 0; j < s[3]; ++j) {
+    e.mid.resize((size_t)std::max<int64_t>(1, e.s[3]) * 16);
+    e.keep.resize((size_t)std::max<int64_t>(1, e.s[3]));
+    for (int64_t j = 0; j < e.s[3]; ++j) {
         ZB_REQUIRE(members[j] < st.total_rows, ZB_ERR_STATE, "member ordinal out of range");
-        memcpy(mid.data() + 16 * (size_t)j, ids.data() + 16 * (size_t)members[j], 16);
-        keep[j] = live[members[j]];
+        memcpy(e.mid.data() + 16 * (size_t)j, ids.data() + 16 * (size_t)members[j], 16);
+        e.keep[j] = live[members[j]];
     }
-    const uint64_t need = encode_tree(opt.dim, s[0], nodes.data(), roots[tree], coef.data(), cst.data(), leaf_off.data(), mid.data(),
-                                      keep.data(), out, cap);
+    return ZB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int zb_index_export_tree_blob(zb_index* index, uint32_t tree, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(index && out_bytes, ZB_ERR_INVALID, "NULL argument");
+    Exported e;
+    int rc = export_forest_with_ids(index, e);
+    if (rc != ZB_OK) return rc;
+    ZB_REQUIRE(tree < e.opt.num_trees, ZB_ERR_INVALID, "tree %u out of range (%u trees)", tree, e.opt.num_trees);
+    const uint64_t need = encode_tree(e.opt.dim, e.s[0], e.nodes.data(), e.roots[tree], e.coef.data(), e.cst.data(), e.leaf_off.data(),
+                                      e.mid.data(), e.keep.data(), out, cap);
     *out_bytes = need;
     ZB_REQUIRE(!out || need <= cap, ZB_ERR_INVALID, "tree blob needs %llu bytes, buffer holds %llu", (unsigned long long)need,
+               (unsigned long long)cap);
+    ZB_API_END
+}
+
+int zb_index_export_tree_blobs(zb_index* index, uint8_t* out, uint64_t cap, uint64_t* out_blob_bytes, uint64_t* out_total) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(index && out_total, ZB_ERR_INVALID, "NULL argument");
+    Exported e;
+    int rc = export_forest_with_ids(index, e);  // ONE export of the forest for all trees
+    if (rc != ZB_OK) return rc;
+    uint64_t at = 0;
+    for (uint32_t t = 0; t < e.opt.num_trees; ++t) {
+        const uint64_t room = out && at < cap ? cap - at : 0;
+        const uint64_t need = encode_tree(e.opt.dim, e.s[0], e.nodes.data(), e.roots[t], e.coef.data(), e.cst.data(), e.leaf_off.data(),
+                                          e.mid.data(), e.keep.data(), room ? out + at : nullptr, room);
+        if (out_blob_bytes) out_blob_bytes[t] = need;
+        at += need;
+    }
+    *out_total = at;
+    ZB_REQUIRE(!out || at <= cap, ZB_ERR_INVALID, "the tree blobs need %llu bytes, buffer holds %llu", (unsigned long long)at,
                (unsigned long long)cap);
     ZB_API_END
 }

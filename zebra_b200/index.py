@@ -279,15 +279,26 @@ class LSHIndex:
         return rows, ids, live.astype(bool)
 
     def export_tree_blobs(self) -> List[bytes]:
-        """Every tree as the reference's `trees` value (bincode(legacy) Node<N>); removed rows are left out of the leaves."""
-        out = []
-        for t in range(self.options.num_trees):
-            need = C.c_uint64()
-            _ffi.check(_ffi.lib().zb_index_export_tree_blob(self._h, t, None, 0, C.byref(need)))
-            buf = np.empty(int(need.value), dtype=np.uint8)
-            _ffi.check(_ffi.lib().zb_index_export_tree_blob(self._h, t, buf.ctypes.data, buf.size, C.byref(need)))
-            out.append(buf.tobytes())
+        """Every tree as the reference's `trees` value (bincode(legacy) Node<N>); removed rows are left out of the leaves.
+        One export of the forest serves all trees (zb_index_export_tree_blobs)."""
+        t = self.options.num_trees
+        sizes = np.zeros(t, dtype=np.uint64)
+        total = C.c_uint64()
+        _ffi.check(_ffi.lib().zb_index_export_tree_blobs(self._h, None, 0, sizes.ctypes.data, C.byref(total)))
+        buf = np.empty(max(1, int(total.value)), dtype=np.uint8)
+        _ffi.check(_ffi.lib().zb_index_export_tree_blobs(self._h, buf.ctypes.data, int(total.value), sizes.ctypes.data, C.byref(total)))
+        out, at = [], 0
+        for n in sizes:
+            out.append(buf[at:at + int(n)].tobytes())
+            at += int(n)
         return out
+
+    def export_tree_blob(self, tree: int) -> bytes:
+        need = C.c_uint64()
+        _ffi.check(_ffi.lib().zb_index_export_tree_blob(self._h, tree, None, 0, C.byref(need)))
+        buf = np.empty(int(need.value), dtype=np.uint8)
+        _ffi.check(_ffi.lib().zb_index_export_tree_blob(self._h, tree, buf.ctypes.data, buf.size, C.byref(need)))
+        return buf.tobytes()
 
     def save_store(self, path: str, zebra: bytes = b"") -> None:
         """Dump both partitions (live rows only, as the reference deletes removed keys) into one file, see interchange.py."""

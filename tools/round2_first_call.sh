@@ -6,8 +6,10 @@
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 200 python -m pytest tests/test_zz_flat_tables_gpu.py -q --durations=5 > $OUT/r02a_flat_tests.log 2>&1; echo "flat tests rc=$?" >> $OUT/r02a_flat_tests.log
+timeout 200 python -m pytest tests/test_zz_flat_tables_gpu.py tests/test_zz_quad_tile_gpu.py -q --durations=5 > $OUT/r02a_flat_tests.log 2>&1; echo "flat + quad-tile tests rc=$?" >> $OUT/r02a_flat_tests.log
 tail -12 $OUT/r02a_flat_tests.log
+# top-100 (BASELINE config 5 asks for it): one quad per pair vs the keys-only tile scan (never run on a GPU in round 1)
+for q in 0 1; do timeout 150 python bench.py --topk 100 --metric cosine --dim 384 --steps 3 --warmup 3 --no-cpu-baseline --set quad_tile=$q > $OUT/r02a_bench_top100_quad$q.json 2>> $OUT/r02a.err; echo "top-100 quad_tile=$q rc=$?"; done
 for cfg in "16 1" "16 8" "16 15"; do
   set -- $cfg
   timeout 150 python bench.py --workload hash --flat-bits $1 --trees $2 --steps 5 --warmup 3 --cpu-seconds 3 > $OUT/r02a_bench_hash_flat_K$1_T$2.json 2>> $OUT/r02a.err; echo "flat K=$1 T=$2 rc=$?"

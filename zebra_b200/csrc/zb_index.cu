@@ -158,9 +158,10 @@ struct zb_index {
     DBuf<int> b_slot_a, b_slot_b;
     DBuf<float> b_pair_rows;
     ScanWorkspace scan_ws;
+    ScanWorkspace qt_ws;  // keys-only tile scan of the visits the fused kernel leaves (cosine / L2, n' > 32)
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 0;
     zb_stats st{};
 
     ForestView view() const {
@@ -920,7 +921,11 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     if (ix->opt.metric > ZB_METRIC_L2 && ix->p_seq_tile && total_pairs && seq_tile_scan_supported(ix->dimp))
         seq_tile_scan(ix->scan_ws, fs, ix->opt.metric, (int)ix->opt.metric_power, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p,
                       ix->pair_key.p, (u32)ix->h_leaf_off.size(), (int)ix->p_seq_prefetch, s);
-    if (!ix->scan_ws.seq_launched)
+    ix->qt_ws.seq_launched = false;
+    if (ix->opt.metric <= ZB_METRIC_L2 && ix->p_quad_tile && total_pairs && quad_tile_scan_supported(ix->dimp))
+        quad_tile_scan(ix->qt_ws, fs, ix->opt.metric, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p, ix->pair_key.p,
+                       (u32)ix->h_leaf_off.size(), s);
+    if (!ix->scan_ws.seq_launched && !ix->qt_ws.seq_launched)
         launch_score_pairs(fs, (int)ix->opt.metric, (int)ix->opt.metric_power, d_q, nv, ix->v_leaf.p, ix->v_q.p, ix->v_pair_off.p,
                            total_pairs, ix->pair_key.p, s);
     ZB_CUDA(cudaEventRecord(ix->ev[2], s));
@@ -979,6 +984,14 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved, &tile_ms, &tiles);
     u64 seq_moved = 0;
     if (ix->scan_ws.seq_launched) seq_tile_scan_stats(ix->scan_ws, s, &seq_moved, &tile_ms, &tiles);
+    u64 qt_moved = 0;
+    if (ix->qt_ws.seq_launched) {  // next to the fused kernel (if it ran too): times and tiles add up
+        float qt_ms = 0.f;
+        u32 qt_tiles = 0;
+        seq_tile_scan_stats(ix->qt_ws, s, &qt_moved, &qt_ms, &qt_tiles);
+        tile_ms += qt_ms;
+        tiles += qt_tiles;
+    }
     ix->st.last_ms_tile_kernel = tile_ms;
     ix->st.last_tiles = tiles;
     ix->sync();
@@ -993,11 +1006,12 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->st.last_pairs = total_pairs + tile_pairs;
     ix->st.last_tile_visits = tile_visits;
     ix->st.last_tile_pairs = tile_pairs;
-    ix->st.last_moved_bytes = ix->scan_ws.seq_launched ? seq_moved : moved + total_pairs * (u64)ix->dim * 4;
+    ix->st.last_moved_bytes = ix->scan_ws.seq_launched ? seq_moved
+                              : (ix->qt_ws.seq_launched ? moved + qt_moved : moved + total_pairs * (u64)ix->dim * 4);
     ix->st.last_scan_launches = scan_launches + (total_pairs ? (ix->scan_ws.seq_launched ? 7 : 1) : 0);
     // generic-path launches: the score kernel (or the 7 of seq_tile_scan: count, scan, scatter, tile count, scan, fill, scan
     // kernel) + select; then the merge
-    ix->st.last_total_launches += scan_launches + 5 + (sharded ? 1 : 0) + (ix->scan_ws.seq_launched ? 6 : 0);
+    ix->st.last_total_launches += scan_launches + 5 + (sharded ? 1 : 0) + ((ix->scan_ws.seq_launched || ix->qt_ws.seq_launched) ? 6 : 0);
 }
 
 static const float* stage_queries_device(zb_index* ix, const float* d_q, u64 nq) {
@@ -1855,6 +1869,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "use_tile_scan") ix->p_use_tile_scan = value;
     else if (k == "classify_variant") ix->p_classify_variant = value;  // 0: rows gathered through L1; 1: rows staged by TMA bulk copies
     else if (k == "seq_prefetch") ix->p_seq_prefetch = value;  // scalar metrics: L2 prefetch distance of the row stream in 128-byte lines (0 = off, the default: measured slower)
+    else if (k == "quad_tile") ix->p_quad_tile = value;  // cosine / L2 visits outside the fused kernel (n' > 32): 1 = keys-only leaf-tile scan, 0 = one quad per pair (default until measured)
     else if (k == "flat_project") ix->p_flat_project = value;  // flat tables: 1 = dense projection + ballot packing (default), 0 = the generic tree walk
     else if (k == "seq_tile") ix->p_seq_tile = value;          // scalar metrics: 1 = leaf-tile scan (default), 0 = one thread per pair
     else if (k == "hash_variant") ix->p_hash_variant = value;  // 0: quad per (row, tree), rows through L1; 1: row staged in shared memory

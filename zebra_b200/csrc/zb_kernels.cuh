@@ -6,6 +6,7 @@
 #include "zb_device.cuh"
 #include "zb_metrics.cuh"
 #include "zb_project.cuh"
+#include "zb_quadtile.cuh"
 
 namespace zb {
 

@@ -16,7 +16,10 @@
 #define ZB_PJ_HD __host__ __device__ __forceinline__
 #else
 #include <math.h>
+#ifndef ZB_HOST_FLOAT4
+#define ZB_HOST_FLOAT4
 struct float4 { float x, y, z, w; };
+#endif
 #define ZB_PJ_HD static inline
 #endif
 

@@ -990,4 +990,186 @@ void seq_tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* moved_bytes, fl
     *moved_bytes = h[2];
 }
 
+// =====================================================================================================
+// Keys-only leaf-tile scan for cosine / L2 (zb_quadtile.cuh): the visits the fused kernel does not take (n' > 32, e.g.
+// BASELINE config 5's top-100) grouped by leaf into (leaf, <= 8 queries) tiles; a quad scores 4 rows x 4 queries per pass
+// in the canonical order and writes the keys into the gather path's pair_key layout; select_visits_kernel keeps each
+// visit's top-n'.  Rows cross HBM once per tile instead of once per pair.  Knob quad_tile (default 0 until measured).
+// =====================================================================================================
+#define QT_THREADS 256
+
+struct QuadTileParams {
+    const u32* tile_leaf;
+    const u32* tile_first;
+    const u32* tile_count;
+    const u32* ntiles;
+    u32* tile_counter;
+    const u32* order;
+    const u32* v_q;
+    const u64* v_pair_off;
+    u64* pair_key;
+    const float* queries;
+    u64* stats;  // [0] visits, [1] pairs, [2] bytes asked of HBM by design
+};
+
+template <int METRIC>
+__global__ void __launch_bounds__(QT_THREADS) quad_tile_kernel(ForestView f, QuadTileParams tp) {
+    extern __shared__ __align__(16) float s_q[];  // [8][dimp]
+    __shared__ u32 s_tile;
+    __shared__ u32 s_v[8];
+    __shared__ u64 s_pbase[8];
+    const u32 ntiles = *tp.ntiles;
+    const int q4 = f.dimp >> 2;
+    const int quad = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    for (;;) {
+        __syncthreads();  // the previous tile's queries are no longer read
+        if (threadIdx.x == 0) s_tile = atomicAdd(tp.tile_counter, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u32 leaf = tp.tile_leaf[tile], first = tp.tile_first[tile], c = tp.tile_count[tile];
+        if (threadIdx.x < 8) {
+            const u32 v = tp.order[first + (threadIdx.x < c ? threadIdx.x : 0u)];
+            s_v[threadIdx.x] = v;
+            s_pbase[threadIdx.x] = tp.v_pair_off[v];
+        }
+        __syncthreads();
+        const u32 nqp = c <= 4 ? 4u : 8u;  // query slots: one or two groups of ZB_QT_Q
+        for (u32 idx = threadIdx.x; idx < nqp * (u32)q4; idx += QT_THREADS) {
+            const u32 j = idx / (u32)q4, k = idx - j * (u32)q4;
+            reinterpret_cast<float4*>(s_q)[idx] =
+                j < c ? __ldg(reinterpret_cast<const float4*>(tp.queries + (size_t)tp.v_q[s_v[j]] * f.dimp) + k)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        const u32 len = f.leaf_len[leaf];
+        const long long off = f.leaf_off[leaf];
+        // 64 quads: with one query group every quad takes its own 4 rows (256 rows per pass), with two groups the quads of a
+        // pair share 4 rows and split the queries (128 rows per pass)
+        const u32 qg = nqp == 8 ? (u32)(quad & 1) : 0u;
+        const u32 rg = nqp == 8 ? (u32)(quad >> 1) : (u32)quad;
+        const u32 rows_per_pass = nqp == 8 ? 128u : 256u;
+        const float4* qp = reinterpret_cast<const float4*>(s_q) + (size_t)qg * ZB_QT_Q * q4 + sub;
+        for (u32 base = 0; base < len; base += rows_per_pass) {
+            const u32 r0 = base + rg * ZB_QT_R;
+            if (r0 >= len) continue;  // the whole quad skips together
+            const float4* xr[ZB_QT_R];
+            bool dead[ZB_QT_R];
+#pragma unroll
+            for (int i = 0; i < ZB_QT_R; ++i) {  // tail rows: clamp the loads, mask the stores
+                const u32 r = r0 + i < len ? r0 + i : len - 1;
+                const u32 slot = f.members[off + r];
+                dead[i] = tomb_test(f.tomb, slot);
+                xr[i] = reinterpret_cast<const float4*>(f.rows + (size_t)slot * f.dimp) + sub;
+            }
+            QtAcc acc;
+            qt_init(acc);
+#pragma unroll 2
+            for (int ch = 0; ch < f.chunks; ++ch) {
+                float4 x[ZB_QT_R], q[ZB_QT_Q];
+#pragma unroll
+                for (int i = 0; i < ZB_QT_R; ++i) x[i] = __ldg(xr[i] + ch * 4);
+#pragma unroll
+                for (int j = 0; j < ZB_QT_Q; ++j) q[j] = qp[(size_t)j * q4 + ch * 4];
+                qt_chunk<METRIC>(acc, x, q);
+            }
+            float a2[ZB_QT_R], b2[ZB_QT_Q];
+            if (METRIC == 0) {
+#pragma unroll
+                for (int i = 0; i < ZB_QT_R; ++i) a2[i] = quad_reduce16(acc.a2[i], mask);
+#pragma unroll
+                for (int j = 0; j < ZB_QT_Q; ++j) b2[j] = quad_reduce16(acc.b2[j], mask);
+            }
+#pragma unroll
+            for (int i = 0; i < ZB_QT_R; ++i) {
+#pragma unroll
+                for (int j = 0; j < ZB_QT_Q; ++j) {
+                    const float sum = quad_reduce16(acc.m[i][j], mask);  // every thread of the quad takes part
+                    const u32 jq = qg * ZB_QT_Q + j;
+                    if (sub == 0 && r0 + i < len && jq < c) {
+                        u64 key;
+                        if (dead[i]) key = ZB_SENTINEL;
+                        else if (METRIC == 0) key = cos_bits(sum, a2[i], b2[j]);
+                        else key = METRIC == 1 ? l2sq_bits(sum) : l2_bits(sum);
+                        tp.pair_key[s_pbase[jq] + r0 + i] = key;
+                    }
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            atomicAdd(&tp.stats[0], (u64)c);
+            atomicAdd(&tp.stats[1], (u64)len * c);
+            atomicAdd(&tp.stats[2], ((u64)len + c) * 4ull * (u64)f.dim);
+        }
+    }
+}
+
+bool quad_tile_scan_supported(int dimp) { return (size_t)8 * dimp * 4 <= 96 * 1024; }
+
+void quad_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, const float* d_q, u32 nv, const u32* v_leaf, const u32* v_q,
+                    const u64* v_pair_off, u64* pair_key, u32 nleaves, cudaStream_t s) {
+    ws.seq_launched = false;
+    if (!nv || !nleaves || metric > M_L2 || !quad_tile_scan_supported(f.dimp)) return;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ws.leaf_count.ensure(nleaves + 1);
+    ws.leaf_start.ensure(nleaves + 1);
+    ws.leaf_cursor.ensure(nleaves + 1);
+    ws.tile_per_leaf.ensure(nleaves + 1);
+    ws.tile_start.ensure(nleaves + 1);
+    ws.order.ensure(nv);
+    ws.tile_leaf.ensure(nv);
+    ws.tile_first.ensure(nv);
+    ws.tile_cnt.ensure(nv);
+    ws.counters.ensure(64);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const u32*)nullptr, (u32*)nullptr, (long long)(nleaves + 1));
+    ws.tmp.ensure(tmp_bytes + 256);
+    ZB_CUDA(cudaMemsetAsync(ws.leaf_count.p, 0, (size_t)(nleaves + 1) * 4, s));
+    ZB_CUDA(cudaMemsetAsync(ws.leaf_cursor.p, 0, (size_t)(nleaves + 1) * 4, s));
+    ZB_CUDA(cudaMemsetAsync(ws.counters.p, 0, 64 * 4, s));
+    sq_count_kernel<<<(nv + 255) / 256, 256, 0, s>>>(nv, v_leaf, v_pair_off, ws.leaf_count.p);
+    cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.leaf_count.p, ws.leaf_start.p, (long long)(nleaves + 1), s);
+    sq_scatter_kernel<<<(nv + 255) / 256, 256, 0, s>>>(nv, v_leaf, v_pair_off, ws.leaf_start.p, ws.leaf_cursor.p, ws.order.p);
+    ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, 8, ws.tile_per_leaf.p);
+    cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
+    ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, 8,
+                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p);
+    QuadTileParams tp;
+    tp.tile_leaf = ws.tile_leaf.p;
+    tp.tile_first = ws.tile_first.p;
+    tp.tile_count = ws.tile_cnt.p;
+    tp.ntiles = ws.tile_start.p + nleaves;
+    ws.ntiles_ptr = tp.ntiles;
+    tp.tile_counter = ws.counters.p;
+    tp.order = ws.order.p;
+    tp.v_q = v_q;
+    tp.v_pair_off = v_pair_off;
+    tp.pair_key = pair_key;
+    tp.queries = d_q;
+    tp.stats = reinterpret_cast<u64*>(ws.counters.p + 4);
+    const size_t smem = (size_t)8 * f.dimp * 4;
+    const int grid = sms * 2;
+    if (!ws.ev0) {
+        ZB_CUDA(cudaEventCreate(&ws.ev0));
+        ZB_CUDA(cudaEventCreate(&ws.ev1));
+    }
+    ZB_CUDA(cudaEventRecord(ws.ev0, s));
+#define ZB_QT_CALL(M)                                                                                                    \
+    do {                                                                                                                 \
+        if (smem > 48 * 1024)                                                                                            \
+            ZB_CUDA(cudaFuncSetAttribute(quad_tile_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        quad_tile_kernel<M><<<grid, QT_THREADS, smem, s>>>(f, tp);                                                       \
+    } while (0)
+    if (metric == 0) ZB_QT_CALL(0);
+    else if (metric == 1) ZB_QT_CALL(1);
+    else ZB_QT_CALL(2);
+#undef ZB_QT_CALL
+    ZB_CUDA(cudaGetLastError());
+    ZB_CUDA(cudaEventRecord(ws.ev1, s));
+    ws.seq_launched = true;  // the same stats reader as the scalar-metric scan (seq_tile_scan_stats)
+}
+
 }  // namespace zb

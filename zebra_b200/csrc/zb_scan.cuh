@@ -51,6 +51,12 @@ void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* t
 bool seq_tile_scan_supported(int dimp);
 void seq_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, int power, const float* d_q, u32 nv, const u32* v_leaf,
                    const u32* v_q, const u64* v_pair_off, u64* pair_key, u32 nleaves, int prefetch_lines, cudaStream_t s);
+// Cosine / L2 visits the fused kernel does not take (n' > 32): the same grouping, a quad scores 4 rows x 4 queries in the
+// canonical order (zb_quadtile.cuh), keys into pair_key.  Use a ScanWorkspace of its own (the fused kernel's statistics live
+// in the other one until the end of the batch).  Statistics through seq_tile_scan_stats.
+bool quad_tile_scan_supported(int dimp);
+void quad_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, const float* d_q, u32 nv, const u32* v_leaf, const u32* v_q,
+                    const u64* v_pair_off, u64* pair_key, u32 nleaves, cudaStream_t s);
 void seq_tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* moved_bytes, float* kernel_ms, u32* tiles);
 
 }  // namespace zb

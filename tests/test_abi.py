@@ -97,3 +97,19 @@ def test_invalid_arguments_are_reported():
     assert lib.zb_zebra_file_encode(None, 0, 0, 5, 15, None, 0, C.byref(u)) == -1
     assert lib.zb_metric_distance_batch(0, 12, 0, 0, 16, None, None, None) == -1          # not a zb_metric
     assert lib.zb_metric_distance_batch(0, 10, 65, 0, 16, None, None, None) == -1         # Minkowski power out of range
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/zebra_b200.h must compile as C99 (no C++-isms), and a C program links against it."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "zebra_b200.h"\n'
+                   'int main(void) { zb_options o; zb_stats s; zb_import_report r; int n = -1; (void)o; (void)s; (void)r;\n'
+                   '  if (zb_abi_version() != ZB_ABI_VERSION) return 1;\n'
+                   '  if (zb_device_count(&n) != ZB_OK || n < 0) return 2;\n'
+                   '  if (zb_index_create(0, 0) != ZB_ERR_INVALID || !zb_last_error()[0]) return 3;\n'
+                   '  return 0; }\n')
+    exe = str(tmp_path / "abi_c")
+    lib = os.path.join(ROOT, "zebra_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           str(src), "-L" + lib, "-lzebra_b200", "-Wl,-rpath," + lib])
+    assert subprocess.run([exe]).returncode == 0

@@ -68,12 +68,41 @@ def parse():
     ap.add_argument("--flat-bits", type=int, default=0,
                     help="workload hash: K > 0 hashes FLAT tables (every level of a tree shares one plane: K bits per table, "
                          "H = K * trees planes per row, dense projection kernel) instead of the built forest")
-    return ap.parse_args()
+    ap.add_argument("--delete-frac", type=float, default=0.0,
+                    help="workload query: tombstone this fraction of the rows (seeded selection) before the queries, BASELINE config 5")
+    ap.add_argument("--preset", type=int, default=0, choices=[0, 3, 5],
+                    help="BASELINE.json configs as STRONG-scaling runs: 3 = 10M x 768 cosine over the GPUs, 10k top-10 queries; "
+                         "5 = 100M x 384 L2 squared, 10 %% tombstones, 100k top-100 queries (sized for 8 GPUs)")
+    a = ap.parse_args()
+    a.scaling = "weak"
+    if a.preset == 3:
+        a.metric, a.dim, a.topk = "cosine", 768, 10
+        a.rows, a.queries, a.scaling = 10_000_000 // a.gpus, max(1, 10_000 // a.gpus), "strong"
+    elif a.preset == 5:
+        a.metric, a.dim, a.topk, a.delete_frac = "l2sq", 384, 100, 0.1
+        a.rows, a.queries, a.scaling = 100_000_000 // a.gpus, max(1, 100_000 // a.gpus), "strong"
+    return a
+
+
+def seeded_deletes(total_rows, frac, seed):
+    """Ordinals to tombstone: a counter-based choice (the same list on every rank, no 100M-element permutation)."""
+    out = []
+    thr = int(frac * (1 << 32))
+    for lo in range(0, total_rows, 1 << 24):
+        o = np.arange(lo, min(total_rows, lo + (1 << 24)), dtype=np.uint64)
+        h = (o + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
+        h ^= h >> np.uint64(29)
+        h *= np.uint64(0xBF58476D1CE4E5B9)
+        h ^= h >> np.uint64(32)
+        out.append(o[(h & np.uint64(0xFFFFFFFF)) < np.uint64(thr)])
+    return np.concatenate(out) if out else np.zeros(0, np.uint64)
 
 
 def workload_name(a, n_gpus):
     return (f"{a.rows * n_gpus // 1000}k x {a.dim} f32 {a.metric.upper()} LSH index "
-            f"(max_node_size {a.max_node_size}, {a.trees} trees), {a.queries * n_gpus} batched top-{a.topk} queries")
+            f"(max_node_size {a.max_node_size}, {a.trees} trees), "
+            + (f"{a.delete_frac:.0%} of the rows tombstoned, " if a.delete_frac > 0 else "")
+            + f"{a.queries * n_gpus} batched top-{a.topk} queries")
 
 
 class ClockSampler:
@@ -171,6 +200,8 @@ def run_reference(a):
     zo.set_build_threads(min(cores, a.trees))
     orc = zo.OracleIndex(a.dim, METRIC_IDS[a.metric], a.max_node_size, a.trees, seed=a.seed)
     orc.add(rows)
+    if a.delete_frac > 0:
+        orc.remove(seeded_deletes(total_rows, a.delete_frac, a.seed + 3))
     t_build = time.time() - t0
     nq_step = a.queries * n_gpus
     # calibrate the sample so that the whole run stays within a couple of minutes
@@ -191,7 +222,7 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": "queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": n_gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times) * (nq_step / sample),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, n_gpus), "rows_per_gpu": a.rows, "queries_per_gpu": a.queries,
                    "top_k": a.topk, "metric": a.metric, "max_node_size": a.max_node_size, "num_trees": a.trees,
                    "data": "Philox clustered (centre[row % 4096] + 0.25 noise)"},
@@ -246,6 +277,10 @@ def run_ours(a):
     else:
         ix.add_device(d_rows.data_ptr(), n_local)
     del d_rows
+    dead = None
+    if a.delete_frac > 0:   # mixed CRUD (config 5): tombstones before the queries; collective on a sharded index
+        dead = seeded_deletes(total_rows, a.delete_frac, a.seed + 3)
+        ix.remove_ordinals(dead)
     torch.cuda.synchronize()
     t_build = time.time() - t0
 
@@ -349,6 +384,8 @@ def run_ours(a):
         rows = zo.synth(0, 1, total_rows, a.dim, a.seed, 1, cores)
         orc = zo.OracleIndex(a.dim, METRIC_IDS[a.metric], a.max_node_size, a.trees, seed=a.seed)
         orc.load_forest(rows, ix.export_forest())      # same forest as the GPU arm (build parity is a separate test)
+        if dead is not None:
+            orc.remove(dead)
         b = a.warmup + a.steps - 1
         qh = h_q[b].numpy()
         # parity: the last timed step's batch (whose GPU results are in the host buffers) against the oracle
@@ -380,7 +417,7 @@ def run_ours(a):
         st = ix.stats()
         line = {
             "metric": "queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": G, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a, G), "rows_per_gpu": a.rows, "queries_per_gpu": a.queries,
                        "top_k": a.topk, "metric": a.metric, "max_node_size": a.max_node_size, "num_trees": a.trees,

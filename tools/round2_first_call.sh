@@ -26,3 +26,7 @@ for f in sorted(glob.glob("gpurun_out/r02a_bench_hash_*.json")):
     except Exception as e:
         print(f, "unreadable", e)
 PY
+
+# Later calls of round 2 (multi-GPU, charged N x): the BASELINE configs at their own sizes, strong scaling
+#   gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --preset 3 --steps 5 --warmup 3'
+#   gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 8 --preset 5 --steps 3 --warmup 3 --set quad_tile=1'

@@ -2,8 +2,8 @@
 does not take (n' > 32: BASELINE config 5 asks for top-100) scored tile by tile instead of pair by pair.  Ids, distance
 bits and counts must equal the oracle's, and the default path's (knob 0).
 
-NOT YET RUN ON A GPU when it was committed (round 1's GPU budget was spent; the arithmetic of the tile is verified on the
-CPU by tests/test_quadtile.py).  The knob is OFF by default, so nothing else depends on this path; the file sorts last."""
+NOT YET RUN ON A GPU when it was committed (round 1's GPU budget was spent); on the CPU, tests/test_quadtile.py runs the
+kernel's own source thread by thread (tests/quadtile_emu.cpp) and every key equals the oracle's.  The knob is OFF by default, so nothing else depends on this path; the file sorts last."""
 import numpy as np
 import pytest
 

@@ -1,7 +1,8 @@
 // quadtile_emu.cpp -- TEST INFRASTRUCTURE.  Runs the SOURCE of quad_tile_kernel (zebra_b200/csrc/zb_quadtile_kernel.cuh) on the
 // CPU: one std::thread per CUDA thread of a block, __syncthreads = a block barrier, __shfl_xor_sync = an exchange through
 // a per-quad mailbox, shared memory = block-local storage, atomics = GCC atomics, the device helpers (quad_reduce16, cos_bits, ...)
-// restated with plain IEEE operations (build with -ffp-contract=off).  Blocks run one after the other, which is a legal
+// restated with plain IEEE operations (build with -ffp-contract=off, and with -fvisibility=hidden -Wl,-Bsymbolic: the host
+// stub nvcc emits for the real kernel in libzebra_b200.so has the same mangled name as the emulated function).  Blocks run one after the other, which is a legal
 // schedule of the persistent kernel (the first block drains the tile counter).  tests/test_quadtile.py feeds it leaves,
 // tombstones and visits and compares every key with the oracle.
 #include <math.h>
@@ -98,7 +99,7 @@ static inline u64 cos_bits(float ab_, float a2_, float b2_) {  // zb_device.cuh 
 
 // Tiles are given directly (what sq_count / sq_scatter / ts_* build on the device): tile t = leaf tile_leaf[t], visits
 // order[tile_first[t] .. + tile_count[t]).  Runs `blocks` blocks of QT_THREADS threads.
-extern "C" int emu_quad_tile(int metric, int blocks, int dim, const long long* leaf_off, const uint32_t* leaf_len,
+extern "C" __attribute__((visibility("default"))) int emu_quad_tile(int metric, int blocks, int dim, const long long* leaf_off, const uint32_t* leaf_len,
                              const uint32_t* members, const float* rows_padded, const uint32_t* tomb, uint32_t ntiles,
                              const uint32_t* tile_leaf, const uint32_t* tile_first, const uint32_t* tile_count, const uint32_t* order,
                              const uint32_t* v_q, const uint64_t* v_pair_off, const float* queries_padded, uint64_t* pair_key,

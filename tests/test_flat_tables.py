@@ -80,7 +80,7 @@ def flat_forest(rows, coef, cst, T, K):
 @pytest.fixture(scope="module")
 def twin(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("pj") / "libproject_twin.so")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", out,
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-o", out,
                            os.path.join(HERE, "project_twin.cpp")])
     L = C.CDLL(out)
     L.twin_project.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

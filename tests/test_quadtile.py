@@ -18,7 +18,7 @@ F32 = np.float32
 @pytest.fixture(scope="module")
 def twin(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("qt") / "libquadtile_twin.so")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", out,
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-o", out,
                            os.path.join(HERE, "quadtile_twin.cpp")])
     L = C.CDLL(out)
     L.twin_quadtile.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -61,8 +61,8 @@ def test_quad_tile_twin_equals_oracle_sums(twin, n, m, dim):
 def emu(tmp_path_factory):
     """tests/quadtile_emu.cpp: quad_tile_kernel's own source compiled for the CPU, one std::thread per CUDA thread."""
     out = str(tmp_path_factory.mktemp("qtemu") / "libquadtile_emu.so")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread", "-o", out,
-                           os.path.join(HERE, "quadtile_emu.cpp")])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
+                           "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out, os.path.join(HERE, "quadtile_emu.cpp")])
     L = C.CDLL(out)
     L.emu_quad_tile.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 9
     return L

@@ -187,7 +187,7 @@ def test_root_p_exact_on_perfect_powers_and_within_one_ulp_of_libm():
 @pytest.fixture(scope="module")
 def twin(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("twin") / "libmetric_twin.so")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", out,
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-o", out,
                            os.path.join(HERE, "metric_twin.cpp")])
     L = C.CDLL(out)
     L.twin_distance_bits_batch.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

@@ -247,7 +247,7 @@ int zb_index_stats(zb_index* index, zb_stats* out);
  * device work with their own events. */
 int zb_index_stream(zb_index* index, void** out_stream);
 /* Tuning knobs (tests and ablations): key in {"tile_min_rows", "tile_queries", "use_tile_scan", "visit_slots", "seq_tile",
- * "seq_prefetch", "hash_variant", "classify_variant", "flat_project", "quad_tile"}. */
+ * "seq_prefetch", "hash_variant", "classify_variant", "flat_project", "quad_tile", "select_variant"}. */
 int zb_index_set_param(zb_index* index, const char* key, int64_t value);
 
 /* Sharding over the GPUs of one box: one process per GPU, each with its own index

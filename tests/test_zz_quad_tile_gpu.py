@@ -78,3 +78,29 @@ def test_quad_tile_scan_next_to_the_fused_kernel():
     ix.set_param("use_tile_scan", 0)
     assert_search_equal(ix, orc, queries, 10)
     assert ix.stats()["last_tile_pairs"] == 0 and ix.stats()["last_tiles"] > 0
+
+
+@pytest.mark.parametrize("mid,mname,k,quad", [(zo.MANHATTAN, "ManhattanDistance", 10, 0), (zo.COSINE, "CosineDistance", 100, 1),
+                                              (zo.L2SQ, "L2SquaredDistance", 40, 1), (zo.HAMMING, "HammingDistance", 33, 0)])
+def test_warp_select_equals_oracle_and_block_select(mid, mname, k, quad):
+    """select_variant = 1: the per-visit top-n' with the list in a warp's registers (zb_select_kernel.cuh; its source is run on
+    the CPU by tests/test_select.py) instead of the block-wide bitonic sort -- same entries, so the same final answer.
+    Hamming gives long runs of equal keys (ties by ordinal)."""
+    z = zb()
+    rng = np.random.default_rng(k)
+    dim, n = 64, 5000
+    rows = clustered(rng, n, dim)
+    rows[2000:2200] = rows[:200]
+    orc = zo.OracleIndex(dim, mid, 400, 3, seed=6)
+    orc.add(rows)
+    ix = z.LSHIndex(dim, z.LSHIndexOptions(400, 3), getattr(z, mname)(), seed=6)
+    ix.add(rows)
+    queries = np.concatenate([rows[:40], rng.standard_normal((40, dim)).astype(F32)])
+    dead = rng.choice(n, n // 8, replace=False).astype(np.uint64)
+    assert np.array_equal(ix.remove_ordinals(dead), orc.remove(dead))
+    ix.set_param("use_tile_scan", 0)                        # every visit through the gather path and its select
+    ix.set_param("quad_tile", quad)
+    ix.set_param("select_variant", 1)
+    assert_search_equal(ix, orc, queries, k)
+    ix.set_param("select_variant", 0)
+    assert_search_equal(ix, orc, queries, k)

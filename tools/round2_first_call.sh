@@ -27,6 +27,9 @@ for f in sorted(glob.glob("gpurun_out/r02a_bench_hash_*.json")):
         print(f, "unreadable", e)
 PY
 
+# the per-visit select of the gather path: block bitonic vs one warp per visit (scalar-metric step, config-2 shape)
+for v in 0 1; do timeout 100 python bench.py --metric manhattan --steps 3 --warmup 3 --no-cpu-baseline --set select_variant=$v > $OUT/r02a_bench_manhattan_select$v.json 2>> $OUT/r02a.err; echo "manhattan select_variant=$v rc=$?"; done
+
 # Later calls of round 2 (multi-GPU, charged N x): the BASELINE configs at their own sizes, strong scaling
 #   gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --preset 3 --steps 5 --warmup 3'
 #   gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 8 --preset 5 --steps 3 --warmup 3 --set quad_tile=1'

@@ -161,7 +161,7 @@ struct zb_index {
     ScanWorkspace qt_ws;  // keys-only tile scan of the visits the fused kernel leaves (cosine / L2, n' > 32)
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 0;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 0, p_select_variant = 0;
     zb_stats st{};
 
     ForestView view() const {
@@ -932,7 +932,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->trace_mark("scan");
     if (total_pairs)
         launch_select_visits(fs, nv, ix->v_leaf.p, ix->v_np.p, ix->v_pair_off.p, ix->pair_key.p, ix->v_ent_off.p,
-                             ix->entries.p, ix->v_done.p, (u32)top_k, s);
+                             ix->entries.p, ix->v_done.p, (u32)top_k, (int)ix->p_select_variant, s);
     ZB_CUDA(cudaEventRecord(ix->ev[3], s));
     ix->trace_mark("select");
     if (sharded) {
@@ -1869,6 +1869,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "use_tile_scan") ix->p_use_tile_scan = value;
     else if (k == "classify_variant") ix->p_classify_variant = value;  // 0: rows gathered through L1; 1: rows staged by TMA bulk copies
     else if (k == "seq_prefetch") ix->p_seq_prefetch = value;  // scalar metrics: L2 prefetch distance of the row stream in 128-byte lines (0 = off, the default: measured slower)
+    else if (k == "select_variant") ix->p_select_variant = value;  // per-visit top-n' of the gather path: 0 = block bitonic (default), 1 = one warp per visit, list in registers (until measured)
     else if (k == "quad_tile") ix->p_quad_tile = value;  // cosine / L2 visits outside the fused kernel (n' > 32): 1 = keys-only leaf-tile scan, 0 = one quad per pair (default until measured)
     else if (k == "flat_project") ix->p_flat_project = value;  // flat tables: 1 = dense projection + ballot packing (default), 0 = the generic tree walk
     else if (k == "seq_tile") ix->p_seq_tile = value;          // scalar metrics: 1 = leaf-tile scan (default), 0 = one thread per pair

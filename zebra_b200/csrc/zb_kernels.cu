@@ -447,10 +447,24 @@ static void set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+}  // namespace zb
+#include "zb_select_kernel.cuh"
+namespace zb {
+
 void launch_select_visits(const ForestView& f, u32 nv, const u32* d_vleaf, const u32* d_vnp, const u64* d_pair_off,
                           const u64* d_pair_key, const u32* d_ent_off, Entry* d_entries, const u8* d_vdone, u32 top_k,
-                          cudaStream_t s) {
+                          int variant, cudaStream_t s) {
     if (!nv) return;
+    if (variant == 1 && top_k <= 128) {  // one warp per visit, the n' best in registers (zb_select_kernel.cuh)
+        const u32 blocks = (nv + WS_WARPS - 1) / WS_WARPS;
+        if (top_k <= 32)
+            warp_select_visits_kernel<1><<<blocks, 32 * WS_WARPS, 0, s>>>(f, nv, d_vleaf, d_vnp, d_pair_off, d_pair_key, d_ent_off, d_entries, d_vdone);
+        else if (top_k <= 64)
+            warp_select_visits_kernel<2><<<blocks, 32 * WS_WARPS, 0, s>>>(f, nv, d_vleaf, d_vnp, d_pair_off, d_pair_key, d_ent_off, d_entries, d_vdone);
+        else
+            warp_select_visits_kernel<4><<<blocks, 32 * WS_WARPS, 0, s>>>(f, nv, d_vleaf, d_vnp, d_pair_off, d_pair_key, d_ent_off, d_entries, d_vdone);
+        return;
+    }
     int pmax = topk_pmax(top_k), kmax = (int)top_k;
     size_t smem = topk_smem(pmax, kmax);
     set_smem(select_visits_kernel, smem);

@@ -68,7 +68,7 @@ void launch_score_pairs(const ForestView& f, int metric, int power, const float*
 // ---- per-visit top-n' (Q2) and per-query union/dedup/top-k (lsh.rs:557-564) ----
 void launch_select_visits(const ForestView& f, u32 nv, const u32* d_vleaf, const u32* d_vnp, const u64* d_pair_off,
                           const u64* d_pair_key, const u32* d_ent_off, Entry* d_entries, const u8* d_vdone,
-                          u32 top_k, cudaStream_t s);
+                          u32 top_k, int variant, cudaStream_t s);
 void launch_merge_ranks(u32 nv, const u32* d_ent_off, u32 total_slots, u32 nranks, const Entry* d_gathered,
                         Entry* d_entries, u32 top_k, cudaStream_t s);
 void launch_merge_queries(u32 nq, u32 num_trees, const u32* d_woff, const u32* d_ent_off, const Entry* d_entries,

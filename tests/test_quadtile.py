@@ -63,7 +63,7 @@ def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("qtemu") / "libquadtile_emu.so")
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
                            "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out, os.path.join(HERE, "quadtile_emu.cpp")])
-    L = C.CDLL(out)
+    L = C.CDLL(os.environ.get("ZB_QUADTILE_EMU_SO", out))     # a prebuilt (sanitizer) build may be substituted
     L.emu_quad_tile.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 9
     return L
 

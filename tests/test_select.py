@@ -19,7 +19,7 @@ def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("selemu") / "libselect_emu.so")
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out,
                            os.path.join(HERE, "select_emu.cpp")])
-    L = C.CDLL(out)
+    L = C.CDLL(os.environ.get("ZB_SELECT_EMU_SO", out))     # a prebuilt (sanitizer) build may be substituted
     L.emu_warp_select.argtypes = [C.c_int, C.c_uint32] + [C.c_void_p] * 11
     return L
 

@@ -33,3 +33,7 @@ for v in 0 1; do timeout 100 python bench.py --metric manhattan --steps 3 --warm
 # Later calls of round 2 (multi-GPU, charged N x): the BASELINE configs at their own sizes, strong scaling
 #   gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --preset 3 --steps 5 --warmup 3'
 #   gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 8 --preset 5 --steps 3 --warmup 3 --set quad_tile=1'
+# 8-GPU plan exchange: the volume is nqp x T x visit_slots x 8 B per rank (82 MB at 32 slots, ~97 % padding on the config-2 shape).
+# Cheapest experiment first -- fewer slots per walker (the plan grows and replans on overflow, so run enough warm-up steps):
+#   ... bench.py --gpus 8 --steps 10 --warmup 5 --set visit_slots=8      (and 4), ZB_TRACE=1 for the per-phase times
+

@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-oracle-gb", type=float, default=40.0,
+                    help="skip the oracle legs (parity sample, cpu_baseline) when the rows would not fit this much host memory")
     ap.add_argument("--set", action="append", default=[], help="library knob key=value (ablations)")
     ap.add_argument("--workload", default="query", choices=["query", "hash", "build"],
                     help="query = BASELINE config 2 (the default, the driver's line); hash / build = BASELINE config 4 "
@@ -96,6 +98,15 @@ def seeded_deletes(total_rows, frac, seed):
         h ^= h >> np.uint64(32)
         out.append(o[(h & np.uint64(0xFFFFFFFF)) < np.uint64(thr)])
     return np.concatenate(out) if out else np.zeros(0, np.uint64)
+
+
+def config_dict(a, n_gpus):
+    """`config` of the JSON line: the SAME keys and values in both arms (ours and --impl reference)."""
+    return {"workload": workload_name(a, n_gpus), "rows_per_gpu": a.rows, "queries_per_gpu": a.queries, "dim": a.dim,
+            "top_k": a.topk, "metric": a.metric, "max_node_size": a.max_node_size, "num_trees": a.trees,
+            "delete_frac": a.delete_frac, "seed": a.seed,
+            "data": "synthetic: Philox clustered rows (centre[row % 4096] + 0.25 noise) and queries, seeds 0 / 1",
+            "l2_policy": "every step uses a fresh query batch and streams >1 GB of rows (>> 126 MB L2)"}
 
 
 def workload_name(a, n_gpus):
@@ -223,9 +234,9 @@ def run_reference(a):
         "impl": "reference", "metric": "queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": n_gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times) * (nq_step / sample),
         "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a, n_gpus), "rows_per_gpu": a.rows, "queries_per_gpu": a.queries,
-                   "top_k": a.topk, "metric": a.metric, "max_node_size": a.max_node_size, "num_trees": a.trees,
-                   "data": "Philox clustered (centre[row % 4096] + 0.25 noise)"},
+        "config": config_dict(a, n_gpus),
+        "reference_ms_per_step_is": ("measured" if sample >= nq_step else
+                                     f"extrapolated from a {sample}-query sample of the {nq_step}-query step"),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} of {nq_step} queries per step, {len(times)} steps, in-memory forest built by "
                                    f"the oracle in {t_build:.1f}s (storage engine excluded)"},
@@ -236,6 +247,26 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------------------------------- our arm
+def gather_forest(ix, z, dist, rank, G):
+    """The forest of a sharded index on rank 0: structure and planes are replicated, every rank holds the members (global
+    ordinals) of its own rows; rank 0 merges the member lists leaf by leaf (ascending ordinal, D3)."""
+    f = ix.export_forest()
+    if G == 1:
+        return f
+    parts = [None] * G if rank == 0 else None
+    dist.gather_object((f.leaf_off, f.members), parts, dst=0)
+    if rank != 0:
+        return None
+    nl = f.leaf_off.size - 1
+    lens = sum(np.diff(p[0]) for p in parts)
+    off = np.zeros(nl + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    leaf_of = np.concatenate([np.repeat(np.arange(nl, dtype=np.int64), np.diff(p[0])) for p in parts])
+    members = np.concatenate([p[1] for p in parts])
+    order = np.lexsort((members, leaf_of))
+    return z.Forest(f.nodes, f.roots, f.coef, f.cst, off, members[order])
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -277,6 +308,7 @@ def run_ours(a):
     else:
         ix.add_device(d_rows.data_ptr(), n_local)
     del d_rows
+    torch.cuda.empty_cache()
     dead = None
     if a.delete_frac > 0:   # mixed CRUD (config 5): tombstones before the queries; collective on a sharded index
         dead = seeded_deletes(total_rows, a.delete_frac, a.seed + 3)
@@ -284,18 +316,21 @@ def run_ours(a):
     torch.cuda.synchronize()
     t_build = time.time() - t0
 
-    # ---- query batches (distinct per step, so no step re-reads its predecessor's working set from L2) ----
+    # ---- query batches (distinct per step, so no step re-reads its predecessor's working set from L2).  A rank holds only
+    #      the SLICE of every batch it fronts (queries [lo, hi) of the batch): zb_index_search_slice* ----
     nb = a.steps + a.warmup
-    d_q = torch.empty((nb, nq, a.dim), dtype=torch.float32, device=dev)
+    lo, hi = ix.slice_bounds(nq, rank, G)
+    ns = hi - lo
+    d_q = torch.empty((nb, ns, a.dim), dtype=torch.float32, device=dev)
     for b in range(nb):
-        z.synth_fill_device(local, d_q[b].data_ptr(), b * nq, 1, nq, a.dim, a.seed + 1, 1)
+        z.synth_fill_device(local, d_q[b].data_ptr(), b * nq + lo, 1, ns, a.dim, a.seed + 1, 1)
     h_q = d_q.cpu().pin_memory()
-    d_ord = torch.empty((nq, a.topk), dtype=torch.int64, device=dev)
-    d_bits = torch.empty((nq, a.topk), dtype=torch.int64, device=dev)
-    d_cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
-    h_ord = torch.empty((nq, a.topk), dtype=torch.int64).pin_memory()
-    h_bits = torch.empty((nq, a.topk), dtype=torch.int64).pin_memory()
-    h_cnt = torch.empty((nq,), dtype=torch.int32).pin_memory()
+    d_ord = torch.empty((ns, a.topk), dtype=torch.int64, device=dev)
+    d_bits = torch.empty((ns, a.topk), dtype=torch.int64, device=dev)
+    d_cnt = torch.empty((ns,), dtype=torch.int32, device=dev)
+    h_ord = torch.empty((ns, a.topk), dtype=torch.int64).pin_memory()
+    h_bits = torch.empty((ns, a.topk), dtype=torch.int64).pin_memory()
+    h_cnt = torch.empty((ns,), dtype=torch.int32).pin_memory()
     stream = torch.cuda.ExternalStream(ix.stream_ptr(), device=dev)
 
     def barrier():
@@ -304,10 +339,10 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     def step_device(b):
-        ix.search_batch_device(nq, d_q[b].data_ptr(), a.topk, d_ord.data_ptr(), d_bits.data_ptr(), d_cnt.data_ptr())
+        ix.search_slice_device(nq, d_q[b].data_ptr(), a.topk, d_ord.data_ptr(), d_bits.data_ptr(), d_cnt.data_ptr())
 
     def step_e2e(b):
-        ix.search_batch_ptr(nq, h_q[b].data_ptr(), a.topk, h_ord.data_ptr(), h_bits.data_ptr(), h_cnt.data_ptr())
+        ix.search_slice_ptr(nq, h_q[b].data_ptr(), a.topk, h_ord.data_ptr(), h_bits.data_ptr(), h_cnt.data_ptr())
 
     # ---- device-resident leg: `value` ----
     sampler = ClockSampler(local)
@@ -317,7 +352,7 @@ def run_ours(a):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = {"scan_ms": 0.0, "plan_ms": 0.0, "select_ms": 0.0, "merge_ms": 0.0, "tile_ms": 0.0, "tiles": 0, "moved": 0, "pairs": 0, "visits": 0,
-           "tile_pairs": 0, "scan_launches": 0, "launches": 0}
+           "tile_pairs": 0, "scan_launches": 0, "launches": 0, "unique": 0}
     t_wall = time.perf_counter()
     e0.record(stream)
     for s in range(a.steps):
@@ -327,7 +362,7 @@ def run_ours(a):
         agg["select_ms"] += st["last_ms_select"]; agg["merge_ms"] += st["last_ms_merge"]
         agg["tile_ms"] += st["last_ms_tile_kernel"]; agg["tiles"] += st["last_tiles"]
         agg["moved"] += st["last_moved_bytes"]; agg["pairs"] += st["last_pairs"]; agg["visits"] += st["last_visits"]
-        agg["tile_pairs"] += st["last_tile_pairs"]
+        agg["tile_pairs"] += st["last_tile_pairs"]; agg["unique"] += st["last_unique_bytes"]
         agg["scan_launches"] += st["last_scan_launches"]; agg["launches"] += st["last_total_launches"]
     e1.record(stream)
     barrier()
@@ -339,8 +374,9 @@ def run_ours(a):
     dev_ms, wall_ms = float(t[0]), float(t[1])
     ms_per_step = dev_ms / a.steps
     value = nq * a.steps / (dev_ms / 1e3)
+    d_last = (d_ord.cpu(), d_bits.cpu())
 
-    # ---- end-to-end leg through the host-buffer C ABI call: H2D of the queries, D2H of ids/distances/counts ----
+    # ---- end-to-end leg through the host-buffer C ABI call: H2D of the rank's query slice, D2H of its ids/distances/counts ----
     for b in range(min(2, a.warmup)):
         step_e2e(b)
     barrier()
@@ -355,9 +391,9 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t[0])
     e2e_value = nq * a.steps / (e2e_ms / 1e3)
-    h2d = nq * a.dim * 4
+    h2d = nq * a.dim * 4                      # whole job: every query crosses PCIe once (1/G of them per rank)
     d2h = nq * a.topk * 16 + nq * 4
-    same = bool(torch.equal(h_ord, d_ord.cpu()) and torch.equal(h_bits, d_bits.cpu()))
+    same = bool(torch.equal(h_ord, d_last[0]) and torch.equal(h_bits, d_last[1]))
 
     # ---- roofline of the dominant kernel (the leaf scan): bytes it asks HBM for by design / its event time ----
     peak, peak_src = hbm_peak()
@@ -365,46 +401,56 @@ def run_ours(a):
     # index's stream; its algorithmic bytes = sum over tiles of (leaf rows + tile queries) x 4 x dim, counted by the kernel
     scan_s = (agg["tile_ms"] if agg["tile_ms"] > 0 else agg["scan_ms"]) / 1e3
     achieved = agg["moved"] / scan_s / 1e9 if scan_s > 0 else 0.0
+    traffic = ncu_traffic(a)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(a), "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": "committed ncu --set full capture of this workload (profiles/traffic.json), not this run" if traffic else None,
+                "peak_source": peak_src,
                 "kernel": "tile_scan_kernel (zb_scan.cu)" if agg["tile_ms"] > 0 else "score_pairs kernels (zb_kernels.cu, gather path)",
                 "algorithmic_bytes_per_launch": agg["moved"] // max(1, a.steps), "launches_per_step": 1,
+                "unique_bytes_per_launch": agg["unique"] // max(1, a.steps),
+                "unique_bytes_frac": (agg["unique"] / scan_s / 1e9 / peak) if scan_s > 0 else 0.0,
                 "tiles_per_launch": agg["tiles"] // max(1, a.steps),
                 "kernel_ms_per_launch": scan_s * 1e3 / a.steps,
                 "pair_gbs": agg["pairs"] * a.dim * 4 / scan_s / 1e9 if scan_s > 0 else 0.0,
-                "kernel_share_of_step": scan_s * 1e3 / dev_ms}
+                "kernel_share_of_step": scan_s * 1e3 / dev_ms,
+                "scope": "rank 0" if G > 1 else "the GPU"}
 
-    # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1) ----
+    # ---- CPU baseline (N = 1) + parity on a bounded sample of rank 0's slice of the last timed batch (every N) ----
     cpu = None
     parity = None
-    if rank == 0 and G == 1 and not a.no_cpu_baseline:
+    host_gb = total_rows * a.dim * 4 / 1e9
+    do_cpu = not a.no_cpu_baseline and host_gb <= a.max_oracle_gb   # the oracle needs every row in host memory
+    forest = gather_forest(ix, z, dist, rank, G) if do_cpu else None
+    if rank == 0 and do_cpu:
         from oracle import zb_oracle as zo
 
         cores = os.cpu_count() or 1
         rows = zo.synth(0, 1, total_rows, a.dim, a.seed, 1, cores)
         orc = zo.OracleIndex(a.dim, METRIC_IDS[a.metric], a.max_node_size, a.trees, seed=a.seed)
-        orc.load_forest(rows, ix.export_forest())      # same forest as the GPU arm (build parity is a separate test)
+        orc.load_forest(rows, forest)      # same forest as the GPU arm (build parity is a separate test)
         if dead is not None:
             orc.remove(dead)
         b = a.warmup + a.steps - 1
         qh = h_q[b].numpy()
         # parity: the last timed step's batch (whose GPU results are in the host buffers) against the oracle
         tq = time.time(); orc.search_batch(qh[:64], a.topk, nthreads=cores); per_q = max((time.time() - tq) / 64, 1e-6)
-        sample = int(max(64, min(nq, 2 * a.cpu_seconds / per_q)))   # bounded for configs far larger than the default
+        budget = 2 * a.cpu_seconds if G == 1 else 4.0
+        sample = int(max(64, min(ns, budget / per_q)))   # bounded for configs far larger than the default
         tq = time.time()
         eo, eb, ec = orc.search_batch(qh[:sample], a.topk, nthreads=cores)
         dt = time.time() - tq
-        # baseline: keep going over the other steps' batches until about cpu_seconds of CPU work is spent
-        done_q, spent = sample, dt
-        for bb in range(nb - 1):
-            if spent >= a.cpu_seconds or sample < nq:
-                break
-            tq = time.time(); orc.search_batch(h_q[bb].numpy(), a.topk, nthreads=cores); spent += time.time() - tq; done_q += nq
-        cpu = {"value": done_q / spent, "unit": "queries/s", "cores": cores, "kind": "port",
-               "sample": f"{done_q} queries ({done_q // nq} of the run's {nb} batches), {spent:.1f}s on {cores} threads; "
-                         "restated reference, in-memory forest (storage engine excluded)"}
         go, gb, gc = h_ord.numpy()[:sample].view(np.uint64), h_bits.numpy()[:sample].view(np.uint64), h_cnt.numpy()[:sample]
         parity = bool(np.array_equal(go, eo) and np.array_equal(gb, eb) and np.array_equal(gc.astype(np.uint32), ec))
+        if G == 1:
+            # baseline: keep going over the other steps' batches until about cpu_seconds of CPU work is spent
+            done_q, spent = sample, dt
+            for bb in range(nb - 1):
+                if spent >= a.cpu_seconds or sample < nq:
+                    break
+                tq = time.time(); orc.search_batch(h_q[bb].numpy(), a.topk, nthreads=cores); spent += time.time() - tq; done_q += nq
+            cpu = {"value": done_q / spent, "unit": "queries/s", "cores": cores, "kind": "port",
+                   "sample": f"{done_q} queries ({done_q // nq} of the run's {nb} batches), {spent:.1f}s on {cores} threads; "
+                             "restated reference, in-memory forest (storage engine excluded)"}
 
     per_rank = None
     if G > 1:   # per-rank phase times (ms per step): the step time is the max over ranks, these show where it goes
@@ -419,21 +465,23 @@ def run_ours(a):
             "metric": "queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": G, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a, G), "rows_per_gpu": a.rows, "queries_per_gpu": a.queries,
-                       "top_k": a.topk, "metric": a.metric, "max_node_size": a.max_node_size, "num_trees": a.trees,
-                       "data": "Philox clustered (centre[row % 4096] + 0.25 noise), generated on device",
-                       "l2_policy": "every step uses a fresh query batch and streams >1 GB of rows (>> 126 MB L2)",
-                       "parallelism": f"bucket-sharded x{G} (leaf l on rank l % {G}; plan sharded by query, NCCL allgather of visits and of per-query local top-k)" if G > 1 else "single GPU",
-                       "index_build_s": round(t_build, 2), "leaves": st["leaves"], "planes": st["planes"]},
+            "config": config_dict(a, G),
+            "parallelism": (f"bucket-sharded x{G}: leaf l on rank l % {G}; every rank fronts 1/{G} of the batch (plans it, uploads / "
+                            "downloads only that slice); NCCL: allgather of the query slices and of the compacted visit records, "
+                            "all-to-all of per-query local top-k") if G > 1 else "single GPU",
+            "index": {"build_s": round(t_build, 2), "leaves": st["leaves"], "planes": st["planes"], "device_bytes": st["device_bytes"]},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / a.steps, "matches_device_leg": same},
+                    "ms_per_step": e2e_ms / a.steps, "matches_device_leg": same,
+                    "api": "zb_index_search_slice (host buffers)" if G > 1 else "zb_index_search_batch (host buffers)"},
             "gpu_launches": int(agg["launches"]), "clocks": clocks,
             "phases_ms_per_step": {k: agg[k] / a.steps for k in ("plan_ms", "scan_ms", "tile_ms", "select_ms", "merge_ms")},
             "per_rank_plan_scan_tile_select_merge_ms_pairs_tiles": per_rank,
             "wall_ms_per_step": wall_ms / a.steps, "visits_per_step": agg["visits"] // a.steps,
             "pairs_per_step": agg["pairs"] // a.steps, "tile_pairs_per_step": agg["tile_pairs"] // a.steps,
-            "parity_sample_ok": parity, "device_bytes": st["device_bytes"],
+            "parity_sample_ok": parity,
+            "parity_sample": ("rank 0's slice of the last timed batch vs the oracle on the gathered forest" if do_cpu else
+                              f"skipped: the oracle would hold {host_gb:.0f} GB of rows on the host (--max-oracle-gb {a.max_oracle_gb})"),
         }
         print(json.dumps(line), flush=True)
     if G > 1:

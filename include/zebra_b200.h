@@ -89,8 +89,10 @@ typedef struct zb_stats {
     float last_ms_plan, last_ms_scan, last_ms_select, last_ms_merge, last_ms_total;
     uint32_t last_scan_launches, last_total_launches;
     float last_ms_tile_kernel;    /* the fused leaf-tile scan kernel alone (CUDA events around its launch) */
-    uint32_t last_tiles;          /* (leaf, <= 8 queries) tiles it processed */
-    uint32_t reserved[6];
+    uint32_t last_tiles;          /* (leaf, query tile) tiles it processed */
+    uint32_t reserved0;
+    uint64_t last_unique_bytes;   /* floor of the scan's HBM traffic: row bytes of the DISTINCT leaves the tile kernel visited */
+    uint32_t reserved[3];
 } zb_stats;
 
 const char* zb_last_error(void);
@@ -141,6 +143,17 @@ int zb_index_search_batch(zb_index* index, uint64_t nq, const float* queries, ui
                           uint64_t* out_ordinals, uint64_t* out_dist_bits, uint32_t* out_counts);
 /* Same with queries and outputs resident in HBM (the device-side leg the bench reports as `value`). */
 int zb_index_search_batch_device(zb_index* index, uint64_t nq, const float* d_queries, uint64_t top_k,
+                                 uint64_t* d_out_ordinals, uint64_t* d_out_dist_bits, uint32_t* d_out_counts);
+/* The same call in its scalable form for a sharded index (shard_count = G > 1; collective, every rank calls it with the
+ * same nq_total and top_k): the batch of nq_total queries is cut into G contiguous slices of nqp = ceil(nq_total / G)
+ * queries, rank r fronts slice r = queries [r * nqp, min(nq_total, (r + 1) * nqp)).  `queries` holds ONLY that slice and
+ * the outputs receive ONLY its results ([slice][top_k]), so the host<->device traffic of a rank is 1/G of the batch: the
+ * slices are exchanged between the GPUs (ncclAllGather over NVLink), every rank scores the visits of the leaves it owns,
+ * and the per-query local lists travel to the rank that fronts the query.  Replaces the same par_iter (core.rs:299-303),
+ * one slice of `vectors` per process.  On an unsharded index it is zb_index_search_batch. */
+int zb_index_search_slice(zb_index* index, uint64_t nq_total, const float* slice_queries, uint64_t top_k, uint8_t* out_ids16,
+                          uint64_t* out_ordinals, uint64_t* out_dist_bits, uint32_t* out_counts);
+int zb_index_search_slice_device(zb_index* index, uint64_t nq_total, const float* d_slice_queries, uint64_t top_k,
                                  uint64_t* d_out_ordinals, uint64_t* d_out_dist_bits, uint32_t* d_out_counts);
 
 /* Bucket keys: the root-to-leaf sign path of Hyperplane::point_is_above decisions (lsh.rs:39-43 along

@@ -53,12 +53,22 @@ def main():
             nonlocal ok
             _, ords, bits, counts = ix.search_batch(queries, k, want_ids=False)
             keys, depth, leaf = ix.hash(queries[:32])
+            # the scalable form: every rank passes only the slice of the batch it fronts and gets that slice's results
+            nqs = queries.shape[0] - 3                           # not a multiple of the world size: the last slice is short
+            lo, hi = ix.slice_bounds(nqs, rank, world)
+            _, s_ords, s_bits, s_counts = ix.search_slice(nqs, queries[lo:hi], k, want_ids=False)
+            parts = [None] * world
+            dist.all_gather_object(parts, (s_ords, s_bits, s_counts))
+            if rank == 0:
+                so = np.concatenate([p[0] for p in parts]); sb = np.concatenate([p[1] for p in parts]); sc = np.concatenate([p[2] for p in parts])
+                slice_ok = (so.shape[0] == nqs and np.array_equal(sc, counts[:nqs]) and np.array_equal(so, ords[:nqs])
+                            and np.array_equal(sb, bits[:nqs]))
             if rank == 0:
                 eo, eb, ec = orc.search_batch(queries, k, nthreads=8)
                 ek, ed, el = orc.hash(queries[:32])
                 good = (np.array_equal(counts, ec) and all(np.array_equal(ords[q, :ec[q]], eo[q, :ec[q]]) and
                                                            np.array_equal(bits[q, :ec[q]], eb[q, :ec[q]]) for q in range(len(ec)))
-                        and np.array_equal(keys, ek) and np.array_equal(depth, ed) and np.array_equal(leaf, el))
+                        and np.array_equal(keys, ek) and np.array_equal(depth, ed) and np.array_equal(leaf, el) and slice_ok)
                 print(f"[mgpu G={world}] {mname} n={n} dim={dim} leaf<{mns} trees={trees} k={k} {tag}: {'ok' if good else 'MISMATCH'}", flush=True)
                 ok = ok and good
 

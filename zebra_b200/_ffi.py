@@ -62,11 +62,13 @@ class Stats(C.Structure):
         ("last_total_launches", C.c_uint32),
         ("last_ms_tile_kernel", C.c_float),
         ("last_tiles", C.c_uint32),
-        ("reserved", C.c_uint32 * 6),
+        ("reserved0", C.c_uint32),
+        ("last_unique_bytes", C.c_uint64),
+        ("reserved", C.c_uint32 * 3),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
 
 
 class ImportReport(C.Structure):
@@ -82,7 +84,7 @@ class ImportReport(C.Structure):
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
 
 
 # every symbol include/zebra_b200.h declares: name -> (restype, argtypes)
@@ -105,6 +107,8 @@ SYMBOLS = {
     "zb_index_no_trees": (C.c_int, [_vp, _vp]),
     "zb_index_search_batch": (C.c_int, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp]),
     "zb_index_search_batch_device": (C.c_int, [_vp, _u64, _vp, _u64, _vp, _vp, _vp]),
+    "zb_index_search_slice": (C.c_int, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "zb_index_search_slice_device": (C.c_int, [_vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "zb_index_hash": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "zb_index_hash_device": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "zb_index_forest_sizes": (C.c_int, [_vp, _vp]),

@@ -136,7 +136,10 @@ struct zb_index {
 
     // ---- workspaces ----
     DBuf<u8> cub_tmp;
-    DBuf<u32> w_counts, w_off, w_flag, w_own;
+    DBuf<u32> w_counts, w_off, w_flag, w_loc_off, v_w, x_flags, x_pos;
+    DBuf<uint4> x_send, x_all;  // sharded plan exchange: [header | visit records] of this rank / of every rank
+    u32 x_cap = 0;              // records per rank in an exchange block (grows on demand, kept between batches)
+    DBuf<float> q_all;          // sliced search: the query slices of all ranks
     DBuf<u64> plan_totals;
     DBuf<uint2> w_visits;
     u32 vpw = 32;  // slots per walker in the visit plan: 1 header + up to vpw - 1 visits (grows on demand)
@@ -144,9 +147,9 @@ struct zb_index {
     DBuf<u64> v_pair_len, v_pair_off, pair_key;
     DBuf<u8> v_done;
     DBuf<Entry> entries, gathered;
-    DBuf<float> q_stage, r_stage;
+    DBuf<float> q_stage, r_stage, hash_in;
     DBuf<u64> o_ord, o_bits, h_keys;
-    DBuf<u32> o_counts, h_depths, rm_slots;
+    DBuf<u32> o_counts, o_counts2, h_depths, rm_slots;
     DBuf<int> h_leaves;
     DBuf<u8> rm_flags;
     HBuf<u8> pin;
@@ -335,10 +338,12 @@ struct zb_index {
     }
     // (Re)build the bucket-major store after the forest or the row set changed.  Only forests whose leaves can reach
     // the tile kernel's minimum size get one; an allocation failure degrades to the generic gather path.
+    // Whether the batch may use the fused leaf-tile kernel at all is the CALLER's decision (knobs use_tile_scan /
+    // tile_min_rows are looked at per search call, search_device): this function only answers "is there a store".
     bool ensure_bucket_major() {
         if (bm_valid) return true;
         if (G > 1) return ensure_bucket_major_sharded();
-        if (bm_failed || !built || !p_use_tile_scan || opt.max_node_size < (u64)p_tile_min_rows || !members_used) return false;
+        if (bm_failed || !built || !members_used) return false;
         const u32 nl = (u32)h_leaf_off.size();
         try {
             bm_rows.ensure(members_used * (u64)dimp, 0, stream, true);
@@ -799,8 +804,12 @@ struct zb_index {
 // =====================================================================================================
 namespace zb {
 
+// nq = queries of the whole batch.  Unsharded, or sharded with sliced == false: d_q holds all of them and the outputs hold
+// all nq results (on every rank).  Sharded with sliced == true (the scalable form): d_q holds only the slice this rank
+// fronts, queries [rank * nqp, (rank + 1) * nqp) with nqp = ceil(nq / G); the slices are allgathered over NVLink into
+// q_all, and the outputs receive the results of the rank's own slice only (no result allgather).
 static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64* d_out_ord, u64* d_out_bits,
-                          u32* d_out_counts) {
+                          u32* d_out_counts, bool sliced) {
     cudaStream_t s = ix->stream;
     const u32 T = ix->T;
     ix->st.last_queries = nq;
@@ -808,84 +817,133 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->st.last_moved_bytes = 0;
     ix->st.last_scan_launches = ix->st.last_total_launches = 0;
     if (!nq) return;
-    if (!ix->built || top_k == 0) {
-        launch_fill_u64(d_out_ord, nq * top_k, ZB_SENTINEL, s);
-        launch_fill_u64(d_out_bits, nq * top_k, ZB_SENTINEL, s);
-        ZB_CUDA(cudaMemsetAsync(d_out_counts, 0, nq * 4, s));
-        return;
-    }
     const bool sharded = ix->G > 1;
     const u32 G = ix->G;
+    const u64 nqp = sharded ? (nq + G - 1) / G : nq;
+    const u64 q0 = sharded ? std::min<u64>(nq, (u64)ix->rank * nqp) : 0;
+    const u64 qn = sharded ? std::min<u64>(nqp, nq - q0) : nq;
+    sliced = sliced && sharded;
+    const u64 n_out = sliced ? qn : nq;
+    if (!ix->built || top_k == 0) {
+        launch_fill_u64(d_out_ord, n_out * top_k, ZB_SENTINEL, s);
+        launch_fill_u64(d_out_bits, n_out * top_k, ZB_SENTINEL, s);
+        if (n_out) ZB_CUDA(cudaMemsetAsync(d_out_counts, 0, n_out * 4, s));
+        return;
+    }
     if (sharded) ix->ensure_bucket_major();  // collective (rebuilds the bucket-sharded store after a forest change)
     ForestView f = ix->view();              // the plan walks the replicated forest with GLOBAL live leaf counts
     const ForestView fs = ix->scan_view();  // scoring reads the leaves this rank holds
-    // Sharded: rank r walks queries [r * nqp, (r + 1) * nqp) only and the visit records are allgathered (in place), so the
-    // plan costs 1/G per rank; every rank then holds the identical, complete visit list.
-    const u64 nqp = sharded ? (nq + G - 1) / G : nq;
     const u64 nw = nqp * (sharded ? G : 1) * T;  // walkers, padded to G equal slices
+    const u64 nwl = nqp * T;                     // walkers this rank plans
     ZB_REQUIRE(nw < (1ull << 31), ZB_ERR_INVALID, "batch too large: %llu walkers", (unsigned long long)nw);
     ZB_CUDA(cudaEventRecord(ix->ev[0], s));
     ix->trace_mark("start");
+    const float* d_q_mine = d_q + (sliced ? 0 : q0 * (u64)ix->dimp);  // the queries this rank plans
+    if (sliced) {  // every rank needs every query for the scan of the leaves it owns: allgather of the slices (in place)
+        ix->q_all.ensure(nqp * G * (u64)ix->dimp);
+        float* mine = ix->q_all.p + (u64)ix->rank * nqp * ix->dimp;
+        if (qn) ZB_CUDA(cudaMemcpyAsync(mine, d_q, qn * (u64)ix->dimp * 4, cudaMemcpyDeviceToDevice, s));
+        if (qn < nqp) ZB_CUDA(cudaMemsetAsync(mine + qn * (u64)ix->dimp, 0, (nqp - qn) * (u64)ix->dimp * 4, s));
+        ix->nccl.allgather(mine, ix->q_all.p, nqp * (u64)ix->dimp * 4, s);
+        d_q = ix->q_all.p;
+        ix->trace_mark("allgather of queries");
+    }
     ix->w_counts.ensure(nw + 1);
     ix->w_off.ensure(nw + 1);
     ix->w_flag.ensure(4);
     ix->scan_tmp(nw + 1);
     u32 nv = 0, total_slots = 0;
     u64 total_pairs = 0;
-    const u64 q0 = sharded ? std::min<u64>(nq, (u64)ix->rank * nqp) : 0;
-    const u64 qn = sharded ? std::min<u64>(nqp, nq - q0) : nq;
     // the fused tile kernel takes every visit of a leaf with >= tile_min_rows rows (here) and n' <= 32; known up front, so
     // the compaction can already set those visits aside and the host reads ONE record {flag, visits, slots, pairs} per batch
     // (the scalar metrics 3..11 are a sequential fold per pair: gather path only)
-    const bool tile_on = ix->opt.metric <= ZB_METRIC_L2 && tile_scan_supported(ix->dimp, (u32)top_k) && ix->ensure_bucket_major();
+    const bool tile_on = ix->opt.metric <= ZB_METRIC_L2 && ix->p_use_tile_scan && ix->opt.max_node_size >= (u64)ix->p_tile_min_rows &&
+                         tile_scan_supported(ix->dimp, (u32)top_k) && ix->ensure_bucket_major();
     u64 v_cap = std::max<u64>(ix->v_leaf.cap ? ix->v_leaf.cap - 1 : 0, nw + nw / 2 + 1024);
-    ix->plan_totals.ensure(4);
+    if (sharded && !ix->x_cap) ix->x_cap = (u32)std::min<u64>(nwl + nwl / 2 + 64, 0x7FFFFFFFull);
+    ix->plan_totals.ensure(8);
+    // Three nested retries, each decided from data every rank sees identically or from purely local state:
+    //   replan   (a walker produced more visits than its region holds): flag travels in the exchanged headers;
+    //   re-exchange (a rank packed more records than the exchange block holds): counts travel in the headers;
+    //   re-compact  (more visits land here than the local arrays hold): local arrays only, no collective is repeated.
+    bool need_plan = true, need_exchange = true;
     for (;;) {
-        ix->w_visits.ensure(nw * ix->vpw);
         ix->v_leaf.ensure(v_cap + 1); ix->v_np.ensure(v_cap + 1); ix->v_q.ensure(v_cap + 1);
         ix->v_pair_len.ensure(v_cap + 1); ix->v_pair_off.ensure(v_cap + 1);
         ix->v_ent_len.ensure(v_cap + 1); ix->v_ent_off.ensure(v_cap + 1);
         ix->v_done.ensure(v_cap + 1);
-        ix->scan_tmp(std::max<u64>(nw, v_cap) + 1);
-        ZB_CUDA(cudaMemsetAsync(ix->w_flag.p, 0, 16, s));
-        ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + nw, 0, 4, s));
-        const u64 w0 = (u64)(sharded ? ix->rank : 0) * nqp * T;
-        // padding walkers of my slice (queries beyond nq) must carry an empty header
-        if (sharded && qn < nqp) ZB_CUDA(cudaMemsetAsync(ix->w_visits.p + (w0 + qn * T) * ix->vpw, 0, (nqp - qn) * T * ix->vpw * sizeof(uint2), s));
-        launch_plan(f, d_q + q0 * (u64)ix->dimp, (u32)qn, (u32)top_k, ix->vpw, ix->w_visits.p + w0 * ix->vpw, ix->w_counts.p + w0,
-                    ix->w_flag.p, s);
-        ix->trace_mark("plan walk");
-        if (sharded) {
-            // one collective: every walker's region starts with its header {count, overflow}, so counts and the replan flag
-            // travel with the visit records
-            ix->nccl.allgather(ix->w_visits.p + w0 * ix->vpw, ix->w_visits.p, nqp * T * ix->vpw * sizeof(uint2), s);
-            ix->trace_mark("allgather of visits");
-            // from here on this rank only deals with the visits of the leaves it owns
-            ix->w_own.ensure(nw + 1);
-            ZB_CUDA(cudaMemsetAsync(ix->w_own.p + nw, 0, 4, s));
-            launch_own_counts((u32)nw, ix->vpw, ix->w_visits.p, G, ix->rank, ix->w_counts.p, ix->w_own.p, ix->w_flag.p, s);
+        if (sharded) ix->v_w.ensure(v_cap + 1);
+        ix->scan_tmp(std::max<u64>(std::max<u64>(nw, v_cap), sharded ? (u64)G * ix->x_cap : 0) + 1);
+        if (need_plan) {
+            ix->w_visits.ensure(nwl * ix->vpw);
+            ZB_CUDA(cudaMemsetAsync(ix->w_flag.p, 0, 16, s));
+            ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + nwl, 0, 4, s));
+            // padding walkers of my slice (queries beyond nq) carry an empty header
+            if (sharded && qn < nqp) {
+                ZB_CUDA(cudaMemsetAsync(ix->w_visits.p + qn * T * ix->vpw, 0, (nqp - qn) * T * ix->vpw * sizeof(uint2), s));
+                ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + qn * T, 0, (nqp - qn) * T * 4, s));
+            }
+            launch_plan(f, d_q_mine, (u32)qn, (u32)top_k, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_flag.p, s);
+            ix->trace_mark("plan walk");
+            if (sharded) {
+                ix->w_loc_off.ensure(nwl + 1);
+                exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->w_counts.p, ix->w_loc_off.p, nwl + 1, s);
+            }
+            need_plan = false;
+            need_exchange = true;
+            ix->st.last_total_launches += 1;
         }
-        exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), sharded ? ix->w_own.p : ix->w_counts.p, ix->w_off.p, nw + 1, s);
+        if (sharded && need_exchange) {
+            const u32 C = ix->x_cap;
+            ix->x_send.ensure((size_t)C + 1);
+            ix->x_all.ensure(((size_t)C + 1) * G);
+            ix->x_flags.ensure((size_t)C * G + 1);
+            ix->x_pos.ensure((size_t)C * G + 1);
+            launch_pack_visits((u32)nwl, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_loc_off.p, (u32)((u64)ix->rank * nwl), C,
+                               ix->w_flag.p, ix->x_send.p, s);
+            ix->nccl.allgather(ix->x_send.p, ix->x_all.p, ((size_t)C + 1) * sizeof(uint4), s);
+            ix->trace_mark("allgather of visits");
+            launch_own_flags(G, C, ix->x_all.p, ix->rank, ix->x_flags.p, ix->w_flag.p + 2, s);
+            exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->x_flags.p, ix->x_pos.p, (size_t)C * G + 1, s);
+            need_exchange = false;
+            ix->st.last_total_launches += 3;
+        }
         ZB_CUDA(cudaMemsetAsync(ix->v_pair_len.p, 0, (v_cap + 1) * 8, s));
         ZB_CUDA(cudaMemsetAsync(ix->v_ent_len.p, 0, (v_cap + 1) * 4, s));
-        launch_compact_visits(fs, (u32)nw, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_off.p, G, ix->rank, (u32)v_cap,
-                              tile_on ? 1u : 0u, (u32)ix->p_tile_min_rows, (u32)top_k, ix->v_leaf.p, ix->v_np.p, ix->v_q.p,
-                              ix->v_pair_len.p, ix->v_ent_len.p, ix->v_done.p, s);
+        if (sharded) {
+            const u32 C = ix->x_cap;
+            launch_own_scatter(fs, G, C, ix->x_all.p, ix->x_flags.p, ix->x_pos.p, (u32)v_cap, tile_on ? 1u : 0u, (u32)ix->p_tile_min_rows,
+                               (u32)top_k, ix->v_leaf.p, ix->v_np.p, ix->v_q.p, ix->v_w.p, ix->v_pair_len.p, ix->v_ent_len.p,
+                               ix->v_done.p, s);
+            launch_walker_offsets((u32)nw, ix->x_pos.p + (size_t)C * G, (u32)v_cap, ix->v_w.p, ix->w_off.p, s);
+        } else {
+            exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->w_counts.p, ix->w_off.p, nw + 1, s);
+            launch_compact_visits(fs, (u32)nw, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_off.p, 1, 0, (u32)v_cap,
+                                  tile_on ? 1u : 0u, (u32)ix->p_tile_min_rows, (u32)top_k, ix->v_leaf.p, ix->v_np.p, ix->v_q.p,
+                                  ix->v_pair_len.p, ix->v_ent_len.p, ix->v_done.p, s);
+        }
         exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_ent_len.p, ix->v_ent_off.p, v_cap + 1, s);
         exclusive_scan_u64(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->v_pair_len.p, ix->v_pair_off.p, v_cap + 1, s);
-        launch_plan_totals(ix->w_flag.p, ix->w_off.p, (u32)nw, (u32)v_cap, ix->v_ent_off.p, ix->v_pair_off.p, ix->plan_totals.p, s);
-        u64 h_tot[4] = {0, 0, 0, 0};
-        ZB_CUDA(cudaMemcpyAsync(h_tot, ix->plan_totals.p, 32, cudaMemcpyDeviceToHost, s));
+        launch_plan_totals(sharded ? ix->w_flag.p + 2 : ix->w_flag.p, ix->w_off.p, (u32)nw, (u32)v_cap, ix->v_ent_off.p, ix->v_pair_off.p,
+                           sharded ? ix->w_flag.p + 3 : nullptr, ix->plan_totals.p, s);
+        u64 h_tot[5] = {0, 0, 0, 0, 0};
+        ZB_CUDA(cudaMemcpyAsync(h_tot, ix->plan_totals.p, 40, cudaMemcpyDeviceToHost, s));
         ix->sync();
         ix->st.last_total_launches += 6;
         if (h_tot[0]) {
             ZB_REQUIRE(h_tot[0] == 1, ZB_ERR_STATE, "forest deeper than %d levels", ZB_MAX_DEPTH);
             ix->vpw *= 2;  // a walker produced more visits than its region holds: grow and replan
             ZB_REQUIRE(ix->vpw <= (1u << 16), ZB_ERR_STATE, "visit plan does not converge");
+            need_plan = true;
+            continue;
+        }
+        if (sharded && h_tot[4] > ix->x_cap) {  // some rank packed more records than a block holds: every rank sees it
+            ix->x_cap = (u32)std::min<u64>(h_tot[4] + h_tot[4] / 4 + 64, 0x7FFFFFFFull);
+            need_exchange = true;
             continue;
         }
         nv = (u32)h_tot[1];
-        if (nv > v_cap) {  // more visits than the arrays hold: grow and compact again
+        if (nv > v_cap) {  // more visits than the local arrays hold: grow and compact again (no collective involved)
             v_cap = (u64)nv + nv / 4;
             continue;
         }
@@ -966,13 +1024,18 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
         ZB_CUDA(cudaMemcpyAsync(gath + (u64)ix->rank * 2 * nsk, loc_ord + (u64)ix->rank * nsk, nsk * 8, cudaMemcpyDeviceToDevice, s));
         ZB_CUDA(cudaMemcpyAsync(gath + (u64)ix->rank * 2 * nsk + nsk, loc_bits + (u64)ix->rank * nsk, nsk * 8, cudaMemcpyDeviceToDevice, s));
         ix->trace_mark("all-to-all of local top-k");
-        const u64 blk = 2 * nsk + (nqp + 1) / 2;  // [ord nsk | bits nsk | counts nqp u32]
-        ix->res_all.ensure(blk * G + 1);
-        u64* mine = ix->res_all.p + (u64)ix->rank * blk;
-        launch_merge_gathered((u32)qn, (u32)nqp, (u32)top_k, G, gath, mine, mine + nsk, reinterpret_cast<u32*>(mine + 2 * nsk), s);
-        ix->trace_mark("final merge of my slice");
-        ix->nccl.allgather(mine, ix->res_all.p, blk * 8, s);
-        launch_unpack_results(ix->res_all.p, blk, (u32)nq, (u32)nqp, (u32)top_k, d_out_ord, d_out_bits, d_out_counts, s);
+        if (sliced) {  // the finished slice is this rank's answer: nothing else to exchange
+            launch_merge_gathered((u32)qn, (u32)nqp, (u32)top_k, G, gath, d_out_ord, d_out_bits, d_out_counts, s);
+            ix->trace_mark("final merge of my slice");
+        } else {
+            const u64 blk = 2 * nsk + (nqp + 1) / 2;  // [ord nsk | bits nsk | counts nqp u32]
+            ix->res_all.ensure(blk * G + 1);
+            u64* mine = ix->res_all.p + (u64)ix->rank * blk;
+            launch_merge_gathered((u32)qn, (u32)nqp, (u32)top_k, G, gath, mine, mine + nsk, reinterpret_cast<u32*>(mine + 2 * nsk), s);
+            ix->trace_mark("final merge of my slice");
+            ix->nccl.allgather(mine, ix->res_all.p, blk * 8, s);
+            launch_unpack_results(ix->res_all.p, blk, (u32)nq, (u32)nqp, (u32)top_k, d_out_ord, d_out_bits, d_out_counts, s);
+        }
     } else {
         launch_merge_queries((u32)nq, T, ix->w_off.p, ix->v_ent_off.p, ix->entries.p, (u32)top_k, d_out_ord, d_out_bits,
                              d_out_counts, s);
@@ -981,7 +1044,9 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ix->trace_mark(sharded ? "allgather of results" : "merge");
     float tile_ms = 0.f;
     u32 tiles = 0;
-    tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved, &tile_ms, &tiles);
+    u64 unique_bytes = 0;
+    tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved, &tile_ms, &tiles, &unique_bytes);
+    ix->st.last_unique_bytes = unique_bytes;
     u64 seq_moved = 0;
     if (ix->scan_ws.seq_launched) seq_tile_scan_stats(ix->scan_ws, s, &seq_moved, &tile_ms, &tiles);
     u64 qt_moved = 0;
@@ -1122,20 +1187,25 @@ static void add_common(zb_index* ix, u64 n, const float* src, bool src_on_device
     auto t0 = std::chrono::steady_clock::now();
     ix->use_device();
     if (ix->G > 1) ZB_REQUIRE(ix->comm_ready, ZB_ERR_STATE, "sharded index used before zb_index_comm_init");
-    const int mode = ids16 ? 2 : 1;
-    if (n) {
-        ZB_REQUIRE(ix->id_mode == 0 || ix->id_mode == mode, ZB_ERR_INVALID,
-                   "ids must be supplied for every row of an index or for none");
-        ix->id_mode = mode;
-    }
+    // Ids: an index holds either library-minted ids (mode 1: id <-> ordinal is arithmetic) or registered ids (mode 2: a map).
+    // Rows without ids may be added to a mode-2 index (one reopened from a store, Database::open -> insert_records): their
+    // ids are minted and registered like the caller's.  The whole batch is validated before anything is committed.
+    const bool registered = ids16 || (ix->id_mode == 2 && n);
     const u64 first = ix->total_rows;
-    if (ids16) {
-        for (u64 i = 0; i < n; ++i) {
-            Id16 id{load_be64(ids16 + 16 * i), load_be64(ids16 + 16 * i + 8)};
-            ZB_REQUIRE(ix->ordinal_by_id.find(id) == ix->ordinal_by_id.end(), ZB_ERR_INVALID, "duplicate id at row %llu",
-                       (unsigned long long)i);
-            ix->ordinal_by_id.emplace(id, first + i);
-            ix->ids_by_ordinal.push_back(id);
+    std::vector<Id16> new_ids;
+    if (n) {
+        ZB_REQUIRE(ix->id_mode == 0 || ix->id_mode == (registered ? 2 : 1), ZB_ERR_INVALID,
+                   "ids must be supplied for every row of an index or for none");
+        if (registered) {
+            new_ids.resize(n);
+            std::unordered_map<Id16, u64, Id16Hash> batch;
+            batch.reserve(n);
+            for (u64 i = 0; i < n; ++i) {
+                const Id16 id = ids16 ? Id16{load_be64(ids16 + 16 * i), load_be64(ids16 + 16 * i + 8)} : ix->mint(first + i);
+                ZB_REQUIRE(ix->ordinal_by_id.find(id) == ix->ordinal_by_id.end() && batch.emplace(id, i).second, ZB_ERR_INVALID,
+                           "duplicate id at row %llu", (unsigned long long)i);
+                new_ids[i] = id;
+            }
         }
     }
     // rows this shard owns
@@ -1160,6 +1230,11 @@ static void add_common(zb_index* ix, u64 n, const float* src, bool src_on_device
                                       (size_t)ix->dim * 4, nloc, cudaMemcpyHostToDevice, ix->stream));
             ix->append_rows_device(ix->r_stage.p, ix->dim, nloc, ordinals.data());
         }
+    }
+    if (n) ix->id_mode = registered ? 2 : 1;
+    for (u64 i = 0; i < new_ids.size(); ++i) {
+        ix->ordinal_by_id.emplace(new_ids[i], first + i);
+        ix->ids_by_ordinal.push_back(new_ids[i]);
     }
     ix->total_rows += n;
     for (u64 i = 0; i < n; ++i) {
@@ -1388,21 +1463,12 @@ int zb_index_deduplicate(zb_index* ix, uint64_t* out_count, uint64_t* out_ordina
     ZB_API_END
 }
 
+static void clear_locked(zb_index* ix);
 int zb_index_clear(zb_index* ix) {
     ZB_API_BEGIN
     ZB_REQUIRE(ix, ZB_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(ix->mu);
-    ix->use_device();
-    ix->sync();
-    ix->clear_forest();
-    ix->n_slots = ix->n_live = ix->total_rows = 0;
-    ix->h_ord.clear();
-    ix->h_tomb.clear();
-    ix->flat_bits = 0;
-    ix->flat_nodes = 0;
-    ix->ids_by_ordinal.clear();
-    ix->ordinal_by_id.clear();
-    ix->id_mode = 0;
+    clear_locked(ix);
     ZB_API_END
 }
 
@@ -1426,21 +1492,96 @@ int zb_index_no_trees(zb_index* ix, int* out) {
     ZB_API_END
 }
 
+// Batches beyond 131072 queries are cut into chunks (walker count < 2^31, bounded workspaces).  sliced: see search_device;
+// the chunks of a sliced call are chunks of the whole batch, so every rank sees the same sequence of collectives.
+static void search_entry_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64* d_out_ord, u64* d_out_bits,
+                                u32* d_out_counts, bool sliced) {
+    ix->use_device();
+    const u64 G = ix->G;
+    sliced = sliced && G > 1;
+    const u64 chunk = sliced ? 131072 / G * G : 131072;
+    u64 in_off = 0;  // queries consumed from d_q / results written so far (sliced: of this rank's slices)
+    for (u64 c0 = 0; c0 < nq; c0 += chunk) {
+        const u64 c = std::min<u64>(chunk, nq - c0);
+        u64 mine = c;
+        if (sliced) {
+            const u64 nqp = (c + G - 1) / G, lo = std::min<u64>(c, ix->rank * nqp);
+            mine = std::min<u64>(nqp, c - lo);
+        }
+        const float* q = stage_queries_device(ix, d_q + in_off * (u64)ix->dim, mine);
+        search_device(ix, c, q, top_k, d_out_ord + in_off * top_k, d_out_bits + in_off * top_k, d_out_counts + in_off, sliced);
+        in_off += mine;
+    }
+    ix->sync();
+}
+
 int zb_index_search_batch_device(zb_index* ix, uint64_t nq, const float* d_q, uint64_t top_k, uint64_t* d_out_ord,
                                  uint64_t* d_out_bits, uint32_t* d_out_counts) {
     ZB_API_BEGIN
     ZB_REQUIRE(ix && (d_q || !nq) && ((d_out_ord && d_out_bits && d_out_counts) || !nq), ZB_ERR_INVALID, "NULL argument");
     ZB_REQUIRE(top_k <= ZB_MAX_TOPK, ZB_ERR_INVALID, "top_k %llu exceeds %d", (unsigned long long)top_k, ZB_MAX_TOPK);
     std::lock_guard<std::mutex> lk(ix->mu);
-    ix->use_device();
-    const u64 chunk = 131072;
-    for (u64 q0 = 0; q0 < nq; q0 += chunk) {
-        u64 c = std::min<u64>(chunk, nq - q0);
-        const float* q = stage_queries_device(ix, d_q + q0 * (u64)ix->dim, c);
-        search_device(ix, c, q, top_k, (u64*)d_out_ord + q0 * top_k, (u64*)d_out_bits + q0 * top_k, d_out_counts + q0);
-    }
-    ix->sync();
+    search_entry_device(ix, nq, d_q, top_k, (u64*)d_out_ord, (u64*)d_out_bits, d_out_counts, false);
     ZB_API_END
+}
+int zb_index_search_slice_device(zb_index* ix, uint64_t nq_total, const float* d_q, uint64_t top_k, uint64_t* d_out_ord,
+                                 uint64_t* d_out_bits, uint32_t* d_out_counts) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix, ZB_ERR_INVALID, "NULL argument");
+    ZB_REQUIRE(top_k <= ZB_MAX_TOPK, ZB_ERR_INVALID, "top_k %llu exceeds %d", (unsigned long long)top_k, ZB_MAX_TOPK);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    search_entry_device(ix, nq_total, d_q, top_k, (u64*)d_out_ord, (u64*)d_out_bits, d_out_counts, true);
+    ZB_API_END
+}
+
+// Host buffers in, host buffers out.  sliced: `queries` and the outputs hold this rank's slices only.
+static void search_entry_host(zb_index* ix, u64 nq, const float* queries, u64 top_k, uint8_t* out_ids16, u64* out_ordinals,
+                              u64* out_bits, u32* out_counts, bool sliced) {
+    ix->use_device();
+    cudaStream_t s = ix->stream;
+    const u64 G = ix->G;
+    sliced = sliced && G > 1;
+    const u64 chunk = sliced ? 131072 / G * G : 131072;
+    std::vector<u64> ord_tmp;
+    u64 in_off = 0;
+    for (u64 c0 = 0; c0 < nq; c0 += chunk) {
+        const u64 c = std::min<u64>(chunk, nq - c0);
+        u64 mine = c;
+        if (sliced) {
+            const u64 nqp = (c + G - 1) / G, lo = std::min<u64>(c, ix->rank * nqp);
+            mine = std::min<u64>(nqp, c - lo);
+        }
+        ix->q_stage.ensure(std::max<u64>(1, mine * (u64)ix->dimp));
+        if (mine) {
+            if (ix->dim == ix->dimp) {
+                ZB_CUDA(cudaMemcpyAsync(ix->q_stage.p, queries + in_off * (u64)ix->dim, mine * (u64)ix->dim * 4, cudaMemcpyHostToDevice, s));
+            } else {
+                ZB_CUDA(cudaMemsetAsync(ix->q_stage.p, 0, mine * (u64)ix->dimp * 4, s));
+                ZB_CUDA(cudaMemcpy2DAsync(ix->q_stage.p, (size_t)ix->dimp * 4, queries + in_off * (u64)ix->dim, (size_t)ix->dim * 4,
+                                          (size_t)ix->dim * 4, mine, cudaMemcpyHostToDevice, s));
+            }
+        }
+        ix->o_ord.ensure(mine * top_k + 1);
+        ix->o_bits.ensure(mine * top_k + 1);
+        ix->o_counts2.ensure(mine + 1);
+        search_device(ix, c, ix->q_stage.p, top_k, ix->o_ord.p, ix->o_bits.p, ix->o_counts2.p, sliced);
+        if (!out_ordinals && out_ids16) ord_tmp.resize(mine * top_k);
+        u64* ords = out_ordinals ? out_ordinals + in_off * top_k : ord_tmp.data();
+        if (top_k && mine) {
+            if (out_ordinals || out_ids16) ZB_CUDA(cudaMemcpyAsync(ords, ix->o_ord.p, mine * top_k * 8, cudaMemcpyDeviceToHost, s));
+            ZB_CUDA(cudaMemcpyAsync(out_bits + in_off * top_k, ix->o_bits.p, mine * top_k * 8, cudaMemcpyDeviceToHost, s));
+        }
+        if (mine) ZB_CUDA(cudaMemcpyAsync(out_counts + in_off, ix->o_counts2.p, mine * 4, cudaMemcpyDeviceToHost, s));
+        ix->sync();
+        if (out_ids16) {
+            for (u64 i = 0; i < mine * top_k; ++i) {
+                uint8_t* dst = out_ids16 + (in_off * top_k + i) * 16;
+                if (ords[i] == ZB_SENTINEL) memset(dst, 0xFF, 16);
+                else ix->id_of(ords[i], dst);
+            }
+        }
+        in_off += mine;
+    }
 }
 
 int zb_index_search_batch(zb_index* ix, uint64_t nq, const float* queries, uint64_t top_k, uint8_t* out_ids16,
@@ -1449,47 +1590,21 @@ int zb_index_search_batch(zb_index* ix, uint64_t nq, const float* queries, uint6
     ZB_REQUIRE(ix && (queries || !nq) && ((out_bits && out_counts) || !nq), ZB_ERR_INVALID, "NULL argument");
     ZB_REQUIRE(top_k <= ZB_MAX_TOPK, ZB_ERR_INVALID, "top_k %llu exceeds %d", (unsigned long long)top_k, ZB_MAX_TOPK);
     std::lock_guard<std::mutex> lk(ix->mu);
-    ix->use_device();
-    cudaStream_t s = ix->stream;
-    const u64 chunk = 131072;
-    std::vector<u64> ord_tmp;
-    if (!out_ordinals && out_ids16) ord_tmp.resize(std::min<u64>(chunk, nq) * top_k);
-    for (u64 q0 = 0; q0 < nq; q0 += chunk) {
-        const u64 c = std::min<u64>(chunk, nq - q0);
-        ix->q_stage.ensure(c * (u64)ix->dimp);
-        if (ix->dim == ix->dimp) {
-            ZB_CUDA(cudaMemcpyAsync(ix->q_stage.p, queries + q0 * (u64)ix->dim, c * (u64)ix->dim * 4, cudaMemcpyHostToDevice, s));
-        } else {
-            ZB_CUDA(cudaMemsetAsync(ix->q_stage.p, 0, c * (u64)ix->dimp * 4, s));
-            ZB_CUDA(cudaMemcpy2DAsync(ix->q_stage.p, (size_t)ix->dimp * 4, queries + q0 * (u64)ix->dim, (size_t)ix->dim * 4,
-                                      (size_t)ix->dim * 4, c, cudaMemcpyHostToDevice, s));
-        }
-        ix->o_ord.ensure(c * top_k + 1);
-        ix->o_bits.ensure(c * top_k + 1);
-        ix->o_counts.ensure(c);
-        search_device(ix, c, ix->q_stage.p, top_k, ix->o_ord.p, ix->o_bits.p, ix->o_counts.p);
-        u64* ords = out_ordinals ? (u64*)out_ordinals + q0 * top_k : ord_tmp.data();
-        if (top_k) {
-            if (out_ordinals || out_ids16) ZB_CUDA(cudaMemcpyAsync(ords, ix->o_ord.p, c * top_k * 8, cudaMemcpyDeviceToHost, s));
-            ZB_CUDA(cudaMemcpyAsync(out_bits + q0 * top_k, ix->o_bits.p, c * top_k * 8, cudaMemcpyDeviceToHost, s));
-        }
-        ZB_CUDA(cudaMemcpyAsync(out_counts + q0, ix->o_counts.p, c * 4, cudaMemcpyDeviceToHost, s));
-        ix->sync();
-        if (out_ids16) {
-            for (u64 i = 0; i < c * top_k; ++i) {
-                uint8_t* dst = out_ids16 + (q0 * top_k + i) * 16;
-                if (ords[i] == ZB_SENTINEL) memset(dst, 0xFF, 16);
-                else ix->id_of(ords[i], dst);
-            }
-        }
-    }
+    search_entry_host(ix, nq, queries, top_k, out_ids16, (u64*)out_ordinals, (u64*)out_bits, out_counts, false);
+    ZB_API_END
+}
+int zb_index_search_slice(zb_index* ix, uint64_t nq_total, const float* queries, uint64_t top_k, uint8_t* out_ids16,
+                          uint64_t* out_ordinals, uint64_t* out_bits, uint32_t* out_counts) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix, ZB_ERR_INVALID, "NULL argument");
+    ZB_REQUIRE(top_k <= ZB_MAX_TOPK, ZB_ERR_INVALID, "top_k %llu exceeds %d", (unsigned long long)top_k, ZB_MAX_TOPK);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    search_entry_host(ix, nq_total, queries, top_k, out_ids16, (u64*)out_ordinals, (u64*)out_bits, out_counts, true);
     ZB_API_END
 }
 
-int zb_index_hash_device(zb_index* ix, uint64_t n, const float* d_rows, uint64_t* d_keys, uint32_t* d_depths, int32_t* d_leaves) {
-    ZB_API_BEGIN
-    ZB_REQUIRE(ix && (d_rows || !n), ZB_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+// caller holds ix->mu
+static void hash_device_impl(zb_index* ix, uint64_t n, const float* d_rows, uint64_t* d_keys, uint32_t* d_depths, int32_t* d_leaves) {
     ix->use_device();
     ZB_REQUIRE(ix->built, ZB_ERR_STATE, "hash on an index without trees");
     const float* x = d_rows;
@@ -1522,35 +1637,36 @@ int zb_index_hash_device(zb_index* ix, uint64_t n, const float* d_rows, uint64_t
         if (tot) remap_leaves_kernel<<<(u32)((tot + 255) / 256), 256, 0, ix->stream>>>(d_leaves, tot, ix->d_leaf_export.p);
     }
     ix->sync();
+}
+
+int zb_index_hash_device(zb_index* ix, uint64_t n, const float* d_rows, uint64_t* d_keys, uint32_t* d_depths, int32_t* d_leaves) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (d_rows || !n), ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    hash_device_impl(ix, n, d_rows, d_keys, d_depths, d_leaves);
     ZB_API_END
 }
 
+// The handle stays locked for the whole call: the staging and result buffers are the index's own.
 int zb_index_hash(zb_index* ix, uint64_t n, const float* rows, uint64_t* out_keys, uint32_t* out_depths, int32_t* out_leaves) {
     ZB_API_BEGIN
     ZB_REQUIRE(ix && (rows || !n), ZB_ERR_INVALID, "NULL argument");
-    {
-        std::lock_guard<std::mutex> lk(ix->mu);
-        ix->use_device();
-        ZB_REQUIRE(ix->built, ZB_ERR_STATE, "hash on an index without trees");
-        ix->r_stage.ensure(n * (u64)ix->dimp + 4);
-        ix->h_keys.ensure(n * (u64)ix->T + 1);
-        ix->h_depths.ensure(n * (u64)ix->T + 1);
-        ix->h_leaves.ensure(n * (u64)ix->T + 1);
-    }
-    // stage rows (padded) then reuse the device entry point
-    DBuf<float> tmp;
+    std::lock_guard<std::mutex> lk(ix->mu);
     ix->use_device();
-    tmp.ensure(n * (u64)ix->dim + 4);
+    ZB_REQUIRE(ix->built, ZB_ERR_STATE, "hash on an index without trees");
+    ix->h_keys.ensure(n * (u64)ix->T + 1);
+    ix->h_depths.ensure(n * (u64)ix->T + 1);
+    ix->h_leaves.ensure(n * (u64)ix->T + 1);
+    ix->hash_in.ensure(n * (u64)ix->dim + 4);
     // on the index's stream: a pageable cudaMemcpy on the legacy stream may return before its DMA has landed, and the
     // index's stream is non-blocking, so the hash kernel could otherwise read rows that are not there yet
-    ZB_CUDA(cudaMemcpyAsync(tmp.p, rows, n * (u64)ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
-    ZB_CUDA(cudaStreamSynchronize(ix->stream));
-    int rc = zb_index_hash_device(ix, n, tmp.p, (uint64_t*)ix->h_keys.p, ix->h_depths.p, ix->h_leaves.p);
-    if (rc != ZB_OK) return rc;
+    ZB_CUDA(cudaMemcpyAsync(ix->hash_in.p, rows, n * (u64)ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
+    hash_device_impl(ix, n, ix->hash_in.p, (uint64_t*)ix->h_keys.p, ix->h_depths.p, ix->h_leaves.p);
     const u64 tot = n * (u64)ix->T;
-    if (out_keys) ZB_CUDA(cudaMemcpy(out_keys, ix->h_keys.p, tot * 8, cudaMemcpyDeviceToHost));
-    if (out_depths) ZB_CUDA(cudaMemcpy(out_depths, ix->h_depths.p, tot * 4, cudaMemcpyDeviceToHost));
-    if (out_leaves) ZB_CUDA(cudaMemcpy(out_leaves, ix->h_leaves.p, tot * 4, cudaMemcpyDeviceToHost));
+    if (out_keys) ZB_CUDA(cudaMemcpyAsync(out_keys, ix->h_keys.p, tot * 8, cudaMemcpyDeviceToHost, ix->stream));
+    if (out_depths) ZB_CUDA(cudaMemcpyAsync(out_depths, ix->h_depths.p, tot * 4, cudaMemcpyDeviceToHost, ix->stream));
+    if (out_leaves) ZB_CUDA(cudaMemcpyAsync(out_leaves, ix->h_leaves.p, tot * 4, cudaMemcpyDeviceToHost, ix->stream));
+    ix->sync();
     ZB_API_END
 }
 
@@ -1624,26 +1740,106 @@ int zb_index_export_forest(zb_index* ix, int32_t* nodes, int32_t* roots, float* 
     ZB_API_END
 }
 
+static void clear_locked(zb_index* ix) {
+    ix->use_device();
+    ix->sync();
+    ix->clear_forest();
+    ix->n_slots = ix->n_live = ix->total_rows = 0;
+    ix->h_ord.clear();
+    ix->h_tomb.clear();
+    ix->flat_bits = 0;
+    ix->flat_nodes = 0;
+    ix->ids_by_ordinal.clear();
+    ix->ordinal_by_id.clear();
+    ix->id_mode = 0;
+}
+
+// Everything is validated against the caller's arrays BEFORE the index is touched (a rejected forest leaves the index as
+// it was), and the replace happens under one lock: node ranges, leaf_off monotone, every leaf referenced by exactly one
+// node reachable from a root, depth <= ZB_MAX_DEPTH, no cycle, every row exactly once in every tree, ids distinct.
 int zb_index_load_forest(zb_index* ix, uint64_t n, const float* rows, const uint8_t* ids16, const int64_t* sizes4,
                          const int32_t* nodes, const int32_t* roots, const float* coef, const float* cst,
                          const int64_t* leaf_off, const uint64_t* members) {
     ZB_API_BEGIN
     ZB_REQUIRE(ix && sizes4 && nodes && roots && leaf_off && (rows || !n), ZB_ERR_INVALID, "NULL argument");
-    int rc = zb_index_clear(ix);
-    if (rc != ZB_OK) return rc;
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->use_device();
     if (ix->G > 1) ZB_REQUIRE(ix->comm_ready, ZB_ERR_STATE, "sharded index used before zb_index_comm_init");
     const int64_t nn = sizes4[0], npl = sizes4[1], nl = sizes4[2], nm = sizes4[3];
     ZB_REQUIRE(nn >= ix->T && npl >= 0 && nl >= 1 && nm >= 0, ZB_ERR_INVALID, "bad forest sizes");
-    // rows: ordinals 0..n-1
-    ix->id_mode = ids16 ? 2 : 1;
-    if (ids16)
-        for (u64 i = 0; i < n; ++i) {
-            Id16 id{load_be64(ids16 + 16 * i), load_be64(ids16 + 16 * i + 8)};
-            ix->ordinal_by_id.emplace(id, i);
-            ix->ids_by_ordinal.push_back(id);
+    ZB_REQUIRE((members && coef && cst) || (!nm && !npl), ZB_ERR_INVALID, "NULL argument");
+    const int T = ix->T;
+    // ---- validation pass (no index state is modified) ----
+    std::vector<int4> v_nodes((size_t)nn);
+    for (int64_t i = 0; i < nn; ++i) {
+        const int32_t* nd = nodes + 4 * i;
+        if (nd[0] >= 0) {
+            ZB_REQUIRE(nd[0] < npl && nd[1] >= 0 && nd[1] < nn && nd[2] >= 0 && nd[2] < nn, ZB_ERR_INVALID, "node %lld malformed", (long long)i);
+        } else {
+            ZB_REQUIRE(nd[3] >= 0 && nd[3] < nl, ZB_ERR_INVALID, "leaf node %lld malformed", (long long)i);
         }
+        v_nodes[i] = make_int4(nd[0], nd[1], nd[2], nd[3]);
+    }
+    ZB_REQUIRE(leaf_off[0] == 0, ZB_ERR_INVALID, "leaf_off must start at 0");
+    for (int64_t l = 0; l < nl; ++l)
+        ZB_REQUIRE(leaf_off[l] <= leaf_off[l + 1] && leaf_off[l + 1] <= nm, ZB_ERR_INVALID, "leaf_off not monotone");
+    for (int64_t j = 0; j < leaf_off[nl]; ++j) ZB_REQUIRE(members[j] < n, ZB_ERR_INVALID, "member ordinal out of range");
+    std::vector<u64> v_key((size_t)nl, 0);
+    std::vector<int> v_depth((size_t)nl, 0), v_node((size_t)nl, -1), v_tree((size_t)nl, 0);
+    {
+        struct Fr { int node; u64 key; int depth; };
+        std::vector<Fr> stack;
+        std::vector<u8> in_tree((size_t)n);
+        size_t visited = 0;
+        for (int t = 0; t < T; ++t) {
+            ZB_REQUIRE(roots[t] >= 0 && roots[t] < nn, ZB_ERR_INVALID, "root %d out of range", t);
+            std::fill(in_tree.begin(), in_tree.end(), 0);
+            u64 rows_in_tree = 0;
+            stack.push_back(Fr{roots[t], root_key(ix->opt.seed, t), 0});
+            while (!stack.empty()) {
+                Fr fr = stack.back();
+                stack.pop_back();
+                ZB_REQUIRE(++visited <= (size_t)nn, ZB_ERR_INVALID, "forest has a cycle or shares nodes between trees");
+                ZB_REQUIRE(fr.depth <= ZB_MAX_DEPTH, ZB_ERR_INVALID, "tree %d deeper than %d levels", t, ZB_MAX_DEPTH);
+                const int4 nd = v_nodes[fr.node];
+                if (nd.x >= 0) {
+                    stack.push_back(Fr{nd.z, child_key(fr.key, 1), fr.depth + 1});
+                    stack.push_back(Fr{nd.y, child_key(fr.key, 0), fr.depth + 1});
+                } else {
+                    ZB_REQUIRE(v_node[nd.w] < 0, ZB_ERR_INVALID, "leaf %d referenced twice", nd.w);
+                    v_node[nd.w] = fr.node;
+                    v_key[nd.w] = fr.key;
+                    v_depth[nd.w] = fr.depth;
+                    v_tree[nd.w] = t;
+                    for (int64_t j = leaf_off[nd.w]; j < leaf_off[nd.w + 1]; ++j) {
+                        ZB_REQUIRE(!in_tree[members[j]], ZB_ERR_INVALID, "row %llu is in two leaves of tree %d",
+                                   (unsigned long long)members[j], t);
+                        in_tree[members[j]] = 1;
+                        ++rows_in_tree;
+                    }
+                }
+            }
+            ZB_REQUIRE(rows_in_tree == n, ZB_ERR_INVALID, "tree %d holds %llu of the %llu rows", t,
+                       (unsigned long long)rows_in_tree, (unsigned long long)n);
+        }
+        for (int64_t l = 0; l < nl; ++l)
+            ZB_REQUIRE(v_node[l] >= 0, ZB_ERR_INVALID, "leaf %lld is not reachable from any root", (long long)l);
+    }
+    std::vector<Id16> v_ids;
+    std::unordered_map<Id16, u64, Id16Hash> v_map;
+    if (ids16) {
+        v_ids.resize((size_t)n);
+        v_map.reserve((size_t)n);
+        for (u64 i = 0; i < n; ++i) {
+            v_ids[i] = Id16{load_be64(ids16 + 16 * i), load_be64(ids16 + 16 * i + 8)};
+            ZB_REQUIRE(v_map.emplace(v_ids[i], i).second, ZB_ERR_INVALID, "duplicate id at row %llu", (unsigned long long)i);
+        }
+    }
+    // ---- commit ----
+    clear_locked(ix);
+    ix->id_mode = n ? (ids16 ? 2 : 1) : 0;
+    ix->ids_by_ordinal.swap(v_ids);
+    ix->ordinal_by_id.swap(v_map);
     std::vector<u64> ordinals;
     for (u64 i = ix->rank; i < n; i += ix->G) ordinals.push_back(i);
     if (!ordinals.empty()) {
@@ -1653,60 +1849,23 @@ int zb_index_load_forest(zb_index* ix, uint64_t n, const float* rows, const uint
         ix->append_rows_device(ix->r_stage.p, ix->dim, ordinals.size(), ordinals.data());
     }
     ix->total_rows = n;
-    // structure: validate, compute keys/depths by traversal
-    ix->h_nodes.resize(nn);
-    for (int64_t i = 0; i < nn; ++i) {
-        const int32_t* nd = nodes + 4 * i;
-        if (nd[0] >= 0) {
-            ZB_REQUIRE(nd[0] < npl && nd[1] >= 0 && nd[1] < nn && nd[2] >= 0 && nd[2] < nn, ZB_ERR_INVALID, "node %lld malformed", (long long)i);
-        } else {
-            ZB_REQUIRE(nd[3] >= 0 && nd[3] < nl, ZB_ERR_INVALID, "leaf node %lld malformed", (long long)i);
-        }
-        ix->h_nodes[i] = make_int4(nd[0], nd[1], nd[2], nd[3]);
-    }
+    ix->h_nodes.swap(v_nodes);
     ix->h_leaf_off.assign(nl, 0); ix->h_leaf_len.assign(nl, 0); ix->h_leaf_cap.assign(nl, 0);
-    ix->h_leaf_key.assign(nl, 0); ix->h_leaf_depth.assign(nl, 0); ix->h_leaf_node.assign(nl, -1); ix->h_leaf_tree.assign(nl, 0);
+    ix->h_leaf_key.swap(v_key); ix->h_leaf_depth.swap(v_depth); ix->h_leaf_node.swap(v_node); ix->h_leaf_tree.swap(v_tree);
     // local member lists (owned rows only), leaf-major
     ix->h_members.clear();
+    std::vector<u32> slot_leaf_h((size_t)T * std::max<u64>(ix->n_slots, 1), 0);
     for (int64_t l = 0; l < nl; ++l) {
-        ZB_REQUIRE(leaf_off[l] <= leaf_off[l + 1] && leaf_off[l + 1] <= nm, ZB_ERR_INVALID, "leaf_off not monotone");
         ix->h_leaf_off[l] = (long long)ix->h_members.size();
-        for (int64_t j = leaf_off[l]; j < leaf_off[l + 1]; ++j) {
-            ZB_REQUIRE(members[j] < n, ZB_ERR_INVALID, "member ordinal out of range");
+        for (int64_t j = leaf_off[l]; j < leaf_off[l + 1]; ++j)
             if (ix->owns(members[j])) ix->h_members.push_back((u32)ix->slot_of(members[j]));
-        }
         ix->h_leaf_len[l] = ix->h_leaf_cap[l] = (u32)(ix->h_members.size() - ix->h_leaf_off[l]);
         // invariant of the bucket-major store: inside a leaf, position order == ordinal order (ties by id, D3)
         std::sort(ix->h_members.begin() + ix->h_leaf_off[l], ix->h_members.end());
+        const size_t t = (size_t)ix->h_leaf_tree[l];
+        for (u32 j = 0; j < ix->h_leaf_len[l]; ++j) slot_leaf_h[t * ix->n_slots + ix->h_members[ix->h_leaf_off[l] + j]] = (u32)l;
     }
-    struct Fr { int node; u64 key; int depth; };
-    std::vector<Fr> stack;
-    std::vector<u32> slot_leaf_h((size_t)ix->T * std::max<u64>(ix->n_slots, 1), 0);
-    for (int t = 0; t < ix->T; ++t) {
-        ZB_REQUIRE(roots[t] >= 0 && roots[t] < nn, ZB_ERR_INVALID, "root %d out of range", t);
-        ix->h_roots[t] = roots[t];
-        stack.push_back(Fr{roots[t], root_key(ix->opt.seed, t), 0});
-        size_t visited = 0;
-        while (!stack.empty()) {
-            Fr fr = stack.back();
-            stack.pop_back();
-            ZB_REQUIRE(++visited <= (size_t)nn, ZB_ERR_INVALID, "forest has a cycle");
-            ZB_REQUIRE(fr.depth <= ZB_MAX_DEPTH, ZB_ERR_INVALID, "tree %d deeper than %d levels", t, ZB_MAX_DEPTH);
-            int4 nd = ix->h_nodes[fr.node];
-            if (nd.x >= 0) {
-                stack.push_back(Fr{nd.z, child_key(fr.key, 1), fr.depth + 1});
-                stack.push_back(Fr{nd.y, child_key(fr.key, 0), fr.depth + 1});
-            } else {
-                ZB_REQUIRE(ix->h_leaf_node[nd.w] < 0, ZB_ERR_INVALID, "leaf %d referenced twice", nd.w);
-                ix->h_leaf_node[nd.w] = fr.node;
-                ix->h_leaf_key[nd.w] = fr.key;
-                ix->h_leaf_depth[nd.w] = fr.depth;
-                ix->h_leaf_tree[nd.w] = t;
-                for (u32 j = 0; j < ix->h_leaf_len[nd.w]; ++j)
-                    slot_leaf_h[(size_t)t * ix->n_slots + ix->h_members[ix->h_leaf_off[nd.w] + j]] = (u32)nd.w;
-            }
-        }
-    }
+    for (int t = 0; t < T; ++t) ix->h_roots[t] = roots[t];
     ix->n_planes = (u64)npl;
     ix->d_coef.ensure(std::max<u64>(1, (u64)npl * ix->dimp));
     ix->d_cst.ensure(std::max<u64>(1, (u64)npl));
@@ -1722,7 +1881,7 @@ int zb_index_load_forest(zb_index* ix, uint64_t n, const float* rows, const uint
     if (ix->members_used)
         ZB_CUDA(cudaMemcpyAsync(ix->d_members.p, ix->h_members.data(), ix->members_used * 4, cudaMemcpyHostToDevice, ix->stream));
     if (ix->n_slots)
-        ZB_CUDA(cudaMemcpy2DAsync(ix->slot_leaf.p, ix->slot_stride * 4, slot_leaf_h.data(), ix->n_slots * 4, ix->n_slots * 4, ix->T,
+        ZB_CUDA(cudaMemcpy2DAsync(ix->slot_leaf.p, ix->slot_stride * 4, slot_leaf_h.data(), ix->n_slots * 4, ix->n_slots * 4, T,
                                   cudaMemcpyHostToDevice, ix->stream));
     ix->sync();
     ix->built = true;

@@ -85,25 +85,6 @@ void launch_plan(const ForestView& f, const float* d_queries, u32 nq, u32 top_k,
     plan_walk_kernel<<<(nwalkers + 31) / 32, 128, 0, s>>>(f, d_queries, nq, top_k, vpw, d_wvisits, d_wcounts, d_overflow);
 }
 
-// Sharded: the visit records of all walkers are on every rank; a rank keeps only the visits of the leaves it owns
-// (leaf % G == rank).  own_counts gives the per-walker counts the compaction offsets are scanned from.
-__global__ void own_counts_kernel(u32 nwalkers, u32 vpw, const uint2* __restrict__ wvisits, u32 G, u32 rank,
-                                  u32* __restrict__ wcounts, u32* __restrict__ wown, u32* __restrict__ overflow) {
-    u32 w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwalkers) return;
-    const uint2 hdr = wvisits[(size_t)w * vpw];
-    const u32 c = hdr.x;
-    if (hdr.y) atomicMax(overflow, hdr.y);
-    u32 n = 0;
-    for (u32 i = 0; i < c; ++i) n += (wvisits[(size_t)w * vpw + 1 + i].x % G == rank) ? 1u : 0u;
-    wcounts[w] = c;
-    wown[w] = n;
-}
-void launch_own_counts(u32 nwalkers, u32 vpw, const uint2* d_wvisits, u32 G, u32 rank, u32* d_wcounts, u32* d_wown,
-                       u32* d_overflow, cudaStream_t s) {
-    if (!nwalkers) return;
-    own_counts_kernel<<<(nwalkers + 255) / 256, 256, 0, s>>>(nwalkers, vpw, d_wvisits, G, rank, d_wcounts, d_wown, d_overflow);
-}
 // Visit records -> flat visit arrays.  A visit the fused tile kernel will take (tile_on, leaf holds >= min_rows rows here,
 // n' <= kmax) is marked done with no generic-path pairs right here, so that the entry-slot and pair totals are known
 // before any scoring starts and the host needs ONE readback per batch.  Writes are guarded by `cap` (the host grows the
@@ -141,19 +122,119 @@ void launch_compact_visits(const ForestView& f, u32 nwalkers, u32 vpw, const uin
     compact_visits_kernel<<<(nwalkers + 255) / 256, 256, 0, s>>>(f, nwalkers, vpw, d_wvisits, d_wcounts, d_woff, G, rank, cap, tile_on,
                                                                  min_rows, kmax, d_vleaf, d_vnp, d_vq, d_pair_len, d_ent_len, d_vdone);
 }
-// {replan flag, visits, entry slots, generic-path pairs} of the batch in one 32-byte record
+// ---- sharded plan exchange: compacted visit records instead of padded per-walker regions ----
+// A rank packs the visits of the walkers it planned into [header | records]: header = {visits, replan flag}; a record =
+// {leaf, n', global walker}.  One ncclAllGather of (1 + cap) records per rank puts every rank's block on every rank; the
+// header travels with the records, so the decisions "replan" and "grow cap" are taken from replicated data (identical on
+// every rank: no rank can leave the loop alone).
+__global__ void pack_visits_kernel(u32 nwalkers, u32 vpw, const uint2* __restrict__ wvisits, const u32* __restrict__ wcounts,
+                                   const u32* __restrict__ woff, u32 walker_base, u32 cap, const u32* __restrict__ flag,
+                                   uint4* __restrict__ out) {
+    const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w == 0) out[0] = make_uint4(woff[nwalkers], flag[0], 0u, 0u);
+    if (w >= nwalkers) return;
+    const u32 c = wcounts[w];
+    u32 base = woff[w];
+    for (u32 i = 0; i < c; ++i, ++base) {
+        if (base >= cap) break;
+        const uint2 v = wvisits[(size_t)w * vpw + 1 + i];
+        out[1 + base] = make_uint4(v.x, v.y, walker_base + w, 0u);
+    }
+}
+void launch_pack_visits(u32 nwalkers, u32 vpw, const uint2* d_wvisits, const u32* d_wcounts, const u32* d_woff, u32 walker_base,
+                        u32 cap, const u32* d_flag, uint4* d_out, cudaStream_t s) {
+    pack_visits_kernel<<<(nwalkers + 256) / 256, 256, 0, s>>>(nwalkers, vpw, d_wvisits, d_wcounts, d_woff, walker_base, cap, d_flag, d_out);
+}
+// flags[r * cap + i] = record i of rank r exists and its leaf lives here; summary = {max replan flag, max visit count}
+__global__ void own_flags_kernel(u32 G, u32 cap, const uint4* __restrict__ all, u32 rank, u32* __restrict__ flags,
+                                 u32* __restrict__ summary) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        u32 f = 0, c = 0;
+        for (u32 r = 0; r < G; ++r) {
+            const uint4 h = all[(size_t)r * (cap + 1)];
+            f = max(f, h.y);
+            c = max(c, h.x);
+        }
+        summary[0] = f;
+        summary[1] = c;
+    }
+    if (i > G * cap) return;
+    u32 fl = 0;
+    if (i < G * cap) {
+        const u32 r = i / cap, j = i - r * cap;
+        const uint4* blk = all + (size_t)r * (cap + 1);
+        if (j < blk[0].x) fl = (blk[1 + j].x % G == rank) ? 1u : 0u;
+    }
+    flags[i] = fl;  // [G * cap] = 0: the exclusive scan leaves the total there
+}
+void launch_own_flags(u32 G, u32 cap, const uint4* d_all, u32 rank, u32* d_flags, u32* d_summary, cudaStream_t s) {
+    own_flags_kernel<<<(G * cap + 256) / 256, 256, 0, s>>>(G, cap, d_all, rank, d_flags, d_summary);
+}
+// the records this rank owns -> flat visit arrays, in (planning rank, walker) order = global walker order
+__global__ void own_scatter_kernel(ForestView f, u32 G, u32 cap, const uint4* __restrict__ all, const u32* __restrict__ flags,
+                                   const u32* __restrict__ pos, u32 vcap, u32 tile_on, u32 min_rows, u32 kmax,
+                                   u32* __restrict__ vleaf, u32* __restrict__ vnp, u32* __restrict__ vq, u32* __restrict__ vw,
+                                   u64* __restrict__ pair_len, u32* __restrict__ ent_len, u8* __restrict__ vdone) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * cap || !flags[i]) return;
+    const u32 base = pos[i];
+    if (base >= vcap) return;
+    const u32 r = i / cap, j = i - r * cap;
+    const uint4 v = all[(size_t)r * (cap + 1) + 1 + j];
+    const u32 len = f.leaf_len[v.x];
+    const bool tiled = tile_on && len >= min_rows && v.y <= kmax;
+    vleaf[base] = v.x;
+    vnp[base] = v.y;
+    vq[base] = v.z / (u32)f.num_trees;
+    vw[base] = v.z;
+    pair_len[base] = tiled ? 0ull : (u64)len;
+    vdone[base] = tiled ? 1 : 0;
+    const u32 live = f.leaf_plan[v.x];
+    ent_len[base] = live < v.y ? live : v.y;
+}
+void launch_own_scatter(const ForestView& f, u32 G, u32 cap, const uint4* d_all, const u32* d_flags, const u32* d_pos, u32 vcap,
+                        u32 tile_on, u32 min_rows, u32 kmax, u32* d_vleaf, u32* d_vnp, u32* d_vq, u32* d_vw, u64* d_pair_len,
+                        u32* d_ent_len, u8* d_vdone, cudaStream_t s) {
+    own_scatter_kernel<<<(G * cap + 255) / 256, 256, 0, s>>>(f, G, cap, d_all, d_flags, d_pos, vcap, tile_on, min_rows, kmax, d_vleaf,
+                                                             d_vnp, d_vq, d_vw, d_pair_len, d_ent_len, d_vdone);
+}
+// woff[w] = first visit of walker w (visits are in walker order), woff[nwalkers] = number of visits
+__global__ void walker_offsets_kernel(u32 nwalkers, const u32* __restrict__ nv_ptr, u32 vcap, const u32* __restrict__ vw,
+                                      u32* __restrict__ woff) {
+    const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > nwalkers) return;
+    const u32 nv = *nv_ptr;
+    if (w == nwalkers || nv > vcap) {  // nv > vcap: the host grows the arrays and compacts again
+        woff[w] = w == nwalkers ? nv : 0u;
+        return;
+    }
+    u32 lo = 0, hi = nv;  // first index with vw[index] >= w
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (vw[mid] < w) lo = mid + 1; else hi = mid;
+    }
+    woff[w] = lo;
+}
+void launch_walker_offsets(u32 nwalkers, const u32* d_nv, u32 vcap, const u32* d_vw, u32* d_woff, cudaStream_t s) {
+    walker_offsets_kernel<<<(nwalkers + 256) / 256, 256, 0, s>>>(nwalkers, d_nv, vcap, d_vw, d_woff);
+}
+
+// {replan flag, visits, entry slots, generic-path pairs, largest per-rank visit count (sharded)} of the batch in one record
 __global__ void plan_totals_kernel(const u32* __restrict__ flag, const u32* __restrict__ woff, u32 nwalkers, u32 cap,
-                                   const u32* __restrict__ ent_off, const u64* __restrict__ pair_off, u64* __restrict__ out) {
+                                   const u32* __restrict__ ent_off, const u64* __restrict__ pair_off, const u32* __restrict__ maxcount,
+                                   u64* __restrict__ out) {
     const u32 nv = woff[nwalkers];
     const u32 at = nv < cap ? nv : cap;
     out[0] = flag[0];
     out[1] = nv;
     out[2] = ent_off[at];
     out[3] = pair_off[at];
+    out[4] = maxcount ? maxcount[0] : 0u;
 }
 void launch_plan_totals(const u32* d_flag, const u32* d_woff, u32 nwalkers, u32 cap, const u32* d_ent_off, const u64* d_pair_off,
-                        u64* d_out, cudaStream_t s) {
-    plan_totals_kernel<<<1, 1, 0, s>>>(d_flag, d_woff, nwalkers, cap, d_ent_off, d_pair_off, d_out);
+                        const u32* d_maxcount, u64* d_out, cudaStream_t s) {
+    plan_totals_kernel<<<1, 1, 0, s>>>(d_flag, d_woff, nwalkers, cap, d_ent_off, d_pair_off, d_maxcount, d_out);
 }
 
 // =====================================================================================================

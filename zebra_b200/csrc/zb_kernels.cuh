@@ -55,13 +55,19 @@ struct RecvSeg {      // rows of one (source rank, owned leaf) pair in the recei
 // ---- plan (tree_result control flow, lsh.rs:290-348) ----
 void launch_plan(const ForestView& f, const float* d_queries, u32 nq, u32 top_k, u32 vpw, uint2* d_wvisits,
                  u32* d_wcounts, u32* d_overflow, cudaStream_t s);
-void launch_own_counts(u32 nwalkers, u32 vpw, const uint2* d_wvisits, u32 G, u32 rank, u32* d_wcounts, u32* d_wown,
-                       u32* d_overflow, cudaStream_t s);
+// sharded plan exchange (compacted visit records, header first): pack -> ncclAllGather -> flags -> scan -> scatter -> offsets
+void launch_pack_visits(u32 nwalkers, u32 vpw, const uint2* d_wvisits, const u32* d_wcounts, const u32* d_woff, u32 walker_base,
+                        u32 cap, const u32* d_flag, uint4* d_out, cudaStream_t s);
+void launch_own_flags(u32 G, u32 cap, const uint4* d_all, u32 rank, u32* d_flags, u32* d_summary, cudaStream_t s);
+void launch_own_scatter(const ForestView& f, u32 G, u32 cap, const uint4* d_all, const u32* d_flags, const u32* d_pos, u32 vcap,
+                        u32 tile_on, u32 min_rows, u32 kmax, u32* d_vleaf, u32* d_vnp, u32* d_vq, u32* d_vw, u64* d_pair_len,
+                        u32* d_ent_len, u8* d_vdone, cudaStream_t s);
+void launch_walker_offsets(u32 nwalkers, const u32* d_nv, u32 vcap, const u32* d_vw, u32* d_woff, cudaStream_t s);
 void launch_compact_visits(const ForestView& f, u32 nwalkers, u32 vpw, const uint2* d_wvisits, const u32* d_wcounts,
                            const u32* d_woff, u32 G, u32 rank, u32 cap, u32 tile_on, u32 min_rows, u32 kmax, u32* d_vleaf,
                            u32* d_vnp, u32* d_vq, u64* d_pair_len, u32* d_ent_len, u8* d_vdone, cudaStream_t s);
 void launch_plan_totals(const u32* d_flag, const u32* d_woff, u32 nwalkers, u32 cap, const u32* d_ent_off, const u64* d_pair_off,
-                        u64* d_out, cudaStream_t s);
+                        const u32* d_maxcount, u64* d_out, cudaStream_t s);
 // ---- scoring of (visit, member) pairs, generic path ----
 void launch_score_pairs(const ForestView& f, int metric, int power, const float* d_queries, u32 nv, const u32* d_vleaf,
                         const u32* d_vq, const u64* d_pair_off, u64 total_pairs, u64* d_pair_key, cudaStream_t s);

@@ -557,11 +557,13 @@ __global__ void ts_scatter_kernel(ForestView f, u32 nv, const u32* __restrict__ 
 }
 __global__ void ts_filltiles_kernel(u32 nleaves, const u32* __restrict__ leaf_count, const u32* __restrict__ leaf_start,
                                     const u32* __restrict__ tile_start, u32 tq, u32* __restrict__ tile_leaf,
-                                    u32* __restrict__ tile_first, u32* __restrict__ tile_count) {
+                                    u32* __restrict__ tile_first, u32* __restrict__ tile_count, const u32* __restrict__ leaf_len,
+                                    u64 row_bytes, u64* __restrict__ unique_bytes) {
     u32 l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nleaves) return;
     const u32 c = leaf_count[l], ts = tile_start[l];
     if (!c) return;
+    atomicAdd(unique_bytes, (u64)leaf_len[l] * row_bytes);  // the floor of the scan's HBM traffic: every visited leaf once
     const u32 nt = (c + tq - 1) / tq;   // full tiles first, the remainder last (cost is per started query group)
     for (u32 j = 0, done = 0; j < nt; ++j) {
         const u32 n = c - done < tq ? c - done : tq;
@@ -675,7 +677,8 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
     ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, tq, ws.tile_per_leaf.p);
     cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
     ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, tq,
-                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p);
+                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, f.leaf_len,
+                                                              (u64)f.dimp * 4ull, reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
 
     TileParams tp;
     tp.tile_leaf = ws.tile_leaf.p;
@@ -725,19 +728,20 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
 // Statistics of the last tile_scan launch (visits, scored pairs, bytes asked of HBM by design); call after the
 // stream has been synchronised.
 void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes, float* kernel_ms,
-                     u32* tiles) {
-    *tile_visits = *tile_pairs = *moved_bytes = 0;
+                     u32* tiles, u64* unique_bytes) {
+    *tile_visits = *tile_pairs = *moved_bytes = *unique_bytes = 0;
     *kernel_ms = 0.f;
     *tiles = 0;
     if (!ws.launched) return;
-    u64 h[3] = {0, 0, 0};
-    ZB_CUDA(cudaMemcpyAsync(h, reinterpret_cast<u64*>(ws.counters.p + 4), 24, cudaMemcpyDeviceToHost, s));
+    u64 h[4] = {0, 0, 0, 0};
+    ZB_CUDA(cudaMemcpyAsync(h, reinterpret_cast<u64*>(ws.counters.p + 4), 32, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaMemcpyAsync(tiles, ws.ntiles_ptr, 4, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
     cudaEventElapsedTime(kernel_ms, ws.ev0, ws.ev1);
     *tile_visits = h[0];
     *tile_pairs = h[1];
     *moved_bytes = h[2];
+    *unique_bytes = h[3];
 #ifdef ZB_SCAN_TIMING
     u64 t[8];
     ZB_CUDA(cudaMemcpy(t, reinterpret_cast<u64*>(ws.counters.p + 4) + 8, 64, cudaMemcpyDeviceToHost));
@@ -930,7 +934,8 @@ void seq_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, int power
     ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, SQ_TQ, ws.tile_per_leaf.p);
     cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
     ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, SQ_TQ,
-                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p);
+                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, f.leaf_len,
+                                                              (u64)f.dim * 4ull, reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
     SeqTileParams tp;
     tp.tile_leaf = ws.tile_leaf.p;
     tp.tile_first = ws.tile_first.p;
@@ -982,8 +987,8 @@ void seq_tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* moved_bytes, fl
     *kernel_ms = 0.f;
     *tiles = 0;
     if (!ws.seq_launched) return;
-    u64 h[3] = {0, 0, 0};
-    ZB_CUDA(cudaMemcpyAsync(h, reinterpret_cast<u64*>(ws.counters.p + 4), 24, cudaMemcpyDeviceToHost, s));
+    u64 h[4] = {0, 0, 0, 0};
+    ZB_CUDA(cudaMemcpyAsync(h, reinterpret_cast<u64*>(ws.counters.p + 4), 32, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaMemcpyAsync(tiles, ws.ntiles_ptr, 4, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
     cudaEventElapsedTime(kernel_ms, ws.ev0, ws.ev1);
@@ -1031,7 +1036,8 @@ void quad_tile_scan(ScanWorkspace& ws, const ForestView& f, u32 metric, const fl
     ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, 8, ws.tile_per_leaf.p);
     cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
     ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, 8,
-                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p);
+                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, f.leaf_len,
+                                                              (u64)f.dim * 4ull, reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
     QuadTileParams tp;
     tp.tile_leaf = ws.tile_leaf.p;
     tp.tile_first = ws.tile_first.p;

@@ -43,7 +43,7 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
                u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
                u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s);
 void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes, float* kernel_ms,
-                     u32* tiles);
+                     u32* tiles, u64* unique_bytes);
 
 // The scalar metrics (zb_metric 3..11): every visit with pairs to score, grouped by leaf into (leaf, <= 8 queries) tiles;
 // one thread folds a row against the tile's queries and writes the keys into the gather path's pair_key layout

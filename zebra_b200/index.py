@@ -194,6 +194,33 @@ class LSHIndex:
     def search_batch_device(self, nq: int, d_q_ptr: int, top_k: int, d_ord_ptr: int, d_bits_ptr: int, d_counts_ptr: int):
         _ffi.check(_ffi.lib().zb_index_search_batch_device(self._h, nq, d_q_ptr, top_k, d_ord_ptr, d_bits_ptr, d_counts_ptr))
 
+    # ---- sharded index, scalable form: every rank passes (and gets back) only the slice of the batch it fronts ----
+    def slice_bounds(self, nq_total: int, shard_rank: int, shard_count: int) -> Tuple[int, int]:
+        """Queries [lo, hi) of a batch of nq_total that rank `shard_rank` of `shard_count` fronts (zb_index_search_slice)."""
+        nqp = -(-nq_total // max(1, shard_count))
+        lo = min(nq_total, shard_rank * nqp)
+        return lo, min(nq_total, lo + nqp)
+
+    def search_slice(self, nq_total: int, slice_queries, top_k: int, want_ids: bool = True):
+        """Collective.  `slice_queries` = this rank's slice of the batch; returns that slice's (ids, ordinals, bits, counts)."""
+        q = np.ascontiguousarray(slice_queries, dtype=np.float32).reshape(-1, self.dim)
+        n = q.shape[0]
+        ids = np.empty((n, top_k, 16), dtype=np.uint8) if want_ids else None
+        ords = np.empty((n, top_k), dtype=np.uint64)
+        bits = np.empty((n, top_k), dtype=np.uint64)
+        counts = np.zeros(n, dtype=np.uint32)
+        _ffi.check(_ffi.lib().zb_index_search_slice(self._h, nq_total, q.ctypes.data if n else None, top_k,
+                                                    ids.ctypes.data if want_ids and n else None, ords.ctypes.data if n else None,
+                                                    bits.ctypes.data if n else None, counts.ctypes.data if n else None))
+        return ids, ords, bits, counts
+
+    def search_slice_ptr(self, nq_total: int, q_ptr: int, top_k: int, ord_ptr: int, bits_ptr: int, counts_ptr: int,
+                         ids_ptr: Optional[int] = None) -> None:
+        _ffi.check(_ffi.lib().zb_index_search_slice(self._h, nq_total, q_ptr, top_k, ids_ptr, ord_ptr, bits_ptr, counts_ptr))
+
+    def search_slice_device(self, nq_total: int, d_q_ptr: int, top_k: int, d_ord_ptr: int, d_bits_ptr: int, d_counts_ptr: int):
+        _ffi.check(_ffi.lib().zb_index_search_slice_device(self._h, nq_total, d_q_ptr, top_k, d_ord_ptr, d_bits_ptr, d_counts_ptr))
+
     # ---------------------------------------------------------------- bucket keys
     def hash(self, rows):
         x = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, self.dim)

@@ -1,0 +1,280 @@
+// scan3_emu.cpp -- TEST INFRASTRUCTURE.  Runs the SOURCE of the third-generation fused leaf-tile scan
+// (zebra_b200/csrc/zb_scan3_kernel.cuh, t3_body) on the CPU: one std::thread per CUDA thread of a 384-thread block;
+// warp shuffles / ballots = exchanges through a per-warp mailbox, named barriers = std::barrier, mbarriers = counters with the
+// PTX phase / transaction-count semantics, TMA tensor copies and 1-D bulk copies = memcpy performed LATER by a separate
+// "copy engine" thread (so a consumer that does not wait for its full barrier reads stale data and fails the test), packed
+// f32x2 arithmetic = two IEEE operations (build with -ffp-contract=off).  Blocks run one after the other, which is a legal
+// schedule of the persistent kernel.  tests/test_scan3.py feeds it leaves, tombstones and visits and compares every
+// entry the kernel writes with the oracle.
+#include <math.h>
+#include <stdlib.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <barrier>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+struct Dim3 { unsigned x, y, z; };
+static thread_local Dim3 emu_threadIdx;
+#define threadIdx emu_threadIdx
+
+namespace zb {
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned char u8;
+struct Entry { u64 key, ord; };
+#define ZB_SENTINEL 0xFFFFFFFFFFFFFFFFull
+struct ForestView {  // the fields t3_body reads (names as in zb_kernels.cuh)
+    const long long* leaf_off;
+    const u32* leaf_len;
+    const u32* members;
+    const u64* ord;
+    int dimp, chunks;
+};
+struct T3Map { const float* base; u64 rows; int dimp; };
+}  // namespace zb
+using zb::u32;
+using zb::u64;
+
+// ---------------------------------------------------------------- block-wide state of the emulation
+static unsigned char* emu_smem = nullptr;
+static std::barrier<>* emu_block_bar = nullptr;
+static std::barrier<>* emu_team_bar[2] = {nullptr, nullptr};
+struct WarpBox {
+    u64 slot[32];
+    std::barrier<> bar{32};
+};
+static std::vector<std::unique_ptr<WarpBox>> emu_warps;
+#define __syncthreads() emu_block_bar->arrive_and_wait()
+static inline void __syncwarp() { emu_warps[threadIdx.x >> 5]->bar.arrive_and_wait(); }
+static inline u64 emu_exchange(u64 v, int src) {
+    WarpBox& w = *emu_warps[threadIdx.x >> 5];
+    w.slot[threadIdx.x & 31] = v;
+    w.bar.arrive_and_wait();
+    const u64 r = w.slot[src & 31];
+    w.bar.arrive_and_wait();
+    return r;
+}
+static inline u32 f2u(float f) { u32 u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(u32 u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __shfl_xor_sync(unsigned, float v, int m) { return u2f((u32)emu_exchange(f2u(v), (int)(threadIdx.x & 31) ^ m)); }
+static inline u32 __shfl_sync(unsigned, u32 v, int src) { return (u32)emu_exchange(v, src); }
+static inline u32 __shfl_up_sync(unsigned, u32 v, int d) {
+    const int lane = threadIdx.x & 31;
+    const u32 r = (u32)emu_exchange(v, lane - d < 0 ? lane : lane - d);
+    return r;
+}
+static inline unsigned __ballot_sync(unsigned, bool p) {
+    WarpBox& w = *emu_warps[threadIdx.x >> 5];
+    w.slot[threadIdx.x & 31] = p ? 1 : 0;
+    w.bar.arrive_and_wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= (unsigned)w.slot[i] << i;
+    w.bar.arrive_and_wait();
+    return r;
+}
+static inline int __ffs(unsigned m) { return m ? __builtin_ctz(m) + 1 : 0; }
+template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
+static inline u32 atomicAdd(u32* p, u32 v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline u64 atomicAdd(u64* p, u64 v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+
+// ---------------------------------------------------------------- mbarriers (PTX semantics: arrival count + transaction bytes, phase parity)
+struct MBar { u32 count = 0, pending = 0; long long tx = 0; u64 completed = 0; };
+static std::mutex emu_mbar_mu;
+static std::unordered_map<u32, MBar> emu_mbars;
+static inline u32 smem_u32(const void* p) { return (u32)((const unsigned char*)p - emu_smem); }
+static void mbar_check(MBar& b) {
+    if (b.pending == 0 && b.tx == 0) { b.completed++; b.pending = b.count; }
+}
+static inline void mbar_init(u32 bar, u32 count) {
+    std::lock_guard<std::mutex> lk(emu_mbar_mu);
+    MBar b; b.count = b.pending = count;
+    emu_mbars[bar] = b;
+}
+static inline void mbar_arrive(u32 bar) {
+    std::lock_guard<std::mutex> lk(emu_mbar_mu);
+    MBar& b = emu_mbars.at(bar);
+    if (b.pending == 0) abort();  // more arrivals than the barrier expects: a protocol bug
+    b.pending--;
+    mbar_check(b);
+}
+static inline void mbar_arrive_expect_tx(u32 bar, u32 bytes) {
+    std::lock_guard<std::mutex> lk(emu_mbar_mu);
+    MBar& b = emu_mbars.at(bar);
+    if (b.pending == 0) abort();
+    b.tx += bytes;
+    b.pending--;
+    mbar_check(b);
+}
+static inline void mbar_complete_tx(u32 bar, u32 bytes) {
+    std::lock_guard<std::mutex> lk(emu_mbar_mu);
+    MBar& b = emu_mbars.at(bar);
+    b.tx -= bytes;
+    mbar_check(b);
+}
+static std::atomic<long long> emu_spins{0};
+static inline void mbar_wait(u32 bar, u32 parity) {
+    for (long long n = 0;; ++n) {
+        {
+            std::lock_guard<std::mutex> lk(emu_mbar_mu);
+            if ((emu_mbars.at(bar).completed & 1) != (parity & 1)) return;
+        }
+        if (n > 200000000LL) abort();  // deadlock
+        std::this_thread::yield();
+    }
+}
+
+// ---------------------------------------------------------------- the copy engine: copies land some time AFTER they were issued
+struct CopyEngine {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool stop = false;
+    std::thread th;
+    std::mt19937 rng{12345};
+    void start() {
+        th = std::thread([this] {
+            for (;;) {
+                std::function<void()> job;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [this] { return stop || !q.empty(); });
+                    if (q.empty()) return;
+                    job = std::move(q.front());
+                    q.pop_front();
+                }
+                if ((rng() & 3) == 0) std::this_thread::sleep_for(std::chrono::microseconds(rng() % 200));
+                job();
+            }
+        });
+    }
+    void push(std::function<void()> f) {
+        { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(f)); }
+        cv.notify_one();
+    }
+    void finish() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_one();
+        th.join();
+    }
+};
+static CopyEngine* emu_dma = nullptr;
+static inline void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+    unsigned char* d = emu_smem + dst;
+    emu_dma->push([=] { memcpy(d, src, bytes); mbar_complete_tx(bar, bytes); });
+}
+
+namespace zb {
+#define T3_EMU_STAGE_ROWS 64
+#define T3_EMU_SLICE 48
+static inline void t3_tma_2d_g2s(u32 dst, const T3Map& map, int c0, long long row, u32 bar) {
+    float* d = reinterpret_cast<float*>(emu_smem + dst);
+    const T3Map m = map;
+    emu_dma->push([=] {
+        for (int r = 0; r < T3_EMU_STAGE_ROWS; ++r)
+            for (int c = 0; c < T3_EMU_SLICE; ++c) {
+                const long long rr = row + r;
+                const int cc = c0 + c;
+                d[r * T3_EMU_SLICE + c] = (rr >= 0 && (u64)rr < m.rows && cc < m.dimp) ? m.base[(size_t)rr * m.dimp + cc] : 0.0f;  // out of bounds: zero fill
+            }
+        mbar_complete_tx(bar, T3_EMU_STAGE_ROWS * T3_EMU_SLICE * 4);
+    });
+}
+static inline bool t3_isinf_pos(double x) { return isinf(x) && x > 0.0; }
+static inline double t3_dmul(double a, double b) { return a * b; }
+static inline double t3_dsub(double a, double b) { return a - b; }
+static inline u64 t3_dbits(double x) { u64 u; memcpy(&u, &x, 8); return u; }
+static inline float t3_fadd(float a, float b) { return a + b; }
+static inline u64 t3_pk2(float lo, float hi) { return (u64)f2u(lo) | ((u64)f2u(hi) << 32); }
+static inline void t3_upk2(u64 v, float& lo, float& hi) { lo = u2f((u32)v); hi = u2f((u32)(v >> 32)); }
+static inline u64 t3_fma2(u64 a, u64 b, u64 c) {
+    return t3_pk2(fmaf(u2f((u32)a), u2f((u32)b), u2f((u32)c)), fmaf(u2f((u32)(a >> 32)), u2f((u32)(b >> 32)), u2f((u32)(c >> 32))));
+}
+static inline u64 t3_sub2(u64 a, u64 b) { return t3_pk2(u2f((u32)a) - u2f((u32)b), u2f((u32)(a >> 32)) - u2f((u32)(b >> 32))); }
+static inline u64 t3_ldcg_u64(const u64* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline void t3_atomic_min_u64(u64* p, u64 v) {
+    u64 cur = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+}
+static inline u64 t3_shfl64(u64 v, int src) { return emu_exchange(v, src); }
+static inline u64 t3_shfl_up64(u64 v) {
+    const int lane = threadIdx.x & 31;
+    return emu_exchange(v, lane == 0 ? 0 : lane - 1);
+}
+static inline void t3_team_sync(int team) { emu_team_bar[team]->arrive_and_wait(); }
+static inline void t3_fence_barrier_init() {}
+static inline void t3_setmaxnreg_dec() {}
+static inline void t3_setmaxnreg_inc() {}
+static inline void t3_prefetch_map(const T3Map&) {}
+static inline u64 l2sq_bits(float s) { return t3_dbits((double)s); }
+static inline u64 l2_bits(float s) { return t3_dbits(sqrt((double)s)); }
+}  // namespace zb
+
+#include "../zebra_b200/csrc/zb_scan3_kernel.cuh"
+
+// Tiles are given directly (what ts_count / ts_scatter / ts_filltiles build on the device).  The bucket-major store is
+// addressed by position: members = identity is supplied by the caller together with ord[position].
+extern "C" __attribute__((visibility("default"))) int emu_scan3(
+    int metric, int blocks, int dim, int nst, int qcap, uint32_t top_k, uint64_t positions, const float* bm_rows_padded,
+    const double* bm_rinv, const uint32_t* bm_tomb, const uint64_t* ord, const uint32_t* members, const long long* leaf_off,
+    const uint32_t* leaf_len, uint32_t ntiles, const uint32_t* tile_leaf, const uint32_t* tile_first, const uint32_t* tile_count,
+    const uint32_t* order, const uint32_t* v_np, const uint32_t* v_q, const uint32_t* v_ent_off, const float* queries_padded,
+    const double* q_rinv, uint64_t* gthr, uint64_t* entries /* [slots][2] */, uint64_t* stats3) {
+    zb::ForestView f;
+    f.leaf_off = leaf_off; f.leaf_len = leaf_len; f.members = members; f.ord = reinterpret_cast<const zb::u64*>(ord);
+    f.dimp = (dim + 15) / 16 * 16; f.chunks = f.dimp / 16;
+    uint32_t counter = 0;
+    zb::T3Params tp;
+    tp.tile_leaf = tile_leaf; tp.tile_first = tile_first; tp.tile_count = tile_count; tp.ntiles = &ntiles; tp.tile_counter = &counter;
+    tp.order = order; tp.v_np = v_np; tp.v_q = v_q; tp.v_ent_off = v_ent_off; tp.entries = reinterpret_cast<zb::Entry*>(entries);
+    tp.queries = queries_padded; tp.q_rinv = q_rinv; tp.bm_rinv = bm_rinv; tp.bm_tomb = bm_tomb;
+    tp.stats = reinterpret_cast<zb::u64*>(stats3); tp.gthr = reinterpret_cast<zb::u64*>(gthr); tp.top_k = top_k; tp.nst = nst; tp.qcap = qcap;
+    zb::T3Map map{bm_rows_padded, positions, f.dimp};
+    const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap);
+    std::vector<unsigned char> smem((size_t)T3_TEAMS * lay.total + 1024);
+    emu_warps.clear();
+    for (int i = 0; i < T3_THREADS / 32; ++i) emu_warps.emplace_back(new WarpBox());
+    for (int b = 0; b < blocks; ++b) {
+        // garbage in shared memory at block start: nothing may depend on its content
+        for (size_t i = 0; i < smem.size(); ++i) smem[i] = (unsigned char)(0xA5 ^ (i * 131));
+        emu_smem = smem.data();
+        emu_mbars.clear();
+        CopyEngine dma;
+        emu_dma = &dma;
+        dma.start();
+        std::barrier<> bar(T3_THREADS), tb0(128), tb1(128);
+        emu_block_bar = &bar;
+        emu_team_bar[0] = &tb0;
+        emu_team_bar[1] = &tb1;
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T3_THREADS; ++t)
+            th.emplace_back([&, t] {
+                emu_threadIdx = Dim3{t, 0, 0};
+                if (metric == 0) zb::t3_body<0>(map, f, tp, emu_smem);
+                else if (metric == 1) zb::t3_body<1>(map, f, tp, emu_smem);
+                else zb::t3_body<2>(map, f, tp, emu_smem);
+            });
+        for (auto& x : th) x.join();
+        dma.finish();
+    }
+    return (int)counter;
+}
+
+extern "C" __attribute__((visibility("default"))) void emu_scan3_layout(int nst, int dim, int qcap, uint32_t* out8) {
+    const zb::T3Layout l = zb::t3_layout(nst, (dim + 15) / 16 * 16, qcap);
+    out8[0] = l.stage; out8[1] = l.queries; out8[2] = l.sums; out8[3] = l.lists; out8[4] = l.meta; out8[5] = l.info; out8[6] = l.bars; out8[7] = l.total;
+}

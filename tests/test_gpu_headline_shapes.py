@@ -63,7 +63,8 @@ def test_tile_kernel_on_headline_shapes(dim, mid, mname):
         for k in (1, 10, 32):
             assert_search_equal(ix, orc, queries, k)
             st = ix.stats()
-            assert st["last_tile_pairs"] > 0 and st["last_tile_pairs"] == st["last_pairs"], (phase, k, st)
+            # (a few leaves end up below tile_min_rows = 64 rows and stay on the gather path)
+            assert st["last_tile_pairs"] > 0.99 * st["last_pairs"], (phase, k, st)
     # the gather path alone on the same (tombstoned) index: same answer, nothing through the tile kernel
     ix.set_param("use_tile_scan", 0)
     for k in (1, 10, 32):
@@ -73,6 +74,11 @@ def test_tile_kernel_on_headline_shapes(dim, mid, mname):
     ix.set_param("use_tile_scan", 1)
     assert_search_equal(ix, orc, queries[:200], 10)
     assert ix.stats()["last_tile_pairs"] > 0
+    # the second-generation kernel (8-query tiles, 128-row stages) stays selectable and must agree
+    ix.set_param("scan_gen", 2)
+    for k in (1, 10, 32):
+        assert_search_equal(ix, orc, queries, k)
+        assert ix.stats()["last_tile_pairs"] > 0
 
 
 def test_tile_kernel_crowded_leaves():
@@ -89,7 +95,7 @@ def test_tile_kernel_crowded_leaves():
     queries = make_queries(rng, rows, 6000)
     for k in (10, 32):
         assert_search_equal(ix, orc, queries, k)
-        assert ix.stats()["last_tile_pairs"] == ix.stats()["last_pairs"]
+        assert ix.stats()["last_tile_pairs"] > 0.99 * ix.stats()["last_pairs"]
 
 
 def test_database_open_then_insert_search_remove(tmp_path):

@@ -1,0 +1,167 @@
+"""The third-generation fused leaf-tile scan (zebra_b200/csrc/zb_scan3_kernel.cuh) run ON THE CPU from its own source
+(tests/scan3_emu.cpp: one std::thread per CUDA thread; mbarriers, the TMA copy engine, shuffles and ballots emulated) and
+compared with the oracle: every (key, ordinal) entry of every visit's top-n' list, bit for bit -- the leaf branch of
+tree_result (/root/reference/src/database/index/lsh.rs:299-331) with Metric::distance of distance.rs:19-49, :103-114.
+
+What this covers without a GPU: the ring protocol (full / empty / tile-info / query barriers: a missing wait reads stale
+data because copies land late, an extra arrival aborts), the 16-lane fold over the half-warp and which thread ends up with
+which row, the transposition through shared memory, list insertion with ties and tombstones, partial row blocks, partial
+query tiles (QH = 2, 4, 6, 8), dim % 48 != 0 and dim % 16 != 0, and the shared per-query bound."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import zb_oracle as zo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+F32 = np.float32
+SENT = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("s3") / "libscan3_emu.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
+                           "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out, os.path.join(HERE, "scan3_emu.cpp")])
+    L = C.CDLL(out)
+    L.emu_scan3.restype = C.c_int
+    L.emu_scan3.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint64] + [C.c_void_p] * 7 + \
+                           [C.c_uint32] + [C.c_void_p] * 12
+    return L
+
+
+def canonical_sq_norm(x):
+    """|x|^2 as the kernels accumulate it (16-lane order): the dot product of x with itself through the oracle."""
+    return np.array([zo.dot(v, v) for v in x], dtype=F32)
+
+
+def build_case(rng, dim, leaf_lens, nq, visits_per_leaf, np_max, tomb_frac, dup=True):
+    dimp = (dim + 15) // 16 * 16
+    P = int(sum(leaf_lens))
+    rows = rng.standard_normal((P, dim)).astype(F32)
+    if dup and P > 40:
+        rows[P // 2:P // 2 + 10] = rows[:10]              # equal keys: order by position
+    queries = rng.standard_normal((nq, dim)).astype(F32)
+    if dup:
+        queries[0] = rows[3]                                # distance exactly 0
+    leaf_off = np.concatenate([[0], np.cumsum(leaf_lens)]).astype(np.int64)
+    tomb_bits = rng.random(P) < tomb_frac
+    ordv = (rng.permutation(P).astype(np.uint64) + np.uint64(1000))   # ordinal of every position (any injective map)
+    # visits: for every leaf a random subset of queries, each with its own n'
+    v_leaf, v_q, v_np = [], [], []
+    for l, c in enumerate(visits_per_leaf):
+        for q in rng.choice(nq, size=min(c, nq), replace=False):
+            v_leaf.append(l); v_q.append(int(q)); v_np.append(int(rng.integers(1, np_max + 1)))
+    perm = rng.permutation(len(v_leaf))                     # visits arrive in walker order, not grouped by leaf
+    v_leaf = np.array(v_leaf, np.uint32)[perm]; v_q = np.array(v_q, np.uint32)[perm]; v_np = np.array(v_np, np.uint32)[perm]
+    return dict(dim=dim, dimp=dimp, P=P, rows=rows, queries=queries, leaf_off=leaf_off, leaf_len=np.array(leaf_lens, np.uint32),
+                tomb=tomb_bits, ord=ordv, v_leaf=v_leaf, v_q=v_q, v_np=v_np)
+
+
+def run_emu(emu, case, metric, top_k, tq, qcap=16, nst=4, blocks=2, same_np=None):
+    dim, dimp, P = case["dim"], case["dimp"], case["P"]
+    rows_p = np.zeros((P + 1, dimp), F32); rows_p[:P, :dim] = case["rows"]
+    q_p = np.zeros((case["queries"].shape[0], dimp), F32); q_p[:, :dim] = case["queries"]
+    tomb_words = np.zeros(P // 32 + 8, np.uint32)
+    for p in np.nonzero(case["tomb"])[0]:
+        tomb_words[p >> 5] |= np.uint32(1 << (p & 31))
+    with np.errstate(divide="ignore"):
+        bm_rinv = 1.0 / np.sqrt(canonical_sq_norm(case["rows"]).astype(np.float64))
+        q_rinv = 1.0 / np.sqrt(canonical_sq_norm(case["queries"]).astype(np.float64))
+    v_leaf, v_q = case["v_leaf"], case["v_q"]
+    v_np = case["v_np"] if same_np is None else np.full_like(case["v_np"], same_np)
+    nv = v_leaf.size
+    live_len = np.array([int((~case["tomb"][case["leaf_off"][l]:case["leaf_off"][l + 1]]).sum()) for l in range(case["leaf_len"].size)])
+    ent_len = np.minimum(live_len[v_leaf], v_np).astype(np.uint32)
+    v_ent_off = np.concatenate([[0], np.cumsum(ent_len)]).astype(np.uint32)
+    # group visits by leaf, cut tiles of <= tq queries (full tiles first), as ts_scatter / ts_filltiles do
+    order = np.argsort(v_leaf, kind="stable").astype(np.uint32)
+    tile_leaf, tile_first, tile_count = [], [], []
+    pos = 0
+    for l in range(case["leaf_len"].size):
+        c = int((v_leaf == l).sum())
+        done = 0
+        while done < c:
+            n = min(tq, c - done)
+            tile_leaf.append(l); tile_first.append(pos + done); tile_count.append(n)
+            done += n
+        pos += c
+    tile_leaf = np.array(tile_leaf, np.uint32); tile_first = np.array(tile_first, np.uint32); tile_count = np.array(tile_count, np.uint32)
+    members = np.arange(P + 1, dtype=np.uint32)
+    gthr = np.full(case["queries"].shape[0], SENT, np.uint64)
+    entries = np.zeros((int(v_ent_off[-1]) + 1, 2), np.uint64)
+    stats = np.zeros(8, np.uint64)
+    done_tiles = emu.emu_scan3(metric, blocks, dim, nst, qcap, top_k, P, rows_p.ctypes.data, bm_rinv.ctypes.data, tomb_words.ctypes.data,
+                               case["ord"].ctypes.data, members.ctypes.data, case["leaf_off"].ctypes.data, case["leaf_len"].ctypes.data,
+                               tile_leaf.size, tile_leaf.ctypes.data, tile_first.ctypes.data, tile_count.ctypes.data, order.ctypes.data,
+                               v_np.ctypes.data, v_q.ctypes.data, v_ent_off.ctypes.data, q_p.ctypes.data, q_rinv.ctypes.data,
+                               gthr.ctypes.data, entries.ctypes.data, stats.ctypes.data)
+    assert done_tiles >= tile_leaf.size
+    assert int(stats[0]) == nv and int(stats[1]) == int(case["leaf_len"][v_leaf].astype(np.int64).sum())
+    return entries, v_ent_off, v_np, gthr
+
+
+def expected_visit(case, metric, v, np_v):
+    l, q = int(case["v_leaf"][v]), int(case["v_q"][v])
+    lo, hi = int(case["leaf_off"][l]), int(case["leaf_off"][l + 1])
+    pos = np.arange(lo, hi)
+    pos = pos[~case["tomb"][lo:hi]]
+    if pos.size == 0:
+        return np.zeros((0, 2), np.uint64)
+    keys = zo.distance_bits_batch(metric, case["rows"][pos], np.broadcast_to(case["queries"][q], (pos.size, case["dim"])).copy())
+    idx = np.lexsort((pos, keys))[:np_v]                    # (key, position): position order == ordinal order inside a leaf (D3)
+    return np.stack([keys[idx], case["ord"][pos[idx]]], axis=1)
+
+
+@pytest.mark.parametrize("metric", [zo.COSINE, zo.L2SQ, zo.L2])
+@pytest.mark.parametrize("dim,tq", [(48, 16), (100, 16), (40, 7), (200, 11)])
+def test_per_visit_lists_equal_oracle(emu, metric, dim, tq):
+    rng = np.random.default_rng(dim * 7 + metric)
+    leaf_lens = [1, 63, 64, 65, 130, 17, 200, 128, 5]
+    visits = [1, 2, 5, 9, 16, 3, 21, 13, 4]                 # tiles of 1..16 queries: every QH variant, several tiles per leaf
+    case = build_case(rng, dim, leaf_lens, 24, visits, np_max=32, tomb_frac=0.15)
+    # top_k no visit's n' equals: the shared per-query bound is never published, every list is the exact per-visit top-n'
+    entries, ent_off, v_np, _ = run_emu(emu, case, metric, top_k=0xFFFFFFFF, tq=tq)
+    for v in range(case["v_leaf"].size):
+        exp = expected_visit(case, metric, v, int(v_np[v]))
+        got = entries[ent_off[v]:ent_off[v + 1]]
+        assert got.shape[0] == exp.shape[0], v
+        assert np.array_equal(got, exp), (v, int(case["v_leaf"][v]), int(case["v_q"][v]), int(v_np[v]))
+
+
+def test_shared_bound_keeps_the_per_query_answer(emu):
+    """All visits ask for n' = top_k, so full lists publish their k-th key and later visits of the same query drop candidates
+    above it: per-visit lists may be shorter, the per-query top-k over all visits (dedup by ordinal) must not change."""
+    rng = np.random.default_rng(99)
+    leaf_lens = [150, 90, 200, 64, 70, 129]
+    visits = [12, 12, 12, 12, 12, 12]
+    case = build_case(rng, 64, leaf_lens, 12, visits, np_max=8, tomb_frac=0.1)
+    k = 8
+    entries, ent_off, _, gthr = run_emu(emu, case, zo.L2SQ, top_k=k, tq=16, same_np=k, blocks=3)
+    assert (gthr != SENT).any()
+    for q in range(12):
+        got, exp = [], []
+        for v in np.nonzero(case["v_q"] == q)[0]:
+            e = entries[ent_off[v]:ent_off[v + 1]]
+            got += [tuple(x) for x in e if x[1] != SENT]
+            exp += [tuple(x) for x in expected_visit(case, zo.L2SQ, v, k)]
+        got_k = sorted(set(got))[:k]
+        exp_k = sorted(set(exp))[:k]
+        assert got_k == exp_k, q
+
+
+def test_small_query_capacity_and_deep_ring(emu):
+    """qcap = 8 (long rows: the query block leaves room for 8 queries only) with a 6-stage ring, one block."""
+    rng = np.random.default_rng(5)
+    case = build_case(rng, 96, [70, 131, 64], 10, [8, 10, 3], np_max=20, tomb_frac=0.0)
+    entries, ent_off, v_np, _ = run_emu(emu, case, zo.COSINE, top_k=0xFFFFFFFF, tq=8, qcap=8, nst=6, blocks=1)
+    for v in range(case["v_leaf"].size):
+        assert np.array_equal(entries[ent_off[v]:ent_off[v + 1]], expected_visit(case, zo.COSINE, v, int(v_np[v]))), v
+
+
+def test_fold_row_is_a_bijection():
+    rows = sorted(((t >> 1) & 1) | ((t & 1) << 1) | (t & 4) | (t & 8) for t in range(16))
+    assert rows == list(range(16))

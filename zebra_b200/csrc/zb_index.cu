@@ -120,6 +120,7 @@ struct zb_index {
     DBuf<double> bm_rinv, q_rinv;
     DBuf<u32> bm_tomb, slot_pos, d_leaf_tree;
     alignas(64) unsigned char bm_tmap[128];
+    alignas(64) unsigned char bm_tmap3[128];
     bool bm_valid = false, bm_failed = false;
     u64 bm_positions = 0;
     // bucket-sharded layout (G > 1): leaf l lives, whole, on rank l % G; positions are tree-major, then leaf, then ordinal
@@ -164,7 +165,7 @@ struct zb_index {
     ScanWorkspace qt_ws;  // keys-only tile scan of the visits the fused kernel leaves (cosine / L2, n' > 32)
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 0, p_select_variant = 0;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 0, p_select_variant = 1, p_scan_gen = 3;
     zb_stats st{};
 
     ForestView view() const {
@@ -366,7 +367,8 @@ struct zb_index {
         launch_bm_gather(nl, d_leaf_off.p, d_leaf_len.p, d_leaf_tree.p, d_members.p, rows.p, tomb.p, dimp, slot_stride, bm_rows.p,
                          slot_pos.p, bm_tomb.p, stream);
         if (opt.metric == ZB_METRIC_COSINE) launch_rinv(bm_rows.p, members_used, dimp, bm_rinv.p, stream);
-        make_row_tile_map(bm_tmap, bm_rows.p, members_used, dimp);
+        make_row_tile_map(bm_tmap, bm_rows.p, members_used, dimp, 128);
+        make_row_tile_map(bm_tmap3, bm_rows.p, members_used, dimp, 64);
         sync();
         bm_positions = members_used;
         bm_valid = true;
@@ -503,7 +505,8 @@ struct zb_index {
             sync();
         }
         if (opt.metric == ZB_METRIC_COSINE) launch_rinv(bm_rows.p, P, dimp, bm_rinv.p, stream);
-        make_row_tile_map(bm_tmap, bm_rows.p, Pa, dimp);
+        make_row_tile_map(bm_tmap, bm_rows.p, Pa, dimp, 128);
+        make_row_tile_map(bm_tmap3, bm_rows.p, Pa, dimp, 64);
         sync();
         bm_positions = P;
         bm_valid = true;
@@ -515,6 +518,7 @@ struct zb_index {
         b.rinv = bm_rinv.p;
         b.tomb = bm_tomb.p;
         b.tmap = bm_tmap;
+        b.tmap3 = bm_tmap3;
         b.positions = bm_positions;
         return b;
     }
@@ -857,8 +861,9 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     // the fused tile kernel takes every visit of a leaf with >= tile_min_rows rows (here) and n' <= 32; known up front, so
     // the compaction can already set those visits aside and the host reads ONE record {flag, visits, slots, pairs} per batch
     // (the scalar metrics 3..11 are a sequential fold per pair: gather path only)
+    const bool gen3 = ix->p_scan_gen != 2 && tile_scan3_supported(ix->dimp, (u32)top_k);
     const bool tile_on = ix->opt.metric <= ZB_METRIC_L2 && ix->p_use_tile_scan && ix->opt.max_node_size >= (u64)ix->p_tile_min_rows &&
-                         tile_scan_supported(ix->dimp, (u32)top_k) && ix->ensure_bucket_major();
+                         (gen3 || tile_scan_supported(ix->dimp, (u32)top_k)) && ix->ensure_bucket_major();
     u64 v_cap = std::max<u64>(ix->v_leaf.cap ? ix->v_leaf.cap - 1 : 0, nw + nw / 2 + 1024);
     if (sharded && !ix->x_cap) ix->x_cap = (u32)std::min<u64>(nwl + nwl / 2 + 64, 0x7FFFFFFFull);
     ix->plan_totals.ensure(8);
@@ -965,9 +970,10 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
             ix->q_rinv.ensure(nq);
             launch_rinv(d_q, nq, ix->dimp, ix->q_rinv.p, s);
         }
-        tile_scan(ix->scan_ws, fs, ix->bm_view(), ix->opt.metric, d_q, ix->q_rinv.p, (u32)nq, nv, ix->v_leaf.p, ix->v_np.p, ix->v_q.p,
-                  ix->v_ent_off.p, ix->v_pair_len.p, ix->v_done.p, ix->entries.p, (u32)top_k, (u32)ix->p_tile_min_rows,
-                  (u32)ix->p_tile_queries, (u32)ix->h_leaf_off.size(), s);
+        (gen3 ? tile_scan3 : tile_scan)(ix->scan_ws, fs, ix->bm_view(), ix->opt.metric, d_q, ix->q_rinv.p, (u32)nq, nv, ix->v_leaf.p,
+                                        ix->v_np.p, ix->v_q.p, ix->v_ent_off.p, ix->v_pair_len.p, ix->v_done.p, ix->entries.p,
+                                        (u32)top_k, (u32)ix->p_tile_min_rows, (u32)ix->p_tile_queries,
+                                        (u32)ix->h_leaf_off.size(), s);
         ZB_REQUIRE(ix->scan_ws.launched, ZB_ERR_STATE, "tile scan did not launch for visits set aside for it");
         scan_launches = ix->scan_ws.launches + (ix->opt.metric == ZB_METRIC_COSINE ? 1 : 0);
     }
@@ -2026,6 +2032,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     if (k == "tile_min_rows") ix->p_tile_min_rows = value;
     else if (k == "tile_queries") ix->p_tile_queries = value;
     else if (k == "use_tile_scan") ix->p_use_tile_scan = value;
+    else if (k == "scan_gen") ix->p_scan_gen = value;  // fused leaf-tile scan: 3 = third generation (default), 2 = second (8-query tiles, 128-row stages)
     else if (k == "classify_variant") ix->p_classify_variant = value;  // 0: rows gathered through L1; 1: rows staged by TMA bulk copies
     else if (k == "seq_prefetch") ix->p_seq_prefetch = value;  // scalar metrics: L2 prefetch distance of the row stream in 128-byte lines (0 = off, the default: measured slower)
     else if (k == "select_variant") ix->p_select_variant = value;  // per-visit top-n' of the gather path: 0 = block bitonic (default), 1 = one warp per visit, list in registers (until measured)

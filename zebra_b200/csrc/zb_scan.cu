@@ -529,6 +529,52 @@ tile_scan_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, TilePar
 }
 
 // =====================================================================================================
+// Third-generation fused leaf-tile scan (zb_scan3_kernel.cuh): device-side primitives, then the kernel.
+// =====================================================================================================
+typedef CUtensorMap T3Map;
+__device__ __forceinline__ bool t3_isinf_pos(double x) { return isinf(x) && x > 0.0; }
+__device__ __forceinline__ double t3_dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double t3_dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ u64 t3_dbits(double x) { return (u64)__double_as_longlong(x); }
+__device__ __forceinline__ float t3_fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ u64 t3_pk2(float lo, float hi) { return pk2(lo, hi); }
+__device__ __forceinline__ void t3_upk2(u64 v, float& lo, float& hi) { upk2(v, lo, hi); }
+__device__ __forceinline__ u64 t3_fma2(u64 a, u64 b, u64 c) {  // two IEEE fused multiply-adds (bit-identical to __fmaf_rn per half)
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 t3_sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 t3_ldcg_u64(const u64* p) { return __ldcg(p); }
+__device__ __forceinline__ void t3_atomic_min_u64(u64* p, u64 v) { atomicMin(p, v); }
+__device__ __forceinline__ u64 t3_shfl64(u64 v, int src) { return shfl64(v, src); }
+__device__ __forceinline__ u64 t3_shfl_up64(u64 v) { return shfl_up64(v); }
+__device__ __forceinline__ void t3_team_sync(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
+__device__ __forceinline__ void t3_fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void t3_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); }
+__device__ __forceinline__ void t3_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;"); }
+__device__ __forceinline__ void t3_prefetch_map(const T3Map& m) { asm volatile("prefetch.tensormap [%0];" ::"l"(&m) : "memory"); }
+__device__ __forceinline__ void t3_tma_2d_g2s(u32 dst, const T3Map& map, int c0, long long row, u32 bar) {
+    tma_2d_g2s(dst, &map, c0, (int)row, bar);
+}
+}  // namespace zb
+#include "zb_scan3_kernel.cuh"
+namespace zb {
+
+template <int METRIC>
+__global__ void __launch_bounds__(T3_THREADS, 1) tile_scan3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
+    extern __shared__ __align__(1024) unsigned char smem3[];
+    t3_body<METRIC>(tmap, f, tp, smem3);
+}
+
+// =====================================================================================================
 // grouping of visits by leaf and tile construction (all on device; no host round trip)
 // =====================================================================================================
 __global__ void ts_count_kernel(ForestView f, u32 nv, const u32* __restrict__ v_leaf, const u32* __restrict__ v_np,
@@ -610,11 +656,11 @@ static EncodeTiledFn encode_tiled_fn() {
     }
     return fn;
 }
-void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp) {
+void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp, int box_rows) {
     CUtensorMap* m = reinterpret_cast<CUtensorMap*>(out_map128);
     cuuint64_t gdim[2] = {(cuuint64_t)dimp, (cuuint64_t)(positions ? positions : 1)};
     cuuint64_t gstride[1] = {(cuuint64_t)dimp * 4};
-    cuuint32_t box[2] = {TS_SLICE_FLOATS, TS_RB};
+    cuuint32_t box[2] = {TS_SLICE_FLOATS, (cuuint32_t)box_rows};  // TS_SLICE_FLOATS == T3_SLICE_FLOATS
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_tiled_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bm_rows, gdim, gstride, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -748,6 +794,112 @@ void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* t
     fprintf(stderr, "[scan timing, Mcycles summed over math warps] tile-wait %.1f stage-wait %.1f math %.1f fold %.1f insert %.1f merge %.1f idle %.1f\n",
             t[0] / 1e6, t[1] / 1e6, t[2] / 1e6, t[3] / 1e6, t[4] / 1e6, t[5] / 1e6, t[7] / 1e6);
 #endif
+}
+
+// ---- third generation (zb_scan3_kernel.cuh): same visit grouping, tiles of up to 16 queries, 64-row stages ----
+static size_t t3_smem_bytes(int nst, int dimp, int qcap) { return T3_TEAMS * (size_t)t3_layout(nst, dimp, qcap).total + 1024; }
+// ring depth and query capacity for this row length: the largest tile (16, then 8, then 4 queries) that leaves >= 3 stages
+static bool t3_config(int dimp, int* nst_out, int* qcap_out) {
+    int dev = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    for (int qcap = T3_QT; qcap >= 4; qcap >>= 1)
+        for (int nst = T3_MAX_STAGES; nst >= 3; --nst)
+            if (t3_smem_bytes(nst, dimp, qcap) <= (size_t)max_smem) {
+                *nst_out = nst;
+                *qcap_out = qcap;
+                return true;
+            }
+    return false;
+}
+bool tile_scan3_supported(int dimp, u32 top_k) {
+    int nst, qcap;
+    return top_k >= 1 && top_k <= T3_KL && t3_config(dimp, &nst, &qcap);
+}
+
+void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u32 metric, const float* d_q, const double* d_q_rinv,
+                u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
+                u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s) {
+    ws.launched = false;
+    int nst = 0, qcap = 0;
+    if (!nv || !nleaves || top_k < 1 || top_k > T3_KL || !t3_config(f.dimp, &nst, &qcap)) return;
+    tile_queries &= 0xFF;
+    const u32 tq = tile_queries >= 1 && tile_queries <= (u32)qcap ? tile_queries : (u32)qcap;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = t3_smem_bytes(nst, f.dimp, qcap);
+
+    ws.leaf_count.ensure(nleaves + 1);
+    ws.leaf_start.ensure(nleaves + 1);
+    ws.leaf_cursor.ensure(nleaves + 1);
+    ws.order.ensure(nv);
+    ws.tile_leaf.ensure(nv);
+    ws.tile_first.ensure(nv);
+    ws.counters.ensure(64);
+    ws.gthr.ensure(nq ? nq : 1);
+    ZB_CUDA(cudaMemsetAsync(ws.gthr.p, 0xFF, (size_t)(nq ? nq : 1) * 8, s));
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const u32*)nullptr, (u32*)nullptr, (long long)(nleaves + 1));
+    ws.tmp.ensure(tmp_bytes + 256);
+    ZB_CUDA(cudaMemsetAsync(ws.leaf_count.p, 0, (size_t)(nleaves + 1) * 4, s));
+    ZB_CUDA(cudaMemsetAsync(ws.leaf_cursor.p, 0, (size_t)(nleaves + 1) * 4, s));
+    ZB_CUDA(cudaMemsetAsync(ws.counters.p, 0, 64 * 4, s));
+    const u32 kmax = top_k;
+    ts_count_kernel<<<(nv + 255) / 256, 256, 0, s>>>(f, nv, v_leaf, v_np, min_rows, kmax, ws.leaf_count.p);
+    cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.leaf_count.p, ws.leaf_start.p, (long long)(nleaves + 1), s);
+    ts_scatter_kernel<<<(nv + 255) / 256, 256, 0, s>>>(f, nv, v_leaf, v_np, min_rows, kmax, ws.leaf_start.p,
+                                                       ws.leaf_cursor.p, ws.order.p, v_pair_len, v_done);
+    ws.tile_per_leaf.ensure(nleaves + 1);
+    ws.tile_start.ensure(nleaves + 1);
+    ws.tile_cnt.ensure(nv);
+    ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, tq, ws.tile_per_leaf.p);
+    cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
+    ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, tq,
+                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, f.leaf_len,
+                                                              (u64)f.dimp * 4ull, reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
+    T3Params tp;
+    tp.tile_leaf = ws.tile_leaf.p;
+    tp.tile_first = ws.tile_first.p;
+    tp.tile_count = ws.tile_cnt.p;
+    tp.ntiles = ws.tile_start.p + nleaves;
+    ws.ntiles_ptr = tp.ntiles;
+    tp.tile_counter = ws.counters.p;
+    tp.order = ws.order.p;
+    tp.v_np = v_np;
+    tp.v_q = v_q;
+    tp.v_ent_off = v_ent_off;
+    tp.entries = entries;
+    tp.queries = d_q;
+    tp.q_rinv = d_q_rinv;
+    tp.bm_rinv = bm.rinv;
+    tp.bm_tomb = bm.tomb;
+    tp.stats = reinterpret_cast<u64*>(ws.counters.p + 4);
+    tp.gthr = ws.gthr.p;
+    tp.top_k = top_k;
+    tp.nst = nst;
+    tp.qcap = qcap;
+    const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(bm.tmap3);
+    const int grid = sms;
+    if (!ws.ev0) {
+        ZB_CUDA(cudaEventCreate(&ws.ev0));
+        ZB_CUDA(cudaEventCreate(&ws.ev1));
+    }
+    ZB_CUDA(cudaEventRecord(ws.ev0, s));
+    if (metric == 0) {
+        ZB_CUDA(cudaFuncSetAttribute(tile_scan3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tile_scan3_kernel<0><<<grid, T3_THREADS, smem, s>>>(tmap, f, tp);
+    } else if (metric == 1) {
+        ZB_CUDA(cudaFuncSetAttribute(tile_scan3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tile_scan3_kernel<1><<<grid, T3_THREADS, smem, s>>>(tmap, f, tp);
+    } else {
+        ZB_CUDA(cudaFuncSetAttribute(tile_scan3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tile_scan3_kernel<2><<<grid, T3_THREADS, smem, s>>>(tmap, f, tp);
+    }
+    ZB_CUDA(cudaGetLastError());
+    ZB_CUDA(cudaEventRecord(ws.ev1, s));
+    ws.launched = true;
+    ws.launches = 7;
 }
 
 // =====================================================================================================

@@ -25,11 +25,12 @@ struct BucketMajor {
     const double* rinv = nullptr;   // [positions] 1/sqrt(|row|^2), f64 (cosine only)
     const u32* tomb = nullptr;      // bit per position
     const void* tmap = nullptr;     // host copy of the CUtensorMap (128 bytes) over `rows`, box = 48 floats x 128 rows
+    const void* tmap3 = nullptr;    // the same tensor with a 48 floats x 64 rows box (third-generation scan)
     u64 positions = 0;
 };
 
 // Encodes the 2-D tensor map of the bucket-major store into out_map128 (128 bytes, 64-byte aligned).
-void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp);
+void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp, int box_rows);
 // True when the tile kernel can serve this shape (top_k <= 32, query block + ring fit in shared memory).
 bool tile_scan_supported(int dimp, u32 top_k);
 void launch_rinv(const float* d_x, u64 n, int dimp, double* d_out, cudaStream_t s);
@@ -42,6 +43,12 @@ void launch_rinv(const float* d_x, u64 n, int dimp, double* d_out, cudaStream_t 
 void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u32 metric, const float* d_q, const double* d_q_rinv,
                u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
                u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s);
+// Third generation (zb_scan3_kernel.cuh; the default): tiles of up to 16 queries, 64-row stages, one accumulator lane per
+// thread, distances transposed through shared memory so that one warp owns a query's list.  Same contract as tile_scan.
+bool tile_scan3_supported(int dimp, u32 top_k);
+void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u32 metric, const float* d_q, const double* d_q_rinv,
+                u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
+                u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s);
 void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes, float* kernel_ms,
                      u32* tiles, u64* unique_bytes);
 

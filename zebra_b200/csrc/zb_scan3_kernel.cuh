@@ -1,0 +1,471 @@
+// zb_scan3_kernel.cuh -- body of the fused leaf-tile scan, third generation (tile_scan3_kernel, launched from zb_scan.cu).
+//
+// Replaces, for visits of large leaves, the leaf branch of tree_result
+// (/root/reference/src/database/index/lsh.rs:299-331: fetch every member, metric.distance, sort, take n) and the
+// rescoring of search (:557-563).  Work unit ("tile") = (leaf, <= 16 of the queries that visit it).
+//
+// What changed against the second generation (zb_scan.cu, tile_scan_kernel) and why:
+//   * 16 queries per tile instead of 8: the average leaf of BASELINE config 2 is visited by 12.6 queries per batch, so
+//     most leaves are now read from HBM exactly once per batch (algorithmic bytes 27.2 GB -> ~14 GB per batch).
+//   * register tile 16 rows x 8 queries per HALF-WARP with ONE accumulator lane per thread (thread t of a half-warp owns
+//     lane t of every pair's canonical 16-lane accumulator) instead of 8 x 4 per quad with four lanes per thread.  Shared
+//     memory delivers 128 thread-bytes per clock whatever the access width or broadcast pattern (measured: 4.03
+//     wavefronts per LDS.128 in profiles/r01_scan_g_raw.csv), so what counts is loaded floats per FMA per thread:
+//     (8 + 4) x 4 per 128 before, 16 + 8 per 128 now -- half the shared-memory pipe time, which is what bound cosine.
+//   * the query tile adapts to the tile's population: QH = 2, 4, 6 or 8 queries per half-warp, so a 9-query tile does not
+//     pay the FP32 work of 16.
+//   * the distances of a row block are transposed through shared memory so that ONE warp owns a query's top-n' list for the
+//     whole tile (no per-slab lists, no end-of-tile merge, exact filter threshold per query).
+//   * row blocks of 64 rows (12 KB stages): smaller tails, more stages in flight per byte of ring.
+//
+// Canonical arithmetic (zb_device.cuh): lane j of the 16-lane accumulator receives elements j, j+16,
+// ... by one fused multiply-add each; fold x[i] = acc[i] + acc[i+8], r[i] = x[i] + x[i+4], s = (r0 + r1) + (r2 + r3).
+// Here the four folds are shuffles over the half-warp (xor 8, 4, 1, 2); at every step a thread keeps half of its rows and
+// hands the other half to its partner, so the fold costs 15 shuffles + 15 adds per pair in total and leaves thread t with
+// the finished sums of row fold_row(t) for its QH queries.
+//
+// This file holds only code that is also compiled for the CPU by tests/scan3_emu.cpp (one std::thread per CUDA thread,
+// mbarriers / bulk copies / shuffles emulated): every hardware-specific operation goes through a t3_* / mbar_* wrapper.
+#pragma once
+
+namespace zb {
+
+#define T3_TEAMS 2           // independent teams per CTA: each streams its own tiles through its own ring
+#define T3_TWARPS 4          // math warps per team (one per SM sub-partition)
+#define T3_QT 16             // most queries per tile (two half-warp groups of up to 8)
+#define T3_RB 64             // rows per row block = rows per ring stage (4 warps x 16 rows)
+#define T3_KC 3              // 16-float chunks per stage
+#define T3_SLICE_FLOATS (T3_KC * 16)
+#define T3_STAGE_BYTES (T3_RB * T3_SLICE_FLOATS * 4)   // 12288
+#define T3_CWARPS (T3_TEAMS * T3_TWARPS)
+#define T3_THREADS 384       // 2 math warpgroups (= teams) + 1 producer warpgroup (one TMA-driving warp per team)
+#define T3_MAX_STAGES 8
+#define T3_KL 32             // list length of the register top-n' (one entry per lane)
+#define T3_NOPOS 0xFFFFFFFFu
+#define T3_NOTILE 0xFFFFFFFFu
+
+struct T3TileInfo {
+    u32 tile, leaf, first, nqt, L, qh;
+    long long moff;
+};
+
+struct T3Params {
+    const u32* tile_leaf;
+    const u32* tile_first;
+    const u32* tile_count;
+    const u32* ntiles;      // device scalar
+    u32* tile_counter;      // device scalar, zeroed before launch
+    const u32* order;       // visits grouped by leaf
+    const u32* v_np;
+    const u32* v_q;
+    const u32* v_ent_off;
+    Entry* entries;
+    const float* queries;
+    const double* q_rinv;   // [nq] 1/sqrt(|q|^2) in f64 (cosine)
+    const double* bm_rinv;  // [positions] 1/sqrt(|row|^2) in f64 (cosine)
+    const u32* bm_tomb;     // bit per position
+    u64* stats;             // [0] visits, [1] pairs, [2] moved bytes
+    u64* gthr;              // [nq] per-query bound shared by all of the query's visits: min over full lists of their n'-th key
+    u32 top_k;
+    int nst;                // ring depth
+    int qcap;               // query capacity of a tile (16, 8 or 4: what fits in shared memory next to a useful ring)
+};
+
+// ---- shared memory layout of one team (byte offsets from the team's base) ----
+struct T3Layout {
+    u32 stage, queries, sums, lists, meta, info, bars, total;
+};
+__host__ __device__ __forceinline__ T3Layout t3_layout(int nst, int dimp, int qcap) {
+    T3Layout l;
+    u32 o = 0;
+    l.stage = o; o += (u32)nst * T3_STAGE_BYTES;
+    l.queries = o; o += ((u32)qcap * (u32)dimp + 16u) * 4u;     // two regions of qcap / 2 queries, the second 64 bytes further
+    o = (o + 127u) & ~127u;
+    l.sums = o; o += 2u * (u32)qcap * T3_RB * 4u;               // [2][qcap][64] f32: finished sums of a row block, double buffered
+    l.lists = o; o += (u32)qcap * 3u * T3_KL * 4u;              // [qcap][3][32] u32: key lo, key hi, position
+    l.meta = o; o += (u32)qcap * 3u * 4u;                       // [3][qcap] u32: visit, n', query of every tile slot
+    o = (o + 15u) & ~15u;
+    l.info = o; o += 2u * (u32)sizeof(T3TileInfo);
+    l.bars = o; o += (2u * T3_MAX_STAGES + 4u) * 8u;            // full[8], empty[8], ifull[2], qfull, qempty
+    l.total = (o + 127u) & ~127u;
+    return l;
+}
+// Queries per half-warp for a tile of nqt queries: the FP32 work of a tile is rows x 2 QH.
+__host__ __device__ __forceinline__ u32 t3_qh(u32 nqt) { return nqt <= 4 ? 2u : (nqt <= 8 ? 4u : (nqt <= 12 ? 6u : 8u)); }
+// Where tile slot q sits in the query block: region q / qh (the two regions are read by the two half-warps of every warp in
+// the same instruction: 64 bytes apart modulo 128, so the two 64-byte segments fall into different bank halves).
+__host__ __device__ __forceinline__ u32 t3_qslot_floats(u32 q, u32 qh, int dimp, int qcap) {
+    const u32 region = q / qh, j = q - region * qh;
+    return region * ((u32)(qcap / 2) * (u32)dimp + 16u) + j * (u32)dimp;
+}
+// Row (0..15 of the warp's 16) whose finished sums thread t of a half-warp holds after the fold.
+__host__ __device__ __forceinline__ int t3_fold_row(int t) { return ((t >> 1) & 1) | ((t & 1) << 1) | (t & 4) | (t & 8); }
+
+__device__ __forceinline__ bool t3_kp_less(u64 ka, u32 pa, u64 kb, u32 pb) { return ka < kb || (ka == kb && pa < pb); }
+
+// Cosine epilogue from precomputed reciprocal norms: the operation order of cos_bits (zb_device.cuh) with
+// ra = 1/sqrt(a2), rb = 1/sqrt(b2) hoisted (ra is +inf exactly when a2 == 0).
+__device__ __forceinline__ u64 t3_cos_bits_rinv(float ab_, double ra, double rb) {
+    const double ab = (double)ab_;
+    double c;
+    if (t3_isinf_pos(ra) && t3_isinf_pos(rb)) c = 0.0;
+    else if (ab == 0.0) c = 1.0;
+    else {
+        double t = t3_dmul(t3_dmul(ab, ra), rb);
+        double r = t3_dsub(1.0, t);
+        c = r > 0.0 ? r : 0.0;
+    }
+    return t3_dbits(t3_dsub(1.0, c));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// One math warp's share of one tile: rows 16 * tw .. 16 * tw + 15 of every 64-row stage, against the QH queries of its
+// half-warp (half-warp h of every warp serves tile slots h * QH .. h * QH + QH - 1); then, per row block, the list
+// maintenance of the tile slots this warp owns (slot q is owned by warp q % 4).
+// ------------------------------------------------------------------------------------------------------------------
+template <int METRIC, int QH>
+__device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& lay, const ForestView& f, const T3Params& tp,
+                                             const T3TileInfo& inf, const int tw, const int lane, u32& buf, u32& ph, u32& blk,
+                                             const int team, u64 (&thr)[4]) {
+    const int t = lane & 15, h = lane >> 4;
+    const int dimp = f.dimp, chunks = f.chunks;
+    const int nsl = (chunks + T3_KC - 1) / T3_KC;
+    const u32 S = (u32)tp.nst, L = inf.L, nqt = inf.nqt;
+    const u32 nblocks = (L + T3_RB - 1) / T3_RB;
+    const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
+    const float* s_q = reinterpret_cast<const float*>(tb + lay.queries) + (u32)h * ((u32)(tp.qcap / 2) * (u32)dimp + 16u) + t;
+    float* s_sums = reinterpret_cast<float*>(tb + lay.sums);
+    u32* s_lists = reinterpret_cast<u32*>(tb + lay.lists);
+    const u32* s_meta = reinterpret_cast<const u32*>(tb + lay.meta);
+    const int myrow = t3_fold_row(t);
+
+    for (u32 b = 0; b < nblocks; ++b, ++blk) {
+        const u32 nrows = min((u32)T3_RB, L - b * T3_RB);
+        const u32 base = (u32)(inf.moff + (long long)b * T3_RB);  // position of row 0 of the block
+        u64 acc[8][QH];  // acc[u][j] = packed lane partials of rows 2u, 2u+1 against query j
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int j = 0; j < QH; ++j) acc[u][j] = 0ull;
+        for (int sl = 0; sl < nsl; ++sl) {
+            const int kcs = min(T3_KC, chunks - sl * T3_KC);
+            mbar_wait(bar_full + 8 * buf, ph);
+            const float* rp = reinterpret_cast<const float*>(tb + lay.stage + (size_t)buf * T3_STAGE_BYTES) +
+                              (tw * 16) * T3_SLICE_FLOATS + t;
+            const float* qp = s_q + sl * T3_SLICE_FLOATS;
+            auto chunk = [&](int c) {
+                u64 qq[QH];
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    const float q = qp[j * dimp + c * 16];
+                    qq[j] = t3_pk2(q, q);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const u64 ra = t3_pk2(rp[(2 * u) * T3_SLICE_FLOATS + c * 16], rp[(2 * u + 1) * T3_SLICE_FLOATS + c * 16]);
+#pragma unroll
+                    for (int j = 0; j < QH; ++j) {
+                        if (METRIC == 0) acc[u][j] = t3_fma2(ra, qq[j], acc[u][j]);
+                        else {
+                            const u64 d = t3_sub2(ra, qq[j]);
+                            acc[u][j] = t3_fma2(d, d, acc[u][j]);
+                        }
+                    }
+                }
+            };
+            if (kcs == T3_KC) {  // the common case, straight-line: the next chunk's shared-memory loads can be hoisted over this chunk's math
+#pragma unroll
+                for (int c = 0; c < T3_KC; ++c) chunk(c);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < kcs; ++c) chunk(c);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
+            if (++buf == S) { buf = 0; ph ^= 1u; }
+        }
+        // ---- what the epilogue needs from global memory, requested before the fold hides the latency ----
+        const u32 r_lo = (u32)lane, r_hi = (u32)lane + 32u;  // the two rows of the block this lane finishes in the epilogue
+        double rinv_lo = 0.0, rinv_hi = 0.0;
+        if (METRIC == 0) {
+            if (r_lo < nrows) rinv_lo = tp.bm_rinv[base + r_lo];
+            if (r_hi < nrows) rinv_hi = tp.bm_rinv[base + r_hi];
+        }
+        u32 tword = 0;  // tombstone words covering positions base .. base + 63 (at most 3 words), one per lane
+        if (lane < 3) tword = tp.bm_tomb[(base >> 5) + lane];
+        u64 gbound[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const u32 q = (u32)tw + 4u * e;
+            gbound[e] = q < nqt ? t3_ldcg_u64(tp.gthr + s_meta[2 * tp.qcap + q]) : ZB_SENTINEL;
+        }
+        // ---- fold: canonical tree over the 16 lanes of the half-warp; a thread keeps half of its rows per step ----
+        float v8[8][QH];
+        {
+            const bool t3b = (t & 8) != 0;
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    // rows a and a + 8 of the warp's 16: row r lives in acc[r / 2][j], half r % 2
+                    float lo0, hi0, lo1, hi1;
+                    t3_upk2(acc[a >> 1][j], lo0, hi0);
+                    t3_upk2(acc[(a + 8) >> 1][j], lo1, hi1);
+                    const float va = (a & 1) ? hi0 : lo0, vb = (a & 1) ? hi1 : lo1;
+                    const float mine = t3b ? vb : va, send = t3b ? va : vb;
+                    v8[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 8));  // lane i + lane i + 8
+                }
+        }
+        float v4[4][QH];
+        {
+            const bool t2b = (t & 4) != 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    const float mine = t2b ? v8[a + 4][j] : v8[a][j], send = t2b ? v8[a][j] : v8[a + 4][j];
+                    v4[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 4));  // x[i] + x[i + 4]
+                }
+        }
+        float v2[2][QH];
+        {
+            const bool t0b = (t & 1) != 0;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    const float mine = t0b ? v4[a + 2][j] : v4[a][j], send = t0b ? v4[a][j] : v4[a + 2][j];
+                    v2[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 1));  // r0 + r1, r2 + r3
+                }
+        }
+        {
+            const bool t1b = (t & 2) != 0;
+            float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * 16 + myrow;
+#pragma unroll
+            for (int j = 0; j < QH; ++j) {
+                const float mine = t1b ? v2[1][j] : v2[0][j], send = t1b ? v2[0][j] : v2[1][j];
+                const float sum = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 2));  // (r0 + r1) + (r2 + r3)
+                dst[(size_t)(h * QH + j) * T3_RB] = sum;
+            }
+        }
+        t3_team_sync(team);  // the block's sums are complete; the previous use of this buffer was consumed two blocks ago
+        // ---- epilogue: this warp finishes the tile slots it owns (q = tw, tw + 4, ...): keys, filter, list insertion ----
+        const float* sums = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const u32 q = (u32)tw + 4u * e;
+            if (q >= nqt) break;  // warp uniform
+            if (gbound[e] < thr[e]) thr[e] = gbound[e];
+            const int np = (int)s_meta[tp.qcap + q];
+            const u32 gq = s_meta[2 * tp.qcap + q];
+            const float s_lo = sums[(size_t)q * T3_RB + r_lo], s_hi = sums[(size_t)q * T3_RB + r_hi];
+            u64 k_lo = ZB_SENTINEL, k_hi = ZB_SENTINEL;
+            if (METRIC == 0) {
+                const double qr = tp.q_rinv[gq];
+                if (r_lo < nrows) k_lo = t3_cos_bits_rinv(s_lo, rinv_lo, qr);
+                if (r_hi < nrows) k_hi = t3_cos_bits_rinv(s_hi, rinv_hi, qr);
+            } else {
+                if (r_lo < nrows) k_lo = METRIC == 1 ? l2sq_bits(s_lo) : l2_bits(s_lo);
+                if (r_hi < nrows) k_hi = METRIC == 1 ? l2sq_bits(s_hi) : l2_bits(s_hi);
+            }
+            const u64 thr0 = thr[e];
+            // most blocks have no candidate under the filter: one ballot and out
+            if (!__ballot_sync(0xffffffffu, (r_lo < nrows && k_lo <= thr0) || (r_hi < nrows && k_hi <= thr0))) continue;
+            u32* lst = s_lists + (size_t)q * 3 * T3_KL;
+            u64 Lk = ((u64)lst[T3_KL + lane] << 32) | lst[lane];
+            u32 Lp = lst[2 * T3_KL + lane];
+            u64 th = thr0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const u64 key = i ? k_hi : k_lo;
+                const bool valid = (i ? r_hi : r_lo) < nrows;
+                unsigned m = __ballot_sync(0xffffffffu, valid && key <= th);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const u64 nk = t3_shfl64(key, src);
+                    if (nk > th) continue;  // the filter tightened since the ballot
+                    const u32 npos = base + (u32)src + 32u * i;
+                    const u32 w = __shfl_sync(0xffffffffu, tword, (int)((npos >> 5) - (base >> 5)));
+                    if ((w >> (npos & 31)) & 1u) continue;  // tombstoned (D1)
+                    const unsigned mm = __ballot_sync(0xffffffffu, t3_kp_less(nk, npos, Lk, Lp));
+                    const int ins = mm ? __ffs(mm) - 1 : 32;
+                    if (ins >= np) continue;
+                    const u64 upk = t3_shfl_up64(Lk);
+                    const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
+                    if (lane > ins) { Lk = upk; Lp = upp; }
+                    else if (lane == ins) { Lk = nk; Lp = npos; }
+                    const u64 lk = t3_shfl64(Lk, np - 1);
+                    if (lk < th) th = lk;
+                }
+            }
+            lst[lane] = (u32)Lk;
+            lst[T3_KL + lane] = (u32)(Lk >> 32);
+            lst[2 * T3_KL + lane] = Lp;
+            thr[e] = th;
+            // publish: a full list of n' == top_k distinct rows bounds the query's final k-th best
+            if (lane == 0 && np == (int)tp.top_k && th < gbound[e]) t3_atomic_min_u64(tp.gthr + gq, th);
+            __syncwarp();
+        }
+    }
+}
+
+// Two teams per CTA, each = 4 math warps (one per SM sub-partition) + 1 producer warp, each streaming its own tiles:
+// the two math warps that share a sub-partition belong to different tiles, so one warp's fold / epilogue / tile change
+// overlaps the other's FP32 loop, and a bandwidth-bound tile (few queries) shares the SM with a pipe-bound one.
+template <int METRIC>
+__device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, const T3Params& tp, unsigned char* smem) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dimp = f.dimp, chunks = f.chunks;
+    const int nsl = (chunks + T3_KC - 1) / T3_KC;
+    const u32 S = (u32)tp.nst;
+    const T3Layout lay = t3_layout(tp.nst, dimp, tp.qcap);
+    const int team = warp < T3_CWARPS ? warp / T3_TWARPS : (warp - T3_CWARPS) % T3_TEAMS;
+    unsigned char* tb = smem + (size_t)team * lay.total;
+    T3TileInfo* s_info = reinterpret_cast<T3TileInfo*>(tb + lay.info);
+    const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
+    const u32 bar_ifull = bar_full + 16 * T3_MAX_STAGES, bar_qfull = bar_ifull + 16, bar_qempty = bar_ifull + 24;
+
+    if (tid == 0) {
+        for (int tm = 0; tm < T3_TEAMS; ++tm) {
+            const u32 o = (u32)(tm * lay.total);  // this thread is in team 0: the other teams' barriers sit lay.total apart
+            for (u32 i = 0; i < S; ++i) {
+                mbar_init(bar_full + o + 8 * i, 1);
+                mbar_init(bar_empty + o + 8 * i, T3_TWARPS);
+            }
+            mbar_init(bar_ifull + o, 1);
+            mbar_init(bar_ifull + o + 8, 1);
+            mbar_init(bar_qfull + o, 1);
+            mbar_init(bar_qempty + o, T3_TWARPS);
+        }
+        t3_fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp >= T3_CWARPS) {
+        // =========================== producer warpgroup: one thread per team drives TMA ===========================
+        t3_setmaxnreg_dec();
+        if (warp >= T3_CWARPS + T3_TEAMS || lane != 0) return;
+        t3_prefetch_map(tmap);
+        float* s_q = reinterpret_cast<float*>(tb + lay.queries);
+        const u32 ntiles = *tp.ntiles;
+        u32 buf = 0, eph = 1;  // ring slot of the next stage to issue; parity to wait for on its empty barrier (first lap: free)
+        u32 tile = atomicAdd(tp.tile_counter, 1u);
+        for (u32 it = 0;; ++it) {
+            T3TileInfo* inf = s_info + (it & 1);
+            if (tile >= ntiles) {
+                inf->tile = T3_NOTILE;
+                mbar_arrive(bar_ifull + 8 * (it & 1));
+                break;
+            }
+            const u32 leaf = tp.tile_leaf[tile], first = tp.tile_first[tile], nqt = tp.tile_count[tile];
+            const u32 L = f.leaf_len[leaf];
+            const long long moff = f.leaf_off[leaf];
+            const u32 qh = t3_qh(nqt);
+            inf->tile = tile; inf->leaf = leaf; inf->first = first; inf->nqt = nqt; inf->L = L; inf->qh = qh; inf->moff = moff;
+            mbar_arrive(bar_ifull + 8 * (it & 1));
+            const u32 nblocks = (L + T3_RB - 1) / T3_RB;
+            const u32 total = nblocks * (u32)nsl;
+            u32 b = 0, sl = 0;
+            auto issue = [&](u32 count) {
+                for (u32 j = 0; j < count; ++j) {
+                    mbar_wait(bar_empty + 8 * buf, eph);
+                    mbar_arrive_expect_tx(bar_full + 8 * buf, T3_STAGE_BYTES);
+                    t3_tma_2d_g2s(smem_u32(tb + lay.stage + (size_t)buf * T3_STAGE_BYTES), tmap, (int)(sl * T3_SLICE_FLOATS),
+                                  (long long)(moff + (long long)b * T3_RB), bar_full + 8 * buf);
+                    if (++sl == (u32)nsl) { sl = 0; ++b; }
+                    if (++buf == S) { buf = 0; eph ^= 1u; }
+                }
+            };
+            // rows of this tile may run ahead into the ring while the math warps still finish the previous tile ...
+            const u32 pre = total < S ? total : S;
+            issue(pre);
+            // ... the resident query block is single-buffered: wait until the previous tile is done with it
+            if (it > 0) mbar_wait(bar_qempty, (it - 1) & 1);
+            mbar_arrive_expect_tx(bar_qfull, nqt * (u32)dimp * 4u);
+            {  // address loads batched (independent chains), then the copies
+                u32 qi[T3_QT];
+#pragma unroll
+                for (int j = 0; j < T3_QT; ++j) qi[j] = (u32)j < nqt ? tp.order[first + j] : 0u;
+#pragma unroll
+                for (int j = 0; j < T3_QT; ++j) qi[j] = (u32)j < nqt ? tp.v_q[qi[j]] : 0u;
+#pragma unroll
+                for (int j = 0; j < T3_QT; ++j)
+                    if ((u32)j < nqt)
+                        bulk_g2s(smem_u32(s_q + t3_qslot_floats((u32)j, qh, dimp, tp.qcap)), tp.queries + (size_t)qi[j] * dimp,
+                                 (u32)dimp * 4u, bar_qfull);
+            }
+            issue(total - pre);
+            // fetched only now (not while the tile is in flight), so consecutive tiles start back to back
+            const u32 next_tile = atomicAdd(tp.tile_counter, 1u);
+            atomicAdd(&tp.stats[0], (u64)nqt);
+            atomicAdd(&tp.stats[1], (u64)nqt * L);
+            atomicAdd(&tp.stats[2], ((u64)L + nqt) * (u64)dimp * 4ull);  // algorithmic bytes: leaf rows once + the tile's queries
+            tile = next_tile;
+        }
+        return;
+    }
+
+    // =================================== consumer (math) warps ===================================
+    t3_setmaxnreg_inc();
+    const int tw = warp % T3_TWARPS;
+    u32 rbuf = 0, rph = 0, blk = 0;  // ring position of the next stage to consume (slot, phase parity); running row-block count
+    u32* s_lists = reinterpret_cast<u32*>(tb + lay.lists);
+    u32* s_meta = reinterpret_cast<u32*>(tb + lay.meta);
+    for (u32 it = 0;; ++it) {
+        mbar_wait(bar_ifull + 8 * (it & 1), (it >> 1) & 1);
+        const T3TileInfo inf = s_info[it & 1];
+        if (inf.tile == T3_NOTILE) break;
+        const u32 nqt = inf.nqt;
+        // the tile slots this warp owns: visit, n', query -> shared memory (read back as broadcasts in the epilogue), empty lists
+        if (lane < 4) {
+            const u32 q = (u32)tw + 4u * lane;
+            if (q < nqt) {
+                const u32 visit = tp.order[inf.first + q];
+                s_meta[q] = visit;
+                s_meta[tp.qcap + q] = tp.v_np[visit];
+                s_meta[2 * tp.qcap + q] = tp.v_q[visit];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const u32 q = (u32)tw + 4u * e;
+            if (q < nqt) {
+                u32* lst = s_lists + (size_t)q * 3 * T3_KL;
+                lst[lane] = 0xFFFFFFFFu;
+                lst[T3_KL + lane] = 0xFFFFFFFFu;
+                lst[2 * T3_KL + lane] = T3_NOPOS;
+            }
+        }
+        u64 thr[4] = {ZB_SENTINEL, ZB_SENTINEL, ZB_SENTINEL, ZB_SENTINEL};  // filter of each owned slot: its list's n'-th key or the shared bound
+        __syncwarp();
+        mbar_wait(bar_qfull, it & 1);
+        switch (inf.qh) {
+            case 2: t3_scan_tile<METRIC, 2>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr); break;
+            case 4: t3_scan_tile<METRIC, 4>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr); break;
+            case 6: t3_scan_tile<METRIC, 6>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr); break;
+            default: t3_scan_tile<METRIC, 8>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr); break;
+        }
+        // ---- end of tile: release the query block, write the owned visits' top lists ----
+        if (lane == 0) mbar_arrive(bar_qempty);
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e) {
+            const u32 q = (u32)tw + 4u * e;
+            if (q >= nqt) break;
+            const u32 v = s_meta[q];
+            const int np = (int)s_meta[tp.qcap + q];
+            const u32* lst = s_lists + (size_t)q * 3 * T3_KL;
+            const u64 k = ((u64)lst[T3_KL + lane] << 32) | lst[lane];
+            const u32 p = lst[2 * T3_KL + lane];
+            const u32 e0 = tp.v_ent_off[v], e1 = tp.v_ent_off[v + 1];
+            if ((u32)lane < e1 - e0) {
+                Entry en{ZB_SENTINEL, ZB_SENTINEL};
+                if (lane < np && p != T3_NOPOS) en = Entry{k, f.ord[f.members[p]]};
+                tp.entries[e0 + lane] = en;
+            }
+        }
+        __syncwarp();  // the slots' shared-memory state may be re-initialised for the next tile
+    }
+}
+
+}  // namespace zb

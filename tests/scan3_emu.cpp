@@ -21,6 +21,7 @@
 #include <random>
 #include <thread>
 #include <unordered_map>
+#include <algorithm>
 #include <vector>
 
 #define __global__
@@ -220,6 +221,8 @@ static inline void t3_fence_barrier_init() {}
 static inline void t3_setmaxnreg_dec() {}
 static inline void t3_setmaxnreg_inc() {}
 static inline void t3_prefetch_map(const T3Map&) {}
+static inline void t3_prefetch_l1(const void*) {}
+static inline bool t3_above_from_dot(float dot, float constant) { return (double)dot + (double)constant >= 0.0; }
 static inline u64 l2sq_bits(float s) { return t3_dbits((double)s); }
 static inline u64 l2_bits(float s) { return t3_dbits(sqrt((double)s)); }
 }  // namespace zb
@@ -243,6 +246,7 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
     tp.order = order; tp.v_np = v_np; tp.v_q = v_q; tp.v_ent_off = v_ent_off; tp.entries = reinterpret_cast<zb::Entry*>(entries);
     tp.queries = queries_padded; tp.q_rinv = q_rinv; tp.bm_rinv = bm_rinv; tp.bm_tomb = bm_tomb;
     tp.stats = reinterpret_cast<zb::u64*>(stats3); tp.gthr = reinterpret_cast<zb::u64*>(gthr); tp.top_k = top_k; tp.nst = nst; tp.qcap = qcap;
+    tp.pj_cst = nullptr; tp.pj_sign = nullptr; tp.pj_hp = 0;
     zb::T3Map map{bm_rows_padded, positions, f.dimp};
     const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap);
     std::vector<unsigned char> smem((size_t)T3_TEAMS * lay.total + 1024);
@@ -264,9 +268,59 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
         for (unsigned t = 0; t < T3_THREADS; ++t)
             th.emplace_back([&, t] {
                 emu_threadIdx = Dim3{t, 0, 0};
-                if (metric == 0) zb::t3_body<0>(map, f, tp, emu_smem);
-                else if (metric == 1) zb::t3_body<1>(map, f, tp, emu_smem);
-                else zb::t3_body<2>(map, f, tp, emu_smem);
+                if (metric == 0) zb::t3_body<0, 0>(map, f, tp, emu_smem);
+                else if (metric == 1) zb::t3_body<1, 0>(map, f, tp, emu_smem);
+                else zb::t3_body<2, 0>(map, f, tp, emu_smem);
+            });
+        for (auto& x : th) x.join();
+        dma.finish();
+    }
+    return (int)counter;
+}
+
+// Projection mode: rows [n][dimp] x planes [H][dimp] -> sign[n][Hp]; tiles = (row range, <= tq planes), built here the way
+// launch_project3 builds them.
+extern "C" __attribute__((visibility("default"))) int emu_project3(int blocks, int dim, int nst, int qcap, uint64_t n, const float* rows_padded,
+                                                                 int H, const float* coef_padded, const float* cst, uint32_t range_rows,
+                                                                 uint32_t tq, uint8_t* sign, int Hp, uint64_t* stats3) {
+    zb::ForestView f;
+    f.dimp = (dim + 15) / 16 * 16; f.chunks = f.dimp / 16;
+    const uint32_t nranges = (uint32_t)((n + range_rows - 1) / range_rows), npt = (uint32_t)((H + tq - 1) / tq);
+    std::vector<long long> leaf_off(nranges);
+    std::vector<uint32_t> leaf_len(nranges), tile_leaf, tile_first, tile_count;
+    for (uint32_t r = 0; r < nranges; ++r) {
+        leaf_off[r] = (long long)r * range_rows;
+        leaf_len[r] = (uint32_t)std::min<uint64_t>(range_rows, n - (uint64_t)r * range_rows);
+        for (uint32_t p = 0; p < npt; ++p) {
+            tile_leaf.push_back(r); tile_first.push_back(p * tq); tile_count.push_back(std::min<uint32_t>(tq, (uint32_t)H - p * tq));
+        }
+    }
+    f.leaf_off = leaf_off.data(); f.leaf_len = leaf_len.data(); f.members = nullptr; f.ord = nullptr;
+    uint32_t counter = 0, ntiles = (uint32_t)tile_leaf.size();
+    zb::T3Params tp;
+    memset(&tp, 0, sizeof tp);
+    tp.tile_leaf = tile_leaf.data(); tp.tile_first = tile_first.data(); tp.tile_count = tile_count.data(); tp.ntiles = &ntiles;
+    tp.tile_counter = &counter; tp.queries = coef_padded; tp.stats = reinterpret_cast<zb::u64*>(stats3); tp.nst = nst; tp.qcap = qcap;
+    tp.pj_cst = cst; tp.pj_sign = sign; tp.pj_hp = Hp;
+    zb::T3Map map{rows_padded, n, f.dimp};
+    const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap);
+    std::vector<unsigned char> smem((size_t)T3_TEAMS * lay.total + 1024);
+    emu_warps.clear();
+    for (int i = 0; i < T3_THREADS / 32; ++i) emu_warps.emplace_back(new WarpBox());
+    for (int b = 0; b < blocks; ++b) {
+        for (size_t i = 0; i < smem.size(); ++i) smem[i] = (unsigned char)(0x5A ^ (i * 37));
+        emu_smem = smem.data();
+        emu_mbars.clear();
+        CopyEngine dma;
+        emu_dma = &dma;
+        dma.start();
+        std::barrier<> bar(T3_THREADS), tb0(128), tb1(128);
+        emu_block_bar = &bar; emu_team_bar[0] = &tb0; emu_team_bar[1] = &tb1;
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T3_THREADS; ++t)
+            th.emplace_back([&, t] {
+                emu_threadIdx = Dim3{t, 0, 0};
+                zb::t3_body<0, 1>(map, f, tp, emu_smem);
             });
         for (auto& x : th) x.join();
         dma.finish();

@@ -162,6 +162,32 @@ def test_small_query_capacity_and_deep_ring(emu):
         assert np.array_equal(entries[ent_off[v]:ent_off[v + 1]], expected_visit(case, zo.COSINE, v, int(v_np[v]))), v
 
 
+@pytest.mark.parametrize("dim,H,n,tq", [(48, 16, 200, 16), (100, 37, 333, 16), (64, 5, 70, 16), (200, 24, 150, 8)])
+def test_projection_mode_signs_equal_point_is_above(emu, dim, H, n, tq):
+    """MODE 1 of the same kernel body (flat-table hashing): sign[row][plane] = Hyperplane::point_is_above (lsh.rs:39-43) for
+    every (row, plane), planes in tiles of <= 16, rows in ranges that are not multiples of the 64-row stage."""
+    rng = np.random.default_rng(dim + H)
+    dimp = (dim + 15) // 16 * 16
+    rows = rng.standard_normal((n, dim)).astype(F32)
+    coef = rng.standard_normal((H, dim)).astype(F32)
+    cst = rng.standard_normal(H).astype(F32)
+    coef[0] = 0; cst[0] = -0.0                              # dot = +0, constant -0: above
+    rows[5] = 0
+    rows_p = np.zeros((n + 1, dimp), F32); rows_p[:n, :dim] = rows
+    coef_p = np.zeros((H, dimp), F32); coef_p[:, :dim] = coef
+    Hp = (H + 15) // 16 * 16
+    sign = np.full((n, Hp), 7, np.uint8)
+    stats = np.zeros(8, np.uint64)
+    emu.emu_project3.restype = C.c_int
+    emu.emu_project3.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]
+    emu.emu_project3(2, dim, 4, 16, n, rows_p.ctypes.data, H, coef_p.ctypes.data, cst.ctypes.data, 100, tq, sign.ctypes.data, Hp,
+                     stats.ctypes.data)
+    exp = np.stack([zo.above_batch(np.broadcast_to(coef[h], rows.shape).copy(), np.full(n, cst[h], F32), rows) for h in range(H)], axis=1)
+    assert np.array_equal(sign[:, :H], exp.astype(np.uint8))
+    assert np.all(sign[:, H:] == 7)                        # nothing written beyond the planes
+
+
 def test_fold_row_is_a_bijection():
     rows = sorted(((t >> 1) & 1) | ((t & 1) << 1) | (t & 4) | (t & 8) for t in range(16))
     assert rows == list(range(16))

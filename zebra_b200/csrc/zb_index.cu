@@ -162,6 +162,7 @@ struct zb_index {
     DBuf<int> b_slot_a, b_slot_b;
     DBuf<float> b_pair_rows;
     ScanWorkspace scan_ws;
+    ScanWorkspace pj_ws;  // flat-table projection (project3)
     ScanWorkspace qt_ws;  // keys-only tile scan of the visits the fused kernel leaves (cosine / L2, n' > 32)
 
     // ---- knobs / stats ----
@@ -1624,7 +1625,10 @@ static void hash_device_impl(zb_index* ix, uint64_t n, const float* d_rows, uint
     if (flat) {  // every row asks the same T x K planes: one dense pass, sign bits packed into the keys
         const int H = ix->T * (int)ix->flat_bits, Hp = (H + 15) / 16 * 16;
         ix->pj_sign.ensure(std::max<u64>(1, n * (u64)Hp));
-        launch_project_flat(x, n, ix->d_coef.p, ix->d_cst.p, H, ix->dimp, ix->pj_sign.p, Hp, ix->stream);
+        if (ix->p_flat_project == 1 && project3_supported(ix->dimp))   // knob flat_project: 1 = TMA-staged tile kernel, 2 = the first kernel (rows and planes through L1)
+            project3(ix->pj_ws, x, n, ix->d_coef.p, ix->d_cst.p, H, ix->dimp, ix->pj_sign.p, Hp, ix->stream);
+        else
+            launch_project_flat(x, n, ix->d_coef.p, ix->d_cst.p, H, ix->dimp, ix->pj_sign.p, Hp, ix->stream);
         launch_pack_flat_keys(ix->pj_sign.p, n, Hp, ix->T, (int)ix->flat_bits, (u64*)d_keys, d_depths, d_leaves, ix->stream);
     } else {
         launch_hash(ix->view(), x, n, (u64*)d_keys, d_depths, d_leaves, (int)ix->p_hash_variant, ix->stream);

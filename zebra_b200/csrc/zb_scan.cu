@@ -15,6 +15,7 @@
 //     with a ballot + shuffle-up.  No block-wide barrier anywhere in the steady state.  The two row halves of a
 //     query are merged once per tile with a shuffle bitonic network, tombstoned rows are masked at insertion.
 // The kernel is persistent (one CTA per SM, tiles handed out by an atomic counter).
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda.h>
 
@@ -564,6 +565,8 @@ __device__ __forceinline__ void t3_prefetch_map(const T3Map& m) { asm volatile("
 __device__ __forceinline__ void t3_tma_2d_g2s(u32 dst, const T3Map& map, int c0, long long row, u32 bar) {
     tma_2d_g2s(dst, &map, c0, (int)row, bar);
 }
+__device__ __forceinline__ void t3_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ bool t3_above_from_dot(float dot, float constant) { return above_from_dot(dot, constant); }
 }  // namespace zb
 #include "zb_scan3_kernel.cuh"
 namespace zb {
@@ -571,7 +574,12 @@ namespace zb {
 template <int METRIC>
 __global__ void __launch_bounds__(T3_THREADS, 1) tile_scan3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
     extern __shared__ __align__(1024) unsigned char smem3[];
-    t3_body<METRIC>(tmap, f, tp, smem3);
+    t3_body<METRIC, 0>(tmap, f, tp, smem3);
+}
+// Flat-table projection on the same skeleton (MODE 1): tmap covers the INPUT rows, tp.queries the plane coefficients.
+__global__ void __launch_bounds__(T3_THREADS, 1) project3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
+    extern __shared__ __align__(1024) unsigned char smem3[];
+    t3_body<0, 1>(tmap, f, tp, smem3);
 }
 
 // =====================================================================================================
@@ -613,6 +621,44 @@ __global__ void ts_filltiles_kernel(u32 nleaves, const u32* __restrict__ leaf_co
     const u32 nt = (c + tq - 1) / tq;   // full tiles first, the remainder last (cost is per started query group)
     for (u32 j = 0, done = 0; j < nt; ++j) {
         const u32 n = c - done < tq ? c - done : tq;
+        tile_leaf[ts + j] = l;
+        tile_first[ts + j] = leaf_start[l] + done;
+        tile_count[ts + j] = n;
+        done += n;
+    }
+}
+
+// Longest-processing-time-first dispatch: leaves ordered by (rows x visiting queries) descending, the tiles of one leaf
+// kept together (sibling tiles start back to back and share the leaf's rows through L2).  The persistent teams pull tiles
+// from one counter, so the big tiles go first and the short ones fill the tail.
+__global__ void ts_leafkey_kernel(u32 nleaves, const u32* __restrict__ leaf_count, const u32* __restrict__ leaf_len,
+                                  u32* __restrict__ key, u32* __restrict__ val) {
+    const u32 l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaves) return;
+    const u64 cost = (u64)leaf_count[l] * leaf_len[l];
+    key[l] = leaf_count[l] ? ~(u32)(cost > 0xFFFFFFFEull ? 0xFFFFFFFEull : cost) : 0xFFFFFFFFu;  // ascending sort = cost descending, unvisited leaves last
+    val[l] = l;
+}
+__global__ void ts_tilecount_sorted_kernel(u32 nleaves, const u32* __restrict__ sorted_leaf, const u32* __restrict__ leaf_count, u32 tq,
+                                           u32* __restrict__ tile_cnt) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nleaves) tile_cnt[i] = i < nleaves ? (leaf_count[sorted_leaf[i]] + tq - 1) / tq : 0u;
+}
+__global__ void ts_filltiles_sorted_kernel(u32 nleaves, const u32* __restrict__ sorted_leaf, const u32* __restrict__ leaf_count,
+                                           const u32* __restrict__ leaf_start, const u32* __restrict__ tile_start, u32 tq,
+                                           u32* __restrict__ tile_leaf, u32* __restrict__ tile_first, u32* __restrict__ tile_count,
+                                           const u32* __restrict__ leaf_len, u64 row_bytes, u64* __restrict__ unique_bytes) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nleaves) return;
+    const u32 l = sorted_leaf[i];
+    const u32 c = leaf_count[l], ts = tile_start[i];
+    if (!c) return;
+    atomicAdd(unique_bytes, (u64)leaf_len[l] * row_bytes);
+    const u32 nt = (c + tq - 1) / tq;
+    // the leaf's queries spread evenly over its tiles: 17 queries are 9 + 8, not 16 + 1 (the cost of a tile grows in steps of QH)
+    const u32 per = c / nt, extra = c - per * nt;
+    for (u32 j = 0, done = 0; j < nt; ++j) {
+        const u32 n = per + (j < extra ? 1u : 0u);
         tile_leaf[ts + j] = l;
         tile_first[ts + j] = leaf_start[l] + done;
         tile_count[ts + j] = n;
@@ -679,7 +725,8 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
                u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
                u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s) {
     ws.launched = false;
-    const u32 pace_window = tile_queries >> 8;  // knob: bits 8.. of tile_queries carry the pacing window (tests / ablations)
+    const u32 pace_window = tile_queries >> 9;  // knob: bits 9.. of tile_queries carry the pacing window (tests / ablations)
+    const bool lpt_order = false;               // second generation: tiles stay in leaf order
     tile_queries &= 0xFF;
     if (!nv || !nleaves || !tile_scan_supported(f.dimp, top_k)) return;
     const u32 tq = tile_queries >= 1 && tile_queries <= TS_QT ? tile_queries : TS_QT;
@@ -720,11 +767,31 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
     ws.tile_per_leaf.ensure(nleaves + 1);
     ws.tile_start.ensure(nleaves + 1);
     ws.tile_cnt.ensure(nv);
-    ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, tq, ws.tile_per_leaf.p);
-    cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
-    ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, tq,
-                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, f.leaf_len,
-                                                              (u64)f.dimp * 4ull, reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
+    if (lpt_order) {
+        for (int b = 0; b < 2; ++b) {
+            ws.sort_key[b].ensure(nleaves);
+            ws.sort_val[b].ensure(nleaves);
+        }
+        size_t sort_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const u32*)nullptr, (u32*)nullptr, (const u32*)nullptr, (u32*)nullptr,
+                                        (long long)nleaves, 0, 32, s);
+        ws.sort_tmp.ensure(sort_bytes + 256);
+        ts_leafkey_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, f.leaf_len, ws.sort_key[0].p, ws.sort_val[0].p);
+        cub::DeviceRadixSort::SortPairs(ws.sort_tmp.p, sort_bytes, ws.sort_key[0].p, ws.sort_key[1].p, ws.sort_val[0].p, ws.sort_val[1].p,
+                                        (long long)nleaves, 0, 32, s);
+        ts_tilecount_sorted_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.sort_val[1].p, ws.leaf_count.p, tq, ws.tile_per_leaf.p);
+        cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
+        ts_filltiles_sorted_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.sort_val[1].p, ws.leaf_count.p, ws.leaf_start.p,
+                                                                         ws.tile_start.p, tq, ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p,
+                                                                         f.leaf_len, (u64)f.dimp * 4ull,
+                                                                         reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
+    } else {
+        ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, tq, ws.tile_per_leaf.p);
+        cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
+        ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, tq,
+                                                                  ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, f.leaf_len,
+                                                                  (u64)f.dimp * 4ull, reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
+    }
 
     TileParams tp;
     tp.tile_leaf = ws.tile_leaf.p;
@@ -823,6 +890,7 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
     ws.launched = false;
     int nst = 0, qcap = 0;
     if (!nv || !nleaves || top_k < 1 || top_k > T3_KL || !t3_config(f.dimp, &nst, &qcap)) return;
+    const bool lpt_order = ((tile_queries >> 8) & 1u) == 0;  // knob bit 8 of tile_queries: 1 = tiles in leaf order (ablation)
     tile_queries &= 0xFF;
     const u32 tq = tile_queries >= 1 && tile_queries <= (u32)qcap ? tile_queries : (u32)qcap;
     int dev = 0, sms = 0;
@@ -853,11 +921,31 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
     ws.tile_per_leaf.ensure(nleaves + 1);
     ws.tile_start.ensure(nleaves + 1);
     ws.tile_cnt.ensure(nv);
-    ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, tq, ws.tile_per_leaf.p);
-    cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
-    ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, tq,
-                                                              ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, f.leaf_len,
-                                                              (u64)f.dimp * 4ull, reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
+    if (lpt_order) {
+        for (int b = 0; b < 2; ++b) {
+            ws.sort_key[b].ensure(nleaves);
+            ws.sort_val[b].ensure(nleaves);
+        }
+        size_t sort_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const u32*)nullptr, (u32*)nullptr, (const u32*)nullptr, (u32*)nullptr,
+                                        (long long)nleaves, 0, 32, s);
+        ws.sort_tmp.ensure(sort_bytes + 256);
+        ts_leafkey_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, f.leaf_len, ws.sort_key[0].p, ws.sort_val[0].p);
+        cub::DeviceRadixSort::SortPairs(ws.sort_tmp.p, sort_bytes, ws.sort_key[0].p, ws.sort_key[1].p, ws.sort_val[0].p, ws.sort_val[1].p,
+                                        (long long)nleaves, 0, 32, s);
+        ts_tilecount_sorted_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.sort_val[1].p, ws.leaf_count.p, tq, ws.tile_per_leaf.p);
+        cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
+        ts_filltiles_sorted_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.sort_val[1].p, ws.leaf_count.p, ws.leaf_start.p,
+                                                                         ws.tile_start.p, tq, ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p,
+                                                                         f.leaf_len, (u64)f.dimp * 4ull,
+                                                                         reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
+    } else {
+        ts_tilecount_kernel<<<(nleaves + 256) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, tq, ws.tile_per_leaf.p);
+        cub::DeviceScan::ExclusiveSum(ws.tmp.p, tmp_bytes, ws.tile_per_leaf.p, ws.tile_start.p, (long long)(nleaves + 1), s);
+        ts_filltiles_kernel<<<(nleaves + 255) / 256, 256, 0, s>>>(nleaves, ws.leaf_count.p, ws.leaf_start.p, ws.tile_start.p, tq,
+                                                                  ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, f.leaf_len,
+                                                                  (u64)f.dimp * 4ull, reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
+    }
     T3Params tp;
     tp.tile_leaf = ws.tile_leaf.p;
     tp.tile_first = ws.tile_first.p;
@@ -900,6 +988,84 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
     ZB_CUDA(cudaEventRecord(ws.ev1, s));
     ws.launched = true;
     ws.launches = 7;
+}
+
+// ---- flat-table projection on the third-generation skeleton (t3_body MODE 1) ----
+// tiles = (range of `range_rows` input rows, <= qcap planes); tile t = range t / npt, plane tile t % npt, so the plane
+// tiles of one row range are handed out back to back and meet the range's rows in L2.
+__global__ void pj_tiles_kernel(u32 nranges, u32 npt, u32 range_rows, u64 n, u32 H, u32 tq, long long* __restrict__ leaf_off,
+                                u32* __restrict__ leaf_len, u32* __restrict__ tile_leaf, u32* __restrict__ tile_first,
+                                u32* __restrict__ tile_count, u32* __restrict__ ntiles) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *ntiles = nranges * npt;
+    if (i < nranges) {
+        leaf_off[i] = (long long)i * range_rows;
+        const u64 left = n - (u64)i * range_rows;
+        leaf_len[i] = left < range_rows ? (u32)left : range_rows;
+    }
+    if (i < nranges * npt) {
+        const u32 r = i / npt, p = i - r * npt;
+        tile_leaf[i] = r;
+        tile_first[i] = p * tq;
+        tile_count[i] = H - p * tq < tq ? H - p * tq : tq;
+    }
+}
+bool project3_supported(int dimp) {
+    int nst, qcap;
+    return t3_config(dimp, &nst, &qcap);
+}
+// sign[n][Hp] = Hyperplane::point_is_above (lsh.rs:39-43) of every (row, plane); rows = [n][dimp] f32, 16-byte aligned.
+void project3(ScanWorkspace& ws, const float* d_rows, u64 n, const float* d_coef, const float* d_cst, int H, int dimp, u8* d_sign, int Hp,
+              cudaStream_t s) {
+    int nst = 0, qcap = 0;
+    if (!n || !H) return;
+    ZB_REQUIRE(t3_config(dimp, &nst, &qcap), ZB_ERR_STATE, "project3: rows of %d floats do not fit the tile kernel", dimp);
+    ZB_REQUIRE(n < (1ull << 31), ZB_ERR_INVALID, "project3: too many rows in one call");
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const u32 tq = (u32)qcap;
+    const u32 npt = ((u32)H + tq - 1) / tq;
+    // enough tiles for every team several times over, ranges a multiple of the 64-row stage
+    u32 range_rows = 2048;
+    while (range_rows > 64 && (n + range_rows - 1) / range_rows * npt < (u64)sms * T3_TEAMS * 8) range_rows >>= 1;
+    const u32 nranges = (u32)((n + range_rows - 1) / range_rows);
+    const u64 nt = (u64)nranges * npt;
+    ZB_REQUIRE(nt < (1ull << 31), ZB_ERR_INVALID, "project3: too many tiles");
+    ws.pj_off.ensure(nranges);
+    ws.leaf_count.ensure(nranges);   // leaf_len of the ranges
+    ws.tile_leaf.ensure(nt);
+    ws.tile_first.ensure(nt);
+    ws.tile_cnt.ensure(nt);
+    ws.counters.ensure(64);
+    ZB_CUDA(cudaMemsetAsync(ws.counters.p, 0, 64 * 4, s));
+    pj_tiles_kernel<<<(u32)((nt + 255) / 256), 256, 0, s>>>(nranges, npt, range_rows, n, (u32)H, tq, ws.pj_off.p, ws.leaf_count.p,
+                                                           ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, ws.counters.p + 2);
+    alignas(64) CUtensorMap tmap;
+    make_row_tile_map(&tmap, d_rows, n, dimp, T3_RB);
+    ForestView f{};
+    f.leaf_off = ws.pj_off.p;
+    f.leaf_len = ws.leaf_count.p;
+    f.dimp = dimp;
+    f.dim = dimp;
+    f.chunks = dimp / 16;
+    T3Params tp{};
+    tp.tile_leaf = ws.tile_leaf.p;
+    tp.tile_first = ws.tile_first.p;
+    tp.tile_count = ws.tile_cnt.p;
+    tp.ntiles = ws.counters.p + 2;
+    tp.tile_counter = ws.counters.p;
+    tp.queries = d_coef;
+    tp.stats = reinterpret_cast<u64*>(ws.counters.p + 4);
+    tp.nst = nst;
+    tp.qcap = qcap;
+    tp.pj_cst = d_cst;
+    tp.pj_sign = d_sign;
+    tp.pj_hp = Hp;
+    const size_t smem = t3_smem_bytes(nst, dimp, qcap);
+    ZB_CUDA(cudaFuncSetAttribute(project3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    project3_kernel<<<sms, T3_THREADS, smem, s>>>(tmap, f, tp);
+    ZB_CUDA(cudaGetLastError());
 }
 
 // =====================================================================================================

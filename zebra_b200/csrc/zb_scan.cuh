@@ -9,7 +9,9 @@ struct ScanWorkspace {
     DBuf<u32> leaf_count, leaf_start, leaf_cursor, tile_per_leaf, tile_start, order, tile_leaf, tile_first, tile_cnt;
     DBuf<u32> counters, tile_prog;
     DBuf<u64> gthr;
-    DBuf<u8> tmp;
+    DBuf<long long> pj_off;   // project3: first row of every row range
+    DBuf<u8> tmp, sort_tmp;
+    DBuf<u32> sort_key[2], sort_val[2];   // tile order: leaves sorted by cost
     bool launched = false;
     bool seq_launched = false;   // seq_tile_scan (scalar metrics) ran for the last batch
     u32 launches = 0;
@@ -49,6 +51,10 @@ bool tile_scan3_supported(int dimp, u32 top_k);
 void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u32 metric, const float* d_q, const double* d_q_rinv,
                 u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
                 u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s);
+// Flat-table projection on the same kernel skeleton: sign[n][Hp] = point_is_above of every (row, plane) (lsh.rs:39-43).
+bool project3_supported(int dimp);
+void project3(ScanWorkspace& ws, const float* d_rows, u64 n, const float* d_coef, const float* d_cst, int H, int dimp, u8* d_sign, int Hp,
+              cudaStream_t s);
 void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes, float* kernel_ms,
                      u32* tiles, u64* unique_bytes);
 

@@ -69,6 +69,11 @@ struct T3Params {
     u32 top_k;
     int nst;                // ring depth
     int qcap;               // query capacity of a tile (16, 8 or 4: what fits in shared memory next to a useful ring)
+    // projection mode (MODE == 1, zb_index_hash on flat tables): "leaves" are row ranges of the input, "queries" are planes
+    // (tp.queries = plane coefficients, order / v_q are not read: tile slot q is plane tile_first + q)
+    const float* pj_cst;    // [planes] constants
+    u8* pj_sign;            // [rows][pj_hp] point_is_above of every (row, plane)
+    int pj_hp;
 };
 
 // ---- shared memory layout of one team (byte offsets from the team's base) ----
@@ -119,21 +124,120 @@ __device__ __forceinline__ u64 t3_cos_bits_rinv(float ab_, double ra, double rb)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// One math warp's share of one tile: rows 16 * tw .. 16 * tw + 15 of every 64-row stage, against the QH queries of its
-// half-warp (half-warp h of every warp serves tile slots h * QH .. h * QH + QH - 1); then, per row block, the list
-// maintenance of the tile slots this warp owns (slot q is owned by warp q % 4).
+// One row block (64 rows x the tile's queries) of one math warp: consumes the block's nsl ring stages -- rows
+// 16 * tw .. 16 * tw + 15 of every stage against the QH queries of the thread's half-warp (half-warp h serves tile slots
+// h * QH .. h * QH + QH - 1) -- and folds the 16 accumulator lanes over the half-warp.  Returns, in sum[j], the finished
+// canonical sum of (row 16 * tw + t3_fold_row(t), tile slot h * QH + j).  METRIC 0: dot product, otherwise sum of (a - b)^2.
+// ------------------------------------------------------------------------------------------------------------------
+template <int METRIC, int QH>
+__device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout& lay, const int dimp, const int chunks, const int qcap,
+                                              const u32 S, const int tw, const int lane, u32& buf, u32& ph, float (&sum)[QH]) {
+    const int t = lane & 15, h = lane >> 4;
+    const int nsl = (chunks + T3_KC - 1) / T3_KC;
+    const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
+    const float* s_q = reinterpret_cast<const float*>(tb + lay.queries) + (u32)h * ((u32)(qcap / 2) * (u32)dimp + 16u) + t;
+    u64 acc[8][QH];  // acc[u][j] = packed lane partials of rows 2u, 2u+1 against query j
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < QH; ++j) acc[u][j] = 0ull;
+    for (int sl = 0; sl < nsl; ++sl) {
+        const int kcs = min(T3_KC, chunks - sl * T3_KC);
+        mbar_wait(bar_full + 8 * buf, ph);
+        const float* rp = reinterpret_cast<const float*>(tb + lay.stage + (size_t)buf * T3_STAGE_BYTES) +
+                          (tw * 16) * T3_SLICE_FLOATS + t;
+        const float* qp = s_q + sl * T3_SLICE_FLOATS;
+        auto chunk = [&](int c) {
+            u64 qq[QH];
+#pragma unroll
+            for (int j = 0; j < QH; ++j) {
+                const float q = qp[j * dimp + c * 16];
+                qq[j] = t3_pk2(q, q);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const u64 ra = t3_pk2(rp[(2 * u) * T3_SLICE_FLOATS + c * 16], rp[(2 * u + 1) * T3_SLICE_FLOATS + c * 16]);
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    if (METRIC == 0) acc[u][j] = t3_fma2(ra, qq[j], acc[u][j]);
+                    else {
+                        const u64 d = t3_sub2(ra, qq[j]);
+                        acc[u][j] = t3_fma2(d, d, acc[u][j]);
+                    }
+                }
+            }
+        };
+        if (kcs == T3_KC) {  // the common case, straight-line: the next chunk's shared-memory loads can be hoisted over this chunk's math
+#pragma unroll
+            for (int c = 0; c < T3_KC; ++c) chunk(c);
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < kcs; ++c) chunk(c);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
+        if (++buf == S) { buf = 0; ph ^= 1u; }
+    }
+    // ---- fold: canonical tree over the 16 lanes of the half-warp; a thread keeps half of its rows per step ----
+    float v8[8][QH];
+    {
+        const bool t3b = (t & 8) != 0;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int j = 0; j < QH; ++j) {
+                // rows a and a + 8 of the warp's 16: row r lives in acc[r / 2][j], half r % 2
+                float lo0, hi0, lo1, hi1;
+                t3_upk2(acc[a >> 1][j], lo0, hi0);
+                t3_upk2(acc[(a + 8) >> 1][j], lo1, hi1);
+                const float va = (a & 1) ? hi0 : lo0, vb = (a & 1) ? hi1 : lo1;
+                const float mine = t3b ? vb : va, send = t3b ? va : vb;
+                v8[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 8));  // lane i + lane i + 8
+            }
+    }
+    float v4[4][QH];
+    {
+        const bool t2b = (t & 4) != 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < QH; ++j) {
+                const float mine = t2b ? v8[a + 4][j] : v8[a][j], send = t2b ? v8[a][j] : v8[a + 4][j];
+                v4[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 4));  // x[i] + x[i + 4]
+            }
+    }
+    float v2[2][QH];
+    {
+        const bool t0b = (t & 1) != 0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int j = 0; j < QH; ++j) {
+                const float mine = t0b ? v4[a + 2][j] : v4[a][j], send = t0b ? v4[a][j] : v4[a + 2][j];
+                v2[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 1));  // r0 + r1, r2 + r3
+            }
+    }
+    {
+        const bool t1b = (t & 2) != 0;
+#pragma unroll
+        for (int j = 0; j < QH; ++j) {
+            const float mine = t1b ? v2[1][j] : v2[0][j], send = t1b ? v2[0][j] : v2[1][j];
+            sum[j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 2));  // (r0 + r1) + (r2 + r3)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Scan mode: one math warp's share of one tile; per row block the sums are transposed through shared memory and the warp
+// maintains the lists of the tile slots it owns (slot q is owned by warp q % 4).
 // ------------------------------------------------------------------------------------------------------------------
 template <int METRIC, int QH>
 __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& lay, const ForestView& f, const T3Params& tp,
                                              const T3TileInfo& inf, const int tw, const int lane, u32& buf, u32& ph, u32& blk,
                                              const int team, u64 (&thr)[4]) {
     const int t = lane & 15, h = lane >> 4;
-    const int dimp = f.dimp, chunks = f.chunks;
-    const int nsl = (chunks + T3_KC - 1) / T3_KC;
     const u32 S = (u32)tp.nst, L = inf.L, nqt = inf.nqt;
     const u32 nblocks = (L + T3_RB - 1) / T3_RB;
-    const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
-    const float* s_q = reinterpret_cast<const float*>(tb + lay.queries) + (u32)h * ((u32)(tp.qcap / 2) * (u32)dimp + 16u) + t;
     float* s_sums = reinterpret_cast<float*>(tb + lay.sums);
     u32* s_lists = reinterpret_cast<u32*>(tb + lay.lists);
     const u32* s_meta = reinterpret_cast<const u32*>(tb + lay.meta);
@@ -142,50 +246,21 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
     for (u32 b = 0; b < nblocks; ++b, ++blk) {
         const u32 nrows = min((u32)T3_RB, L - b * T3_RB);
         const u32 base = (u32)(inf.moff + (long long)b * T3_RB);  // position of row 0 of the block
-        u64 acc[8][QH];  // acc[u][j] = packed lane partials of rows 2u, 2u+1 against query j
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-#pragma unroll
-            for (int j = 0; j < QH; ++j) acc[u][j] = 0ull;
-        for (int sl = 0; sl < nsl; ++sl) {
-            const int kcs = min(T3_KC, chunks - sl * T3_KC);
-            mbar_wait(bar_full + 8 * buf, ph);
-            const float* rp = reinterpret_cast<const float*>(tb + lay.stage + (size_t)buf * T3_STAGE_BYTES) +
-                              (tw * 16) * T3_SLICE_FLOATS + t;
-            const float* qp = s_q + sl * T3_SLICE_FLOATS;
-            auto chunk = [&](int c) {
-                u64 qq[QH];
-#pragma unroll
-                for (int j = 0; j < QH; ++j) {
-                    const float q = qp[j * dimp + c * 16];
-                    qq[j] = t3_pk2(q, q);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const u64 ra = t3_pk2(rp[(2 * u) * T3_SLICE_FLOATS + c * 16], rp[(2 * u + 1) * T3_SLICE_FLOATS + c * 16]);
-#pragma unroll
-                    for (int j = 0; j < QH; ++j) {
-                        if (METRIC == 0) acc[u][j] = t3_fma2(ra, qq[j], acc[u][j]);
-                        else {
-                            const u64 d = t3_sub2(ra, qq[j]);
-                            acc[u][j] = t3_fma2(d, d, acc[u][j]);
-                        }
-                    }
-                }
-            };
-            if (kcs == T3_KC) {  // the common case, straight-line: the next chunk's shared-memory loads can be hoisted over this chunk's math
-#pragma unroll
-                for (int c = 0; c < T3_KC; ++c) chunk(c);
-            } else {
-#pragma unroll 1
-                for (int c = 0; c < kcs; ++c) chunk(c);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
-            if (++buf == S) { buf = 0; ph ^= 1u; }
-        }
-        // ---- what the epilogue needs from global memory, requested before the fold hides the latency ----
         const u32 r_lo = (u32)lane, r_hi = (u32)lane + 32u;  // the two rows of the block this lane finishes in the epilogue
+        // what the epilogue reads from global memory is pulled towards the SM while the block is being scored
+        if (METRIC == 0) {
+            t3_prefetch_l1(tp.bm_rinv + base + r_lo);
+            t3_prefetch_l1(tp.bm_rinv + base + r_hi);
+        }
+        if (lane < 3) t3_prefetch_l1(tp.bm_tomb + (base >> 5) + lane);
+        float sum[QH];
+        t3_block_sums<METRIC, QH>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, sum);
+        {
+            float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * 16 + myrow;
+#pragma unroll
+            for (int j = 0; j < QH; ++j) dst[(size_t)(h * QH + j) * T3_RB] = sum[j];
+        }
+        // ---- what the epilogue needs from global memory (prefetched above; the team barrier below hides the rest) ----
         double rinv_lo = 0.0, rinv_hi = 0.0;
         if (METRIC == 0) {
             if (r_lo < nrows) rinv_lo = tp.bm_rinv[base + r_lo];
@@ -198,55 +273,6 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
         for (int e = 0; e < 4; ++e) {
             const u32 q = (u32)tw + 4u * e;
             gbound[e] = q < nqt ? t3_ldcg_u64(tp.gthr + s_meta[2 * tp.qcap + q]) : ZB_SENTINEL;
-        }
-        // ---- fold: canonical tree over the 16 lanes of the half-warp; a thread keeps half of its rows per step ----
-        float v8[8][QH];
-        {
-            const bool t3b = (t & 8) != 0;
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int j = 0; j < QH; ++j) {
-                    // rows a and a + 8 of the warp's 16: row r lives in acc[r / 2][j], half r % 2
-                    float lo0, hi0, lo1, hi1;
-                    t3_upk2(acc[a >> 1][j], lo0, hi0);
-                    t3_upk2(acc[(a + 8) >> 1][j], lo1, hi1);
-                    const float va = (a & 1) ? hi0 : lo0, vb = (a & 1) ? hi1 : lo1;
-                    const float mine = t3b ? vb : va, send = t3b ? va : vb;
-                    v8[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 8));  // lane i + lane i + 8
-                }
-        }
-        float v4[4][QH];
-        {
-            const bool t2b = (t & 4) != 0;
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int j = 0; j < QH; ++j) {
-                    const float mine = t2b ? v8[a + 4][j] : v8[a][j], send = t2b ? v8[a][j] : v8[a + 4][j];
-                    v4[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 4));  // x[i] + x[i + 4]
-                }
-        }
-        float v2[2][QH];
-        {
-            const bool t0b = (t & 1) != 0;
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int j = 0; j < QH; ++j) {
-                    const float mine = t0b ? v4[a + 2][j] : v4[a][j], send = t0b ? v4[a][j] : v4[a + 2][j];
-                    v2[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 1));  // r0 + r1, r2 + r3
-                }
-        }
-        {
-            const bool t1b = (t & 2) != 0;
-            float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * 16 + myrow;
-#pragma unroll
-            for (int j = 0; j < QH; ++j) {
-                const float mine = t1b ? v2[1][j] : v2[0][j], send = t1b ? v2[0][j] : v2[1][j];
-                const float sum = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 2));  // (r0 + r1) + (r2 + r3)
-                dst[(size_t)(h * QH + j) * T3_RB] = sum;
-            }
         }
         t3_team_sync(team);  // the block's sums are complete; the previous use of this buffer was consumed two blocks ago
         // ---- epilogue: this warp finishes the tile slots it owns (q = tw, tw + 4, ...): keys, filter, list insertion ----
@@ -310,10 +336,42 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Projection mode (flat-table hashing, Hyperplane::point_is_above of lsh.rs:39-43 for every (row, plane)): the tile's
+// "queries" are planes tile_first .. tile_first + nqt - 1, its "leaf" is a range of input rows; the thread that holds a
+// finished dot product tests its sign and stores it.  No lists, no transposition.
+// ------------------------------------------------------------------------------------------------------------------
+template <int QH>
+__device__ __forceinline__ void t3_project_tile(unsigned char* tb, const T3Layout& lay, const ForestView& f, const T3Params& tp,
+                                                const T3TileInfo& inf, const int tw, const int lane, u32& buf, u32& ph) {
+    const int t = lane & 15, h = lane >> 4;
+    const u32 S = (u32)tp.nst, L = inf.L, nqt = inf.nqt;
+    const u32 nblocks = (L + T3_RB - 1) / T3_RB;
+    const int myrow = tw * 16 + t3_fold_row(t);
+    float cst[QH];
+#pragma unroll
+    for (int j = 0; j < QH; ++j) {
+        const u32 q = (u32)(h * QH + j);
+        cst[j] = q < nqt ? tp.pj_cst[inf.first + q] : 0.0f;
+    }
+    for (u32 b = 0; b < nblocks; ++b) {
+        const u32 nrows = min((u32)T3_RB, L - b * T3_RB);
+        float sum[QH];
+        t3_block_sums<0, QH>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, sum);
+        if ((u32)myrow < nrows) {
+            u8* dst = tp.pj_sign + (size_t)(inf.moff + (long long)b * T3_RB + myrow) * tp.pj_hp + inf.first + h * QH;
+#pragma unroll
+            for (int j = 0; j < QH; ++j)
+                if ((u32)(h * QH + j) < nqt) dst[j] = t3_above_from_dot(sum[j], cst[j]) ? 1 : 0;
+        }
+    }
+}
+
 // Two teams per CTA, each = 4 math warps (one per SM sub-partition) + 1 producer warp, each streaming its own tiles:
 // the two math warps that share a sub-partition belong to different tiles, so one warp's fold / epilogue / tile change
 // overlaps the other's FP32 loop, and a bandwidth-bound tile (few queries) shares the SM with a pipe-bound one.
-template <int METRIC>
+// MODE 0: leaf scan (METRIC 0 cosine, 1 L2 squared, 2 L2).  MODE 1: flat-table projection (METRIC ignored).
+template <int METRIC, int MODE>
 __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, const T3Params& tp, unsigned char* smem) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dimp = f.dimp, chunks = f.chunks;
@@ -386,9 +444,11 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
             {  // address loads batched (independent chains), then the copies
                 u32 qi[T3_QT];
 #pragma unroll
-                for (int j = 0; j < T3_QT; ++j) qi[j] = (u32)j < nqt ? tp.order[first + j] : 0u;
+                for (int j = 0; j < T3_QT; ++j) qi[j] = (u32)j < nqt ? (MODE == 1 ? first + (u32)j : tp.order[first + j]) : 0u;
+                if (MODE == 0) {
 #pragma unroll
-                for (int j = 0; j < T3_QT; ++j) qi[j] = (u32)j < nqt ? tp.v_q[qi[j]] : 0u;
+                    for (int j = 0; j < T3_QT; ++j) qi[j] = (u32)j < nqt ? tp.v_q[qi[j]] : 0u;
+                }
 #pragma unroll
                 for (int j = 0; j < T3_QT; ++j)
                     if ((u32)j < nqt)
@@ -417,6 +477,17 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
         const T3TileInfo inf = s_info[it & 1];
         if (inf.tile == T3_NOTILE) break;
         const u32 nqt = inf.nqt;
+        if (MODE == 1) {
+            mbar_wait(bar_qfull, it & 1);
+            switch (inf.qh) {
+                case 2: t3_project_tile<2>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 4: t3_project_tile<4>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 6: t3_project_tile<6>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                default: t3_project_tile<8>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+            }
+            if (lane == 0) mbar_arrive(bar_qempty);
+            continue;
+        }
         // the tile slots this warp owns: visit, n', query -> shared memory (read back as broadcasts in the epilogue), empty lists
         if (lane < 4) {
             const u32 q = (u32)tw + 4u * lane;

@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="end-to-end leg without zb_index_search_prefetch (uploads serialised)")
     ap.add_argument("--max-oracle-gb", type=float, default=40.0,
                     help="skip the oracle legs (parity sample, cpu_baseline) when the rows would not fit this much host memory")
     ap.add_argument("--set", action="append", default=[], help="library knob key=value (ablations)")
@@ -72,11 +73,22 @@ def parse():
                          "H = K * trees planes per row, dense projection kernel) instead of the built forest")
     ap.add_argument("--delete-frac", type=float, default=0.0,
                     help="workload query: tombstone this fraction of the rows (seeded selection) before the queries, BASELINE config 5")
-    ap.add_argument("--preset", type=int, default=0, choices=[0, 3, 5],
-                    help="BASELINE.json configs as STRONG-scaling runs: 3 = 10M x 768 cosine over the GPUs, 10k top-10 queries; "
-                         "5 = 100M x 384 L2 squared, 10 %% tombstones, 100k top-100 queries (sized for 8 GPUs)")
+    ap.add_argument("--preset", type=int, default=0, choices=[0, 3, 4, 5, 6],
+                    help="BASELINE.json configs at their stated sizes, as STRONG-scaling runs: 3 = 10M x 768 cosine over the GPUs, "
+                         "10k top-10 queries; 4 = bucket keys of 100M x 768 rows streamed through the GPUs in 2.5M-row chunks "
+                         "(workload hash; --flat-bits / --trees choose the tables); 5 = 100M x 384 L2 squared, 10 %% tombstones, "
+                         "100k top-100 queries (sized for 8 GPUs); 6 = the north-star target size: 100M x 768 L2, 10k top-10 "
+                         "queries (sized for 8 GPUs; 3 trees: a bucket-sharded store holds one copy of the rows per tree)")
     a = ap.parse_args()
     a.scaling = "weak"
+    a.total_hash_rows = 0
+    if a.preset == 4:
+        a.workload, a.dim, a.rows, a.hash_rows, a.scaling = "hash", 768, 1_000_000, 2_500_000, "strong"
+        a.total_hash_rows = 100_000_000
+        a.steps = max(1, a.total_hash_rows // (a.gpus * a.hash_rows))
+    elif a.preset == 6:
+        a.metric, a.dim, a.topk, a.trees = "l2", 768, 10, 3
+        a.rows, a.queries, a.scaling = 100_000_000 // a.gpus, max(1, 10_000 // a.gpus), "strong"
     if a.preset == 3:
         a.metric, a.dim, a.topk = "cosine", 768, 10
         a.rows, a.queries, a.scaling = 10_000_000 // a.gpus, max(1, 10_000 // a.gpus), "strong"
@@ -341,7 +353,11 @@ def run_ours(a):
     def step_device(b):
         ix.search_slice_device(nq, d_q[b].data_ptr(), a.topk, d_ord.data_ptr(), d_bits.data_ptr(), d_cnt.data_ptr())
 
-    def step_e2e(b):
+    def step_e2e(b, nxt=None):
+        # double buffering through the public API: the upload of the next batch (zb_index_search_prefetch, pinned host memory)
+        # overlaps this batch's scan; every batch still crosses PCIe once, inside the timed region
+        if nxt is not None and not a.no_prefetch:
+            ix.search_prefetch_ptr(ns, h_q[nxt].data_ptr())
         ix.search_slice_ptr(nq, h_q[b].data_ptr(), a.topk, h_ord.data_ptr(), h_bits.data_ptr(), h_cnt.data_ptr())
 
     # ---- device-resident leg: `value` ----
@@ -382,7 +398,7 @@ def run_ours(a):
     barrier()
     t_e = time.perf_counter()
     for s in range(a.steps):
-        step_e2e(a.warmup + s)
+        step_e2e(a.warmup + s, a.warmup + s + 1 if s + 1 < a.steps else None)
     barrier()
     e2e_ms = (time.perf_counter() - t_e) * 1e3
     clocks = sampler.stop()
@@ -473,7 +489,8 @@ def run_ours(a):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / a.steps, "matches_device_leg": same,
-                    "api": "zb_index_search_slice (host buffers)" if G > 1 else "zb_index_search_batch (host buffers)"},
+                    "api": ("zb_index_search_slice (host buffers)" if G > 1 else "zb_index_search_batch (host buffers)")
+                           + ("" if a.no_prefetch else " + zb_index_search_prefetch of the next batch (double-buffered upload)")},
             "gpu_launches": int(agg["launches"]), "clocks": clocks,
             "phases_ms_per_step": {k: agg[k] / a.steps for k in ("plan_ms", "scan_ms", "tile_ms", "select_ms", "merge_ms")},
             "per_rank_plan_scan_tile_select_merge_ms_pairs_tiles": per_rank,
@@ -561,32 +578,49 @@ def run_aux(a):
             ix.add_device(d_rows.data_ptr(), a.rows)
         del d_rows
         n = a.hash_rows
-        d_x = torch.empty((nb, n, a.dim), dtype=torch.float32, device=dev)
-        for b in range(nb):
-            z.synth_fill_device(local, d_x[b].data_ptr(), a.rows + (b * G + rank) * n, 1, n, a.dim, a.seed, 1)
+        # every step hashes a FRESH chunk (n rows x 4 dim bytes >> L2); the chunks live in a ring of buffers that is refilled
+        # on the device between the timed sections, so 100M x 768 rows stream through one GPU without 307 GB of HBM
+        ring = min(nb, max(2, int(24e9 // (n * a.dim * 4))))
+        d_x = torch.empty((ring, n, a.dim), dtype=torch.float32, device=dev)
+
+        def fill(b):
+            z.synth_fill_device(local, d_x[b % ring].data_ptr(), a.rows + (b * G + rank) * n, 1, n, a.dim, a.seed, 1)
+
+        for b in range(min(ring, nb)):
+            fill(b)
         d_keys = torch.empty((n, a.trees), dtype=torch.int64, device=dev)
         d_depth = torch.empty((n, a.trees), dtype=torch.int32, device=dev)
         d_leaf = torch.empty((n, a.trees), dtype=torch.int32, device=dev)
-        h_x = d_x[nb - 1].cpu().pin_memory()
-        h_keys = np.empty((n, a.trees), dtype=np.uint64)
         stream = torch.cuda.ExternalStream(ix.stream_ptr(), device=dev)
         sampler.start()
         for b in range(a.warmup):
-            ix.hash_device(n, d_x[b].data_ptr(), d_keys.data_ptr(), d_depth.data_ptr(), d_leaf.data_ptr())
+            ix.hash_device(n, d_x[b % ring].data_ptr(), d_keys.data_ptr(), d_depth.data_ptr(), d_leaf.data_ptr())
         barrier()
+        dev_ms = 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for s in range(a.steps):
-            ix.hash_device(n, d_x[a.warmup + s].data_ptr(), d_keys.data_ptr(), d_depth.data_ptr(), d_leaf.data_ptr())
-        e1.record(stream)
-        barrier()
-        dev_ms = e0.elapsed_time(e1)
+        s = 0
+        while s < a.steps:          # timed in sections of at most `ring` steps; the refill between sections is not timed
+            sec = min(ring, a.steps - s)
+            for b in range(a.warmup + s, a.warmup + s + sec):
+                if b >= ring:
+                    fill(b)
+            barrier()
+            e0.record(stream)
+            for b in range(a.warmup + s, a.warmup + s + sec):
+                ix.hash_device(n, d_x[b % ring].data_ptr(), d_keys.data_ptr(), d_depth.data_ptr(), d_leaf.data_ptr())
+            e1.record(stream)
+            barrier()
+            dev_ms += e0.elapsed_time(e1)
+            s += sec
+        h_x = d_x[(nb - 1) % ring].cpu().pin_memory()
+        h_keys = np.empty((n, a.trees), dtype=np.uint64)
         barrier()
         t_e = time.perf_counter()
-        for s in range(a.steps):   # end to end: host rows in, host keys out (zb_index_hash stages through the device)
+        e2e_steps = min(a.steps, 5)
+        for s in range(e2e_steps):   # end to end: host rows in, host keys out (zb_index_hash stages through the device)
             hk, hd, hl = ix.hash(h_x.numpy())
         barrier()
-        e2e_ms = (time.perf_counter() - t_e) * 1e3
+        e2e_ms = (time.perf_counter() - t_e) * 1e3 * a.steps / e2e_steps
         clocks = sampler.stop()
         depth_sum = float(d_depth.sum().item())           # plane rows streamed = sum of path lengths
         units, unit_name = n * G, "rows/s"
@@ -597,7 +631,8 @@ def run_aux(a):
         h2d, d2h = n * a.dim * 4, n * a.trees * 16
         if a.flat_bits:
             H = a.flat_bits * a.trees
-            kernel = "project_flat_kernel + pack_flat_keys_kernel (zb_kernels.cu): dense rows x planes projection, ballot-packed keys"
+            kernel = ("project3_kernel (zb_scan.cu: t3_body MODE 1, rows staged by 2-D TMA, planes resident in shared memory) + "
+                      "pack_flat_keys_kernel (zb_kernels.cu, __ballot_sync)")
             extra.update({"flat_bits": a.flat_bits, "planes_per_row": H,
                           "fp32_tflops": 2.0 * a.dim * H * n * a.steps / (dev_ms / 1e3) / 1e12,
                           "fp32_peak_tflops_measured": 72.0, "fp32_peak_source": "profiles/r01_fp32_pipe.txt (FFMA, 128 lanes/clk/SM)"})
@@ -724,11 +759,16 @@ def run_aux(a):
                 "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{a.workload}: {a.dim}-dim f32 rows, forest of {a.trees} trees with leaves < {a.max_node_size} "
-                                       f"over {a.rows * (G if a.workload == 'build' else 1)} rows", **extra,
+                                       f"over {a.rows * (G if a.workload == 'build' else 1)} rows"
+                                       + (f"; {units * a.steps} rows hashed in all (BASELINE config 4)" if a.workload == "hash" else ""), **extra,
                            "data": "Philox clustered, generated on device", "l2_policy": "every step streams fresh rows (>= 3 GB >> 126 MB L2)"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src, "kernel": kernel,
                              "algorithmic_bytes_per_step": alg_bytes,
+                             "fp32": ({"achieved_tflops": extra["fp32_tflops"] / G, "peak_tflops": 72.0,
+                                       "frac": extra["fp32_tflops"] / G / 72.0,
+                                       "binding": "fp32 FMA issue" if extra["planes_per_row"] > 20 else "hbm"}
+                                      if "fp32_tflops" in extra else None),
                              "note": "whole-step time (the step is dominated by this kernel); hash: the descent also streams one "
                                      "plane row per level from L2 (plane_bytes_from_l2_per_step), which is what bounds it"},
                 "cpu_baseline": cpu,

@@ -155,6 +155,13 @@ int zb_index_search_slice(zb_index* index, uint64_t nq_total, const float* slice
                           uint64_t* out_ordinals, uint64_t* out_dist_bits, uint32_t* out_counts);
 int zb_index_search_slice_device(zb_index* index, uint64_t nq_total, const float* d_slice_queries, uint64_t top_k,
                                  uint64_t* d_out_ordinals, uint64_t* d_out_dist_bits, uint32_t* d_out_counts);
+/* Double buffering for a caller that streams batches (a server looping over Database::query_vectors, core.rs:290-313):
+ * starts the host-to-device copy of the `n` query rows at `queries` on the index's copy stream and returns at once.  The next
+ * zb_index_search_batch / zb_index_search_slice call that is handed the SAME pointer (and at most `n` rows) finds its queries
+ * in HBM, so the upload of batch i + 1 overlaps the scan of batch i.  Two uploads may be pending; the buffer must stay
+ * unchanged (and, for the copy to be asynchronous, pinned) until that search call returns.  Purely an optimisation: a search
+ * call whose pointer was not announced uploads its queries itself, and results never depend on it. */
+int zb_index_search_prefetch(zb_index* index, uint64_t n, const float* queries);
 
 /* Bucket keys: the root-to-leaf sign path of Hyperplane::point_is_above decisions (lsh.rs:39-43 along
  * :350-366), MSB = root, 1 = above/right, for every (row, tree): out_keys/out_depths/out_leaves are

@@ -44,6 +44,8 @@ def main():
         ix.comm_init(uid[0])
         if mns == 5:
             ix.set_param("visit_slots", 4)   # force the (collective) grow-and-replan path
+        if dim == 768:
+            ix.set_param("bm_stage_mb", 1)   # the bucket-major store is exchanged in several leaf groups per tree
         ix.add(rows)
         orc = zo.OracleIndex(dim, mid, mns, trees, seed=7) if rank == 0 else None
         if rank == 0:

@@ -89,6 +89,7 @@ static inline unsigned __ballot_sync(unsigned, bool p) {
     return r;
 }
 static inline int __ffs(unsigned m) { return m ? __builtin_ctz(m) + 1 : 0; }
+static inline int __popc(unsigned m) { return __builtin_popcount(m); }
 template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
 static inline u32 atomicAdd(u32* p, u32 v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline u64 atomicAdd(u64* p, u64 v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -181,7 +182,10 @@ static inline void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
 
 namespace zb {
 #define T3_EMU_STAGE_ROWS 64
-#define T3_EMU_SLICE 48
+#ifndef T3_KC
+#define T3_KC 3
+#endif
+#define T3_EMU_SLICE (T3_KC * 16)
 static inline void t3_tma_2d_g2s(u32 dst, const T3Map& map, int c0, long long row, u32 bar) {
     float* d = reinterpret_cast<float*>(emu_smem + dst);
     const T3Map m = map;
@@ -228,11 +232,12 @@ static inline u64 l2_bits(float s) { return t3_dbits(sqrt((double)s)); }
 }  // namespace zb
 
 #include "../zebra_b200/csrc/zb_scan3_kernel.cuh"
+static_assert(T3_EMU_SLICE == T3_SLICE_FLOATS && T3_EMU_STAGE_ROWS == T3_RB, "the emulated TMA box is the kernel's stage");
 
 // Tiles are given directly (what ts_count / ts_scatter / ts_filltiles build on the device).  The bucket-major store is
 // addressed by position: members = identity is supplied by the caller together with ord[position].
 extern "C" __attribute__((visibility("default"))) int emu_scan3(
-    int metric, int blocks, int dim, int nst, int qcap, uint32_t top_k, uint64_t positions, const float* bm_rows_padded,
+    int metric, int blocks, int dim, int nst, int qcap, int kr, uint32_t top_k, uint64_t positions, const float* bm_rows_padded,
     const double* bm_rinv, const uint32_t* bm_tomb, const uint64_t* ord, const uint32_t* members, const long long* leaf_off,
     const uint32_t* leaf_len, uint32_t ntiles, const uint32_t* tile_leaf, const uint32_t* tile_first, const uint32_t* tile_count,
     const uint32_t* order, const uint32_t* v_np, const uint32_t* v_q, const uint32_t* v_ent_off, const float* queries_padded,
@@ -245,10 +250,11 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
     tp.tile_leaf = tile_leaf; tp.tile_first = tile_first; tp.tile_count = tile_count; tp.ntiles = &ntiles; tp.tile_counter = &counter;
     tp.order = order; tp.v_np = v_np; tp.v_q = v_q; tp.v_ent_off = v_ent_off; tp.entries = reinterpret_cast<zb::Entry*>(entries);
     tp.queries = queries_padded; tp.q_rinv = q_rinv; tp.bm_rinv = bm_rinv; tp.bm_tomb = bm_tomb;
-    tp.stats = reinterpret_cast<zb::u64*>(stats3); tp.gthr = reinterpret_cast<zb::u64*>(gthr); tp.top_k = top_k; tp.nst = nst; tp.qcap = qcap;
+    tp.stats = reinterpret_cast<zb::u64*>(stats3); tp.gthr = reinterpret_cast<zb::u64*>(gthr); tp.top_k = top_k; tp.nst = nst; tp.qcap = qcap; tp.kr = kr;
     tp.pj_cst = nullptr; tp.pj_sign = nullptr; tp.pj_hp = 0;
     zb::T3Map map{bm_rows_padded, positions, f.dimp};
-    const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap);
+    if (kr != 1 && kr != T3_KR_MAX) return -1;
+    const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap, kr);
     std::vector<unsigned char> smem((size_t)T3_TEAMS * lay.total + 1024);
     emu_warps.clear();
     for (int i = 0; i < T3_THREADS / 32; ++i) emu_warps.emplace_back(new WarpBox());
@@ -268,9 +274,15 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
         for (unsigned t = 0; t < T3_THREADS; ++t)
             th.emplace_back([&, t] {
                 emu_threadIdx = Dim3{t, 0, 0};
-                if (metric == 0) zb::t3_body<0, 0>(map, f, tp, emu_smem);
-                else if (metric == 1) zb::t3_body<1, 0>(map, f, tp, emu_smem);
-                else zb::t3_body<2, 0>(map, f, tp, emu_smem);
+                if (kr == 1) {
+                    if (metric == 0) zb::t3_body<0, 0, 1>(map, f, tp, emu_smem);
+                    else if (metric == 1) zb::t3_body<1, 0, 1>(map, f, tp, emu_smem);
+                    else zb::t3_body<2, 0, 1>(map, f, tp, emu_smem);
+                } else {
+                    if (metric == 0) zb::t3_body<0, 0, T3_KR_MAX>(map, f, tp, emu_smem);
+                    else if (metric == 1) zb::t3_body<1, 0, T3_KR_MAX>(map, f, tp, emu_smem);
+                    else zb::t3_body<2, 0, T3_KR_MAX>(map, f, tp, emu_smem);
+                }
             });
         for (auto& x : th) x.join();
         dma.finish();
@@ -300,10 +312,10 @@ extern "C" __attribute__((visibility("default"))) int emu_project3(int blocks, i
     zb::T3Params tp;
     memset(&tp, 0, sizeof tp);
     tp.tile_leaf = tile_leaf.data(); tp.tile_first = tile_first.data(); tp.tile_count = tile_count.data(); tp.ntiles = &ntiles;
-    tp.tile_counter = &counter; tp.queries = coef_padded; tp.stats = reinterpret_cast<zb::u64*>(stats3); tp.nst = nst; tp.qcap = qcap;
+    tp.tile_counter = &counter; tp.queries = coef_padded; tp.stats = reinterpret_cast<zb::u64*>(stats3); tp.nst = nst; tp.qcap = qcap; tp.kr = 1;
     tp.pj_cst = cst; tp.pj_sign = sign; tp.pj_hp = Hp;
     zb::T3Map map{rows_padded, n, f.dimp};
-    const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap);
+    const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap, 1);
     std::vector<unsigned char> smem((size_t)T3_TEAMS * lay.total + 1024);
     emu_warps.clear();
     for (int i = 0; i < T3_THREADS / 32; ++i) emu_warps.emplace_back(new WarpBox());
@@ -320,7 +332,7 @@ extern "C" __attribute__((visibility("default"))) int emu_project3(int blocks, i
         for (unsigned t = 0; t < T3_THREADS; ++t)
             th.emplace_back([&, t] {
                 emu_threadIdx = Dim3{t, 0, 0};
-                zb::t3_body<0, 1>(map, f, tp, emu_smem);
+                zb::t3_body<0, 1, 1>(map, f, tp, emu_smem);
             });
         for (auto& x : th) x.join();
         dma.finish();
@@ -329,6 +341,6 @@ extern "C" __attribute__((visibility("default"))) int emu_project3(int blocks, i
 }
 
 extern "C" __attribute__((visibility("default"))) void emu_scan3_layout(int nst, int dim, int qcap, uint32_t* out8) {
-    const zb::T3Layout l = zb::t3_layout(nst, (dim + 15) / 16 * 16, qcap);
+    const zb::T3Layout l = zb::t3_layout(nst, (dim + 15) / 16 * 16, qcap, 1);
     out8[0] = l.stage; out8[1] = l.queries; out8[2] = l.sums; out8[3] = l.lists; out8[4] = l.meta; out8[5] = l.info; out8[6] = l.bars; out8[7] = l.total;
 }

@@ -81,6 +81,31 @@ def test_tile_kernel_on_headline_shapes(dim, mid, mname):
         assert ix.stats()["last_tile_pairs"] > 0
 
 
+@pytest.mark.parametrize("dim,mid,mname", [(384, zo.L2SQ, "L2SquaredDistance"), (768, zo.COSINE, "CosineDistance"),
+                                           (100, zo.L2, "L2Distance")])
+def test_fused_kernel_with_lists_of_up_to_128_entries(dim, mid, mname):
+    """BASELINE config 5 asks for top-100: n' in 33..128 stays in the fused kernel (four list entries per lane, KR = 4);
+    above 128 the visits go to the keys-only tile scan + warp select.  10 % tombstones, exact duplicates."""
+    z = zb()
+    rng = np.random.default_rng(dim * 3 + mid)
+    n, mns, trees = 60_000, 2048, 3
+    rows = clustered(rng, n, dim)
+    rows[30_000:30_300] = rows[:300]
+    orc = zo.OracleIndex(dim, mid, mns, trees, seed=11)
+    orc.add(rows)
+    ix = z.LSHIndex(dim, z.LSHIndexOptions(mns, trees), getattr(z, mname)(), seed=11)
+    ix.add(rows)
+    dead = rng.choice(n, n // 10, replace=False).astype(np.uint64)
+    assert np.array_equal(ix.remove_ordinals(dead), orc.remove(dead))
+    queries = make_queries(rng, rows, 500)
+    for k in (33, 100, 128):
+        assert_search_equal(ix, orc, queries, k)
+        st = ix.stats()
+        assert st["last_tile_pairs"] > 0.99 * st["last_pairs"], (k, st)
+    assert_search_equal(ix, orc, queries[:100], 129)
+    assert ix.stats()["last_tile_pairs"] == 0
+
+
 def test_tile_kernel_crowded_leaves():
     """Far more queries than a tile holds on every leaf (hundreds per leaf): many sibling tiles of one leaf, the shared
     per-query bound (k distinct candidates already found elsewhere) and the dedup across trees all at work."""

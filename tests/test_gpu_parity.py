@@ -369,3 +369,34 @@ def test_sharded_two_gpus_equals_oracle():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(": ok") == 17 and "MISMATCH" not in out.stdout
+
+
+# ------------------------------------------------------------------------------------------ double-buffered uploads
+@pytest.mark.parametrize("dim", [100, 384])
+def test_prefetched_batches_give_the_same_answers(dim):
+    """zb_index_search_prefetch only moves the upload of an announced batch ahead of the search call that consumes it:
+    announced, unannounced, stale and twice-announced batches all return what the oracle returns (lsh.rs:544-565)."""
+    rng = np.random.default_rng(77 + dim)
+    rows = clustered(rng, 6000, dim)
+    ix = zb().LSHIndex(dim, zb().LSHIndexOptions(256, 3), metric_obj("L2Distance"), seed=5)
+    orc = zo.OracleIndex(dim, zo.L2, 256, 3, seed=5)
+    ix.add(rows); orc.add(rows)
+    batches = [np.ascontiguousarray(make_queries(rng, rows, 96 + 8 * i)) for i in range(4)]
+    ix.search_prefetch_ptr(batches[0].shape[0], batches[0].ctypes.data)
+    for i, q in enumerate(batches):
+        if i + 1 < len(batches):                       # announce the next batch, then consume this one
+            nxt = batches[i + 1]
+            ix.search_prefetch_ptr(nxt.shape[0], nxt.ctypes.data)
+        assert_search_equal(ix, orc, q, 10)
+    # an announcement nobody consumes, a third one that displaces the oldest, and a search of something else entirely
+    ix.search_prefetch_ptr(batches[0].shape[0], batches[0].ctypes.data)
+    ix.search_prefetch_ptr(batches[1].shape[0], batches[1].ctypes.data)
+    ix.search_prefetch_ptr(batches[2].shape[0], batches[2].ctypes.data)
+    other = np.ascontiguousarray(make_queries(rng, rows, 50))
+    assert_search_equal(ix, orc, other, 10)
+    assert_search_equal(ix, orc, batches[2], 10)
+    assert_search_equal(ix, orc, batches[1], 10)
+    # fewer rows announced than searched: the call uploads by itself
+    ix.search_prefetch_ptr(10, batches[3].ctypes.data)
+    assert_search_equal(ix, orc, batches[3], 10)
+    ix.close()

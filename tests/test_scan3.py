@@ -6,7 +6,7 @@ tree_result (/root/reference/src/database/index/lsh.rs:299-331) with Metric::dis
 What this covers without a GPU: the ring protocol (full / empty / tile-info / query barriers: a missing wait reads stale
 data because copies land late, an extra arrival aborts), the 16-lane fold over the half-warp and which thread ends up with
 which row, the transposition through shared memory, list insertion with ties and tombstones, partial row blocks, partial
-query tiles (QH = 2, 4, 6, 8), dim % 48 != 0 and dim % 16 != 0, and the shared per-query bound."""
+query tiles (QH = 1 .. 8), dim % 48 != 0 and dim % 16 != 0, and the shared per-query bound."""
 import ctypes as C
 import os
 import subprocess
@@ -21,14 +21,17 @@ F32 = np.float32
 SENT = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("s3") / "libscan3_emu.so")
+@pytest.fixture(scope="module", params=[3, 2], ids=["kc3", "kc2"])
+def emu(tmp_path_factory, request):
+    """Both stage depths of the kernel body: T3_KC = 3 (the default: a stage's chunks straight-line) and 2 (operands
+    software-pipelined across stage boundaries)."""
+    out = str(tmp_path_factory.mktemp("s3") / f"libscan3_emu_kc{request.param}.so")
     subprocess.check_call(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
-                           "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out, os.path.join(HERE, "scan3_emu.cpp")])
+                           f"-DT3_KC={request.param}", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out,
+                           os.path.join(HERE, "scan3_emu.cpp")])
     L = C.CDLL(out)
     L.emu_scan3.restype = C.c_int
-    L.emu_scan3.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint64] + [C.c_void_p] * 7 + \
+    L.emu_scan3.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint64] + [C.c_void_p] * 7 + \
                            [C.c_uint32] + [C.c_void_p] * 12
     return L
 
@@ -61,7 +64,7 @@ def build_case(rng, dim, leaf_lens, nq, visits_per_leaf, np_max, tomb_frac, dup=
                 tomb=tomb_bits, ord=ordv, v_leaf=v_leaf, v_q=v_q, v_np=v_np)
 
 
-def run_emu(emu, case, metric, top_k, tq, qcap=16, nst=4, blocks=2, same_np=None):
+def run_emu(emu, case, metric, top_k, tq, qcap=16, nst=4, blocks=2, same_np=None, kr=1):
     dim, dimp, P = case["dim"], case["dimp"], case["P"]
     rows_p = np.zeros((P + 1, dimp), F32); rows_p[:P, :dim] = case["rows"]
     q_p = np.zeros((case["queries"].shape[0], dimp), F32); q_p[:, :dim] = case["queries"]
@@ -94,7 +97,7 @@ def run_emu(emu, case, metric, top_k, tq, qcap=16, nst=4, blocks=2, same_np=None
     gthr = np.full(case["queries"].shape[0], SENT, np.uint64)
     entries = np.zeros((int(v_ent_off[-1]) + 1, 2), np.uint64)
     stats = np.zeros(8, np.uint64)
-    done_tiles = emu.emu_scan3(metric, blocks, dim, nst, qcap, top_k, P, rows_p.ctypes.data, bm_rinv.ctypes.data, tomb_words.ctypes.data,
+    done_tiles = emu.emu_scan3(metric, blocks, dim, nst, qcap, kr, top_k, P, rows_p.ctypes.data, bm_rinv.ctypes.data, tomb_words.ctypes.data,
                                case["ord"].ctypes.data, members.ctypes.data, case["leaf_off"].ctypes.data, case["leaf_len"].ctypes.data,
                                tile_leaf.size, tile_leaf.ctypes.data, tile_first.ctypes.data, tile_count.ctypes.data, order.ctypes.data,
                                v_np.ctypes.data, v_q.ctypes.data, v_ent_off.ctypes.data, q_p.ctypes.data, q_rinv.ctypes.data,
@@ -186,6 +189,41 @@ def test_projection_mode_signs_equal_point_is_above(emu, dim, H, n, tq):
     exp = np.stack([zo.above_batch(np.broadcast_to(coef[h], rows.shape).copy(), np.full(n, cst[h], F32), rows) for h in range(H)], axis=1)
     assert np.array_equal(sign[:, :H], exp.astype(np.uint8))
     assert np.all(sign[:, H:] == 7)                        # nothing written beyond the planes
+
+
+@pytest.mark.parametrize("metric", [zo.COSINE, zo.L2SQ])
+def test_lists_of_up_to_128_entries(emu, metric):
+    """KR = 4 (n' up to 128, BASELINE config 5's top-100): entry i of a list lives in lane i / 4, register i % 4; every
+    visit's list against the oracle, with n' from 1 to 128, ties, tombstones and leaves shorter than n'."""
+    rng = np.random.default_rng(4 + metric)
+    leaf_lens = [300, 64, 129, 40, 257]
+    visits = [9, 16, 5, 3, 12]
+    case = build_case(rng, 48, leaf_lens, 16, visits, np_max=128, tomb_frac=0.2)
+    case["v_np"][:4] = [128, 127, 100, 33]
+    entries, ent_off, v_np, _ = run_emu(emu, case, metric, top_k=0xFFFFFFFF, tq=16, kr=4)
+    for v in range(case["v_leaf"].size):
+        exp = expected_visit(case, metric, v, int(v_np[v]))
+        got = entries[ent_off[v]:ent_off[v + 1]]
+        assert got.shape[0] == exp.shape[0], v
+        assert np.array_equal(got, exp), (v, int(case["v_leaf"][v]), int(case["v_q"][v]), int(v_np[v]))
+
+
+def test_shared_bound_with_long_lists(emu):
+    """KR = 4 with every visit asking for n' = top_k = 100: published bounds may shorten later lists, the per-query top-100
+    over all visits must not change."""
+    rng = np.random.default_rng(123)
+    leaf_lens = [260, 190, 300, 150]
+    case = build_case(rng, 32, leaf_lens, 6, [6, 6, 6, 6], np_max=100, tomb_frac=0.1)
+    k = 100
+    entries, ent_off, _, gthr = run_emu(emu, case, zo.L2SQ, top_k=k, tq=16, same_np=k, blocks=2, kr=4)
+    assert (gthr != SENT).any()
+    for q in range(6):
+        got, exp = [], []
+        for v in np.nonzero(case["v_q"] == q)[0]:
+            e = entries[ent_off[v]:ent_off[v + 1]]
+            got += [tuple(x) for x in e if x[1] != SENT]
+            exp += [tuple(x) for x in expected_visit(case, zo.L2SQ, v, k)]
+        assert sorted(set(got))[:k] == sorted(set(exp))[:k], q
 
 
 def test_fold_row_is_a_bijection():

@@ -1,9 +1,7 @@
-"""GPU leg of the keys-only leaf-tile scan for cosine / L2 (quad_tile_kernel, knob quad_tile = 1): visits the fused kernel
-does not take (n' > 32: BASELINE config 5 asks for top-100) scored tile by tile instead of pair by pair.  Ids, distance
-bits and counts must equal the oracle's, and the default path's (knob 0).
-
-NOT YET RUN ON A GPU when it was committed (round 1's GPU budget was spent); on the CPU, tests/test_quadtile.py runs the
-kernel's own source thread by thread (tests/quadtile_emu.cpp) and every key equals the oracle's.  The knob is OFF by default, so nothing else depends on this path; the file sorts last."""
+"""GPU leg of the keys-only leaf-tile scan for cosine / L2 (quad_tile_kernel, knob quad_tile, default on): visits the fused
+kernel does not take (n' > 128, or the fused kernel switched off) scored tile by tile instead of pair by pair.  Ids, distance
+bits and counts must equal the oracle's, and the one-quad-per-pair path's (knob 0).  On the CPU, tests/test_quadtile.py runs
+the kernel's own source thread by thread (tests/quadtile_emu.cpp) and every key equals the oracle's."""
 import numpy as np
 import pytest
 
@@ -50,9 +48,10 @@ def test_quad_tile_scan_equals_oracle_and_default_path(mid, mname, dim, mns, tre
     ix.add(rows)
     queries = np.concatenate([rows[:48], rng.standard_normal((48, dim)).astype(F32)])
     ix.set_param("quad_tile", 1)
+    ix.set_param("use_tile_scan", 0)                                      # the fused kernel takes n' <= 128 itself: keep it out
     assert_search_equal(ix, orc, queries, k)
     st = ix.stats()
-    assert st["last_tiles"] > 0 and st["last_tile_pairs"] == 0           # n' > 32: nothing for the fused kernel
+    assert st["last_tiles"] > 0 and st["last_tile_pairs"] == 0           # nothing went through the fused kernel
     dead = rng.choice(n, n // 10, replace=False).astype(np.uint64)
     assert np.array_equal(ix.remove_ordinals(dead), orc.remove(dead))
     assert_search_equal(ix, orc, queries, k)                             # tombstones

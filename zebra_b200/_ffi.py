@@ -109,6 +109,7 @@ SYMBOLS = {
     "zb_index_search_batch_device": (C.c_int, [_vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "zb_index_search_slice": (C.c_int, [_vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp]),
     "zb_index_search_slice_device": (C.c_int, [_vp, _u64, _vp, _u64, _vp, _vp, _vp]),
+    "zb_index_search_prefetch": (C.c_int, [_vp, _u64, _vp]),
     "zb_index_hash": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "zb_index_hash_device": (C.c_int, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "zb_index_forest_sizes": (C.c_int, [_vp, _vp]),

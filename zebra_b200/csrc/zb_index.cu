@@ -149,6 +149,15 @@ struct zb_index {
     DBuf<u8> v_done;
     DBuf<Entry> entries, gathered;
     DBuf<float> q_stage, r_stage, hash_in;
+    // zb_index_search_prefetch: up to two announced uploads, staged on their own stream
+    struct Prefetch {
+        DBuf<float> buf;
+        const float* host = nullptr;
+        u64 rows = 0, seq = 0;
+        cudaEvent_t done = nullptr;
+    } pf[2];
+    cudaStream_t copy_stream = nullptr;
+    u64 pf_seq = 0;
     DBuf<u64> o_ord, o_bits, h_keys;
     DBuf<u32> o_counts, o_counts2, h_depths, rm_slots;
     DBuf<int> h_leaves;
@@ -166,7 +175,7 @@ struct zb_index {
     ScanWorkspace qt_ws;  // keys-only tile scan of the visits the fused kernel leaves (cosine / L2, n' > 32)
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 0, p_select_variant = 1, p_scan_gen = 3;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 1, p_select_variant = 1, p_scan_gen = 3, p_bm_stage_mb = 2048;
     zb_stats st{};
 
     ForestView view() const {
@@ -368,8 +377,8 @@ struct zb_index {
         launch_bm_gather(nl, d_leaf_off.p, d_leaf_len.p, d_leaf_tree.p, d_members.p, rows.p, tomb.p, dimp, slot_stride, bm_rows.p,
                          slot_pos.p, bm_tomb.p, stream);
         if (opt.metric == ZB_METRIC_COSINE) launch_rinv(bm_rows.p, members_used, dimp, bm_rinv.p, stream);
-        make_row_tile_map(bm_tmap, bm_rows.p, members_used, dimp, 128);
-        make_row_tile_map(bm_tmap3, bm_rows.p, members_used, dimp, 64);
+        make_row_tile_map(bm_tmap, bm_rows.p, members_used, dimp, 128, tile_scan_box_floats(2));
+        make_row_tile_map(bm_tmap3, bm_rows.p, members_used, dimp, 64, tile_scan_box_floats(3));
         sync();
         bm_positions = members_used;
         bm_valid = true;
@@ -437,77 +446,111 @@ struct zb_index {
         std::vector<std::vector<u32>> by_tree(T);  // live leaves of each tree, ascending
         for (u32 l = 0; l < nl; ++l)
             if (h_leaf_node[l] >= 0) by_tree[h_leaf_tree[l]].push_back(l);
+        // The leaves of a tree travel in GROUPS (ascending leaf ranges, the same cut on every rank: it is computed from the
+        // allgathered leaf shares), so that neither the send nor the receive staging area of any rank exceeds
+        // `stage_rows` rows: the store of a 100M x 768 index is built with ~4 GB of staging instead of 2/T of the store.
+        const u64 stage_rows = std::max<u64>(4096, (u64)p_bm_stage_mb * (1ull << 20) / ((u64)dimp * 4));
         for (int t = 0; t < T; ++t) {
-            // send side: my rows of the tree's leaves, grouped by destination, leaf ascending, member order
-            std::vector<u32> slots;
-            std::vector<u64> send_off(G + 1, 0);
-            for (u32 d = 0; d < G; ++d) {
-                send_off[d] = slots.size();
-                for (u32 l : by_tree[t])
-                    if (l % G == d)
-                        slots.insert(slots.end(), h_members.begin() + h_leaf_off[l], h_members.begin() + h_leaf_off[l] + h_leaf_len[l]);
-            }
-            send_off[G] = slots.size();
-            // receive side: for every source, the owned leaves in ascending order
-            std::vector<RecvSeg> segs;
-            std::vector<u64> recv_off(G + 1, 0);
-            u64 R = 0;
-            for (u32 r = 0; r < G; ++r) {
-                recv_off[r] = R;
-                for (u32 i = 0; i < owned[t].size(); ++i) {
-                    const u32 c = all_len[(size_t)r * nl + owned[t][i]];
-                    if (c) segs.push_back(RecvSeg{R, c, i});
-                    R += c;
+            const std::vector<u32>& tl = by_tree[t];
+            size_t own_i = 0;  // next leaf of owned[t] not yet placed
+            u64 tree_pos = h_tree_base[t];
+            for (size_t g0 = 0; g0 < tl.size();) {
+                // cut the group
+                std::vector<u64> snd_r(G, 0), st_r(G, 0);
+                size_t g1 = g0;
+                for (; g1 < tl.size(); ++g1) {
+                    const u32 l = tl[g1];
+                    u64 gl = 0, worst = 0;
+                    for (u32 r = 0; r < G; ++r) gl += all_len[(size_t)r * nl + l];
+                    for (u32 r = 0; r < G; ++r)
+                        worst = std::max(worst, std::max(snd_r[r] + all_len[(size_t)r * nl + l], st_r[r] + (l % G == r ? gl : 0)));
+                    if (g1 > g0 && worst > stage_rows) break;
+                    for (u32 r = 0; r < G; ++r) snd_r[r] += all_len[(size_t)r * nl + l];
+                    st_r[l % G] += gl;
                 }
-            }
-            recv_off[G] = R;
-            ZB_REQUIRE(R == h_tree_base[t + 1] - h_tree_base[t], ZB_ERR_STATE, "bucket-sharded layout mismatch");
-            const u64 ns = slots.size();
-            d_slots.ensure(ns ? ns : 1);
-            snd_rows.ensure((ns ? ns : 1) * (u64)dimp);
-            snd_key.ensure(ns ? ns : 1);
-            st_rows.ensure((R ? R : 1) * (u64)dimp);
-            st_key.ensure(R ? R : 1);
-            for (int b = 0; b < 2; ++b) {
-                sort_key[b].ensure(R ? R : 1);
-                sort_val[b].ensure(R ? R : 1);
-            }
-            d_segs.ensure(segs.size() ? segs.size() : 1);
-            sort_tmp.ensure(sort_temp_bytes(R ? R : 1));
-            if (ns) ZB_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), ns * 4, cudaMemcpyHostToDevice, stream));
-            if (!segs.empty()) ZB_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(RecvSeg), cudaMemcpyHostToDevice, stream));
-            launch_pack_rows(d_slots.p, ns, rows.p, ord.p, tomb.p, dimp, snd_rows.p, snd_key.p, stream);
-            const size_t rb = (size_t)dimp * 4;
-            nccl.group_start();
-            for (u32 r = 0; r < G; ++r) {
-                if (r == rank) continue;
-                const u64 sc = send_off[r + 1] - send_off[r], rc = recv_off[r + 1] - recv_off[r];
-                nccl.send(snd_rows.p + send_off[r] * (u64)dimp, sc * rb, (int)r, stream);
-                nccl.send(snd_key.p + send_off[r], sc * 8, (int)r, stream);
-                nccl.recv(st_rows.p + recv_off[r] * (u64)dimp, rc * rb, (int)r, stream);
-                nccl.recv(st_key.p + recv_off[r], rc * 8, (int)r, stream);
-            }
-            nccl.group_end();
-            {   // my own share never leaves the device
-                const u64 sc = send_off[rank + 1] - send_off[rank];
-                ZB_REQUIRE(sc == recv_off[rank + 1] - recv_off[rank], ZB_ERR_STATE, "bucket-sharded self share mismatch");
-                if (sc) {
-                    ZB_CUDA(cudaMemcpyAsync(st_rows.p + recv_off[rank] * (u64)dimp, snd_rows.p + send_off[rank] * (u64)dimp, sc * rb,
-                                            cudaMemcpyDeviceToDevice, stream));
-                    ZB_CUDA(cudaMemcpyAsync(st_key.p + recv_off[rank], snd_key.p + send_off[rank], sc * 8, cudaMemcpyDeviceToDevice, stream));
+                // send side: my rows of the group's leaves, grouped by destination, leaf ascending, member order
+                std::vector<u32> slots;
+                std::vector<u64> send_off(G + 1, 0);
+                for (u32 d = 0; d < G; ++d) {
+                    send_off[d] = slots.size();
+                    for (size_t i = g0; i < g1; ++i) {
+                        const u32 l = tl[i];
+                        if (l % G == d)
+                            slots.insert(slots.end(), h_members.begin() + h_leaf_off[l], h_members.begin() + h_leaf_off[l] + h_leaf_len[l]);
+                    }
                 }
+                send_off[G] = slots.size();
+                // receive side: for every source, the group's owned leaves in ascending order
+                size_t own_j = own_i;
+                while (own_j < owned[t].size() && owned[t][own_j] <= tl[g1 - 1]) ++own_j;
+                std::vector<RecvSeg> segs;
+                std::vector<u64> recv_off(G + 1, 0);
+                u64 R = 0;
+                for (u32 r = 0; r < G; ++r) {
+                    recv_off[r] = R;
+                    for (size_t i = own_i; i < own_j; ++i) {
+                        const u32 c = all_len[(size_t)r * nl + owned[t][i]];
+                        if (c) segs.push_back(RecvSeg{R, c, (u32)(i - own_i)});
+                        R += c;
+                    }
+                }
+                recv_off[G] = R;
+                ZB_REQUIRE(R == st_r[rank], ZB_ERR_STATE, "bucket-sharded layout mismatch");
+                ZB_REQUIRE(own_j - own_i < (1u << 24), ZB_ERR_STATE, "too many leaves in one exchange group");
+                const u64 ns = slots.size();
+                d_slots.ensure(ns ? ns : 1);
+                snd_rows.ensure((ns ? ns : 1) * (u64)dimp);
+                snd_key.ensure(ns ? ns : 1);
+                st_rows.ensure((R ? R : 1) * (u64)dimp);
+                st_key.ensure(R ? R : 1);
+                for (int b = 0; b < 2; ++b) {
+                    sort_key[b].ensure(R ? R : 1);
+                    sort_val[b].ensure(R ? R : 1);
+                }
+                d_segs.ensure(segs.size() ? segs.size() : 1);
+                sort_tmp.ensure(sort_temp_bytes(R ? R : 1));
+                if (ns) ZB_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), ns * 4, cudaMemcpyHostToDevice, stream));
+                if (!segs.empty()) ZB_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(RecvSeg), cudaMemcpyHostToDevice, stream));
+                launch_pack_rows(d_slots.p, ns, rows.p, ord.p, tomb.p, dimp, snd_rows.p, snd_key.p, stream);
+                const size_t rb = (size_t)dimp * 4;
+                nccl.group_start();
+                for (u32 r = 0; r < G; ++r) {
+                    if (r == rank) continue;
+                    const u64 sc = send_off[r + 1] - send_off[r], rc = recv_off[r + 1] - recv_off[r];
+                    nccl.send(snd_rows.p + send_off[r] * (u64)dimp, sc * rb, (int)r, stream);
+                    nccl.send(snd_key.p + send_off[r], sc * 8, (int)r, stream);
+                    nccl.recv(st_rows.p + recv_off[r] * (u64)dimp, rc * rb, (int)r, stream);
+                    nccl.recv(st_key.p + recv_off[r], rc * 8, (int)r, stream);
+                }
+                nccl.group_end();
+                {   // my own share never leaves the device
+                    const u64 sc = send_off[rank + 1] - send_off[rank];
+                    ZB_REQUIRE(sc == recv_off[rank + 1] - recv_off[rank], ZB_ERR_STATE, "bucket-sharded self share mismatch");
+                    if (sc) {
+                        ZB_CUDA(cudaMemcpyAsync(st_rows.p + recv_off[rank] * (u64)dimp, snd_rows.p + send_off[rank] * (u64)dimp, sc * rb,
+                                                cudaMemcpyDeviceToDevice, stream));
+                        ZB_CUDA(cudaMemcpyAsync(st_key.p + recv_off[rank], snd_key.p + send_off[rank], sc * 8, cudaMemcpyDeviceToDevice, stream));
+                    }
+                }
+                launch_seg_keys(d_segs.p, (u32)segs.size(), st_key.p, sort_key[0].p, sort_val[0].p, stream);
+                sort_pairs_u64_u32(sort_tmp.p, sort_tmp.bytes(), sort_key[0].p, sort_key[1].p, sort_val[0].p, sort_val[1].p, R, 64, stream);
+                launch_place_rows(sort_val[1].p, R, st_rows.p, st_key.p, dimp, tree_pos, bm_rows.p, bm_ord.p, bm_tomb.p, stream);
+                sync();  // the host vectors of this group (slots, segs) and the staging areas are reused by the next one
+                tree_pos += R;
+                own_i = own_j;
+                g0 = g1;
             }
-            launch_seg_keys(d_segs.p, (u32)segs.size(), st_key.p, sort_key[0].p, sort_val[0].p, stream);
-            sort_pairs_u64_u32(sort_tmp.p, sort_tmp.bytes(), sort_key[0].p, sort_key[1].p, sort_val[0].p, sort_val[1].p, R, 64, stream);
-            launch_place_rows(sort_val[1].p, R, st_rows.p, st_key.p, dimp, h_tree_base[t], bm_rows.p, bm_ord.p, bm_tomb.p, stream);
+            ZB_REQUIRE(tree_pos == h_tree_base[t + 1] && own_i == owned[t].size(), ZB_ERR_STATE, "bucket-sharded layout mismatch");
             // ordinal -> position index of the tree's region
+            const u64 Rt = h_tree_base[t + 1] - h_tree_base[t];
+            sort_tmp.ensure(sort_temp_bytes(Rt ? Rt : 1));
             sort_pairs_u64_u32(sort_tmp.p, sort_tmp.bytes(), bm_ord.p + h_tree_base[t], srt_ord.p + h_tree_base[t],
-                               d_iota.p + h_tree_base[t], srt_pos.p + h_tree_base[t], R, 40, stream);
+                               d_iota.p + h_tree_base[t], srt_pos.p + h_tree_base[t], Rt, 40, stream);
             sync();
         }
         if (opt.metric == ZB_METRIC_COSINE) launch_rinv(bm_rows.p, P, dimp, bm_rinv.p, stream);
-        make_row_tile_map(bm_tmap, bm_rows.p, Pa, dimp, 128);
-        make_row_tile_map(bm_tmap3, bm_rows.p, Pa, dimp, 64);
+        make_row_tile_map(bm_tmap, bm_rows.p, Pa, dimp, 128, tile_scan_box_floats(2));
+        make_row_tile_map(bm_tmap3, bm_rows.p, Pa, dimp, 64, tile_scan_box_floats(3));
         sync();
         bm_positions = P;
         bm_valid = true;
@@ -1184,6 +1227,12 @@ int zb_index_destroy(zb_index* ix) {
     cudaStreamSynchronize(ix->stream);
     ix->nccl.destroy();
     for (auto& ev : ix->ev) cudaEventDestroy(ev);
+    if (ix->copy_stream) {
+        cudaStreamSynchronize(ix->copy_stream);
+        cudaStreamDestroy(ix->copy_stream);
+    }
+    for (auto& p : ix->pf)
+        if (p.done) cudaEventDestroy(p.done);
     cudaStreamDestroy(ix->stream);
     delete ix;
     ZB_API_END
@@ -1558,8 +1607,20 @@ static void search_entry_host(zb_index* ix, u64 nq, const float* queries, u64 to
             const u64 nqp = (c + G - 1) / G, lo = std::min<u64>(c, ix->rank * nqp);
             mine = std::min<u64>(nqp, c - lo);
         }
+        bool staged = false;
+        if (c0 == 0 && mine) {  // announced by zb_index_search_prefetch: the rows are (being) copied on the copy stream
+            for (auto& p : ix->pf)
+                if (p.host == queries && p.rows >= mine && nq <= chunk) {
+                    ZB_CUDA(cudaStreamWaitEvent(s, p.done, 0));
+                    std::swap(ix->q_stage.p, p.buf.p);
+                    std::swap(ix->q_stage.cap, p.buf.cap);
+                    p.host = nullptr;
+                    staged = true;
+                    break;
+                }
+        }
         ix->q_stage.ensure(std::max<u64>(1, mine * (u64)ix->dimp));
-        if (mine) {
+        if (mine && !staged) {
             if (ix->dim == ix->dimp) {
                 ZB_CUDA(cudaMemcpyAsync(ix->q_stage.p, queries + in_off * (u64)ix->dim, mine * (u64)ix->dim * 4, cudaMemcpyHostToDevice, s));
             } else {
@@ -1598,6 +1659,41 @@ int zb_index_search_batch(zb_index* ix, uint64_t nq, const float* queries, uint6
     ZB_REQUIRE(top_k <= ZB_MAX_TOPK, ZB_ERR_INVALID, "top_k %llu exceeds %d", (unsigned long long)top_k, ZB_MAX_TOPK);
     std::lock_guard<std::mutex> lk(ix->mu);
     search_entry_host(ix, nq, queries, top_k, out_ids16, (u64*)out_ordinals, (u64*)out_bits, out_counts, false);
+    ZB_API_END
+}
+int zb_index_search_prefetch(zb_index* ix, uint64_t n, const float* queries) {
+    ZB_API_BEGIN
+    ZB_REQUIRE(ix && (queries || !n), ZB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!n) return ZB_OK;
+    ix->use_device();
+    if (!ix->copy_stream) {  // highest priority: the upload must not queue behind the scan's own memsets / device copies
+        int lo = 0, hi = 0;
+        ZB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ZB_CUDA(cudaStreamCreateWithPriority(&ix->copy_stream, cudaStreamNonBlocking, hi));
+    }
+    zb_index::Prefetch* slot = nullptr;
+    for (auto& p : ix->pf)
+        if (p.host == queries) slot = &p;            // announced again: refresh
+    if (!slot)
+        for (auto& p : ix->pf)
+            if (!p.host) { slot = &p; break; }       // a free slot
+    if (!slot) slot = ix->pf[0].seq < ix->pf[1].seq ? &ix->pf[0] : &ix->pf[1];  // both pending: the older announcement goes
+    if (!slot->done) ZB_CUDA(cudaEventCreateWithFlags(&slot->done, cudaEventDisableTiming));
+    // the slot's buffer may still be read by a search in flight on the main stream only if it was swapped in: it is not (a
+    // swapped-in buffer belongs to q_stage); searches are synchronous, so whatever used this buffer before has completed
+    slot->buf.ensure(n * (u64)ix->dimp);
+    if (ix->dim == ix->dimp) {
+        ZB_CUDA(cudaMemcpyAsync(slot->buf.p, queries, n * (u64)ix->dim * 4, cudaMemcpyHostToDevice, ix->copy_stream));
+    } else {
+        ZB_CUDA(cudaMemsetAsync(slot->buf.p, 0, n * (u64)ix->dimp * 4, ix->copy_stream));
+        ZB_CUDA(cudaMemcpy2DAsync(slot->buf.p, (size_t)ix->dimp * 4, queries, (size_t)ix->dim * 4, (size_t)ix->dim * 4, n,
+                                  cudaMemcpyHostToDevice, ix->copy_stream));
+    }
+    ZB_CUDA(cudaEventRecord(slot->done, ix->copy_stream));
+    slot->host = queries;
+    slot->rows = n;
+    slot->seq = ++ix->pf_seq;
     ZB_API_END
 }
 int zb_index_search_slice(zb_index* ix, uint64_t nq_total, const float* queries, uint64_t top_k, uint8_t* out_ids16,
@@ -2039,9 +2135,10 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "scan_gen") ix->p_scan_gen = value;  // fused leaf-tile scan: 3 = third generation (default), 2 = second (8-query tiles, 128-row stages)
     else if (k == "classify_variant") ix->p_classify_variant = value;  // 0: rows gathered through L1; 1: rows staged by TMA bulk copies
     else if (k == "seq_prefetch") ix->p_seq_prefetch = value;  // scalar metrics: L2 prefetch distance of the row stream in 128-byte lines (0 = off, the default: measured slower)
-    else if (k == "select_variant") ix->p_select_variant = value;  // per-visit top-n' of the gather path: 0 = block bitonic (default), 1 = one warp per visit, list in registers (until measured)
-    else if (k == "quad_tile") ix->p_quad_tile = value;  // cosine / L2 visits outside the fused kernel (n' > 32): 1 = keys-only leaf-tile scan, 0 = one quad per pair (default until measured)
+    else if (k == "select_variant") ix->p_select_variant = value;  // per-visit top-n' of the gather path: 0 = block bitonic, 1 = one warp per visit, list in registers (default: 4.9 -> 0.38 ms on 2047-row visits, profiles/r02a_bench_manhattan_select*.json)
+    else if (k == "quad_tile") ix->p_quad_tile = value;  // cosine / L2 visits outside the fused kernel (n' > 32): 1 = keys-only leaf-tile scan (default: 2.4x the gather path on top-100, profiles/r02a_bench_top100_quad*.json), 0 = one quad per pair
     else if (k == "flat_project") ix->p_flat_project = value;  // flat tables: 1 = dense projection + ballot packing (default), 0 = the generic tree walk
+    else if (k == "bm_stage_mb") ix->p_bm_stage_mb = value > 0 ? value : 1;  // bucket-sharded store build: staging area per direction, MiB (default 2048)
     else if (k == "seq_tile") ix->p_seq_tile = value;          // scalar metrics: 1 = leaf-tile scan (default), 0 = one thread per pair
     else if (k == "hash_variant") ix->p_hash_variant = value;  // 0: quad per (row, tree), rows through L1; 1: row staged in shared memory
     else if (k == "visit_slots") {  // initial per-walker capacity of the visit plan (tests force the grow-and-replan path)

@@ -540,14 +540,17 @@ __device__ __forceinline__ u64 t3_dbits(double x) { return (u64)__double_as_long
 __device__ __forceinline__ float t3_fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ u64 t3_pk2(float lo, float hi) { return pk2(lo, hi); }
 __device__ __forceinline__ void t3_upk2(u64 v, float& lo, float& hi) { upk2(v, lo, hi); }
+#ifndef T3_ASM_ORDER
+#define T3_ASM_ORDER   // `volatile` pins the FP32 stream to the order the kernel body states (needed by the T3_KC == 2 pipelining; no gain for 3)
+#endif
 __device__ __forceinline__ u64 t3_fma2(u64 a, u64 b, u64 c) {  // two IEEE fused multiply-adds (bit-identical to __fmaf_rn per half)
     u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    asm T3_ASM_ORDER("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
 __device__ __forceinline__ u64 t3_sub2(u64 a, u64 b) {
     u64 d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm T3_ASM_ORDER("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 __device__ __forceinline__ u64 t3_ldcg_u64(const u64* p) { return __ldcg(p); }
@@ -571,15 +574,16 @@ __device__ __forceinline__ bool t3_above_from_dot(float dot, float constant) { r
 #include "zb_scan3_kernel.cuh"
 namespace zb {
 
-template <int METRIC>
+// KR = list entries per lane: 1 serves n' <= 32, 4 serves n' <= 128 (BASELINE config 5 asks for top-100)
+template <int METRIC, int KR>
 __global__ void __launch_bounds__(T3_THREADS, 1) tile_scan3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
     extern __shared__ __align__(1024) unsigned char smem3[];
-    t3_body<METRIC, 0>(tmap, f, tp, smem3);
+    t3_body<METRIC, 0, KR>(tmap, f, tp, smem3);
 }
 // Flat-table projection on the same skeleton (MODE 1): tmap covers the INPUT rows, tp.queries the plane coefficients.
 __global__ void __launch_bounds__(T3_THREADS, 1) project3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
     extern __shared__ __align__(1024) unsigned char smem3[];
-    t3_body<0, 1>(tmap, f, tp, smem3);
+    t3_body<0, 1, 1>(tmap, f, tp, smem3);
 }
 
 // =====================================================================================================
@@ -702,17 +706,19 @@ static EncodeTiledFn encode_tiled_fn() {
     }
     return fn;
 }
-void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp, int box_rows) {
+void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp, int box_rows, int box_floats) {
     CUtensorMap* m = reinterpret_cast<CUtensorMap*>(out_map128);
     cuuint64_t gdim[2] = {(cuuint64_t)dimp, (cuuint64_t)(positions ? positions : 1)};
     cuuint64_t gstride[1] = {(cuuint64_t)dimp * 4};
-    cuuint32_t box[2] = {TS_SLICE_FLOATS, (cuuint32_t)box_rows};  // TS_SLICE_FLOATS == T3_SLICE_FLOATS
+    cuuint32_t box[2] = {(cuuint32_t)box_floats, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_tiled_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bm_rows, gdim, gstride, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ZB_REQUIRE(r == CUDA_SUCCESS, ZB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
 }
+
+int tile_scan_box_floats(int generation) { return generation == 2 ? TS_SLICE_FLOATS : T3_SLICE_FLOATS; }
 
 bool tile_scan_supported(int dimp, u32 top_k) {
     int dev = 0, max_smem = 0;
@@ -864,15 +870,16 @@ void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* t
 }
 
 // ---- third generation (zb_scan3_kernel.cuh): same visit grouping, tiles of up to 16 queries, 64-row stages ----
-static size_t t3_smem_bytes(int nst, int dimp, int qcap) { return T3_TEAMS * (size_t)t3_layout(nst, dimp, qcap).total + 1024; }
+static size_t t3_smem_bytes(int nst, int dimp, int qcap, int kr) { return T3_TEAMS * (size_t)t3_layout(nst, dimp, qcap, kr).total + 1024; }
+static int t3_kr(u32 top_k) { return top_k <= T3_KL ? 1 : T3_KR_MAX; }
 // ring depth and query capacity for this row length: the largest tile (16, then 8, then 4 queries) that leaves >= 3 stages
-static bool t3_config(int dimp, int* nst_out, int* qcap_out) {
+static bool t3_config(int dimp, int kr, int* nst_out, int* qcap_out) {
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     for (int qcap = T3_QT; qcap >= 4; qcap >>= 1)
         for (int nst = T3_MAX_STAGES; nst >= 3; --nst)
-            if (t3_smem_bytes(nst, dimp, qcap) <= (size_t)max_smem) {
+            if (t3_smem_bytes(nst, dimp, qcap, kr) <= (size_t)max_smem) {
                 *nst_out = nst;
                 *qcap_out = qcap;
                 return true;
@@ -881,7 +888,7 @@ static bool t3_config(int dimp, int* nst_out, int* qcap_out) {
 }
 bool tile_scan3_supported(int dimp, u32 top_k) {
     int nst, qcap;
-    return top_k >= 1 && top_k <= T3_KL && t3_config(dimp, &nst, &qcap);
+    return top_k >= 1 && top_k <= T3_KL * T3_KR_MAX && t3_config(dimp, t3_kr(top_k), &nst, &qcap);
 }
 
 void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u32 metric, const float* d_q, const double* d_q_rinv,
@@ -889,14 +896,15 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
                 u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s) {
     ws.launched = false;
     int nst = 0, qcap = 0;
-    if (!nv || !nleaves || top_k < 1 || top_k > T3_KL || !t3_config(f.dimp, &nst, &qcap)) return;
+    const int kr = t3_kr(top_k);
+    if (!nv || !nleaves || top_k < 1 || top_k > T3_KL * T3_KR_MAX || !t3_config(f.dimp, kr, &nst, &qcap)) return;
     const bool lpt_order = ((tile_queries >> 8) & 1u) == 0;  // knob bit 8 of tile_queries: 1 = tiles in leaf order (ablation)
     tile_queries &= 0xFF;
     const u32 tq = tile_queries >= 1 && tile_queries <= (u32)qcap ? tile_queries : (u32)qcap;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = t3_smem_bytes(nst, f.dimp, qcap);
+    const size_t smem = t3_smem_bytes(nst, f.dimp, qcap, kr);
 
     ws.leaf_count.ensure(nleaves + 1);
     ws.leaf_start.ensure(nleaves + 1);
@@ -967,6 +975,7 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
     tp.top_k = top_k;
     tp.nst = nst;
     tp.qcap = qcap;
+    tp.kr = kr;
     const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(bm.tmap3);
     const int grid = sms;
     if (!ws.ev0) {
@@ -974,15 +983,18 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
         ZB_CUDA(cudaEventCreate(&ws.ev1));
     }
     ZB_CUDA(cudaEventRecord(ws.ev0, s));
-    if (metric == 0) {
-        ZB_CUDA(cudaFuncSetAttribute(tile_scan3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tile_scan3_kernel<0><<<grid, T3_THREADS, smem, s>>>(tmap, f, tp);
-    } else if (metric == 1) {
-        ZB_CUDA(cudaFuncSetAttribute(tile_scan3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tile_scan3_kernel<1><<<grid, T3_THREADS, smem, s>>>(tmap, f, tp);
+    auto launch = [&](auto kern) {
+        ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, T3_THREADS, smem, s>>>(tmap, f, tp);
+    };
+    if (kr == 1) {
+        if (metric == 0) launch(tile_scan3_kernel<0, 1>);
+        else if (metric == 1) launch(tile_scan3_kernel<1, 1>);
+        else launch(tile_scan3_kernel<2, 1>);
     } else {
-        ZB_CUDA(cudaFuncSetAttribute(tile_scan3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tile_scan3_kernel<2><<<grid, T3_THREADS, smem, s>>>(tmap, f, tp);
+        if (metric == 0) launch(tile_scan3_kernel<0, T3_KR_MAX>);
+        else if (metric == 1) launch(tile_scan3_kernel<1, T3_KR_MAX>);
+        else launch(tile_scan3_kernel<2, T3_KR_MAX>);
     }
     ZB_CUDA(cudaGetLastError());
     ZB_CUDA(cudaEventRecord(ws.ev1, s));
@@ -1012,14 +1024,14 @@ __global__ void pj_tiles_kernel(u32 nranges, u32 npt, u32 range_rows, u64 n, u32
 }
 bool project3_supported(int dimp) {
     int nst, qcap;
-    return t3_config(dimp, &nst, &qcap);
+    return t3_config(dimp, 1, &nst, &qcap);
 }
 // sign[n][Hp] = Hyperplane::point_is_above (lsh.rs:39-43) of every (row, plane); rows = [n][dimp] f32, 16-byte aligned.
 void project3(ScanWorkspace& ws, const float* d_rows, u64 n, const float* d_coef, const float* d_cst, int H, int dimp, u8* d_sign, int Hp,
               cudaStream_t s) {
     int nst = 0, qcap = 0;
     if (!n || !H) return;
-    ZB_REQUIRE(t3_config(dimp, &nst, &qcap), ZB_ERR_STATE, "project3: rows of %d floats do not fit the tile kernel", dimp);
+    ZB_REQUIRE(t3_config(dimp, 1, &nst, &qcap), ZB_ERR_STATE, "project3: rows of %d floats do not fit the tile kernel", dimp);
     ZB_REQUIRE(n < (1ull << 31), ZB_ERR_INVALID, "project3: too many rows in one call");
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -1042,7 +1054,7 @@ void project3(ScanWorkspace& ws, const float* d_rows, u64 n, const float* d_coef
     pj_tiles_kernel<<<(u32)((nt + 255) / 256), 256, 0, s>>>(nranges, npt, range_rows, n, (u32)H, tq, ws.pj_off.p, ws.leaf_count.p,
                                                            ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, ws.counters.p + 2);
     alignas(64) CUtensorMap tmap;
-    make_row_tile_map(&tmap, d_rows, n, dimp, T3_RB);
+    make_row_tile_map(&tmap, d_rows, n, dimp, T3_RB, T3_SLICE_FLOATS);
     ForestView f{};
     f.leaf_off = ws.pj_off.p;
     f.leaf_len = ws.leaf_count.p;
@@ -1059,10 +1071,11 @@ void project3(ScanWorkspace& ws, const float* d_rows, u64 n, const float* d_coef
     tp.stats = reinterpret_cast<u64*>(ws.counters.p + 4);
     tp.nst = nst;
     tp.qcap = qcap;
+    tp.kr = 1;
     tp.pj_cst = d_cst;
     tp.pj_sign = d_sign;
     tp.pj_hp = Hp;
-    const size_t smem = t3_smem_bytes(nst, dimp, qcap);
+    const size_t smem = t3_smem_bytes(nst, dimp, qcap, 1);
     ZB_CUDA(cudaFuncSetAttribute(project3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     project3_kernel<<<sms, T3_THREADS, smem, s>>>(tmap, f, tp);
     ZB_CUDA(cudaGetLastError());

@@ -32,7 +32,8 @@ struct BucketMajor {
 };
 
 // Encodes the 2-D tensor map of the bucket-major store into out_map128 (128 bytes, 64-byte aligned).
-void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp, int box_rows);
+void make_row_tile_map(void* out_map128, const float* bm_rows, u64 positions, int dimp, int box_rows, int box_floats);
+int tile_scan_box_floats(int generation);   // K slice of a ring stage, in floats: second / third generation kernel
 // True when the tile kernel can serve this shape (top_k <= 32, query block + ring fit in shared memory).
 bool tile_scan_supported(int dimp, u32 top_k);
 void launch_rinv(const float* d_x, u64 n, int dimp, double* d_out, cudaStream_t s);

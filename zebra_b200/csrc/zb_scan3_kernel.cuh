@@ -12,11 +12,12 @@
 //     memory delivers 128 thread-bytes per clock whatever the access width or broadcast pattern (measured: 4.03
 //     wavefronts per LDS.128 in profiles/r01_scan_g_raw.csv), so what counts is loaded floats per FMA per thread:
 //     (8 + 4) x 4 per 128 before, 16 + 8 per 128 now -- half the shared-memory pipe time, which is what bound cosine.
-//   * the query tile adapts to the tile's population: QH = 2, 4, 6 or 8 queries per half-warp, so a 9-query tile does not
-//     pay the FP32 work of 16.
+//   * the query tile adapts to the tile's population: QH = 1 .. 8 queries per half-warp, so a 9-query tile pays the FP32
+//     work of 10, not of 16 (measured with QH in {2, 4, 6, 8}: 17.6 % of the executed FFMA2 / FADD2 were padding,
+//     profiles/r02c_scan3_l2_stalls.txt).
 //   * the distances of a row block are transposed through shared memory so that ONE warp owns a query's top-n' list for the
 //     whole tile (no per-slab lists, no end-of-tile merge, exact filter threshold per query).
-//   * row blocks of 64 rows (12 KB stages): smaller tails, more stages in flight per byte of ring.
+//   * row blocks of 64 rows (12 KB stages of 3 chunks): smaller tails, more stages in flight per byte of ring.
 //
 // Canonical arithmetic (zb_device.cuh): lane j of the 16-lane accumulator receives elements j, j+16,
 // ... by one fused multiply-add each; fold x[i] = acc[i] + acc[i+8], r[i] = x[i] + x[i+4], s = (r0 + r1) + (r2 + r3).
@@ -34,13 +35,22 @@ namespace zb {
 #define T3_TWARPS 4          // math warps per team (one per SM sub-partition)
 #define T3_QT 16             // most queries per tile (two half-warp groups of up to 8)
 #define T3_RB 64             // rows per row block = rows per ring stage (4 warps x 16 rows)
-#define T3_KC 3              // 16-float chunks per stage
+// Build variants measured on a B200 (profiles/r02g_*.json; kernel ms on BASELINE config 2 with L2 / cosine, and 384-dim L2
+// squared): KC 3 + QH step 1: 4.18 / 3.09 / 2.51 (the default);  KC 3 + QH step 2: 4.28 / 3.18 / 2.45;  KC 2 with the
+// operands software-pipelined across stages + QH step 1: 4.50 / 3.50 / 2.53;  KC 2 + QH step 2: 4.73 / 3.57 / 2.58.
+#ifndef T3_KC
+#define T3_KC 3              // 16-float chunks per stage (3: 12 KB stages, a stage's chunks straight-line; 2: 8 KB stages, software-pipelined)
+#endif
+#ifndef T3_QH_STEP
+#define T3_QH_STEP 1         // granularity of the per-half-warp query count (1: QH = 1..8; 2: QH in {2, 4, 6, 8}, half the code)
+#endif
 #define T3_SLICE_FLOATS (T3_KC * 16)
-#define T3_STAGE_BYTES (T3_RB * T3_SLICE_FLOATS * 4)   // 12288
+#define T3_STAGE_BYTES (T3_RB * T3_SLICE_FLOATS * 4)   // 12288 (KC 3) or 8192 (KC 2)
 #define T3_CWARPS (T3_TEAMS * T3_TWARPS)
 #define T3_THREADS 384       // 2 math warpgroups (= teams) + 1 producer warpgroup (one TMA-driving warp per team)
 #define T3_MAX_STAGES 8
-#define T3_KL 32             // list length of the register top-n' (one entry per lane)
+#define T3_KL 32             // lanes of a list: the register top-n' holds KR entries per lane (KR = 1: n' <= 32; KR = 4: n' <= 128)
+#define T3_KR_MAX 4
 #define T3_NOPOS 0xFFFFFFFFu
 #define T3_NOTILE 0xFFFFFFFFu
 
@@ -69,6 +79,7 @@ struct T3Params {
     u32 top_k;
     int nst;                // ring depth
     int qcap;               // query capacity of a tile (16, 8 or 4: what fits in shared memory next to a useful ring)
+    int kr;                 // list entries per lane (the kernel's KR)
     // projection mode (MODE == 1, zb_index_hash on flat tables): "leaves" are row ranges of the input, "queries" are planes
     // (tp.queries = plane coefficients, order / v_q are not read: tile slot q is plane tile_first + q)
     const float* pj_cst;    // [planes] constants
@@ -80,14 +91,14 @@ struct T3Params {
 struct T3Layout {
     u32 stage, queries, sums, lists, meta, info, bars, total;
 };
-__host__ __device__ __forceinline__ T3Layout t3_layout(int nst, int dimp, int qcap) {
+__host__ __device__ __forceinline__ T3Layout t3_layout(int nst, int dimp, int qcap, int kr) {
     T3Layout l;
     u32 o = 0;
     l.stage = o; o += (u32)nst * T3_STAGE_BYTES;
     l.queries = o; o += ((u32)qcap * (u32)dimp + 16u) * 4u;     // two regions of qcap / 2 queries, the second 64 bytes further
     o = (o + 127u) & ~127u;
     l.sums = o; o += 2u * (u32)qcap * T3_RB * 4u;               // [2][qcap][64] f32: finished sums of a row block, double buffered
-    l.lists = o; o += (u32)qcap * 3u * T3_KL * 4u;              // [qcap][3][32] u32: key lo, key hi, position
+    l.lists = o; o += (u32)qcap * 3u * (u32)kr * T3_KL * 4u;    // [qcap][3][kr][32] u32: key lo, key hi, position of entry lane * kr + r
     l.meta = o; o += (u32)qcap * 3u * 4u;                       // [3][qcap] u32: visit, n', query of every tile slot
     o = (o + 15u) & ~15u;
     l.info = o; o += 2u * (u32)sizeof(T3TileInfo);
@@ -96,7 +107,10 @@ __host__ __device__ __forceinline__ T3Layout t3_layout(int nst, int dimp, int qc
     return l;
 }
 // Queries per half-warp for a tile of nqt queries: the FP32 work of a tile is rows x 2 QH.
-__host__ __device__ __forceinline__ u32 t3_qh(u32 nqt) { return nqt <= 4 ? 2u : (nqt <= 8 ? 4u : (nqt <= 12 ? 6u : 8u)); }
+__host__ __device__ __forceinline__ u32 t3_qh(u32 nqt) {
+    const u32 q = nqt <= 2 ? 1u : (nqt + 1u) / 2u;
+    return (q + T3_QH_STEP - 1u) / T3_QH_STEP * T3_QH_STEP;
+}
 // Where tile slot q sits in the query block: region q / qh (the two regions are read by the two half-warps of every warp in
 // the same instruction: 64 bytes apart modulo 128, so the two 64-byte segments fall into different bank halves).
 __host__ __device__ __forceinline__ u32 t3_qslot_floats(u32 q, u32 qh, int dimp, int qcap) {
@@ -134,24 +148,99 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
                                               const u32 S, const int tw, const int lane, u32& buf, u32& ph, float (&sum)[QH]) {
     const int t = lane & 15, h = lane >> 4;
     const int nsl = (chunks + T3_KC - 1) / T3_KC;
+    (void)nsl;
     const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
-    const float* s_q = reinterpret_cast<const float*>(tb + lay.queries) + (u32)h * ((u32)(qcap / 2) * (u32)dimp + 16u) + t;
+    const float* qp = reinterpret_cast<const float*>(tb + lay.queries) + (u32)h * ((u32)(qcap / 2) * (u32)dimp + 16u) + t;
+    const float* stage0 = reinterpret_cast<const float*>(tb + lay.stage) + (tw * 16) * T3_SLICE_FLOATS + t;
     u64 acc[8][QH];  // acc[u][j] = packed lane partials of rows 2u, 2u+1 against query j
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int j = 0; j < QH; ++j) acc[u][j] = 0ull;
+#if T3_KC == 2
+    // A ring stage holds T3_KC == 2 chunks of the block's 64 rows.  The operands of a chunk (16 row floats + QH query floats
+    // per thread) are loaded from shared memory HALF A CHUNK AHEAD of the FP32 work that consumes them, across stage
+    // boundaries too: a row register is reloaded with the next chunk's value as soon as its last FFMA2 has been issued, the
+    // queries alternate between two register sets, and the wait on the next stage's full barrier sits in the middle of the
+    // current stage's last chunk -- neither the barrier round trip nor the shared-memory latency is in front of a warp's
+    // FFMA2 stream (the second warp of the sub-partition is busy with its own tile and cannot be counted on to fill the gap).
+    float r[16], qa[QH], qb[QH];
+    auto loadq = [&](float (&q)[QH], const float* qq_, int c) {
+#pragma unroll
+        for (int j = 0; j < QH; ++j) q[j] = qq_[j * dimp + c * 16];
+    };
+    auto loadr = [&](const float* rp, int c, int half) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[8 * half + i] = rp[(8 * half + i) * T3_SLICE_FLOATS + c * 16];
+    };
+    auto math = [&](const float (&q)[QH], int half) {
+#pragma unroll
+        for (int u = 4 * half; u < 4 * half + 4; ++u) {
+            const u64 rr = t3_pk2(r[2 * u], r[2 * u + 1]);
+#pragma unroll
+            for (int j = 0; j < QH; ++j) {
+                const u64 qq = t3_pk2(q[j], q[j]);
+                if (METRIC == 0) acc[u][j] = t3_fma2(rr, qq, acc[u][j]);
+                else {
+                    const u64 d = t3_sub2(rr, qq);
+                    acc[u][j] = t3_fma2(d, d, acc[u][j]);
+                }
+            }
+        }
+    };
+    mbar_wait(bar_full + 8 * buf, ph);
+    {
+        const float* rp = stage0 + (size_t)buf * (T3_STAGE_BYTES / 4);
+        loadq(qa, qp, 0);
+        loadr(rp, 0, 0);
+        loadr(rp, 0, 1);
+    }
+    const int nfull = chunks / T3_KC;          // stages that hold two chunks; an odd chunk count ends with a one-chunk stage
+    const bool tail = (chunks & 1) != 0;
+#pragma unroll 1
+    for (int sl = 0; sl < nfull; ++sl) {
+        const u32 cur = buf;
+        const float* rp = stage0 + (size_t)cur * (T3_STAGE_BYTES / 4);
+        const bool more = sl + 1 < nfull || tail;
+        if (++buf == S) { buf = 0; ph ^= 1u; }
+        const float* np_ = stage0 + (size_t)buf * (T3_STAGE_BYTES / 4);
+        // ---- chunk 0 of the stage: rows in r, queries in qa; chunk 1's operands arrive behind it ----
+        loadq(qb, qp, 1);
+        math(qa, 0);
+        loadr(rp, 1, 0);
+        math(qa, 1);
+        loadr(rp, 1, 1);
+        qp += T3_SLICE_FLOATS;
+        // ---- chunk 1: queries in qb; the next stage's chunk 0 arrives behind it ----
+        math(qb, 0);
+        if (more) {
+            mbar_wait(bar_full + 8 * buf, ph);
+            loadq(qa, qp, 0);
+            loadr(np_, 0, 0);
+        }
+        math(qb, 1);
+        if (more) loadr(np_, 0, 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * cur);
+    }
+    if (tail) {  // warp uniform
+        math(qa, 0);
+        math(qa, 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
+        if (++buf == S) { buf = 0; ph ^= 1u; }
+    }
+#else
     for (int sl = 0; sl < nsl; ++sl) {
         const int kcs = min(T3_KC, chunks - sl * T3_KC);
         mbar_wait(bar_full + 8 * buf, ph);
-        const float* rp = reinterpret_cast<const float*>(tb + lay.stage + (size_t)buf * T3_STAGE_BYTES) +
-                          (tw * 16) * T3_SLICE_FLOATS + t;
-        const float* qp = s_q + sl * T3_SLICE_FLOATS;
+        const float* rp = stage0 + (size_t)buf * (T3_STAGE_BYTES / 4);
+        const float* qs = qp + sl * T3_SLICE_FLOATS;
         auto chunk = [&](int c) {
             u64 qq[QH];
 #pragma unroll
             for (int j = 0; j < QH; ++j) {
-                const float q = qp[j * dimp + c * 16];
+                const float q = qs[j * dimp + c * 16];
                 qq[j] = t3_pk2(q, q);
             }
 #pragma unroll
@@ -178,6 +267,7 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
         if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
         if (++buf == S) { buf = 0; ph ^= 1u; }
     }
+#endif
     // ---- fold: canonical tree over the 16 lanes of the half-warp; a thread keeps half of its rows per step ----
     float v8[8][QH];
     {
@@ -231,11 +321,25 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
 // Scan mode: one math warp's share of one tile; per row block the sums are transposed through shared memory and the warp
 // maintains the lists of the tile slots it owns (slot q is owned by warp q % 4).
 // ------------------------------------------------------------------------------------------------------------------
+// The finished sums of (row 16 * tw + t3_fold_row(t), tile slot h * QH + j) go to sums[slot][row] of the block's buffer.
 template <int METRIC, int QH>
+__device__ __forceinline__ void t3_block_sums_store(unsigned char* tb, const T3Layout& lay, const int dimp, const int chunks, const int qcap,
+                                                    const u32 S, const int tw, const int lane, u32& buf, u32& ph, float* dst) {
+    float sum[QH];
+    t3_block_sums<METRIC, QH>(tb, lay, dimp, chunks, qcap, S, tw, lane, buf, ph, sum);
+    const int h = lane >> 4;
+#pragma unroll
+    for (int j = 0; j < QH; ++j) dst[(size_t)(h * QH + j) * T3_RB] = sum[j];
+}
+
+// One copy of the block loop and of the epilogue for all query counts: only the FP32 loop + fold is specialised by QH (the
+// instruction working set of a warp -- loop, fold, epilogue -- has to stay inside the SM's 32 KB instruction cache while the
+// two teams of a CTA run different tiles).
+template <int METRIC, int KR>
 __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& lay, const ForestView& f, const T3Params& tp,
                                              const T3TileInfo& inf, const int tw, const int lane, u32& buf, u32& ph, u32& blk,
                                              const int team, u64 (&thr)[4]) {
-    const int t = lane & 15, h = lane >> 4;
+    const int t = lane & 15;
     const u32 S = (u32)tp.nst, L = inf.L, nqt = inf.nqt;
     const u32 nblocks = (L + T3_RB - 1) / T3_RB;
     float* s_sums = reinterpret_cast<float*>(tb + lay.sums);
@@ -243,9 +347,19 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
     const u32* s_meta = reinterpret_cast<const u32*>(tb + lay.meta);
     const int myrow = t3_fold_row(t);
 
+    // The per-query bound shared by all of a query's visits (gthr) is read branch free right after a block's FP32 loop: four
+    // independent loads in flight behind the transposition and the team barrier.  A stale bound only costs work.
+    u32 gq4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const u32 q = (u32)tw + 4u * e;
+        const u32 m = s_meta[2 * tp.qcap + (q < (u32)tp.qcap ? q : 0u)];
+        gq4[e] = q < nqt ? m : 0u;
+    }
     for (u32 b = 0; b < nblocks; ++b, ++blk) {
         const u32 nrows = min((u32)T3_RB, L - b * T3_RB);
         const u32 base = (u32)(inf.moff + (long long)b * T3_RB);  // position of row 0 of the block
+
         const u32 r_lo = (u32)lane, r_hi = (u32)lane + 32u;  // the two rows of the block this lane finishes in the epilogue
         // what the epilogue reads from global memory is pulled towards the SM while the block is being scored
         if (METRIC == 0) {
@@ -253,13 +367,24 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
             t3_prefetch_l1(tp.bm_rinv + base + r_hi);
         }
         if (lane < 3) t3_prefetch_l1(tp.bm_tomb + (base >> 5) + lane);
-        float sum[QH];
-        t3_block_sums<METRIC, QH>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, sum);
         {
             float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * 16 + myrow;
-#pragma unroll
-            for (int j = 0; j < QH; ++j) dst[(size_t)(h * QH + j) * T3_RB] = sum[j];
+            switch (inf.qh) {
+#if T3_QH_STEP == 1
+                case 1: t3_block_sums_store<METRIC, 1>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 3: t3_block_sums_store<METRIC, 3>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 5: t3_block_sums_store<METRIC, 5>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 7: t3_block_sums_store<METRIC, 7>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+#endif
+                case 2: t3_block_sums_store<METRIC, 2>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 4: t3_block_sums_store<METRIC, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 6: t3_block_sums_store<METRIC, 6>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                default: t3_block_sums_store<METRIC, 8>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+            }
         }
+        u64 gbound[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gbound[e] = t3_ldcg_u64(tp.gthr + gq4[e]);
         // ---- what the epilogue needs from global memory (prefetched above; the team barrier below hides the rest) ----
         double rinv_lo = 0.0, rinv_hi = 0.0;
         if (METRIC == 0) {
@@ -268,12 +393,6 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
         }
         u32 tword = 0;  // tombstone words covering positions base .. base + 63 (at most 3 words), one per lane
         if (lane < 3) tword = tp.bm_tomb[(base >> 5) + lane];
-        u64 gbound[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const u32 q = (u32)tw + 4u * e;
-            gbound[e] = q < nqt ? t3_ldcg_u64(tp.gthr + s_meta[2 * tp.qcap + q]) : ZB_SENTINEL;
-        }
         t3_team_sync(team);  // the block's sums are complete; the previous use of this buffer was consumed two blocks ago
         // ---- epilogue: this warp finishes the tile slots it owns (q = tw, tw + 4, ...): keys, filter, list insertion ----
         const float* sums = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB;
@@ -297,9 +416,16 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
             const u64 thr0 = thr[e];
             // most blocks have no candidate under the filter: one ballot and out
             if (!__ballot_sync(0xffffffffu, (r_lo < nrows && k_lo <= thr0) || (r_hi < nrows && k_hi <= thr0))) continue;
-            u32* lst = s_lists + (size_t)q * 3 * T3_KL;
-            u64 Lk = ((u64)lst[T3_KL + lane] << 32) | lst[lane];
-            u32 Lp = lst[2 * T3_KL + lane];
+            // the slot's list, sorted by (key, position): entry i sits in lane i / KR, register i % KR
+            u32* lst = s_lists + (size_t)q * 3 * KR * T3_KL;
+            u64 Lk[KR];
+            u32 Lp[KR];
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                Lk[r] = ((u64)lst[(KR + r) * T3_KL + lane] << 32) | lst[r * T3_KL + lane];
+                Lp[r] = lst[(2 * KR + r) * T3_KL + lane];
+            }
+            const int tl = (np - 1) / KR, tr = (np - 1) % KR;  // where the n'-th best sits
             u64 th = thr0;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -314,20 +440,39 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
                     const u32 npos = base + (u32)src + 32u * i;
                     const u32 w = __shfl_sync(0xffffffffu, tword, (int)((npos >> 5) - (base >> 5)));
                     if ((w >> (npos & 31)) & 1u) continue;  // tombstoned (D1)
-                    const unsigned mm = __ballot_sync(0xffffffffu, t3_kp_less(nk, npos, Lk, Lp));
-                    const int ins = mm ? __ffs(mm) - 1 : 32;
-                    if (ins >= np) continue;
-                    const u64 upk = t3_shfl_up64(Lk);
-                    const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
-                    if (lane > ins) { Lk = upk; Lp = upp; }
-                    else if (lane == ins) { Lk = nk; Lp = npos; }
-                    const u64 lk = t3_shfl64(Lk, np - 1);
+                    // insertion point: the entries that precede the candidate are a prefix of the list
+                    int c = 0;
+#pragma unroll
+                    for (int r = 0; r < KR; ++r) c += t3_kp_less(Lk[r], Lp[r], nk, npos) ? 1 : 0;
+                    const int il = __popc(__ballot_sync(0xffffffffu, c == KR));  // lanes whose entries all precede it
+                    if (il >= T3_KL) continue;
+                    const int ir = (int)__shfl_sync(0xffffffffu, (u32)c, il);
+                    if (il * KR + ir >= np) continue;
+                    const u64 upk = t3_shfl_up64(Lk[KR - 1]);
+                    const u32 upp = __shfl_up_sync(0xffffffffu, Lp[KR - 1], 1);
+#pragma unroll
+                    for (int r = KR - 1; r >= 1; --r)
+                        if (lane > il || (lane == il && r > ir)) { Lk[r] = Lk[r - 1]; Lp[r] = Lp[r - 1]; }
+                    if (lane > il) { Lk[0] = upk; Lp[0] = upp; }
+                    if (lane == il) {
+#pragma unroll
+                        for (int r = 0; r < KR; ++r)
+                            if (r == ir) { Lk[r] = nk; Lp[r] = npos; }
+                    }
+                    u64 tk = Lk[0];
+#pragma unroll
+                    for (int r = 1; r < KR; ++r)
+                        if (r == tr) tk = Lk[r];
+                    const u64 lk = t3_shfl64(tk, tl);
                     if (lk < th) th = lk;
                 }
             }
-            lst[lane] = (u32)Lk;
-            lst[T3_KL + lane] = (u32)(Lk >> 32);
-            lst[2 * T3_KL + lane] = Lp;
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                lst[r * T3_KL + lane] = (u32)Lk[r];
+                lst[(KR + r) * T3_KL + lane] = (u32)(Lk[r] >> 32);
+                lst[(2 * KR + r) * T3_KL + lane] = Lp[r];
+            }
             thr[e] = th;
             // publish: a full list of n' == top_k distinct rows bounds the query's final k-th best
             if (lane == 0 && np == (int)tp.top_k && th < gbound[e]) t3_atomic_min_u64(tp.gthr + gq, th);
@@ -371,13 +516,13 @@ __device__ __forceinline__ void t3_project_tile(unsigned char* tb, const T3Layou
 // the two math warps that share a sub-partition belong to different tiles, so one warp's fold / epilogue / tile change
 // overlaps the other's FP32 loop, and a bandwidth-bound tile (few queries) shares the SM with a pipe-bound one.
 // MODE 0: leaf scan (METRIC 0 cosine, 1 L2 squared, 2 L2).  MODE 1: flat-table projection (METRIC ignored).
-template <int METRIC, int MODE>
+template <int METRIC, int MODE, int KR>
 __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, const T3Params& tp, unsigned char* smem) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dimp = f.dimp, chunks = f.chunks;
     const int nsl = (chunks + T3_KC - 1) / T3_KC;
     const u32 S = (u32)tp.nst;
-    const T3Layout lay = t3_layout(tp.nst, dimp, tp.qcap);
+    const T3Layout lay = t3_layout(tp.nst, dimp, tp.qcap, tp.kr);
     const int team = warp < T3_CWARPS ? warp / T3_TWARPS : (warp - T3_CWARPS) % T3_TEAMS;
     unsigned char* tb = smem + (size_t)team * lay.total;
     T3TileInfo* s_info = reinterpret_cast<T3TileInfo*>(tb + lay.info);
@@ -480,6 +625,12 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
         if (MODE == 1) {
             mbar_wait(bar_qfull, it & 1);
             switch (inf.qh) {
+#if T3_QH_STEP == 1
+                case 1: t3_project_tile<1>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 3: t3_project_tile<3>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 5: t3_project_tile<5>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 7: t3_project_tile<7>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+#endif
                 case 2: t3_project_tile<2>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
                 case 4: t3_project_tile<4>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
                 case 6: t3_project_tile<6>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
@@ -502,21 +653,15 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
         for (int e = 0; e < 4; ++e) {
             const u32 q = (u32)tw + 4u * e;
             if (q < nqt) {
-                u32* lst = s_lists + (size_t)q * 3 * T3_KL;
-                lst[lane] = 0xFFFFFFFFu;
-                lst[T3_KL + lane] = 0xFFFFFFFFu;
-                lst[2 * T3_KL + lane] = T3_NOPOS;
+                u32* lst = s_lists + (size_t)q * 3 * KR * T3_KL;
+#pragma unroll
+                for (int x = 0; x < 3 * KR; ++x) lst[x * T3_KL + lane] = 0xFFFFFFFFu;  // empty: key all ones, position T3_NOPOS
             }
         }
         u64 thr[4] = {ZB_SENTINEL, ZB_SENTINEL, ZB_SENTINEL, ZB_SENTINEL};  // filter of each owned slot: its list's n'-th key or the shared bound
         __syncwarp();
         mbar_wait(bar_qfull, it & 1);
-        switch (inf.qh) {
-            case 2: t3_scan_tile<METRIC, 2>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr); break;
-            case 4: t3_scan_tile<METRIC, 4>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr); break;
-            case 6: t3_scan_tile<METRIC, 6>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr); break;
-            default: t3_scan_tile<METRIC, 8>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr); break;
-        }
+        t3_scan_tile<METRIC, KR>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr);
         // ---- end of tile: release the query block, write the owned visits' top lists ----
         if (lane == 0) mbar_arrive(bar_qempty);
 #pragma unroll 1
@@ -525,14 +670,18 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
             if (q >= nqt) break;
             const u32 v = s_meta[q];
             const int np = (int)s_meta[tp.qcap + q];
-            const u32* lst = s_lists + (size_t)q * 3 * T3_KL;
-            const u64 k = ((u64)lst[T3_KL + lane] << 32) | lst[lane];
-            const u32 p = lst[2 * T3_KL + lane];
+            const u32* lst = s_lists + (size_t)q * 3 * KR * T3_KL;
             const u32 e0 = tp.v_ent_off[v], e1 = tp.v_ent_off[v + 1];
-            if ((u32)lane < e1 - e0) {
-                Entry en{ZB_SENTINEL, ZB_SENTINEL};
-                if (lane < np && p != T3_NOPOS) en = Entry{k, f.ord[f.members[p]]};
-                tp.entries[e0 + lane] = en;
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                const u64 k = ((u64)lst[(KR + r) * T3_KL + lane] << 32) | lst[r * T3_KL + lane];
+                const u32 p = lst[(2 * KR + r) * T3_KL + lane];
+                const u32 idx = (u32)lane * KR + r;
+                if (idx < e1 - e0) {
+                    Entry en{ZB_SENTINEL, ZB_SENTINEL};
+                    if ((int)idx < np && p != T3_NOPOS) en = Entry{k, f.ord[f.members[p]]};
+                    tp.entries[e0 + idx] = en;
+                }
             }
         }
         __syncwarp();  // the slots' shared-memory state may be re-initialised for the next tile

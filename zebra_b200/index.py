@@ -218,6 +218,10 @@ class LSHIndex:
                          ids_ptr: Optional[int] = None) -> None:
         _ffi.check(_ffi.lib().zb_index_search_slice(self._h, nq_total, q_ptr, top_k, ids_ptr, ord_ptr, bits_ptr, counts_ptr))
 
+    def search_prefetch_ptr(self, n: int, q_ptr: int):
+        """Announce the next batch (zb_index_search_prefetch): its upload overlaps the search call in between."""
+        _ffi.check(_ffi.lib().zb_index_search_prefetch(self._h, n, q_ptr))
+
     def search_slice_device(self, nq_total: int, d_q_ptr: int, top_k: int, d_ord_ptr: int, d_bits_ptr: int, d_counts_ptr: int):
         _ffi.check(_ffi.lib().zb_index_search_slice_device(self._h, nq_total, d_q_ptr, top_k, d_ord_ptr, d_bits_ptr, d_counts_ptr))
 

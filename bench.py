@@ -393,10 +393,12 @@ def run_ours(a):
     d_last = (d_ord.cpu(), d_bits.cpu())
 
     # ---- end-to-end leg through the host-buffer C ABI call: H2D of the rank's query slice, D2H of its ids/distances/counts ----
-    for b in range(min(2, a.warmup)):
-        step_e2e(b)
+    for b in range(min(3, a.warmup)):
+        step_e2e(b, b + 1 if b + 1 < min(3, a.warmup) else None)
     barrier()
     t_e = time.perf_counter()
+    if not a.no_prefetch:      # the first batch of the timed region is announced too (its upload has nothing to hide behind)
+        ix.search_prefetch_ptr(ns, h_q[a.warmup].data_ptr())
     for s in range(a.steps):
         step_e2e(a.warmup + s, a.warmup + s + 1 if s + 1 < a.steps else None)
     barrier()

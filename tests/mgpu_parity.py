@@ -46,6 +46,13 @@ def main():
             ix.set_param("visit_slots", 4)   # force the (collective) grow-and-replan path
         if dim == 768:
             ix.set_param("bm_stage_mb", 1)   # the bucket-major store is exchanged in several leaf groups per tree
+        # sliced search, three ways to get every rank's query slice to every rank: pushed into the peers' buffers over NVLink
+        # (CUDA IPC, the default), inside the visit-record allgather, in an allgather of their own
+        if dim == 100:
+            ix.set_param("p2p_queries", 0)
+        if mns == 5:
+            ix.set_param("p2p_queries", 0)
+            ix.set_param("single_exchange", 0)
         ix.add(rows)
         orc = zo.OracleIndex(dim, mid, mns, trees, seed=7) if rank == 0 else None
         if rank == 0:

@@ -216,6 +216,7 @@ static inline void t3_atomic_min_u64(u64* p, u64 v) {
     while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
 }
 static inline u64 t3_shfl64(u64 v, int src) { return emu_exchange(v, src); }
+static inline double t3_shfl_f64(double v, int src) { u64 u; memcpy(&u, &v, 8); u = emu_exchange(u, src); double r; memcpy(&r, &u, 8); return r; }
 static inline u64 t3_shfl_up64(u64 v) {
     const int lane = threadIdx.x & 31;
     return emu_exchange(v, lane == 0 ? 0 : lane - 1);

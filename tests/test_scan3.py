@@ -21,13 +21,14 @@ F32 = np.float32
 SENT = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
-@pytest.fixture(scope="module", params=[3, 2], ids=["kc3", "kc2"])
+@pytest.fixture(scope="module", params=[(3, 0), (3, 1), (2, 0)], ids=["kc3", "kc3-epilogue-warp", "kc2"])
 def emu(tmp_path_factory, request):
-    """Both stage depths of the kernel body: T3_KC = 3 (the default: a stage's chunks straight-line) and 2 (operands
-    software-pipelined across stage boundaries)."""
-    out = str(tmp_path_factory.mktemp("s3") / f"libscan3_emu_kc{request.param}.so")
+    """The build variants of the kernel body: T3_KC = 3 (the default: a stage's chunks straight-line) and 2 (operands
+    software-pipelined across stage boundaries); T3_EPW = 1 (a dedicated epilogue warp per team keeps the lists of n' <= 32)."""
+    kc, epw = request.param
+    out = str(tmp_path_factory.mktemp("s3") / f"libscan3_emu_kc{kc}_epw{epw}.so")
     subprocess.check_call(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
-                           f"-DT3_KC={request.param}", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out,
+                           f"-DT3_KC={kc}", f"-DT3_EPW={epw}", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out,
                            os.path.join(HERE, "scan3_emu.cpp")])
     L = C.CDLL(out)
     L.emu_scan3.restype = C.c_int

@@ -141,6 +141,18 @@ struct zb_index {
     DBuf<uint4> x_send, x_all;  // sharded plan exchange: [header | visit records] of this rank / of every rank
     u32 x_cap = 0;              // records per rank in an exchange block (grows on demand, kept between batches)
     DBuf<float> q_all;          // sliced search: the query slices of all ranks
+    // Peer-memory exchange of the query slices (knob p2p_queries): every rank maps every other rank's batch buffer (CUDA IPC)
+    // and PUSHES its slice into all of them with device-to-device copies over NVLink; the visit-record allgather that follows
+    // is the barrier (a rank enters it only after its own pushes completed).  NCCL's allgather stays as the fallback.
+    struct PeerQ {
+        float* mine = nullptr;              // cudaMalloc'd (IPC needs a plain allocation, not the stream-ordered pool)
+        u64 cap = 0;                        // floats
+        std::vector<float*> peer;           // [G] mapped pointers (peer[rank] == mine)
+        bool failed = false;
+        static const int NS = 4;            // side streams: the pushes to different peers run on different copy engines
+        cudaStream_t stream[NS] = {};
+        cudaEvent_t fork = nullptr, done[NS] = {};
+    } pq;
     DBuf<u64> plan_totals;
     DBuf<uint2> w_visits;
     u32 vpw = 32;  // slots per walker in the visit plan: 1 header + up to vpw - 1 visits (grows on demand)
@@ -175,7 +187,7 @@ struct zb_index {
     ScanWorkspace qt_ws;  // keys-only tile scan of the visits the fused kernel leaves (cosine / L2, n' > 32)
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 1, p_select_variant = 1, p_scan_gen = 3, p_bm_stage_mb = 2048;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 1, p_select_variant = 1, p_scan_gen = 3, p_bm_stage_mb = 2048, p_single_exchange = 1, p_p2p_queries = 1;
     zb_stats st{};
 
     ForestView view() const {
@@ -215,6 +227,7 @@ struct zb_index {
     }
     // ZB_TRACE=1: sub-phase times of every search call (CUDA events on the index's stream), printed by rank 0
     bool trace_on = getenv("ZB_TRACE") != nullptr;
+    bool trace_all = getenv("ZB_TRACE") != nullptr && atoi(getenv("ZB_TRACE")) >= 2;   // every rank prints (one line per call: fprintf is atomic enough)
     std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
     size_t trace_n = 0;
     void trace_mark(const char* what) {
@@ -230,14 +243,15 @@ struct zb_index {
     void trace_dump() {
         if (!trace_on || trace_n < 2) { trace_n = 0; return; }
         sync();
-        if (rank == 0) {
-            fprintf(stderr, "[zb trace]");
+        if (rank == 0 || trace_all) {  // one write per call, so the lines of concurrent ranks do not interleave
+            std::string line = fmt("[zb trace r%u]", rank);
             for (size_t i = 1; i < trace_n; ++i) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, trace_ev[i - 1].second, trace_ev[i].second);
-                fprintf(stderr, " %s %.3f |", trace_ev[i].first, ms);
+                line += fmt(" %s %.3f |", trace_ev[i].first, ms);
             }
-            fprintf(stderr, "\n");
+            line += "\n";
+            fputs(line.c_str(), stderr);
         }
         trace_n = 0;
     }
@@ -555,6 +569,85 @@ struct zb_index {
         bm_positions = P;
         bm_valid = true;
         return true;
+    }
+    // Collective (every rank calls it with the same `need`): (re)allocates the batch buffer, exchanges the IPC handles through
+    // the communicator and maps the peers.  Any rank failing makes every rank fall back to the NCCL allgather for good.
+    bool ensure_peer_queries(u64 need) {
+        if (pq.failed || !p_p2p_queries) return false;
+        if (need <= pq.cap && !pq.peer.empty()) return true;
+        release_peer_queries();
+        const u64 ncap = need + need / 2;
+        u32 ok = 1;
+        if (cudaMalloc((void**)&pq.mine, ncap * 4) != cudaSuccess) { cudaGetLastError(); pq.mine = nullptr; ok = 0; }
+        cudaIpcMemHandle_t h;
+        memset(&h, 0, sizeof h);
+        if (ok && cudaIpcGetMemHandle(&h, pq.mine) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        // [handle (64 bytes) | ok flag] of every rank
+        const size_t rec = 80;
+        DBuf<u8> d_rec, d_all;
+        d_rec.ensure(rec);
+        d_all.ensure(rec * G);
+        u8 hrec[80];
+        memset(hrec, 0, sizeof hrec);
+        memcpy(hrec, &h, sizeof h);
+        memcpy(hrec + 64, &ok, 4);
+        ZB_CUDA(cudaMemcpyAsync(d_rec.p, hrec, rec, cudaMemcpyHostToDevice, stream));
+        nccl.allgather(d_rec.p, d_all.p, rec, stream);
+        std::vector<u8> all(rec * G);
+        ZB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, rec * G, cudaMemcpyDeviceToHost, stream));
+        sync();
+        bool all_ok = true;
+        for (u32 r = 0; r < G; ++r) {
+            u32 f = 0;
+            memcpy(&f, all.data() + r * rec + 64, 4);
+            all_ok = all_ok && f;
+        }
+        pq.peer.assign(G, nullptr);
+        u32 mapped = all_ok ? 1u : 0u;
+        if (all_ok) {
+            for (u32 r = 0; r < G && mapped; ++r) {
+                if (r == rank) { pq.peer[r] = pq.mine; continue; }
+                cudaIpcMemHandle_t ph;
+                memcpy(&ph, all.data() + r * rec, sizeof ph);
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mapped = 0; }
+                pq.peer[r] = (float*)ptr;
+            }
+        }
+        // second round: did every rank map every peer?
+        DBuf<u32> d_flag;
+        d_flag.ensure(1);
+        ZB_CUDA(cudaMemcpyAsync(d_flag.p, &mapped, 4, cudaMemcpyHostToDevice, stream));
+        nccl.allreduce(d_flag.p, 1, Nccl::U32, Nccl::MIN, stream);
+        ZB_CUDA(cudaMemcpyAsync(&mapped, d_flag.p, 4, cudaMemcpyDeviceToHost, stream));
+        sync();
+        if (!mapped) {
+            release_peer_queries();
+            pq.failed = true;
+            return false;
+        }
+        if (!pq.fork) {
+            ZB_CUDA(cudaEventCreateWithFlags(&pq.fork, cudaEventDisableTiming));
+            for (int i = 0; i < PeerQ::NS; ++i) {
+                ZB_CUDA(cudaStreamCreateWithFlags(&pq.stream[i], cudaStreamNonBlocking));
+                ZB_CUDA(cudaEventCreateWithFlags(&pq.done[i], cudaEventDisableTiming));
+            }
+        }
+        pq.cap = ncap;
+        g_device_bytes += ncap * 4;
+        return true;
+    }
+    void release_peer_queries() {
+        cudaDeviceSynchronize();
+        for (u32 r = 0; r < pq.peer.size(); ++r)
+            if (r != rank && pq.peer[r]) cudaIpcCloseMemHandle(pq.peer[r]);
+        pq.peer.clear();
+        if (pq.mine) {
+            cudaFree(pq.mine);
+            if (pq.cap) g_device_bytes -= pq.cap * 4;
+        }
+        pq.mine = nullptr;
+        pq.cap = 0;
     }
     BucketMajor bm_view() const {
         BucketMajor b;
@@ -887,7 +980,29 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     ZB_CUDA(cudaEventRecord(ix->ev[0], s));
     ix->trace_mark("start");
     const float* d_q_mine = d_q + (sliced ? 0 : q0 * (u64)ix->dimp);  // the queries this rank plans
-    if (sliced) {  // every rank needs every query for the scan of the leaves it owns: allgather of the slices (in place)
+    // knob single_exchange (default 1): the query slices travel in the SAME allgather as the visit records, after the plan walk
+    // (which needs only the rank's own slice) -- one collective before the scan instead of two
+    const bool p2p = sliced && ix->ensure_peer_queries(nqp * G * (u64)ix->dimp);
+    const bool one_exchange = sliced && !p2p && ix->p_single_exchange;
+    if (p2p) {
+        // my slice goes to every rank's batch buffer on a side stream (copy engines over NVLink), overlapped with the plan
+        // walk; the main stream joins before the visit-record allgather, which is then also the barrier for the pushes
+        const u64 slice = nqp * (u64)ix->dimp;
+        ZB_CUDA(cudaEventRecord(ix->pq.fork, s));
+        for (int i = 0; i < zb_index::PeerQ::NS; ++i) ZB_CUDA(cudaStreamWaitEvent(ix->pq.stream[i], ix->pq.fork, 0));
+        for (u32 i = 0; i < G; ++i) {
+            const u32 r = (ix->rank + i) % G;   // start with myself, then round the ring: the ranks do not all hit the same target first
+            cudaStream_t ps = ix->pq.stream[i % zb_index::PeerQ::NS];
+            float* dst = ix->pq.peer[r] + (u64)ix->rank * slice;
+            if (qn) ZB_CUDA(cudaMemcpyAsync(dst, d_q, qn * (u64)ix->dimp * 4, cudaMemcpyDeviceToDevice, ps));
+            if (qn < nqp) ZB_CUDA(cudaMemsetAsync(dst + qn * (u64)ix->dimp, 0, (nqp - qn) * (u64)ix->dimp * 4, ps));
+        }
+        for (int i = 0; i < zb_index::PeerQ::NS; ++i) ZB_CUDA(cudaEventRecord(ix->pq.done[i], ix->pq.stream[i]));
+        d_q = ix->pq.mine;
+    } else if (one_exchange) {
+        ix->q_all.ensure(nqp * G * (u64)ix->dimp);
+        d_q = ix->q_all.p;   // filled from the exchanged blocks below
+    } else if (sliced) {  // every rank needs every query for the scan of the leaves it owns: allgather of the slices (in place)
         ix->q_all.ensure(nqp * G * (u64)ix->dimp);
         float* mine = ix->q_all.p + (u64)ix->rank * nqp * ix->dimp;
         if (qn) ZB_CUDA(cudaMemcpyAsync(mine, d_q, qn * (u64)ix->dimp * 4, cudaMemcpyDeviceToDevice, s));
@@ -942,17 +1057,30 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
             need_exchange = true;
             ix->st.last_total_launches += 1;
         }
+        // a rank's block of the exchange: [header | C visit records | (one_exchange) its query slice, nqp rows], in uint4 units
+        const size_t q4 = one_exchange ? (size_t)nqp * ix->dimp / 4 : 0;
         if (sharded && need_exchange) {
             const u32 C = ix->x_cap;
-            ix->x_send.ensure((size_t)C + 1);
-            ix->x_all.ensure(((size_t)C + 1) * G);
+            const size_t B4 = (size_t)C + 1 + q4;
+            ix->x_send.ensure(B4);
+            ix->x_all.ensure(B4 * G);
             ix->x_flags.ensure((size_t)C * G + 1);
             ix->x_pos.ensure((size_t)C * G + 1);
             launch_pack_visits((u32)nwl, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_loc_off.p, (u32)((u64)ix->rank * nwl), C,
                                ix->w_flag.p, ix->x_send.p, s);
-            ix->nccl.allgather(ix->x_send.p, ix->x_all.p, ((size_t)C + 1) * sizeof(uint4), s);
-            ix->trace_mark("allgather of visits");
-            launch_own_flags(G, C, ix->x_all.p, ix->rank, ix->x_flags.p, ix->w_flag.p + 2, s);
+            if (one_exchange) {
+                float* qdst = reinterpret_cast<float*>(ix->x_send.p + (size_t)C + 1);
+                if (qn) ZB_CUDA(cudaMemcpyAsync(qdst, d_q_mine, qn * (u64)ix->dimp * 4, cudaMemcpyDeviceToDevice, s));
+                if (qn < nqp) ZB_CUDA(cudaMemsetAsync(qdst + qn * (u64)ix->dimp, 0, (nqp - qn) * (u64)ix->dimp * 4, s));
+            }
+            if (p2p)  // my pushes are complete before I enter the collective
+                for (int i = 0; i < zb_index::PeerQ::NS; ++i) ZB_CUDA(cudaStreamWaitEvent(s, ix->pq.done[i], 0));
+            ix->nccl.allgather(ix->x_send.p, ix->x_all.p, B4 * sizeof(uint4), s);
+            ix->trace_mark(p2p ? "push of queries + allgather of visits" : one_exchange ? "allgather of visits + queries" : "allgather of visits");
+            if (one_exchange)  // the G slices, one per block, into the contiguous batch the scoring kernels index by query number
+                ZB_CUDA(cudaMemcpy2DAsync(ix->q_all.p, (size_t)nqp * ix->dimp * 4, ix->x_all.p + (size_t)C + 1, B4 * sizeof(uint4),
+                                          (size_t)nqp * ix->dimp * 4, G, cudaMemcpyDeviceToDevice, s));
+            launch_own_flags(G, C, B4, ix->x_all.p, ix->rank, ix->x_flags.p, ix->w_flag.p + 2, s);
             exclusive_scan_u32(ix->cub_tmp.p, ix->cub_tmp.bytes(), ix->x_flags.p, ix->x_pos.p, (size_t)C * G + 1, s);
             need_exchange = false;
             ix->st.last_total_launches += 3;
@@ -961,7 +1089,7 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
         ZB_CUDA(cudaMemsetAsync(ix->v_ent_len.p, 0, (v_cap + 1) * 4, s));
         if (sharded) {
             const u32 C = ix->x_cap;
-            launch_own_scatter(fs, G, C, ix->x_all.p, ix->x_flags.p, ix->x_pos.p, (u32)v_cap, tile_on ? 1u : 0u, (u32)ix->p_tile_min_rows,
+            launch_own_scatter(fs, G, C, (size_t)C + 1 + q4, ix->x_all.p, ix->x_flags.p, ix->x_pos.p, (u32)v_cap, tile_on ? 1u : 0u, (u32)ix->p_tile_min_rows,
                                (u32)top_k, ix->v_leaf.p, ix->v_np.p, ix->v_q.p, ix->v_w.p, ix->v_pair_len.p, ix->v_ent_len.p,
                                ix->v_done.p, s);
             launch_walker_offsets((u32)nw, ix->x_pos.p + (size_t)C * G, (u32)v_cap, ix->v_w.p, ix->w_off.p, s);
@@ -1225,6 +1353,14 @@ int zb_index_destroy(zb_index* ix) {
     if (!ix) return ZB_OK;
     cudaSetDevice(ix->device);
     cudaStreamSynchronize(ix->stream);
+    ix->release_peer_queries();
+    if (ix->pq.fork) {
+        cudaEventDestroy(ix->pq.fork);
+        for (int i = 0; i < zb_index::PeerQ::NS; ++i) {
+            cudaStreamDestroy(ix->pq.stream[i]);
+            cudaEventDestroy(ix->pq.done[i]);
+        }
+    }
     ix->nccl.destroy();
     for (auto& ev : ix->ev) cudaEventDestroy(ev);
     if (ix->copy_stream) {
@@ -2138,6 +2274,8 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "select_variant") ix->p_select_variant = value;  // per-visit top-n' of the gather path: 0 = block bitonic, 1 = one warp per visit, list in registers (default: 4.9 -> 0.38 ms on 2047-row visits, profiles/r02a_bench_manhattan_select*.json)
     else if (k == "quad_tile") ix->p_quad_tile = value;  // cosine / L2 visits outside the fused kernel (n' > 32): 1 = keys-only leaf-tile scan (default: 2.4x the gather path on top-100, profiles/r02a_bench_top100_quad*.json), 0 = one quad per pair
     else if (k == "flat_project") ix->p_flat_project = value;  // flat tables: 1 = dense projection + ballot packing (default), 0 = the generic tree walk
+    else if (k == "p2p_queries") ix->p_p2p_queries = value;  // sliced search: 1 = query slices pushed into the peers' buffers over NVLink (CUDA IPC; default), 0 = NCCL
+    else if (k == "single_exchange") ix->p_single_exchange = value;  // sliced search: 1 = query slices ride in the visit-record allgather (default), 0 = their own allgather first
     else if (k == "bm_stage_mb") ix->p_bm_stage_mb = value > 0 ? value : 1;  // bucket-sharded store build: staging area per direction, MiB (default 2048)
     else if (k == "seq_tile") ix->p_seq_tile = value;          // scalar metrics: 1 = leaf-tile scan (default), 0 = one thread per pair
     else if (k == "hash_variant") ix->p_hash_variant = value;  // 0: quad per (row, tree), rows through L1; 1: row staged in shared memory

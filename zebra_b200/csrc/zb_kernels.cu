@@ -146,13 +146,13 @@ void launch_pack_visits(u32 nwalkers, u32 vpw, const uint2* d_wvisits, const u32
     pack_visits_kernel<<<(nwalkers + 256) / 256, 256, 0, s>>>(nwalkers, vpw, d_wvisits, d_wcounts, d_woff, walker_base, cap, d_flag, d_out);
 }
 // flags[r * cap + i] = record i of rank r exists and its leaf lives here; summary = {max replan flag, max visit count}
-__global__ void own_flags_kernel(u32 G, u32 cap, const uint4* __restrict__ all, u32 rank, u32* __restrict__ flags,
+__global__ void own_flags_kernel(u32 G, u32 cap, size_t stride, const uint4* __restrict__ all, u32 rank, u32* __restrict__ flags,
                                  u32* __restrict__ summary) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         u32 f = 0, c = 0;
         for (u32 r = 0; r < G; ++r) {
-            const uint4 h = all[(size_t)r * (cap + 1)];
+            const uint4 h = all[(size_t)r * stride];
             f = max(f, h.y);
             c = max(c, h.x);
         }
@@ -163,16 +163,16 @@ __global__ void own_flags_kernel(u32 G, u32 cap, const uint4* __restrict__ all, 
     u32 fl = 0;
     if (i < G * cap) {
         const u32 r = i / cap, j = i - r * cap;
-        const uint4* blk = all + (size_t)r * (cap + 1);
+        const uint4* blk = all + (size_t)r * stride;
         if (j < blk[0].x) fl = (blk[1 + j].x % G == rank) ? 1u : 0u;
     }
     flags[i] = fl;  // [G * cap] = 0: the exclusive scan leaves the total there
 }
-void launch_own_flags(u32 G, u32 cap, const uint4* d_all, u32 rank, u32* d_flags, u32* d_summary, cudaStream_t s) {
-    own_flags_kernel<<<(G * cap + 256) / 256, 256, 0, s>>>(G, cap, d_all, rank, d_flags, d_summary);
+void launch_own_flags(u32 G, u32 cap, size_t stride, const uint4* d_all, u32 rank, u32* d_flags, u32* d_summary, cudaStream_t s) {
+    own_flags_kernel<<<(G * cap + 256) / 256, 256, 0, s>>>(G, cap, stride, d_all, rank, d_flags, d_summary);
 }
 // the records this rank owns -> flat visit arrays, in (planning rank, walker) order = global walker order
-__global__ void own_scatter_kernel(ForestView f, u32 G, u32 cap, const uint4* __restrict__ all, const u32* __restrict__ flags,
+__global__ void own_scatter_kernel(ForestView f, u32 G, u32 cap, size_t stride, const uint4* __restrict__ all, const u32* __restrict__ flags,
                                    const u32* __restrict__ pos, u32 vcap, u32 tile_on, u32 min_rows, u32 kmax,
                                    u32* __restrict__ vleaf, u32* __restrict__ vnp, u32* __restrict__ vq, u32* __restrict__ vw,
                                    u64* __restrict__ pair_len, u32* __restrict__ ent_len, u8* __restrict__ vdone) {
@@ -181,7 +181,7 @@ __global__ void own_scatter_kernel(ForestView f, u32 G, u32 cap, const uint4* __
     const u32 base = pos[i];
     if (base >= vcap) return;
     const u32 r = i / cap, j = i - r * cap;
-    const uint4 v = all[(size_t)r * (cap + 1) + 1 + j];
+    const uint4 v = all[(size_t)r * stride + 1 + j];
     const u32 len = f.leaf_len[v.x];
     const bool tiled = tile_on && len >= min_rows && v.y <= kmax;
     vleaf[base] = v.x;
@@ -193,10 +193,10 @@ __global__ void own_scatter_kernel(ForestView f, u32 G, u32 cap, const uint4* __
     const u32 live = f.leaf_plan[v.x];
     ent_len[base] = live < v.y ? live : v.y;
 }
-void launch_own_scatter(const ForestView& f, u32 G, u32 cap, const uint4* d_all, const u32* d_flags, const u32* d_pos, u32 vcap,
+void launch_own_scatter(const ForestView& f, u32 G, u32 cap, size_t stride, const uint4* d_all, const u32* d_flags, const u32* d_pos, u32 vcap,
                         u32 tile_on, u32 min_rows, u32 kmax, u32* d_vleaf, u32* d_vnp, u32* d_vq, u32* d_vw, u64* d_pair_len,
                         u32* d_ent_len, u8* d_vdone, cudaStream_t s) {
-    own_scatter_kernel<<<(G * cap + 255) / 256, 256, 0, s>>>(f, G, cap, d_all, d_flags, d_pos, vcap, tile_on, min_rows, kmax, d_vleaf,
+    own_scatter_kernel<<<(G * cap + 255) / 256, 256, 0, s>>>(f, G, cap, stride, d_all, d_flags, d_pos, vcap, tile_on, min_rows, kmax, d_vleaf,
                                                              d_vnp, d_vq, d_vw, d_pair_len, d_ent_len, d_vdone);
 }
 // woff[w] = first visit of walker w (visits are in walker order), woff[nwalkers] = number of visits

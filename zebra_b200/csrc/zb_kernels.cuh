@@ -58,8 +58,8 @@ void launch_plan(const ForestView& f, const float* d_queries, u32 nq, u32 top_k,
 // sharded plan exchange (compacted visit records, header first): pack -> ncclAllGather -> flags -> scan -> scatter -> offsets
 void launch_pack_visits(u32 nwalkers, u32 vpw, const uint2* d_wvisits, const u32* d_wcounts, const u32* d_woff, u32 walker_base,
                         u32 cap, const u32* d_flag, uint4* d_out, cudaStream_t s);
-void launch_own_flags(u32 G, u32 cap, const uint4* d_all, u32 rank, u32* d_flags, u32* d_summary, cudaStream_t s);
-void launch_own_scatter(const ForestView& f, u32 G, u32 cap, const uint4* d_all, const u32* d_flags, const u32* d_pos, u32 vcap,
+void launch_own_flags(u32 G, u32 cap, size_t stride, const uint4* d_all, u32 rank, u32* d_flags, u32* d_summary, cudaStream_t s);
+void launch_own_scatter(const ForestView& f, u32 G, u32 cap, size_t stride, const uint4* d_all, const u32* d_flags, const u32* d_pos, u32 vcap,
                         u32 tile_on, u32 min_rows, u32 kmax, u32* d_vleaf, u32* d_vnp, u32* d_vq, u32* d_vw, u64* d_pair_len,
                         u32* d_ent_len, u8* d_vdone, cudaStream_t s);
 void launch_walker_offsets(u32 nwalkers, const u32* d_nv, u32 vcap, const u32* d_vw, u32* d_woff, cudaStream_t s);

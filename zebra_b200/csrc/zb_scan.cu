@@ -556,14 +556,24 @@ __device__ __forceinline__ u64 t3_sub2(u64 a, u64 b) {
 __device__ __forceinline__ u64 t3_ldcg_u64(const u64* p) { return __ldcg(p); }
 __device__ __forceinline__ void t3_atomic_min_u64(u64* p, u64 v) { atomicMin(p, v); }
 __device__ __forceinline__ u64 t3_shfl64(u64 v, int src) { return shfl64(v, src); }
+__device__ __forceinline__ double t3_shfl_f64(double v, int src) { return __longlong_as_double((long long)shfl64((u64)__double_as_longlong(v), src)); }
 __device__ __forceinline__ u64 t3_shfl_up64(u64 v) { return shfl_up64(v); }
 __device__ __forceinline__ void t3_team_sync(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
 __device__ __forceinline__ void t3_fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void t3_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); }
-__device__ __forceinline__ void t3_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;"); }
+// register split of the CTA's 384 x 168 allocation: 256 math threads x T3_REGS_MATH + 128 producer / epilogue threads x T3_REGS_AUX
+// must not exceed it (232 / 40 or 224 / 56)
+#ifndef T3_REGS_MATH
+#define T3_REGS_MATH 232
+#define T3_REGS_AUX 40
+#endif
+#define T3_STR2(x) #x
+#define T3_STR(x) T3_STR2(x)
+static_assert(256 * T3_REGS_MATH + 128 * T3_REGS_AUX <= 384 * 168, "setmaxnreg split exceeds the CTA's registers");
+__device__ __forceinline__ void t3_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 " T3_STR(T3_REGS_AUX) ";"); }
+__device__ __forceinline__ void t3_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 " T3_STR(T3_REGS_MATH) ";"); }
 __device__ __forceinline__ void t3_prefetch_map(const T3Map& m) { asm volatile("prefetch.tensormap [%0];" ::"l"(&m) : "memory"); }
 __device__ __forceinline__ void t3_tma_2d_g2s(u32 dst, const T3Map& map, int c0, long long row, u32 bar) {
     tma_2d_g2s(dst, &map, c0, (int)row, bar);

@@ -41,6 +41,11 @@ namespace zb {
 #ifndef T3_KC
 #define T3_KC 3              // 16-float chunks per stage (3: 12 KB stages, a stage's chunks straight-line; 2: 8 KB stages, software-pipelined)
 #endif
+#ifndef T3_EPW
+#define T3_EPW 0             // 1: for n' <= 32 the per-query lists are kept by a dedicated epilogue warp per team (the math warps never leave
+                             // the FP32 loop + fold); 0 (default): by the math warps themselves.  Measured (profiles/r02o_*, kernel ms L2 / cosine /
+                             // 384-dim L2 squared): off 4.22 / 3.11 / 2.54; on with 232 / 40 registers 4.29 / 3.33 / 2.65; on with 224 / 56: 4.20 / 3.19 / 2.58
+#endif
 #ifndef T3_QH_STEP
 #define T3_QH_STEP 1         // granularity of the per-half-warp query count (1: QH = 1..8; 2: QH in {2, 4, 6, 8}, half the code)
 #endif
@@ -102,7 +107,7 @@ __host__ __device__ __forceinline__ T3Layout t3_layout(int nst, int dimp, int qc
     l.meta = o; o += (u32)qcap * 3u * 4u;                       // [3][qcap] u32: visit, n', query of every tile slot
     o = (o + 15u) & ~15u;
     l.info = o; o += 2u * (u32)sizeof(T3TileInfo);
-    l.bars = o; o += (2u * T3_MAX_STAGES + 4u) * 8u;            // full[8], empty[8], ifull[2], qfull, qempty
+    l.bars = o; o += (2u * T3_MAX_STAGES + 8u) * 8u;            // full[8], empty[8], ifull[2], qfull, qempty, sfull[2], sempty[2]
     l.total = (o + 127u) & ~127u;
     return l;
 }
@@ -324,9 +329,11 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
 // The finished sums of (row 16 * tw + t3_fold_row(t), tile slot h * QH + j) go to sums[slot][row] of the block's buffer.
 template <int METRIC, int QH>
 __device__ __forceinline__ void t3_block_sums_store(unsigned char* tb, const T3Layout& lay, const int dimp, const int chunks, const int qcap,
-                                                    const u32 S, const int tw, const int lane, u32& buf, u32& ph, float* dst) {
+                                                    const u32 S, const int tw, const int lane, u32& buf, u32& ph, float* dst,
+                                                    const u32 wait_bar = 0, const u32 wait_parity = 0) {
     float sum[QH];
     t3_block_sums<METRIC, QH>(tb, lay, dimp, chunks, qcap, S, tw, lane, buf, ph, sum);
+    if (wait_bar) mbar_wait(wait_bar, wait_parity);  // T3_EPW: the epilogue warp is done with this buffer's previous block
     const int h = lane >> 4;
 #pragma unroll
     for (int j = 0; j < QH; ++j) dst[(size_t)(h * QH + j) * T3_RB] = sum[j];
@@ -482,6 +489,165 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Epilogue warp (T3_EPW, n' <= 32): one warp per team keeps ALL the tile's lists.  The math warps hand over a row block's
+// finished sums through the double-buffered sums area (mbarriers sfull / sempty) and go straight on to the next block's FP32
+// loop; this warp turns the sums into keys, filters and inserts, one tile slot after the other.  Per-slot state (visit, n',
+// query, filter) lives in lane q's registers and is broadcast by shuffles; the lists live in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+template <int METRIC>
+__device__ __forceinline__ void t3_epilogue_warp(unsigned char* tb, const T3Layout& lay, const ForestView& f, const T3Params& tp,
+                                                 const int lane, const u32 bar_ifull, const u32 bar_qempty, const u32 bar_sfull,
+                                                 const u32 bar_sempty) {
+    const T3TileInfo* s_info = reinterpret_cast<const T3TileInfo*>(tb + lay.info);
+    const float* s_sums = reinterpret_cast<const float*>(tb + lay.sums);
+    u32* s_lists = reinterpret_cast<u32*>(tb + lay.lists);
+    u32 blk = 0;
+    for (u32 it = 0;; ++it) {
+        mbar_wait(bar_ifull + 8 * (it & 1), (it >> 1) & 1);
+        const u32 tile = s_info[it & 1].tile;
+        if (tile == T3_NOTILE) break;
+        const u32 nqt = s_info[it & 1].nqt, L = s_info[it & 1].L, first = s_info[it & 1].first;
+        const long long moff = s_info[it & 1].moff;
+        // lane q: the state of tile slot q
+        u32 visit_l = 0, np_l = 0, gq_l = 0;
+        double qr_l = 0.0;
+        if ((u32)lane < nqt) {
+            visit_l = tp.order[first + lane];
+            np_l = tp.v_np[visit_l];
+            gq_l = tp.v_q[visit_l];
+            if (METRIC == 0) qr_l = tp.q_rinv[gq_l];
+        }
+        u64 thr_l = ZB_SENTINEL;
+        for (u32 q = 0; q < nqt; ++q) {
+            u32* lst = s_lists + (size_t)q * 3 * T3_KL;
+            lst[lane] = 0xFFFFFFFFu;
+            lst[T3_KL + lane] = 0xFFFFFFFFu;
+            lst[2 * T3_KL + lane] = T3_NOPOS;
+        }
+        __syncwarp();
+        const u32 nblocks = (L + T3_RB - 1) / T3_RB;
+        for (u32 b = 0; b < nblocks; ++b, ++blk) {
+            const u32 nrows = min((u32)T3_RB, L - b * T3_RB);
+            const u32 base = (u32)(moff + (long long)b * T3_RB);
+            const u32 r_lo = (u32)lane, r_hi = (u32)lane + 32u;
+            // what this block needs from global memory, requested before the wait for its sums
+            double rinv_lo = 0.0, rinv_hi = 0.0;
+            if (METRIC == 0) {
+                if (r_lo < nrows) rinv_lo = tp.bm_rinv[base + r_lo];
+                if (r_hi < nrows) rinv_hi = tp.bm_rinv[base + r_hi];
+            }
+            u32 tword = 0;
+            if (lane < 3) tword = tp.bm_tomb[(base >> 5) + lane];
+            const u64 gb_l = t3_ldcg_u64(tp.gthr + gq_l);   // lanes >= nqt read gthr[0]: unused
+            if (gb_l < thr_l) thr_l = gb_l;
+            mbar_wait(bar_sfull + 8 * (blk & 1u), (blk >> 1) & 1u);
+            const float* sums = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB;
+#pragma unroll 1
+            for (u32 q = 0; q < nqt; ++q) {
+                const u64 thr0 = t3_shfl64(thr_l, (int)q);
+                const float s_lo = sums[(size_t)q * T3_RB + r_lo], s_hi = sums[(size_t)q * T3_RB + r_hi];
+                u64 k_lo = ZB_SENTINEL, k_hi = ZB_SENTINEL;
+                if (METRIC == 0) {
+                    const double qr = t3_shfl_f64(qr_l, (int)q);
+                    if (r_lo < nrows) k_lo = t3_cos_bits_rinv(s_lo, rinv_lo, qr);
+                    if (r_hi < nrows) k_hi = t3_cos_bits_rinv(s_hi, rinv_hi, qr);
+                } else {
+                    if (r_lo < nrows) k_lo = METRIC == 1 ? l2sq_bits(s_lo) : l2_bits(s_lo);
+                    if (r_hi < nrows) k_hi = METRIC == 1 ? l2sq_bits(s_hi) : l2_bits(s_hi);
+                }
+                // most blocks have no candidate under the filter: one ballot and on to the next slot
+                if (!__ballot_sync(0xffffffffu, (r_lo < nrows && k_lo <= thr0) || (r_hi < nrows && k_hi <= thr0))) continue;
+                const int np = (int)__shfl_sync(0xffffffffu, np_l, (int)q);
+                u32* lst = s_lists + (size_t)q * 3 * T3_KL;
+                u64 Lk = ((u64)lst[T3_KL + lane] << 32) | lst[lane];
+                u32 Lp = lst[2 * T3_KL + lane];
+                u64 th = thr0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const u64 key = i ? k_hi : k_lo;
+                    const bool valid = (i ? r_hi : r_lo) < nrows;
+                    unsigned m = __ballot_sync(0xffffffffu, valid && key <= th);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const u64 nk = t3_shfl64(key, src);
+                        if (nk > th) continue;  // the filter tightened since the ballot
+                        const u32 npos = base + (u32)src + 32u * i;
+                        const u32 w = __shfl_sync(0xffffffffu, tword, (int)((npos >> 5) - (base >> 5)));
+                        if ((w >> (npos & 31)) & 1u) continue;  // tombstoned (D1)
+                        const unsigned mm = __ballot_sync(0xffffffffu, t3_kp_less(nk, npos, Lk, Lp));
+                        const int ins = mm ? __ffs(mm) - 1 : 32;
+                        if (ins >= np) continue;
+                        const u64 upk = t3_shfl_up64(Lk);
+                        const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
+                        if (lane > ins) { Lk = upk; Lp = upp; }
+                        else if (lane == ins) { Lk = nk; Lp = npos; }
+                        const u64 lk = t3_shfl64(Lk, np - 1);
+                        if (lk < th) th = lk;
+                    }
+                }
+                lst[lane] = (u32)Lk;
+                lst[T3_KL + lane] = (u32)(Lk >> 32);
+                lst[2 * T3_KL + lane] = Lp;
+                // publish: a full list of n' == top_k distinct rows bounds the query's final k-th best
+                if ((u32)lane == q) {
+                    if (np == (int)tp.top_k && th < thr_l) t3_atomic_min_u64(tp.gthr + gq_l, th);
+                    thr_l = th;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sempty + 8 * (blk & 1u));  // the block's sums buffer may be overwritten
+        }
+        // ---- end of tile: every visit's list ----
+#pragma unroll 1
+        for (u32 q = 0; q < nqt; ++q) {
+            const u32 v = __shfl_sync(0xffffffffu, visit_l, (int)q);
+            const int np = (int)__shfl_sync(0xffffffffu, np_l, (int)q);
+            const u32* lst = s_lists + (size_t)q * 3 * T3_KL;
+            const u64 k = ((u64)lst[T3_KL + lane] << 32) | lst[lane];
+            const u32 p = lst[2 * T3_KL + lane];
+            const u32 e0 = tp.v_ent_off[v], e1 = tp.v_ent_off[v + 1];
+            if ((u32)lane < e1 - e0) {
+                Entry en{ZB_SENTINEL, ZB_SENTINEL};
+                if (lane < np && p != T3_NOPOS) en = Entry{k, f.ord[f.members[p]]};
+                tp.entries[e0 + lane] = en;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_qempty);  // this warp is done with the tile too: its info slot and lists may be reused
+    }
+}
+
+// Math-warp side of T3_EPW: a tile is its row blocks' FP32 loops + folds, the sums handed to the epilogue warp.
+template <int METRIC>
+__device__ __forceinline__ void t3_scan_tile_math(unsigned char* tb, const T3Layout& lay, const ForestView& f, const T3Params& tp,
+                                                  const T3TileInfo& inf, const int tw, const int lane, u32& buf, u32& ph, u32& blk,
+                                                  const u32 bar_sfull, const u32 bar_sempty) {
+    const u32 S = (u32)tp.nst;
+    const u32 nblocks = (inf.L + T3_RB - 1) / T3_RB;
+    float* s_sums = reinterpret_cast<float*>(tb + lay.sums);
+    const int myrow = t3_fold_row(lane & 15);
+    for (u32 b = 0; b < nblocks; ++b, ++blk) {
+        float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * 16 + myrow;
+        // the buffer's previous content (two blocks ago) has been consumed: checked right before the store inside, i.e. after the FP32 loop
+        switch (inf.qh) {
+#if T3_QH_STEP == 1
+            case 1: t3_block_sums_store<METRIC, 1>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 3: t3_block_sums_store<METRIC, 3>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 5: t3_block_sums_store<METRIC, 5>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 7: t3_block_sums_store<METRIC, 7>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+#endif
+            case 2: t3_block_sums_store<METRIC, 2>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 4: t3_block_sums_store<METRIC, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 6: t3_block_sums_store<METRIC, 6>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            default: t3_block_sums_store<METRIC, 8>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sfull + 8 * (blk & 1u));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Projection mode (flat-table hashing, Hyperplane::point_is_above of lsh.rs:39-43 for every (row, plane)): the tile's
 // "queries" are planes tile_first .. tile_first + nqt - 1, its "leaf" is a range of input rows; the thread that holds a
 // finished dot product tests its sign and stores it.  No lists, no transposition.
@@ -528,6 +694,8 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
     T3TileInfo* s_info = reinterpret_cast<T3TileInfo*>(tb + lay.info);
     const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
     const u32 bar_ifull = bar_full + 16 * T3_MAX_STAGES, bar_qfull = bar_ifull + 16, bar_qempty = bar_ifull + 24;
+    const u32 bar_sfull = bar_ifull + 32, bar_sempty = bar_ifull + 48;
+    constexpr bool EPW = T3_EPW && MODE == 0 && KR == 1;
 
     if (tid == 0) {
         for (int tm = 0; tm < T3_TEAMS; ++tm) {
@@ -539,7 +707,11 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
             mbar_init(bar_ifull + o, 1);
             mbar_init(bar_ifull + o + 8, 1);
             mbar_init(bar_qfull + o, 1);
-            mbar_init(bar_qempty + o, T3_TWARPS);
+            mbar_init(bar_qempty + o, T3_TWARPS + (EPW ? 1 : 0));
+            for (u32 i = 0; i < 2; ++i) {
+                mbar_init(bar_sfull + o + 8 * i, T3_TWARPS);
+                mbar_init(bar_sempty + o + 8 * i, 1);
+            }
         }
         t3_fence_barrier_init();
     }
@@ -548,7 +720,11 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
     if (warp >= T3_CWARPS) {
         // =========================== producer warpgroup: one thread per team drives TMA ===========================
         t3_setmaxnreg_dec();
-        if (warp >= T3_CWARPS + T3_TEAMS || lane != 0) return;
+        if (warp >= T3_CWARPS + T3_TEAMS) {  // the warpgroup's other two warps: one epilogue warp per team, or nothing
+            if (EPW) t3_epilogue_warp<METRIC>(tb, lay, f, tp, lane, bar_ifull, bar_qempty, bar_sfull, bar_sempty);
+            return;
+        }
+        if (lane != 0) return;
         t3_prefetch_map(tmap);
         float* s_q = reinterpret_cast<float*>(tb + lay.queries);
         const u32 ntiles = *tp.ntiles;
@@ -636,6 +812,12 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
                 case 6: t3_project_tile<6>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
                 default: t3_project_tile<8>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
             }
+            if (lane == 0) mbar_arrive(bar_qempty);
+            continue;
+        }
+        if (EPW) {
+            mbar_wait(bar_qfull, it & 1);
+            t3_scan_tile_math<METRIC>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, bar_sfull, bar_sempty);
             if (lane == 0) mbar_arrive(bar_qempty);
             continue;
         }

@@ -7,6 +7,7 @@
 // schedule of the persistent kernel.  tests/test_scan3.py feeds it leaves, tombstones and visits and compares every
 // entry the kernel writes with the oracle.
 #include <math.h>
+#include <cmath>
 #include <stdlib.h>
 #include <stdint.h>
 #include <string.h>
@@ -204,6 +205,11 @@ static inline double t3_dmul(double a, double b) { return a * b; }
 static inline double t3_dsub(double a, double b) { return a - b; }
 static inline u64 t3_dbits(double x) { u64 u; memcpy(&u, &x, 8); return u; }
 static inline float t3_fadd(float a, float b) { return a + b; }
+static inline u32 t3_fbits(float x) { return f2u(x); }
+static inline float t3_bitsf(u32 b) { return u2f(b); }
+static inline float t3_fadd_ru(float a, float b) { const float r = a + b; return r == r && !std::isinf(r) ? nextafterf(r, INFINITY) : r; }   // at least as large as the device's round-up
+static inline float t3_fmul_ru(float a, float b) { const float r = a * b; return r == r && !std::isinf(r) ? nextafterf(r, INFINITY) : r; }
+static inline float t3_fmaf(float a, float b, float c) { return fmaf(a, b, c); }
 static inline u64 t3_pk2(float lo, float hi) { return (u64)f2u(lo) | ((u64)f2u(hi) << 32); }
 static inline void t3_upk2(u64 v, float& lo, float& hi) { lo = u2f((u32)v); hi = u2f((u32)(v >> 32)); }
 static inline u64 t3_fma2(u64 a, u64 b, u64 c) {

@@ -538,6 +538,23 @@ __device__ __forceinline__ double t3_dmul(double a, double b) { return __dmul_rn
 __device__ __forceinline__ double t3_dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ u64 t3_dbits(double x) { return (u64)__double_as_longlong(x); }
 __device__ __forceinline__ float t3_fadd(float a, float b) { return __fadd_rn(a, b); }
+__host__ __device__ __forceinline__ u32 t3_fbits(float x) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(x);
+#else
+    u32 b; memcpy(&b, &x, 4); return b;
+#endif
+}
+__host__ __device__ __forceinline__ float t3_bitsf(u32 b) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float x; memcpy(&x, &b, 4); return x;
+#endif
+}
+__device__ __forceinline__ float t3_fadd_ru(float a, float b) { return __fadd_ru(a, b); }
+__device__ __forceinline__ float t3_fmul_ru(float a, float b) { return __fmul_ru(a, b); }
+__device__ __forceinline__ float t3_fmaf(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ u64 t3_pk2(float lo, float hi) { return pk2(lo, hi); }
 __device__ __forceinline__ void t3_upk2(u64 v, float& lo, float& hi) { upk2(v, lo, hi); }
 #ifndef T3_ASM_ORDER

@@ -85,6 +85,14 @@ struct T3Params {
     int nst;                // ring depth
     int qcap;               // query capacity of a tile (16, 8 or 4: what fits in shared memory next to a useful ring)
     int kr;                 // list entries per lane (the kernel's KR)
+    // METRIC 3 (L2 / L2 squared through the dot-product filter, see t3_l2f_* below)
+    const float* bm_n2;     // [positions] canonical squared norm of every stored row
+    const float* q_n2;      // [nq] canonical squared norm of every query
+    float n2max;            // largest finite bm_n2 of the store: rows above it (or not finite) are always candidates
+    float ecoef;            // (4 chunks + 32) * 2^-24 * 1.01: |A - exact| <= ecoef * (|row|^2 + |query|^2), see DESIGN 3.1b
+    u32* cand;              // [visits][32][2]: ordered(A), position of the visit's 32 best rows by A
+    float* cand_cut;        // [visits] A-domain cutoff: every row of the exact top-n' has A <= cut
+    u8* cand_flag;          // [visits] 1: the 32-entry list may not hold every row below the cutoff (refine scans the leaf)
     // projection mode (MODE == 1, zb_index_hash on flat tables): "leaves" are row ranges of the input, "queries" are planes
     // (tp.queries = plane coefficients, order / v_q are not read: tile slot q is plane tile_first + q)
     const float* pj_cst;    // [planes] constants
@@ -142,6 +150,21 @@ __device__ __forceinline__ u64 t3_cos_bits_rinv(float ab_, double ra, double rb)
     return t3_dbits(t3_dsub(1.0, c));
 }
 
+// ---- METRIC 3: L2 / L2 squared through the dot-product filter ----------------------------------------------------------
+// sum (a - b)^2 costs two FP32 operations per element, a dot product one: at 768 dimensions and ~12 queries per leaf the
+// exact scan is FP32-issue bound (2.33 ms floor per config-2 batch against 1.88 ms of HBM).  The fused kernel therefore scores
+// A = (|a|^2 + |q|^2) - 2 a.q from the canonical dot product and precomputed canonical norms, which differs from the EXACT
+// canonical f32 value D_c (what the reference's simsimd kernel returns) by at most E = ecoef * (|a|^2 + |q|^2) (forward error
+// of the two accumulations, derivation in DESIGN 3.1b), keeps the 32 best rows by A per visit, and a second pass
+// (refine_visits_kernel) evaluates D_c -- same order of operations as METRIC 1 / 2 -- only for rows with
+// A <= A_(n') + 2 E, which provably contain the exact top-n'.  Keys, ids and ties are therefore bit-identical to the exact scan.
+// Float <-> unsigned with the same order (any non-NaN float).
+__host__ __device__ __forceinline__ u32 t3_ford(float x) {
+    u32 b = t3_fbits(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float t3_funord(u32 k) { return t3_bitsf((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
+
 // ------------------------------------------------------------------------------------------------------------------
 // One row block (64 rows x the tile's queries) of one math warp: consumes the block's nsl ring stages -- rows
 // 16 * tw .. 16 * tw + 15 of every stage against the QH queries of the thread's half-warp (half-warp h serves tile slots
@@ -185,7 +208,7 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
 #pragma unroll
             for (int j = 0; j < QH; ++j) {
                 const u64 qq = t3_pk2(q[j], q[j]);
-                if (METRIC == 0) acc[u][j] = t3_fma2(rr, qq, acc[u][j]);
+                if (METRIC == 0 || METRIC == 3) acc[u][j] = t3_fma2(rr, qq, acc[u][j]);
                 else {
                     const u64 d = t3_sub2(rr, qq);
                     acc[u][j] = t3_fma2(d, d, acc[u][j]);
@@ -253,7 +276,7 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
                 const u64 ra = t3_pk2(rp[(2 * u) * T3_SLICE_FLOATS + c * 16], rp[(2 * u + 1) * T3_SLICE_FLOATS + c * 16]);
 #pragma unroll
                 for (int j = 0; j < QH; ++j) {
-                    if (METRIC == 0) acc[u][j] = t3_fma2(ra, qq[j], acc[u][j]);
+                    if (METRIC == 0 || METRIC == 3) acc[u][j] = t3_fma2(ra, qq[j], acc[u][j]);
                     else {
                         const u64 d = t3_sub2(ra, qq[j]);
                         acc[u][j] = t3_fma2(d, d, acc[u][j]);
@@ -398,6 +421,11 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
             if (r_lo < nrows) rinv_lo = tp.bm_rinv[base + r_lo];
             if (r_hi < nrows) rinv_hi = tp.bm_rinv[base + r_hi];
         }
+        float n2_lo = 0.f, n2_hi = 0.f;
+        if (METRIC == 3) {
+            if (r_lo < nrows) n2_lo = tp.bm_n2[base + r_lo];
+            if (r_hi < nrows) n2_hi = tp.bm_n2[base + r_hi];
+        }
         u32 tword = 0;  // tombstone words covering positions base .. base + 63 (at most 3 words), one per lane
         if (lane < 3) tword = tp.bm_tomb[(base >> 5) + lane];
         t3_team_sync(team);  // the block's sums are complete; the previous use of this buffer was consumed two blocks ago
@@ -407,12 +435,26 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
         for (int e = 0; e < 4; ++e) {
             const u32 q = (u32)tw + 4u * e;
             if (q >= nqt) break;  // warp uniform
-            if (gbound[e] < thr[e]) thr[e] = gbound[e];
             const int np = (int)s_meta[tp.qcap + q];
             const u32 gq = s_meta[2 * tp.qcap + q];
             const float s_lo = sums[(size_t)q * T3_RB + r_lo], s_hi = sums[(size_t)q * T3_RB + r_hi];
             u64 k_lo = ZB_SENTINEL, k_hi = ZB_SENTINEL;
-            if (METRIC == 0) {
+            float Eq = 0.f;   // METRIC 3: this query's error bound on this store (uniform over the rows: ordering by A = ordering by A -+ Eq)
+            if (METRIC == 3) {
+                const float n2q = tp.q_n2[gq];
+                Eq = t3_fadd_ru(t3_fmul_ru(tp.ecoef, t3_fadd_ru(tp.n2max, n2q)), 1e-37f);
+                // the shared bound holds an upper bound G of the query's final k-th exact value: a row with A - Eq > G is out
+                if (gbound[e] != ZB_SENTINEL) {
+                    const u64 gf = (u64)t3_ford(t3_fadd_ru(t3_funord((u32)gbound[e]), Eq));
+                    if (gf < thr[e]) thr[e] = gf;
+                }
+                const float a_lo = t3_fmaf(-2.0f, s_lo, t3_fadd(n2_lo, n2q)), a_hi = t3_fmaf(-2.0f, s_hi, t3_fadd(n2_hi, n2q));
+                // rows whose norm is not a finite number within the store's bound, or whose A is NaN: always candidates (key 0)
+                if (r_lo < nrows) k_lo = (n2_lo <= tp.n2max && a_lo == a_lo) ? (u64)t3_ford(a_lo) : 0ull;
+                if (r_hi < nrows) k_hi = (n2_hi <= tp.n2max && a_hi == a_hi) ? (u64)t3_ford(a_hi) : 0ull;
+            } else if (gbound[e] < thr[e]) thr[e] = gbound[e];
+            if (METRIC == 3) {
+            } else if (METRIC == 0) {
                 const double qr = tp.q_rinv[gq];
                 if (r_lo < nrows) k_lo = t3_cos_bits_rinv(s_lo, rinv_lo, qr);
                 if (r_hi < nrows) k_hi = t3_cos_bits_rinv(s_hi, rinv_hi, qr);
@@ -454,7 +496,7 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
                     const int il = __popc(__ballot_sync(0xffffffffu, c == KR));  // lanes whose entries all precede it
                     if (il >= T3_KL) continue;
                     const int ir = (int)__shfl_sync(0xffffffffu, (u32)c, il);
-                    if (il * KR + ir >= np) continue;
+                    if (il * KR + ir >= (METRIC == 3 ? T3_KL : np)) continue;   // METRIC 3 keeps all 32 entries (the superset refine needs)
                     const u64 upk = t3_shfl_up64(Lk[KR - 1]);
                     const u32 upp = __shfl_up_sync(0xffffffffu, Lp[KR - 1], 1);
 #pragma unroll
@@ -470,7 +512,9 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
 #pragma unroll
                     for (int r = 1; r < KR; ++r)
                         if (r == tr) tk = Lk[r];
-                    const u64 lk = t3_shfl64(tk, tl);
+                    u64 lk = t3_shfl64(tk, tl);
+                    // METRIC 3: the filter is the n'-th best A plus 2 Eq (everything that could still beat it exactly)
+                    if (METRIC == 3 && lk != ZB_SENTINEL) lk = (u64)t3_ford(t3_fadd_ru(t3_funord((u32)lk), t3_fadd_ru(Eq, Eq)));
                     if (lk < th) th = lk;
                 }
             }
@@ -482,7 +526,10 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
             }
             thr[e] = th;
             // publish: a full list of n' == top_k distinct rows bounds the query's final k-th best
-            if (lane == 0 && np == (int)tp.top_k && th < gbound[e]) t3_atomic_min_u64(tp.gthr + gq, th);
+            if (METRIC == 3) {
+                // th = ordered(A_(n') + 2 Eq) once n' rows are listed; the exact values of those n' rows are <= A_(n') + Eq <= th's value
+                if (lane == 0 && np == (int)tp.top_k && th != thr0 && th < gbound[e]) t3_atomic_min_u64(tp.gthr + gq, th);
+            } else if (lane == 0 && np == (int)tp.top_k && th < gbound[e]) t3_atomic_min_u64(tp.gthr + gq, th);
             __syncwarp();
         }
     }
@@ -695,7 +742,7 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
     const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
     const u32 bar_ifull = bar_full + 16 * T3_MAX_STAGES, bar_qfull = bar_ifull + 16, bar_qempty = bar_ifull + 24;
     const u32 bar_sfull = bar_ifull + 32, bar_sempty = bar_ifull + 48;
-    constexpr bool EPW = T3_EPW && MODE == 0 && KR == 1;
+    constexpr bool EPW = T3_EPW && MODE == 0 && KR == 1 && METRIC != 3;
 
     if (tid == 0) {
         for (int tm = 0; tm < T3_TEAMS; ++tm) {
@@ -853,6 +900,27 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
             const u32 v = s_meta[q];
             const int np = (int)s_meta[tp.qcap + q];
             const u32* lst = s_lists + (size_t)q * 3 * KR * T3_KL;
+            if (METRIC == 3) {  // the visit's 32 best rows by A, the cutoff below which the exact top-n' lies, the overflow flag
+                const u64 k = ((u64)lst[KR * T3_KL + lane] << 32) | lst[lane];
+                const u32 p = lst[2 * KR * T3_KL + lane];
+                tp.cand[((size_t)v * T3_KL + lane) * 2] = (u32)k;
+                tp.cand[((size_t)v * T3_KL + lane) * 2 + 1] = k == ZB_SENTINEL ? T3_NOPOS : p;
+                const u64 kn = t3_shfl64(k, np - 1), k31 = t3_shfl64(k, T3_KL - 1);
+                if (lane == 0) {
+                    const float n2q = tp.q_n2[s_meta[2 * tp.qcap + q]];
+                    const float Eq = t3_fadd_ru(t3_fmul_ru(tp.ecoef, t3_fadd_ru(tp.n2max, n2q)), 1e-37f);
+                    float cut = t3_bitsf(0x7F800000u);  // +inf: fewer than n' rows listed, all of them are candidates
+                    bool over = false;
+                    if (kn == 0ull) over = true;         // n' or more rows without a usable A: the leaf is scanned exactly
+                    else if (kn != ZB_SENTINEL) {
+                        cut = t3_fadd_ru(t3_funord((u32)kn), t3_fadd_ru(Eq, Eq));
+                        over = !(cut == cut) || (k31 != ZB_SENTINEL && (u32)k31 <= t3_ford(cut));
+                    }
+                    tp.cand_cut[v] = cut;
+                    tp.cand_flag[v] = over ? 1 : 0;
+                }
+                continue;
+            }
             const u32 e0 = tp.v_ent_off[v], e1 = tp.v_ent_off[v + 1];
 #pragma unroll
             for (int r = 0; r < KR; ++r) {

@@ -368,7 +368,8 @@ def run_ours(a):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = {"scan_ms": 0.0, "plan_ms": 0.0, "select_ms": 0.0, "merge_ms": 0.0, "tile_ms": 0.0, "tiles": 0, "moved": 0, "pairs": 0, "visits": 0,
-           "tile_pairs": 0, "scan_launches": 0, "launches": 0, "unique": 0}
+           "tile_pairs": 0, "scan_launches": 0, "launches": 0, "unique": 0, "refine_ms": 0.0, "filter_rows": 0, "filter_flagged": 0,
+           "filter_used": 0, "tile_visits": 0}
     t_wall = time.perf_counter()
     e0.record(stream)
     for s in range(a.steps):
@@ -380,6 +381,9 @@ def run_ours(a):
         agg["moved"] += st["last_moved_bytes"]; agg["pairs"] += st["last_pairs"]; agg["visits"] += st["last_visits"]
         agg["tile_pairs"] += st["last_tile_pairs"]; agg["unique"] += st["last_unique_bytes"]
         agg["scan_launches"] += st["last_scan_launches"]; agg["launches"] += st["last_total_launches"]
+        agg["refine_ms"] += st["last_ms_refine"]; agg["filter_rows"] += st["last_filter_rows"]
+        agg["filter_flagged"] += st["last_filter_flagged"]; agg["filter_used"] += st["last_filter_used"]
+        agg["tile_visits"] += st["last_tile_visits"]
     e1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
@@ -423,7 +427,10 @@ def run_ours(a):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": "committed ncu --set full capture of this workload (profiles/traffic.json), not this run" if traffic else None,
                 "peak_source": peak_src,
-                "kernel": "tile_scan_kernel (zb_scan.cu)" if agg["tile_ms"] > 0 else "score_pairs kernels (zb_kernels.cu, gather path)",
+                "kernel": (("tile_scan3_kernel<METRIC 3> (zb_scan3_kernel.cuh: L2 through the dot-product filter; the exact second pass "
+                            "refine_visits_kernel is timed separately, see l2_filter)" if agg["filter_used"] else
+                            "tile_scan3_kernel (zb_scan3_kernel.cuh)") if agg["tile_ms"] > 0
+                           else "score_pairs kernels (zb_kernels.cu, gather path)"),
                 "algorithmic_bytes_per_launch": agg["moved"] // max(1, a.steps), "launches_per_step": 1,
                 "unique_bytes_per_launch": agg["unique"] // max(1, a.steps),
                 "unique_bytes_frac": (agg["unique"] / scan_s / 1e9 / peak) if scan_s > 0 else 0.0,
@@ -495,6 +502,9 @@ def run_ours(a):
                            + ("" if a.no_prefetch else " + zb_index_search_prefetch of the next batch (double-buffered upload)")},
             "gpu_launches": int(agg["launches"]), "clocks": clocks,
             "phases_ms_per_step": {k: agg[k] / a.steps for k in ("plan_ms", "scan_ms", "tile_ms", "select_ms", "merge_ms")},
+            "l2_filter": {"batches_filtered": agg["filter_used"], "refine_ms_per_step": agg["refine_ms"] / a.steps,
+                          "exact_rows_per_visit": agg["filter_rows"] / max(1, agg["tile_visits"]),
+                          "visits_rescanned_exactly_per_step": agg["filter_flagged"] / a.steps},
             "per_rank_plan_scan_tile_select_merge_ms_pairs_tiles": per_rank,
             "wall_ms_per_step": wall_ms / a.steps, "visits_per_step": agg["visits"] // a.steps,
             "pairs_per_step": agg["pairs"] // a.steps, "tile_pairs_per_step": agg["tile_pairs"] // a.steps,

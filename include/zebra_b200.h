@@ -90,9 +90,11 @@ typedef struct zb_stats {
     uint32_t last_scan_launches, last_total_launches;
     float last_ms_tile_kernel;    /* the fused leaf-tile scan kernel alone (CUDA events around its launch) */
     uint32_t last_tiles;          /* (leaf, query tile) tiles it processed */
-    uint32_t reserved0;
+    uint32_t last_filter_flagged; /* L2 dot-product filter: visits of the last batch whose leaf the second pass rescanned exactly */
     uint64_t last_unique_bytes;   /* floor of the scan's HBM traffic: row bytes of the DISTINCT leaves the tile kernel visited */
-    uint32_t reserved[3];
+    uint32_t last_filter_rows;    /* L2 dot-product filter: rows whose exact distance the second pass evaluated */
+    float last_ms_refine;         /* ... and the duration of that pass (refine_visits_kernel) */
+    uint32_t last_filter_used;    /* 1: the last batch's L2 / L2 squared visits went through the filter */
 } zb_stats;
 
 const char* zb_last_error(void);

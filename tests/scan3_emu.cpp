@@ -210,6 +210,9 @@ static inline float t3_bitsf(u32 b) { return u2f(b); }
 static inline float t3_fadd_ru(float a, float b) { const float r = a + b; return r == r && !std::isinf(r) ? nextafterf(r, INFINITY) : r; }   // at least as large as the device's round-up
 static inline float t3_fmul_ru(float a, float b) { const float r = a * b; return r == r && !std::isinf(r) ? nextafterf(r, INFINITY) : r; }
 static inline float t3_fmaf(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float t3_fsub(float a, float b) { return a - b; }
+struct T3F4 { float x, y, z, w; };
+static inline T3F4 t3_ld_f4(const float* p) { T3F4 v; memcpy(&v, p, 16); return v; }
 static inline u64 t3_pk2(float lo, float hi) { return (u64)f2u(lo) | ((u64)f2u(hi) << 32); }
 static inline void t3_upk2(u64 v, float& lo, float& hi) { lo = u2f((u32)v); hi = u2f((u32)(v >> 32)); }
 static inline u64 t3_fma2(u64 a, u64 b, u64 c) {
@@ -243,6 +246,13 @@ static_assert(T3_EMU_SLICE == T3_SLICE_FLOATS && T3_EMU_STAGE_ROWS == T3_RB, "th
 
 // Tiles are given directly (what ts_count / ts_scatter / ts_filltiles build on the device).  The bucket-major store is
 // addressed by position: members = identity is supplied by the caller together with ord[position].
+// METRIC 3 (dot-product filter): what the launch code adds to T3Params, set before emu_scan3(metric = 3, ...)
+static struct { const float* bm_n2; const float* q_n2; const float* leaf_n2max; float ecoef; uint64_t* cand; float* cand_cut; uint8_t* cand_flag; } emu_filter;
+extern "C" __attribute__((visibility("default"))) void emu_scan3_set_filter(const float* bm_n2, const float* q_n2, const float* leaf_n2max, float ecoef,
+                                                                          uint64_t* cand, float* cand_cut, uint8_t* cand_flag) {
+    emu_filter = {bm_n2, q_n2, leaf_n2max, ecoef, cand, cand_cut, cand_flag};
+}
+
 extern "C" __attribute__((visibility("default"))) int emu_scan3(
     int metric, int blocks, int dim, int nst, int qcap, int kr, uint32_t top_k, uint64_t positions, const float* bm_rows_padded,
     const double* bm_rinv, const uint32_t* bm_tomb, const uint64_t* ord, const uint32_t* members, const long long* leaf_off,
@@ -259,8 +269,11 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
     tp.queries = queries_padded; tp.q_rinv = q_rinv; tp.bm_rinv = bm_rinv; tp.bm_tomb = bm_tomb;
     tp.stats = reinterpret_cast<zb::u64*>(stats3); tp.gthr = reinterpret_cast<zb::u64*>(gthr); tp.top_k = top_k; tp.nst = nst; tp.qcap = qcap; tp.kr = kr;
     tp.pj_cst = nullptr; tp.pj_sign = nullptr; tp.pj_hp = 0;
+    tp.bm_n2 = emu_filter.bm_n2; tp.q_n2 = emu_filter.q_n2; tp.leaf_n2max = emu_filter.leaf_n2max; tp.ecoef = emu_filter.ecoef;
+    tp.cand = reinterpret_cast<zb::u64*>(emu_filter.cand); tp.cand_cut = emu_filter.cand_cut; tp.cand_flag = emu_filter.cand_flag;
     zb::T3Map map{bm_rows_padded, positions, f.dimp};
     if (kr != 1 && kr != T3_KR_MAX) return -1;
+    if (metric == 3 && (kr != 1 || !tp.cand)) return -1;
     const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap, kr);
     std::vector<unsigned char> smem((size_t)T3_TEAMS * lay.total + 1024);
     emu_warps.clear();
@@ -284,6 +297,7 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
                 if (kr == 1) {
                     if (metric == 0) zb::t3_body<0, 0, 1>(map, f, tp, emu_smem);
                     else if (metric == 1) zb::t3_body<1, 0, 1>(map, f, tp, emu_smem);
+                    else if (metric == 3) zb::t3_body<3, 0, 1>(map, f, tp, emu_smem);
                     else zb::t3_body<2, 0, 1>(map, f, tp, emu_smem);
                 } else {
                     if (metric == 0) zb::t3_body<0, 0, T3_KR_MAX>(map, f, tp, emu_smem);
@@ -293,6 +307,37 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
             });
         for (auto& x : th) x.join();
         dma.finish();
+    }
+    return (int)counter;
+}
+
+// Second pass of METRIC 3: `warps` warps (run one after the other: a legal schedule) pull visits from the work counter.
+extern "C" __attribute__((visibility("default"))) int emu_refine(
+    int metric /* 1 or 2 */, int warps, int dim, const float* bm_rows_padded, const uint32_t* bm_tomb, const uint64_t* ord, const uint32_t* members,
+    const long long* leaf_off, const uint32_t* leaf_len, const float* queries_padded, const uint32_t* order, uint32_t nvisits,
+    const uint32_t* v_leaf, const uint32_t* v_np, const uint32_t* v_q, const uint32_t* v_ent_off, const uint64_t* gthr, uint64_t* entries,
+    uint64_t* stats8) {
+    zb::ForestView f;
+    f.leaf_off = leaf_off; f.leaf_len = leaf_len; f.members = members; f.ord = reinterpret_cast<const zb::u64*>(ord);
+    f.dimp = (dim + 15) / 16 * 16; f.chunks = f.dimp / 16;
+    uint32_t counter = 0;
+    zb::T3RefineParams rp;
+    rp.bm_rows = bm_rows_padded; rp.bm_tomb = bm_tomb; rp.queries = queries_padded; rp.order = order; rp.nvisits = &nvisits;
+    rp.v_leaf = v_leaf; rp.v_np = v_np; rp.v_q = v_q; rp.v_ent_off = v_ent_off;
+    rp.cand = reinterpret_cast<const zb::u64*>(emu_filter.cand); rp.cand_cut = emu_filter.cand_cut; rp.cand_flag = emu_filter.cand_flag;
+    rp.gthr = reinterpret_cast<const zb::u64*>(gthr); rp.q_n2 = emu_filter.q_n2; rp.leaf_n2max = emu_filter.leaf_n2max; rp.ecoef = emu_filter.ecoef;
+    rp.entries = reinterpret_cast<zb::Entry*>(entries); rp.work_counter = &counter; rp.stats = reinterpret_cast<zb::u64*>(stats8);
+    emu_warps.clear();
+    emu_warps.emplace_back(new WarpBox());
+    for (int w = 0; w < warps; ++w) {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < 32; ++t)
+            th.emplace_back([&, t] {
+                emu_threadIdx = Dim3{t, 0, 0};
+                if (metric == 1) zb::t3_refine_warp<1>(f, rp, (int)t);
+                else zb::t3_refine_warp<2>(f, rp, (int)t);
+            });
+        for (auto& x : th) x.join();
     }
     return (int)counter;
 }

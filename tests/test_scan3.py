@@ -65,7 +65,9 @@ def build_case(rng, dim, leaf_lens, nq, visits_per_leaf, np_max, tomb_frac, dup=
                 tomb=tomb_bits, ord=ordv, v_leaf=v_leaf, v_q=v_q, v_np=v_np)
 
 
-def run_emu(emu, case, metric, top_k, tq, qcap=16, nst=4, blocks=2, same_np=None, kr=1):
+def run_emu(emu, case, metric, top_k, tq, qcap=16, nst=4, blocks=2, same_np=None, kr=1, l2_filter=False, info=None):
+    """l2_filter: METRIC 3 of the kernel (the dot-product filter for L2 / L2 squared) followed by the exact second pass
+    (t3_refine_warp); the entries must be what the exact kernel writes.  info (a dict) receives flags, candidates, stats."""
     dim, dimp, P = case["dim"], case["dimp"], case["P"]
     rows_p = np.zeros((P + 1, dimp), F32); rows_p[:P, :dim] = case["rows"]
     q_p = np.zeros((case["queries"].shape[0], dimp), F32); q_p[:, :dim] = case["queries"]
@@ -98,13 +100,46 @@ def run_emu(emu, case, metric, top_k, tq, qcap=16, nst=4, blocks=2, same_np=None
     gthr = np.full(case["queries"].shape[0], SENT, np.uint64)
     entries = np.zeros((int(v_ent_off[-1]) + 1, 2), np.uint64)
     stats = np.zeros(8, np.uint64)
-    done_tiles = emu.emu_scan3(metric, blocks, dim, nst, qcap, kr, top_k, P, rows_p.ctypes.data, bm_rinv.ctypes.data, tomb_words.ctypes.data,
+    if l2_filter:
+        assert metric in (zo.L2SQ, zo.L2) and kr == 1
+        chunks = dimp // 16
+        with np.errstate(over="ignore", invalid="ignore"):
+            bm_n2 = np.concatenate([canonical_sq_norm(case["rows"]), np.zeros(1, F32)])
+            q_n2 = canonical_sq_norm(case["queries"])
+        leaf_n2max = np.zeros(case["leaf_len"].size, F32)
+        for l in range(case["leaf_len"].size):
+            x = bm_n2[case["leaf_off"][l]:case["leaf_off"][l + 1]]
+            x = x[x <= F32(1e37)]                            # NaN and inf compare false
+            leaf_n2max[l] = x.max() if x.size else 0
+        ecoef = F32(F32(4 * chunks + 32) * F32(2.0 ** -24) * F32(1.01))
+        cand = np.full(nv * 32 + 1, 0xDEADBEEFDEADBEEF, np.uint64)
+        cut = np.full(nv + 1, np.nan, F32)
+        flag = np.full(nv + 1, 7, np.uint8)
+        emu.emu_scan3_set_filter.restype = None
+        emu.emu_scan3_set_filter.argtypes = [C.c_void_p] * 3 + [C.c_float] + [C.c_void_p] * 3
+        emu.emu_scan3_set_filter(bm_n2.ctypes.data, q_n2.ctypes.data, leaf_n2max.ctypes.data, ecoef, cand.ctypes.data, cut.ctypes.data,
+                                 flag.ctypes.data)
+    done_tiles = emu.emu_scan3(3 if l2_filter else metric, blocks, dim, nst, qcap, kr, top_k, P, rows_p.ctypes.data, bm_rinv.ctypes.data, tomb_words.ctypes.data,
                                case["ord"].ctypes.data, members.ctypes.data, case["leaf_off"].ctypes.data, case["leaf_len"].ctypes.data,
                                tile_leaf.size, tile_leaf.ctypes.data, tile_first.ctypes.data, tile_count.ctypes.data, order.ctypes.data,
                                v_np.ctypes.data, v_q.ctypes.data, v_ent_off.ctypes.data, q_p.ctypes.data, q_rinv.ctypes.data,
                                gthr.ctypes.data, entries.ctypes.data, stats.ctypes.data)
     assert done_tiles >= tile_leaf.size
     assert int(stats[0]) == nv and int(stats[1]) == int(case["leaf_len"][v_leaf].astype(np.int64).sum())
+    if l2_filter:
+        assert not (entries != 0).any()                     # the first pass writes candidates, not entries
+        assert set(np.unique(flag[:nv])) <= {0, 1}
+        emu.emu_refine.restype = C.c_int
+        emu.emu_refine.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_uint32] + [C.c_void_p] * 7
+        pulled = emu.emu_refine(metric, 2, dim, rows_p.ctypes.data, tomb_words.ctypes.data, case["ord"].ctypes.data, members.ctypes.data,
+                                case["leaf_off"].ctypes.data, case["leaf_len"].ctypes.data, q_p.ctypes.data, order.ctypes.data, nv,
+                                v_leaf.ctypes.data, v_np.ctypes.data, v_q.ctypes.data, v_ent_off.ctypes.data, gthr.ctypes.data,
+                                entries.ctypes.data, stats.ctypes.data)
+        assert pulled >= nv
+        assert int(stats[4]) == int(flag[:nv].sum())
+        if info is not None:
+            info.update(flag=flag[:nv].copy(), cut=cut[:nv].copy(), cand=cand[:nv * 32].reshape(nv, 32).copy(), exact_rows=int(stats[5]),
+                        flagged=int(stats[4]))
     return entries, v_ent_off, v_np, gthr
 
 
@@ -230,3 +265,100 @@ def test_shared_bound_with_long_lists(emu):
 def test_fold_row_is_a_bijection():
     rows = sorted(((t >> 1) & 1) | ((t & 1) << 1) | (t & 4) | (t & 8) for t in range(16))
     assert rows == list(range(16))
+
+
+# ---- METRIC 3: L2 / L2 squared through the dot-product filter + exact second pass ---------------------------------------
+def check_every_visit(case, metric, entries, ent_off, v_np):
+    for v in range(case["v_leaf"].size):
+        exp = expected_visit(case, metric, v, int(v_np[v]))
+        got = entries[ent_off[v]:ent_off[v + 1]]
+        assert got.shape[0] == exp.shape[0], v
+        assert np.array_equal(got, exp), (v, int(case["v_leaf"][v]), int(case["v_q"][v]), int(v_np[v]))
+
+
+@pytest.mark.parametrize("metric", [zo.L2SQ, zo.L2])
+@pytest.mark.parametrize("dim,tq", [(48, 16), (100, 16), (200, 11)])
+def test_l2_filter_per_visit_lists_equal_oracle(emu, metric, dim, tq):
+    """Every visit's list after the two passes is the exact top-n' (n' up to 16: what the launch code admits), with ties,
+    tombstones, a distance of exactly zero, partial blocks and every QH."""
+    rng = np.random.default_rng(dim * 11 + metric)
+    leaf_lens = [1, 63, 64, 65, 130, 17, 200, 128, 5]
+    visits = [1, 2, 5, 9, 16, 3, 21, 13, 4]
+    case = build_case(rng, dim, leaf_lens, 24, visits, np_max=16, tomb_frac=0.15)
+    info = {}
+    entries, ent_off, v_np, _ = run_emu(emu, case, metric, top_k=0xFFFFFFFF, tq=tq, l2_filter=True, info=info)
+    check_every_visit(case, metric, entries, ent_off, v_np)
+    assert info["flagged"] == 0                             # well-separated random data: the filter alone decides
+    live = sum(min(int(n), 32) for n in case["leaf_len"][case["v_leaf"]])
+    assert info["exact_rows"] < live                        # ... and the second pass looked at a fraction of the listed rows
+
+
+def test_l2_filter_crowded_keys_flag_the_visit(emu):
+    """More than 32 rows within the error band of the n'-th best (here: 50 copies of one row, and rows a few ulps apart):
+    the 32-entry list cannot hold every candidate, the visit is flagged and its leaf scanned exactly -- ties by position."""
+    rng = np.random.default_rng(77)
+    case = build_case(rng, 64, [150, 90, 64], 6, [6, 6, 6], np_max=12, tomb_frac=0.1, dup=False)
+    case["rows"][20:70] = case["rows"][5]                   # leaf 0: 51 equal rows
+    near = case["rows"][160].copy()
+    for i in range(40):                                      # leaf 1: 40 rows that differ in the last bits of one coordinate
+        case["rows"][170 + i] = near
+        case["rows"][170 + i, 3] = np.nextafter(near[3], F32(np.inf) if i % 2 else F32(-np.inf), dtype=F32)
+    case["queries"][0] = case["rows"][5]
+    case["queries"][1] = near
+    info = {}
+    entries, ent_off, v_np, _ = run_emu(emu, case, zo.L2SQ, top_k=0xFFFFFFFF, tq=16, l2_filter=True, info=info)
+    check_every_visit(case, zo.L2SQ, entries, ent_off, v_np)
+    assert info["flagged"] >= 2
+
+
+def test_l2_filter_unusable_norms_fall_back_to_the_exact_scan(emu):
+    """Rows and queries whose squared norms overflow, are infinite or NaN, and subnormal / zero vectors."""
+    rng = np.random.default_rng(78)
+    case = build_case(rng, 48, [100, 70, 40, 64], 8, [8, 8, 8, 8], np_max=10, tomb_frac=0.05, dup=False)
+    case["rows"][3, 0] = F32(3e19)                          # |row|^2 = 9e38: inf
+    case["rows"][7, 5] = F32(np.nan)
+    case["rows"][110, 2] = F32(np.inf)
+    case["rows"][120] *= F32(1e18)                          # |row|^2 ~ 5e37: above the limit, finite
+    case["rows"][175] = 0
+    case["rows"][176] = F32(1e-30)                          # squares underflow to subnormals / zero
+    case["rows"][177] = F32(1e-22)
+    case["queries"][2] = 0
+    case["queries"][3] = F32(1e-25)
+    case["queries"][4, 1] = F32(np.nan)
+    case["queries"][5] *= F32(2e18)
+    info = {}
+    with np.errstate(over="ignore", invalid="ignore"):
+        entries, ent_off, v_np, _ = run_emu(emu, case, zo.L2, top_k=0xFFFFFFFF, tq=16, l2_filter=True, info=info)
+        check_every_visit(case, zo.L2, entries, ent_off, v_np)
+    assert info["flagged"] >= 8
+
+
+def test_l2_filter_wide_norm_range_inside_a_leaf(emu):
+    """The error bound of a leaf follows its largest row: small rows next to rows 10^4 times longer stay exact (more candidates,
+    possibly flagged visits, never a wrong list)."""
+    rng = np.random.default_rng(79)
+    case = build_case(rng, 80, [120, 200], 10, [10, 10], np_max=8, tomb_frac=0.0, dup=False)
+    case["rows"][:120:3] *= F32(1e4)
+    case["rows"][130:200] *= F32(1e-3)
+    case["queries"][:5] *= F32(1e-3)
+    entries, ent_off, v_np, _ = run_emu(emu, case, zo.L2SQ, top_k=0xFFFFFFFF, tq=16, l2_filter=True)
+    check_every_visit(case, zo.L2SQ, entries, ent_off, v_np)
+
+
+@pytest.mark.parametrize("metric", [zo.L2SQ, zo.L2])
+def test_l2_filter_shared_bound_keeps_the_per_query_answer(emu, metric):
+    """n' = top_k everywhere: full lists publish G = A_(n') + Eq, later visits (and the second pass) drop rows above it; the
+    per-query top-k over all visits must be the exact one."""
+    rng = np.random.default_rng(101 + metric)
+    leaf_lens = [150, 90, 200, 64, 70, 129]
+    case = build_case(rng, 64, leaf_lens, 12, [12] * 6, np_max=8, tomb_frac=0.1)
+    k = 8
+    entries, ent_off, _, gthr = run_emu(emu, case, metric, top_k=k, tq=16, same_np=k, blocks=3, l2_filter=True)
+    assert (gthr != SENT).any()
+    for q in range(12):
+        got, exp = [], []
+        for v in np.nonzero(case["v_q"] == q)[0]:
+            e = entries[ent_off[v]:ent_off[v + 1]]
+            got += [tuple(x) for x in e if x[1] != SENT]
+            exp += [tuple(x) for x in expected_visit(case, metric, v, k)]
+        assert sorted(set(got))[:k] == sorted(set(exp))[:k], q

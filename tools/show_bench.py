@@ -15,6 +15,8 @@ for path in sys.argv[1:]:
           f"  parity {d.get('parity_sample_ok')}  cpu {(d.get('cpu_baseline') or {}).get('value')}")
     if d.get("phases_ms_per_step"):
         print("    phases", {k: round(v, 3) for k, v in d["phases_ms_per_step"].items()}, "clocks", d.get("clocks"))
+    if d.get("l2_filter"):
+        print("    l2_filter", d["l2_filter"])
     for row in d.get("per_rank_plan_scan_tile_select_merge_ms_pairs_tiles") or []:
         print("     ", row)
     cfg = d.get("config", {})

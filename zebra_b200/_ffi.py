@@ -62,9 +62,11 @@ class Stats(C.Structure):
         ("last_total_launches", C.c_uint32),
         ("last_ms_tile_kernel", C.c_float),
         ("last_tiles", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("last_filter_flagged", C.c_uint32),
         ("last_unique_bytes", C.c_uint64),
-        ("reserved", C.c_uint32 * 3),
+        ("last_filter_rows", C.c_uint32),
+        ("last_ms_refine", C.c_float),
+        ("last_filter_used", C.c_uint32),
     ]
 
     def as_dict(self):

@@ -118,6 +118,8 @@ struct zb_index {
     // ---- bucket-major store (search path): position p of the member array holds a copy of row members[p] ----
     DBuf<float> bm_rows;
     DBuf<double> bm_rinv, q_rinv;
+    DBuf<float> bm_n2, bm_leaf_n2max;   // L2 / L2 squared: canonical |row|^2 per position, its usable maximum per leaf (the dot-product filter)
+    int filter_backoff = 0;             // batches the filter sits out after one in which too many visits had to be rescanned exactly
     DBuf<u32> bm_tomb, slot_pos, d_leaf_tree;
     alignas(64) unsigned char bm_tmap[128];
     alignas(64) unsigned char bm_tmap3[128];
@@ -187,7 +189,7 @@ struct zb_index {
     ScanWorkspace qt_ws;  // keys-only tile scan of the visits the fused kernel leaves (cosine / L2, n' > 32)
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 1, p_select_variant = 1, p_scan_gen = 3, p_bm_stage_mb = 2048, p_single_exchange = 1, p_p2p_queries = 1;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 1, p_select_variant = 1, p_scan_gen = 3, p_bm_stage_mb = 2048, p_single_exchange = 1, p_p2p_queries = 1, p_l2_filter = 1;
     zb_stats st{};
 
     ForestView view() const {
@@ -376,6 +378,10 @@ struct zb_index {
             slot_pos.ensure(slot_stride * (u64)T);
             d_leaf_tree.ensure(nl);
             if (opt.metric == ZB_METRIC_COSINE) bm_rinv.ensure(members_used);
+            if (opt.metric == ZB_METRIC_L2SQ || opt.metric == ZB_METRIC_L2) {
+                bm_n2.ensure(members_used);
+                bm_leaf_n2max.ensure(nl ? nl : 1);
+            }
         } catch (const Error& e) {
             if (e.code != ZB_ERR_OOM) throw;
             bm_rows.release();
@@ -391,6 +397,10 @@ struct zb_index {
         launch_bm_gather(nl, d_leaf_off.p, d_leaf_len.p, d_leaf_tree.p, d_members.p, rows.p, tomb.p, dimp, slot_stride, bm_rows.p,
                          slot_pos.p, bm_tomb.p, stream);
         if (opt.metric == ZB_METRIC_COSINE) launch_rinv(bm_rows.p, members_used, dimp, bm_rinv.p, stream);
+        if (opt.metric == ZB_METRIC_L2SQ || opt.metric == ZB_METRIC_L2) {
+            launch_n2(bm_rows.p, members_used, dimp, bm_n2.p, stream);
+            launch_leaf_n2max(nl, d_leaf_off.p, d_leaf_len.p, bm_n2.p, bm_leaf_n2max.p, stream);
+        }
         make_row_tile_map(bm_tmap, bm_rows.p, members_used, dimp, 128, tile_scan_box_floats(2));
         make_row_tile_map(bm_tmap3, bm_rows.p, members_used, dimp, 64, tile_scan_box_floats(3));
         sync();
@@ -444,6 +454,10 @@ struct zb_index {
         d_bm_len.ensure(nl ? nl : 1);
         d_tree_base.ensure(T + 1);
         if (opt.metric == ZB_METRIC_COSINE) bm_rinv.ensure(Pa);
+        if (opt.metric == ZB_METRIC_L2SQ || opt.metric == ZB_METRIC_L2) {
+            bm_n2.ensure(Pa);
+            bm_leaf_n2max.ensure(nl ? nl : 1);
+        }
         ZB_CUDA(cudaMemsetAsync(bm_tomb.p, 0, (Pa / 32 + 8) * 4, stream));
         if (nl) {
             ZB_CUDA(cudaMemcpyAsync(d_bm_off.p, off.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, stream));
@@ -563,6 +577,10 @@ struct zb_index {
             sync();
         }
         if (opt.metric == ZB_METRIC_COSINE) launch_rinv(bm_rows.p, P, dimp, bm_rinv.p, stream);
+        if (opt.metric == ZB_METRIC_L2SQ || opt.metric == ZB_METRIC_L2) {   // leaves this rank does not own have length 0 here
+            launch_n2(bm_rows.p, P, dimp, bm_n2.p, stream);
+            launch_leaf_n2max(nl, d_bm_off.p, d_bm_len.p, bm_n2.p, bm_leaf_n2max.p, stream);
+        }
         make_row_tile_map(bm_tmap, bm_rows.p, Pa, dimp, 128, tile_scan_box_floats(2));
         make_row_tile_map(bm_tmap3, bm_rows.p, Pa, dimp, 64, tile_scan_box_floats(3));
         sync();
@@ -654,6 +672,10 @@ struct zb_index {
         b.rows = bm_rows.p;
         b.rinv = bm_rinv.p;
         b.tomb = bm_tomb.p;
+        if (opt.metric == ZB_METRIC_L2SQ || opt.metric == ZB_METRIC_L2) {
+            b.n2 = bm_n2.p;
+            b.leaf_n2max = bm_leaf_n2max.p;
+        }
         b.tmap = bm_tmap;
         b.tmap3 = bm_tmap3;
         b.positions = bm_positions;
@@ -1142,6 +1164,11 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
             ix->q_rinv.ensure(nq);
             launch_rinv(d_q, nq, ix->dimp, ix->q_rinv.p, s);
         }
+        // L2 / L2 squared, top_k <= 16, rows of 128 floats or more: the fused kernel scores through the dot product and a second
+        // pass evaluates the exact distance of the few rows that can reach a visit's list (knob l2_filter: 0 off, 1 unless the
+        // last batches had to rescan too many visits exactly, 2 always)
+        ix->scan_ws.l2_filter = gen3 && ix->dimp >= 128 && (ix->p_l2_filter == 2 || (ix->p_l2_filter == 1 && ix->filter_backoff == 0));
+        if (ix->filter_backoff > 0) --ix->filter_backoff;
         (gen3 ? tile_scan3 : tile_scan)(ix->scan_ws, fs, ix->bm_view(), ix->opt.metric, d_q, ix->q_rinv.p, (u32)nq, nv, ix->v_leaf.p,
                                         ix->v_np.p, ix->v_q.p, ix->v_ent_off.p, ix->v_pair_len.p, ix->v_done.p, ix->entries.p,
                                         (u32)top_k, (u32)ix->p_tile_min_rows, (u32)ix->p_tile_queries,
@@ -1223,8 +1250,15 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
     float tile_ms = 0.f;
     u32 tiles = 0;
     u64 unique_bytes = 0;
-    tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved, &tile_ms, &tiles, &unique_bytes);
+    u64 flagged = 0, refined = 0;
+    float refine_ms = 0.f;
+    tile_scan_stats(ix->scan_ws, s, &tile_visits, &tile_pairs, &moved, &tile_ms, &tiles, &unique_bytes, &flagged, &refined, &refine_ms);
     ix->st.last_unique_bytes = unique_bytes;
+    ix->st.last_filter_flagged = (u32)std::min<u64>(flagged, 0xFFFFFFFFull);
+    ix->st.last_filter_rows = (u32)std::min<u64>(refined, 0xFFFFFFFFull);
+    ix->st.last_ms_refine = refine_ms;
+    ix->st.last_filter_used = ix->scan_ws.launched && ix->scan_ws.filtered ? 1u : 0u;
+    if (ix->scan_ws.launched && ix->scan_ws.filtered && flagged * 16 > tile_visits) ix->filter_backoff = 32;  // crowded keys: the exact kernel is cheaper
     u64 seq_moved = 0;
     if (ix->scan_ws.seq_launched) seq_tile_scan_stats(ix->scan_ws, s, &seq_moved, &tile_ms, &tiles);
     u64 qt_moved = 0;
@@ -2274,6 +2308,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "select_variant") ix->p_select_variant = value;  // per-visit top-n' of the gather path: 0 = block bitonic, 1 = one warp per visit, list in registers (default: 4.9 -> 0.38 ms on 2047-row visits, profiles/r02a_bench_manhattan_select*.json)
     else if (k == "quad_tile") ix->p_quad_tile = value;  // cosine / L2 visits outside the fused kernel (n' > 32): 1 = keys-only leaf-tile scan (default: 2.4x the gather path on top-100, profiles/r02a_bench_top100_quad*.json), 0 = one quad per pair
     else if (k == "flat_project") ix->p_flat_project = value;  // flat tables: 1 = dense projection + ballot packing (default), 0 = the generic tree walk
+    else if (k == "l2_filter") { ix->p_l2_filter = value; ix->filter_backoff = 0; }  // L2 / L2 squared through the dot-product filter + exact second pass: 0 off, 1 adaptive (default), 2 always
     else if (k == "p2p_queries") ix->p_p2p_queries = value;  // sliced search: 1 = query slices pushed into the peers' buffers over NVLink (CUDA IPC; default), 0 = NCCL
     else if (k == "single_exchange") ix->p_single_exchange = value;  // sliced search: 1 = query slices ride in the visit-record allgather (default), 0 = their own allgather first
     else if (k == "bm_stage_mb") ix->p_bm_stage_mb = value > 0 ? value : 1;  // bucket-sharded store build: staging area per direction, MiB (default 2048)

@@ -14,6 +14,38 @@ namespace zb {
 // budget n returns min(live, n), so which leaves are visited, and with which budget, depends only on the
 // query's sign bits and on the live leaf sizes.  The walker emits (leaf, n) records; scoring happens later.
 // =====================================================================================================
+// The walker's dot product: same fused multiply-add sequence per accumulator lane as quad_dot, but 12 chunks of the plane row
+// (and of the query, an L1 hit after the first node) are requested before the first is consumed.  A walk is a chain of
+// dependent nodes; a walker the count cascade sends through dozens of tiny leaves (Q1) visits hundreds of them, and while
+// the bulk of a batch's walkers is L2-bandwidth bound, such a walker finishes alone: its time is round trips to L2 per node.
+// With quad_dot's 4 chunks in flight a 768-float node costs 12 round trips and one such walker held a whole 8-GPU step back
+// by ~1 ms (profiles/r02q_trace_8gpu_all_ranks_peer_push.txt: the same (batch, rank) pairs in every run); now 4.
+__device__ __forceinline__ float quad_dot_deep(const float4* __restrict__ a, const float4* __restrict__ b, int chunks, int sub, unsigned mask) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int c = 0;
+    for (; c + 12 <= chunks; c += 12) {
+        float4 av[12], bv[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) av[i] = __ldg(a + (c + i) * 4 + sub);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) bv[i] = __ldg(b + (c + i) * 4 + sub);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) fma4(acc, av[i], bv[i]);
+    }
+    for (; c + 4 <= chunks; c += 4) {
+        float4 a0 = __ldg(a + (c + 0) * 4 + sub), a1 = __ldg(a + (c + 1) * 4 + sub);
+        float4 a2 = __ldg(a + (c + 2) * 4 + sub), a3 = __ldg(a + (c + 3) * 4 + sub);
+        float4 b0 = __ldg(b + (c + 0) * 4 + sub), b1 = __ldg(b + (c + 1) * 4 + sub);
+        float4 b2 = __ldg(b + (c + 2) * 4 + sub), b3 = __ldg(b + (c + 3) * 4 + sub);
+        fma4(acc, a0, b0);
+        fma4(acc, a1, b1);
+        fma4(acc, a2, b2);
+        fma4(acc, a3, b3);
+    }
+    for (; c < chunks; ++c) fma4(acc, __ldg(a + c * 4 + sub), __ldg(b + c * 4 + sub));
+    return quad_reduce16(acc, mask);
+}
+
 __global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const float* __restrict__ queries, u32 nq,
                                                         u32 top_k, u32 vpw, uint2* __restrict__ wvisits,
                                                         u32* __restrict__ wcounts, u32* __restrict__ overflow) {
@@ -36,8 +68,9 @@ __global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const floa
     for (;;) {
         int4 nd = f.nodes[cur];
         while (nd.x >= 0) {  // inner node: lsh.rs:333-338
-            float d = quad_dot(reinterpret_cast<const float4*>(f.coef + (size_t)nd.x * f.dimp), qv, f.chunks, sub, mask);
-            bool ab = above_from_dot(d, f.cst[nd.x]);
+            const float cst = f.cst[nd.x];
+            float d = quad_dot_deep(reinterpret_cast<const float4*>(f.coef + (size_t)nd.x * f.dimp), qv, f.chunks, sub, mask);
+            bool ab = above_from_dot(d, cst);
             if (sp < ZB_MAX_DEPTH + 2) {
                 stack_node[sp] = ab ? nd.y : nd.z;  // backup
                 stack_n[sp] = n;

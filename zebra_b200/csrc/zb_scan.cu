@@ -555,6 +555,9 @@ __host__ __device__ __forceinline__ float t3_bitsf(u32 b) {
 __device__ __forceinline__ float t3_fadd_ru(float a, float b) { return __fadd_ru(a, b); }
 __device__ __forceinline__ float t3_fmul_ru(float a, float b) { return __fmul_ru(a, b); }
 __device__ __forceinline__ float t3_fmaf(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float t3_fsub(float a, float b) { return __fsub_rn(a, b); }
+typedef float4 T3F4;
+__device__ __forceinline__ T3F4 t3_ld_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ u64 t3_pk2(float lo, float hi) { return pk2(lo, hi); }
 __device__ __forceinline__ void t3_upk2(u64 v, float& lo, float& hi) { upk2(v, lo, hi); }
 #ifndef T3_ASM_ORDER
@@ -606,6 +609,12 @@ template <int METRIC, int KR>
 __global__ void __launch_bounds__(T3_THREADS, 1) tile_scan3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
     extern __shared__ __align__(1024) unsigned char smem3[];
     t3_body<METRIC, 0, KR>(tmap, f, tp, smem3);
+}
+// Second pass of the dot-product filter (METRIC 3 of the kernel above): exact keys of every visit's candidates, one warp per visit.
+#define RF_THREADS 256
+template <int METRIC>
+__global__ void __launch_bounds__(RF_THREADS) refine_visits_kernel(ForestView f, T3RefineParams rp) {
+    t3_refine_warp<METRIC>(f, rp, (int)(threadIdx.x & 31u));
 }
 // Flat-table projection on the same skeleton (MODE 1): tmap covers the INPUT rows, tp.queries the plane coefficients.
 __global__ void __launch_bounds__(T3_THREADS, 1) project3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
@@ -716,6 +725,44 @@ void launch_rinv(const float* d_x, u64 n, int dimp, double* d_out, cudaStream_t 
     rinv_kernel<<<(u32)((n + 31) / 32), 128, 0, s>>>(d_x, n, dimp, d_out);
 }
 
+// canonical squared norms in f32 (one quad per vector): what METRIC 3 of the third-generation scan adds to -2 a.q
+__global__ void __launch_bounds__(128) n2_kernel(const float* __restrict__ x_, u64 n, int dimp, float* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * 32ull + (threadIdx.x >> 2);
+    if (i >= n) return;
+    const int sub = threadIdx.x & 3;
+    const float4* x = reinterpret_cast<const float4*>(x_ + i * dimp);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < dimp / 16; ++c) {
+        float4 v = x[c * 4 + sub];
+        fma4(acc, v, v);
+    }
+    float sum = quad_reduce16(acc, quad_mask());
+    if (sub == 0) out[i] = sum;
+}
+void launch_n2(const float* d_x, u64 n, int dimp, float* d_out, cudaStream_t s) {
+    if (!n) return;
+    n2_kernel<<<(u32)((n + 31) / 32), 128, 0, s>>>(d_x, n, dimp, d_out);
+}
+// largest usable squared norm of every leaf (one warp per leaf): the leaf's share of the filter's error bound
+__global__ void __launch_bounds__(256) leaf_n2max_kernel(u32 nleaves, const long long* __restrict__ leaf_off, const u32* __restrict__ leaf_len,
+                                                         const float* __restrict__ n2, float* __restrict__ out) {
+    const u32 l = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (l >= nleaves) return;
+    const u32 lane = threadIdx.x & 31u, len = leaf_len[l];
+    const float* x = n2 + leaf_off[l];
+    float m = 0.f;
+    for (u32 i = lane; i < len; i += 32u) {
+        const float v = x[i];
+        if (v <= T3_N2_LIMIT && v > m) m = v;   // NaN and inf compare false
+    }
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[l] = m;
+}
+void launch_leaf_n2max(u32 nleaves, const long long* d_leaf_off, const u32* d_leaf_len, const float* d_n2, float* d_out, cudaStream_t s) {
+    if (!nleaves) return;
+    leaf_n2max_kernel<<<(nleaves + 7) / 8, 256, 0, s>>>(nleaves, d_leaf_off, d_leaf_len, d_n2, d_out);
+}
+
 static size_t ts_smem_bytes(int nst, int dimp) { return TS_TEAMS * ts_team_bytes(nst, dimp) + 1024; }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
@@ -758,6 +805,7 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
                u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
                u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s) {
     ws.launched = false;
+    ws.filtered = false;
     const u32 pace_window = tile_queries >> 9;  // knob: bits 9.. of tile_queries carry the pacing window (tests / ablations)
     const bool lpt_order = false;               // second generation: tiles stay in leaf order
     tile_queries &= 0xFF;
@@ -874,13 +922,16 @@ void tile_scan(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u3
 // Statistics of the last tile_scan launch (visits, scored pairs, bytes asked of HBM by design); call after the
 // stream has been synchronised.
 void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes, float* kernel_ms,
-                     u32* tiles, u64* unique_bytes) {
+                     u32* tiles, u64* unique_bytes, u64* flagged_visits, u64* refined_rows, float* refine_ms) {
     *tile_visits = *tile_pairs = *moved_bytes = *unique_bytes = 0;
     *kernel_ms = 0.f;
     *tiles = 0;
+    if (flagged_visits) *flagged_visits = 0;
+    if (refined_rows) *refined_rows = 0;
+    if (refine_ms) *refine_ms = 0.f;
     if (!ws.launched) return;
-    u64 h[4] = {0, 0, 0, 0};
-    ZB_CUDA(cudaMemcpyAsync(h, reinterpret_cast<u64*>(ws.counters.p + 4), 32, cudaMemcpyDeviceToHost, s));
+    u64 h[6] = {0, 0, 0, 0, 0, 0};
+    ZB_CUDA(cudaMemcpyAsync(h, reinterpret_cast<u64*>(ws.counters.p + 4), 48, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaMemcpyAsync(tiles, ws.ntiles_ptr, 4, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
     cudaEventElapsedTime(kernel_ms, ws.ev0, ws.ev1);
@@ -888,6 +939,11 @@ void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* t
     *tile_pairs = h[1];
     *moved_bytes = h[2];
     *unique_bytes = h[3];
+    if (ws.filtered) {
+        if (flagged_visits) *flagged_visits = h[4];
+        if (refined_rows) *refined_rows = h[5];
+        if (refine_ms) cudaEventElapsedTime(refine_ms, ws.ev1, ws.ev2);
+    }
 #ifdef ZB_SCAN_TIMING
     u64 t[8];
     ZB_CUDA(cudaMemcpy(t, reinterpret_cast<u64*>(ws.counters.p + 4) + 8, 64, cudaMemcpyDeviceToHost));
@@ -922,6 +978,7 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
                 u32 nq, u32 nv, const u32* v_leaf, const u32* v_np, const u32* v_q, const u32* v_ent_off, u64* v_pair_len,
                 u8* v_done, Entry* entries, u32 top_k, u32 min_rows, u32 tile_queries, u32 nleaves, cudaStream_t s) {
     ws.launched = false;
+    ws.filtered = false;
     int nst = 0, qcap = 0;
     const int kr = t3_kr(top_k);
     if (!nv || !nleaves || top_k < 1 || top_k > T3_KL * T3_KR_MAX || !t3_config(f.dimp, kr, &nst, &qcap)) return;
@@ -981,7 +1038,24 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
                                                                   ws.tile_leaf.p, ws.tile_first.p, ws.tile_cnt.p, f.leaf_len,
                                                                   (u64)f.dimp * 4ull, reinterpret_cast<u64*>(ws.counters.p + 4) + 3);
     }
-    T3Params tp;
+    // L2 / L2 squared with short lists: score through the dot product (half the FP32 work), exact second pass below
+    const bool filt = ws.l2_filter && (metric == 1 || metric == 2) && kr == 1 && top_k <= ZB_L2_FILTER_MAX_K && bm.n2 && bm.leaf_n2max;
+    ws.filtered = filt;
+    T3Params tp{};
+    if (filt) {
+        ws.q_n2.ensure(nq ? nq : 1);
+        launch_n2(d_q, nq, f.dimp, ws.q_n2.p, s);
+        ws.cand.ensure((size_t)nv * T3_KL);
+        ws.cand_cut.ensure(nv);
+        ws.cand_flag.ensure(nv);
+        tp.bm_n2 = bm.n2;
+        tp.q_n2 = ws.q_n2.p;
+        tp.leaf_n2max = bm.leaf_n2max;
+        tp.ecoef = (float)(4 * f.chunks + 32) * 5.9604645e-8f * 1.01f;
+        tp.cand = ws.cand.p;
+        tp.cand_cut = ws.cand_cut.p;
+        tp.cand_flag = ws.cand_flag.p;
+    }
     tp.tile_leaf = ws.tile_leaf.p;
     tp.tile_first = ws.tile_first.p;
     tp.tile_count = ws.tile_cnt.p;
@@ -1014,7 +1088,8 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
         ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, T3_THREADS, smem, s>>>(tmap, f, tp);
     };
-    if (kr == 1) {
+    if (filt) launch(tile_scan3_kernel<3, 1>);
+    else if (kr == 1) {
         if (metric == 0) launch(tile_scan3_kernel<0, 1>);
         else if (metric == 1) launch(tile_scan3_kernel<1, 1>);
         else launch(tile_scan3_kernel<2, 1>);
@@ -1027,6 +1102,35 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
     ZB_CUDA(cudaEventRecord(ws.ev1, s));
     ws.launched = true;
     ws.launches = 7;
+    if (filt) {
+        T3RefineParams rp{};
+        rp.bm_rows = bm.rows;
+        rp.bm_tomb = bm.tomb;
+        rp.queries = d_q;
+        rp.order = ws.order.p;
+        rp.nvisits = ws.leaf_start.p + nleaves;   // the exclusive scan's total: visits the fused kernel took
+        rp.v_leaf = v_leaf;
+        rp.v_np = v_np;
+        rp.v_q = v_q;
+        rp.v_ent_off = v_ent_off;
+        rp.cand = ws.cand.p;
+        rp.cand_cut = ws.cand_cut.p;
+        rp.cand_flag = ws.cand_flag.p;
+        rp.gthr = ws.gthr.p;
+        rp.q_n2 = ws.q_n2.p;
+        rp.leaf_n2max = bm.leaf_n2max;
+        rp.ecoef = tp.ecoef;
+        rp.entries = entries;
+        rp.work_counter = ws.counters.p + 1;
+        rp.stats = tp.stats;
+        const int rgrid = sms * 6;   // 48 warps per SM: the pass is a latency-bound gather of ~10 rows per visit
+        if (metric == 1) refine_visits_kernel<1><<<rgrid, RF_THREADS, 0, s>>>(f, rp);
+        else refine_visits_kernel<2><<<rgrid, RF_THREADS, 0, s>>>(f, rp);
+        ZB_CUDA(cudaGetLastError());
+        if (!ws.ev2) ZB_CUDA(cudaEventCreate(&ws.ev2));
+        ZB_CUDA(cudaEventRecord(ws.ev2, s));
+        ws.launches = 9;   // + the queries' norms and the second pass
+    }
 }
 
 // ---- flat-table projection on the third-generation skeleton (t3_body MODE 1) ----

@@ -9,6 +9,13 @@ struct ScanWorkspace {
     DBuf<u32> leaf_count, leaf_start, leaf_cursor, tile_per_leaf, tile_start, order, tile_leaf, tile_first, tile_cnt;
     DBuf<u32> counters, tile_prog;
     DBuf<u64> gthr;
+    // dot-product filter for L2 / L2 squared (METRIC 3 of the third-generation kernel + refine_visits_kernel)
+    DBuf<float> q_n2, cand_cut;
+    DBuf<u64> cand;
+    DBuf<u8> cand_flag;
+    bool l2_filter = false;      // in: the caller allows the filter for this batch;  filtered: the last launch used it
+    bool filtered = false;
+    cudaEvent_t ev2 = nullptr;   // after the second pass
     DBuf<long long> pj_off;   // project3: first row of every row range
     DBuf<u8> tmp, sort_tmp;
     DBuf<u32> sort_key[2], sort_val[2];   // tile order: leaves sorted by cost
@@ -26,6 +33,8 @@ struct BucketMajor {
     const float* rows = nullptr;    // [positions][dimp]
     const double* rinv = nullptr;   // [positions] 1/sqrt(|row|^2), f64 (cosine only)
     const u32* tomb = nullptr;      // bit per position
+    const float* n2 = nullptr;      // [positions] canonical |row|^2, f32 (L2 / L2 squared: the dot-product filter)
+    const float* leaf_n2max = nullptr;  // [leaves] largest usable n2 of the leaf
     const void* tmap = nullptr;     // host copy of the CUtensorMap (128 bytes) over `rows`, box = 48 floats x 128 rows
     const void* tmap3 = nullptr;    // the same tensor with a 48 floats x 64 rows box (third-generation scan)
     u64 positions = 0;
@@ -37,6 +46,10 @@ int tile_scan_box_floats(int generation);   // K slice of a ring stage, in float
 // True when the tile kernel can serve this shape (top_k <= 32, query block + ring fit in shared memory).
 bool tile_scan_supported(int dimp, u32 top_k);
 void launch_rinv(const float* d_x, u64 n, int dimp, double* d_out, cudaStream_t s);
+void launch_n2(const float* d_x, u64 n, int dimp, float* d_out, cudaStream_t s);
+void launch_leaf_n2max(u32 nleaves, const long long* d_leaf_off, const u32* d_leaf_len, const float* d_n2, float* d_out, cudaStream_t s);
+// Largest top_k the dot-product filter serves (its 32-entry candidate lists need slack above n').
+#define ZB_L2_FILTER_MAX_K 16
 
 // Handles every visit whose leaf holds at least `min_rows` rows: groups those visits by leaf, and for each
 // (leaf, tile of <= tile_queries queries) streams the leaf's rows once through shared memory, scores them
@@ -57,7 +70,7 @@ bool project3_supported(int dimp);
 void project3(ScanWorkspace& ws, const float* d_rows, u64 n, const float* d_coef, const float* d_cst, int H, int dimp, u8* d_sign, int Hp,
               cudaStream_t s);
 void tile_scan_stats(ScanWorkspace& ws, cudaStream_t s, u64* tile_visits, u64* tile_pairs, u64* moved_bytes, float* kernel_ms,
-                     u32* tiles, u64* unique_bytes);
+                     u32* tiles, u64* unique_bytes, u64* flagged_visits = nullptr, u64* refined_rows = nullptr, float* refine_ms = nullptr);
 
 // The scalar metrics (zb_metric 3..11): every visit with pairs to score, grouped by leaf into (leaf, <= 8 queries) tiles;
 // one thread folds a row against the tile's queries and writes the keys into the gather path's pair_key layout

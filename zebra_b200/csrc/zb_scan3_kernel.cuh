@@ -85,14 +85,14 @@ struct T3Params {
     int nst;                // ring depth
     int qcap;               // query capacity of a tile (16, 8 or 4: what fits in shared memory next to a useful ring)
     int kr;                 // list entries per lane (the kernel's KR)
-    // METRIC 3 (L2 / L2 squared through the dot-product filter, see t3_l2f_* below)
-    const float* bm_n2;     // [positions] canonical squared norm of every stored row
-    const float* q_n2;      // [nq] canonical squared norm of every query
-    float n2max;            // largest finite bm_n2 of the store: rows above it (or not finite) are always candidates
-    float ecoef;            // (4 chunks + 32) * 2^-24 * 1.01: |A - exact| <= ecoef * (|row|^2 + |query|^2), see DESIGN 3.1b
-    u32* cand;              // [visits][32][2]: ordered(A), position of the visit's 32 best rows by A
-    float* cand_cut;        // [visits] A-domain cutoff: every row of the exact top-n' has A <= cut
-    u8* cand_flag;          // [visits] 1: the 32-entry list may not hold every row below the cutoff (refine scans the leaf)
+    // METRIC 3 (L2 / L2 squared through the dot-product filter, see below and DESIGN 3.1b)
+    const float* bm_n2;        // [positions] canonical squared norm of every stored row
+    const float* q_n2;         // [nq] canonical squared norm of every query
+    const float* leaf_n2max;   // [leaves] largest usable bm_n2 of the leaf (rows above T3_N2_LIMIT or not finite are scanned exactly)
+    float ecoef;               // (4 chunks + 32) * 2^-24 * 1.01: |A - exact| <= ecoef * (|row|^2 + |query|^2)
+    u64* cand;                 // [visits][32]: ordered(A) | position << 32 of the visit's 32 best rows by A
+    float* cand_cut;           // [visits] A-domain cutoff: every row of the exact top-n' has A <= cut
+    u8* cand_flag;             // [visits] 1: the list cannot stand for the leaf (refine scans the leaf exactly)
     // projection mode (MODE == 1, zb_index_hash on flat tables): "leaves" are row ranges of the input, "queries" are planes
     // (tp.queries = plane coefficients, order / v_q are not read: tile slot q is plane tile_first + q)
     const float* pj_cst;    // [planes] constants
@@ -112,7 +112,7 @@ __host__ __device__ __forceinline__ T3Layout t3_layout(int nst, int dimp, int qc
     o = (o + 127u) & ~127u;
     l.sums = o; o += 2u * (u32)qcap * T3_RB * 4u;               // [2][qcap][64] f32: finished sums of a row block, double buffered
     l.lists = o; o += (u32)qcap * 3u * (u32)kr * T3_KL * 4u;    // [qcap][3][kr][32] u32: key lo, key hi, position of entry lane * kr + r
-    l.meta = o; o += (u32)qcap * 3u * 4u;                       // [3][qcap] u32: visit, n', query of every tile slot
+    l.meta = o; o += (u32)qcap * 5u * 4u;                       // [5][qcap] u32: visit, n', query of every tile slot; METRIC 3: |q|^2, Eq (f32 bits)
     o = (o + 15u) & ~15u;
     l.info = o; o += 2u * (u32)sizeof(T3TileInfo);
     l.bars = o; o += (2u * T3_MAX_STAGES + 8u) * 8u;            // full[8], empty[8], ifull[2], qfull, qempty, sfull[2], sempty[2]
@@ -153,11 +153,18 @@ __device__ __forceinline__ u64 t3_cos_bits_rinv(float ab_, double ra, double rb)
 // ---- METRIC 3: L2 / L2 squared through the dot-product filter ----------------------------------------------------------
 // sum (a - b)^2 costs two FP32 operations per element, a dot product one: at 768 dimensions and ~12 queries per leaf the
 // exact scan is FP32-issue bound (2.33 ms floor per config-2 batch against 1.88 ms of HBM).  The fused kernel therefore scores
-// A = (|a|^2 + |q|^2) - 2 a.q from the canonical dot product and precomputed canonical norms, which differs from the EXACT
-// canonical f32 value D_c (what the reference's simsimd kernel returns) by at most E = ecoef * (|a|^2 + |q|^2) (forward error
-// of the two accumulations, derivation in DESIGN 3.1b), keeps the 32 best rows by A per visit, and a second pass
-// (refine_visits_kernel) evaluates D_c -- same order of operations as METRIC 1 / 2 -- only for rows with
-// A <= A_(n') + 2 E, which provably contain the exact top-n'.  Keys, ids and ties are therefore bit-identical to the exact scan.
+// A = (|a|^2 + |q|^2) - 2 a.q from the canonical dot product and precomputed canonical norms.  A differs from the EXACT
+// canonical f32 value D_c (what the reference's simsimd kernel returns, what METRIC 1 / 2 compute) by at most
+// Eq = ecoef * (n2max(leaf) + |q|^2) for every row of the leaf (forward error of the two accumulations, derivation in DESIGN
+// 3.1b; the same bound for all rows of a leaf, so ordering by A is ordering by A -+ Eq).  The kernel keeps the 32 best rows
+// by A per visit; the n' rows with the smallest A have D_c <= A_(n') + Eq, so the n'-th smallest D_c is at most that and every
+// row of the exact top-n' has A <= A_(n') + 2 Eq =: cut.  A second pass (t3_refine_warp) evaluates D_c -- the operation order
+// of METRIC 1 / 2 -- for the listed rows with A <= cut and sorts them by (key, position): keys, ids and ties are
+// bit-identical to the exact scan.  Where the list cannot stand for the leaf (more than 32 rows under the cut, rows whose
+// norms are not finite or so large that a sum may overflow) the visit is flagged and the second pass scans its leaf exactly.
+// The bound shared by a query's visits (gthr) holds, for this metric, ordered(G) with G >= the query's final k-th D_c
+// (G = A_(n') + Eq of a full list): a row with A > G + Eq cannot reach the final top-k.
+#define T3_N2_LIMIT 1e37f    // |row|^2 + |query|^2 above this: some sum may overflow, the row is scored exactly
 // Float <-> unsigned with the same order (any non-NaN float).
 __host__ __device__ __forceinline__ u32 t3_ford(float x) {
     u32 b = t3_fbits(x);
@@ -439,19 +446,20 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
             const u32 gq = s_meta[2 * tp.qcap + q];
             const float s_lo = sums[(size_t)q * T3_RB + r_lo], s_hi = sums[(size_t)q * T3_RB + r_hi];
             u64 k_lo = ZB_SENTINEL, k_hi = ZB_SENTINEL;
-            float Eq = 0.f;   // METRIC 3: this query's error bound on this store (uniform over the rows: ordering by A = ordering by A -+ Eq)
+            float Eq = 0.f;   // METRIC 3: the error bound of this (leaf, query)
             if (METRIC == 3) {
-                const float n2q = tp.q_n2[gq];
-                Eq = t3_fadd_ru(t3_fmul_ru(tp.ecoef, t3_fadd_ru(tp.n2max, n2q)), 1e-37f);
-                // the shared bound holds an upper bound G of the query's final k-th exact value: a row with A - Eq > G is out
+                const float n2q = t3_bitsf(s_meta[3 * tp.qcap + q]);
+                Eq = t3_bitsf(s_meta[4 * tp.qcap + q]);
+                // the shared bound holds ordered(G), G >= the query's final k-th exact value: a row with A > G + Eq is out
                 if (gbound[e] != ZB_SENTINEL) {
                     const u64 gf = (u64)t3_ford(t3_fadd_ru(t3_funord((u32)gbound[e]), Eq));
                     if (gf < thr[e]) thr[e] = gf;
                 }
-                const float a_lo = t3_fmaf(-2.0f, s_lo, t3_fadd(n2_lo, n2q)), a_hi = t3_fmaf(-2.0f, s_hi, t3_fadd(n2_hi, n2q));
-                // rows whose norm is not a finite number within the store's bound, or whose A is NaN: always candidates (key 0)
-                if (r_lo < nrows) k_lo = (n2_lo <= tp.n2max && a_lo == a_lo) ? (u64)t3_ford(a_lo) : 0ull;
-                if (r_hi < nrows) k_hi = (n2_hi <= tp.n2max && a_hi == a_hi) ? (u64)t3_ford(a_hi) : 0ull;
+                const float w_lo = t3_fadd(n2_lo, n2q), w_hi = t3_fadd(n2_hi, n2q);
+                const float a_lo = t3_fmaf(-2.0f, s_lo, w_lo), a_hi = t3_fmaf(-2.0f, s_hi, w_hi);
+                // rows whose sums may have overflowed (or are not numbers): key 0, always listed first -> the visit is flagged
+                if (r_lo < nrows) k_lo = (w_lo <= T3_N2_LIMIT && a_lo == a_lo) ? (u64)t3_ford(a_lo) : 0ull;
+                if (r_hi < nrows) k_hi = (w_hi <= T3_N2_LIMIT && a_hi == a_hi) ? (u64)t3_ford(a_hi) : 0ull;
             } else if (gbound[e] < thr[e]) thr[e] = gbound[e];
             if (METRIC == 3) {
             } else if (METRIC == 0) {
@@ -527,8 +535,18 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
             thr[e] = th;
             // publish: a full list of n' == top_k distinct rows bounds the query's final k-th best
             if (METRIC == 3) {
-                // th = ordered(A_(n') + 2 Eq) once n' rows are listed; the exact values of those n' rows are <= A_(n') + Eq <= th's value
-                if (lane == 0 && np == (int)tp.top_k && th != thr0 && th < gbound[e]) t3_atomic_min_u64(tp.gthr + gq, th);
+                // the n' listed rows have exact values <= A_(n') + Eq (unless a row without a usable A, key 0, is among them)
+                if (np == (int)tp.top_k) {
+                    u64 tk = Lk[0];
+#pragma unroll
+                    for (int r = 1; r < KR; ++r)
+                        if (r == tr) tk = Lk[r];
+                    const u64 kn = t3_shfl64(tk, tl);
+                    if (lane == 0 && kn != ZB_SENTINEL && Lk[0] != 0ull) {
+                        const u64 g = (u64)t3_ford(t3_fadd_ru(t3_funord((u32)kn), Eq));
+                        if (g < gbound[e]) t3_atomic_min_u64(tp.gthr + gq, g);
+                    }
+                }
             } else if (lane == 0 && np == (int)tp.top_k && th < gbound[e]) t3_atomic_min_u64(tp.gthr + gq, th);
             __syncwarp();
         }
@@ -875,7 +893,13 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
                 const u32 visit = tp.order[inf.first + q];
                 s_meta[q] = visit;
                 s_meta[tp.qcap + q] = tp.v_np[visit];
-                s_meta[2 * tp.qcap + q] = tp.v_q[visit];
+                const u32 gq = tp.v_q[visit];
+                s_meta[2 * tp.qcap + q] = gq;
+                if (METRIC == 3) {
+                    const float n2q = tp.q_n2[gq];
+                    s_meta[3 * tp.qcap + q] = t3_fbits(n2q);
+                    s_meta[4 * tp.qcap + q] = t3_fbits(t3_fadd_ru(t3_fmul_ru(tp.ecoef, t3_fadd_ru(tp.leaf_n2max[inf.leaf], n2q)), 1e-37f));
+                }
             }
         }
 #pragma unroll
@@ -900,19 +924,16 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
             const u32 v = s_meta[q];
             const int np = (int)s_meta[tp.qcap + q];
             const u32* lst = s_lists + (size_t)q * 3 * KR * T3_KL;
-            if (METRIC == 3) {  // the visit's 32 best rows by A, the cutoff below which the exact top-n' lies, the overflow flag
+            if (METRIC == 3) {  // the visit's 32 best rows by A, the cutoff below which the exact top-n' lies, the flag
                 const u64 k = ((u64)lst[KR * T3_KL + lane] << 32) | lst[lane];
                 const u32 p = lst[2 * KR * T3_KL + lane];
-                tp.cand[((size_t)v * T3_KL + lane) * 2] = (u32)k;
-                tp.cand[((size_t)v * T3_KL + lane) * 2 + 1] = k == ZB_SENTINEL ? T3_NOPOS : p;
-                const u64 kn = t3_shfl64(k, np - 1), k31 = t3_shfl64(k, T3_KL - 1);
+                tp.cand[(size_t)v * T3_KL + lane] = (u64)(u32)k | ((u64)(k == ZB_SENTINEL ? T3_NOPOS : p) << 32);
+                const u64 kn = t3_shfl64(k, np - 1), k31 = t3_shfl64(k, T3_KL - 1), k0 = t3_shfl64(k, 0);
                 if (lane == 0) {
-                    const float n2q = tp.q_n2[s_meta[2 * tp.qcap + q]];
-                    const float Eq = t3_fadd_ru(t3_fmul_ru(tp.ecoef, t3_fadd_ru(tp.n2max, n2q)), 1e-37f);
+                    const float Eq = t3_bitsf(s_meta[4 * tp.qcap + q]);
                     float cut = t3_bitsf(0x7F800000u);  // +inf: fewer than n' rows listed, all of them are candidates
-                    bool over = false;
-                    if (kn == 0ull) over = true;         // n' or more rows without a usable A: the leaf is scanned exactly
-                    else if (kn != ZB_SENTINEL) {
+                    bool over = k0 == 0ull;             // a row without a usable A: the leaf is scanned exactly
+                    if (!over && kn != ZB_SENTINEL) {
                         cut = t3_fadd_ru(t3_funord((u32)kn), t3_fadd_ru(Eq, Eq));
                         over = !(cut == cut) || (k31 != ZB_SENTINEL && (u32)k31 <= t3_ford(cut));
                     }
@@ -935,6 +956,145 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
             }
         }
         __syncwarp();  // the slots' shared-memory state may be re-initialised for the next tile
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Second pass of METRIC 3 (refine_visits_kernel): one warp per visit the fused kernel scored through the dot-product filter.
+// The warp evaluates the EXACT canonical sum of (a - b)^2 -- one quad per row, thread `sub` of the quad keeps accumulator
+// lanes 4 sub .. 4 sub + 3, folds by xor 2, xor 1, (r0 + r1) + (r2 + r3): the order of zb_device.cuh -- for the visit's
+// candidates (listed rows with A <= cut and A <= G + Eq), or for every live row of the leaf when the visit is flagged,
+// and keeps the n' smallest (key, position) in a list of one entry per lane: what METRIC 1 / 2 write for the visit.
+// Visits are handed out through one counter (flagged visits take ~100 times longer than the others).
+// ------------------------------------------------------------------------------------------------------------------
+struct T3RefineParams {
+    const float* bm_rows;      // [positions][dimp]
+    const u32* bm_tomb;
+    const float* queries;      // [nq][dimp]
+    const u32* order;          // the fused kernel's visits, grouped by leaf
+    const u32* nvisits;        // device scalar: how many
+    const u32* v_leaf;
+    const u32* v_np;
+    const u32* v_q;
+    const u32* v_ent_off;
+    const u64* cand;
+    const float* cand_cut;
+    const u8* cand_flag;
+    const u64* gthr;
+    const float* q_n2;
+    const float* leaf_n2max;
+    float ecoef;
+    Entry* entries;
+    u32* work_counter;         // zeroed before launch
+    u64* stats;                // [4] flagged visits, [5] rows scored exactly
+};
+
+template <int METRIC>   // 1: L2 squared, 2: L2 (the key of the exact sum)
+__device__ __forceinline__ void t3_refine_warp(const ForestView& f, const T3RefineParams& rp, const int lane) {
+    const int sub = lane & 3, quad = lane >> 2;
+    const u32 nvis = *rp.nvisits;
+    for (;;) {
+        u32 i = 0;
+        if (lane == 0) i = atomicAdd(rp.work_counter, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nvis) break;
+        const u32 v = rp.order[i];
+        const u32 leaf = rp.v_leaf[v], gq = rp.v_q[v];
+        const int np = (int)rp.v_np[v];
+        const bool flagged = rp.cand_flag[v] != 0;
+        const u64 G = t3_ldcg_u64(rp.gthr + gq);
+        // exact-key filter: the n'-th key of the list so far, or the key of G (k distinct rows at or below it exist)
+        u64 th = ZB_SENTINEL;
+        if (G != ZB_SENTINEL) th = METRIC == 1 ? l2sq_bits(t3_funord((u32)G)) : l2_bits(t3_funord((u32)G));
+        const long long moff = f.leaf_off[leaf];
+        u32 nitems, cpos = T3_NOPOS;
+        unsigned cmask = 0;
+        if (flagged) nitems = f.leaf_len[leaf];
+        else {
+            const u64 c = rp.cand[(size_t)v * T3_KL + lane];
+            const u32 oa = (u32)c;
+            cpos = (u32)(c >> 32);
+            bool is = cpos != T3_NOPOS && oa <= t3_ford(rp.cand_cut[v]);
+            if (G != ZB_SENTINEL) {
+                const float Eq = t3_fadd_ru(t3_fmul_ru(rp.ecoef, t3_fadd_ru(rp.leaf_n2max[leaf], rp.q_n2[gq])), 1e-37f);
+                is = is && oa <= t3_ford(t3_fadd_ru(t3_funord((u32)G), Eq));
+            }
+            cmask = __ballot_sync(0xffffffffu, is);
+            nitems = (u32)__popc(cmask);
+        }
+        if (lane == 0) {
+            if (flagged) atomicAdd(&rp.stats[4], 1ull);
+            atomicAdd(&rp.stats[5], (u64)nitems);
+        }
+        u64 Lk = ZB_SENTINEL;   // entry `lane` of the list, sorted by (key, position)
+        u32 Lp = T3_NOPOS;
+        const float* qrow = rp.queries + (size_t)gq * f.dimp + 4 * sub;
+        unsigned rest = cmask;
+        for (u32 base = 0; base < nitems; base += 8) {
+            // the row of this quad in this round
+            u32 p = T3_NOPOS;
+            if (flagged) {
+                const u32 item = base + (u32)quad;
+                if (item < nitems) {
+                    p = (u32)(moff + item);
+                    if ((rp.bm_tomb[p >> 5] >> (p & 31)) & 1u) p = T3_NOPOS;   // tombstoned (D1)
+                }
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < 8 && rest; ++j) {   // the next eight listed candidates, in list order
+                    const int src = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    const u32 pp = __shfl_sync(0xffffffffu, cpos, src);
+                    if (quad == j) p = pp;
+                }
+            }
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            if (p != T3_NOPOS) {
+                const float* row = rp.bm_rows + (size_t)p * f.dimp + 4 * sub;
+#pragma unroll 4
+                for (int c = 0; c < f.chunks; ++c) {
+                    const T3F4 r = t3_ld_f4(row + c * 16), q = t3_ld_f4(qrow + c * 16);
+                    const float d0 = t3_fsub(r.x, q.x), d1 = t3_fsub(r.y, q.y), d2 = t3_fsub(r.z, q.z), d3 = t3_fsub(r.w, q.w);
+                    a0 = t3_fmaf(d0, d0, a0);
+                    a1 = t3_fmaf(d1, d1, a1);
+                    a2 = t3_fmaf(d2, d2, a2);
+                    a3 = t3_fmaf(d3, d3, a3);
+                }
+            }
+            a0 = t3_fadd(a0, __shfl_xor_sync(0xffffffffu, a0, 2));   // lane i + lane i + 8
+            a1 = t3_fadd(a1, __shfl_xor_sync(0xffffffffu, a1, 2));
+            a2 = t3_fadd(a2, __shfl_xor_sync(0xffffffffu, a2, 2));
+            a3 = t3_fadd(a3, __shfl_xor_sync(0xffffffffu, a3, 2));
+            a0 = t3_fadd(a0, __shfl_xor_sync(0xffffffffu, a0, 1));   // x[i] + x[i + 4]
+            a1 = t3_fadd(a1, __shfl_xor_sync(0xffffffffu, a1, 1));
+            a2 = t3_fadd(a2, __shfl_xor_sync(0xffffffffu, a2, 1));
+            a3 = t3_fadd(a3, __shfl_xor_sync(0xffffffffu, a3, 1));
+            const float ssum = t3_fadd(t3_fadd(a0, a1), t3_fadd(a2, a3));   // (r0 + r1) + (r2 + r3)
+            const u64 key = METRIC == 1 ? l2sq_bits(ssum) : l2_bits(ssum);
+            unsigned m = __ballot_sync(0xffffffffu, sub == 0 && p != T3_NOPOS && key <= th);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const u64 nk = t3_shfl64(key, src);
+                const u32 npos = __shfl_sync(0xffffffffu, p, src);
+                if (nk > th) continue;  // the filter tightened since the ballot
+                const unsigned mm = __ballot_sync(0xffffffffu, t3_kp_less(nk, npos, Lk, Lp));
+                const int ins = mm ? __ffs(mm) - 1 : 32;
+                if (ins >= np) continue;
+                const u64 upk = t3_shfl_up64(Lk);
+                const u32 upp = __shfl_up_sync(0xffffffffu, Lp, 1);
+                if (lane > ins) { Lk = upk; Lp = upp; }
+                else if (lane == ins) { Lk = nk; Lp = npos; }
+                const u64 lk = t3_shfl64(Lk, np - 1);
+                if (lk < th) th = lk;
+            }
+        }
+        const u32 e0 = rp.v_ent_off[v], e1 = rp.v_ent_off[v + 1];
+        if ((u32)lane < e1 - e0) {
+            Entry en{ZB_SENTINEL, ZB_SENTINEL};
+            if (lane < np && Lp != T3_NOPOS) en = Entry{Lk, f.ord[f.members[Lp]]};
+            rp.entries[e0 + lane] = en;
+        }
     }
 }
 

@@ -31,7 +31,8 @@ def main():
              (zo.L2, "L2Distance", 20000, 768, 512, 4, 10),            # BASELINE config 2 shape: tile kernel
              (zo.L2SQ, "L2SquaredDistance", 9000, 100, 256, 3, 25),    # dim not a multiple of 16
              (zo.COSINE, "CosineDistance", 24000, 768, 1024, 4, 10),   # BASELINE config 3 shape: cosine, bucket-sharded, tile kernel
-             (zo.COSINE, "CosineDistance", 16000, 384, 256, 4, 100)]   # BASELINE config 5 shape: 384-dim, deletes, top-100 (generic path)
+             (zo.COSINE, "CosineDistance", 16000, 384, 256, 4, 100),   # BASELINE config 5 shape: 384-dim, deletes, top-100 (generic path)
+             (zo.L2SQ, "L2SquaredDistance", 24000, 384, 1024, 4, 16)]  # L2 squared through the dot-product filter at its largest k
     for mid, mname, n, dim, mns, trees, k in cases:
         rng = np.random.default_rng(1234 + n)     # same data on every rank
         rows = clustered(rng, n, dim)
@@ -78,7 +79,9 @@ def main():
                 good = (np.array_equal(counts, ec) and all(np.array_equal(ords[q, :ec[q]], eo[q, :ec[q]]) and
                                                            np.array_equal(bits[q, :ec[q]], eb[q, :ec[q]]) for q in range(len(ec)))
                         and np.array_equal(keys, ek) and np.array_equal(depth, ed) and np.array_equal(leaf, el) and slice_ok)
-                print(f"[mgpu G={world}] {mname} n={n} dim={dim} leaf<{mns} trees={trees} k={k} {tag}: {'ok' if good else 'MISMATCH'}", flush=True)
+                st = ix.stats()
+                print(f"[mgpu G={world}] {mname} n={n} dim={dim} leaf<{mns} trees={trees} k={k} {tag} "
+                      f"(l2 filter {'on' if st['last_filter_used'] else 'off'}): {'ok' if good else 'MISMATCH'}", flush=True)
                 ok = ok and good
 
         check("bulk build")

@@ -368,7 +368,7 @@ def test_sharded_two_gpus_equals_oracle():
            "--master-port", "29517", os.path.join(root, "tests", "mgpu_parity.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count(": ok") == 17 and "MISMATCH" not in out.stdout
+    assert out.stdout.count(": ok") == 20 and "MISMATCH" not in out.stdout
 
 
 # ------------------------------------------------------------------------------------------ double-buffered uploads

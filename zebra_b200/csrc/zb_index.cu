@@ -118,6 +118,7 @@ struct zb_index {
     // ---- bucket-major store (search path): position p of the member array holds a copy of row members[p] ----
     DBuf<float> bm_rows;
     DBuf<double> bm_rinv, q_rinv;
+    DBuf<u32> w_tail;                   // plan walk: [0] count, then the walkers set aside for the tail kernel
     DBuf<float> bm_n2, bm_leaf_n2max;   // L2 / L2 squared: canonical |row|^2 per position, its usable maximum per leaf (the dot-product filter)
     int filter_backoff = 0;             // batches the filter sits out after one in which too many visits had to be rescanned exactly
     DBuf<u32> bm_tomb, slot_pos, d_leaf_tree;
@@ -189,7 +190,7 @@ struct zb_index {
     ScanWorkspace qt_ws;  // keys-only tile scan of the visits the fused kernel leaves (cosine / L2, n' > 32)
 
     // ---- knobs / stats ----
-    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 1, p_select_variant = 1, p_scan_gen = 3, p_bm_stage_mb = 2048, p_single_exchange = 1, p_p2p_queries = 1, p_l2_filter = 1;
+    int64_t p_tile_min_rows = 64, p_tile_queries = 0, p_use_tile_scan = 1, p_hash_variant = 0, p_classify_variant = 0, p_seq_tile = 1, p_seq_prefetch = 0, p_flat_project = 1, p_quad_tile = 1, p_select_variant = 1, p_scan_gen = 3, p_bm_stage_mb = 2048, p_single_exchange = 1, p_p2p_queries = 1, p_l2_filter = 1, p_plan_tail = 1;
     zb_stats st{};
 
     ForestView view() const {
@@ -1069,7 +1070,15 @@ static void search_device(zb_index* ix, u64 nq, const float* d_q, u64 top_k, u64
                 ZB_CUDA(cudaMemsetAsync(ix->w_visits.p + qn * T * ix->vpw, 0, (nqp - qn) * T * ix->vpw * sizeof(uint2), s));
                 ZB_CUDA(cudaMemsetAsync(ix->w_counts.p + qn * T, 0, (nqp - qn) * T * 4, s));
             }
-            launch_plan(f, d_q_mine, (u32)qn, (u32)top_k, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_flag.p, s);
+            // walkers whose first leaf cannot fill the budget (the count cascade goes on: few, but each a long chain of dependent
+            // nodes) go to the latency-optimised tail kernel -- unless the leaves are so small that every walker cascades
+            u32* tail = nullptr;
+            if (ix->p_plan_tail && ix->opt.max_node_size >= 4 * top_k) {
+                ix->w_tail.ensure(nwl + 2);
+                tail = ix->w_tail.p;
+            }
+            launch_plan(f, d_q_mine, (u32)qn, (u32)top_k, ix->vpw, ix->w_visits.p, ix->w_counts.p, ix->w_flag.p, tail, s);
+            if (tail) ix->st.last_total_launches += 1;
             ix->trace_mark("plan walk");
             if (sharded) {
                 ix->w_loc_off.ensure(nwl + 1);
@@ -2309,6 +2318,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "quad_tile") ix->p_quad_tile = value;  // cosine / L2 visits outside the fused kernel (n' > 32): 1 = keys-only leaf-tile scan (default: 2.4x the gather path on top-100, profiles/r02a_bench_top100_quad*.json), 0 = one quad per pair
     else if (k == "flat_project") ix->p_flat_project = value;  // flat tables: 1 = dense projection + ballot packing (default), 0 = the generic tree walk
     else if (k == "l2_filter") { ix->p_l2_filter = value; ix->filter_backoff = 0; }  // L2 / L2 squared through the dot-product filter + exact second pass: 0 off, 1 adaptive (default), 2 always
+    else if (k == "plan_tail") ix->p_plan_tail = value;  // plan walk: 1 = cascade walkers go to the latency-optimised tail kernel (default), 0 = one kernel
     else if (k == "p2p_queries") ix->p_p2p_queries = value;  // sliced search: 1 = query slices pushed into the peers' buffers over NVLink (CUDA IPC; default), 0 = NCCL
     else if (k == "single_exchange") ix->p_single_exchange = value;  // sliced search: 1 = query slices ride in the visit-record allgather (default), 0 = their own allgather first
     else if (k == "bm_stage_mb") ix->p_bm_stage_mb = value > 0 ? value : 1;  // bucket-sharded store build: staging area per direction, MiB (default 2048)

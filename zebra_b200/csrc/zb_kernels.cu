@@ -14,23 +14,31 @@ namespace zb {
 // budget n returns min(live, n), so which leaves are visited, and with which budget, depends only on the
 // query's sign bits and on the live leaf sizes.  The walker emits (leaf, n) records; scoring happens later.
 // =====================================================================================================
-// The walker's dot product: same fused multiply-add sequence per accumulator lane as quad_dot, but 12 chunks of the plane row
-// (and of the query, an L1 hit after the first node) are requested before the first is consumed.  A walk is a chain of
-// dependent nodes; a walker the count cascade sends through dozens of tiny leaves (Q1) visits hundreds of them, and while
-// the bulk of a batch's walkers is L2-bandwidth bound, such a walker finishes alone: its time is round trips to L2 per node.
-// With quad_dot's 4 chunks in flight a 768-float node costs 12 round trips and one such walker held a whole 8-GPU step back
-// by ~1 ms (profiles/r02q_trace_8gpu_all_ranks_peer_push.txt: the same (batch, rank) pairs in every run); now 4.
-__device__ __forceinline__ float quad_dot_deep(const float4* __restrict__ a, const float4* __restrict__ b, int chunks, int sub, unsigned mask) {
+// The dot product of the tail kernel (walkers the count cascade sends past their first leaf).  A walk is a chain of dependent
+// nodes; a walker that Q1 sends through dozens of tiny leaves visits hundreds of them, long after the bulk of the batch
+// (L2-bandwidth bound) has finished: alone on the machine its time is round trips to L2 per node, and with quad_dot's 4 chunks
+// in flight a 768-float node costs 12 of them -- one such walker held a whole 8-GPU step back by ~1 ms
+// (profiles/r02q_trace_8gpu_all_ranks_peer_push.txt: the same (batch, rank) pairs in every run).  Here 24 chunks of the plane
+// row are requested before the first is consumed.  ptxas, left alone, interleaves requests and FFMAs to save registers (the
+// first FFMA then stalls with 4-6 requests in flight), so the requests are `volatile` loads (kept in program order; they
+// bypass L1, which holds nothing of a deep node's plane anyway) and the head of every accumulator chain is made to depend
+// on the LAST request by or-ing in `bits & zero`.  Same fused multiply-add sequence per accumulator lane as quad_dot.
+__device__ __forceinline__ float quad_dot_tail(const float4* __restrict__ a, const float4* __restrict__ b, int chunks, int sub, unsigned mask,
+                                               const u32 zero /* 0, derived from a kernel argument: the compiler cannot know */) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int c = 0;
-    for (; c + 12 <= chunks; c += 12) {
-        float4 av[12], bv[12];
+    for (; c + 24 <= chunks; c += 24) {
+        float4 av[24];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) av[i] = __ldg(a + (c + i) * 4 + sub);
+        for (int i = 0; i < 24; ++i)
+            asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(av[i].x), "=f"(av[i].y), "=f"(av[i].z), "=f"(av[i].w) : "l"(a + (c + i) * 4 + sub));
+        const u32 dep = __float_as_uint(av[23].w) & zero;
+        av[0].x = __uint_as_float(__float_as_uint(av[0].x) | dep);
+        av[0].y = __uint_as_float(__float_as_uint(av[0].y) | dep);
+        av[0].z = __uint_as_float(__float_as_uint(av[0].z) | dep);
+        av[0].w = __uint_as_float(__float_as_uint(av[0].w) | dep);
 #pragma unroll
-        for (int i = 0; i < 12; ++i) bv[i] = __ldg(b + (c + i) * 4 + sub);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) fma4(acc, av[i], bv[i]);
+        for (int i = 0; i < 24; ++i) fma4(acc, av[i], __ldg(b + (c + i) * 4 + sub));   // the query: L1 hits
     }
     for (; c + 4 <= chunks; c += 4) {
         float4 a0 = __ldg(a + (c + 0) * 4 + sub), a1 = __ldg(a + (c + 1) * 4 + sub);
@@ -46,14 +54,14 @@ __device__ __forceinline__ float quad_dot_deep(const float4* __restrict__ a, con
     return quad_reduce16(acc, mask);
 }
 
-__global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const float* __restrict__ queries, u32 nq,
-                                                        u32 top_k, u32 vpw, uint2* __restrict__ wvisits,
-                                                        u32* __restrict__ wcounts, u32* __restrict__ overflow) {
-    const u32 w = blockIdx.x * 32u + (threadIdx.x >> 2);
-    const int sub = threadIdx.x & 3;
-    const unsigned mask = quad_mask();
-    const u32 nwalkers = nq * (u32)f.num_trees;
-    if (w >= nwalkers) return;
+// One walker.  TAIL == false (plan_walk_kernel): with `defer` set, a walker whose first leaf cannot fill its budget (the count
+// cascade goes on) is put on the tail list and left to plan_walk_tail_kernel, which walks it again from the root with
+// quad_dot_tail; returns without writing anything for it.
+template <bool TAIL>
+__device__ __forceinline__ void plan_walk_one(const ForestView& f, const float* __restrict__ queries, const u32 w, const int sub,
+                                              const unsigned mask, const u32 top_k, const u32 vpw, uint2* __restrict__ wvisits,
+                                              u32* __restrict__ wcounts, u32* __restrict__ overflow, u32* __restrict__ tail_list,
+                                              u32* __restrict__ tail_count) {
     const u32 q = w / (u32)f.num_trees;
     const u32 t = w - q * (u32)f.num_trees;
     const float4* qv = reinterpret_cast<const float4*>(queries + (size_t)q * f.dimp);
@@ -69,7 +77,8 @@ __global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const floa
         int4 nd = f.nodes[cur];
         while (nd.x >= 0) {  // inner node: lsh.rs:333-338
             const float cst = f.cst[nd.x];
-            float d = quad_dot_deep(reinterpret_cast<const float4*>(f.coef + (size_t)nd.x * f.dimp), qv, f.chunks, sub, mask);
+            const float4* plane = reinterpret_cast<const float4*>(f.coef + (size_t)nd.x * f.dimp);
+            float d = TAIL ? quad_dot_tail(plane, qv, f.chunks, sub, mask, top_k >> 31) : quad_dot(plane, qv, f.chunks, sub, mask);
             bool ab = above_from_dot(d, cst);
             if (sp < ZB_MAX_DEPTH + 2) {
                 stack_node[sp] = ab ? nd.y : nd.z;  // backup
@@ -85,6 +94,11 @@ __global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const floa
         }
         const int live = (int)f.leaf_plan[nd.w];
         const int r = live < n ? live : n;  // lsh.rs:307 / :329
+        if (!TAIL && tail_list && nvis == 0 && sp > 0 && r < n) {
+            // first leaf, budget not filled, backups exist (they all carry n = top_k > r): the walk goes on -> tail kernel
+            if (sub == 0) tail_list[atomicAdd(tail_count, 1u)] = w;
+            return;
+        }
         if (live > 0 && n > 0) {
             if (nvis < cap && sub == 0) wvisits[(size_t)w * vpw + 1 + nvis] = make_uint2((u32)nd.w, (u32)n);
             ++nvis;
@@ -111,11 +125,41 @@ __global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const floa
     }
 }
 
+__global__ void __launch_bounds__(128) plan_walk_kernel(ForestView f, const float* __restrict__ queries, u32 nq,
+                                                        u32 top_k, u32 vpw, uint2* __restrict__ wvisits,
+                                                        u32* __restrict__ wcounts, u32* __restrict__ overflow,
+                                                        u32* __restrict__ tail_list, u32* __restrict__ tail_count) {
+    const u32 w = blockIdx.x * 32u + (threadIdx.x >> 2);
+    const u32 nwalkers = nq * (u32)f.num_trees;
+    if (w >= nwalkers) return;
+    plan_walk_one<false>(f, queries, w, (int)(threadIdx.x & 3), quad_mask(), top_k, vpw, wvisits, wcounts, overflow, tail_list, tail_count);
+}
+// The walkers the main kernel set aside, one quad each, a quad taking list entries in a grid-stride loop.
+__global__ void __launch_bounds__(128, 1) plan_walk_tail_kernel(ForestView f, const float* __restrict__ queries, u32 top_k, u32 vpw,
+                                                                uint2* __restrict__ wvisits, u32* __restrict__ wcounts,
+                                                                u32* __restrict__ overflow, const u32* __restrict__ tail_list,
+                                                                const u32* __restrict__ tail_count) {
+    const u32 n = *tail_count;
+    const unsigned mask = quad_mask();
+    for (u32 i = blockIdx.x * 32u + (threadIdx.x >> 2); i < n; i += gridDim.x * 32u)
+        plan_walk_one<true>(f, queries, tail_list[i], (int)(threadIdx.x & 3), mask, top_k, vpw, wvisits, wcounts, overflow, nullptr, nullptr);
+}
+
+// tail_list: [walkers + 1] u32 scratch, element 0 is the counter; pass nullptr to keep every walker in the main kernel (what a
+// forest whose leaves cannot hold top_k rows wants: there every walker cascades).
 void launch_plan(const ForestView& f, const float* d_queries, u32 nq, u32 top_k, u32 vpw, uint2* d_wvisits,
-                 u32* d_wcounts, u32* d_overflow, cudaStream_t s) {
+                 u32* d_wcounts, u32* d_overflow, u32* d_tail_list, cudaStream_t s) {
     u32 nwalkers = nq * (u32)f.num_trees;
     if (!nwalkers) return;
-    plan_walk_kernel<<<(nwalkers + 31) / 32, 128, 0, s>>>(f, d_queries, nq, top_k, vpw, d_wvisits, d_wcounts, d_overflow);
+    if (d_tail_list) cudaMemsetAsync(d_tail_list, 0, 4, s);
+    plan_walk_kernel<<<(nwalkers + 31) / 32, 128, 0, s>>>(f, d_queries, nq, top_k, vpw, d_wvisits, d_wcounts, d_overflow,
+                                                          d_tail_list ? d_tail_list + 1 : nullptr, d_tail_list);
+    if (d_tail_list) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        plan_walk_tail_kernel<<<sms * 2, 128, 0, s>>>(f, d_queries, top_k, vpw, d_wvisits, d_wcounts, d_overflow, d_tail_list + 1, d_tail_list);
+    }
 }
 
 // Visit records -> flat visit arrays.  A visit the fused tile kernel will take (tile_on, leaf holds >= min_rows rows here,

@@ -7,12 +7,17 @@
 // schedule of the persistent kernel.  tests/test_scan3.py feeds it leaves, tombstones and visits and compares every
 // entry the kernel writes with the oracle.
 #include <math.h>
+#include <stdio.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 #include <cmath>
 #include <stdlib.h>
 #include <stdint.h>
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <barrier>
 #include <condition_variable>
 #include <deque>
@@ -33,6 +38,18 @@
 struct Dim3 { unsigned x, y, z; };
 static thread_local Dim3 emu_threadIdx;
 #define threadIdx emu_threadIdx
+
+// A crash inside the emulation (abort of a protocol check, a C++ exception in a thread) says where it came from.
+static void emu_abort_handler(int sig) {
+    void* frames[48];
+    const int n = backtrace(frames, 48);
+    const char msg[] = "[scan3_emu] fatal signal, backtrace:\n";
+    (void)!write(2, msg, sizeof msg - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+static const int emu_handler_installed = (signal(SIGABRT, emu_abort_handler), signal(SIGSEGV, emu_abort_handler), 0);
 
 namespace zb {
 typedef unsigned long long u64;
@@ -61,14 +78,31 @@ struct WarpBox {
     std::barrier<> bar{32};
 };
 static std::vector<std::unique_ptr<WarpBox>> emu_warps;
-#define __syncthreads() emu_block_bar->arrive_and_wait()
-static inline void __syncwarp() { emu_warps[threadIdx.x >> 5]->bar.arrive_and_wait(); }
+// where every emulated thread currently waits (0: running; 1: mbarrier; 2: team barrier; 3: block barrier; 4: warp barrier),
+// printed by the deadlock watchdog
+static volatile unsigned emu_where[1024][3];
+static inline void emu_at(unsigned code, unsigned a = 0, unsigned b = 0) { emu_where[threadIdx.x][0] = code; emu_where[threadIdx.x][1] = a; emu_where[threadIdx.x][2] = b; }
+static void emu_dump_where(unsigned nthreads) {
+    for (unsigned w = 0; w * 32 < nthreads; ++w) {
+        fprintf(stderr, "[scan3_emu]   warp %2u:", w);
+        for (unsigned l = 0; l < 32; ++l) {
+            const unsigned t = w * 32 + l;
+            if (l == 0 || emu_where[t][0] != emu_where[t - 1][0] || emu_where[t][1] != emu_where[t - 1][1])
+                fprintf(stderr, " [lane %u: %u %u/%u]", l, emu_where[t][0], emu_where[t][1], emu_where[t][2]);
+        }
+        fprintf(stderr, "\n");
+    }
+}
+#define __syncthreads() (emu_at(3), emu_block_bar->arrive_and_wait(), emu_at(0))
+static inline void __syncwarp() { emu_at(4, 1); emu_warps[threadIdx.x >> 5]->bar.arrive_and_wait(); emu_at(0); }
 static inline u64 emu_exchange(u64 v, int src) {
     WarpBox& w = *emu_warps[threadIdx.x >> 5];
     w.slot[threadIdx.x & 31] = v;
+    emu_at(4, 2);
     w.bar.arrive_and_wait();
     const u64 r = w.slot[src & 31];
     w.bar.arrive_and_wait();
+    emu_at(0);
     return r;
 }
 static inline u32 f2u(float f) { u32 u; memcpy(&u, &f, 4); return u; }
@@ -83,10 +117,12 @@ static inline u32 __shfl_up_sync(unsigned, u32 v, int d) {
 static inline unsigned __ballot_sync(unsigned, bool p) {
     WarpBox& w = *emu_warps[threadIdx.x >> 5];
     w.slot[threadIdx.x & 31] = p ? 1 : 0;
+    emu_at(4, 3);
     w.bar.arrive_and_wait();
     unsigned r = 0;
     for (int i = 0; i < 32; ++i) r |= (unsigned)w.slot[i] << i;
     w.bar.arrive_and_wait();
+    emu_at(0);
     return r;
 }
 static inline int __ffs(unsigned m) { return m ? __builtin_ctz(m) + 1 : 0; }
@@ -111,14 +147,14 @@ static inline void mbar_init(u32 bar, u32 count) {
 static inline void mbar_arrive(u32 bar) {
     std::lock_guard<std::mutex> lk(emu_mbar_mu);
     MBar& b = emu_mbars.at(bar);
-    if (b.pending == 0) abort();  // more arrivals than the barrier expects: a protocol bug
+    if (b.pending == 0) { fprintf(stderr, "[scan3_emu] mbarrier %u: more arrivals than expected (thread %u)\n", bar, threadIdx.x); abort(); }  // a protocol bug
     b.pending--;
     mbar_check(b);
 }
 static inline void mbar_arrive_expect_tx(u32 bar, u32 bytes) {
     std::lock_guard<std::mutex> lk(emu_mbar_mu);
     MBar& b = emu_mbars.at(bar);
-    if (b.pending == 0) abort();
+    if (b.pending == 0) { fprintf(stderr, "[scan3_emu] mbarrier %u: expect_tx arrival beyond the count (thread %u)\n", bar, threadIdx.x); abort(); }
     b.tx += bytes;
     b.pending--;
     mbar_check(b);
@@ -131,12 +167,26 @@ static inline void mbar_complete_tx(u32 bar, u32 bytes) {
 }
 static std::atomic<long long> emu_spins{0};
 static inline void mbar_wait(u32 bar, u32 parity) {
+    std::chrono::steady_clock::time_point t0;
+    emu_at(1, bar, parity);
     for (long long n = 0;; ++n) {
         {
             std::lock_guard<std::mutex> lk(emu_mbar_mu);
-            if ((emu_mbars.at(bar).completed & 1) != (parity & 1)) return;
+            if ((emu_mbars.at(bar).completed & 1) != (parity & 1)) { emu_at(0); return; }
         }
-        if (n > 200000000LL) abort();  // deadlock
+        // deadlock watchdog by wall clock (a spin count says little with several hundred threads on a few cores)
+        if (n == 1000) t0 = std::chrono::steady_clock::now();
+        if (n > 1000 && (n & 0xFFFF) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) {
+            fprintf(stderr, "[scan3_emu] mbarrier %u parity %u: no progress for 60 s (thread %u)\n", bar, parity, threadIdx.x);
+            emu_dump_where(1024);
+            {
+                std::lock_guard<std::mutex> lk(emu_mbar_mu);
+                for (auto& kv : emu_mbars)
+                    fprintf(stderr, "[scan3_emu]   mbarrier %u: count %u pending %u tx %lld completed %llu\n", kv.first, kv.second.count, kv.second.pending,
+                            kv.second.tx, (unsigned long long)kv.second.completed);
+            }
+            abort();
+        }
         std::this_thread::yield();
     }
 }
@@ -230,7 +280,7 @@ static inline u64 t3_shfl_up64(u64 v) {
     const int lane = threadIdx.x & 31;
     return emu_exchange(v, lane == 0 ? 0 : lane - 1);
 }
-static inline void t3_team_sync(int team) { emu_team_bar[team]->arrive_and_wait(); }
+static inline void t3_team_sync(int team) { emu_at(2, (unsigned)team); emu_team_bar[team]->arrive_and_wait(); emu_at(0); }
 static inline void t3_fence_barrier_init() {}
 static inline void t3_setmaxnreg_dec() {}
 static inline void t3_setmaxnreg_inc() {}
@@ -286,7 +336,7 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
         CopyEngine dma;
         emu_dma = &dma;
         dma.start();
-        std::barrier<> bar(T3_THREADS), tb0(128), tb1(128);
+        std::barrier<> bar(T3_THREADS), tb0(T3_TEAM_THREADS), tb1(T3_TEAM_THREADS);
         emu_block_bar = &bar;
         emu_team_bar[0] = &tb0;
         emu_team_bar[1] = &tb1;
@@ -378,7 +428,7 @@ extern "C" __attribute__((visibility("default"))) int emu_project3(int blocks, i
         CopyEngine dma;
         emu_dma = &dma;
         dma.start();
-        std::barrier<> bar(T3_THREADS), tb0(128), tb1(128);
+        std::barrier<> bar(T3_THREADS), tb0(T3_TEAM_THREADS), tb1(T3_TEAM_THREADS);
         emu_block_bar = &bar; emu_team_bar[0] = &tb0; emu_team_bar[1] = &tb1;
         std::vector<std::thread> th;
         for (unsigned t = 0; t < T3_THREADS; ++t)

@@ -21,14 +21,15 @@ F32 = np.float32
 SENT = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
-@pytest.fixture(scope="module", params=[(3, 0), (3, 1), (2, 0)], ids=["kc3", "kc3-epilogue-warp", "kc2"])
+@pytest.fixture(scope="module", params=[(3, 0, 4), (3, 0, 8), (3, 1, 4), (2, 0, 4)], ids=["kc3", "kc3-8warps", "kc3-epilogue-warp", "kc2"])
 def emu(tmp_path_factory, request):
     """The build variants of the kernel body: T3_KC = 3 (the default: a stage's chunks straight-line) and 2 (operands
-    software-pipelined across stage boundaries); T3_EPW = 1 (a dedicated epilogue warp per team keeps the lists of n' <= 32)."""
-    kc, epw = request.param
-    out = str(tmp_path_factory.mktemp("s3") / f"libscan3_emu_kc{kc}_epw{epw}.so")
+    software-pipelined across stage boundaries); T3_EPW = 1 (a dedicated epilogue warp per team keeps the lists of n' <= 32);
+    T3_TWARPS = 8 (eight math warps per team, 8 rows of a block each: 640 threads)."""
+    kc, epw, tw = request.param
+    out = str(tmp_path_factory.mktemp("s3") / f"libscan3_emu_kc{kc}_epw{epw}_tw{tw}.so")
     subprocess.check_call(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
-                           f"-DT3_KC={kc}", f"-DT3_EPW={epw}", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out,
+                           f"-DT3_KC={kc}", f"-DT3_EPW={epw}", f"-DT3_TWARPS={tw}", "-g", "-rdynamic", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out,
                            os.path.join(HERE, "scan3_emu.cpp")])
     L = C.CDLL(out)
     L.emu_scan3.restype = C.c_int
@@ -265,6 +266,8 @@ def test_shared_bound_with_long_lists(emu):
 def test_fold_row_is_a_bijection():
     rows = sorted(((t >> 1) & 1) | ((t & 1) << 1) | (t & 4) | (t & 8) for t in range(16))
     assert rows == list(range(16))
+    rows8 = sorted((t & 1) | ((t >> 1) & 2) | ((t >> 1) & 4) for t in range(16))   # 8 rows per warp: every row on threads t and t ^ 2
+    assert rows8 == sorted(list(range(8)) * 2)
 
 
 # ---- METRIC 3: L2 / L2 squared through the dot-product filter + exact second pass ---------------------------------------

@@ -578,7 +578,10 @@ __device__ __forceinline__ void t3_atomic_min_u64(u64* p, u64 v) { atomicMin(p, 
 __device__ __forceinline__ u64 t3_shfl64(u64 v, int src) { return shfl64(v, src); }
 __device__ __forceinline__ double t3_shfl_f64(double v, int src) { return __longlong_as_double((long long)shfl64((u64)__double_as_longlong(v), src)); }
 __device__ __forceinline__ u64 t3_shfl_up64(u64 v) { return shfl_up64(v); }
-__device__ __forceinline__ void t3_team_sync(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
+#ifndef T3_TWARPS
+#define T3_TWARPS 4
+#endif
+__device__ __forceinline__ void t3_team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(T3_TWARPS * 32) : "memory"); }
 __device__ __forceinline__ void t3_fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -586,12 +589,18 @@ __device__ __forceinline__ void t3_fence_barrier_init() {
 // register split of the CTA's 384 x 168 allocation: 256 math threads x T3_REGS_MATH + 128 producer / epilogue threads x T3_REGS_AUX
 // must not exceed it (232 / 40 or 224 / 56)
 #ifndef T3_REGS_MATH
+#if T3_TWARPS == 4
 #define T3_REGS_MATH 232
 #define T3_REGS_AUX 40
+#else   // 640 threads launch with 96 registers each: 512 x 112 + 128 x 32 = 640 x 96
+#define T3_REGS_MATH 112
+#define T3_REGS_AUX 32
+#endif
 #endif
 #define T3_STR2(x) #x
 #define T3_STR(x) T3_STR2(x)
-static_assert(256 * T3_REGS_MATH + 128 * T3_REGS_AUX <= 384 * 168, "setmaxnreg split exceeds the CTA's registers");
+static_assert(T3_TWARPS * 64 * T3_REGS_MATH + 128 * T3_REGS_AUX <= (T3_TWARPS * 64 + 128) * ((65536 / (T3_TWARPS * 64 + 128)) / 8 * 8),
+              "setmaxnreg split exceeds the CTA's registers");
 __device__ __forceinline__ void t3_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 " T3_STR(T3_REGS_AUX) ";"); }
 __device__ __forceinline__ void t3_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 " T3_STR(T3_REGS_MATH) ";"); }
 __device__ __forceinline__ void t3_prefetch_map(const T3Map& m) { asm volatile("prefetch.tensormap [%0];" ::"l"(&m) : "memory"); }

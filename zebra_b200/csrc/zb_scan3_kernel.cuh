@@ -32,7 +32,10 @@
 namespace zb {
 
 #define T3_TEAMS 2           // independent teams per CTA: each streams its own tiles through its own ring
-#define T3_TWARPS 4          // math warps per team (one per SM sub-partition)
+#ifndef T3_TWARPS
+#define T3_TWARPS 4          // math warps per team: 4 (one per SM sub-partition, 16 rows of a block each) or 8 (two per sub-partition, 8 rows
+                             // each: half the accumulator registers per thread, so twice the warps fit -- four math warps per scheduler)
+#endif
 #define T3_QT 16             // most queries per tile (two half-warp groups of up to 8)
 #define T3_RB 64             // rows per row block = rows per ring stage (4 warps x 16 rows)
 // Build variants measured on a B200 (profiles/r02g_*.json; kernel ms on BASELINE config 2 with L2 / cosine, and 384-dim L2
@@ -52,7 +55,10 @@ namespace zb {
 #define T3_SLICE_FLOATS (T3_KC * 16)
 #define T3_STAGE_BYTES (T3_RB * T3_SLICE_FLOATS * 4)   // 12288 (KC 3) or 8192 (KC 2)
 #define T3_CWARPS (T3_TEAMS * T3_TWARPS)
-#define T3_THREADS 384       // 2 math warpgroups (= teams) + 1 producer warpgroup (one TMA-driving warp per team)
+#define T3_RW (T3_RB / T3_TWARPS)                  // rows of a row block per math warp: 16 or 8
+#define T3_SLOTS (T3_QT / T3_TWARPS)               // tile slots (query lists) a math warp owns: 4 or 2
+#define T3_TEAM_THREADS (T3_TWARPS * 32)
+#define T3_THREADS (T3_CWARPS * 32 + 128)          // the teams' math warps + 1 producer warpgroup (one TMA-driving warp per team): 384 or 640
 #define T3_MAX_STAGES 8
 #define T3_KL 32             // lanes of a list: the register top-n' holds KR entries per lane (KR = 1: n' <= 32; KR = 4: n' <= 128)
 #define T3_KR_MAX 4
@@ -131,7 +137,13 @@ __host__ __device__ __forceinline__ u32 t3_qslot_floats(u32 q, u32 qh, int dimp,
     return region * ((u32)(qcap / 2) * (u32)dimp + 16u) + j * (u32)dimp;
 }
 // Row (0..15 of the warp's 16) whose finished sums thread t of a half-warp holds after the fold.
+#if T3_TWARPS == 4
 __host__ __device__ __forceinline__ int t3_fold_row(int t) { return ((t >> 1) & 1) | ((t & 1) << 1) | (t & 4) | (t & 8); }
+#else   // 8 rows per warp: the xor-8, xor-4 and xor-1 steps each halve a thread's rows, the xor-2 step leaves threads t and t ^ 2 with the same row
+__host__ __device__ __forceinline__ int t3_fold_row(int t) { return (t & 1) | ((t >> 1) & 2) | ((t >> 1) & 4); }
+#endif
+static_assert(T3_TWARPS == 4 || T3_TWARPS == 8, "math warps per team");
+static_assert(T3_TWARPS == 4 || (T3_KC == 3 && T3_EPW == 0), "the 8-warp teams exist for the default stage shape only");
 
 __device__ __forceinline__ bool t3_kp_less(u64 ka, u32 pa, u64 kb, u32 pb) { return ka < kb || (ka == kb && pa < pb); }
 
@@ -186,10 +198,11 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
     (void)nsl;
     const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
     const float* qp = reinterpret_cast<const float*>(tb + lay.queries) + (u32)h * ((u32)(qcap / 2) * (u32)dimp + 16u) + t;
-    const float* stage0 = reinterpret_cast<const float*>(tb + lay.stage) + (tw * 16) * T3_SLICE_FLOATS + t;
-    u64 acc[8][QH];  // acc[u][j] = packed lane partials of rows 2u, 2u+1 against query j
+    const float* stage0 = reinterpret_cast<const float*>(tb + lay.stage) + (tw * T3_RW) * T3_SLICE_FLOATS + t;
+    constexpr int RP = T3_RW / 2;   // row pairs of the warp
+    u64 acc[RP][QH];  // acc[u][j] = packed lane partials of rows 2u, 2u+1 against query j
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < RP; ++u)
 #pragma unroll
         for (int j = 0; j < QH; ++j) acc[u][j] = 0ull;
 #if T3_KC == 2
@@ -279,7 +292,7 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
                 qq[j] = t3_pk2(q, q);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < RP; ++u) {
                 const u64 ra = t3_pk2(rp[(2 * u) * T3_SLICE_FLOATS + c * 16], rp[(2 * u + 1) * T3_SLICE_FLOATS + c * 16]);
 #pragma unroll
                 for (int j = 0; j < QH; ++j) {
@@ -304,6 +317,7 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
     }
 #endif
     // ---- fold: canonical tree over the 16 lanes of the half-warp; a thread keeps half of its rows per step ----
+#if T3_TWARPS == 4
     float v8[8][QH];
     {
         const bool t3b = (t & 8) != 0;
@@ -350,13 +364,52 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
             sum[j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 2));  // (r0 + r1) + (r2 + r3)
         }
     }
+#else
+    // 8 rows: xor 8 pairs rows a / a + 4, xor 4 rows a / a + 2, xor 1 rows 0 / 1; the last step (xor 2) adds the two halves
+    // (r0 + r1) and (r2 + r3) of the one row left, on both threads
+    float v4[4][QH];
+    {
+        const bool t3b = (t & 8) != 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < QH; ++j) {
+                float lo0, hi0, lo1, hi1;
+                t3_upk2(acc[a >> 1][j], lo0, hi0);
+                t3_upk2(acc[(a + 4) >> 1][j], lo1, hi1);
+                const float va = (a & 1) ? hi0 : lo0, vb = (a & 1) ? hi1 : lo1;
+                const float mine = t3b ? vb : va, send = t3b ? va : vb;
+                v4[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 8));  // lane i + lane i + 8
+            }
+    }
+    float v2[2][QH];
+    {
+        const bool t2b = (t & 4) != 0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int j = 0; j < QH; ++j) {
+                const float mine = t2b ? v4[a + 2][j] : v4[a][j], send = t2b ? v4[a][j] : v4[a + 2][j];
+                v2[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 4));  // x[i] + x[i + 4]
+            }
+    }
+    {
+        const bool t0b = (t & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < QH; ++j) {
+            const float mine = t0b ? v2[1][j] : v2[0][j], send = t0b ? v2[0][j] : v2[1][j];
+            const float h2 = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 1));  // r0 + r1, r2 + r3
+            sum[j] = t3_fadd(h2, __shfl_xor_sync(0xffffffffu, h2, 2));              // (r0 + r1) + (r2 + r3)
+        }
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // Scan mode: one math warp's share of one tile; per row block the sums are transposed through shared memory and the warp
-// maintains the lists of the tile slots it owns (slot q is owned by warp q % 4).
+// maintains the lists of the tile slots it owns (slot q is owned by warp q % T3_TWARPS).
 // ------------------------------------------------------------------------------------------------------------------
-// The finished sums of (row 16 * tw + t3_fold_row(t), tile slot h * QH + j) go to sums[slot][row] of the block's buffer.
+// The finished sums of (row T3_RW * tw + t3_fold_row(t), tile slot h * QH + j) go to sums[slot][row] of the block's buffer.
 template <int METRIC, int QH>
 __device__ __forceinline__ void t3_block_sums_store(unsigned char* tb, const T3Layout& lay, const int dimp, const int chunks, const int qcap,
                                                     const u32 S, const int tw, const int lane, u32& buf, u32& ph, float* dst,
@@ -375,7 +428,7 @@ __device__ __forceinline__ void t3_block_sums_store(unsigned char* tb, const T3L
 template <int METRIC, int KR>
 __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& lay, const ForestView& f, const T3Params& tp,
                                              const T3TileInfo& inf, const int tw, const int lane, u32& buf, u32& ph, u32& blk,
-                                             const int team, u64 (&thr)[4]) {
+                                             const int team, u64 (&thr)[T3_SLOTS]) {
     const int t = lane & 15;
     const u32 S = (u32)tp.nst, L = inf.L, nqt = inf.nqt;
     const u32 nblocks = (L + T3_RB - 1) / T3_RB;
@@ -386,10 +439,10 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
 
     // The per-query bound shared by all of a query's visits (gthr) is read branch free right after a block's FP32 loop: four
     // independent loads in flight behind the transposition and the team barrier.  A stale bound only costs work.
-    u32 gq4[4];
+    u32 gq4[T3_SLOTS];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const u32 q = (u32)tw + 4u * e;
+    for (int e = 0; e < T3_SLOTS; ++e) {
+        const u32 q = (u32)tw + (u32)T3_TWARPS * e;
         const u32 m = s_meta[2 * tp.qcap + (q < (u32)tp.qcap ? q : 0u)];
         gq4[e] = q < nqt ? m : 0u;
     }
@@ -405,7 +458,7 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
         }
         if (lane < 3) t3_prefetch_l1(tp.bm_tomb + (base >> 5) + lane);
         {
-            float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * 16 + myrow;
+            float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * T3_RW + myrow;
             switch (inf.qh) {
 #if T3_QH_STEP == 1
                 case 1: t3_block_sums_store<METRIC, 1>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
@@ -419,9 +472,9 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
                 default: t3_block_sums_store<METRIC, 8>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
             }
         }
-        u64 gbound[4];
+        u64 gbound[T3_SLOTS];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) gbound[e] = t3_ldcg_u64(tp.gthr + gq4[e]);
+        for (int e = 0; e < T3_SLOTS; ++e) gbound[e] = t3_ldcg_u64(tp.gthr + gq4[e]);
         // ---- what the epilogue needs from global memory (prefetched above; the team barrier below hides the rest) ----
         double rinv_lo = 0.0, rinv_hi = 0.0;
         if (METRIC == 0) {
@@ -436,15 +489,18 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
         u32 tword = 0;  // tombstone words covering positions base .. base + 63 (at most 3 words), one per lane
         if (lane < 3) tword = tp.bm_tomb[(base >> 5) + lane];
         t3_team_sync(team);  // the block's sums are complete; the previous use of this buffer was consumed two blocks ago
-        // ---- epilogue: this warp finishes the tile slots it owns (q = tw, tw + 4, ...): keys, filter, list insertion ----
+        // ---- epilogue: this warp finishes the tile slots it owns (q = tw, tw + T3_TWARPS, ...): keys, filter, list insertion ----
         const float* sums = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const u32 q = (u32)tw + 4u * e;
+        for (int e = 0; e < T3_SLOTS; ++e) {
+            const u32 q = (u32)tw + (u32)T3_TWARPS * e;
             if (q >= nqt) break;  // warp uniform
             const int np = (int)s_meta[tp.qcap + q];
             const u32 gq = s_meta[2 * tp.qcap + q];
             const float s_lo = sums[(size_t)q * T3_RB + r_lo], s_hi = sums[(size_t)q * T3_RB + r_hi];
+            // every lane loaded the bound itself; other tiles lower it concurrently and the epilogue's control flow depends on it,
+            // so ONE lane's copy decides for the warp (the load has long arrived: no wait here)
+            gbound[e] = t3_shfl64(gbound[e], 0);
             u64 k_lo = ZB_SENTINEL, k_hi = ZB_SENTINEL;
             float Eq = 0.f;   // METRIC 3: the error bound of this (leaf, query)
             if (METRIC == 3) {
@@ -693,7 +749,7 @@ __device__ __forceinline__ void t3_scan_tile_math(unsigned char* tb, const T3Lay
     float* s_sums = reinterpret_cast<float*>(tb + lay.sums);
     const int myrow = t3_fold_row(lane & 15);
     for (u32 b = 0; b < nblocks; ++b, ++blk) {
-        float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * 16 + myrow;
+        float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * T3_RW + myrow;
         // the buffer's previous content (two blocks ago) has been consumed: checked right before the store inside, i.e. after the FP32 loop
         switch (inf.qh) {
 #if T3_QH_STEP == 1
@@ -723,7 +779,7 @@ __device__ __forceinline__ void t3_project_tile(unsigned char* tb, const T3Layou
     const int t = lane & 15, h = lane >> 4;
     const u32 S = (u32)tp.nst, L = inf.L, nqt = inf.nqt;
     const u32 nblocks = (L + T3_RB - 1) / T3_RB;
-    const int myrow = tw * 16 + t3_fold_row(t);
+    const int myrow = tw * T3_RW + t3_fold_row(t);
     float cst[QH];
 #pragma unroll
     for (int j = 0; j < QH; ++j) {
@@ -887,8 +943,8 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
             continue;
         }
         // the tile slots this warp owns: visit, n', query -> shared memory (read back as broadcasts in the epilogue), empty lists
-        if (lane < 4) {
-            const u32 q = (u32)tw + 4u * lane;
+        if (lane < T3_SLOTS) {
+            const u32 q = (u32)tw + (u32)T3_TWARPS * lane;
             if (q < nqt) {
                 const u32 visit = tp.order[inf.first + q];
                 s_meta[q] = visit;
@@ -903,23 +959,25 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
             }
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const u32 q = (u32)tw + 4u * e;
+        for (int e = 0; e < T3_SLOTS; ++e) {
+            const u32 q = (u32)tw + (u32)T3_TWARPS * e;
             if (q < nqt) {
                 u32* lst = s_lists + (size_t)q * 3 * KR * T3_KL;
 #pragma unroll
                 for (int x = 0; x < 3 * KR; ++x) lst[x * T3_KL + lane] = 0xFFFFFFFFu;  // empty: key all ones, position T3_NOPOS
             }
         }
-        u64 thr[4] = {ZB_SENTINEL, ZB_SENTINEL, ZB_SENTINEL, ZB_SENTINEL};  // filter of each owned slot: its list's n'-th key or the shared bound
+        u64 thr[T3_SLOTS];  // filter of each owned slot: its list's n'-th key or the shared bound
+#pragma unroll
+        for (int e = 0; e < T3_SLOTS; ++e) thr[e] = ZB_SENTINEL;
         __syncwarp();
         mbar_wait(bar_qfull, it & 1);
         t3_scan_tile<METRIC, KR>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr);
         // ---- end of tile: release the query block, write the owned visits' top lists ----
         if (lane == 0) mbar_arrive(bar_qempty);
 #pragma unroll 1
-        for (int e = 0; e < 4; ++e) {
-            const u32 q = (u32)tw + 4u * e;
+        for (int e = 0; e < T3_SLOTS; ++e) {
+            const u32 q = (u32)tw + (u32)T3_TWARPS * e;
             if (q >= nqt) break;
             const u32 v = s_meta[q];
             const int np = (int)s_meta[tp.qcap + q];

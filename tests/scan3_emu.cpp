@@ -280,10 +280,10 @@ static inline u64 t3_shfl_up64(u64 v) {
     const int lane = threadIdx.x & 31;
     return emu_exchange(v, lane == 0 ? 0 : lane - 1);
 }
-static inline void t3_team_sync(int team) { emu_at(2, (unsigned)team); emu_team_bar[team]->arrive_and_wait(); emu_at(0); }
+static inline void t3_team_sync(int team, int /*threads: the barrier objects are built for the launch's team size*/) { emu_at(2, (unsigned)team); emu_team_bar[team]->arrive_and_wait(); emu_at(0); }
 static inline void t3_fence_barrier_init() {}
-static inline void t3_setmaxnreg_dec() {}
-static inline void t3_setmaxnreg_inc() {}
+template <int TW> static inline void t3_setmaxnreg_dec() {}
+template <int TW> static inline void t3_setmaxnreg_inc() {}
 static inline void t3_prefetch_map(const T3Map&) {}
 static inline void t3_prefetch_l1(const void*) {}
 static inline bool t3_above_from_dot(float dot, float constant) { return (double)dot + (double)constant >= 0.0; }
@@ -293,9 +293,30 @@ static inline u64 l2_bits(float s) { return t3_dbits(sqrt((double)s)); }
 
 #include "../zebra_b200/csrc/zb_scan3_kernel.cuh"
 static_assert(T3_EMU_SLICE == T3_SLICE_FLOATS && T3_EMU_STAGE_ROWS == T3_RB, "the emulated TMA box is the kernel's stage");
+static_assert(zb::T3Shape<8>::THREADS <= 1024, "emu_where holds 1024 threads");
 
 // Tiles are given directly (what ts_count / ts_scatter / ts_filltiles build on the device).  The bucket-major store is
 // addressed by position: members = identity is supplied by the caller together with ord[position].
+// math warps per team of the next emu_scan3 / emu_project3 launch (the kernel body's TW: 4 or 8)
+static int emu_tw = 4;
+extern "C" __attribute__((visibility("default"))) int emu_scan3_set_team_warps(int tw) {
+    if (tw != 4 && tw != 8) return -1;
+    emu_tw = tw;
+    return 0;
+}
+template <int TW> static void emu_run_scan3(int metric, int kr, const zb::T3Map& map, const zb::ForestView& f, const zb::T3Params& tp) {
+    if (kr == 1) {
+        if (metric == 0) zb::t3_body<0, 0, 1, TW>(map, f, tp, emu_smem);
+        else if (metric == 1) zb::t3_body<1, 0, 1, TW>(map, f, tp, emu_smem);
+        else if (metric == 3) zb::t3_body<3, 0, 1, TW>(map, f, tp, emu_smem);
+        else zb::t3_body<2, 0, 1, TW>(map, f, tp, emu_smem);
+    } else {
+        if (metric == 0) zb::t3_body<0, 0, T3_KR_MAX, TW>(map, f, tp, emu_smem);
+        else if (metric == 1) zb::t3_body<1, 0, T3_KR_MAX, TW>(map, f, tp, emu_smem);
+        else zb::t3_body<2, 0, T3_KR_MAX, TW>(map, f, tp, emu_smem);
+    }
+}
+
 // METRIC 3 (dot-product filter): what the launch code adds to T3Params, set before emu_scan3(metric = 3, ...)
 static struct { const float* bm_n2; const float* q_n2; const float* leaf_n2max; float ecoef; uint64_t* cand; float* cand_cut; uint8_t* cand_flag; } emu_filter;
 extern "C" __attribute__((visibility("default"))) void emu_scan3_set_filter(const float* bm_n2, const float* q_n2, const float* leaf_n2max, float ecoef,
@@ -326,8 +347,13 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
     if (metric == 3 && (kr != 1 || !tp.cand)) return -1;
     const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap, kr);
     std::vector<unsigned char> smem((size_t)T3_TEAMS * lay.total + 1024);
+    const int tw = emu_tw;
+#if T3_KC != 3 || T3_EPW
+    if (tw != 4) return -1;
+#endif
+    const unsigned nthreads = tw == 4 ? zb::T3Shape<4>::THREADS : zb::T3Shape<8>::THREADS;
     emu_warps.clear();
-    for (int i = 0; i < T3_THREADS / 32; ++i) emu_warps.emplace_back(new WarpBox());
+    for (unsigned i = 0; i < nthreads / 32; ++i) emu_warps.emplace_back(new WarpBox());
     for (int b = 0; b < blocks; ++b) {
         // garbage in shared memory at block start: nothing may depend on its content
         for (size_t i = 0; i < smem.size(); ++i) smem[i] = (unsigned char)(0xA5 ^ (i * 131));
@@ -336,24 +362,19 @@ extern "C" __attribute__((visibility("default"))) int emu_scan3(
         CopyEngine dma;
         emu_dma = &dma;
         dma.start();
-        std::barrier<> bar(T3_THREADS), tb0(T3_TEAM_THREADS), tb1(T3_TEAM_THREADS);
+        std::barrier<> bar(nthreads), tb0(tw * 32), tb1(tw * 32);
         emu_block_bar = &bar;
         emu_team_bar[0] = &tb0;
         emu_team_bar[1] = &tb1;
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < T3_THREADS; ++t)
+        for (unsigned t = 0; t < nthreads; ++t)
             th.emplace_back([&, t] {
                 emu_threadIdx = Dim3{t, 0, 0};
-                if (kr == 1) {
-                    if (metric == 0) zb::t3_body<0, 0, 1>(map, f, tp, emu_smem);
-                    else if (metric == 1) zb::t3_body<1, 0, 1>(map, f, tp, emu_smem);
-                    else if (metric == 3) zb::t3_body<3, 0, 1>(map, f, tp, emu_smem);
-                    else zb::t3_body<2, 0, 1>(map, f, tp, emu_smem);
-                } else {
-                    if (metric == 0) zb::t3_body<0, 0, T3_KR_MAX>(map, f, tp, emu_smem);
-                    else if (metric == 1) zb::t3_body<1, 0, T3_KR_MAX>(map, f, tp, emu_smem);
-                    else zb::t3_body<2, 0, T3_KR_MAX>(map, f, tp, emu_smem);
-                }
+#if T3_KC == 3 && !T3_EPW
+                if (tw == 8) emu_run_scan3<8>(metric, kr, map, f, tp);
+                else
+#endif
+                    emu_run_scan3<4>(metric, kr, map, f, tp);
             });
         for (auto& x : th) x.join();
         dma.finish();
@@ -419,8 +440,13 @@ extern "C" __attribute__((visibility("default"))) int emu_project3(int blocks, i
     zb::T3Map map{rows_padded, n, f.dimp};
     const zb::T3Layout lay = zb::t3_layout(nst, f.dimp, qcap, 1);
     std::vector<unsigned char> smem((size_t)T3_TEAMS * lay.total + 1024);
+    const int tw = emu_tw;
+#if T3_KC != 3 || T3_EPW
+    if (tw != 4) return -1;
+#endif
+    const unsigned nthreads = tw == 4 ? zb::T3Shape<4>::THREADS : zb::T3Shape<8>::THREADS;
     emu_warps.clear();
-    for (int i = 0; i < T3_THREADS / 32; ++i) emu_warps.emplace_back(new WarpBox());
+    for (unsigned i = 0; i < nthreads / 32; ++i) emu_warps.emplace_back(new WarpBox());
     for (int b = 0; b < blocks; ++b) {
         for (size_t i = 0; i < smem.size(); ++i) smem[i] = (unsigned char)(0x5A ^ (i * 37));
         emu_smem = smem.data();
@@ -428,13 +454,17 @@ extern "C" __attribute__((visibility("default"))) int emu_project3(int blocks, i
         CopyEngine dma;
         emu_dma = &dma;
         dma.start();
-        std::barrier<> bar(T3_THREADS), tb0(T3_TEAM_THREADS), tb1(T3_TEAM_THREADS);
+        std::barrier<> bar(nthreads), tb0(tw * 32), tb1(tw * 32);
         emu_block_bar = &bar; emu_team_bar[0] = &tb0; emu_team_bar[1] = &tb1;
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < T3_THREADS; ++t)
+        for (unsigned t = 0; t < nthreads; ++t)
             th.emplace_back([&, t] {
                 emu_threadIdx = Dim3{t, 0, 0};
-                zb::t3_body<0, 1, 1>(map, f, tp, emu_smem);
+#if T3_KC == 3 && !T3_EPW
+                if (tw == 8) zb::t3_body<0, 1, 1, 8>(map, f, tp, emu_smem);
+                else
+#endif
+                    zb::t3_body<0, 1, 1, 4>(map, f, tp, emu_smem);
             });
         for (auto& x : th) x.join();
         dma.finish();

@@ -104,6 +104,12 @@ def test_fused_kernel_with_lists_of_up_to_128_entries(dim, mid, mname):
         assert st["last_tile_pairs"] > 0.99 * st["last_pairs"], (k, st)
     assert_search_equal(ix, orc, queries[:100], 129)
     assert ix.stats()["last_tile_pairs"] == 0
+    # long lists run with eight math warps per team (8 rows of a block each) by default; the four-warp shape must agree
+    ix.set_param("long_list_warps", 4)
+    for k in (33, 100):
+        assert_search_equal(ix, orc, queries, k)
+        assert ix.stats()["last_tile_pairs"] > 0.99 * ix.stats()["last_pairs"]
+    ix.set_param("long_list_warps", 8)
 
 
 def test_tile_kernel_crowded_leaves():

@@ -25,13 +25,14 @@ SENT = np.uint64(0xFFFFFFFFFFFFFFFF)
 def emu(tmp_path_factory, request):
     """The build variants of the kernel body: T3_KC = 3 (the default: a stage's chunks straight-line) and 2 (operands
     software-pipelined across stage boundaries); T3_EPW = 1 (a dedicated epilogue warp per team keeps the lists of n' <= 32);
-    T3_TWARPS = 8 (eight math warps per team, 8 rows of a block each: 640 threads)."""
+    TW = 8 (eight math warps per team, 8 rows of a block each: 640 threads; what the library launches for n' > 32)."""
     kc, epw, tw = request.param
     out = str(tmp_path_factory.mktemp("s3") / f"libscan3_emu_kc{kc}_epw{epw}_tw{tw}.so")
     subprocess.check_call(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
-                           f"-DT3_KC={kc}", f"-DT3_EPW={epw}", f"-DT3_TWARPS={tw}", "-g", "-rdynamic", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out,
+                           f"-DT3_KC={kc}", f"-DT3_EPW={epw}", "-g", "-rdynamic", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-o", out,
                            os.path.join(HERE, "scan3_emu.cpp")])
     L = C.CDLL(out)
+    assert L.emu_scan3_set_team_warps(tw) == 0               # the kernel body's TW (a template parameter: both shapes are in every build)
     L.emu_scan3.restype = C.c_int
     L.emu_scan3.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint64] + [C.c_void_p] * 7 + \
                            [C.c_uint32] + [C.c_void_p] * 12

@@ -2318,6 +2318,7 @@ int zb_index_set_param(zb_index* ix, const char* key, int64_t value) {
     else if (k == "quad_tile") ix->p_quad_tile = value;  // cosine / L2 visits outside the fused kernel (n' > 32): 1 = keys-only leaf-tile scan (default: 2.4x the gather path on top-100, profiles/r02a_bench_top100_quad*.json), 0 = one quad per pair
     else if (k == "flat_project") ix->p_flat_project = value;  // flat tables: 1 = dense projection + ballot packing (default), 0 = the generic tree walk
     else if (k == "l2_filter") { ix->p_l2_filter = value; ix->filter_backoff = 0; }  // L2 / L2 squared through the dot-product filter + exact second pass: 0 off, 1 adaptive (default), 2 always
+    else if (k == "long_list_warps") { ZB_REQUIRE(value == 4 || value == 8, ZB_ERR_INVALID, "long_list_warps is 4 or 8"); ix->scan_ws.long_list_warps = (int)value; }  // fused scan with n' > 32: math warps per team
     else if (k == "plan_tail") ix->p_plan_tail = value;  // plan walk: 1 = cascade walkers go to the latency-optimised tail kernel (default), 0 = one kernel
     else if (k == "p2p_queries") ix->p_p2p_queries = value;  // sliced search: 1 = query slices pushed into the peers' buffers over NVLink (CUDA IPC; default), 0 = NCCL
     else if (k == "single_exchange") ix->p_single_exchange = value;  // sliced search: 1 = query slices ride in the visit-record allgather (default), 0 = their own allgather first

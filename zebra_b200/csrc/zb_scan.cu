@@ -578,31 +578,31 @@ __device__ __forceinline__ void t3_atomic_min_u64(u64* p, u64 v) { atomicMin(p, 
 __device__ __forceinline__ u64 t3_shfl64(u64 v, int src) { return shfl64(v, src); }
 __device__ __forceinline__ double t3_shfl_f64(double v, int src) { return __longlong_as_double((long long)shfl64((u64)__double_as_longlong(v), src)); }
 __device__ __forceinline__ u64 t3_shfl_up64(u64 v) { return shfl_up64(v); }
-#ifndef T3_TWARPS
-#define T3_TWARPS 4
-#endif
-__device__ __forceinline__ void t3_team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(T3_TWARPS * 32) : "memory"); }
+__device__ __forceinline__ void t3_team_sync(int team, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(threads) : "memory"); }
 __device__ __forceinline__ void t3_fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// register split of the CTA's 384 x 168 allocation: 256 math threads x T3_REGS_MATH + 128 producer / epilogue threads x T3_REGS_AUX
-// must not exceed it (232 / 40 or 224 / 56)
+// register split of the CTA's allocation between the math warps and the producer warpgroup (setmaxnreg): 4 math warps per team =
+// 384 threads launched with 168 registers: 256 x 232 + 128 x 40 = 384 x 168;  8 per team = 640 threads launched with 96:
+// 512 x 112 + 128 x 32 = 640 x 96
 #ifndef T3_REGS_MATH
-#if T3_TWARPS == 4
 #define T3_REGS_MATH 232
 #define T3_REGS_AUX 40
-#else   // 640 threads launch with 96 registers each: 512 x 112 + 128 x 32 = 640 x 96
-#define T3_REGS_MATH 112
-#define T3_REGS_AUX 32
-#endif
 #endif
 #define T3_STR2(x) #x
 #define T3_STR(x) T3_STR2(x)
-static_assert(T3_TWARPS * 64 * T3_REGS_MATH + 128 * T3_REGS_AUX <= (T3_TWARPS * 64 + 128) * ((65536 / (T3_TWARPS * 64 + 128)) / 8 * 8),
-              "setmaxnreg split exceeds the CTA's registers");
-__device__ __forceinline__ void t3_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 " T3_STR(T3_REGS_AUX) ";"); }
-__device__ __forceinline__ void t3_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 " T3_STR(T3_REGS_MATH) ";"); }
+static_assert(256 * T3_REGS_MATH + 128 * T3_REGS_AUX <= 384 * 168, "setmaxnreg split exceeds the CTA's registers");
+template <int TW>
+__device__ __forceinline__ void t3_setmaxnreg_dec() {
+    if (TW == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 " T3_STR(T3_REGS_AUX) ";");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+}
+template <int TW>
+__device__ __forceinline__ void t3_setmaxnreg_inc() {
+    if (TW == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 " T3_STR(T3_REGS_MATH) ";");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+}
 __device__ __forceinline__ void t3_prefetch_map(const T3Map& m) { asm volatile("prefetch.tensormap [%0];" ::"l"(&m) : "memory"); }
 __device__ __forceinline__ void t3_tma_2d_g2s(u32 dst, const T3Map& map, int c0, long long row, u32 bar) {
     tma_2d_g2s(dst, &map, c0, (int)row, bar);
@@ -613,11 +613,11 @@ __device__ __forceinline__ bool t3_above_from_dot(float dot, float constant) { r
 #include "zb_scan3_kernel.cuh"
 namespace zb {
 
-// KR = list entries per lane: 1 serves n' <= 32, 4 serves n' <= 128 (BASELINE config 5 asks for top-100)
-template <int METRIC, int KR>
-__global__ void __launch_bounds__(T3_THREADS, 1) tile_scan3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
+// KR = list entries per lane: 1 serves n' <= 32, 4 serves n' <= 128 (BASELINE config 5 asks for top-100); TW = math warps per team
+template <int METRIC, int KR, int TW>
+__global__ void __launch_bounds__(T3Shape<TW>::THREADS, 1) tile_scan3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
     extern __shared__ __align__(1024) unsigned char smem3[];
-    t3_body<METRIC, 0, KR>(tmap, f, tp, smem3);
+    t3_body<METRIC, 0, KR, TW>(tmap, f, tp, smem3);
 }
 // Second pass of the dot-product filter (METRIC 3 of the kernel above): exact keys of every visit's candidates, one warp per visit.
 #define RF_THREADS 256
@@ -626,9 +626,9 @@ __global__ void __launch_bounds__(RF_THREADS) refine_visits_kernel(ForestView f,
     t3_refine_warp<METRIC>(f, rp, (int)(threadIdx.x & 31u));
 }
 // Flat-table projection on the same skeleton (MODE 1): tmap covers the INPUT rows, tp.queries the plane coefficients.
-__global__ void __launch_bounds__(T3_THREADS, 1) project3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
+__global__ void __launch_bounds__(T3Shape<4>::THREADS, 1) project3_kernel(const __grid_constant__ CUtensorMap tmap, ForestView f, T3Params tp) {
     extern __shared__ __align__(1024) unsigned char smem3[];
-    t3_body<0, 1, 1>(tmap, f, tp, smem3);
+    t3_body<0, 1, 1, 4>(tmap, f, tp, smem3);
 }
 
 // =====================================================================================================
@@ -1093,19 +1093,24 @@ void tile_scan3(ScanWorkspace& ws, const ForestView& f, const BucketMajor& bm, u
         ZB_CUDA(cudaEventCreate(&ws.ev1));
     }
     ZB_CUDA(cudaEventRecord(ws.ev0, s));
-    auto launch = [&](auto kern) {
+    auto launch = [&](auto kern, int threads) {
         ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, T3_THREADS, smem, s>>>(tmap, f, tp);
+        kern<<<grid, threads, smem, s>>>(tmap, f, tp);
     };
-    if (filt) launch(tile_scan3_kernel<3, 1>);
+    // short lists (n' <= 32): 4 math warps per team x 16 rows;  long lists (top-100): 8 x 8 rows -- sixteen warps keep the lists (measured, T3Shape)
+    if (filt) launch(tile_scan3_kernel<3, 1, 4>, T3Shape<4>::THREADS);
     else if (kr == 1) {
-        if (metric == 0) launch(tile_scan3_kernel<0, 1>);
-        else if (metric == 1) launch(tile_scan3_kernel<1, 1>);
-        else launch(tile_scan3_kernel<2, 1>);
+        if (metric == 0) launch(tile_scan3_kernel<0, 1, 4>, T3Shape<4>::THREADS);
+        else if (metric == 1) launch(tile_scan3_kernel<1, 1, 4>, T3Shape<4>::THREADS);
+        else launch(tile_scan3_kernel<2, 1, 4>, T3Shape<4>::THREADS);
+    } else if (ws.long_list_warps == 4) {   // knob long_list_warps (ablation)
+        if (metric == 0) launch(tile_scan3_kernel<0, T3_KR_MAX, 4>, T3Shape<4>::THREADS);
+        else if (metric == 1) launch(tile_scan3_kernel<1, T3_KR_MAX, 4>, T3Shape<4>::THREADS);
+        else launch(tile_scan3_kernel<2, T3_KR_MAX, 4>, T3Shape<4>::THREADS);
     } else {
-        if (metric == 0) launch(tile_scan3_kernel<0, T3_KR_MAX>);
-        else if (metric == 1) launch(tile_scan3_kernel<1, T3_KR_MAX>);
-        else launch(tile_scan3_kernel<2, T3_KR_MAX>);
+        if (metric == 0) launch(tile_scan3_kernel<0, T3_KR_MAX, 8>, T3Shape<8>::THREADS);
+        else if (metric == 1) launch(tile_scan3_kernel<1, T3_KR_MAX, 8>, T3Shape<8>::THREADS);
+        else launch(tile_scan3_kernel<2, T3_KR_MAX, 8>, T3Shape<8>::THREADS);
     }
     ZB_CUDA(cudaGetLastError());
     ZB_CUDA(cudaEventRecord(ws.ev1, s));
@@ -1217,7 +1222,7 @@ void project3(ScanWorkspace& ws, const float* d_rows, u64 n, const float* d_coef
     tp.pj_hp = Hp;
     const size_t smem = t3_smem_bytes(nst, dimp, qcap, 1);
     ZB_CUDA(cudaFuncSetAttribute(project3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    project3_kernel<<<sms, T3_THREADS, smem, s>>>(tmap, f, tp);
+    project3_kernel<<<sms, T3Shape<4>::THREADS, smem, s>>>(tmap, f, tp);
     ZB_CUDA(cudaGetLastError());
 }
 

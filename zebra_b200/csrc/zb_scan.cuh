@@ -15,6 +15,7 @@ struct ScanWorkspace {
     DBuf<u8> cand_flag;
     bool l2_filter = false;      // in: the caller allows the filter for this batch;  filtered: the last launch used it
     bool filtered = false;
+    int long_list_warps = 8;     // in: math warps per team for n' > 32 (knob long_list_warps: 8 = default, 4 = the short-list shape)
     cudaEvent_t ev2 = nullptr;   // after the second pass
     DBuf<long long> pj_off;   // project3: first row of every row range
     DBuf<u8> tmp, sort_tmp;

@@ -32,10 +32,6 @@
 namespace zb {
 
 #define T3_TEAMS 2           // independent teams per CTA: each streams its own tiles through its own ring
-#ifndef T3_TWARPS
-#define T3_TWARPS 4          // math warps per team: 4 (one per SM sub-partition, 16 rows of a block each) or 8 (two per sub-partition, 8 rows
-                             // each: half the accumulator registers per thread, so twice the warps fit -- four math warps per scheduler)
-#endif
 #define T3_QT 16             // most queries per tile (two half-warp groups of up to 8)
 #define T3_RB 64             // rows per row block = rows per ring stage (4 warps x 16 rows)
 // Build variants measured on a B200 (profiles/r02g_*.json; kernel ms on BASELINE config 2 with L2 / cosine, and 384-dim L2
@@ -54,11 +50,20 @@ namespace zb {
 #endif
 #define T3_SLICE_FLOATS (T3_KC * 16)
 #define T3_STAGE_BYTES (T3_RB * T3_SLICE_FLOATS * 4)   // 12288 (KC 3) or 8192 (KC 2)
-#define T3_CWARPS (T3_TEAMS * T3_TWARPS)
-#define T3_RW (T3_RB / T3_TWARPS)                  // rows of a row block per math warp: 16 or 8
-#define T3_SLOTS (T3_QT / T3_TWARPS)               // tile slots (query lists) a math warp owns: 4 or 2
-#define T3_TEAM_THREADS (T3_TWARPS * 32)
-#define T3_THREADS (T3_CWARPS * 32 + 128)          // the teams' math warps + 1 producer warpgroup (one TMA-driving warp per team): 384 or 640
+// Team shape (template parameter TW of the kernel body = math warps per team): 4 (one per SM sub-partition, 16 rows of a block
+// each: 128 accumulator registers per thread) or 8 (two per sub-partition, 8 rows each: half the accumulators, so twice the
+// warps fit -- four math warps per scheduler).  Measured on a B200 (profiles/r02t_*): TW = 8 executes 24 % more instructions
+// (twice the per-stage control, more shared-memory loads per FMA, spills at 112 registers) and loses at 768 dims with short
+// lists (3.10 -> 3.49 ms), but its sixteen warps keep the 128-entry lists of top-100 queries far better (6.06 -> 4.01 ms).
+template <int TW>
+struct T3Shape {
+    static_assert(TW == 4 || TW == 8, "math warps per team");
+    static constexpr int RW = T3_RB / TW;                  // rows of a row block per math warp: 16 or 8
+    static constexpr int SLOTS = T3_QT / TW;               // tile slots (query lists) a math warp owns: 4 or 2
+    static constexpr int TEAM_THREADS = TW * 32;
+    static constexpr int CWARPS = T3_TEAMS * TW;           // math warps of a CTA
+    static constexpr int THREADS = CWARPS * 32 + 128;      // + 1 producer warpgroup (one TMA-driving warp per team): 384 or 640
+};
 #define T3_MAX_STAGES 8
 #define T3_KL 32             // lanes of a list: the register top-n' holds KR entries per lane (KR = 1: n' <= 32; KR = 4: n' <= 128)
 #define T3_KR_MAX 4
@@ -137,13 +142,12 @@ __host__ __device__ __forceinline__ u32 t3_qslot_floats(u32 q, u32 qh, int dimp,
     return region * ((u32)(qcap / 2) * (u32)dimp + 16u) + j * (u32)dimp;
 }
 // Row (0..15 of the warp's 16) whose finished sums thread t of a half-warp holds after the fold.
-#if T3_TWARPS == 4
-__host__ __device__ __forceinline__ int t3_fold_row(int t) { return ((t >> 1) & 1) | ((t & 1) << 1) | (t & 4) | (t & 8); }
-#else   // 8 rows per warp: the xor-8, xor-4 and xor-1 steps each halve a thread's rows, the xor-2 step leaves threads t and t ^ 2 with the same row
-__host__ __device__ __forceinline__ int t3_fold_row(int t) { return (t & 1) | ((t >> 1) & 2) | ((t >> 1) & 4); }
-#endif
-static_assert(T3_TWARPS == 4 || T3_TWARPS == 8, "math warps per team");
-static_assert(T3_TWARPS == 4 || (T3_KC == 3 && T3_EPW == 0), "the 8-warp teams exist for the default stage shape only");
+// TW = 4 (16 rows per warp): every fold step halves a thread's rows.  TW = 8 (8 rows): the xor-8, xor-4 and xor-1 steps do, the
+// xor-2 step leaves threads t and t ^ 2 with the same row.
+template <int TW>
+__host__ __device__ __forceinline__ int t3_fold_row(int t) {
+    return TW == 4 ? (((t >> 1) & 1) | ((t & 1) << 1) | (t & 4) | (t & 8)) : ((t & 1) | ((t >> 1) & 2) | ((t >> 1) & 4));
+}
 
 __device__ __forceinline__ bool t3_kp_less(u64 ka, u32 pa, u64 kb, u32 pb) { return ka < kb || (ka == kb && pa < pb); }
 
@@ -190,7 +194,7 @@ __host__ __device__ __forceinline__ float t3_funord(u32 k) { return t3_bitsf((k 
 // h * QH .. h * QH + QH - 1) -- and folds the 16 accumulator lanes over the half-warp.  Returns, in sum[j], the finished
 // canonical sum of (row 16 * tw + t3_fold_row(t), tile slot h * QH + j).  METRIC 0: dot product, otherwise sum of (a - b)^2.
 // ------------------------------------------------------------------------------------------------------------------
-template <int METRIC, int QH>
+template <int METRIC, int QH, int TW>
 __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout& lay, const int dimp, const int chunks, const int qcap,
                                               const u32 S, const int tw, const int lane, u32& buf, u32& ph, float (&sum)[QH]) {
     const int t = lane & 15, h = lane >> 4;
@@ -198,14 +202,15 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
     (void)nsl;
     const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
     const float* qp = reinterpret_cast<const float*>(tb + lay.queries) + (u32)h * ((u32)(qcap / 2) * (u32)dimp + 16u) + t;
-    const float* stage0 = reinterpret_cast<const float*>(tb + lay.stage) + (tw * T3_RW) * T3_SLICE_FLOATS + t;
-    constexpr int RP = T3_RW / 2;   // row pairs of the warp
+    const float* stage0 = reinterpret_cast<const float*>(tb + lay.stage) + (tw * T3Shape<TW>::RW) * T3_SLICE_FLOATS + t;
+    constexpr int RP = T3Shape<TW>::RW / 2;   // row pairs of the warp
     u64 acc[RP][QH];  // acc[u][j] = packed lane partials of rows 2u, 2u+1 against query j
 #pragma unroll
     for (int u = 0; u < RP; ++u)
 #pragma unroll
         for (int j = 0; j < QH; ++j) acc[u][j] = 0ull;
 #if T3_KC == 2
+    static_assert(TW == 4, "the 2-chunk stage exists for 4 math warps per team");
     // A ring stage holds T3_KC == 2 chunks of the block's 64 rows.  The operands of a chunk (16 row floats + QH query floats
     // per thread) are loaded from shared memory HALF A CHUNK AHEAD of the FP32 work that consumes them, across stage
     // boundaries too: a row register is reloaded with the next chunk's value as soon as its last FFMA2 has been issued, the
@@ -317,92 +322,92 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
     }
 #endif
     // ---- fold: canonical tree over the 16 lanes of the half-warp; a thread keeps half of its rows per step ----
-#if T3_TWARPS == 4
-    float v8[8][QH];
-    {
-        const bool t3b = (t & 8) != 0;
+    if constexpr (TW == 4) {
+        float v8[8][QH];
+        {
+            const bool t3b = (t & 8) != 0;
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    // rows a and a + 8 of the warp's 16: row r lives in acc[r / 2][j], half r % 2
+                    float lo0, hi0, lo1, hi1;
+                    t3_upk2(acc[a >> 1][j], lo0, hi0);
+                    t3_upk2(acc[(a + 8) >> 1][j], lo1, hi1);
+                    const float va = (a & 1) ? hi0 : lo0, vb = (a & 1) ? hi1 : lo1;
+                    const float mine = t3b ? vb : va, send = t3b ? va : vb;
+                    v8[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 8));  // lane i + lane i + 8
+                }
+        }
+        float v4[4][QH];
+        {
+            const bool t2b = (t & 4) != 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    const float mine = t2b ? v8[a + 4][j] : v8[a][j], send = t2b ? v8[a][j] : v8[a + 4][j];
+                    v4[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 4));  // x[i] + x[i + 4]
+                }
+        }
+        float v2[2][QH];
+        {
+            const bool t0b = (t & 1) != 0;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    const float mine = t0b ? v4[a + 2][j] : v4[a][j], send = t0b ? v4[a][j] : v4[a + 2][j];
+                    v2[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 1));  // r0 + r1, r2 + r3
+                }
+        }
+        {
+            const bool t1b = (t & 2) != 0;
 #pragma unroll
             for (int j = 0; j < QH; ++j) {
-                // rows a and a + 8 of the warp's 16: row r lives in acc[r / 2][j], half r % 2
-                float lo0, hi0, lo1, hi1;
-                t3_upk2(acc[a >> 1][j], lo0, hi0);
-                t3_upk2(acc[(a + 8) >> 1][j], lo1, hi1);
-                const float va = (a & 1) ? hi0 : lo0, vb = (a & 1) ? hi1 : lo1;
-                const float mine = t3b ? vb : va, send = t3b ? va : vb;
-                v8[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 8));  // lane i + lane i + 8
+                const float mine = t1b ? v2[1][j] : v2[0][j], send = t1b ? v2[0][j] : v2[1][j];
+                sum[j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 2));  // (r0 + r1) + (r2 + r3)
             }
-    }
-    float v4[4][QH];
-    {
-        const bool t2b = (t & 4) != 0;
+        }
+    } else {
+        // 8 rows: xor 8 pairs rows a / a + 4, xor 4 rows a / a + 2, xor 1 rows 0 / 1; the last step (xor 2) adds the two halves
+        // (r0 + r1) and (r2 + r3) of the one row left, on both threads
+        float v4[4][QH];
+        {
+            const bool t3b = (t & 8) != 0;
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    float lo0, hi0, lo1, hi1;
+                    t3_upk2(acc[a >> 1][j], lo0, hi0);
+                    t3_upk2(acc[(a + 4) >> 1][j], lo1, hi1);
+                    const float va = (a & 1) ? hi0 : lo0, vb = (a & 1) ? hi1 : lo1;
+                    const float mine = t3b ? vb : va, send = t3b ? va : vb;
+                    v4[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 8));  // lane i + lane i + 8
+                }
+        }
+        float v2[2][QH];
+        {
+            const bool t2b = (t & 4) != 0;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int j = 0; j < QH; ++j) {
+                    const float mine = t2b ? v4[a + 2][j] : v4[a][j], send = t2b ? v4[a][j] : v4[a + 2][j];
+                    v2[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 4));  // x[i] + x[i + 4]
+                }
+        }
+        {
+            const bool t0b = (t & 1) != 0;
 #pragma unroll
             for (int j = 0; j < QH; ++j) {
-                const float mine = t2b ? v8[a + 4][j] : v8[a][j], send = t2b ? v8[a][j] : v8[a + 4][j];
-                v4[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 4));  // x[i] + x[i + 4]
+                const float mine = t0b ? v2[1][j] : v2[0][j], send = t0b ? v2[0][j] : v2[1][j];
+                const float h2 = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 1));  // r0 + r1, r2 + r3
+                sum[j] = t3_fadd(h2, __shfl_xor_sync(0xffffffffu, h2, 2));              // (r0 + r1) + (r2 + r3)
             }
-    }
-    float v2[2][QH];
-    {
-        const bool t0b = (t & 1) != 0;
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int j = 0; j < QH; ++j) {
-                const float mine = t0b ? v4[a + 2][j] : v4[a][j], send = t0b ? v4[a][j] : v4[a + 2][j];
-                v2[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 1));  // r0 + r1, r2 + r3
-            }
-    }
-    {
-        const bool t1b = (t & 2) != 0;
-#pragma unroll
-        for (int j = 0; j < QH; ++j) {
-            const float mine = t1b ? v2[1][j] : v2[0][j], send = t1b ? v2[0][j] : v2[1][j];
-            sum[j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 2));  // (r0 + r1) + (r2 + r3)
         }
     }
-#else
-    // 8 rows: xor 8 pairs rows a / a + 4, xor 4 rows a / a + 2, xor 1 rows 0 / 1; the last step (xor 2) adds the two halves
-    // (r0 + r1) and (r2 + r3) of the one row left, on both threads
-    float v4[4][QH];
-    {
-        const bool t3b = (t & 8) != 0;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int j = 0; j < QH; ++j) {
-                float lo0, hi0, lo1, hi1;
-                t3_upk2(acc[a >> 1][j], lo0, hi0);
-                t3_upk2(acc[(a + 4) >> 1][j], lo1, hi1);
-                const float va = (a & 1) ? hi0 : lo0, vb = (a & 1) ? hi1 : lo1;
-                const float mine = t3b ? vb : va, send = t3b ? va : vb;
-                v4[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 8));  // lane i + lane i + 8
-            }
-    }
-    float v2[2][QH];
-    {
-        const bool t2b = (t & 4) != 0;
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int j = 0; j < QH; ++j) {
-                const float mine = t2b ? v4[a + 2][j] : v4[a][j], send = t2b ? v4[a][j] : v4[a + 2][j];
-                v2[a][j] = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 4));  // x[i] + x[i + 4]
-            }
-    }
-    {
-        const bool t0b = (t & 1) != 0;
-#pragma unroll
-        for (int j = 0; j < QH; ++j) {
-            const float mine = t0b ? v2[1][j] : v2[0][j], send = t0b ? v2[0][j] : v2[1][j];
-            const float h2 = t3_fadd(mine, __shfl_xor_sync(0xffffffffu, send, 1));  // r0 + r1, r2 + r3
-            sum[j] = t3_fadd(h2, __shfl_xor_sync(0xffffffffu, h2, 2));              // (r0 + r1) + (r2 + r3)
-        }
-    }
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -410,12 +415,12 @@ __device__ __forceinline__ void t3_block_sums(unsigned char* tb, const T3Layout&
 // maintains the lists of the tile slots it owns (slot q is owned by warp q % T3_TWARPS).
 // ------------------------------------------------------------------------------------------------------------------
 // The finished sums of (row T3_RW * tw + t3_fold_row(t), tile slot h * QH + j) go to sums[slot][row] of the block's buffer.
-template <int METRIC, int QH>
+template <int METRIC, int QH, int TW>
 __device__ __forceinline__ void t3_block_sums_store(unsigned char* tb, const T3Layout& lay, const int dimp, const int chunks, const int qcap,
                                                     const u32 S, const int tw, const int lane, u32& buf, u32& ph, float* dst,
                                                     const u32 wait_bar = 0, const u32 wait_parity = 0) {
     float sum[QH];
-    t3_block_sums<METRIC, QH>(tb, lay, dimp, chunks, qcap, S, tw, lane, buf, ph, sum);
+    t3_block_sums<METRIC, QH, TW>(tb, lay, dimp, chunks, qcap, S, tw, lane, buf, ph, sum);
     if (wait_bar) mbar_wait(wait_bar, wait_parity);  // T3_EPW: the epilogue warp is done with this buffer's previous block
     const int h = lane >> 4;
 #pragma unroll
@@ -425,17 +430,18 @@ __device__ __forceinline__ void t3_block_sums_store(unsigned char* tb, const T3L
 // One copy of the block loop and of the epilogue for all query counts: only the FP32 loop + fold is specialised by QH (the
 // instruction working set of a warp -- loop, fold, epilogue -- has to stay inside the SM's 32 KB instruction cache while the
 // two teams of a CTA run different tiles).
-template <int METRIC, int KR>
+template <int METRIC, int KR, int TW>
 __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& lay, const ForestView& f, const T3Params& tp,
                                              const T3TileInfo& inf, const int tw, const int lane, u32& buf, u32& ph, u32& blk,
-                                             const int team, u64 (&thr)[T3_SLOTS]) {
+                                             const int team, u64 (&thr)[T3Shape<TW>::SLOTS]) {
+    constexpr int T3_SLOTS = T3Shape<TW>::SLOTS, T3_RW = T3Shape<TW>::RW, T3_TWARPS = TW;
     const int t = lane & 15;
     const u32 S = (u32)tp.nst, L = inf.L, nqt = inf.nqt;
     const u32 nblocks = (L + T3_RB - 1) / T3_RB;
     float* s_sums = reinterpret_cast<float*>(tb + lay.sums);
     u32* s_lists = reinterpret_cast<u32*>(tb + lay.lists);
     const u32* s_meta = reinterpret_cast<const u32*>(tb + lay.meta);
-    const int myrow = t3_fold_row(t);
+    const int myrow = t3_fold_row<TW>(t);
 
     // The per-query bound shared by all of a query's visits (gthr) is read branch free right after a block's FP32 loop: four
     // independent loads in flight behind the transposition and the team barrier.  A stale bound only costs work.
@@ -461,15 +467,15 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
             float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * T3_RW + myrow;
             switch (inf.qh) {
 #if T3_QH_STEP == 1
-                case 1: t3_block_sums_store<METRIC, 1>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
-                case 3: t3_block_sums_store<METRIC, 3>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
-                case 5: t3_block_sums_store<METRIC, 5>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
-                case 7: t3_block_sums_store<METRIC, 7>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 1: t3_block_sums_store<METRIC, 1, TW>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 3: t3_block_sums_store<METRIC, 3, TW>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 5: t3_block_sums_store<METRIC, 5, TW>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 7: t3_block_sums_store<METRIC, 7, TW>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
 #endif
-                case 2: t3_block_sums_store<METRIC, 2>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
-                case 4: t3_block_sums_store<METRIC, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
-                case 6: t3_block_sums_store<METRIC, 6>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
-                default: t3_block_sums_store<METRIC, 8>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 2: t3_block_sums_store<METRIC, 2, TW>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 4: t3_block_sums_store<METRIC, 4, TW>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                case 6: t3_block_sums_store<METRIC, 6, TW>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
+                default: t3_block_sums_store<METRIC, 8, TW>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst); break;
             }
         }
         u64 gbound[T3_SLOTS];
@@ -488,7 +494,7 @@ __device__ __forceinline__ void t3_scan_tile(unsigned char* tb, const T3Layout& 
         }
         u32 tword = 0;  // tombstone words covering positions base .. base + 63 (at most 3 words), one per lane
         if (lane < 3) tword = tp.bm_tomb[(base >> 5) + lane];
-        t3_team_sync(team);  // the block's sums are complete; the previous use of this buffer was consumed two blocks ago
+        t3_team_sync(team, T3Shape<TW>::TEAM_THREADS);  // the block's sums are complete; the previous use of this buffer was consumed two blocks ago
         // ---- epilogue: this warp finishes the tile slots it owns (q = tw, tw + T3_TWARPS, ...): keys, filter, list insertion ----
         const float* sums = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB;
 #pragma unroll
@@ -747,21 +753,21 @@ __device__ __forceinline__ void t3_scan_tile_math(unsigned char* tb, const T3Lay
     const u32 S = (u32)tp.nst;
     const u32 nblocks = (inf.L + T3_RB - 1) / T3_RB;
     float* s_sums = reinterpret_cast<float*>(tb + lay.sums);
-    const int myrow = t3_fold_row(lane & 15);
+    const int myrow = t3_fold_row<4>(lane & 15);
     for (u32 b = 0; b < nblocks; ++b, ++blk) {
-        float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * T3_RW + myrow;
+        float* dst = s_sums + (size_t)(blk & 1u) * tp.qcap * T3_RB + tw * 16 + myrow;
         // the buffer's previous content (two blocks ago) has been consumed: checked right before the store inside, i.e. after the FP32 loop
         switch (inf.qh) {
 #if T3_QH_STEP == 1
-            case 1: t3_block_sums_store<METRIC, 1>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
-            case 3: t3_block_sums_store<METRIC, 3>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
-            case 5: t3_block_sums_store<METRIC, 5>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
-            case 7: t3_block_sums_store<METRIC, 7>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 1: t3_block_sums_store<METRIC, 1, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 3: t3_block_sums_store<METRIC, 3, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 5: t3_block_sums_store<METRIC, 5, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 7: t3_block_sums_store<METRIC, 7, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
 #endif
-            case 2: t3_block_sums_store<METRIC, 2>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
-            case 4: t3_block_sums_store<METRIC, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
-            case 6: t3_block_sums_store<METRIC, 6>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
-            default: t3_block_sums_store<METRIC, 8>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 2: t3_block_sums_store<METRIC, 2, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 4: t3_block_sums_store<METRIC, 4, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            case 6: t3_block_sums_store<METRIC, 6, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
+            default: t3_block_sums_store<METRIC, 8, 4>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, dst, bar_sempty + 8 * (blk & 1u), ((blk >> 1) & 1u) ^ 1u); break;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sfull + 8 * (blk & 1u));
@@ -773,13 +779,13 @@ __device__ __forceinline__ void t3_scan_tile_math(unsigned char* tb, const T3Lay
 // "queries" are planes tile_first .. tile_first + nqt - 1, its "leaf" is a range of input rows; the thread that holds a
 // finished dot product tests its sign and stores it.  No lists, no transposition.
 // ------------------------------------------------------------------------------------------------------------------
-template <int QH>
+template <int QH, int TW>
 __device__ __forceinline__ void t3_project_tile(unsigned char* tb, const T3Layout& lay, const ForestView& f, const T3Params& tp,
                                                 const T3TileInfo& inf, const int tw, const int lane, u32& buf, u32& ph) {
     const int t = lane & 15, h = lane >> 4;
     const u32 S = (u32)tp.nst, L = inf.L, nqt = inf.nqt;
     const u32 nblocks = (L + T3_RB - 1) / T3_RB;
-    const int myrow = tw * T3_RW + t3_fold_row(t);
+    const int myrow = tw * T3Shape<TW>::RW + t3_fold_row<TW>(t);
     float cst[QH];
 #pragma unroll
     for (int j = 0; j < QH; ++j) {
@@ -789,7 +795,7 @@ __device__ __forceinline__ void t3_project_tile(unsigned char* tb, const T3Layou
     for (u32 b = 0; b < nblocks; ++b) {
         const u32 nrows = min((u32)T3_RB, L - b * T3_RB);
         float sum[QH];
-        t3_block_sums<0, QH>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, sum);
+        t3_block_sums<0, QH, TW>(tb, lay, f.dimp, f.chunks, tp.qcap, S, tw, lane, buf, ph, sum);
         if ((u32)myrow < nrows) {
             u8* dst = tp.pj_sign + (size_t)(inf.moff + (long long)b * T3_RB + myrow) * tp.pj_hp + inf.first + h * QH;
 #pragma unroll
@@ -803,8 +809,9 @@ __device__ __forceinline__ void t3_project_tile(unsigned char* tb, const T3Layou
 // the two math warps that share a sub-partition belong to different tiles, so one warp's fold / epilogue / tile change
 // overlaps the other's FP32 loop, and a bandwidth-bound tile (few queries) shares the SM with a pipe-bound one.
 // MODE 0: leaf scan (METRIC 0 cosine, 1 L2 squared, 2 L2).  MODE 1: flat-table projection (METRIC ignored).
-template <int METRIC, int MODE, int KR>
+template <int METRIC, int MODE, int KR, int TW>
 __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, const T3Params& tp, unsigned char* smem) {
+    constexpr int T3_TWARPS = TW, T3_CWARPS = T3Shape<TW>::CWARPS, T3_SLOTS = T3Shape<TW>::SLOTS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dimp = f.dimp, chunks = f.chunks;
     const int nsl = (chunks + T3_KC - 1) / T3_KC;
@@ -816,7 +823,7 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
     const u32 bar_full = smem_u32(tb + lay.bars), bar_empty = bar_full + 8 * T3_MAX_STAGES;
     const u32 bar_ifull = bar_full + 16 * T3_MAX_STAGES, bar_qfull = bar_ifull + 16, bar_qempty = bar_ifull + 24;
     const u32 bar_sfull = bar_ifull + 32, bar_sempty = bar_ifull + 48;
-    constexpr bool EPW = T3_EPW && MODE == 0 && KR == 1 && METRIC != 3;
+    constexpr bool EPW = T3_EPW && MODE == 0 && KR == 1 && METRIC != 3 && TW == 4;
 
     if (tid == 0) {
         for (int tm = 0; tm < T3_TEAMS; ++tm) {
@@ -840,7 +847,7 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
 
     if (warp >= T3_CWARPS) {
         // =========================== producer warpgroup: one thread per team drives TMA ===========================
-        t3_setmaxnreg_dec();
+        t3_setmaxnreg_dec<TW>();
         if (warp >= T3_CWARPS + T3_TEAMS) {  // the warpgroup's other two warps: one epilogue warp per team, or nothing
             if (EPW) t3_epilogue_warp<METRIC>(tb, lay, f, tp, lane, bar_ifull, bar_qempty, bar_sfull, bar_sempty);
             return;
@@ -909,7 +916,7 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
     }
 
     // =================================== consumer (math) warps ===================================
-    t3_setmaxnreg_inc();
+    t3_setmaxnreg_inc<TW>();
     const int tw = warp % T3_TWARPS;
     u32 rbuf = 0, rph = 0, blk = 0;  // ring position of the next stage to consume (slot, phase parity); running row-block count
     u32* s_lists = reinterpret_cast<u32*>(tb + lay.lists);
@@ -923,15 +930,15 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
             mbar_wait(bar_qfull, it & 1);
             switch (inf.qh) {
 #if T3_QH_STEP == 1
-                case 1: t3_project_tile<1>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
-                case 3: t3_project_tile<3>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
-                case 5: t3_project_tile<5>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
-                case 7: t3_project_tile<7>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 1: t3_project_tile<1, TW>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 3: t3_project_tile<3, TW>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 5: t3_project_tile<5, TW>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 7: t3_project_tile<7, TW>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
 #endif
-                case 2: t3_project_tile<2>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
-                case 4: t3_project_tile<4>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
-                case 6: t3_project_tile<6>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
-                default: t3_project_tile<8>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 2: t3_project_tile<2, TW>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 4: t3_project_tile<4, TW>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                case 6: t3_project_tile<6, TW>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
+                default: t3_project_tile<8, TW>(tb, lay, f, tp, inf, tw, lane, rbuf, rph); break;
             }
             if (lane == 0) mbar_arrive(bar_qempty);
             continue;
@@ -972,7 +979,7 @@ __device__ __forceinline__ void t3_body(const T3Map& tmap, const ForestView& f, 
         for (int e = 0; e < T3_SLOTS; ++e) thr[e] = ZB_SENTINEL;
         __syncwarp();
         mbar_wait(bar_qfull, it & 1);
-        t3_scan_tile<METRIC, KR>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr);
+        t3_scan_tile<METRIC, KR, TW>(tb, lay, f, tp, inf, tw, lane, rbuf, rph, blk, team, thr);
         // ---- end of tile: release the query block, write the owned visits' top lists ----
         if (lane == 0) mbar_arrive(bar_qempty);
 #pragma unroll 1

@@ -268,8 +268,12 @@ int zb_index_stats(zb_index* index, zb_stats* out);
 /* The CUDA stream (cudaStream_t) every kernel of this index is launched on -- for callers that time the
  * device work with their own events. */
 int zb_index_stream(zb_index* index, void** out_stream);
-/* Tuning knobs (tests and ablations): key in {"tile_min_rows", "tile_queries", "use_tile_scan", "visit_slots", "seq_tile",
- * "seq_prefetch", "hash_variant", "classify_variant", "flat_project", "quad_tile", "select_variant"}. */
+/* Tuning knobs (tests and ablations; results never depend on them): key in {"tile_min_rows", "tile_queries", "use_tile_scan",
+ * "scan_gen", "visit_slots", "seq_tile", "seq_prefetch", "hash_variant", "classify_variant", "flat_project", "quad_tile",
+ * "select_variant", "bm_stage_mb", "single_exchange", "p2p_queries",
+ * "l2_filter" (L2 / L2 squared with top_k <= 16 scored through the dot product + exact second pass: 0 off, 1 adaptive = default,
+ *              2 always), "long_list_warps" (math warps per team of the fused scan for top_k > 32: 8 = default, 4),
+ * "plan_tail" (count-cascade walkers re-walked by the latency-optimised tail kernel: 1 = default, 0)}. */
 int zb_index_set_param(zb_index* index, const char* key, int64_t value);
 
 /* Sharding over the GPUs of one box: one process per GPU, each with its own index

@@ -99,6 +99,24 @@ def test_invalid_arguments_are_reported():
     assert lib.zb_metric_distance_batch(0, 10, 65, 0, 16, None, None, None) == -1         # Minkowski power out of range
 
 
+def test_stats_struct_offsets_match_the_c_compiler(tmp_path):
+    """Every field of zb_stats (round 2 gave the reserved words to the dot-product filter's counters) sits where the C compiler
+    puts it: sizeof and offsetof of the header against the ctypes mirror the tests and the bench read."""
+    from zebra_b200 import _ffi
+
+    names = [n for n, _ in _ffi.Stats._fields_]
+    body = "".join(f'  printf("%s %zu\\n", "{n}", offsetof(zb_stats, {n}));\n' for n in names)
+    src = tmp_path / "off.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "zebra_b200.h"\n'
+                   'int main(void) {\n  printf("sizeof %zu\\n", sizeof(zb_stats));\n' + body + '  return 0; }\n')
+    exe = str(tmp_path / "off")
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), "-o", exe, str(src)])
+    out = dict(line.split() for line in subprocess.check_output([exe], text=True).splitlines())
+    assert int(out.pop("sizeof")) == C.sizeof(_ffi.Stats)
+    for n in names:
+        assert int(out[n]) == getattr(_ffi.Stats, n).offset, n
+
+
 def test_header_is_plain_c(tmp_path):
     """The boundary is a C ABI: include/zebra_b200.h must compile as C99 (no C++-isms), and a C program links against it."""
     src = tmp_path / "abi.c"

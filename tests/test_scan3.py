@@ -33,6 +33,7 @@ def emu(tmp_path_factory, request):
                            os.path.join(HERE, "scan3_emu.cpp")])
     L = C.CDLL(out)
     assert L.emu_scan3_set_team_warps(tw) == 0               # the kernel body's TW (a template parameter: both shapes are in every build)
+    L.variant = (kc, epw, tw)
     L.emu_scan3.restype = C.c_int
     L.emu_scan3.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint64] + [C.c_void_p] * 7 + \
                            [C.c_uint32] + [C.c_void_p] * 12
@@ -366,3 +367,45 @@ def test_l2_filter_shared_bound_keeps_the_per_query_answer(emu, metric):
             got += [tuple(x) for x in e if x[1] != SENT]
             exp += [tuple(x) for x in expected_visit(case, metric, v, k)]
         assert sorted(set(got))[:k] == sorted(set(exp))[:k], q
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_l2_filter_randomised_cases(emu, seed):
+    """Random shapes around the filter's edges: groups of equal and nearly equal rows whose sizes straddle the 32-entry candidate
+    list, scales from 1e-3 to 1e3, n' from 1 to 16, tombstones, queries equal to stored rows -- every visit's list exact, with
+    and without the shared per-query bound."""
+    if emu.variant[0] != 3 or emu.variant[1]:
+        pytest.skip("the filter ships with the default stage shape; the other build variants run the fixed cases above")
+    rng = np.random.default_rng(1000 + seed)
+    dim = int(rng.choice([16, 40, 64, 100, 130]))
+    nleaf = int(rng.integers(3, 7))
+    leaf_lens = [int(x) for x in rng.integers(20, 220, nleaf)]
+    nq = int(rng.integers(6, 20))
+    visits = [int(x) for x in rng.integers(1, min(nq, 16) + 1, nleaf)]
+    case = build_case(rng, dim, leaf_lens, nq, visits, np_max=16, tomb_frac=float(rng.choice([0.0, 0.1, 0.3])), dup=False)
+    scale = F32(10.0 ** rng.uniform(-3, 3))
+    case["rows"] = (case["rows"] * scale).astype(F32)
+    case["queries"] = (case["queries"] * scale).astype(F32)
+    P = case["P"]
+    for _ in range(int(rng.integers(2, 6))):                       # groups of copies / near copies of one row, 2 .. 40 strong
+        g = int(rng.integers(2, 41))
+        idx = rng.choice(P, size=min(g, P), replace=False)
+        src = case["rows"][idx[0]].copy()
+        for j, i in enumerate(idx):
+            case["rows"][i] = src
+            if j % 3 == 1:                                          # a few ulps away in one coordinate
+                c = int(rng.integers(0, dim))
+                case["rows"][i, c] = np.nextafter(src[c], F32(np.inf) if j % 2 else F32(-np.inf), dtype=F32)
+        case["queries"][int(rng.integers(0, nq))] = src             # and a query sitting exactly on the group
+    metric = zo.L2SQ if seed % 2 else zo.L2
+    entries, ent_off, v_np, _ = run_emu(emu, case, metric, top_k=0xFFFFFFFF, tq=16, l2_filter=True)
+    check_every_visit(case, metric, entries, ent_off, v_np)
+    k = int(rng.integers(1, 17))                                    # the same data with n' = top_k everywhere: bounds are published
+    entries, ent_off, _, _ = run_emu(emu, case, metric, top_k=k, tq=16, same_np=k, blocks=2, l2_filter=True)
+    for q in range(nq):
+        got, exp = [], []
+        for v in np.nonzero(case["v_q"] == q)[0]:
+            e = entries[ent_off[v]:ent_off[v + 1]]
+            got += [tuple(x) for x in e if x[1] != SENT]
+            exp += [tuple(x) for x in expected_visit(case, metric, v, k)]
+        assert sorted(set(got))[:k] == sorted(set(exp))[:k], (seed, q)
